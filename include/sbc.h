@@ -1,0 +1,164 @@
+/* sbc.h - C ABI of the B200-native burst-coast hot path (libsbc.so).
+ *
+ * Drop-in boundary: the reference has no FFI layer; its hot path is the
+ * single call `Step(s, agent, &SysPara, preds)` at /root/reference/src/swarmdyn.cpp:76, bracketed
+ * by `split_dead` (:71) and `Output` (:85). A host `main` (ours: sde_burst_coast_b200/host/
+ * swarmdyn_main.cpp; or the reference's own, patched as shown in INTEGRATION.md) keeps argv
+ * parsing, initial conditions and file output, and replaces that bracket by the calls below.
+ *
+ * Conventions: every function returns 0 on success or a negative sbc_status; the message is
+ * available from sbc_last_error(). No C++ exception crosses this boundary. All pointers are
+ * HOST pointers unless the name ends in `_dev`. Doubles at the ABI (the reference's layout),
+ * FP32 structure-of-arrays inside. A handle owns its device memory and is bound to one device
+ * and one stream; it is not thread-safe, different handles may be used from different threads.
+ *
+ * There is NO CPU fallback: every entry point that computes launches CUDA kernels and fails
+ * with SBC_ERR_CUDA when no device is usable.
+ */
+#ifndef SBC_H
+#define SBC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBC_ABI_VERSION 1
+
+typedef enum sbc_status {
+    SBC_OK = 0,
+    SBC_ERR_INVALID = -1, /* bad argument / unsupported parameter combination */
+    SBC_ERR_CUDA = -2,    /* CUDA runtime error, no device, or kernel fault */
+    SBC_ERR_STATE = -3,   /* call sequence error (e.g. step before set_state) */
+    SBC_ERR_NOMEM = -4
+} sbc_status;
+
+/* neighbour rule: which candidate set feeds the three-zone filter */
+enum { SBC_NEIGHBOUR_METRIC = 0 /* = InteractionGlobal, agents_interact.cpp:144-157 */,
+       SBC_NEIGHBOUR_VORONOI = 1 /* = InteractionVoronoiF2F, :26-77; not implemented yet */ };
+/* pair-search path */
+enum { SBC_PATH_AUTO = 0, SBC_PATH_ALLPAIRS = 1, SBC_PATH_CELLLIST = 2 };
+
+/* POD mirror of the hot fields of `params` (/root/reference/src/agents.h:83-148). */
+typedef struct sbc_params {
+    double sizeL;        /* -L  box length (BC 0..4) or tank radius (BC 5,6)            agents.h:90  */
+    double dt;           /* -d                                                           agents.h:112 */
+    double beta;         /* -b  friction along heading                                   agents.h:143 */
+    double alphaTurn;    /* -Y                                                           agents.h:104 */
+    double soc_strength; /* -H                                                           agents.h:94  */
+    double env_strength; /* -R                                                           agents.h:95  */
+    double prob_social;  /* -Q                                                           agents.h:98  */
+    double burst_rate;   /* -A                                                           agents.h:96  */
+    double rep_range;    /* -h                                                           agents.h:100 */
+    double alg_range;    /* -a                                                           agents.h:101 */
+    double att_range;    /* -r                                                           agents.h:102 */
+    double flee_range;   /* -f                                                           agents.h:105 */
+    double pred_time;    /* -e  predator appears at the first s with s >= pred_time/dt   agents.h:107 */
+    double pred_speed0;  /* -S                                                           agents.h:108 */
+    double kill_range;   /* -G                                                           agents.h:133 */
+    double kill_rate;    /* -O                                                           agents.h:132 */
+    double noisep;       /* sqrt(2 dt Dphi), only for pred_move==0                       agents.h:92  */
+    double sim_time;     /* -t  (fish-net respawn period when pred_speed0==0)            agents.h:110 */
+    double trans_time;   /* -T                                                           agents.h:120 */
+    uint32_t burst_steps; /* int(burst_duration/dt)                                      agents.h:142 */
+    int32_t BC;          /* -B  -1 open, 0 periodic, 1..4 boxes, 5 elastic / 6 inelastic circle */
+    int32_t N_confu;     /* -c                                                           agents.h:116 */
+    int32_t pred_kill;   /* -x  0..4                                                     agents.h:117 */
+    int32_t pred_move;   /* -X  0 random walk, 1 chase closest                           agents.h:118 */
+    int32_t neighbour_mode; /* SBC_NEIGHBOUR_* */
+    int32_t path;           /* SBC_PATH_* */
+    int32_t reserved;
+} sbc_params;
+
+typedef struct sbc_handle sbc_handle;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+
+/* Create a simulation of `n_replicates` independent swarms of `n_agents` prey and `n_pred`
+ * predators (0, 1 = single predator, >1 = fish net) on CUDA device `device`.
+ * Replaces the allocation of `agent`, `preds`, `SysPara` at swarmdyn.cpp:38-57.
+ * `seed` keys the Philox4x32-10 streams; `replicate_offset` is the global id of this handle's
+ * first replicate so that sharded ensembles draw the same numbers for any GPU count. */
+int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates,
+               uint64_t seed, uint64_t replicate_offset, int device, sbc_handle **out);
+int sbc_destroy(sbc_handle *h);
+const char *sbc_last_error(const sbc_handle *h); /* h may be NULL: last create error */
+int sbc_abi_version(void);
+
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) instead of the handle's own. */
+int sbc_set_stream(sbc_handle *h, void *cuda_stream);
+int sbc_synchronize(sbc_handle *h);
+
+/* ---- state in / out (arrays are [n_replicates][n_agents], replicate-major) ----------------- */
+
+/* Upload the agents' state; replaces InitSystem/ResetSystem output (settings.cpp:168-387) as the
+ * source of x, v, phi, vproj, force, bin_step, steps_till_burst. Any pointer may be NULL to
+ * keep the reference's InitSystem default (x,v from phi; vproj=1; force=0; counters=0). */
+int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
+                  const double *vy, const double *phi, const double *vproj, const double *fx,
+                  const double *fy, const uint32_t *bin_step, const uint32_t *steps_till_burst,
+                  const uint8_t *alive);
+int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, double *phi,
+                  double *vproj, double *fx, double *fy, uint32_t *bin_step,
+                  uint32_t *steps_till_burst, uint8_t *alive);
+
+/* Rows in `particle::out()` layout (agents.cpp:4-17): x0 x1 v0 v1 fitness(=0) force0 force1,
+ * indexed by agent id; dead agents keep all-zero rows as in /part (swarmdyn.cpp:561-600). */
+int sbc_get_particles(sbc_handle *h, double *out /* [R][N][7] */, uint8_t *alive /* [R][N] or NULL */);
+/* Rows in `predator::out()` layout (agents.cpp:20-30): x0 x1 v0 v1 0 0. */
+int sbc_get_predators(sbc_handle *h, double *out /* [R][Npred][6] */);
+int sbc_set_predators(sbc_handle *h, const double *x, const double *y, const double *phi,
+                      int spawned);
+int sbc_get_counts(sbc_handle *h, int32_t *n_alive /* [R] */, int32_t *n_dead /* [R] */);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+/* Advance all replicates by `n_steps` consecutive steps s_first, s_first+1, ...; each step is
+ * split_dead + Step (swarmdyn.cpp:71,76,143-204) in metric neighbour mode. */
+int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps);
+
+/* ---- observables (Out_swarm subset, swarmdyn.cpp:237-344) ---------------------------------- */
+/* out[R][8]: N_alive, pol_order, avg_x0, avg_x1, avg_v0, avg_v1, avg_speed, NND(true nearest) */
+int sbc_observables(sbc_handle *h, double *out);
+
+/* ---- test hooks (parity tests call these through the ABI) --------------------------------- */
+
+#define SBC_PAIR_ACTIVE_ROWS 0 /* rows with bin_step == burst_steps (IntCalcPrey gate, :178) */
+#define SBC_PAIR_ALL_ROWS 1    /* every alive row (state at s=1) */
+
+/* Run the three-zone pair pass on the current state without advancing it. Outputs per agent
+ * ([R][N]; any may be NULL): zone counters, accumulated force_rep/alg/att (x,y interleaved,
+ * [R][N][2]) as IntCalcPrey leaves them (agents_interact.cpp:211-225).
+ * `nn_ptr` [R*N+1] / `nn_idx` [nn_capacity]: CSR neighbour lists sorted by j (the reference's
+ * NN holds the same set in visiting order); pass NULL to skip. Returns SBC_ERR_NOMEM if
+ * nn_capacity is too small (nn_ptr[R*N] then holds the needed size). */
+int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_alg,
+                          int32_t *c_att, double *f_rep, double *f_alg, double *f_att,
+                          int64_t *nn_ptr, int32_t *nn_idx, int64_t nn_capacity);
+
+/* Decision-level injection for the NEXT sbc_step call of n_steps == 1:
+ * u_social[i] (compared with prob_social, agents_dynamics.cpp:33-35), u_dir[i] (random cue
+ * direction 2*pi*u, :84) and k_next[i] (geometric inter-burst draw, :257-269) replace the
+ * Philox draws of every agent i; NULL keeps Philox for that quantity. */
+int sbc_inject_decisions(sbc_handle *h, const double *u_social, const double *u_dir,
+                         const uint32_t *k_next);
+
+/* The exact uniform draws of (replicate, agent, step): u_social, u_dir as doubles and the
+ * geometric draw k; lets the CPU oracle replay the device's own Philox stream. */
+int sbc_philox_decisions(sbc_handle *h, int64_t step, double *u_social, double *u_dir,
+                         uint32_t *k_next);
+
+/* Kernel statistics since creation: [0] pair-kernel launches, [1] update launches,
+ * [2] ensemble launches, [3] directed pairs evaluated, [4] ambiguous (FP64 re-checked) pairs,
+ * [5] agent-steps, [6] cell-list builds, [7] other launches. */
+int sbc_get_stats(sbc_handle *h, uint64_t out[8]);
+
+/* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on
+ * the handle's stream; returns mean milliseconds per launch in *ms. */
+int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBC_H */

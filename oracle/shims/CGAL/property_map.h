@@ -1,0 +1,4 @@
+// Oracle shim: included by the reference, nothing used from it on the hot path.
+#ifndef SBC_ORACLE_SHIM_CGAL_property_map_H
+#define SBC_ORACLE_SHIM_CGAL_property_map_H
+#endif
