@@ -149,6 +149,18 @@ int sbc_inject_decisions(sbc_handle *h, const double *u_social, const double *u_
 int sbc_philox_decisions(sbc_handle *h, int64_t step, double *u_social, double *u_dir,
                          uint32_t *k_next);
 
+/* One raw Philox4x32-10 block from the library's host implementation (known-answer tests). */
+int sbc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* Branch flags of ParticleBurstCoast OR-ed over the steps since the last read, per agent:
+ * bit0 burst start, bit1 social cue, bit2 wall redirect, bit3 vproj<0 hack, bit4 overshoot clamp,
+ * bit5 boundary hit, bit6 flee cue, bit7 re-armed. enable!=0 starts collecting; out!=NULL reads
+ * ([R][N]) and clears. */
+int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out);
+/* Route swarms of <= 1024 agents through the multi-kernel path (pair pass + update kernels)
+ * instead of the one-block-per-swarm kernel, so that both paths can be checked on one state. */
+int sbc_debug_force_multikernel(sbc_handle *h, int on);
+
 /* Kernel statistics since creation: [0] pair-kernel launches, [1] update launches,
  * [2] ensemble launches, [3] directed pairs evaluated, [4] ambiguous (FP64 re-checked) pairs,
  * [5] agent-steps, [6] cell-list builds, [7] other launches. */

@@ -54,6 +54,7 @@ class OracleLib:
         L.orc_inject_decisions.argtypes = [ctypes.c_void_p, _dp, _dp, _u32p]
         L.orc_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, _u8p]
         L.orc_philox_decisions.argtypes = [ctypes.c_void_p, ctypes.c_int64, _dp, _dp, _u32p]
+        L.orc_philox_raw.argtypes = [_u32p, _u32p, _u32p]
         L.orc_observables.argtypes = [ctypes.c_void_p, _dp]
         L.orc_ref_voronoi_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_uint32]

@@ -383,6 +383,11 @@ void orc_philox_decisions(orc_world *w, int64_t step, double *u_social, double *
     }
 }
 
+void orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    const OrcPhilox4 q = orc_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    for (int k = 0; k < 4; k++) out[k] = q.v[k];
+}
+
 void orc_observables(orc_world *w, double *out) {
     std::vector<particle> &a = w->agent;
     const int n = (int)a.size();

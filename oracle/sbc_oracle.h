@@ -72,6 +72,9 @@ void orc_step(orc_world *w, int64_t s_first, int64_t n_steps, uint8_t *branch_fl
 void orc_philox_decisions(orc_world *w, int64_t step, double *u_social, double *u_dir,
                           uint32_t *k_next);
 
+/* raw Philox4x32-10 block (known-answer tests) */
+void orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
 /* Out_swarm subset (swarmdyn.cpp:237-344), same layout as sbc_observables: out[8]. */
 void orc_observables(orc_world *w, double *out);
 

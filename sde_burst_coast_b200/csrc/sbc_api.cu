@@ -1,0 +1,668 @@
+// sbc_api.cu - implementation of the C ABI declared in include/sbc.h.
+// Host side only: owns device memory and the stream, converts the reference's double layout to
+// the FP32 SoA state, sequences the kernels of one Step() (swarmdyn.cpp:143-204). No arithmetic
+// of the hot path runs on the host; without a usable CUDA device every call fails loudly.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sbc.h"
+#include "sbc_kernels.cuh"
+
+struct sbc_handle {
+    sbc_params hp;
+    DevParams P;
+    DevState S;
+    int device;
+    uint64_t seed, replicate_offset;
+    cudaStream_t stream;
+    bool own_stream;
+    std::string err;
+    std::vector<uint32_t> geo_host;
+    bool state_set;
+    double *obs_dev;
+    uint8_t *flags_dev;
+    double *inj_social_dev;
+    float *inj_dir_dev;
+    uint32_t *inj_k_dev;
+    unsigned long long host_stats[8];
+    bool force_multikernel;
+};
+
+static std::string g_create_error;
+
+#define SBC_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                   \
+            return SBC_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+static int fail(sbc_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
+static float next_up(float v) { return std::nextafterf(v, INFINITY); }
+
+static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off, DevParams &P) {
+    std::memset(&P, 0, sizeof(P));
+    P.L = (float)p.sizeL;
+    P.halfL = (float)(p.sizeL / 2);
+    P.invL = (float)(1.0 / p.sizeL);
+    P.dt = (float)p.dt;
+    P.beta = (float)p.beta;
+    P.alphaTurn = (float)p.alphaTurn;
+    P.soc = (float)p.soc_strength;
+    P.env = (float)p.env_strength;
+    P.rep = (float)p.rep_range;
+    P.alg = (float)p.alg_range;
+    P.att = (float)p.att_range;
+    const double thr[3] = {p.rep_range, p.alg_range, p.att_range};
+    // FP32 rounding band of the squared distance around each squared threshold: relative part
+    // from dx, dy, the products and the sum (<= 8 u), absolute part from the periodic fold
+    // (error of x_j - x_i up to u L, of the fold up to |L - (float)L|)
+    const double u = 1.0 / 16777216.0;
+    for (int k = 0; k < 3; k++) {
+        const double T = thr[k] * thr[k];
+        double e_dx = 0;
+        if (p.BC == 0) e_dx = 2 * u * p.sizeL + std::fabs(p.sizeL - (double)(float)p.sizeL);
+        const double delta = 16 * u * T + 4 * thr[k] * e_dx + e_dx * e_dx;
+        P.band_lo[k] = next_down((float)(T - delta));
+        P.band_hi[k] = next_up((float)(T + delta));
+    }
+    P.rep2 = (float)(thr[0] * thr[0]);
+    P.alg2 = (float)(thr[1] * thr[1]);
+    P.att2 = (float)(thr[2] * thr[2]);
+    P.flee_range = (float)p.flee_range;
+    P.inv_flee_range = (float)(1.0 / p.flee_range);
+    P.pred_speed = (float)p.pred_speed0;
+    P.kill_range = (float)p.kill_range;
+    P.kill_rate = (float)p.kill_rate;
+    P.noisep = (float)p.noisep;
+    P.wall_margin_r = (float)(p.sizeL - 2);
+    P.t_burst = (float)(p.dt * p.burst_steps);
+    P.dL = p.sizeL;
+    P.d_rep = p.rep_range;
+    P.d_alg = p.alg_range;
+    P.d_att = p.att_range;
+    P.d_prob_social = p.prob_social;
+    P.d_flee_range = p.flee_range;
+    P.d_kill_range = p.kill_range;
+    P.burst_steps = p.burst_steps;
+    P.max_steps = (uint32_t)(5 / (p.burst_rate * p.dt));
+    P.BC = p.BC;
+    P.N_confu = p.N_confu;
+    P.pred_kill = p.pred_kill;
+    P.pred_move = p.pred_move;
+    P.has_alg_zone = p.alg_range > p.rep_range;
+    P.seed_lo = (uint32_t)seed;
+    P.seed_hi = (uint32_t)(seed >> 32);
+    P.replicate_offset = (uint32_t)rep_off;
+}
+
+// inter-burst inverse-CDF table, see DESIGN.md section 5 (the oracle builds its own copy from the
+// same recipe: q_k by repeated IEEE multiplication, thr = floor(2^32 (1 - q_k)))
+static std::vector<uint32_t> geometric_table(double burst_rate, double dt) {
+    const double p = burst_rate * dt;
+    const unsigned max_steps = (unsigned)(5 / p);
+    std::vector<uint32_t> thr(max_steps);
+    double q = 1.0;
+    for (unsigned k = 1; k <= max_steps; k++) {
+        q *= (1.0 - p);
+        double t = 4294967296.0 * (1.0 - q);
+        if (t < 0) t = 0;
+        if (t > 4294967295.0) t = 4294967295.0;
+        thr[k - 1] = (uint32_t)t;
+    }
+    return thr;
+}
+
+template <class T>
+static cudaError_t dev_alloc(T **ptr, size_t n) {
+    return cudaMalloc(reinterpret_cast<void **>(ptr), n * sizeof(T));
+}
+
+extern "C" {
+
+int sbc_abi_version(void) { return SBC_ABI_VERSION; }
+
+const char *sbc_last_error(const sbc_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, uint64_t seed,
+               uint64_t replicate_offset, int device, sbc_handle **out) {
+    if (!p || !out) return fail(nullptr, SBC_ERR_INVALID, "sbc_create: null argument");
+    *out = nullptr;
+    if (n_agents < 1 || n_replicates < 1 || n_pred < 0)
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need n_agents >= 1, n_replicates >= 1, n_pred >= 0");
+    if (p->neighbour_mode != SBC_NEIGHBOUR_METRIC)
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: only the metric neighbour rule is implemented");
+    if (!(p->dt > 0) || !(p->burst_rate > 0) || !(p->burst_rate * p->dt < 1))
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need dt > 0 and 0 < burst_rate*dt < 1");
+    if (!(p->rep_range <= p->alg_range && p->alg_range <= p->att_range))
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need rep_range <= alg_range <= att_range");
+    if (p->BC == 0 && !(p->att_range < p->sizeL / 2))
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: periodic box needs att_range < sizeL/2 (minimum image)");
+    if (p->BC < -1 || p->BC > 6) return fail(nullptr, SBC_ERR_INVALID, "sbc_create: BC must be -1..6");
+    if ((size_t)n_agents * (size_t)n_replicates > (size_t)1 << 30)
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: more than 2^30 agents per handle");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        return fail(nullptr, SBC_ERR_CUDA,
+                    std::string("sbc_create: no usable CUDA device (") + cudaGetErrorString(e) +
+                        "); libsbc has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, SBC_ERR_INVALID, "sbc_create: bad device index");
+    sbc_handle *h = new sbc_handle();
+    h->hp = *p;
+    h->device = device;
+    h->seed = seed;
+    h->replicate_offset = replicate_offset;
+    h->own_stream = true;
+    h->state_set = false;
+    h->obs_dev = nullptr;
+    h->flags_dev = nullptr;
+    h->inj_social_dev = nullptr;
+    h->inj_dir_dev = nullptr;
+    h->inj_k_dev = nullptr;
+    h->force_multikernel = false;
+    std::memset(h->host_stats, 0, sizeof(h->host_stats));
+    std::memset(&h->S, 0, sizeof(h->S));
+    fill_dev_params(*p, seed, replicate_offset, h->P);
+    h->geo_host = geometric_table(p->burst_rate, p->dt);
+    DevState &S = h->S;
+    S.N = n_agents;
+    S.R = n_replicates;
+    S.Npred = n_pred;
+    const size_t total = (size_t)n_agents * n_replicates;
+    const size_t npt = (size_t)(n_pred > 0 ? n_pred : 1) * n_replicates;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && dev_alloc(&S.pv, total) == cudaSuccess && dev_alloc(&S.pv_dead, total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.hv, total) == cudaSuccess && dev_alloc(&S.force, total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.timers, total) == cudaSuccess && dev_alloc(&S.alive, total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.acc, total * 8) == cudaSuccess && dev_alloc(&S.cnt, total * 4) == cudaSuccess;
+    ok = ok && dev_alloc(&S.pred_pv, npt) == cudaSuccess && dev_alloc(&S.pred_phi, npt) == cudaSuccess;
+    ok = ok && dev_alloc(&S.n_dead, (size_t)n_replicates) == cudaSuccess;
+    ok = ok && dev_alloc(&S.pred_spawned, (size_t)n_replicates) == cudaSuccess;
+    ok = ok && dev_alloc(&S.active_list, total) == cudaSuccess && dev_alloc(&S.active_count, 1) == cudaSuccess;
+    ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
+    uint32_t *geo_dev = nullptr;
+    ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
+    ok = ok && dev_alloc(&h->obs_dev, (size_t)n_replicates * 8) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("sbc_create: CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        sbc_destroy(h);
+        return SBC_ERR_NOMEM;
+    }
+    S.geo = geo_dev;
+    cudaMemcpy(geo_dev, h->geo_host.data(), h->geo_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    cudaMemset(S.stats, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(S.n_dead, 0, n_replicates * sizeof(int));
+    cudaMemset(S.pred_spawned, 0, n_replicates * sizeof(int));
+    cudaMemset(S.acc, 0, total * 8 * sizeof(float));
+    cudaMemset(S.cnt, 0, total * 4 * sizeof(int));
+    cudaMemset(S.pv_dead, 0, total * sizeof(float4));
+    {   // InitPredator defaults (settings.cpp:147-166): x = v = 1, phi = 1
+        std::vector<float4> pp(npt, make_float4(1.f, 1.f, 1.f, 1.f));
+        std::vector<float> ph(npt, 1.f);
+        cudaMemcpy(S.pred_pv, pp.data(), npt * sizeof(float4), cudaMemcpyHostToDevice);
+        cudaMemcpy(S.pred_phi, ph.data(), npt * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    *out = h;
+    // InitSystem defaults (settings.cpp:168-193)
+    return sbc_set_state(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, nullptr);
+}
+
+int sbc_destroy(sbc_handle *h) {
+    if (!h) return SBC_OK;
+    cudaSetDevice(h->device);
+    DevState &S = h->S;
+    cudaFree(S.pv); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.force); cudaFree(S.timers);
+    cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
+    cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list); cudaFree(S.active_count);
+    cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo));
+    cudaFree(h->obs_dev); cudaFree(h->flags_dev);
+    cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SBC_OK;
+}
+
+int sbc_set_stream(sbc_handle *h, void *cuda_stream) {
+    if (!h) return SBC_ERR_INVALID;
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return SBC_OK;
+}
+
+int sbc_synchronize(sbc_handle *h) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    return SBC_OK;
+}
+
+int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
+                  const double *vy, const double *phi, const double *vproj, const double *fx,
+                  const double *fy, const uint32_t *bin_step, const uint32_t *stb,
+                  const uint8_t *alive) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    std::vector<float4> pv(total), pvd(total);
+    std::vector<float2> hv(total), fo(total);
+    std::vector<uint2> tm(total);
+    std::vector<uint8_t> al(total);
+    if (h->state_set) {  // NULL keeps the current value
+        SBC_CUDA(cudaStreamSynchronize(h->stream));
+        SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemcpy(pvd.data(), S.pv_dead, total * sizeof(float4), cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemcpy(hv.data(), S.hv, total * sizeof(float2), cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemcpy(tm.data(), S.timers, total * sizeof(uint2), cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
+        for (size_t g = 0; g < total; g++)
+            if (!al[g]) { pv[g].x = pvd[g].x; pv[g].y = pvd[g].y; }
+    } else {
+        for (size_t g = 0; g < total; g++) {
+            pv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            hv[g] = make_float2(0.f, 1.f);
+            fo[g] = make_float2(0.f, 0.f);
+            tm[g] = make_uint2(0u, 0u);
+            al[g] = 1;
+        }
+    }
+    for (size_t g = 0; g < total; g++) {
+        if (x) pv[g].x = (float)x[g];
+        if (y) pv[g].y = (float)y[g];
+        if (phi) hv[g].x = (float)phi[g];
+        if (vproj) hv[g].y = (float)vproj[g];
+        if (vx) pv[g].z = (float)vx[g]; else if (phi) pv[g].z = hv[g].y * cosf(hv[g].x);
+        if (vy) pv[g].w = (float)vy[g]; else if (phi) pv[g].w = hv[g].y * sinf(hv[g].x);
+        if (fx) fo[g].x = (float)fx[g];
+        if (fy) fo[g].y = (float)fy[g];
+        if (bin_step) tm[g].x = bin_step[g];
+        if (stb) tm[g].y = stb[g];
+        if (alive) al[g] = alive[g] ? 1 : 0;
+    }
+    std::vector<int> nd(S.R, 0);
+    const float qnan = std::nanf("");
+    for (size_t g = 0; g < total; g++) {
+        pvd[g] = pv[g];
+        if (!al[g]) {
+            nd[g / S.N]++;
+            pv[g].x = qnan;
+            pv[g].y = qnan;
+        }
+    }
+    SBC_CUDA(cudaMemcpy(S.pv, pv.data(), total * sizeof(float4), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.pv_dead, pvd.data(), total * sizeof(float4), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.hv, hv.data(), total * sizeof(float2), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.force, fo.data(), total * sizeof(float2), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.timers, tm.data(), total * sizeof(uint2), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.alive, al.data(), total, cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.n_dead, nd.data(), S.R * sizeof(int), cudaMemcpyHostToDevice));
+    h->state_set = true;
+    return SBC_OK;
+}
+
+int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, double *phi,
+                  double *vproj, double *fx, double *fy, uint32_t *bin_step, uint32_t *stb,
+                  uint8_t *alive) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<float4> pv(total), pvd(total);
+    std::vector<float2> hv(total), fo(total);
+    std::vector<uint2> tm(total);
+    std::vector<uint8_t> al(total);
+    SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(pvd.data(), S.pv_dead, total * sizeof(float4), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(hv.data(), S.hv, total * sizeof(float2), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(tm.data(), S.timers, total * sizeof(uint2), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
+    for (size_t g = 0; g < total; g++) {
+        const float4 p = al[g] ? pv[g] : pvd[g];
+        if (x) x[g] = p.x;
+        if (y) y[g] = p.y;
+        if (vx) vx[g] = p.z;
+        if (vy) vy[g] = p.w;
+        if (phi) phi[g] = hv[g].x;
+        if (vproj) vproj[g] = hv[g].y;
+        if (fx) fx[g] = fo[g].x;
+        if (fy) fy[g] = fo[g].y;
+        if (bin_step) bin_step[g] = tm[g].x;
+        if (stb) stb[g] = tm[g].y;
+        if (alive) alive[g] = al[g];
+    }
+    return SBC_OK;
+}
+
+int sbc_get_particles(sbc_handle *h, double *out, uint8_t *alive) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<float4> pv(total);
+    std::vector<float2> fo(total);
+    std::vector<uint8_t> al(total);
+    SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
+    for (size_t g = 0; g < total; g++) {
+        double *o = out + g * 7;
+        if (al[g]) {
+            o[0] = pv[g].x; o[1] = pv[g].y; o[2] = pv[g].z; o[3] = pv[g].w;
+            o[4] = 0.0; o[5] = fo[g].x; o[6] = fo[g].y;
+        } else {
+            for (int k = 0; k < 7; k++) o[k] = 0.0;
+        }
+        if (alive) alive[g] = al[g];
+    }
+    return SBC_OK;
+}
+
+int sbc_get_predators(sbc_handle *h, double *out) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t n = (size_t)S.Npred * S.R;
+    if (n == 0) return SBC_OK;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<float4> pp(n);
+    SBC_CUDA(cudaMemcpy(pp.data(), S.pred_pv, n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t j = 0; j < n; j++) {
+        double *o = out + j * 6;
+        o[0] = pp[j].x; o[1] = pp[j].y; o[2] = pp[j].z; o[3] = pp[j].w; o[4] = 0; o[5] = 0;
+    }
+    return SBC_OK;
+}
+
+int sbc_set_predators(sbc_handle *h, const double *x, const double *y, const double *phi,
+                      int spawned) {
+    if (!h || !x || !y || !phi) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t n = (size_t)S.Npred * S.R;
+    if (n == 0) return SBC_OK;
+    std::vector<float4> pp(n);
+    std::vector<float> ph(n);
+    for (size_t j = 0; j < n; j++) {
+        ph[j] = (float)phi[j];
+        pp[j] = make_float4((float)x[j], (float)y[j], h->P.pred_speed * cosf(ph[j]),
+                            h->P.pred_speed * sinf(ph[j]));
+    }
+    std::vector<int> sp(S.R, spawned ? 1 : 0);
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaMemcpy(S.pred_pv, pp.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.pred_phi, ph.data(), n * sizeof(float), cudaMemcpyHostToDevice));
+    SBC_CUDA(cudaMemcpy(S.pred_spawned, sp.data(), S.R * sizeof(int), cudaMemcpyHostToDevice));
+    return SBC_OK;
+}
+
+int sbc_get_counts(sbc_handle *h, int32_t *n_alive, int32_t *n_dead) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> nd(S.R);
+    SBC_CUDA(cudaMemcpy(nd.data(), S.n_dead, S.R * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < S.R; r++) {
+        if (n_alive) n_alive[r] = S.N - nd[r];
+        if (n_dead) n_dead[r] = nd[r];
+    }
+    return SBC_OK;
+}
+
+int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
+    if (!h || n_steps < 0) return SBC_ERR_INVALID;
+    if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_step: no state");
+    if (n_steps == 0) return SBC_OK;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const sbc_params &p = h->hp;
+    const double dt = p.dt;
+    const bool injected = S.inj_social || S.inj_dir || S.inj_k;
+    if (injected && n_steps != 1) return fail(h, SBC_ERR_STATE, "sbc_step: injected decisions hold for one step");
+    const bool block_path = !h->force_multikernel && S.N <= 1024 && S.Npred == 0 &&
+                            p.path != SBC_PATH_CELLLIST;
+    if (block_path) {
+        // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
+        int64_t done = 0;
+        while (done < n_steps) {
+            const int64_t chunk = (n_steps - done > (1ll << 30)) ? (1ll << 30) : (n_steps - done);
+            sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream);
+            done += chunk;
+            h->host_stats[2]++;
+        }
+    } else {
+        for (int64_t s = s_first; s < s_first + n_steps; s++) {
+            const bool pred_phase = S.Npred > 0 && (double)s >= p.pred_time / dt;
+            if (S.Npred > 0 && (double)s >= p.pred_time / dt && (double)(s - 1) < p.pred_time / dt) {
+                sbc_launch_pred_spawn(h->P, S, s, 0, h->stream);  // swarmdyn.cpp:153-158
+                h->host_stats[7]++;
+            }
+            if (S.Npred > 1 && pred_phase) {  // swarmdyn.cpp:160-170
+                const int since = (int)s - (int)(p.pred_time / dt);
+                int needed;
+                if (p.pred_speed0 > 0) needed = (int)(p.sizeL / 2 / (p.pred_speed0 * dt));
+                else needed = (int)((p.sim_time - p.trans_time) / 4 / dt);
+                if (needed > 0 && since % needed == 0) {
+                    sbc_launch_pred_spawn(h->P, S, s, 1, h->stream);
+                    h->host_stats[7]++;
+                }
+            }
+            sbc_launch_pair_allpairs(h->P, S, 0, h->stream);
+            h->host_stats[0]++;
+            h->host_stats[7] += 2;
+            sbc_launch_update(h->P, S, s, pred_phase ? 1 : 0, h->stream);
+            h->host_stats[1]++;
+            if (pred_phase) {
+                sbc_launch_pred_move_kill(h->P, S, s, h->stream);
+                h->host_stats[7]++;
+            }
+        }
+    }
+    h->host_stats[5] += (unsigned long long)n_steps * (unsigned long long)S.N * (unsigned long long)S.R;
+    S.inj_social = nullptr;
+    S.inj_dir = nullptr;
+    S.inj_k = nullptr;
+    SBC_CUDA(cudaGetLastError());
+    return SBC_OK;
+}
+
+int sbc_observables(sbc_handle *h, double *out) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_observables(h->P, h->S, h->obs_dev, h->stream);
+    h->host_stats[7]++;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaMemcpy(out, h->obs_dev, (size_t)h->S.R * 8 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SBC_OK;
+}
+
+int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_alg, int32_t *c_att,
+                          double *f_rep, double *f_alg, double *f_att, int64_t *nn_ptr,
+                          int32_t *nn_idx, int64_t nn_capacity) {
+    if (!h) return SBC_ERR_INVALID;
+    if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_pair_interactions: no state");
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    const int all_rows = (flags == SBC_PAIR_ALL_ROWS);
+    sbc_launch_pair_allpairs(h->P, S, all_rows, h->stream);
+    h->host_stats[0]++;
+    if (all_rows) h->host_stats[3] += (unsigned long long)S.R * S.N * (unsigned long long)(S.N - 1);
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaGetLastError());
+    std::vector<float> acc(total * 8);
+    std::vector<int> cnt(total * 4);
+    SBC_CUDA(cudaMemcpy(acc.data(), S.acc, total * 8 * sizeof(float), cudaMemcpyDeviceToHost));
+    SBC_CUDA(cudaMemcpy(cnt.data(), S.cnt, total * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t g = 0; g < total; g++) {
+        if (c_rep) c_rep[g] = cnt[g * 4 + 0];
+        if (c_alg) c_alg[g] = cnt[g * 4 + 1];
+        if (c_att) c_att[g] = cnt[g * 4 + 2];
+        if (f_rep) { f_rep[2 * g] = acc[g * 8 + 0]; f_rep[2 * g + 1] = acc[g * 8 + 1]; }
+        if (f_alg) { f_alg[2 * g] = acc[g * 8 + 2]; f_alg[2 * g + 1] = acc[g * 8 + 3]; }
+        if (f_att) { f_att[2 * g] = acc[g * 8 + 4]; f_att[2 * g + 1] = acc[g * 8 + 5]; }
+    }
+    if (nn_ptr) {
+        std::vector<long long> ptr(total + 1);
+        long long run = 0;
+        for (size_t g = 0; g < total; g++) {
+            ptr[g] = run;
+            run += cnt[g * 4 + 0] + cnt[g * 4 + 1] + cnt[g * 4 + 2];
+        }
+        ptr[total] = run;
+        for (size_t g = 0; g <= total; g++) nn_ptr[g] = ptr[g];
+        if (nn_idx) {
+            if (run > nn_capacity) return fail(h, SBC_ERR_NOMEM, "sbc_pair_interactions: nn_capacity too small");
+            long long *ptr_dev = nullptr;
+            int *idx_dev = nullptr;
+            SBC_CUDA(dev_alloc(&ptr_dev, total + 1));
+            SBC_CUDA(dev_alloc(&idx_dev, (size_t)(run > 0 ? run : 1)));
+            SBC_CUDA(cudaMemcpy(ptr_dev, ptr.data(), (total + 1) * sizeof(long long), cudaMemcpyHostToDevice));
+            sbc_launch_nn_fill(h->P, S, all_rows, ptr_dev, idx_dev, h->stream);
+            h->host_stats[7]++;
+            SBC_CUDA(cudaStreamSynchronize(h->stream));
+            SBC_CUDA(cudaMemcpy(nn_idx, idx_dev, (size_t)run * sizeof(int), cudaMemcpyDeviceToHost));
+            cudaFree(ptr_dev);
+            cudaFree(idx_dev);
+        }
+    }
+    return SBC_OK;
+}
+
+int sbc_inject_decisions(sbc_handle *h, const double *u_social, const double *u_dir,
+                         const uint32_t *k_next) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (u_social) {
+        if (!h->inj_social_dev) SBC_CUDA(dev_alloc(&h->inj_social_dev, total));
+        SBC_CUDA(cudaMemcpy(h->inj_social_dev, u_social, total * sizeof(double), cudaMemcpyHostToDevice));
+        S.inj_social = h->inj_social_dev;
+    }
+    if (u_dir) {
+        if (!h->inj_dir_dev) SBC_CUDA(dev_alloc(&h->inj_dir_dev, total));
+        std::vector<float> f(total);
+        for (size_t g = 0; g < total; g++) f[g] = (float)u_dir[g];
+        SBC_CUDA(cudaMemcpy(h->inj_dir_dev, f.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+        S.inj_dir = h->inj_dir_dev;
+    }
+    if (k_next) {
+        if (!h->inj_k_dev) SBC_CUDA(dev_alloc(&h->inj_k_dev, total));
+        SBC_CUDA(cudaMemcpy(h->inj_k_dev, k_next, total * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        S.inj_k = h->inj_k_dev;
+    }
+    return SBC_OK;
+}
+
+int sbc_philox_decisions(sbc_handle *h, int64_t step, double *u_social, double *u_dir,
+                         uint32_t *k_next) {
+    if (!h) return SBC_ERR_INVALID;
+    const DevState &S = h->S;
+    for (int r = 0; r < S.R; r++)
+        for (int i = 0; i < S.N; i++) {
+            const uint4 q = sbc_philox4x32_10((uint32_t)i, (uint32_t)step, SBC_SLOT_DECISION,
+                                              (uint32_t)r + h->P.replicate_offset, h->P.seed_lo, h->P.seed_hi);
+            const size_t g = (size_t)r * S.N + i;
+            if (u_social) u_social[g] = (double)q.x * (1.0 / 4294967296.0);
+            if (u_dir) u_dir[g] = (double)((float)(q.y >> 8) * (1.0f / 16777216.0f));
+            if (k_next) {
+                uint32_t lo = 0, hi = (uint32_t)h->geo_host.size();
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (q.z < h->geo_host[mid]) hi = mid; else lo = mid + 1;
+                }
+                k_next[g] = lo + 1;
+            }
+        }
+    return SBC_OK;
+}
+
+int sbc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    const uint4 q = sbc_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+    return SBC_OK;
+}
+
+/* test hook: collect branch flags (OR over steps) into a device buffer; flags==NULL reads+clears */
+int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (enable && !h->flags_dev) {
+        SBC_CUDA(dev_alloc(&h->flags_dev, total));
+        SBC_CUDA(cudaMemset(h->flags_dev, 0, total));
+    }
+    if (out && h->flags_dev) {
+        SBC_CUDA(cudaMemcpy(out, h->flags_dev, total, cudaMemcpyDeviceToHost));
+        SBC_CUDA(cudaMemset(h->flags_dev, 0, total));
+    }
+    S.flags = enable ? h->flags_dev : nullptr;
+    return SBC_OK;
+}
+
+/* test hook: route swarms of <= 1024 agents through the multi-kernel path as well */
+int sbc_debug_force_multikernel(sbc_handle *h, int on) {
+    if (!h) return SBC_ERR_INVALID;
+    h->force_multikernel = on != 0;
+    return SBC_OK;
+}
+
+int sbc_get_stats(sbc_handle *h, uint64_t out[8]) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    unsigned long long dev[8];
+    SBC_CUDA(cudaMemcpy(dev, h->S.stats, sizeof(dev), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 8; k++) out[k] = h->host_stats[k] + dev[k];
+    return SBC_OK;
+}
+
+int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms) {
+    if (!h || !ms || iters < 1) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    SBC_CUDA(cudaEventCreate(&e0));
+    SBC_CUDA(cudaEventCreate(&e1));
+    const int all_rows = (flags == SBC_PAIR_ALL_ROWS);
+    sbc_launch_pair_allpairs(h->P, h->S, all_rows, h->stream);  // warm-up
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaEventRecord(e0, h->stream));
+    for (int k = 0; k < iters; k++) sbc_launch_pair_allpairs(h->P, h->S, all_rows, h->stream);
+    SBC_CUDA(cudaEventRecord(e1, h->stream));
+    SBC_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    SBC_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / (float)iters;
+    h->host_stats[0] += (unsigned long long)iters + 1;
+    if (all_rows)
+        h->host_stats[3] += (unsigned long long)(iters + 1) * h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    SBC_CUDA(cudaGetLastError());
+    return SBC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,479 @@
+// sbc_device.cuh - device-side building blocks shared by every kernel of libsbc.so (sm_100a).
+//
+// FP32 structure-of-arrays state, FP64 only in the rare exact re-checks that make integer
+// results (zone ids, neighbour counts, burst timers) bit-identical to the reference.
+// Reference lines are cited as file:line into /root/reference/src.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SBC_PI_F 3.14159265358979323846f
+#define SBC_TWO_PI_F 6.28318530717958647692f
+#define SBC_PI_D 3.14159265358979323846
+
+// ---------------------------------------------------------------------------------------------
+// parameters as the kernels see them
+// ---------------------------------------------------------------------------------------------
+struct DevParams {
+    // geometry / dynamics (FP32 copies of sbc_params)
+    float L, halfL, invL;
+    float dt, beta, alphaTurn;
+    float soc, env;
+    float rep, alg, att;           // ranges
+    float rep2, alg2, att2;        // squared thresholds for the fast compare
+    float band_lo[3], band_hi[3];  // d2 inside [lo,hi] of any threshold => FP64 re-check
+    float flee_range, inv_flee_range;
+    float pred_speed, kill_range, kill_rate, noisep;
+    float wall_margin_r;           // sizeL - 2 (agents_dynamics.cpp:111)
+    float t_burst;                 // dt * burst_steps
+    // exact copies for FP64 re-checks
+    double dL, d_rep, d_alg, d_att, d_prob_social, d_flee_range, d_kill_range;
+    // integers
+    uint32_t burst_steps, max_steps;
+    int32_t BC, N_confu, pred_kill, pred_move;
+    int32_t has_alg_zone;          // alg_range > rep_range
+    // Philox key / ids
+    uint32_t seed_lo, seed_hi;
+    uint32_t replicate_offset;
+};
+
+// per-agent persistent state (registers in the block kernel, SoA arrays in global memory)
+struct AgentState {
+    float x, y, vx, vy;
+    float phi, vproj;
+    float fx, fy;
+    uint32_t bin_step, stb;
+};
+
+// accumulators of one row (agents_interact.cpp:211-225, :286-290)
+struct RowAcc {
+    float rep_x, rep_y, alg_x, alg_y, att_x, att_y, flee_x, flee_y;
+    int c_rep, c_alg, c_att, c_flee;
+};
+__device__ __forceinline__ void row_acc_clear(RowAcc &a) {
+    a.rep_x = a.rep_y = a.alg_x = a.alg_y = a.att_x = a.att_y = a.flee_x = a.flee_y = 0.f;
+    a.c_rep = a.c_alg = a.c_att = a.c_flee = 0;
+}
+
+// branch flags, same bit meaning as orc_step() in oracle/sbc_oracle.h
+enum {
+    SBC_FL_BURST_START = 1, SBC_FL_SOCIAL = 2, SBC_FL_WALL = 4, SBC_FL_VPROJ_HACK = 8,
+    SBC_FL_OVERSHOOT = 16, SBC_FL_BOUNDARY = 32, SBC_FL_FLEE = 64, SBC_FL_REARM = 128
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10, counter (agent, step, slot, replicate), key (seed_lo, seed_hi)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint4 sbc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                            uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int round = 0; round < 10; round++) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+#else
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+#define SBC_SLOT_DECISION 0u
+#define SBC_SLOT_DETECT0 1u
+#define SBC_PREDATOR_AGENT_ID 0xFFFFFFFFu
+
+__device__ __forceinline__ uint4 sbc_draw(const DevParams &P, uint32_t replicate, uint32_t agent,
+                                          uint32_t step, uint32_t slot) {
+    return sbc_philox4x32_10(agent, step, slot, replicate + P.replicate_offset, P.seed_lo, P.seed_hi);
+}
+
+// smallest k >= 1 with r < thr[k-1]; none -> max_steps + 1 (inverse CDF of the rejection loop
+// agents_dynamics.cpp:250-270, integer-exact against the oracle's table)
+__device__ __forceinline__ uint32_t sbc_geometric_k(const uint32_t *__restrict__ thr, uint32_t n,
+                                                    uint32_t r) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (r < __ldg(thr + mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo + 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+// minimum image of a raw difference with |r| < L (positions are kept in [0,L), so one fold is
+// enough); agrees with fmod(r + sgn(r) L/2, L) - sgn(r) L/2 (mathtools.h:64-71) away from the
+// |r| = L/2 tie, which lies outside att_range (asserted at sbc_create).
+__device__ __forceinline__ float sbc_min_image(float r, const DevParams &P) {
+    // round-to-nearest of r/L through the 1.5*2^23 magic constant: FADD/FFMA only, no FRND
+    const float n = __fadd_rn(__fmaf_rn(r, P.invL, 12582912.f), -12582912.f);
+    return __fmaf_rn(-P.L, n, r);
+}
+
+// FP64 replay of CalcDistVec + vec_length + SFM_4Zone in the reference's operation order
+// (mathtools.h:54-83, social_forces.cpp:33-47): returns 0,1,2 or 3 (= none).
+static __device__ __noinline__ int sbc_zone_exact(float xi, float yi, float xj, float yj,
+                                           const DevParams &P) {
+    double r[2] = {__dsub_rn((double)xj, (double)xi), __dsub_rn((double)yj, (double)yi)};
+    if (P.BC == 0) {
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            const double s = (double)((0.0 < r[d]) - (r[d] < 0.0));
+            const double h = __ddiv_rn(__dmul_rn(s, P.dL), 2.0);
+            const double t = fmod(__dadd_rn(r[d], h), P.dL);
+            r[d] = __dsub_rn(t, h);
+        }
+    }
+    const double len = __dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1]));
+    const double d = __dsqrt_rn(len);
+    if (d <= P.d_rep) return 0;
+    if (d > P.d_rep && d <= P.d_alg) return 1;
+    if (d > P.d_alg && d <= P.d_att) return 2;
+    return 3;
+}
+
+// fast zone from the FP32 squared distance; `amb` is set when d2 falls inside the rounding band
+// of any threshold (then the caller must ask sbc_zone_exact)
+__device__ __forceinline__ int sbc_zone_fast(float d2, const DevParams &P, bool &amb) {
+    amb = (d2 >= P.band_lo[0] && d2 <= P.band_hi[0]) || (d2 >= P.band_lo[1] && d2 <= P.band_hi[1]) ||
+          (d2 >= P.band_lo[2] && d2 <= P.band_hi[2]);
+    return (d2 <= P.rep2) ? 0 : (d2 <= P.alg2) ? 1 : (d2 <= P.att2) ? 2 : 3;
+}
+
+// one directed pair (row i <- j) in the straightforward form used by the block kernel and the
+// exact re-do paths; the tiled all-pairs kernel has its own instruction-tuned inner loop
+__device__ __forceinline__ void sbc_pair_accumulate(RowAcc &acc, float xi, float yi, float4 pj,
+                                                    const DevParams &P, int &zone_out) {
+    float dx = pj.x - xi, dy = pj.y - yi;
+    if (P.BC == 0) {
+        dx = sbc_min_image(dx, P);
+        dy = sbc_min_image(dy, P);
+    }
+    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    bool amb;
+    int z = sbc_zone_fast(d2, P, amb);
+    if (amb) z = sbc_zone_exact(xi, yi, pj.x, pj.y, P);
+    const float rinv = (d2 > 0.f) ? rsqrtf(d2) : 0.f;  // u_ji = 0 when d = 0, agents_interact.cpp:199
+    const float ux = dx * rinv, uy = dy * rinv;
+    if (z == 0) { acc.rep_x -= ux; acc.rep_y -= uy; acc.c_rep++; }
+    else if (z == 1) { acc.alg_x += pj.z; acc.alg_y += pj.w; acc.c_alg++; }
+    else if (z == 2) { acc.att_x += ux; acc.att_y += uy; acc.c_att++; }
+    zone_out = z;
+}
+
+// prey <- predator detection, agents_interact.cpp:252-292; u_detect from the agent's own draw
+__device__ __forceinline__ void sbc_detect_accumulate(RowAcc &acc, float xi, float yi, float px,
+                                                      float py, double u_detect,
+                                                      const DevParams &P) {
+    float dx = px - xi, dy = py - yi;
+    if (P.BC == 0) {
+        dx = sbc_min_image(dx, P);
+        dy = sbc_min_image(dy, P);
+    }
+    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    const float d = sqrtf(d2);
+    const float fs = 2.f / (1.f + d * P.inv_flee_range);
+    bool hit = (float)u_detect < fs;
+    // the decision `u < 2/(1+d/flee_range)` is re-taken in FP64 when FP32 cannot separate the two
+    if (fabsf((float)u_detect - fs) <= 4e-6f * fmaxf(fs, 1.f)) {
+        double r[2] = {__dsub_rn((double)px, (double)xi), __dsub_rn((double)py, (double)yi)};
+        if (P.BC == 0) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const double s = (double)((0.0 < r[k]) - (r[k] < 0.0));
+                const double h = __ddiv_rn(__dmul_rn(s, P.dL), 2.0);
+                r[k] = __dsub_rn(fmod(__dadd_rn(r[k], h), P.dL), h);
+            }
+        }
+        const double dd = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
+        const double fsd = __ddiv_rn(2.0, __dadd_rn(1.0, __ddiv_rn(dd, P.d_flee_range)));
+        hit = u_detect < fsd;
+    }
+    if (hit) {
+        const float rinv = (d2 > 0.f) ? rsqrtf(d2) : 0.f;
+        acc.c_flee++;
+        acc.flee_x -= dx * rinv;
+        acc.flee_y -= dy * rinv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wall look-ahead (agents_dynamics.cpp:627-772) in closed form.
+//
+// With constant force F during tb = min(t_burst, t_tnb) and coasting for t_tnb - tb afterwards,
+// predictXatNextBurst is LINEAR in v and F:  x_fut = x + A v + B F, with
+//   E1 = exp(-beta tb), E2 = exp(-beta (t_tnb - tb)),
+//   A = (1 - E1)/beta + E1 (1 - E2)/beta,
+//   B = tb/beta - (1 - E1)/beta^2 + (1 - E1)(1 - E2)/beta^2
+// (expand predictPos(v,F,tb) + predictPos(predictV(v,F,tb),0,t_tnb-tb)). A and B do not depend on
+// the force direction, so the direction search of forceChange2NotCollide only re-evaluates
+// |P + R (cos a, sin a)| with P = x + A v and R = B |F| - no exponentials inside the search.
+// ---------------------------------------------------------------------------------------------
+struct WallCoef { float A, B; };
+__device__ __forceinline__ WallCoef sbc_wall_coef(uint32_t stb, const DevParams &P) {
+    const float t_tnb = P.dt * (float)stb;
+    const float tb = fminf(P.t_burst, t_tnb);
+    const float E1 = expf(-P.beta * tb), E2 = expf(-P.beta * (t_tnb - tb));
+    const float ib = 1.f / P.beta;
+    WallCoef c;
+    c.A = (1.f - E1) * ib + E1 * (1.f - E2) * ib;
+    c.B = tb * ib - (1.f - E1) * ib * ib + (1.f - E1) * (1.f - E2) * ib * ib;
+    return c;
+}
+
+// forceChange2NotCollide, agents_dynamics.cpp:699-756 (same search schedule, cheap predictor)
+__device__ __forceinline__ float sbc_force_change(float px, float py, float R, float fang,
+                                                  float dphi, const DevParams &P) {
+    float inside_change = SBC_PI_F;
+    bool outside = true, found = false;
+    float change = dphi;
+    const float L2 = P.L * P.L;
+    while (fabsf(change) < SBC_PI_F && outside) {
+        float s, c;
+        sincosf(fang + change, &s, &c);
+        const float qx = px + R * c, qy = py + R * s;
+        if (qx * qx + qy * qy < L2) {
+            inside_change = change;
+            found = true;
+            outside = false;
+        }
+        if (found) dphi *= 0.5f;
+        if (outside) {
+            change += dphi;
+        } else if (fabsf(dphi) > SBC_PI_F / 64.f) {
+            change -= dphi;
+            outside = true;
+        }
+    }
+    return inside_change;
+}
+
+// ---------------------------------------------------------------------------------------------
+// burst decision, agents_dynamics.cpp:23-121 (draw_social_or_environmental_force)
+// returns the force (magnitude force_mag) and updates flags
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sbc_decide(const AgentState &a, const RowAcc &acc, double u_social,
+                                           float u_dir, const DevParams &P, float &fx, float &fy,
+                                           float &force_mag, uint32_t &fl) {
+    float gx = 0.f, gy = 0.f;
+    force_mag = P.soc;
+    if (u_social <= P.d_prob_social) {  // :35, taken in FP64: u = r * 2^-32 is exact
+        fl |= SBC_FL_SOCIAL;
+        if (acc.c_rep > 0) {  // :40
+            gx = acc.rep_x;
+            gy = acc.rep_y;
+        } else {
+            if (acc.alg_x != 0.f || acc.alg_y != 0.f) {  // :47-52 set_mag(force_alg, c_alg)
+                const float s = (float)acc.c_alg * rsqrtf(acc.alg_x * acc.alg_x + acc.alg_y * acc.alg_y);
+                gx += acc.alg_x * s;
+                gy += acc.alg_y * s;
+            }
+            if (acc.att_x != 0.f || acc.att_y != 0.f) {  // :53-58
+                const float s = (float)acc.c_att * rsqrtf(acc.att_x * acc.att_x + acc.att_y * acc.att_y);
+                gx += acc.att_x * s;
+                gy += acc.att_y * s;
+            }
+        }
+        if (gx != 0.f || gy != 0.f) {  // :62-65
+            const float s = rsqrtf(gx * gx + gy * gy);
+            gx *= s;
+            gy *= s;
+        } else {  // :67-71
+            sincosf(a.phi, &gy, &gx);
+        }
+    } else {
+        if (acc.c_flee > 0) {  // :76-80 (a zero flee sum gives NaN in the reference as well)
+            fl |= SBC_FL_FLEE;
+            const float s = rsqrtf(acc.flee_x * acc.flee_x + acc.flee_y * acc.flee_y);
+            gx = acc.flee_x * s;
+            gy = acc.flee_y * s;
+        } else {  // :81-89
+            force_mag = P.env;
+            sincosf(SBC_TWO_PI_F * u_dir, &gy, &gx);
+        }
+    }
+    if (P.BC >= 5) {  // :93-117
+        const WallCoef w = sbc_wall_coef(a.stb, P);
+        const float px = a.x + w.A * a.vx, py = a.y + w.A * a.vy;
+        const float R = w.B * force_mag;
+        const float qx = px + R * gx, qy = py + R * gy;
+        if (qx * qx + qy * qy > P.wall_margin_r * P.wall_margin_r) {
+            fl |= SBC_FL_WALL;
+            const float fang = atan2f(gy, gx);
+            const float ccw = sbc_force_change(px, py, R, fang, SBC_PI_F / 4.f, P);
+            const float cw = sbc_force_change(px, py, R, fang, -SBC_PI_F / 4.f, P);
+            float ang = ccw;
+            if (fabsf(cw) < fabsf(ang)) ang = cw;
+            sincosf(ang + fang, &gy, &gx);
+        }
+    }
+    fx = force_mag * gx;
+    fy = force_mag * gy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Boundary<agent>, agents_dynamics.cpp:276-471. Returns true when the state was changed.
+// BC 0 is applied as a conditional shift (== fmod(x + L, L) for x in [-L, 2L), without the
+// rounding that x + L would cost in FP32).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool sbc_boundary(float &x, float &y, float &vx, float &vy, float &phi,
+                                             const DevParams &P) {
+    const float L = P.L;
+    switch (P.BC) {
+    case 0: {
+        if (x < 0.f) x += L; else if (x >= L) x -= L;
+        if (y < 0.f) y += L; else if (y >= L) y -= L;
+        return false;
+    }
+    case 5:
+    case 6: {
+        const float r2 = x * x + y * y;
+        if (r2 > L * L) {
+            const float r = sqrtf(r2);
+            const float nx = x / r, ny = y / r;
+            const float diff = r - L;
+            x -= 2.f * diff * nx;
+            y -= 2.f * diff * ny;
+            const float vn = nx * vx + ny * vy;
+            const float g = (P.BC == 5) ? 2.f * vn : vn;
+            vx -= g * nx;
+            vy -= g * ny;
+            phi = atan2f(vy, vx);  // u = v/|v|, phi = atan2(u) (:447-449, :467-469)
+            return true;
+        }
+        return false;
+    }
+    case 1: {  // inelastic box :300-356
+        const float dphi = 0.1f;
+        bool hit = false;
+        float t;
+        if (x > L) { x = 0.9999f * L; t = (vy > 0.f) ? (0.5f + dphi) * SBC_PI_F : -(0.5f + dphi) * SBC_PI_F; sincosf(t, &vy, &vx); hit = true; }
+        else if (x < 0.f) { x = 0.0001f; t = (vy > 0.f) ? (0.5f - dphi) * SBC_PI_F : -(0.5f - dphi) * SBC_PI_F; sincosf(t, &vy, &vx); hit = true; }
+        if (y > L) { y = 0.9999f * L; t = (vx > 0.f) ? -dphi : SBC_PI_F + dphi; sincosf(t, &vy, &vx); hit = true; }
+        else if (y < 0.f) { y = 0.0001f; t = (vx > 0.f) ? dphi : SBC_PI_F - dphi; sincosf(t, &vy, &vx); hit = true; }
+        return hit;
+    }
+    case 2: {  // elastic box :358-384
+        bool hit = false;
+        if (x > L) { x -= 2.f * (x - L); vx = -vx; hit = true; } else if (x < 0.f) { x -= 2.f * x; vx = -vx; hit = true; }
+        if (y > L) { y -= 2.f * (y - L); vy = -vy; hit = true; } else if (y < 0.f) { y -= 2.f * y; vy = -vy; hit = true; }
+        return hit;
+    }
+    case 3: {  // x periodic, y elastic :386-406
+        bool hit = false;
+        if (x < 0.f) x += L; else if (x >= L) x -= L;
+        if (y > L) { y -= 2.f * (y - L); vy = -vy; hit = true; } else if (y < 0.f) { y -= 2.f * y; vy = -vy; hit = true; }
+        return hit;
+    }
+    case 4: {  // x periodic, y inelastic :407-430
+        bool hit = false;
+        if (x < 0.f) x += L; else if (x >= L) x -= L;
+        if (y > L) { y = L - 0.0001f; vy = 0.f; hit = true; } else if (y < 0.f) { y = 0.0001f; vy = 0.f; hit = true; }
+        return hit;
+    }
+    default:
+        return false;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ParticleBurstCoast, agents_dynamics.cpp:150-273, for one agent and one step.
+//   acc       : accumulators of this row (only read when the agent starts a burst)
+//   u_social, u_dir, k_next : this agent-step's decisions (Philox or injected)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sbc_agent_step(AgentState &a, float &cu, float &su,
+                                               const RowAcc &acc, double u_social, float u_dir,
+                                               uint32_t k_next, const DevParams &P, uint32_t &fl) {
+    // (cu, su) = (cos, sin)(a.phi) on entry and on exit: the reference recomputes u from phi at
+    // every step (:197,:227-228); caching it lets a coasting agent (force = 0, heading unchanged)
+    // skip every transcendental.
+    const bool first = (a.bin_step == P.burst_steps);
+    const bool bursting = (a.bin_step > 0);
+    float fx, fy, force_mag = P.soc;
+    if (first) {
+        fl |= SBC_FL_BURST_START;
+        sbc_decide(a, acc, u_social, u_dir, P, fx, fy, force_mag, fl);
+        a.fx = fx;
+        a.fy = fy;
+    } else if (bursting) {
+        fx = a.fx;
+        fy = a.fy;
+    } else {
+        fx = fy = 0.f;
+        a.fx = a.fy = 0.f;
+    }
+    if (bursting) a.bin_step -= 1;
+    if (a.stb > 0) a.stb -= 1;
+
+    const float vproj_old = a.vproj;
+    const float forcev = fx * cu + fy * su;
+    float vproj = vproj_old + (-P.beta * vproj_old + forcev) * P.dt;  // :202
+    const bool coast = (fx == 0.f) && (fy == 0.f) && (vproj >= 0.f) &&
+                       (fabsf(a.phi) < SBC_TWO_PI_F);
+    if (!coast) {
+        float lphi = a.phi;
+        float sl = su, cl = cu;
+        if (vproj < 0.f) {  // :206-210
+            fl |= SBC_FL_VPROJ_HACK;
+            vproj = 0.001f;
+            lphi += 0.5f * SBC_PI_F;
+            sincosf(lphi, &sl, &cl);
+        }
+        const float forcep = -fx * sl + fy * cl;
+        lphi += P.alphaTurn * forcep * P.dt / vproj_old;  // :215 (old vproj)
+        float sn, cn;
+        sincosf(lphi, &sn, &cn);
+        const float dphi = fabsf(lphi - a.phi);
+        if (dphi > 0.01f) {
+            // overshoot_check :123-137. acos is monotone decreasing, so the three angles are
+            // compared through their cosines; an argument outside [-1,1] is NaN in the
+            // reference (every comparison false) - reproduced by the `ok` predicates, with a
+            // rounding allowance of 1e-6 so that |cos| = 1 + ulp is not mistaken for it.
+            const float inv = 1.f / force_mag;
+            const float c0 = (cu * fx + su * fy) * inv;  // cos(angle(u_old, F))
+            const float c1 = (cn * fx + sn * fy) * inv;  // cos(angle(u_new, F))
+            const float c01 = cn * cu + sn * su;         // cos(angle(u_new, u_old))
+            const bool ok0 = fabsf(c0) <= 1.000001f, ok1 = fabsf(c1) <= 1.000001f;
+            const bool o1 = ok0 && ok1 && (c0 > c1);
+            const bool o2 = !o1 && ok0 && (c01 < c0);
+            const bool o3 = dphi > SBC_PI_F;
+            if (o1 || o2 || o3) {
+                fl |= SBC_FL_OVERSHOOT;
+                lphi = atan2f(fy, fx);
+                sincosf(lphi, &sn, &cn);
+            }
+        }
+        const float wrapped = fmodf(lphi, SBC_TWO_PI_F);  // :226 (sign kept)
+        if (wrapped != lphi) sincosf(wrapped, &sn, &cn);
+        a.phi = wrapped;
+        cu = cn;
+        su = sn;
+    }
+    a.vproj = vproj;
+    a.vx = vproj * cu;
+    a.vy = vproj * su;
+    a.x += a.vx * P.dt;
+    a.y += a.vy * P.dt;
+    if (P.BC != -1) {  // :247
+        if (sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P)) {
+            fl |= SBC_FL_BOUNDARY;
+            sincosf(a.phi, &su, &cu);
+        }
+    }
+    if (a.stb == 0) {  // :250-270
+        fl |= SBC_FL_REARM;
+        a.bin_step = P.burst_steps;
+        a.stb = k_next;
+    }
+    if (P.BC != -1) {  // :272
+        if (sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P)) sincosf(a.phi, &su, &cu);
+    }
+}

@@ -1,0 +1,57 @@
+// sbc_kernels.cuh - host-callable launchers of the sm_100a kernels (definitions in the .cu files).
+#pragma once
+#include "sbc_device.cuh"
+
+// device-resident state of one handle: R replicates x N agents, index g = r*N + i
+struct DevState {
+    int N, R, Npred;
+    float4 *pv;        // {x, y, vx, vy}; x = y = NaN for dead agents (their last pv is in pv_dead)
+    float4 *pv_dead;   // last {x,y,vx,vy} of killed agents
+    float2 *hv;        // {phi, vproj}
+    float2 *force;     // {fx, fy}
+    uint2 *timers;     // {bin_step, steps_till_burst}
+    uint8_t *alive;
+    // row accumulators written by the pair pass, consumed by the update
+    float *acc;        // [R*N][8] rep.xy alg.xy att.xy flee.xy
+    int *cnt;          // [R*N][4] c_rep c_alg c_att c_flee
+    // predators
+    float4 *pred_pv;   // [R][Npred] {x,y,vx,vy}
+    float *pred_phi;   // [R][Npred]
+    int *n_dead;       // [R]
+    int *pred_spawned; // [R]
+    // decisions
+    const uint32_t *geo; // inter-burst table, max_steps entries
+    double *inj_social;  // [R*N] or nullptr
+    float *inj_dir;
+    uint32_t *inj_k;
+    uint8_t *flags;      // [R*N] branch flags OR-ed over steps (test hook), may be nullptr
+    // scratch of the burst-gated pair pass
+    int *active_list;    // [R*N]
+    int *active_count;   // [1]
+    // counters
+    unsigned long long *stats; // [8] see sbc_get_stats
+};
+
+// --- all-pairs three-zone pass (pair_allpairs.cu) ---------------------------------------------
+// rows: all alive rows (all_rows != 0) or rows with bin_step == burst_steps
+void sbc_launch_pair_allpairs(const DevParams &P, const DevState &S, int all_rows, cudaStream_t st);
+// test hook: CSR neighbour lists (ascending j) for the same row set
+void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,
+                        int *nn_idx, cudaStream_t st);
+
+// --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
+void sbc_launch_update(const DevParams &P, const DevState &S, long long step, int pred_active,
+                       cudaStream_t st);
+
+// --- predator spawn / move / kill (predator.cu) ------------------------------------------------
+void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,
+                           cudaStream_t st);
+void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, cudaStream_t st);
+
+// --- one block per swarm, many steps per launch (swarm_block.cu) -------------------------------
+// returns false when the configuration does not fit this path (N > 1024)
+bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first,
+                            long long n_steps, cudaStream_t st);
+
+// --- observables (observables.cu) --------------------------------------------------------------
+void sbc_launch_observables(const DevParams &P, const DevState &S, double *out_dev, cudaStream_t st);

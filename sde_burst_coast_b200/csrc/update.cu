@@ -1,0 +1,85 @@
+// update.cu - per-agent burst-coast update for swarms that do not fit one thread block:
+// ParticleBurstCoast with the burst decision, wall avoidance, Euler step, boundary and burst
+// re-arm (/root/reference/src/agents_dynamics.cpp:150-273), preceded - for rows that start a
+// burst while a predator is present - by the prey<-predator detection of IntCalcPred
+// (agents_interact.cpp:252-292; only rows that read the result evaluate it).
+//
+// One thread per agent, coalesced SoA traffic: 40 B read + 40 B written per agent-step
+// (pv float4, hv float2, force float2, timers uint2) -> HBM-bound.
+#include "sbc_kernels.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, int pred_active) {
+    const size_t total = (size_t)S.N * S.R;
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    if (!S.alive[g]) return;
+    const int N = S.N;
+    const uint32_t rep = (uint32_t)(g / N), i = (uint32_t)(g - (size_t)rep * N);
+    AgentState a;
+    {
+        const float4 p = S.pv[g];
+        const float2 h = S.hv[g];
+        const float2 f = S.force[g];
+        const uint2 t = S.timers[g];
+        a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
+        a.phi = h.x; a.vproj = h.y;
+        a.fx = f.x; a.fy = f.y;
+        a.bin_step = t.x; a.stb = t.y;
+    }
+    const bool first = (a.bin_step == P.burst_steps);
+    const bool rearm = (a.stb <= 1);
+    RowAcc acc;
+    row_acc_clear(acc);
+    double u_social = 0.0;
+    float u_dir = 0.f;
+    uint32_t k_next = 1;
+    if (first || rearm) {
+        const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
+        u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
+        u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
+        if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z);
+    }
+    if (first) {
+        const float4 *ac = reinterpret_cast<const float4 *>(S.acc + g * 8);
+        const float4 a0 = ac[0], a1 = ac[1];
+        const int4 c = *reinterpret_cast<const int4 *>(S.cnt + g * 4);
+        acc.rep_x = a0.x; acc.rep_y = a0.y; acc.alg_x = a0.z; acc.alg_y = a0.w;
+        acc.att_x = a1.x; acc.att_y = a1.y;
+        acc.c_rep = c.x; acc.c_alg = c.y; acc.c_att = c.z;
+        if (pred_active) {
+            const float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
+            for (int j = 0; j < S.Npred; j += 4) {
+                const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DETECT0 + (uint32_t)(j >> 2));
+                const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (j + k < S.Npred) {
+                        const float4 pr = pp[j + k];
+                        sbc_detect_accumulate(acc, a.x, a.y, pr.x, pr.y,
+                                              (double)r[k] * (1.0 / 4294967296.0), P);
+                    }
+                }
+            }
+        }
+    }
+    uint32_t fl = 0;
+    float cu, su;
+    sincosf(a.phi, &su, &cu);
+    sbc_agent_step(a, cu, su, acc, u_social, u_dir, k_next, P, fl);
+    S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
+    S.hv[g] = make_float2(a.phi, a.vproj);
+    S.force[g] = make_float2(a.fx, a.fy);
+    S.timers[g] = make_uint2(a.bin_step, a.stb);
+    if (S.flags) S.flags[g] |= (uint8_t)fl;
+}
+
+}  // namespace
+
+void sbc_launch_update(const DevParams &P, const DevState &S, long long step, int pred_active,
+                       cudaStream_t st) {
+    const size_t total = (size_t)S.N * S.R;
+    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, pred_active);
+}

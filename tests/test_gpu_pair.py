@@ -1,0 +1,103 @@
+"""GPU parity of the three-zone pair pass against the CPU oracle, through the C ABI.
+
+Bar: zone counters and neighbour sets bit-exact; accumulated forces within
+||d|| <= 4 * 2^-24 * sqrt(n) * max(1, sum|terms|) for n contributing pairs.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_params, random_state, nn_sets, f32
+from oracle import pyorc
+from sde_burst_coast_b200.params import PAIR_ACTIVE_ROWS, PAIR_ALL_ROWS
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(sp, N, st, flags, alive=None):
+    from sde_burst_coast_b200.swarm import Swarm
+    w = pyorc.World(sp, N, 0, kind='port')
+    if alive is not None:
+        st = dict(st, alive=alive)
+    w.set_state(**st)
+    ref = w.pair_interactions(flags)
+    g = Swarm(sp, N)
+    g.set_state(**st)
+    got = g.pair_interactions(flags)
+    for k in ('c_rep', 'c_alg', 'c_att'):
+        assert np.array_equal(ref[k], got[k]), k
+    assert np.array_equal(ref['nn_ptr'], got['nn_ptr'])
+    assert nn_sets(ref, N) == nn_sets(got, N)
+    eps = 2.0 ** -24
+    for k, c, scale in (('f_rep', 'c_rep', 1.0), ('f_att', 'c_att', 1.0), ('f_alg', 'c_alg', 25.0)):
+        n = ref[c].astype(np.float64)
+        tol = 4 * eps * np.sqrt(np.maximum(n, 1)) * np.maximum(1.0, n * scale)
+        err = np.linalg.norm(ref[k] - got[k], axis=1)
+        assert np.all(err <= tol), (k, float(err.max()), float(tol[np.argmax(err)]))
+    g.close()
+    w.close()
+    return ref
+
+
+@pytest.mark.parametrize('mode,BC,L,N', [
+    ('burst_coast', 6, 24.5, 8), ('burst_coast', 6, 24.5, 30), ('burst_coast', 6, 24.5, 64),
+    ('burst_coast', 5, 24.5, 33), ('burst_coast', -1, 0, 257),
+    ('natPred', 0, 100.0, 300), ('natPred', 0, 584.0, 1024), ('natPred', 0, 100.0, 1500),
+])
+@pytest.mark.parametrize('alg', [None, 10.0])
+@pytest.mark.parametrize('flags', [PAIR_ALL_ROWS, PAIR_ACTIVE_ROWS])
+def test_pair_parity(mode, BC, L, N, alg, flags):
+    over = dict(BC=BC, Npred=0)
+    if L:
+        over['size'] = L
+    if alg is not None:
+        over['alg_range'] = alg
+    sp, _, _ = make_params(mode, N, **over)
+    rng = np.random.default_rng(1000 + N + BC)
+    st = random_state(N, sp, rng, spread=60.0 if BC == -1 else None)
+    ref = _compare(sp, N, st, flags)
+    if flags == PAIR_ALL_ROWS:
+        assert ref['c_rep'].sum() + ref['c_att'].sum() > 0
+
+
+def test_pair_threshold_ties_and_coincident():
+    """Distances exactly on the closed upper bounds, coincident agents, a lone agent."""
+    sp, _, _ = make_params('burst_coast', 8, BC=-1, rep_range=4.0, alg_range=8.0, att_range=16.0)
+    x = np.array([0.0, 4.0, 8.0, 16.0, 0.0, -4.0000005, 8.000001, 1000.0])
+    y = np.zeros(8)
+    st = dict(x=f32(x), y=f32(y), phi=np.zeros(8), vproj=np.ones(8))
+    ref = _compare(sp, 8, st, PAIR_ALL_ROWS)
+    assert ref['c_rep'][0] == 2 and ref['c_alg'][0] == 2 and ref['c_att'][0] == 2  # ties are inside
+    assert ref['c_rep'][7] + ref['c_alg'][7] + ref['c_att'][7] == 0
+
+
+def test_pair_dead_agents_and_single():
+    sp, _, _ = make_params('natPred', 40, BC=0, size=100.0, Npred=0)
+    rng = np.random.default_rng(7)
+    st = random_state(40, sp, rng, spread=30.0)
+    alive = (rng.random(40) > 0.3).astype(np.uint8)
+    _compare(sp, 40, st, PAIR_ALL_ROWS, alive=alive)
+    sp1, _, _ = make_params('burst_coast', 1)
+    _compare(sp1, 1, random_state(1, sp1, rng), PAIR_ALL_ROWS)
+
+
+def test_pair_band_recheck_exercised():
+    """Pairs placed within a few FP32 ulps of every threshold must come out exactly as in FP64."""
+    sp, _, _ = make_params('natPred', 8, BC=0, size=100.0, Npred=0, alg_range=10.0)
+    rng = np.random.default_rng(11)
+    N = 512
+    thr = np.array([sp.rep_range, sp.alg_range, sp.att_range])
+    x = np.zeros(N)
+    y = np.zeros(N)
+    x[0], y[0] = 50.0, 50.0
+    ang = 2 * np.pi * rng.random(N)
+    r = thr[rng.integers(0, 3, N)] * (1 + (rng.integers(-6, 7, N)) * 2.0 ** -24)
+    x[1:], y[1:] = 50.0 + (r * np.cos(ang))[1:], 50.0 + (r * np.sin(ang))[1:]
+    st = dict(x=f32(x % 100.0), y=f32(y % 100.0), phi=np.zeros(N), vproj=np.ones(N))
+    from sde_burst_coast_b200.swarm import Swarm
+    sp2, _, _ = make_params('natPred', N, BC=0, size=100.0, Npred=0, alg_range=10.0)
+    _compare(sp2, N, st, PAIR_ALL_ROWS)
+    g = Swarm(sp2, N)
+    g.set_state(**st)
+    g.pair_interactions(PAIR_ALL_ROWS, want_nn=False)
+    assert g.stats()['ambiguous_pairs'] > 0
+    g.close()
