@@ -29,7 +29,7 @@ observables_kernel(const __grid_constant__ DevParams P, DevState S, double *out)
             const float4 q = pv[j];
             if (q.x != q.x) continue;
             float dx = q.x - p.x, dy = q.y - p.y;
-            if (P.BC == 0) { dx = sbc_min_image(dx, P); dy = sbc_min_image(dy, P); }
+            if (P.BC == 0) { dx = sbc_delta_pbc(p.x, q.x, P); dy = sbc_delta_pbc(p.y, q.y, P); }
             const float d2 = dx * dx + dy * dy;
             if (best < 0.f || d2 < best) best = d2;
         }

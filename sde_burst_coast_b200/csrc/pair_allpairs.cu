@@ -30,8 +30,8 @@ __device__ __forceinline__ void pair_fast(Acc9 &A, bool &amb, float xi, float yi
                                           const DevParams &P) {
     float dx = pj.x - xi, dy = pj.y - yi;
     if (PERIODIC) {
-        dx = sbc_min_image(dx, P);
-        dy = sbc_min_image(dy, P);
+        dx = sbc_delta_pbc(xi, pj.x, P);
+        dy = sbc_delta_pbc(yi, pj.y, P);
     }
     const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
     const float rinv = rsqrtf(fmaxf(d2, 1e-30f));  // d = 0 -> u = 0 (agents_interact.cpp:199)
@@ -60,8 +60,8 @@ __device__ __noinline__ void tile_exact(Acc9 &A, float xi, float yi, const float
         const float4 pj = tile[j];
         float dx = pj.x - xi, dy = pj.y - yi;
         if (PERIODIC) {
-            dx = sbc_min_image(dx, P);
-            dy = sbc_min_image(dy, P);
+            dx = sbc_delta_pbc(xi, pj.x, P);
+            dy = sbc_delta_pbc(yi, pj.y, P);
         }
         const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
         const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
@@ -179,8 +179,8 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__r
             const float4 pj = pv[j];
             float dx = pj.x - pi.x, dy = pj.y - pi.y;
             if (P.BC == 0) {
-                dx = sbc_min_image(dx, P);
-                dy = sbc_min_image(dy, P);
+                dx = sbc_delta_pbc(pi.x, pj.x, P);
+                dy = sbc_delta_pbc(pi.y, pj.y, P);
             }
             const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
             bool amb;
@@ -248,8 +248,8 @@ __global__ void nn_fill_kernel(const __grid_constant__ DevParams P, DevState S, 
         const float4 pj = pv[j];
         float dx = pj.x - pi.x, dy = pj.y - pi.y;
         if (P.BC == 0) {
-            dx = sbc_min_image(dx, P);
-            dy = sbc_min_image(dy, P);
+            dx = sbc_delta_pbc(pi.x, pj.x, P);
+            dy = sbc_delta_pbc(pi.y, pj.y, P);
         }
         const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
         bool amb;

@@ -174,7 +174,7 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
                 const float4 p = pv[i];
                 if (p.x != p.x) continue;
                 float dx = p.x - p0.x, dy = p.y - p0.y;
-                if (P.BC == 0) { dx = sbc_min_image(dx, P); dy = sbc_min_image(dy, P); }
+                if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, p.x, P); dy = sbc_delta_pbc(p0.y, p.y, P); }
                 const float d2 = dx * dx + dy * dy;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)i;
                 best = min(best, key);
@@ -189,7 +189,7 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
             } else {
                 const float4 p = pv[(unsigned)(best & 0xffffffffu)];
                 float dx = p.x - p0.x, dy = p.y - p0.y;
-                if (P.BC == 0) { dx = sbc_min_image(dx, P); dy = sbc_min_image(dy, P); }
+                if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, p.x, P); dy = sbc_delta_pbc(p0.y, p.y, P); }
                 lphi = atan2f(dy, dx);
             }
         }

@@ -29,6 +29,10 @@ struct sbc_handle {
     uint32_t *inj_k_dev;
     unsigned long long host_stats[8];
     bool force_multikernel;
+    unsigned char *stage_raw;   // device staging of the ABI-layout arrays (state_io.cu)
+    StateStage stage;
+    double *part_dev;           // [R][N][7] rows of particle::out()
+    uint8_t *part_alive_dev;
 };
 
 static std::string g_create_error;
@@ -55,6 +59,7 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
     P.L = (float)p.sizeL;
     P.halfL = (float)(p.sizeL / 2);
     P.invL = (float)(1.0 / p.sizeL);
+    P.L_lo = (float)(p.sizeL - (double)(float)p.sizeL);
     P.dt = (float)p.dt;
     P.beta = (float)p.beta;
     P.alphaTurn = (float)p.alphaTurn;
@@ -65,13 +70,14 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
     P.att = (float)p.att_range;
     const double thr[3] = {p.rep_range, p.alg_range, p.att_range};
     // FP32 rounding band of the squared distance around each squared threshold: relative part
-    // from dx, dy, the products and the sum (<= 8 u), absolute part from the periodic fold
-    // (error of x_j - x_i up to u L, of the fold up to |L - (float)L|)
+    // from dx, dy, the products and the sum (<= 8 u, doubled for margin); the periodic fold is
+    // done on the far coordinate first (sbc_delta_pbc), which leaves only the rounding of the
+    // low word of a non-representable box length as an absolute term
     const double u = 1.0 / 16777216.0;
     for (int k = 0; k < 3; k++) {
         const double T = thr[k] * thr[k];
         double e_dx = 0;
-        if (p.BC == 0) e_dx = 2 * u * p.sizeL + std::fabs(p.sizeL - (double)(float)p.sizeL);
+        if (p.BC == 0) e_dx = u * std::fabs(p.sizeL - (double)(float)p.sizeL) + 1e-12 * p.sizeL;
         const double delta = 16 * u * T + 4 * thr[k] * e_dx + e_dx * e_dx;
         P.band_lo[k] = next_down((float)(T - delta));
         P.band_hi[k] = next_up((float)(T + delta));
@@ -172,6 +178,9 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->inj_dir_dev = nullptr;
     h->inj_k_dev = nullptr;
     h->force_multikernel = false;
+    h->stage_raw = nullptr;
+    h->part_dev = nullptr;
+    h->part_alive_dev = nullptr;
     std::memset(h->host_stats, 0, sizeof(h->host_stats));
     std::memset(&h->S, 0, sizeof(h->S));
     fill_dev_params(*p, seed, replicate_offset, h->P);
@@ -230,6 +239,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list); cudaFree(S.active_count);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
+    cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -251,67 +261,51 @@ int sbc_synchronize(sbc_handle *h) {
     return SBC_OK;
 }
 
+static int ensure_stage(sbc_handle *h) {
+    if (h->stage_raw) return SBC_OK;
+    const size_t total = (size_t)h->S.N * h->S.R;
+    const size_t bytes = total * (8 * sizeof(double) + 2 * sizeof(uint32_t) + 1) + 256;
+    SBC_CUDA(cudaMalloc(reinterpret_cast<void **>(&h->stage_raw), bytes));
+    unsigned char *q = h->stage_raw;
+    for (int k = 0; k < 8; k++) { h->stage.d[k] = reinterpret_cast<double *>(q); q += total * sizeof(double); }
+    for (int k = 0; k < 2; k++) { h->stage.u[k] = reinterpret_cast<uint32_t *>(q); q += total * sizeof(uint32_t); }
+    h->stage.al = q;
+    return SBC_OK;
+}
+
 int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
                   const double *vy, const double *phi, const double *vproj, const double *fx,
                   const double *fy, const uint32_t *bin_step, const uint32_t *stb,
                   const uint8_t *alive) {
     if (!h) return SBC_ERR_INVALID;
     SBC_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_stage(h)) return rc;
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
-    std::vector<float4> pv(total), pvd(total);
-    std::vector<float2> hv(total), fo(total);
-    std::vector<uint2> tm(total);
-    std::vector<uint8_t> al(total);
-    if (h->state_set) {  // NULL keeps the current value
-        SBC_CUDA(cudaStreamSynchronize(h->stream));
-        SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
-        SBC_CUDA(cudaMemcpy(pvd.data(), S.pv_dead, total * sizeof(float4), cudaMemcpyDeviceToHost));
-        SBC_CUDA(cudaMemcpy(hv.data(), S.hv, total * sizeof(float2), cudaMemcpyDeviceToHost));
-        SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
-        SBC_CUDA(cudaMemcpy(tm.data(), S.timers, total * sizeof(uint2), cudaMemcpyDeviceToHost));
-        SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
-        for (size_t g = 0; g < total; g++)
-            if (!al[g]) { pv[g].x = pvd[g].x; pv[g].y = pvd[g].y; }
-    } else {
-        for (size_t g = 0; g < total; g++) {
-            pv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-            hv[g] = make_float2(0.f, 1.f);
-            fo[g] = make_float2(0.f, 0.f);
-            tm[g] = make_uint2(0u, 0u);
-            al[g] = 1;
+    const double *dsrc[8] = {x, y, vx, vy, phi, vproj, fx, fy};
+    unsigned mask = 0;
+    for (int k = 0; k < 8; k++)
+        if (dsrc[k]) {
+            mask |= 1u << k;
+            SBC_CUDA(cudaMemcpyAsync(h->stage.d[k], dsrc[k], total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         }
+    if (bin_step) {
+        mask |= SBC_ST_BIN;
+        SBC_CUDA(cudaMemcpyAsync(h->stage.u[0], bin_step, total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    for (size_t g = 0; g < total; g++) {
-        if (x) pv[g].x = (float)x[g];
-        if (y) pv[g].y = (float)y[g];
-        if (phi) hv[g].x = (float)phi[g];
-        if (vproj) hv[g].y = (float)vproj[g];
-        if (vx) pv[g].z = (float)vx[g]; else if (phi) pv[g].z = hv[g].y * cosf(hv[g].x);
-        if (vy) pv[g].w = (float)vy[g]; else if (phi) pv[g].w = hv[g].y * sinf(hv[g].x);
-        if (fx) fo[g].x = (float)fx[g];
-        if (fy) fo[g].y = (float)fy[g];
-        if (bin_step) tm[g].x = bin_step[g];
-        if (stb) tm[g].y = stb[g];
-        if (alive) al[g] = alive[g] ? 1 : 0;
+    if (stb) {
+        mask |= SBC_ST_STB;
+        SBC_CUDA(cudaMemcpyAsync(h->stage.u[1], stb, total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     }
-    std::vector<int> nd(S.R, 0);
-    const float qnan = std::nanf("");
-    for (size_t g = 0; g < total; g++) {
-        pvd[g] = pv[g];
-        if (!al[g]) {
-            nd[g / S.N]++;
-            pv[g].x = qnan;
-            pv[g].y = qnan;
-        }
+    if (alive) {
+        mask |= SBC_ST_ALIVE;
+        SBC_CUDA(cudaMemcpyAsync(h->stage.al, alive, total, cudaMemcpyHostToDevice, h->stream));
     }
-    SBC_CUDA(cudaMemcpy(S.pv, pv.data(), total * sizeof(float4), cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.pv_dead, pvd.data(), total * sizeof(float4), cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.hv, hv.data(), total * sizeof(float2), cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.force, fo.data(), total * sizeof(float2), cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.timers, tm.data(), total * sizeof(uint2), cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.alive, al.data(), total, cudaMemcpyHostToDevice));
-    SBC_CUDA(cudaMemcpy(S.n_dead, nd.data(), S.R * sizeof(int), cudaMemcpyHostToDevice));
+    sbc_launch_pack_state(S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
+    h->host_stats[7]++;
+    // the caller's buffers may be reused as soon as we return
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaGetLastError());
     h->state_set = true;
     return SBC_OK;
 }
@@ -321,33 +315,24 @@ int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, d
                   uint8_t *alive) {
     if (!h) return SBC_ERR_INVALID;
     SBC_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_stage(h)) return rc;
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
+    double *ddst[8] = {x, y, vx, vy, phi, vproj, fx, fy};
+    unsigned mask = 0;
+    for (int k = 0; k < 8; k++) if (ddst[k]) mask |= 1u << k;
+    if (bin_step) mask |= SBC_ST_BIN;
+    if (stb) mask |= SBC_ST_STB;
+    if (alive) mask |= SBC_ST_ALIVE;
+    sbc_launch_unpack_state(S, h->stage, mask, h->stream);
+    h->host_stats[7]++;
+    for (int k = 0; k < 8; k++)
+        if (ddst[k]) SBC_CUDA(cudaMemcpyAsync(ddst[k], h->stage.d[k], total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (bin_step) SBC_CUDA(cudaMemcpyAsync(bin_step, h->stage.u[0], total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (stb) SBC_CUDA(cudaMemcpyAsync(stb, h->stage.u[1], total * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (alive) SBC_CUDA(cudaMemcpyAsync(alive, h->stage.al, total, cudaMemcpyDeviceToHost, h->stream));
     SBC_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<float4> pv(total), pvd(total);
-    std::vector<float2> hv(total), fo(total);
-    std::vector<uint2> tm(total);
-    std::vector<uint8_t> al(total);
-    SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(pvd.data(), S.pv_dead, total * sizeof(float4), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(hv.data(), S.hv, total * sizeof(float2), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(tm.data(), S.timers, total * sizeof(uint2), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
-    for (size_t g = 0; g < total; g++) {
-        const float4 p = al[g] ? pv[g] : pvd[g];
-        if (x) x[g] = p.x;
-        if (y) y[g] = p.y;
-        if (vx) vx[g] = p.z;
-        if (vy) vy[g] = p.w;
-        if (phi) phi[g] = hv[g].x;
-        if (vproj) vproj[g] = hv[g].y;
-        if (fx) fx[g] = fo[g].x;
-        if (fy) fy[g] = fo[g].y;
-        if (bin_step) bin_step[g] = tm[g].x;
-        if (stb) stb[g] = tm[g].y;
-        if (alive) alive[g] = al[g];
-    }
+    SBC_CUDA(cudaGetLastError());
     return SBC_OK;
 }
 
@@ -356,23 +341,16 @@ int sbc_get_particles(sbc_handle *h, double *out, uint8_t *alive) {
     SBC_CUDA(cudaSetDevice(h->device));
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
-    SBC_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<float4> pv(total);
-    std::vector<float2> fo(total);
-    std::vector<uint8_t> al(total);
-    SBC_CUDA(cudaMemcpy(pv.data(), S.pv, total * sizeof(float4), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(fo.data(), S.force, total * sizeof(float2), cudaMemcpyDeviceToHost));
-    SBC_CUDA(cudaMemcpy(al.data(), S.alive, total, cudaMemcpyDeviceToHost));
-    for (size_t g = 0; g < total; g++) {
-        double *o = out + g * 7;
-        if (al[g]) {
-            o[0] = pv[g].x; o[1] = pv[g].y; o[2] = pv[g].z; o[3] = pv[g].w;
-            o[4] = 0.0; o[5] = fo[g].x; o[6] = fo[g].y;
-        } else {
-            for (int k = 0; k < 7; k++) o[k] = 0.0;
-        }
-        if (alive) alive[g] = al[g];
+    if (!h->part_dev) {
+        SBC_CUDA(dev_alloc(&h->part_dev, total * 7));
+        SBC_CUDA(dev_alloc(&h->part_alive_dev, total));
     }
+    sbc_launch_particles(S, h->part_dev, h->part_alive_dev, h->stream);
+    h->host_stats[7]++;
+    SBC_CUDA(cudaMemcpyAsync(out, h->part_dev, total * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (alive) SBC_CUDA(cudaMemcpyAsync(alive, h->part_alive_dev, total, cudaMemcpyDeviceToHost, h->stream));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaGetLastError());
     return SBC_OK;
 }
 

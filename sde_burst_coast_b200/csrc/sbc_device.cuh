@@ -16,7 +16,7 @@
 // ---------------------------------------------------------------------------------------------
 struct DevParams {
     // geometry / dynamics (FP32 copies of sbc_params)
-    float L, halfL, invL;
+    float L, halfL, invL, L_lo;   // L_lo = sizeL - (double)(float)sizeL
     float dt, beta, alphaTurn;
     float soc, env;
     float rep, alg, att;           // ranges
@@ -109,13 +109,28 @@ __device__ __forceinline__ uint32_t sbc_geometric_k(const uint32_t *__restrict__
 // ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
-// minimum image of a raw difference with |r| < L (positions are kept in [0,L), so one fold is
-// enough); agrees with fmod(r + sgn(r) L/2, L) - sgn(r) L/2 (mathtools.h:64-71) away from the
-// |r| = L/2 tie, which lies outside att_range (asserted at sbc_create).
-__device__ __forceinline__ float sbc_min_image(float r, const DevParams &P) {
-    // round-to-nearest of r/L through the 1.5*2^23 magic constant: FADD/FFMA only, no FRND
-    const float n = __fadd_rn(__fmaf_rn(r, P.invL, 12582912.f), -12582912.f);
-    return __fmaf_rn(-P.L, n, r);
+// Minimum-image displacement x_j - x_i for positions kept in [0, L) by Boundary case 0, so one
+// fold is enough. Agrees with fmod(r + sgn(r) L/2, L) - sgn(r) L/2 (mathtools.h:64-71) away from
+// the |r| = L/2 tie, which lies outside att_range (asserted at sbc_create).
+//   rough  : r - L rint(r/L); error up to ulp(L) because x_j - x_i itself rounds when the pair
+//            straddles the box edge. Good enough to decide "far".
+//   precise: the coordinate on the far side of the edge is shifted by L first - exact by
+//            Sterbenz since it lies in [L/2, L) - so the final subtraction is of two nearby
+//            numbers and the result is correct to ulp(|dx|), like an unwrapped pair. The low
+//            word of a box length that is not FP32-representable is applied last.
+__device__ __forceinline__ float sbc_fold_count(float r, const DevParams &P) {
+    // round-to-nearest of r/L through the 1.5*2^23 magic constant: FFMA + FADD, no FRND
+    return __fadd_rn(__fmaf_rn(r, P.invL, 12582912.f), -12582912.f);
+}
+__device__ __forceinline__ float sbc_delta_pbc_rough(float xi, float xj, const DevParams &P) {
+    const float r = xj - xi;
+    return __fmaf_rn(-P.L, sbc_fold_count(r, P), r);
+}
+__device__ __forceinline__ float sbc_delta_pbc(float xi, float xj, const DevParams &P) {
+    const float n = sbc_fold_count(xj - xi, P);            // -1, 0 or +1
+    const float a = __fmaf_rn(-fmaxf(n, 0.f), P.L, xj);   // n = +1: x_j - L
+    const float b = __fmaf_rn(fminf(n, 0.f), P.L, xi);    // n = -1: x_i - L  (so a - b = r + L)
+    return __fmaf_rn(-n, P.L_lo, a - b);
 }
 
 // FP64 replay of CalcDistVec + vec_length + SFM_4Zone in the reference's operation order
@@ -154,8 +169,8 @@ __device__ __forceinline__ void sbc_pair_accumulate(RowAcc &acc, float xi, float
                                                     const DevParams &P, int &zone_out) {
     float dx = pj.x - xi, dy = pj.y - yi;
     if (P.BC == 0) {
-        dx = sbc_min_image(dx, P);
-        dy = sbc_min_image(dy, P);
+        dx = sbc_delta_pbc(xi, pj.x, P);
+        dy = sbc_delta_pbc(yi, pj.y, P);
     }
     const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
     bool amb;
@@ -175,8 +190,8 @@ __device__ __forceinline__ void sbc_detect_accumulate(RowAcc &acc, float xi, flo
                                                       const DevParams &P) {
     float dx = px - xi, dy = py - yi;
     if (P.BC == 0) {
-        dx = sbc_min_image(dx, P);
-        dy = sbc_min_image(dy, P);
+        dx = sbc_delta_pbc(xi, px, P);
+        dy = sbc_delta_pbc(yi, py, P);
     }
     const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
     const float d = sqrtf(d2);

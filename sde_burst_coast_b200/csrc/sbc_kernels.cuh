@@ -32,6 +32,20 @@ struct DevState {
     unsigned long long *stats; // [8] see sbc_get_stats
 };
 
+// --- host <-> device state conversion (state_io.cu) ------------------------------------------
+// staging area in device memory holding the caller's arrays in the ABI's own layout
+struct StateStage {
+    double *d[8];   // x y vx vy phi vproj fx fy
+    uint32_t *u[2]; // bin_step, steps_till_burst
+    uint8_t *al;
+};
+enum { SBC_ST_X = 1, SBC_ST_Y = 2, SBC_ST_VX = 4, SBC_ST_VY = 8, SBC_ST_PHI = 16, SBC_ST_VPROJ = 32,
+       SBC_ST_FX = 64, SBC_ST_FY = 128, SBC_ST_BIN = 256, SBC_ST_STB = 512, SBC_ST_ALIVE = 1024 };
+void sbc_launch_pack_state(const DevState &S, const StateStage &st, unsigned mask, int have_prev,
+                           cudaStream_t stream);
+void sbc_launch_unpack_state(const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
+void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
+
 // --- all-pairs three-zone pass (pair_allpairs.cu) ---------------------------------------------
 // rows: all alive rows (all_rows != 0) or rows with bin_step == burst_steps
 void sbc_launch_pair_allpairs(const DevParams &P, const DevState &S, int all_rows, cudaStream_t st);

@@ -86,8 +86,8 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             if (has && alive && lane != src) {  // pair (row src <- me)
                 float dx = a.x - xi, dy = a.y - yi;
                 if (P.BC == 0) {
-                    dx = sbc_min_image(dx, P);
-                    dy = sbc_min_image(dy, P);
+                    dx = sbc_delta_pbc(xi, a.x, P);
+                    dy = sbc_delta_pbc(yi, a.y, P);
                 }
                 const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
                 bool amb;
@@ -208,8 +208,8 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                         const float4 pj = pv_s[j];
                         float dx = pj.x - pi.x, dy = pj.y - pi.y;
                         if (P.BC == 0) {
-                            dx = sbc_min_image(dx, P);
-                            dy = sbc_min_image(dy, P);
+                            dx = sbc_delta_pbc(pi.x, pj.x, P);
+                            dy = sbc_delta_pbc(pi.y, pj.y, P);
                         }
                         const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
                         bool amb;

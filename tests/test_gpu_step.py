@@ -1,0 +1,199 @@
+"""GPU parity of the whole step (interaction + burst decision + burst-coast update + boundary) against
+the CPU oracle, through the C ABI.
+
+Stated tolerances (FP32 device vs FP64 oracle on FP32-representable states):
+  one step with identical decisions : |dx| <= 1e-5 max(1,|x|), |dvproj| <= 1e-5 max(1,vproj),
+                                      |dphi| <= 2e-5 rad (mod 2 pi), force within 1e-5 relative;
+  burst timers (bin_step, steps_till_burst) : bit-exact, for any number of steps;
+  branch decisions : identical except inside a documented guard band; mismatches are counted and
+                     bounded, never hidden.
+"""
+import numpy as np
+import pytest
+
+from helpers import make_params, random_state, ang_diff
+from oracle import pyorc
+
+pytestmark = pytest.mark.gpu
+
+TOL_X, TOL_V, TOL_PHI, TOL_F = 1e-5, 1e-5, 2e-5, 2e-5
+
+
+def _swarm(*a, **k):
+    from sde_burst_coast_b200.swarm import Swarm
+    return Swarm(*a, **k)
+
+
+def _close_state(o, g, sp, what=''):
+    """o: oracle state, g: GPU state (same shapes). Returns the mask of agents that agree."""
+    okx = (np.abs(o['x'] - g['x']) <= TOL_X * np.maximum(1, np.abs(o['x']))) & \
+          (np.abs(o['y'] - g['y']) <= TOL_X * np.maximum(1, np.abs(o['y'])))
+    okv = np.abs(o['vproj'] - g['vproj']) <= TOL_V * np.maximum(1, np.abs(o['vproj']))
+    okp = ang_diff(o['phi'], g['phi']) <= TOL_PHI
+    fmag = np.maximum(1.0, np.hypot(o['fx'], o['fy']))
+    okf = np.hypot(o['fx'] - g['fx'], o['fy'] - g['fy']) <= TOL_F * fmag
+    return okx & okv & okp & okf
+
+
+@pytest.mark.parametrize('mode,over,N', [
+    ('burst_coast', dict(BC=6), 8), ('burst_coast', dict(BC=6), 30), ('burst_coast', dict(BC=5), 64),
+    ('burst_coast', dict(BC=6, alg_range=10.0), 100), ('burst_coast', dict(BC=-1), 40),
+    ('natPred', dict(BC=0, size=100.0, Npred=0), 300),
+    ('natPred', dict(BC=0, size=100.0, Npred=0, alg_range=10.0), 1024),
+    ('natPred', dict(BC=0, size=200.0, Npred=0), 2000),
+    ('burst_coast', dict(BC=2, size=60.0), 50), ('burst_coast', dict(BC=3, size=60.0), 50),
+])
+@pytest.mark.parametrize('multikernel', [False, True])
+def test_one_step_injected(mode, over, N, multikernel):
+    sp, _, _ = make_params(mode, N, **over)
+    rng = np.random.default_rng(N * 3 + sp.BC + 100)
+    bad_total = 0
+    flag_mismatch = 0
+    trials = 6
+    for t in range(trials):
+        wide = sp.BC in (5, 6) and t % 2 == 1
+        st = random_state(N, sp, rng, spread=(0.97 * sp.sizeL if wide else (50.0 if sp.BC in (-1, 2, 3) else None)))
+        us, ud = rng.random(N), rng.random(N)
+        ud = np.asarray(ud, dtype=np.float32).astype(np.float64)
+        kn = rng.integers(1, 600, N).astype(np.uint32)
+        w = pyorc.World(sp, N)
+        w.set_state(**st)
+        w.inject(us, ud, kn)
+        fo = w.step(0, 1, want_flags=True)
+        o = w.get_state()
+        g = _swarm(sp, N)
+        if multikernel:
+            g.force_multikernel(True)
+        g.debug_flags(True)
+        g.set_state(**st)
+        g.inject(us, ud, kn)
+        g.step(0, 1)
+        gs = g.get_state()
+        fg = g.debug_flags(True, read=True)
+        assert np.array_equal(o['bin_step'], gs['bin_step'])
+        assert np.array_equal(o['steps_till_burst'], gs['steps_till_burst'])
+        ok = _close_state(o, gs, sp)
+        same_flags = (fo == fg)
+        # an agent may only disagree if one of its branch decisions flipped (guard band)
+        assert np.all(ok | ~same_flags), 'state differs although every branch agreed: %s' % np.where(~ok & same_flags)[0]
+        bad_total += int((~ok).sum())
+        flag_mismatch += int((~same_flags).sum())
+        g.close()
+        w.close()
+    # branch flips are rare events (ties within FP32 rounding of a threshold)
+    assert flag_mismatch <= max(1, trials * N // 200), (flag_mismatch, bad_total)
+
+
+@pytest.mark.parametrize('N,R', [(8, 64), (16, 32), (30, 16), (64, 8), (200, 3)])
+def test_timers_exact_over_many_steps(N, R):
+    """bin_step / steps_till_burst depend only on the Philox protocol: exact after 3000 steps."""
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(N)
+    sts = [random_state(N, sp, rng, mid_burst=False) for _ in range(R)]
+    g = _swarm(sp, N, n_replicates=R, seed=42, replicate_offset=5)
+    g.set_state(**{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    g.step(0, 3000)
+    gs = g.get_state()
+    for r in range(min(R, 4)):
+        w = pyorc.World(sp, N, seed=42, replicate=5 + r)
+        w.set_state(**sts[r])
+        w.step(0, 3000)
+        o = w.get_state()
+        assert np.array_equal(o['bin_step'], np.atleast_2d(gs['bin_step'])[r])
+        assert np.array_equal(o['steps_till_burst'], np.atleast_2d(gs['steps_till_burst'])[r])
+    assert np.all(np.isfinite(gs['x'])) and np.all(np.hypot(gs['x'], gs['y']) <= sp.sizeL * (1 + 1e-6))
+    g.close()
+
+
+def test_replicates_independent_of_sharding():
+    """Replicate r of an ensemble handle == a single-replicate handle created with
+    replicate_offset = r (bit-exact): results do not depend on how replicates are split over GPUs."""
+    N, R = 16, 12
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(77)
+    sts = [random_state(N, sp, rng) for _ in range(R)]
+    g = _swarm(sp, N, n_replicates=R, seed=9)
+    g.set_state(**{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    g.step(0, 500)
+    full = g.get_state()
+    g.close()
+    for r0, r1 in ((0, 5), (5, 12)):
+        h = _swarm(sp, N, n_replicates=r1 - r0, seed=9, replicate_offset=r0)
+        h.set_state(**{k: np.stack([s[k] for s in sts[r0:r1]]) for k in sts[0]})
+        h.step(0, 500)
+        part = h.get_state()
+        for k in full:
+            assert np.array_equal(full[k][r0:r1], part[k]), k
+        h.close()
+
+
+def test_split_launches_equal_one_launch():
+    """sbc_step(s, a) ; sbc_step(s+a, b) == sbc_step(s, a+b) bit-exactly (state lives in FP32 SoA)."""
+    N, R = 30, 4
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(1)
+    sts = [random_state(N, sp, rng) for _ in range(R)]
+    state = {k: np.stack([s[k] for s in sts]) for k in sts[0]}
+    a = _swarm(sp, N, n_replicates=R, seed=3)
+    b = _swarm(sp, N, n_replicates=R, seed=3)
+    a.set_state(**state)
+    b.set_state(**state)
+    a.step(0, 700)
+    for s in range(0, 700, 70):
+        b.step(s, 70)
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize('N', [30, 64, 300])
+def test_block_path_matches_multikernel_path(N):
+    """The one-block-per-swarm kernel and the pair-pass + update kernels are two schedules of the same
+    arithmetic: identical timers, states within the one-step tolerance for a short run."""
+    over = dict(BC=0, size=100.0, Npred=0) if N > 64 else dict(BC=6)
+    sp, _, _ = make_params('natPred' if N > 64 else 'burst_coast', N, **over)
+    rng = np.random.default_rng(N)
+    st = random_state(N, sp, rng)
+    a = _swarm(sp, N, seed=11)
+    b = _swarm(sp, N, seed=11)
+    b.force_multikernel(True)
+    a.set_state(**st)
+    b.set_state(**st)
+    a.step(0, 3)
+    b.step(0, 3)
+    sa, sb = a.get_state(), b.get_state()
+    assert np.array_equal(sa['bin_step'], sb['bin_step'])
+    assert np.array_equal(sa['steps_till_burst'], sb['steps_till_burst'])
+    ok = _close_state(sa, sb, sp)
+    assert ok.mean() >= 0.97, ok.mean()
+    assert a.stats()['block_launches'] == 1 and b.stats()['update_launches'] == 3
+    a.close()
+    b.close()
+
+
+def test_trajectory_divergence_reported():
+    """Many steps with the shared Philox decisions: report steps-to-divergence (chaotic once a
+    branch flips); the first 100 steps of a tank must still agree to 1e-3."""
+    N = 8
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(2)
+    st = random_state(N, sp, rng, mid_burst=False)
+    w = pyorc.World(sp, N, seed=21, replicate=0)
+    w.set_state(**st)
+    g = _swarm(sp, N, seed=21)
+    g.set_state(**st)
+    first_div = None
+    for s in range(0, 2000, 50):
+        w.step(s, 50)
+        g.step(s, 50)
+        o, gs = w.get_state(), g.get_state()
+        err = max(np.abs(o['x'] - gs['x']).max(), np.abs(o['y'] - gs['y']).max())
+        if first_div is None and err > 1e-3:
+            first_div = s + 50
+        assert np.array_equal(o['steps_till_burst'], gs['steps_till_burst'])
+    print('steps to 1e-3 divergence:', first_div)
+    assert first_div is None or first_div > 100
+    g.close()
+    w.close()
