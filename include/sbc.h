@@ -126,6 +126,7 @@ int sbc_observables(sbc_handle *h, double *out);
 
 #define SBC_PAIR_ACTIVE_ROWS 0 /* rows with bin_step == burst_steps (IntCalcPrey gate, :178) */
 #define SBC_PAIR_ALL_ROWS 1    /* every alive row (state at s=1) */
+#define SBC_PAIR_RESORT 2      /* sbc_bench_pair_pass: rebuild the Morton order inside every timed pass */
 
 /* Run the three-zone pair pass on the current state without advancing it. Outputs per agent
  * ([R][N]; any may be NULL): zone counters, accumulated force_rep/alg/att (x,y interleaved,

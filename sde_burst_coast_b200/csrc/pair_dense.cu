@@ -1,0 +1,387 @@
+// pair_dense.cu - the dense all-pairs three-zone pass: every alive row active (the reference's
+// state at s = 1), all N(N-1) directed pairs evaluated - the GPU counterpart of
+// InteractionGlobal -> IntCalcPrey -> SFM_4Zone (/root/reference/src/agents_interact.cpp:144-157,
+// 172-250; social_forces.cpp:25-52) and the kernel the FP32 roofline is quoted on.
+//
+// Design:
+//   1. agents are put in Morton order of their position (keys: morton_key_kernel, sort: CUB radix
+//      sort, gather: gather_sorted_kernel), so that the 64 rows of a warp are neighbours in space;
+//   2. grid = (row blocks of 256 rows) x (j splits) x (replicates); a block stages j-tiles of 256
+//      agents in shared memory, every thread owns two rows (ILP 2) and sweeps the tile with one
+//      broadcast LDS per j;
+//   3. per pair the distance is ALWAYS evaluated; the three-zone arithmetic (precise periodic fold,
+//      rounding-band check with FP64 re-decision, rsqrt, zone sums, counters) runs only behind a
+//      branch `min(d2_row0, d2_row1) <= far2`, which is warp-uniformly false for most j once rows
+//      are spatially sorted;
+//   4. periodic boxes: rows and tile are expressed relative to the block's first row (minimum
+//      image, computed once per j per block), so the inner loop needs no fold; blocks whose rows
+//      are not compact enough for that to be safe (unsorted input, tiny boxes) take a generic
+//      loop that folds every pair;
+//   5. partial sums of the j splits are combined in a fixed order by reduce_partials_kernel
+//      (deterministic results), which also scatters rows back to agent-id order and removes the
+//      self pair from c_rep.
+#include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "sbc_kernels.cuh"
+
+namespace {
+
+constexpr int DT = 128;          // threads per block
+constexpr int ROWS = 2 * DT;     // rows per block (two per thread)
+constexpr int TILE = 256;        // j per shared-memory tile
+
+struct Acc9 {
+    float rx, ry, ax, ay, tx, ty;
+    int cr, ca, ct;
+};
+
+__device__ __forceinline__ uint32_t part1by1(uint32_t v) {
+    v &= 0x0000ffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// ordered-int image of a float for atomicMin/atomicMax
+__device__ __forceinline__ int float_ordered(float f) {
+    const int i = __float_as_int(f);
+    return (i >= 0) ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float ordered_float(int i) {
+    return __int_as_float((i >= 0) ? i : (i ^ 0x7fffffff));
+}
+
+__global__ void bbox_init_kernel(int *bbox) {
+    bbox[0] = bbox[1] = 0x7fffffff;             // min x, min y
+    bbox[2] = bbox[3] = (int)0x80000000;        // max x, max y
+}
+__global__ void bbox_kernel(const float4 *__restrict__ pv, int n, int *bbox) {
+    float lo_x = INFINITY, lo_y = INFINITY, hi_x = -INFINITY, hi_y = -INFINITY;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 p = pv[i];
+        if (p.x != p.x) continue;
+        lo_x = fminf(lo_x, p.x); hi_x = fmaxf(hi_x, p.x);
+        lo_y = fminf(lo_y, p.y); hi_y = fmaxf(hi_y, p.y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo_x = fminf(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o));
+        lo_y = fminf(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o));
+        hi_x = fmaxf(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+        hi_y = fmaxf(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo_x <= hi_x) {
+        atomicMin(bbox + 0, float_ordered(lo_x));
+        atomicMin(bbox + 1, float_ordered(lo_y));
+        atomicMax(bbox + 2, float_ordered(hi_x));
+        atomicMax(bbox + 3, float_ordered(hi_y));
+    }
+}
+
+// 32-bit Morton key of the position quantised to 16 bits per axis; dead agents sort last
+__global__ void morton_key_kernel(const float4 *__restrict__ pv, int n, const int *__restrict__ bbox,
+                                  float fixed_lo, float fixed_hi, int use_bbox,
+                                  uint32_t *__restrict__ key, int *__restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float lo_x = fixed_lo, lo_y = fixed_lo, hi_x = fixed_hi, hi_y = fixed_hi;
+    if (use_bbox) {
+        lo_x = ordered_float(bbox[0]); lo_y = ordered_float(bbox[1]);
+        hi_x = ordered_float(bbox[2]); hi_y = ordered_float(bbox[3]);
+    }
+    const float4 p = pv[i];
+    uint32_t k = 0xffffffffu;
+    if (p.x == p.x) {
+        const float sx = 65535.f / fmaxf(hi_x - lo_x, 1e-20f), sy = 65535.f / fmaxf(hi_y - lo_y, 1e-20f);
+        const uint32_t qx = (uint32_t)fminf(fmaxf((p.x - lo_x) * sx, 0.f), 65535.f);
+        const uint32_t qy = (uint32_t)fminf(fmaxf((p.y - lo_y) * sy, 0.f), 65535.f);
+        k = part1by1(qx) | (part1by1(qy) << 1);
+        if (k == 0xffffffffu) k = 0xfffffffeu;
+    }
+    key[i] = k;
+    idx[i] = i;
+}
+
+__global__ void iota_kernel(int *idx, int n_per_rep, size_t total) {
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g < total) idx[g] = (int)(g % n_per_rep);
+}
+
+__global__ void gather_sorted_kernel(const float4 *__restrict__ pv, const int *__restrict__ idx,
+                                     int n_per_rep, size_t total, float4 *__restrict__ spv) {
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const size_t rep = g / n_per_rep;
+    spv[g] = pv[rep * n_per_rep + idx[g]];
+}
+
+// the three-zone arithmetic for one directed pair (row i <- j), precise displacement, branch-free
+// except for the rare rounding-band case (then the zone is re-decided in FP64)
+template <bool PERIODIC, bool HAS_ALG>
+__device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float xi, float yi,
+                                          const float4 pj, const DevParams &P) {
+    float dx, dy;
+    if (PERIODIC) {
+        dx = sbc_delta_pbc(xi, pj.x, P);
+        dy = sbc_delta_pbc(yi, pj.y, P);
+    } else {
+        dx = pj.x - xi;
+        dy = pj.y - yi;
+    }
+    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    // two compares per threshold: below the band / not above the band. Equal answers = the zone
+    // decision is safe in FP32; different answers = the pair sits in the rounding band.
+    const bool r_lo = d2 < P.band_lo[0], r_hi = d2 <= P.band_hi[0];
+    const bool t_lo = d2 < P.band_lo[2], t_hi = d2 <= P.band_hi[2];   // NaN (dead) -> all false
+    bool amb = (r_lo != r_hi) || (t_lo != t_hi);
+    bool in_rep = r_hi;
+    bool in_alg = false;
+    if (HAS_ALG) {
+        const bool a_lo = d2 < P.band_lo[1], a_hi = d2 <= P.band_hi[1];
+        amb = amb || (a_lo != a_hi);
+        in_alg = !in_rep && a_hi;
+    }
+    bool in_att = !in_rep && !in_alg && t_hi;
+    if (amb) {
+        const int z = sbc_zone_exact(xi, yi, pj.x, pj.y, P);
+        in_rep = (z == 0);
+        in_alg = (z == 1);
+        in_att = (z == 2);
+        n_amb++;
+    }
+    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));  // d = 0 -> dx = dy = 0 -> u = 0 (agents_interact.cpp:199)
+    const float wr = in_rep ? -rinv : 0.f;
+    const float wt = in_att ? rinv : 0.f;
+    A.rx = __fmaf_rn(dx, wr, A.rx);
+    A.ry = __fmaf_rn(dy, wr, A.ry);
+    A.tx = __fmaf_rn(dx, wt, A.tx);
+    A.ty = __fmaf_rn(dy, wt, A.ty);
+    A.cr += in_rep ? 1 : 0;
+    A.ct += in_att ? 1 : 0;
+    if (HAS_ALG) {
+        A.ax += in_alg ? pj.z : 0.f;
+        A.ay += in_alg ? pj.w : 0.f;
+        A.ca += in_alg ? 1 : 0;
+    }
+}
+
+template <bool PERIODIC, bool HAS_ALG>
+__global__ void __launch_bounds__(DT, 6)
+pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float4 *__restrict__ spv_all,
+                  int jchunk, int nsplit, float *__restrict__ part_f, int *__restrict__ part_i,
+                  unsigned long long *__restrict__ stats) {
+    __shared__ __align__(16) float2 tA[TILE];   // tile positions for the inner loop (block-relative if periodic)
+    __shared__ float4 tB[TILE];                 // tile agents as stored
+    __shared__ int s_ref;
+    const int rep = blockIdx.z, sp = blockIdx.y, rb = blockIdx.x;
+    const float4 *spv = spv_all + (size_t)rep * N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = rb * ROWS + warp * 64 + lane, row1 = row0 + 32;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float4 nan4 = make_float4(qnan, qnan, 0.f, 0.f);
+    const float4 p0 = (row0 < N) ? spv[row0] : nan4;
+    const float4 p1 = (row1 < N) ? spv[row1] : nan4;
+    // block reference point = the block's first alive row (dead agents sort last, but small or
+    // replicated swarms are processed in agent-id order)
+    if (threadIdx.x == 0) s_ref = 0x7fffffff;
+    __syncthreads();
+    if (p0.x == p0.x) atomicMin(&s_ref, row0);
+    if (p1.x == p1.x) atomicMin(&s_ref, row1);
+    __syncthreads();
+    const bool any_alive = (s_ref != 0x7fffffff);
+    const float4 c = any_alive ? spv[s_ref] : nan4;
+    Acc9 A0 = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, 0, 0}, A1 = A0;
+    unsigned n_amb = 0;
+    float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
+    int generic = 0;
+    if (PERIODIC) {
+        x0 = sbc_delta_pbc(c.x, p0.x, P); y0 = sbc_delta_pbc(c.y, p0.y, P);
+        x1 = sbc_delta_pbc(c.x, p1.x, P); y1 = sbc_delta_pbc(c.y, p1.y, P);
+        // block-relative coordinates are only safe while |x'_i| < L/2 - att (see header)
+        const float m = fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fmaxf(fabsf(x1), fabsf(y1)));
+        generic = __syncthreads_or(m > P.compact_lim);   // NaN rows compare false
+    }
+    const float far2 = P.far2;
+    if (any_alive) {
+        // tiles are dealt to the splits round-robin: a split's tiles are spread over the whole
+        // Morton curve, so every block sees about the same share of near pairs
+        const int j_end = N;
+        for (int j0 = sp * TILE; j0 < N; j0 += nsplit * TILE) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < TILE; t += DT) {
+                const int j = j0 + t;
+                const float4 pj = (j < j_end) ? spv[j] : nan4;
+                tB[t] = pj;
+                tA[t] = PERIODIC ? make_float2(sbc_delta_pbc(c.x, pj.x, P), sbc_delta_pbc(c.y, pj.y, P))
+                                 : make_float2(pj.x, pj.y);
+            }
+            __syncthreads();
+            if (!generic) {
+                const float4 *tA2 = reinterpret_cast<const float4 *>(tA);  // two j per LDS.128
+#pragma unroll 2
+                for (int jj = 0; jj < TILE / 2; jj++) {
+                    const float4 q = tA2[jj];
+                    const float ax0 = q.x - x0, ay0 = q.y - y0, ax1 = q.x - x1, ay1 = q.y - y1;
+                    const float bx0 = q.z - x0, by0 = q.w - y0, bx1 = q.z - x1, by1 = q.w - y1;
+                    const float da0 = __fmaf_rn(ay0, ay0, ax0 * ax0), da1 = __fmaf_rn(ay1, ay1, ax1 * ax1);
+                    const float db0 = __fmaf_rn(by0, by0, bx0 * bx0), db1 = __fmaf_rn(by1, by1, bx1 * bx1);
+                    const float ma = fminf(da0, da1), mb = fminf(db0, db1);
+                    if (fminf(ma, mb) <= far2) {  // NaN (dead or padding) never passes
+                        if (ma <= far2) {
+                            const float4 pj = tB[2 * jj];
+                            near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
+                            near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                        }
+                        if (mb <= far2) {
+                            const float4 pj = tB[2 * jj + 1];
+                            near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
+                            near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                        }
+                    }
+                }
+            } else {
+                const int n = min(TILE, j_end - j0);
+                for (int jj = 0; jj < n; jj++) {
+                    const float4 pj = tB[jj];
+                    near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
+                    near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                }
+            }
+        }
+    }
+    // partial sums: layout [k][rep][split][row] so that a warp's stores are contiguous
+    const size_t plane = (size_t)R * nsplit * N;
+    const size_t base = ((size_t)rep * nsplit + sp) * N;
+    if (row0 < N) {
+        float *f = part_f + base + row0;
+        f[0] = A0.rx; f[plane] = A0.ry; f[2 * plane] = A0.ax; f[3 * plane] = A0.ay;
+        f[4 * plane] = A0.tx; f[5 * plane] = A0.ty;
+        int *q = part_i + base + row0;
+        q[0] = A0.cr; q[plane] = A0.ca; q[2 * plane] = A0.ct;
+    }
+    if (row1 < N) {
+        float *f = part_f + base + row1;
+        f[0] = A1.rx; f[plane] = A1.ry; f[2 * plane] = A1.ax; f[3 * plane] = A1.ay;
+        f[4 * plane] = A1.tx; f[5 * plane] = A1.ty;
+        int *q = part_i + base + row1;
+        q[0] = A1.cr; q[plane] = A1.ca; q[2 * plane] = A1.ct;
+    }
+    n_amb = __reduce_add_sync(0xffffffffu, n_amb);
+    if (lane == 0 && n_amb) atomicAdd(stats + 4, (unsigned long long)n_amb);
+}
+
+// sum the j-split partials in split order, drop the self pair, scatter to agent-id order.
+// One thread per (plane, row): planes 0..5 are the zone sums, 6..8 the zone counts.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(DevState S, const float4 *__restrict__ spv, const int *__restrict__ idx,
+                       int nsplit, const float *__restrict__ part_f, const int *__restrict__ part_i) {
+    const int N = S.N, R = S.R;
+    const size_t total = (size_t)N * R;
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= total * 9) return;
+    const int k = (int)(t / total);
+    const size_t rr = t - (size_t)k * total;
+    const int rep = (int)(rr / N), row = (int)(rr - (size_t)rep * N);
+    const size_t plane = (size_t)R * nsplit * N;
+    const bool alive = (spv[rr].x == spv[rr].x);
+    const size_t g = (size_t)rep * N + idx[rr];
+    const size_t o = (size_t)rep * nsplit * N + row;
+    if (k < 6) {
+        const float *src = part_f + (size_t)k * plane + o;
+        float f = 0.f;
+        for (int sp = 0; sp < nsplit; sp++) f += src[(size_t)sp * N];
+        S.acc[g * 8 + k] = alive ? f : 0.f;
+    } else {
+        const int *src = part_i + (size_t)(k - 6) * plane + o;
+        int c = 0;
+        for (int sp = 0; sp < nsplit; sp++) c += src[(size_t)sp * N];
+        if (k == 6) c -= 1;  // the self pair (d = 0, zero force) was counted as repulsion
+        S.cnt[g * 4 + (k - 6)] = alive ? c : 0;
+    }
+}
+
+}  // namespace
+
+// ---- host side --------------------------------------------------------------------------------
+static void dense_plan(int N, int R, int &nsplit, int &jchunk) {
+    const int row_blocks = (N + ROWS - 1) / ROWS;
+    int waves = 4;
+    if (const char *e = getenv("SBC_DENSE_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 4;
+    const int target = 148 * 6 * waves;  // four waves at 6 resident blocks per SM: block run times differ
+                                     // by the share of near pairs, the block scheduler evens them out
+    int want = (target + row_blocks * R - 1) / (row_blocks * R);
+    const int max_split = (N + TILE - 1) / TILE;
+    if (want < 1) want = 1;
+    if (want > max_split) want = max_split;
+    jchunk = (N + want - 1) / want;
+    jchunk = ((jchunk + TILE - 1) / TILE) * TILE;
+    nsplit = (N + jchunk - 1) / jchunk;
+}
+
+cudaError_t sbc_dense_scratch_alloc(DenseScratch &D, int N, int R) {
+    const size_t total = (size_t)N * R;
+    int nsplit, jchunk;
+    dense_plan(N, R, nsplit, jchunk);
+    D.nsplit = nsplit;
+    D.jchunk = jchunk;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&D.key_in, total * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.key_out, total * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.idx_in, total * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.idx_out, total * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.spv, total * sizeof(float4))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.part_f, total * nsplit * 6 * sizeof(float))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.part_i, total * nsplit * 3 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.bbox, 4 * sizeof(int))) != cudaSuccess) return e;
+    D.cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, D.cub_bytes, D.key_in, D.key_out, D.idx_in, D.idx_out, N);
+    if ((e = cudaMalloc(&D.cub_tmp, D.cub_bytes ? D.cub_bytes : 16)) != cudaSuccess) return e;
+    D.sorted_valid = false;
+    return cudaSuccess;
+}
+
+void sbc_dense_scratch_free(DenseScratch &D) {
+    cudaFree(D.key_in); cudaFree(D.key_out); cudaFree(D.idx_in); cudaFree(D.idx_out);
+    cudaFree(D.spv); cudaFree(D.part_f); cudaFree(D.part_i); cudaFree(D.bbox); cudaFree(D.cub_tmp);
+    D = DenseScratch();
+}
+
+// (re)build the Morton order of the current positions; R > 1 keeps agent-id order
+void sbc_launch_dense_sort(const DevParams &P, const DevState &S, DenseScratch &D, cudaStream_t st) {
+    const int N = S.N;
+    const size_t total = (size_t)N * S.R;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (S.R == 1 && N > ROWS) {
+        float lo = 0.f, hi = P.L;
+        int use_bbox = 0;
+        if (P.BC == 5 || P.BC == 6) { lo = -P.L; hi = P.L; }
+        if (P.BC == -1) {
+            use_bbox = 1;
+            bbox_init_kernel<<<1, 1, 0, st>>>(D.bbox);
+            bbox_kernel<<<148, 256, 0, st>>>(S.pv, N, D.bbox);
+        }
+        morton_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, D.bbox, lo, hi, use_bbox, D.key_in, D.idx_in);
+        cub::DeviceRadixSort::SortPairs(D.cub_tmp, D.cub_bytes, D.key_in, D.key_out, D.idx_in, D.idx_out,
+                                        N, 0, 32, st);
+    } else {
+        iota_kernel<<<blocks, 256, 0, st>>>(D.idx_out, N, total);
+    }
+    D.sorted_valid = true;
+}
+
+// the pass itself: gather in the stored order, all pairs, combine
+void sbc_launch_pair_dense(const DevParams &P, const DevState &S, DenseScratch &D, cudaStream_t st) {
+    const int N = S.N;
+    const size_t total = (size_t)N * S.R;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    gather_sorted_kernel<<<blocks, 256, 0, st>>>(S.pv, D.idx_out, N, total, D.spv);
+    dim3 grid((N + ROWS - 1) / ROWS, D.nsplit, S.R);
+#define SBC_DENSE_LAUNCH(PER, ALG) pair_dense_kernel<PER, ALG><<<grid, DT, 0, st>>>( \
+        P, N, S.R, D.spv, D.jchunk, D.nsplit, D.part_f, D.part_i, S.stats)
+    if (P.BC == 0) { if (P.has_alg_zone) SBC_DENSE_LAUNCH(true, true); else SBC_DENSE_LAUNCH(true, false); }
+    else { if (P.has_alg_zone) SBC_DENSE_LAUNCH(false, true); else SBC_DENSE_LAUNCH(false, false); }
+#undef SBC_DENSE_LAUNCH
+    reduce_partials_kernel<<<(unsigned)((total * 9 + 255) / 256), 256, 0, st>>>(S, D.spv, D.idx_out, D.nsplit, D.part_f, D.part_i);
+}

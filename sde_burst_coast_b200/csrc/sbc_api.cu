@@ -31,6 +31,8 @@ struct sbc_handle {
     bool force_multikernel;
     unsigned char *stage_raw;   // device staging of the ABI-layout arrays (state_io.cu)
     StateStage stage;
+    DenseScratch dense;
+    bool dense_ready;
     double *part_dev;           // [R][N][7] rows of particle::out()
     uint8_t *part_alive_dev;
 };
@@ -81,6 +83,13 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
         const double delta = 16 * u * T + 4 * thr[k] * e_dx + e_dx * e_dx;
         P.band_lo[k] = next_down((float)(T - delta));
         P.band_hi[k] = next_up((float)(T + delta));
+    }
+    {   // dense pass (pair_dense.cu): conservative "far" threshold and compactness limit
+        const double e_abs = (p.BC == 0) ? 4 * u * p.sizeL : 0.0;
+        const double att_far = p.att_range + e_abs;
+        P.far2 = next_up((float)(att_far * att_far * (1 + 32 * u)));
+        if (P.far2 < P.band_hi[2]) P.far2 = P.band_hi[2];
+        P.compact_lim = (float)(p.sizeL / 2 - att_far - 1e-4 * p.sizeL);
     }
     P.rep2 = (float)(thr[0] * thr[0]);
     P.alg2 = (float)(thr[1] * thr[1]);
@@ -179,6 +188,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->inj_k_dev = nullptr;
     h->force_multikernel = false;
     h->stage_raw = nullptr;
+    h->dense_ready = false;
     h->part_dev = nullptr;
     h->part_alive_dev = nullptr;
     std::memset(h->host_stats, 0, sizeof(h->host_stats));
@@ -239,6 +249,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list); cudaFree(S.active_count);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
+    if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -258,6 +269,37 @@ int sbc_synchronize(sbc_handle *h) {
     if (!h) return SBC_ERR_INVALID;
     SBC_CUDA(cudaSetDevice(h->device));
     SBC_CUDA(cudaStreamSynchronize(h->stream));
+    return SBC_OK;
+}
+
+static int ensure_dense(sbc_handle *h) {
+    if (h->dense_ready) return SBC_OK;
+    cudaError_t e = sbc_dense_scratch_alloc(h->dense, h->S.N, h->S.R);
+    if (e != cudaSuccess) {
+        sbc_dense_scratch_free(h->dense);
+        return fail(h, SBC_ERR_NOMEM, std::string("dense pass scratch: ") + cudaGetErrorString(e));
+    }
+    h->dense_ready = true;
+    return SBC_OK;
+}
+
+// one three-zone pass over the current state: dense (all rows) or burst-gated rows
+static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort) {
+    if (all_rows) {
+        if (int rc = ensure_dense(h)) return rc;
+        if (resort || !h->dense.sorted_valid) {
+            sbc_launch_dense_sort(h->P, h->S, h->dense, h->stream);
+            h->host_stats[7] += 3;
+        }
+        sbc_launch_pair_dense(h->P, h->S, h->dense, h->stream);
+        h->host_stats[0]++;
+        h->host_stats[7] += 2;
+        h->host_stats[3] += (unsigned long long)h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
+    } else {
+        sbc_launch_pair_rows(h->P, h->S, h->stream);
+        h->host_stats[0]++;
+        h->host_stats[7] += 2;
+    }
     return SBC_OK;
 }
 
@@ -302,6 +344,7 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
         SBC_CUDA(cudaMemcpyAsync(h->stage.al, alive, total, cudaMemcpyHostToDevice, h->stream));
     }
     sbc_launch_pack_state(S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
+    h->dense.sorted_valid = false;
     h->host_stats[7]++;
     // the caller's buffers may be reused as soon as we return
     SBC_CUDA(cudaStreamSynchronize(h->stream));
@@ -444,9 +487,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     h->host_stats[7]++;
                 }
             }
-            sbc_launch_pair_allpairs(h->P, S, 0, h->stream);
-            h->host_stats[0]++;
-            h->host_stats[7] += 2;
+            if (int rc = launch_pair_pass(h, 0, false)) return rc;
             sbc_launch_update(h->P, S, s, pred_phase ? 1 : 0, h->stream);
             h->host_stats[1]++;
             if (pred_phase) {
@@ -481,10 +522,8 @@ int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_a
     SBC_CUDA(cudaSetDevice(h->device));
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
-    const int all_rows = (flags == SBC_PAIR_ALL_ROWS);
-    sbc_launch_pair_allpairs(h->P, S, all_rows, h->stream);
-    h->host_stats[0]++;
-    if (all_rows) h->host_stats[3] += (unsigned long long)S.R * S.N * (unsigned long long)(S.N - 1);
+    const int all_rows = (flags & SBC_PAIR_ALL_ROWS) != 0;
+    if (int rc = launch_pair_pass(h, all_rows, true)) return rc;
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     SBC_CUDA(cudaGetLastError());
     std::vector<float> acc(total * 8);
@@ -518,7 +557,7 @@ int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_a
             sbc_launch_nn_fill(h->P, S, all_rows, ptr_dev, idx_dev, h->stream);
             h->host_stats[7]++;
             SBC_CUDA(cudaStreamSynchronize(h->stream));
-            SBC_CUDA(cudaMemcpy(nn_idx, idx_dev, (size_t)run * sizeof(int), cudaMemcpyDeviceToHost));
+            if (run > 0) SBC_CUDA(cudaMemcpy(nn_idx, idx_dev, (size_t)run * sizeof(int), cudaMemcpyDeviceToHost));
             cudaFree(ptr_dev);
             cudaFree(idx_dev);
         }
@@ -624,19 +663,18 @@ int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms) {
     cudaEvent_t e0, e1;
     SBC_CUDA(cudaEventCreate(&e0));
     SBC_CUDA(cudaEventCreate(&e1));
-    const int all_rows = (flags == SBC_PAIR_ALL_ROWS);
-    sbc_launch_pair_allpairs(h->P, h->S, all_rows, h->stream);  // warm-up
+    const int all_rows = (flags & SBC_PAIR_ALL_ROWS) != 0;
+    const bool resort = (flags & SBC_PAIR_RESORT) != 0;
+    if (int rc = launch_pair_pass(h, all_rows, true)) return rc;  // warm-up, builds the Morton order
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     SBC_CUDA(cudaEventRecord(e0, h->stream));
-    for (int k = 0; k < iters; k++) sbc_launch_pair_allpairs(h->P, h->S, all_rows, h->stream);
+    for (int k = 0; k < iters; k++)
+        if (int rc = launch_pair_pass(h, all_rows, resort)) return rc;
     SBC_CUDA(cudaEventRecord(e1, h->stream));
     SBC_CUDA(cudaEventSynchronize(e1));
     float t = 0.f;
     SBC_CUDA(cudaEventElapsedTime(&t, e0, e1));
     *ms = t / (float)iters;
-    h->host_stats[0] += (unsigned long long)iters + 1;
-    if (all_rows)
-        h->host_stats[3] += (unsigned long long)(iters + 1) * h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     SBC_CUDA(cudaGetLastError());

@@ -22,6 +22,8 @@ struct DevParams {
     float rep, alg, att;           // ranges
     float rep2, alg2, att2;        // squared thresholds for the fast compare
     float band_lo[3], band_hi[3];  // d2 inside [lo,hi] of any threshold => FP64 re-check
+    float far2;                    // dense pass: d2 above this is certainly outside att_range
+    float compact_lim;             // dense pass, periodic: max |block-relative coordinate| of a row
     float flee_range, inv_flee_range;
     float pred_speed, kill_range, kill_rate, noisep;
     float wall_margin_r;           // sizeL - 2 (agents_dynamics.cpp:111)
@@ -41,6 +43,7 @@ struct DevParams {
 struct AgentState {
     float x, y, vx, vy;
     float phi, vproj;
+    float cu, su;   // cached (cos, sin)(phi), carried in the state so that launches can be split anywhere
     float fx, fy;
     uint32_t bin_step, stb;
 };
@@ -404,17 +407,33 @@ __device__ __forceinline__ bool sbc_boundary(float &x, float &y, float &vx, floa
 //   acc       : accumulators of this row (only read when the agent starts a burst)
 //   u_social, u_dir, k_next : this agent-step's decisions (Philox or injected)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void sbc_agent_step(AgentState &a, float &cu, float &su,
-                                               const RowAcc &acc, double u_social, float u_dir,
+// (cos d, sin d) for |d| < 0.25 by Taylor polynomials (truncation error < 2e-11, i.e. below FP32
+// rounding); used to turn the cached heading vector instead of calling sincosf every step
+__device__ __forceinline__ void sbc_sincos_small(float d, float &s, float &c) {
+    const float d2 = d * d;
+    float ps = __fmaf_rn(d2, -1.f / 5040.f, 1.f / 120.f);
+    ps = __fmaf_rn(d2, ps, -1.f / 6.f);
+    s = __fmaf_rn(d * d2, ps, d);
+    float pc = __fmaf_rn(d2, 1.f / 40320.f, -1.f / 720.f);
+    pc = __fmaf_rn(d2, pc, 1.f / 24.f);
+    pc = __fmaf_rn(d2, pc, -0.5f);
+    c = __fmaf_rn(d2, pc, 1.f);
+}
+
+__device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc, double u_social, float u_dir,
                                                uint32_t k_next, const DevParams &P, uint32_t &fl) {
-    // (cu, su) = (cos, sin)(a.phi) on entry and on exit: the reference recomputes u from phi at
-    // every step (:197,:227-228); caching it lets a coasting agent (force = 0, heading unchanged)
-    // skip every transcendental.
+    float &cu = a.cu, &su = a.su;
+    // (cu, su) = (cos, sin)(a.phi) on entry and on exit. The reference recomputes u from phi at
+    // every step (:197,:227-228); here the cached vector is turned by the step's small heading
+    // change (exact identity for a coasting agent, whose force is zero) and re-derived from phi
+    // with sincosf at every burst start and at every rare event (wrap, wall hit, clamp), so the
+    // drift is bounded by one burst (< 100 turns of ~1 ulp each).
     const bool first = (a.bin_step == P.burst_steps);
     const bool bursting = (a.bin_step > 0);
     float fx, fy, force_mag = P.soc;
     if (first) {
         fl |= SBC_FL_BURST_START;
+        sincosf(a.phi, &su, &cu);
         sbc_decide(a, acc, u_social, u_dir, P, fx, fy, force_mag, fl);
         a.fx = fx;
         a.fy = fy;
@@ -431,64 +450,71 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, float &cu, float &
     const float vproj_old = a.vproj;
     const float forcev = fx * cu + fy * su;
     float vproj = vproj_old + (-P.beta * vproj_old + forcev) * P.dt;  // :202
-    const bool coast = (fx == 0.f) && (fy == 0.f) && (vproj >= 0.f) &&
-                       (fabsf(a.phi) < SBC_TWO_PI_F);
-    if (!coast) {
-        float lphi = a.phi;
-        float sl = su, cl = cu;
-        if (vproj < 0.f) {  // :206-210
-            fl |= SBC_FL_VPROJ_HACK;
-            vproj = 0.001f;
-            lphi += 0.5f * SBC_PI_F;
-            sincosf(lphi, &sl, &cl);
-        }
-        const float forcep = -fx * sl + fy * cl;
-        lphi += P.alphaTurn * forcep * P.dt / vproj_old;  // :215 (old vproj)
-        float sn, cn;
-        sincosf(lphi, &sn, &cn);
-        const float dphi = fabsf(lphi - a.phi);
-        if (dphi > 0.01f) {
-            // overshoot_check :123-137. acos is monotone decreasing, so the three angles are
-            // compared through their cosines; an argument outside [-1,1] is NaN in the
-            // reference (every comparison false) - reproduced by the `ok` predicates, with a
-            // rounding allowance of 1e-6 so that |cos| = 1 + ulp is not mistaken for it.
-            const float inv = 1.f / force_mag;
-            const float c0 = (cu * fx + su * fy) * inv;  // cos(angle(u_old, F))
-            const float c1 = (cn * fx + sn * fy) * inv;  // cos(angle(u_new, F))
-            const float c01 = cn * cu + sn * su;         // cos(angle(u_new, u_old))
-            const bool ok0 = fabsf(c0) <= 1.000001f, ok1 = fabsf(c1) <= 1.000001f;
-            const bool o1 = ok0 && ok1 && (c0 > c1);
-            const bool o2 = !o1 && ok0 && (c01 < c0);
-            const bool o3 = dphi > SBC_PI_F;
-            if (o1 || o2 || o3) {
-                fl |= SBC_FL_OVERSHOOT;
-                lphi = atan2f(fy, fx);
-                sincosf(lphi, &sn, &cn);
-            }
-        }
-        const float wrapped = fmodf(lphi, SBC_TWO_PI_F);  // :226 (sign kept)
-        if (wrapped != lphi) sincosf(wrapped, &sn, &cn);
-        a.phi = wrapped;
-        cu = cn;
-        su = sn;
+    float lphi = a.phi;
+    float sl = su, cl = cu;
+    const bool hack = vproj < 0.f;
+    if (hack) {  // :206-210
+        fl |= SBC_FL_VPROJ_HACK;
+        vproj = 0.001f;
+        lphi += 0.5f * SBC_PI_F;
+        sincosf(lphi, &sl, &cl);
     }
+    const float forcep = -fx * sl + fy * cl;
+    const float turn = __fdividef(P.alphaTurn * forcep * P.dt, vproj_old);  // :215 (old vproj)
+    lphi += turn;
+    float sn, cn;
+    if (!hack && fabsf(turn) < 0.25f) {
+        float sd, cd;
+        sbc_sincos_small(turn, sd, cd);
+        cn = __fmaf_rn(cu, cd, -su * sd);
+        sn = __fmaf_rn(su, cd, cu * sd);
+    } else {
+        sincosf(lphi, &sn, &cn);
+    }
+    const float dphi = fabsf(lphi - a.phi);
+    if (dphi > 0.01f) {
+        // overshoot_check :123-137. acos is monotone decreasing, so the three angles are compared
+        // through their cosines; an argument outside [-1,1] is NaN in the reference (every
+        // comparison false) - reproduced by the `ok` predicates, with a rounding allowance of
+        // 1e-6 so that |cos| = 1 + ulp is not mistaken for it.
+        const float inv = 1.f / force_mag;
+        const float c0 = (cu * fx + su * fy) * inv;  // cos(angle(u_old, F))
+        const float c1 = (cn * fx + sn * fy) * inv;  // cos(angle(u_new, F))
+        const float c01 = cn * cu + sn * su;         // cos(angle(u_new, u_old))
+        const bool ok0 = fabsf(c0) <= 1.000001f, ok1 = fabsf(c1) <= 1.000001f;
+        const bool o1 = ok0 && ok1 && (c0 > c1);
+        const bool o2 = !o1 && ok0 && (c01 < c0);
+        const bool o3 = dphi > SBC_PI_F;
+        if (o1 || o2 || o3) {
+            fl |= SBC_FL_OVERSHOOT;
+            lphi = atan2f(fy, fx);
+            sincosf(lphi, &sn, &cn);
+        }
+    }
+    if (!(fabsf(lphi) < SBC_TWO_PI_F)) {  // :226 fmod keeps the sign; identity below 2 pi
+        lphi = fmodf(lphi, SBC_TWO_PI_F);
+        sincosf(lphi, &sn, &cn);
+    }
+    a.phi = lphi;
+    cu = cn;
+    su = sn;
     a.vproj = vproj;
     a.vx = vproj * cu;
     a.vy = vproj * su;
     a.x += a.vx * P.dt;
     a.y += a.vy * P.dt;
+    bool hit = false;
     if (P.BC != -1) {  // :247
-        if (sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P)) {
-            fl |= SBC_FL_BOUNDARY;
-            sincosf(a.phi, &su, &cu);
-        }
+        hit = sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P);
+        if (hit) fl |= SBC_FL_BOUNDARY;
     }
     if (a.stb == 0) {  // :250-270
         fl |= SBC_FL_REARM;
         a.bin_step = P.burst_steps;
         a.stb = k_next;
     }
-    if (P.BC != -1) {  // :272
-        if (sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P)) sincosf(a.phi, &su, &cu);
+    if (hit) {  // :272 - the second Boundary call can only act when the first one did
+        sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P);
+        sincosf(a.phi, &su, &cu);
     }
 }

@@ -7,7 +7,7 @@ struct DevState {
     int N, R, Npred;
     float4 *pv;        // {x, y, vx, vy}; x = y = NaN for dead agents (their last pv is in pv_dead)
     float4 *pv_dead;   // last {x,y,vx,vy} of killed agents
-    float2 *hv;        // {phi, vproj}
+    float4 *hv;        // {phi, vproj, cos phi, sin phi}
     float2 *force;     // {fx, fy}
     uint2 *timers;     // {bin_step, steps_till_burst}
     uint8_t *alive;
@@ -46,9 +46,26 @@ void sbc_launch_pack_state(const DevState &S, const StateStage &st, unsigned mas
 void sbc_launch_unpack_state(const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
 
-// --- all-pairs three-zone pass (pair_allpairs.cu) ---------------------------------------------
-// rows: all alive rows (all_rows != 0) or rows with bin_step == burst_steps
-void sbc_launch_pair_allpairs(const DevParams &P, const DevState &S, int all_rows, cudaStream_t st);
+// --- all-pairs three-zone pass -------------------------------------------------------------------
+// burst-gated rows (bin_step == burst_steps), pair_allpairs.cu
+void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st);
+// dense pass (every alive row), pair_dense.cu: Morton order + tiled all pairs + split combine
+struct DenseScratch {
+    uint32_t *key_in = nullptr, *key_out = nullptr;
+    int *idx_in = nullptr, *idx_out = nullptr;   // idx_out[r] = agent id of sorted row r
+    float4 *spv = nullptr;                        // agents in sorted order
+    float *part_f = nullptr;                      // [6][R][nsplit][N] partial zone sums
+    int *part_i = nullptr;                        // [3][R][nsplit][N] partial zone counts
+    int *bbox = nullptr;
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int nsplit = 0, jchunk = 0;
+    bool sorted_valid = false;
+};
+cudaError_t sbc_dense_scratch_alloc(DenseScratch &D, int N, int R);
+void sbc_dense_scratch_free(DenseScratch &D);
+void sbc_launch_dense_sort(const DevParams &P, const DevState &S, DenseScratch &D, cudaStream_t st);
+void sbc_launch_pair_dense(const DevParams &P, const DevState &S, DenseScratch &D, cudaStream_t st);
 // test hook: CSR neighbour lists (ascending j) for the same row set
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,
                         int *nn_idx, cudaStream_t st);

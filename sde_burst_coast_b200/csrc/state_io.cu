@@ -12,7 +12,7 @@ pack_state_kernel(DevState S, StateStage st, unsigned mask, int have_prev) {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= total) return;
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 hv = make_float2(0.f, 1.f);  // InitSystem: phi = 0, vproj = 1 (settings.cpp:168-193)
+    float4 hv = make_float4(0.f, 1.f, 1.f, 0.f);  // InitSystem: phi = 0, vproj = 1 (settings.cpp:168-193)
     float2 fo = make_float2(0.f, 0.f);
     uint2 tm = make_uint2(0u, 0u);
     uint8_t al = 1;
@@ -25,12 +25,15 @@ pack_state_kernel(DevState S, StateStage st, unsigned mask, int have_prev) {
     }
     if (mask & SBC_ST_X) pv.x = (float)st.d[0][g];
     if (mask & SBC_ST_Y) pv.y = (float)st.d[1][g];
-    if (mask & SBC_ST_PHI) hv.x = (float)st.d[4][g];
+    if (mask & SBC_ST_PHI) {
+        hv.x = (float)st.d[4][g];
+        sincosf(hv.x, &hv.w, &hv.z);
+    }
     if (mask & SBC_ST_VPROJ) hv.y = (float)st.d[5][g];
     if (mask & SBC_ST_VX) pv.z = (float)st.d[2][g];
-    else if (mask & SBC_ST_PHI) pv.z = hv.y * cosf(hv.x);  // v = vproj u(phi), settings.cpp:374-377
+    else if (mask & SBC_ST_PHI) pv.z = hv.y * hv.z;  // v = vproj u(phi), settings.cpp:374-377
     if (mask & SBC_ST_VY) pv.w = (float)st.d[3][g];
-    else if (mask & SBC_ST_PHI) pv.w = hv.y * sinf(hv.x);
+    else if (mask & SBC_ST_PHI) pv.w = hv.y * hv.w;
     if (mask & SBC_ST_FX) fo.x = (float)st.d[6][g];
     if (mask & SBC_ST_FY) fo.y = (float)st.d[7][g];
     if (mask & SBC_ST_BIN) tm.x = st.u[0][g];
@@ -57,7 +60,7 @@ unpack_state_kernel(DevState S, StateStage st, unsigned mask) {
     if (g >= total) return;
     const uint8_t al = S.alive[g];
     const float4 pv = al ? S.pv[g] : S.pv_dead[g];
-    const float2 hv = S.hv[g];
+    const float4 hv = S.hv[g];
     const float2 fo = S.force[g];
     const uint2 tm = S.timers[g];
     if (mask & SBC_ST_X) st.d[0][g] = pv.x;

@@ -20,17 +20,17 @@ namespace {
 
 __device__ __forceinline__ void load_agent(const DevState &S, size_t g, AgentState &a) {
     const float4 p = S.pv[g];
-    const float2 h = S.hv[g];
+    const float4 h = S.hv[g];
     const float2 f = S.force[g];
     const uint2 t = S.timers[g];
     a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-    a.phi = h.x; a.vproj = h.y;
+    a.phi = h.x; a.vproj = h.y; a.cu = h.z; a.su = h.w;
     a.fx = f.x; a.fy = f.y;
     a.bin_step = t.x; a.stb = t.y;
 }
 __device__ __forceinline__ void store_agent(const DevState &S, size_t g, const AgentState &a) {
     S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
-    S.hv[g] = make_float2(a.phi, a.vproj);
+    S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
     S.force[g] = make_float2(a.fx, a.fy);
     S.timers[g] = make_uint2(a.bin_step, a.stb);
 }
@@ -66,8 +66,6 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
         load_agent(S, g, a);
         alive = S.alive[g] != 0;
     }
-    float cu = 1.f, su = 0.f;
-    sincosf(a.phi, &su, &cu);
     uint32_t flags_acc = 0;
     unsigned long long n_amb = 0, n_pairs = 0;
 
@@ -133,7 +131,7 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             const bool rearm = a.stb <= 1;
             if (first || rearm) draw_decisions(P, S, g, rep, t, s, rearm, u_social, u_dir, k_next);
             uint32_t fl = 0;
-            sbc_agent_step(a, cu, su, acc, u_social, u_dir, k_next, P, fl);
+            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
             flags_acc |= fl;
         }
     }
@@ -177,8 +175,6 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
         load_agent(S, g, a);
         alive = S.alive[g] != 0;
     }
-    float cu = 1.f, su = 0.f;
-    sincosf(a.phi, &su, &cu);
     uint32_t flags_acc = 0;
     unsigned long long n_amb = 0, n_pairs = 0;
     const float qnan = __int_as_float(0x7fc00000);
@@ -260,7 +256,7 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
             const bool rearm = a.stb <= 1;
             if (first || rearm) draw_decisions(P, S, g, rep, t, s, rearm, u_social, u_dir, k_next);
             uint32_t fl = 0;
-            sbc_agent_step(a, cu, su, acc, u_social, u_dir, k_next, P, fl);
+            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
             flags_acc |= fl;
         }
     }

@@ -4,8 +4,8 @@
 // burst while a predator is present - by the prey<-predator detection of IntCalcPred
 // (agents_interact.cpp:252-292; only rows that read the result evaluate it).
 //
-// One thread per agent, coalesced SoA traffic: 40 B read + 40 B written per agent-step
-// (pv float4, hv float2, force float2, timers uint2) -> HBM-bound.
+// One thread per agent, coalesced SoA traffic: 48 B read + 48 B written per agent-step
+// (pv float4, hv float4, force float2, timers uint2) -> HBM-bound.
 #include "sbc_kernels.cuh"
 
 namespace {
@@ -21,11 +21,11 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, in
     AgentState a;
     {
         const float4 p = S.pv[g];
-        const float2 h = S.hv[g];
+        const float4 h = S.hv[g];
         const float2 f = S.force[g];
         const uint2 t = S.timers[g];
         a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-        a.phi = h.x; a.vproj = h.y;
+        a.phi = h.x; a.vproj = h.y; a.cu = h.z; a.su = h.w;
         a.fx = f.x; a.fy = f.y;
         a.bin_step = t.x; a.stb = t.y;
     }
@@ -66,11 +66,9 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, in
         }
     }
     uint32_t fl = 0;
-    float cu, su;
-    sincosf(a.phi, &su, &cu);
-    sbc_agent_step(a, cu, su, acc, u_social, u_dir, k_next, P, fl);
+    sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
     S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
-    S.hv[g] = make_float2(a.phi, a.vproj);
+    S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
     S.force[g] = make_float2(a.fx, a.fy);
     S.timers[g] = make_uint2(a.bin_step, a.stb);
     if (S.flags) S.flags[g] |= (uint8_t)fl;
