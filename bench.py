@@ -184,7 +184,7 @@ def main():
     ap.add_argument('--tanks', type=int, default=16384, help='tanks per GPU')
     ap.add_argument('--agents', type=int, default=32, help='agents per tank')
     ap.add_argument('--chunk', type=int, default=1000, help='time steps per bench step')
-    ap.add_argument('--pair-n', type=int, default=16384, help='swarm size of the dense pair-kernel measurement')
+    ap.add_argument('--pair-n', type=int, default=65536, help='swarm size of the dense pair-kernel measurement')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
 
@@ -334,31 +334,45 @@ def main():
 
 
 def pair_kernel_roofline(n, device, peak_fp32):
-    """Dense state (every row active, the reference state at s = 1): N(N-1) directed pairs/launch."""
+    """Dense state (every row active, the reference state at s = 1): N(N-1) directed pairs/launch.
+    Timed by sbc_bench_pair_pass with CUDA events on the handle's stream (gather + all-pairs kernel +
+    split combine; the Hilbert sort of the positions is timed separately as `with_sort`). Cases:
+    the probe density of SURVEY section 6 (N=16384 in L=100: ~1960 neighbours inside att_range) in an
+    open and a periodic domain, and the sparse density of config C4 (rho = 0.01: ~12 neighbours)."""
     from helpers import make_params, f32
     from sde_burst_coast_b200.swarm import Swarm
     from sde_burst_coast_b200.params import PAIR_ALL_ROWS
-    res = {}
-    for name, mode, over, flop in (('open', 'burst_coast', dict(BC=-1), FLOP_PER_PAIR_OPEN),
-                                   ('periodic', 'natPred', dict(BC=0, size=100.0, Npred=0), FLOP_PER_PAIR_PERIODIC)):
-        sp, _, _ = make_params(mode, n, **over)
+    res = {'bound': 'fp32', 'kernel': 'pair_dense_kernel', 'unit': 'TFLOP/s', 'peak': peak_fp32, 'cases': []}
+    cases = [('open, dense', n, 'burst_coast', dict(BC=-1), 1.6384, FLOP_PER_PAIR_OPEN),
+             ('periodic, dense', n, 'natPred', dict(BC=0, Npred=0), 1.6384, FLOP_PER_PAIR_PERIODIC),
+             ('periodic, sparse (C4 density)', n, 'natPred', dict(BC=0, Npred=0), 0.01, FLOP_PER_PAIR_PERIODIC),
+             ('open, dense', 16384, 'burst_coast', dict(BC=-1), 1.6384, FLOP_PER_PAIR_OPEN)]
+    for name, nn, mode, over, rho, flop in cases:
+        L = float(np.sqrt(nn / rho))
+        if over.get('BC') == 0:
+            over = dict(over, size=L)
+        sp, _, _ = make_params(mode, nn, **over)
         rng = np.random.default_rng(SEED)
-        L = 100.0
-        st = dict(x=f32(L * rng.random(n)), y=f32(L * rng.random(n)), phi=f32(2 * np.pi * rng.random(n)),
-                  vproj=np.ones(n))
-        g = Swarm(sp, n, device=device)
+        st = dict(x=f32(L * rng.random(nn)), y=f32(L * rng.random(nn)), phi=f32(2 * np.pi * rng.random(nn)),
+                  vproj=np.ones(nn))
+        g = Swarm(sp, nn, device=device)
         g.set_state(**st)
-        ms = g.bench_pair_pass(PAIR_ALL_ROWS, iters=20)
+        ms = g.bench_pair_pass(PAIR_ALL_ROWS, iters=10)
+        ms_sort = g.bench_pair_pass(PAIR_ALL_ROWS | 2, iters=10)
         stats = g.stats()
         g.close()
-        pairs = n * (n - 1)
+        pairs = nn * (nn - 1)
         ach = pairs * flop / (ms * 1e-3) / 1e12
-        res[name] = {'n_agents': n, 'pairs_per_launch': pairs, 'ms_per_launch': ms,
-                     'pairs_per_sec': pairs / (ms * 1e-3), 'flop_per_pair': flop, 'achieved': ach,
-                     'peak': peak_fp32, 'unit': 'TFLOP/s', 'frac': ach / peak_fp32,
-                     'ambiguous_pairs_rechecked': stats['ambiguous_pairs']}
-    res['bound'] = 'fp32'
-    res['kernel'] = 'pair_dense_kernel'
+        res['cases'].append({'case': name, 'n_agents': nn, 'box': L, 'pairs_per_launch': pairs, 'ms_per_launch': ms,
+                             'ms_per_launch_with_sort': ms_sort, 'pairs_per_sec': pairs / (ms * 1e-3),
+                             'flop_per_pair': flop, 'achieved': ach, 'frac': ach / peak_fp32,
+                             'frac_at_13_flop': pairs * 13 / (ms * 1e-3) / 1e12 / peak_fp32,
+                             'ambiguous_pairs_rechecked_per_launch': stats['ambiguous_pairs'] // 22})
+    # headline of this object: the open-domain dense case at the requested N
+    res.update({k: res['cases'][0][k] for k in ('n_agents', 'pairs_per_sec', 'achieved', 'frac', 'ms_per_launch')})
+    res['note'] = ('every directed pair has its distance evaluated; the zone arithmetic runs only for pairs that '
+                   'pass d2 <= att2 (warp-uniform early-out on Hilbert-sorted rows), so sparse states and the '
+                   'periodic 21-FLOP convention can read above 1.0; frac_at_13_flop is the conservative figure')
     return res
 
 

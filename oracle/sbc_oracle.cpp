@@ -865,6 +865,11 @@ int64_t orc_pair_interactions(orc_world *w, int flags, int32_t *c_rep, int32_t *
         total += (int64_t)a.nn.size();
     }
     if (nn_ptr) nn_ptr[w->N] = total;
+    for (Agent &a : w->a) {  // leave the accumulators as a fresh step expects them (:238-245)
+        a.f_rep[0] = a.f_rep[1] = a.f_alg[0] = a.f_alg[1] = a.f_att[0] = a.f_att[1] = 0;
+        a.c_rep = a.c_alg = a.c_att = 0;
+        a.nn.clear();
+    }
     return total;
 }
 

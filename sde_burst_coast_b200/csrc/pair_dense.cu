@@ -4,7 +4,7 @@
 // 172-250; social_forces.cpp:25-52) and the kernel the FP32 roofline is quoted on.
 //
 // Design:
-//   1. agents are put in Morton order of their position (keys: morton_key_kernel, sort: CUB radix
+//   1. agents are put in Hilbert-curve order of their position (keys: curve_key_kernel, sort: CUB radix
 //      sort, gather: gather_sorted_kernel), so that the 64 rows of a warp are neighbours in space;
 //   2. grid = (row blocks of 256 rows) x (j splits) x (replicates); a block stages j-tiles of 256
 //      agents in shared memory, every thread owns two rows (ILP 2) and sweeps the tile with one
@@ -36,13 +36,21 @@ struct Acc9 {
     int cr, ca, ct;
 };
 
-__device__ __forceinline__ uint32_t part1by1(uint32_t v) {
-    v &= 0x0000ffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
+// index of cell (x, y) of a 65536 x 65536 grid along the Hilbert curve. Unlike the Morton order the
+// Hilbert curve has no jumps: any run of consecutive agents is a compact blob, which is what the
+// warp-uniform early-out and the block-relative periodic coordinates rely on.
+__device__ __forceinline__ uint32_t hilbert_key(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+#pragma unroll
+    for (uint32_t s = 32768u; s > 0; s >>= 1) {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) { x = 65535u - x; y = 65535u - y; }
+            const uint32_t t = x; x = y; y = t;
+        }
+    }
+    return d;
 }
 
 // ordered-int image of a float for atomicMin/atomicMax
@@ -80,8 +88,8 @@ __global__ void bbox_kernel(const float4 *__restrict__ pv, int n, int *bbox) {
     }
 }
 
-// 32-bit Morton key of the position quantised to 16 bits per axis; dead agents sort last
-__global__ void morton_key_kernel(const float4 *__restrict__ pv, int n, const int *__restrict__ bbox,
+// 32-bit Hilbert key of the position quantised to 16 bits per axis; dead agents sort last
+__global__ void curve_key_kernel(const float4 *__restrict__ pv, int n, const int *__restrict__ bbox,
                                   float fixed_lo, float fixed_hi, int use_bbox,
                                   uint32_t *__restrict__ key, int *__restrict__ idx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -97,7 +105,7 @@ __global__ void morton_key_kernel(const float4 *__restrict__ pv, int n, const in
         const float sx = 65535.f / fmaxf(hi_x - lo_x, 1e-20f), sy = 65535.f / fmaxf(hi_y - lo_y, 1e-20f);
         const uint32_t qx = (uint32_t)fminf(fmaxf((p.x - lo_x) * sx, 0.f), 65535.f);
         const uint32_t qy = (uint32_t)fminf(fmaxf((p.y - lo_y) * sy, 0.f), 65535.f);
-        k = part1by1(qx) | (part1by1(qy) << 1);
+        k = hilbert_key(qx, qy);
         if (k == 0xffffffffu) k = 0xfffffffeu;
     }
     key[i] = k;
@@ -117,20 +125,28 @@ __global__ void gather_sorted_kernel(const float4 *__restrict__ pv, const int *_
     spv[g] = pv[rep * n_per_rep + idx[g]];
 }
 
-// the three-zone arithmetic for one directed pair (row i <- j), precise displacement, branch-free
-// except for the rare rounding-band case (then the zone is re-decided in FP64)
-template <bool PERIODIC, bool HAS_ALG>
-__device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float xi, float yi,
-                                          const float4 pj, const DevParams &P) {
-    float dx, dy;
-    if (PERIODIC) {
-        dx = sbc_delta_pbc(xi, pj.x, P);
-        dy = sbc_delta_pbc(yi, pj.y, P);
-    } else {
-        dx = pj.x - xi;
-        dy = pj.y - yi;
-    }
-    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+// x_j - x_i folded to the minimum image as a two-float (hi + lo): hi is what sbc_delta_pbc returns,
+// lo the exact rounding residual of its last subtraction (TwoSum) plus the low word of the box
+// length. The dense kernel expresses rows and tile relative to a block reference this way, so that
+// (hi_j - hi_i) + (lo_j - lo_i) is the pair displacement to ulp accuracy without a per-pair fold.
+__device__ __forceinline__ float sbc_delta_pbc2(float xi, float xj, const DevParams &P, float &lo) {
+    const float n = sbc_fold_count(xj - xi, P);
+    const float a = __fmaf_rn(-fmaxf(n, 0.f), P.L, xj);
+    const float b = __fmaf_rn(fminf(n, 0.f), P.L, xi);
+    const float hi = __fsub_rn(a, b);
+    const float bv = __fsub_rn(hi, a);            // TwoSum(a, -b)
+    const float av = __fsub_rn(hi, bv);
+    const float err = __fadd_rn(__fsub_rn(a, av), __fsub_rn(-b, bv));
+    lo = __fmaf_rn(-n, P.L_lo, err);
+    return hi;
+}
+
+// the three-zone arithmetic for one directed pair (row i <- j) given its displacement; branch-free
+// except for the rare rounding-band case (then the zone is re-decided in FP64 from the stored
+// coordinates). xi, yi: the row's stored position; pjp: the tile entry of j as stored.
+template <bool HAS_ALG>
+__device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float dx, float dy, float d2,
+                                          float xi, float yi, const float4 *pjp, const DevParams &P) {
     // two compares per threshold: below the band / not above the band. Equal answers = the zone
     // decision is safe in FP32; different answers = the pair sits in the rounding band.
     const bool r_lo = d2 < P.band_lo[0], r_hi = d2 <= P.band_hi[0];
@@ -145,6 +161,7 @@ __device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float xi, fl
     }
     bool in_att = !in_rep && !in_alg && t_hi;
     if (amb) {
+        const float4 pj = *pjp;
         const int z = sbc_zone_exact(xi, yi, pj.x, pj.y, P);
         in_rep = (z == 0);
         in_alg = (z == 1);
@@ -161,6 +178,7 @@ __device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float xi, fl
     A.cr += in_rep ? 1 : 0;
     A.ct += in_att ? 1 : 0;
     if (HAS_ALG) {
+        const float4 pj = *pjp;
         A.ax += in_alg ? pj.z : 0.f;
         A.ay += in_alg ? pj.w : 0.f;
         A.ca += in_alg ? 1 : 0;
@@ -170,9 +188,10 @@ __device__ __forceinline__ void near_pair(Acc9 &A, unsigned &n_amb, float xi, fl
 template <bool PERIODIC, bool HAS_ALG>
 __global__ void __launch_bounds__(DT, 6)
 pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float4 *__restrict__ spv_all,
-                  int jchunk, int nsplit, float *__restrict__ part_f, int *__restrict__ part_i,
+                  int nsplit, float *__restrict__ part_f, int *__restrict__ part_i,
                   unsigned long long *__restrict__ stats) {
-    __shared__ __align__(16) float2 tA[TILE];   // tile positions for the inner loop (block-relative if periodic)
+    __shared__ __align__(16) float2 tA[TILE];   // tile positions for the far test (block-relative hi part if periodic)
+    __shared__ __align__(16) float2 tL[TILE];   // periodic: lo parts of the block-relative tile positions
     __shared__ float4 tB[TILE];                 // tile agents as stored
     __shared__ int s_ref;
     const int rep = blockIdx.z, sp = blockIdx.y, rb = blockIdx.x;
@@ -195,10 +214,11 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
     Acc9 A0 = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, 0, 0}, A1 = A0;
     unsigned n_amb = 0;
     float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
+    float l0x = 0.f, l0y = 0.f, l1x = 0.f, l1y = 0.f;
     int generic = 0;
     if (PERIODIC) {
-        x0 = sbc_delta_pbc(c.x, p0.x, P); y0 = sbc_delta_pbc(c.y, p0.y, P);
-        x1 = sbc_delta_pbc(c.x, p1.x, P); y1 = sbc_delta_pbc(c.y, p1.y, P);
+        x0 = sbc_delta_pbc2(c.x, p0.x, P, l0x); y0 = sbc_delta_pbc2(c.y, p0.y, P, l0y);
+        x1 = sbc_delta_pbc2(c.x, p1.x, P, l1x); y1 = sbc_delta_pbc2(c.y, p1.y, P, l1y);
         // block-relative coordinates are only safe while |x'_i| < L/2 - att (see header)
         const float m = fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fmaxf(fabsf(x1), fabsf(y1)));
         generic = __syncthreads_or(m > P.compact_lim);   // NaN rows compare false
@@ -206,16 +226,21 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
     const float far2 = P.far2;
     if (any_alive) {
         // tiles are dealt to the splits round-robin: a split's tiles are spread over the whole
-        // Morton curve, so every block sees about the same share of near pairs
-        const int j_end = N;
+        // curve, so every block sees about the same share of near pairs
         for (int j0 = sp * TILE; j0 < N; j0 += nsplit * TILE) {
             __syncthreads();
             for (int t = threadIdx.x; t < TILE; t += DT) {
                 const int j = j0 + t;
-                const float4 pj = (j < j_end) ? spv[j] : nan4;
+                const float4 pj = (j < N) ? spv[j] : nan4;
                 tB[t] = pj;
-                tA[t] = PERIODIC ? make_float2(sbc_delta_pbc(c.x, pj.x, P), sbc_delta_pbc(c.y, pj.y, P))
-                                 : make_float2(pj.x, pj.y);
+                if (PERIODIC) {
+                    float lx, ly;
+                    const float hx = sbc_delta_pbc2(c.x, pj.x, P, lx), hy = sbc_delta_pbc2(c.y, pj.y, P, ly);
+                    tA[t] = make_float2(hx, hy);
+                    tL[t] = make_float2(lx, ly);
+                } else {
+                    tA[t] = make_float2(pj.x, pj.y);
+                }
             }
             __syncthreads();
             if (!generic) {
@@ -225,28 +250,54 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
                     const float4 q = tA2[jj];
                     const float ax0 = q.x - x0, ay0 = q.y - y0, ax1 = q.x - x1, ay1 = q.y - y1;
                     const float bx0 = q.z - x0, by0 = q.w - y0, bx1 = q.z - x1, by1 = q.w - y1;
-                    const float da0 = __fmaf_rn(ay0, ay0, ax0 * ax0), da1 = __fmaf_rn(ay1, ay1, ax1 * ax1);
-                    const float db0 = __fmaf_rn(by0, by0, bx0 * bx0), db1 = __fmaf_rn(by1, by1, bx1 * bx1);
+                    const float da0 = __fmaf_rn(ay0, ay0, __fmul_rn(ax0, ax0)), da1 = __fmaf_rn(ay1, ay1, __fmul_rn(ax1, ax1));
+                    const float db0 = __fmaf_rn(by0, by0, __fmul_rn(bx0, bx0)), db1 = __fmaf_rn(by1, by1, __fmul_rn(bx1, bx1));
                     const float ma = fminf(da0, da1), mb = fminf(db0, db1);
                     if (fminf(ma, mb) <= far2) {  // NaN (dead or padding) never passes
                         if (ma <= far2) {
-                            const float4 pj = tB[2 * jj];
-                            near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
-                            near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                            const float4 *pjp = &tB[2 * jj];
+                            if (PERIODIC) {
+                                const float2 l = tL[2 * jj];
+                                const float dx0 = ax0 + (l.x - l0x), dy0 = ay0 + (l.y - l0y);
+                                const float dx1 = ax1 + (l.x - l1x), dy1 = ay1 + (l.y - l1y);
+                                near_pair<HAS_ALG>(A0, n_amb, dx0, dy0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)), p0.x, p0.y, pjp, P);
+                                near_pair<HAS_ALG>(A1, n_amb, dx1, dy1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)), p1.x, p1.y, pjp, P);
+                            } else {
+                                near_pair<HAS_ALG>(A0, n_amb, ax0, ay0, da0, p0.x, p0.y, pjp, P);
+                                near_pair<HAS_ALG>(A1, n_amb, ax1, ay1, da1, p1.x, p1.y, pjp, P);
+                            }
                         }
                         if (mb <= far2) {
-                            const float4 pj = tB[2 * jj + 1];
-                            near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
-                            near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                            const float4 *pjp = &tB[2 * jj + 1];
+                            if (PERIODIC) {
+                                const float2 l = tL[2 * jj + 1];
+                                const float dx0 = bx0 + (l.x - l0x), dy0 = by0 + (l.y - l0y);
+                                const float dx1 = bx1 + (l.x - l1x), dy1 = by1 + (l.y - l1y);
+                                near_pair<HAS_ALG>(A0, n_amb, dx0, dy0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)), p0.x, p0.y, pjp, P);
+                                near_pair<HAS_ALG>(A1, n_amb, dx1, dy1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)), p1.x, p1.y, pjp, P);
+                            } else {
+                                near_pair<HAS_ALG>(A0, n_amb, bx0, by0, db0, p0.x, p0.y, pjp, P);
+                                near_pair<HAS_ALG>(A1, n_amb, bx1, by1, db1, p1.x, p1.y, pjp, P);
+                            }
                         }
                     }
                 }
             } else {
-                const int n = min(TILE, j_end - j0);
+                // rows of this block are too spread out for block-relative coordinates (unsorted
+                // input or a box barely larger than 2 att_range): fold every pair, rough first
+                const int n = min(TILE, N - j0);
                 for (int jj = 0; jj < n; jj++) {
-                    const float4 pj = tB[jj];
-                    near_pair<PERIODIC, HAS_ALG>(A0, n_amb, p0.x, p0.y, pj, P);
-                    near_pair<PERIODIC, HAS_ALG>(A1, n_amb, p1.x, p1.y, pj, P);
+                    const float4 *pjp = &tB[jj];
+                    const float4 pj = *pjp;
+                    const float rx0 = sbc_delta_pbc_rough(p0.x, pj.x, P), ry0 = sbc_delta_pbc_rough(p0.y, pj.y, P);
+                    const float rx1 = sbc_delta_pbc_rough(p1.x, pj.x, P), ry1 = sbc_delta_pbc_rough(p1.y, pj.y, P);
+                    const float d0 = __fmaf_rn(ry0, ry0, rx0 * rx0), d1 = __fmaf_rn(ry1, ry1, rx1 * rx1);
+                    if (fminf(d0, d1) <= far2) {
+                        const float dx0 = sbc_delta_pbc(p0.x, pj.x, P), dy0 = sbc_delta_pbc(p0.y, pj.y, P);
+                        const float dx1 = sbc_delta_pbc(p1.x, pj.x, P), dy1 = sbc_delta_pbc(p1.y, pj.y, P);
+                        near_pair<HAS_ALG>(A0, n_amb, dx0, dy0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)), p0.x, p0.y, pjp, P);
+                        near_pair<HAS_ALG>(A1, n_amb, dx1, dy1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)), p1.x, p1.y, pjp, P);
+                    }
                 }
             }
         }
@@ -307,8 +358,8 @@ reduce_partials_kernel(DevState S, const float4 *__restrict__ spv, const int *__
 // ---- host side --------------------------------------------------------------------------------
 static void dense_plan(int N, int R, int &nsplit, int &jchunk) {
     const int row_blocks = (N + ROWS - 1) / ROWS;
-    int waves = 4;
-    if (const char *e = getenv("SBC_DENSE_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 4;
+    int waves = 8;
+    if (const char *e = getenv("SBC_DENSE_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 8;
     const int target = 148 * 6 * waves;  // four waves at 6 resident blocks per SM: block run times differ
                                      // by the share of near pairs, the block scheduler evens them out
     int want = (target + row_blocks * R - 1) / (row_blocks * R);
@@ -362,7 +413,7 @@ void sbc_launch_dense_sort(const DevParams &P, const DevState &S, DenseScratch &
             bbox_init_kernel<<<1, 1, 0, st>>>(D.bbox);
             bbox_kernel<<<148, 256, 0, st>>>(S.pv, N, D.bbox);
         }
-        morton_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, D.bbox, lo, hi, use_bbox, D.key_in, D.idx_in);
+        curve_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, D.bbox, lo, hi, use_bbox, D.key_in, D.idx_in);
         cub::DeviceRadixSort::SortPairs(D.cub_tmp, D.cub_bytes, D.key_in, D.key_out, D.idx_in, D.idx_out,
                                         N, 0, 32, st);
     } else {
@@ -379,7 +430,7 @@ void sbc_launch_pair_dense(const DevParams &P, const DevState &S, DenseScratch &
     gather_sorted_kernel<<<blocks, 256, 0, st>>>(S.pv, D.idx_out, N, total, D.spv);
     dim3 grid((N + ROWS - 1) / ROWS, D.nsplit, S.R);
 #define SBC_DENSE_LAUNCH(PER, ALG) pair_dense_kernel<PER, ALG><<<grid, DT, 0, st>>>( \
-        P, N, S.R, D.spv, D.jchunk, D.nsplit, D.part_f, D.part_i, S.stats)
+        P, N, S.R, D.spv, D.nsplit, D.part_f, D.part_i, S.stats)
     if (P.BC == 0) { if (P.has_alg_zone) SBC_DENSE_LAUNCH(true, true); else SBC_DENSE_LAUNCH(true, false); }
     else { if (P.has_alg_zone) SBC_DENSE_LAUNCH(false, true); else SBC_DENSE_LAUNCH(false, false); }
 #undef SBC_DENSE_LAUNCH

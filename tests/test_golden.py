@@ -1,0 +1,73 @@
+"""The CPU restatement (oracle 'port') against golden vectors produced by the reference's own
+translation units (tests/golden/make_golden.py, run where /root/reference is mounted). These
+fixtures keep the oracle pinned on machines where the reference sources are absent."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import make_params
+from oracle import pyorc
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'oracle_vectors.npz'))
+CASES = {'tank8': ('burst_coast', dict(BC=6), 8), 'tank30_alg': ('burst_coast', dict(BC=6, alg_range=10.0), 30),
+         'tank5_64': ('burst_coast', dict(BC=5), 64), 'open40': ('burst_coast', dict(BC=-1), 40),
+         'periodic200': ('natPred', dict(BC=0, size=100.0, Npred=0, alg_range=10.0), 200)}
+STATE = ('x', 'y', 'vx', 'vy', 'phi', 'vproj', 'fx', 'fy', 'bin_step', 'steps_till_burst')
+
+
+def _state(name):
+    return {k: G['%s/state/%s' % (name, k)] for k in STATE}
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_port_reproduces_reference_vectors(name):
+    mode, over, N = CASES[name]
+    sp, _, _ = make_params(mode, N, **over)
+    w = pyorc.World(sp, N, seed=77, replicate=2, kind='port')
+    w.set_state(**_state(name))
+    for flags in (0, 1):
+        res = w.pair_interactions(flags)
+        for k, v in res.items():
+            assert np.array_equal(v, G['%s/pair%d/%s' % (name, flags, k)]), (flags, k)
+    w.inject(G[name + '/inj/us'], G[name + '/inj/ud'], G[name + '/inj/kn'])
+    w.step(0, 1)
+    for k, v in w.get_state().items():
+        assert np.array_equal(v, G['%s/step1/%s' % (name, k)], equal_nan=True), ('step1', k)
+    w.step(1, 199)
+    for k, v in w.get_state().items():
+        assert np.array_equal(v, G['%s/step200/%s' % (name, k)], equal_nan=True), ('step200', k)
+    w.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_gpu_against_reference_vectors(name):
+    """The CUDA path against the same committed vectors: integers exact, one step within tolerance."""
+    from sde_burst_coast_b200.swarm import Swarm
+    from helpers import ang_diff
+    mode, over, N = CASES[name]
+    sp, _, _ = make_params(mode, N, **over)
+    g = Swarm(sp, N, seed=77, replicate_offset=2)
+    g.set_state(**_state(name))
+    for flags in (0, 1):
+        res = g.pair_interactions(flags)
+        for k in ('c_rep', 'c_alg', 'c_att', 'nn_ptr', 'nn_idx'):
+            assert np.array_equal(res[k], G['%s/pair%d/%s' % (name, flags, k)]), (flags, k)
+        for k in ('f_rep', 'f_alg', 'f_att'):
+            ref = G['%s/pair%d/%s' % (name, flags, k)]
+            assert np.allclose(res[k], ref, rtol=1e-5, atol=2e-5), (flags, k)
+    g.inject(G[name + '/inj/us'], G[name + '/inj/ud'], G[name + '/inj/kn'])
+    g.step(0, 1)
+    s = g.get_state()
+    ref = {k: G['%s/step1/%s' % (name, k)] for k in s}
+    assert np.array_equal(s['bin_step'], ref['bin_step']) and np.array_equal(s['steps_till_burst'], ref['steps_till_burst'])
+    ok = (np.abs(s['x'] - ref['x']) <= 1e-5 * np.maximum(1, np.abs(ref['x']))) & \
+         (np.abs(s['y'] - ref['y']) <= 1e-5 * np.maximum(1, np.abs(ref['y']))) & \
+         (np.abs(s['vproj'] - ref['vproj']) <= 1e-5 * np.maximum(1, ref['vproj'])) & (ang_diff(s['phi'], ref['phi']) <= 2e-5)
+    assert ok.mean() >= 0.97, 'more than a guard-band share of agents differ: %s' % np.where(~ok)[0]
+    g.step(1, 199)
+    s = g.get_state()
+    assert np.array_equal(s['steps_till_burst'], G['%s/step200/steps_till_burst' % name])
+    assert np.array_equal(s['bin_step'], G['%s/step200/bin_step' % name])
+    g.close()

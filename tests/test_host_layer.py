@@ -1,0 +1,123 @@
+"""Host-side layers on the CPU: the parameter presets / command builder against the reference's
+SwarmDynByPy (golden fixture), the host executable's argv parsing + parameter derivation against the
+reference main()'s parameters.dat (golden fixture), the C-ABI symbol table, Philox known answers."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from sde_burst_coast_b200 import params as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CMDS = [c for c in json.load(open(os.path.join(HERE, 'golden', 'swarmdyn_commands.json'))) if 'command' in c]
+EXE = os.path.join(ROOT, 'sde_burst_coast_b200', 'host', 'swarmdyn')
+
+
+@pytest.mark.parametrize('case', CMDS, ids=lambda c: '%s_SL%d' % (c['mode'], c['SL']))
+def test_presets_and_command_match_reference(case):
+    d = P.get_base_params(20, 20, mode=case['mode'])
+    P.selection_line_parameter(d, case['SL'])
+    assert d == case['dic']
+    assert P.dic2swarmdyn_command(d) == case['command']
+
+
+def test_unknown_mode_and_negative_time_rejected():
+    with pytest.raises(AssertionError):
+        P.get_base_params(1, 1, mode='nonsense')
+    d = P.get_base_params(1, 1, mode='burst_coast')
+    d['time'] = -1
+    with pytest.raises(AssertionError):
+        P.dic2swarmdyn_command(d)
+
+
+@pytest.fixture(scope='module')
+def exe():
+    if not os.path.exists(EXE):
+        subprocess.run(['make', '-C', os.path.dirname(EXE)], check=True)
+    return EXE
+
+
+@pytest.mark.parametrize('case', CMDS[::3] + CMDS[2::3], ids=lambda c: '%s_SL%d' % (c['mode'], c['SL']))
+def test_executable_parameters_dat_matches_reference_main(case, exe, tmp_path):
+    """Same argv -> byte-identical parameters.dat (input_output.cpp:161-201 after the derivations of
+    settings.cpp:79-145). Without a GPU the run then stops loudly at sbc_create: there is no CPU path."""
+    argv = case['short_command'].split()
+    argv[0] = exe
+    r = subprocess.run(argv, cwd=tmp_path, capture_output=True, text=True)
+    got = open(tmp_path / 'parameters.dat').read()
+    want = open(os.path.join(HERE, 'golden', 'parameters', '%s_SL%d.dat' % (case['mode'], case['SL']))).read()
+    assert got == want
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 2 and 'no usable CUDA device' in r.stderr and 'no CPU fallback' in r.stderr
+
+
+def test_missing_flags_parse_as_zero(exe, tmp_path):
+    """getCmdOption returns "0" for an absent flag (input_output.cpp:108-114)."""
+    subprocess.run([exe, '-N', '4', '-l', './', '-d', '0.01', '-t', '1'], cwd=tmp_path, capture_output=True)
+    txt = open(tmp_path / 'parameters.dat').read()
+    assert re.search(r'particles:\s+4\b', txt) and re.search(r'BC:\s+0\b', txt) and re.search(r'beta:\s+0\b', txt)
+
+
+def test_abi_exports_every_declared_symbol():
+    """Every function include/sbc.h declares is exported by libsbc.so and bound by the ctypes layer."""
+    from sde_burst_coast_b200 import swarm
+    hdr = open(os.path.join(ROOT, 'include', 'sbc.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(sbc_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'sbc_handle', 'sbc_params', 'sbc_status'}
+    lib = swarm.load_library()
+    bound = {n for n, _, _ in swarm.ABI}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.sbc_abi_version() == 1
+    assert ctypes.sizeof(P.SbcParams) == 19 * 8 + 8 * 4
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from sde_burst_coast_b200.swarm import Swarm, SbcError
+    sp, _ = P.make_sbc_params(P.tank_params(8))
+    with pytest.raises(SbcError, match='no CPU fallback'):
+        Swarm(sp, 8)
+
+
+# Philox4x32-10 known-answer vectors of Random123 (kat_vectors: philox4x32 10)
+KAT = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+       ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+       ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+
+
+@pytest.mark.parametrize('ctr,key,want', KAT)
+def test_philox_known_answers(ctr, key, want):
+    from oracle import pyorc
+    from sde_burst_coast_b200 import swarm
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    for fn in (pyorc.load('port').lib.orc_philox_raw, swarm.load_library().sbc_philox_raw):
+        out = np.zeros(4, dtype=np.uint32)
+        fn(c.ctypes.data_as(u32p), k.ctypes.data_as(u32p), out.ctypes.data_as(u32p))
+        assert tuple(int(v) for v in out) == want
+
+
+def test_geometric_table_matches_rejection_loop():
+    """The inverse-CDF table reproduces the distribution of the reference's draw loop
+    (agents_dynamics.cpp:250-270): P(k) = q^(k-1) p, capped at max_steps + 1."""
+    from oracle import pyorc
+    sp, _ = P.make_sbc_params(P.tank_params(8))
+    w = pyorc.World(sp, 4096, seed=1)
+    ks = np.concatenate([w.philox_decisions(s)[2] for s in range(40)]).astype(np.int64)
+    p = sp.burst_rate * sp.dt
+    max_steps = int(5 / p)
+    assert ks.min() >= 1 and ks.max() <= max_steps + 1
+    assert abs(ks.mean() - (1 - (1 - p) ** (max_steps + 1)) / p) < 3 * (1 / p) / np.sqrt(ks.size)
+    assert abs((ks == max_steps + 1).mean() - (1 - p) ** max_steps) < 2e-3
