@@ -32,7 +32,6 @@ def test_c1_tank_run_writes_reference_files(tmp_path):
     P.selection_line_parameter(d, 2)
     d.update(out_h5=0, output_mode=1, N=8)
     _run(d, tmp_path, ['-Z', '11'])
-    n_out = 67  # outputs at s = 1020, 1050, ..., 2970 + the one at s = 1020 - 30? -> counted below
     sw = _rows(tmp_path / 'swarm_xx.dat')
     part = _rows(tmp_path / 'part_xx.dat')
     assert sw.shape[1] == 16 and part.shape[1] == 7
@@ -41,7 +40,7 @@ def test_c1_tank_run_writes_reference_files(tmp_path):
     assert part.shape[0] == n_out * 8
     assert np.all(sw[:, 0] == 8)
     assert np.all((sw[:, 1] >= 0) & (sw[:, 1] <= 1 + 1e-6))            # polarisation
-    assert np.all(np.hypot(part[:, 0], part[:, 1]) <= 24.5 * (1 + 1e-6))  # inside the tank
+    assert np.all(np.hypot(part[:, 0], part[:, 1]) <= 24.5 + 2e-3)  # inside the tank (values are printed with 6 significant digits)
     assert np.all(np.isnan(sw[:, 15]))                                    # ND quirk (swarmdyn.cpp:270)
     assert not (tmp_path / 'pred_xx.dat').exists()
     # same seed -> same files; different seed -> different trajectory
