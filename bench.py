@@ -71,10 +71,16 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def mark(self):
+        """Samples taken before this call are outside the timed region."""
+        self.first = len(self.rows)
+
     def stop(self):
+        time.sleep(0.25)
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
+        self.rows = self.rows[max(0, getattr(self, 'first', 0) - 1):]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
         reasons = set()
@@ -195,6 +201,11 @@ def main():
         run_reference(args, sp, N)
         return
 
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)   # a hung rank prints where and dies instead of idling
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    sampler = ClockSampler(local)   # nvidia-smi child is started before CUDA / NCCL are initialised
+    sampler.start()
     import torch
     import torch.distributed as dist
     from sde_burst_coast_b200.swarm import Swarm, load_library
@@ -204,7 +215,6 @@ def main():
         raise SystemExit('bench.py: no CUDA device - the native arm has no CPU fallback')
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
@@ -233,9 +243,7 @@ def main():
         barrier()
         log('warm-up done')
         stats0 = g.stats()
-        sampler = ClockSampler(local)
-        sampler.start()
-        time.sleep(0.3)
+        sampler.mark()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         for k in range(args.steps):

@@ -142,15 +142,18 @@ __global__ void clear_acc_kernel(DevState S) {
 
 }  // namespace
 
-void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {
+// compact the rows that start a burst this step into S.active_list / S.active_count; `clear` also
+// zeroes every row's accumulators (only the test hook reads rows that were not active)
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st) {
     const size_t total = (size_t)S.N * S.R;
-    const int clear_blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-    int *list = S.active_list;
-    int *count = S.active_count;
-    cudaMemsetAsync(count, 0, sizeof(int), st);
-    clear_acc_kernel<<<clear_blocks, 256, 0, st>>>(S);
-    compact_active_kernel<<<clear_blocks, 256, 0, st>>>(S, P.burst_steps, list, count);
-    pair_rows_kernel<<<148 * 4, 256, 0, st>>>(P, S, list, count);
+    const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
+    cudaMemsetAsync(S.active_count, 0, sizeof(int), st);
+    if (clear) clear_acc_kernel<<<blocks, 256, 0, st>>>(S);
+    compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, S.active_list, S.active_count);
+}
+
+void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {
+    pair_rows_kernel<<<148 * 4, 256, 0, st>>>(P, S, S.active_list, S.active_count);
 }
 
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,

@@ -33,6 +33,8 @@ struct sbc_handle {
     StateStage stage;
     DenseScratch dense;
     bool dense_ready;
+    CellScratch cells;
+    bool cells_ready, use_cells;
     double *part_dev;           // [R][N][7] rows of particle::out()
     uint8_t *part_alive_dev;
 };
@@ -189,6 +191,8 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->force_multikernel = false;
     h->stage_raw = nullptr;
     h->dense_ready = false;
+    h->cells_ready = false;
+    h->use_cells = false;
     h->part_dev = nullptr;
     h->part_alive_dev = nullptr;
     std::memset(h->host_stats, 0, sizeof(h->host_stats));
@@ -234,6 +238,17 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
         cudaMemcpy(S.pred_pv, pp.data(), npt * sizeof(float4), cudaMemcpyHostToDevice);
         cudaMemcpy(S.pred_phi, ph.data(), npt * sizeof(float), cudaMemcpyHostToDevice);
     }
+    // pair-search path for the burst-gated pass (sbc_params.path)
+    if (p->path == SBC_PATH_CELLLIST) {
+        if (!sbc_cells_supported(h->P, n_agents, n_replicates)) {
+            g_create_error = "sbc_create: SBC_PATH_CELLLIST needs one swarm and, when periodic, sizeL >= 3 att_range";
+            sbc_destroy(h);
+            return SBC_ERR_INVALID;
+        }
+        h->use_cells = true;
+    } else if (p->path == SBC_PATH_AUTO) {
+        h->use_cells = n_agents >= 8192 && sbc_cells_supported(h->P, n_agents, n_replicates);
+    }
     *out = h;
     // InitSystem defaults (settings.cpp:168-193)
     return sbc_set_state(h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -250,6 +265,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
+    if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -284,7 +300,7 @@ static int ensure_dense(sbc_handle *h) {
 }
 
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
-static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort) {
+static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false) {
     if (all_rows) {
         if (int rc = ensure_dense(h)) return rc;
         if (resort || !h->dense.sorted_valid) {
@@ -296,9 +312,25 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort) {
         h->host_stats[7] += 2;
         h->host_stats[3] += (unsigned long long)h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
     } else {
-        sbc_launch_pair_rows(h->P, h->S, h->stream);
+        sbc_launch_compact_rows(h->P, h->S, clear_inactive, h->stream);
+        h->host_stats[7] += clear_inactive ? 2 : 1;
+        if (h->use_cells) {
+            if (!h->cells_ready) {
+                cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
+                if (e != cudaSuccess) {
+                    sbc_cell_scratch_free(h->cells);
+                    return fail(h, SBC_ERR_NOMEM, std::string("cell list scratch: ") + cudaGetErrorString(e));
+                }
+                h->cells_ready = true;
+            }
+            sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
+            sbc_launch_pair_cells(h->P, h->S, h->cells, h->stream);
+            h->host_stats[6]++;
+            h->host_stats[7] += 5;
+        } else {
+            sbc_launch_pair_rows(h->P, h->S, h->stream);
+        }
         h->host_stats[0]++;
-        h->host_stats[7] += 2;
     }
     return SBC_OK;
 }
@@ -523,7 +555,7 @@ int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_a
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
     const int all_rows = (flags & SBC_PAIR_ALL_ROWS) != 0;
-    if (int rc = launch_pair_pass(h, all_rows, true)) return rc;
+    if (int rc = launch_pair_pass(h, all_rows, true, true)) return rc;
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     SBC_CUDA(cudaGetLastError());
     std::vector<float> acc(total * 8);

@@ -254,7 +254,11 @@ __device__ __forceinline__ float sbc_force_change(float px, float py, float R, f
     bool outside = true, found = false;
     float change = dphi;
     const float L2 = P.L * P.L;
-    while (fabsf(change) < SBC_PI_F && outside) {
+    // The reference loop ends at the first inside probe once |dphi| <= pi/64. In FP32 the inside test
+    // is not monotone at ulp scale, so a run of outside probes could shrink dphi below ulp(change)
+    // and never end: the iteration count is bounded (4 coarse probes + 24 halvings reach 1e-8 rad)
+    // and the last inside angle is returned.
+    for (int it = 0; it < 40 && fabsf(change) < SBC_PI_F && outside; it++) {
         float s, c;
         sincosf(fang + change, &s, &c);
         const float qx = px + R * c, qy = py + R * s;

@@ -47,8 +47,26 @@ void sbc_launch_unpack_state(const DevState &S, const StateStage &st, unsigned m
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
 
 // --- all-pairs three-zone pass -------------------------------------------------------------------
-// burst-gated rows (bin_step == burst_steps), pair_allpairs.cu
+// burst-gated rows (bin_step == burst_steps), pair_allpairs.cu: compaction, then all-pairs rows
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st);
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st);
+// burst-gated rows through a cell list (celllist.cu), single large swarm
+struct CellScratch {
+    uint32_t *key_in = nullptr, *key_out = nullptr;
+    int *idx_in = nullptr, *idx_out = nullptr;   // idx_out[r] = agent id at sorted position r
+    float4 *spv = nullptr;                        // agents in cell order
+    int *cell_start = nullptr, *cell_end = nullptr;
+    int *bbox = nullptr;
+    void *geom = nullptr;                         // CellGeom on the device
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0, ncells = 0;
+    int key_bits = 0, max_per_axis = 0;
+};
+bool sbc_cells_supported(const DevParams &P, int N, int R);
+cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N);
+void sbc_cell_scratch_free(CellScratch &C);
+void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
+void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
 // dense pass (every alive row), pair_dense.cu: Morton order + tiled all pairs + split combine
 struct DenseScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;

@@ -101,3 +101,64 @@ def test_pair_band_recheck_exercised():
     g.pair_interactions(PAIR_ALL_ROWS, want_nn=False)
     assert g.stats()['ambiguous_pairs'] > 0
     g.close()
+
+
+@pytest.mark.parametrize('BC,L,N,spread', [(0, 300.0, 3000, None), (0, 100.0, 2500, None), (0, 61.0, 500, None),
+                                          (-1, 0, 2000, 400.0), (6, 150.0, 2000, None)])
+@pytest.mark.parametrize('alg', [None, 10.0])
+def test_cell_list_path_matches_oracle(BC, L, N, spread, alg):
+    """Burst-gated rows through the cell list (celllist.cu): same integers as the all-pairs oracle."""
+    from sde_burst_coast_b200 import params as PP
+    from sde_burst_coast_b200.swarm import Swarm
+    from helpers import base_dict
+    over = dict(BC=BC, Npred=0)
+    if L:
+        over['size'] = L
+    if alg is not None:
+        over['alg_range'] = alg
+    d = base_dict('natPred' if BC == 0 else 'burst_coast', N, **over)
+    sp, _ = PP.make_sbc_params(d, path=PP.PATH_CELLLIST)
+    rng = np.random.default_rng(N + BC)
+    st = random_state(N, sp, rng, spread=spread)
+    st['bin_step'] = np.where(rng.random(N) < 0.3, sp.burst_steps, st['bin_step']).astype(np.uint32)
+    w = pyorc.World(sp, N, 0, kind='port')
+    w.set_state(**st)
+    ref = w.pair_interactions(PAIR_ACTIVE_ROWS)
+    g = Swarm(sp, N)
+    g.set_state(**st)
+    got = g.pair_interactions(PAIR_ACTIVE_ROWS)
+    assert g.stats()['cell_builds'] == 1
+    for k in ('c_rep', 'c_alg', 'c_att', 'nn_ptr', 'nn_idx'):
+        assert np.array_equal(ref[k], got[k]), k
+    assert ref['c_att'].sum() > 0
+    for k in ('f_rep', 'f_alg', 'f_att'):
+        assert np.allclose(ref[k], got[k], rtol=2e-5, atol=2e-5), k
+    # candidates examined are far fewer than all pairs once the grid has more than 3 x 3 cells
+    if L >= 100.0 or BC != 0:
+        assert g.stats()['pairs'] < 0.5 * (st['bin_step'] == sp.burst_steps).sum() * (N - 1)
+    g.close()
+    w.close()
+
+
+def test_cell_list_steps_match_all_pairs_path():
+    from sde_burst_coast_b200 import params as PP
+    from sde_burst_coast_b200.swarm import Swarm
+    from helpers import base_dict
+    N = 9000
+    d = base_dict('natPred', N, BC=0, size=300.0, Npred=0)
+    rng = np.random.default_rng(4)
+    out = []
+    for path in (PP.PATH_CELLLIST, PP.PATH_ALLPAIRS):
+        sp, _ = PP.make_sbc_params(d, path=path)
+        if not out:
+            st = random_state(N, sp, rng)
+        g = Swarm(sp, N, seed=8)
+        g.set_state(**st)
+        g.step(0, 20)
+        out.append((g.get_state(), g.stats()))
+        g.close()
+    a, b = out[0][0], out[1][0]
+    assert out[0][1]['cell_builds'] == 20 and out[1][1]['cell_builds'] == 0
+    assert np.array_equal(a['bin_step'], b['bin_step']) and np.array_equal(a['steps_till_burst'], b['steps_till_burst'])
+    close = (np.abs(a['x'] - b['x']) < 1e-3) & (np.abs(a['y'] - b['y']) < 1e-3)
+    assert close.mean() > 0.995
