@@ -1,0 +1,118 @@
+"""GPU parity of the predator phase (prey<-predator detection, spawn, chase / random walk / fish-net move,
+the four kill rules) against the CPU oracle, through the C ABI.
+
+Bars: alive sets and zone/flee counters exact for a given state; predator positions and agent states
+within the one-step FP32 tolerance; longer runs are compared statistically (kills vs time)."""
+import numpy as np
+import pytest
+
+from helpers import make_params, random_state, ang_diff
+from oracle import pyorc
+
+pytestmark = pytest.mark.gpu
+
+
+def _swarm(*a, **k):
+    from sde_burst_coast_b200.swarm import Swarm
+    return Swarm(*a, **k)
+
+
+def _setup(mode, N, npred, kill, move, L=100.0, seed=1, **over):
+    sp, np_, _ = make_params(mode, N, BC=0, size=L, Npred=npred, pred_kill=kill, pred_move=move,
+                             pred_time=0.0, time=50.0, **over)
+    assert np_ == npred
+    rng = np.random.default_rng(seed)
+    st = random_state(N, sp, rng, spread=30.0)
+    return sp, st, rng
+
+
+@pytest.mark.parametrize('kill,move,npred,mode', [(1, 1, 1, 'natPred'), (2, 1, 1, 'natPredNoConfu'), (3, 1, 1, 'natPred'),
+                                                   (4, 1, 1, 'natPred'), (1, 0, 1, 'sinFisher'), (1, 0, 50, 'mulFisher')])
+def test_one_step_with_predator_present(kill, move, npred, mode):
+    """Predator(s) placed inside the swarm: one step = detection for burst-starting rows, update,
+    predator move, kill. Alive sets exact, everything else within tolerance."""
+    N = 200
+    sp, st, rng = _setup(mode, N, npred, kill, move, seed=kill * 7 + npred, N_confu=500, kill_rate=4000.0 if kill == 4 else 400.0)
+    st['bin_step'] = np.where(rng.random(N) < 0.4, sp.burst_steps, st['bin_step']).astype(np.uint32)
+    if npred == 1:
+        px, py, pphi = np.array([50.0]), np.array([50.0]), np.array([0.3])
+    else:
+        px = 40.0 + 0.5 * np.arange(npred, dtype=np.float64)
+        py = np.full(npred, 48.0)
+        pphi = np.full(npred, np.pi / 2)
+    mism = 0
+    killed = 0
+    for trial in range(3):
+        w = pyorc.World(sp, N, npred, seed=100 + trial, replicate=0)
+        g = _swarm(sp, N, npred, seed=100 + trial)
+        g.force_multikernel(True)
+        for obj in (w, g):
+            obj.set_state(**st)
+            obj.set_predators(px, py, pphi, 1)
+        s = 5 + trial   # > pred_time/dt = 0, not the spawn step
+        w.step(s, 1)
+        g.step(s, 1)
+        o, gs = w.get_state(), g.get_state()
+        assert np.array_equal(o['alive'], gs['alive']), np.where(o['alive'] != gs['alive'])[0]
+        killed += N - int(o['alive'].sum())
+        al = o['alive'].astype(bool)
+        assert np.array_equal(o['bin_step'][al], gs['bin_step'][al])
+        ok = (np.abs(o['x'] - gs['x']) <= 1e-5 * np.maximum(1, np.abs(o['x']))) & \
+             (np.abs(o['y'] - gs['y']) <= 1e-5 * np.maximum(1, np.abs(o['y']))) & \
+             (np.hypot(o['fx'] - gs['fx'], o['fy'] - gs['fy']) <= 2e-5 * np.maximum(1, np.hypot(o['fx'], o['fy'])))
+        mism += int((~ok[al]).sum())
+        po, pg = w.get_predators(), g.get_predators()[0]
+        assert np.allclose(po, pg, rtol=1e-5, atol=1e-4), (po[:2], pg[:2])
+        assert w.counts() == tuple(int(v[0]) for v in g.counts())
+        w.close()
+        g.close()
+    assert killed > 0, 'somebody should have been killed'
+    assert mism <= 3, mism   # detection / decision flips at FP32 resolution are rare
+
+
+@pytest.mark.parametrize('npred', [1, 50])
+def test_spawn_step_places_predator_like_oracle(npred):
+    N = 120
+    mode = 'natPred' if npred == 1 else 'mulFisher'
+    sp, np_, _ = make_params(mode, N, BC=0, size=100.0, Npred=npred, pred_kill=0, pred_move=1 if npred == 1 else 0,
+                             pred_time=0.01, time=50.0)
+    rng = np.random.default_rng(3)
+    st = random_state(N, sp, rng, spread=30.0)
+    w = pyorc.World(sp, N, npred, seed=9, replicate=4)
+    g = _swarm(sp, N, npred, seed=9, replicate_offset=4)
+    g.force_multikernel(True)
+    for obj in (w, g):
+        obj.set_state(**st)
+    w.step(0, 12)
+    g.step(0, 12)   # spawn happens at s = 10
+    po, pg = w.get_predators(), g.get_predators()[0]
+    assert np.allclose(po[:, :2] % 100.0, pg[:, :2] % 100.0, atol=2e-3), (po[:3], pg[:3])
+    assert np.allclose(po[:, 2:4], pg[:, 2:4], atol=2e-3)
+    w.close()
+    g.close()
+
+
+def test_survival_curve_matches_oracle_statistically():
+    """natPred (chasing predator, confusion kill rule): the number of survivors after 3000 steps over an
+    ensemble of swarms agrees with the oracle's ensemble within 4 standard errors."""
+    N, R = 30, 48
+    sp, _, _ = make_params('natPred', N, BC=0, size=100.0, Npred=1, pred_kill=2, pred_move=1, pred_time=0.05,
+                           time=50.0, kill_rate=20.0, pred_speed0=20.0)
+    rng = np.random.default_rng(0)
+    sts = [random_state(N, sp, rng, spread=25.0, mid_burst=False) for _ in range(R)]
+    dead_o, dead_g = [], []
+    for r in range(R):
+        w = pyorc.World(sp, N, 1, seed=31, replicate=r)
+        w.set_state(**sts[r])
+        w.step(0, 3000)
+        dead_o.append(w.counts()[1])
+        w.close()
+    g = _swarm(sp, N, 1, n_replicates=R, seed=77)
+    g.set_state(**{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    g.step(0, 3000)
+    dead_g = g.counts()[1]
+    g.close()
+    mo, mg = np.mean(dead_o), np.mean(dead_g)
+    se = np.sqrt(np.var(dead_o) / R + np.var(dead_g) / R) + 1e-9
+    assert mo > 0.5 and mg > 0.5, (mo, mg)
+    assert abs(mo - mg) <= 4 * se + 0.5, (mo, mg, se)
