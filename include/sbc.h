@@ -167,6 +167,27 @@ int sbc_debug_force_multikernel(sbc_handle *h, int on);
  * [5] agent-steps, [6] cell-list builds, [7] other launches. */
 int sbc_get_stats(sbc_handle *h, uint64_t out[8]);
 
+/* ---- spatial domain decomposition of ONE large periodic swarm over several handles -----------------
+ * (one handle per GPU; SURVEY.md section 8e, BASELINE config C5). The reference is a single process and
+ * has no counterpart; Step()'s semantics (swarmdyn.cpp:143-204) are kept: interactions see positions at
+ * the start of the step, every agent is updated once, decisions depend on (seed, GLOBAL id, step).
+ * A handle's n_agents is its slot capacity: slots [0, own_capacity) hold owned agents or free slots,
+ * the rest hold ghosts (copies of the neighbours' agents within att_range of a slab edge).
+ * Buffers are DEVICE pointers of sbc_domain_buffer_bytes(max_records) bytes: a header record with the
+ * count followed by 64-byte records, so messages have a fixed size and no host round trip is needed.
+ * Per step the host does: pack_halos -> exchange -> unpack_ghosts -> sbc_step(h, s, 1) ->
+ * pack_migrants -> exchange -> unpack_migrants (sde_burst_coast_b200/domain.py; transport = NCCL
+ * send/recv over NVLink through torch.distributed). */
+int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid /* [n_agents] */);
+int sbc_get_global_ids(sbc_handle *h, uint32_t *gid /* [n_agents]; 0xFFFFFFFF for empty ghost slots */);
+int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity);
+size_t sbc_domain_buffer_bytes(int max_records);
+int sbc_domain_pack_halos(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records);
+int sbc_domain_unpack_ghosts(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev);
+int sbc_domain_pack_migrants(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records);
+int sbc_domain_unpack_migrants(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev, int max_records);
+int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t *overflow_events);
+
 /* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on
  * the handle's stream; returns mean milliseconds per launch in *ms. */
 int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms);

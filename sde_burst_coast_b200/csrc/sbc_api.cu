@@ -35,6 +35,7 @@ struct sbc_handle {
     bool dense_ready;
     CellScratch cells;
     bool cells_ready, use_cells;
+    DomainScratch dom;
     double *part_dev;           // [R][N][7] rows of particle::out()
     uint8_t *part_alive_dev;
 };
@@ -266,6 +267,8 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
+    if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
+    cudaFree(h->S.gid);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -710,6 +713,99 @@ int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     SBC_CUDA(cudaGetLastError());
+    return SBC_OK;
+}
+
+/* ---- domain decomposition (see include/sbc.h) ------------------------------------------------- */
+int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid) {
+    if (!h || !gid) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    const size_t total = (size_t)h->S.N * h->S.R;
+    if (!h->S.gid) SBC_CUDA(dev_alloc(&h->S.gid, total));
+    SBC_CUDA(cudaMemcpyAsync(h->S.gid, gid, total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    return SBC_OK;
+}
+
+int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity) {
+    if (!h || world < 1 || rank < 0 || rank >= world) return SBC_ERR_INVALID;
+    if (h->S.R != 1) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: one swarm per handle");
+    if (h->hp.BC != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: periodic boundary (BC 0) only");
+    if (h->S.Npred != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators are not decomposed yet");
+    if (own_capacity < 1 || own_capacity > h->S.N) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad own_capacity");
+    const double w = h->hp.sizeL / world, halo = h->hp.att_range * 1.0001;
+    if (world > 1 && w < (world == 2 ? 2 * halo : halo))
+        return fail(h, SBC_ERR_INVALID, "sbc_domain_config: slabs narrower than the halo");
+    if (!h->use_cells) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: needs the cell-list path");
+    SBC_CUDA(cudaSetDevice(h->device));
+    if (!h->dom.enabled) {
+        cudaError_t e = sbc_domain_scratch_alloc(h->dom, h->S.N);
+        if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
+        h->dom.enabled = true;
+    }
+    h->dom.own_cap = own_capacity;
+    h->dom.x_lo = (float)(w * rank);
+    h->dom.x_hi = (rank == world - 1) ? (float)h->hp.sizeL : (float)(w * (rank + 1));
+    if (!h->S.gid) {  // default ids = slot index
+        std::vector<uint32_t> ids((size_t)h->S.N);
+        for (size_t k = 0; k < ids.size(); k++) ids[k] = (uint32_t)k;
+        if (int rc = sbc_set_global_ids(h, ids.data())) return rc;
+    }
+    return SBC_OK;
+}
+
+size_t sbc_domain_buffer_bytes(int max_records) { return (size_t)(max_records + 1) * sbc_domain_record_bytes(); }
+
+int sbc_domain_pack_halos(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_pack_halos(h->P, h->S, h->dom, buf_left_dev, buf_right_dev, max_records, h->stream);
+    h->host_stats[7] += 4;
+    return SBC_OK;
+}
+int sbc_domain_unpack_ghosts(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_unpack_ghosts(h->S, h->dom, buf_a_dev, buf_b_dev, h->stream);
+    h->host_stats[7] += 1;
+    return SBC_OK;
+}
+int sbc_domain_pack_migrants(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_pack_migrants(h->P, h->S, h->dom, buf_left_dev, buf_right_dev, max_records, h->stream);
+    h->host_stats[7] += 4;
+    return SBC_OK;
+}
+int sbc_domain_unpack_migrants(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev, int max_records) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_unpack_migrants(h->S, h->dom, buf_a_dev, buf_b_dev, max_records, h->stream);
+    h->host_stats[7] += 2;
+    return SBC_OK;
+}
+int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t *overflow_events) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    sbc_launch_count_owned(h->S, h->dom, h->stream);
+    int v[4];
+    SBC_CUDA(cudaMemcpyAsync(v, h->dom.n_sel, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (n_owned) *n_owned = v[1];
+    if (n_ghost) *n_ghost = v[2];
+    if (overflow_events) *overflow_events = v[3];
+    return SBC_OK;
+}
+int sbc_get_global_ids(sbc_handle *h, uint32_t *gid) {
+    if (!h || !gid) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    const size_t total = (size_t)h->S.N * h->S.R;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->S.gid) {
+        SBC_CUDA(cudaMemcpy(gid, h->S.gid, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    } else {
+        for (size_t k = 0; k < total; k++) gid[k] = (uint32_t)(k % h->S.N);
+    }
     return SBC_OK;
 }
 

@@ -11,6 +11,7 @@ struct DevState {
     float2 *force;     // {fx, fy}
     uint2 *timers;     // {bin_step, steps_till_burst}
     uint8_t *alive;
+    uint32_t *gid;     // global agent id per slot (domain decomposition), nullptr = slot index
     // row accumulators written by the pair pass, consumed by the update
     float *acc;        // [R*N][8] rep.xy alg.xy att.xy flee.xy
     int *cnt;          // [R*N][4] c_rep c_alg c_att c_flee
@@ -87,6 +88,28 @@ void sbc_launch_pair_dense(const DevParams &P, const DevState &S, DenseScratch &
 // test hook: CSR neighbour lists (ascending j) for the same row set
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,
                         int *nn_idx, cudaStream_t st);
+
+// --- domain decomposition of one large swarm (domain.cu) --------------------------------------------
+struct DomainScratch {
+    int *sel = nullptr;      // selected slot indices
+    int *n_sel = nullptr;    // [0] selection count, [1] owned, [2] ghosts, [3] overflow events
+    void *cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int own_cap = 0;         // slots [0, own_cap) are owned / free, [own_cap, N) ghosts
+    float x_lo = 0.f, x_hi = 0.f;
+    bool enabled = false;
+};
+size_t sbc_domain_record_bytes(void);
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int n_slots);
+void sbc_domain_scratch_free(DomainScratch &D);
+void sbc_launch_pack_halos(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
+                           void *buf_right, int max_records, cudaStream_t st);
+void sbc_launch_unpack_ghosts(const DevState &S, DomainScratch &D, const void *a, const void *b, cudaStream_t st);
+void sbc_launch_pack_migrants(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
+                              void *buf_right, int max_records, cudaStream_t st);
+void sbc_launch_unpack_migrants(const DevState &S, DomainScratch &D, const void *a, const void *b, int max_records,
+                                cudaStream_t st);
+void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, int pred_active,

@@ -17,7 +17,9 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, in
     if (g >= total) return;
     if (!S.alive[g]) return;
     const int N = S.N;
-    const uint32_t rep = (uint32_t)(g / N), i = (uint32_t)(g - (size_t)rep * N);
+    const uint32_t rep = (uint32_t)(g / N);
+    // Philox counters use the GLOBAL agent id, so a decomposed swarm draws what the whole swarm would
+    const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
     AgentState a;
     {
         const float4 p = S.pv[g];

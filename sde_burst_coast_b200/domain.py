@@ -1,0 +1,220 @@
+"""Host side of the spatial domain decomposition of ONE large periodic swarm (BASELINE config C5):
+slabs along x, one libsbc handle per GPU, per-step halo exchange and agent migration.
+
+The device work (selecting edge agents, building / applying 64-byte records) is in libsbc.so
+(csrc/domain.cu, entry points sbc_domain_* of include/sbc.h). This module owns the routing:
+which rank is left / right, who gets which buffer, and the transport - `DistTransport` moves the
+fixed-size record buffers with torch.distributed point-to-point operations (NCCL over NVLink between
+GPUs; the same code runs on CPU tensors with gloo, which is how the routing is tested without GPUs),
+`LoopbackTransport` wires several slabs inside one process (single-GPU emulation in the tests).
+
+Nothing here computes the hot path; the reference has no counterpart (it is a single process).
+"""
+import ctypes
+
+import numpy as np
+
+RECORD_BYTES = 64
+
+
+def slab_bounds(L, world):
+    """[x_lo, x_hi) of every rank; the last slab ends exactly at L."""
+    w = L / world
+    return [(w * r, L if r == world - 1 else w * (r + 1)) for r in range(world)]
+
+
+def owner_of(x, L, world):
+    """Rank owning position x (array) in a periodic box of length L."""
+    r = np.floor(np.asarray(x, dtype=np.float64) / (L / world)).astype(np.int64)
+    return np.clip(r, 0, world - 1)
+
+
+def neighbours(rank, world):
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def check_geometry(L, att_range, world):
+    """Slabs must be at least one halo wide (two when both neighbours are the same rank)."""
+    w, halo = L / world, att_range * 1.0001
+    if world > 1 and w < (2 * halo if world == 2 else halo):
+        raise ValueError('slab width %.3f is narrower than the halo requirement for att_range %.3f' % (w, att_range))
+
+
+class DistTransport:
+    """Exchange with the two ring neighbours through torch.distributed (nccl for CUDA tensors, gloo for CPU)."""
+
+    def __init__(self, rank, world, group=None):
+        import torch.distributed as dist
+        self.dist, self.rank, self.world, self.group = dist, rank, world, group
+
+    def exchange(self, send_left, send_right, recv_from_left, recv_from_right):
+        """send_left -> left neighbour (arrives there as data from its right), send_right -> right neighbour."""
+        d = self.dist
+        left, right = neighbours(self.rank, self.world)
+        if self.world == 1:
+            recv_from_right.copy_(send_left)
+            recv_from_left.copy_(send_right)
+            return
+        if self.world == 2:
+            # both neighbours are the same peer: one ordered pair of messages each way. What I send to
+            # my left arrives as the peer's "from right" and vice versa; the peer posts the same order.
+            ops = [d.P2POp(d.isend, send_left, left, self.group), d.P2POp(d.isend, send_right, right, self.group),
+                   d.P2POp(d.irecv, recv_from_right, right, self.group), d.P2POp(d.irecv, recv_from_left, left, self.group)]
+        else:
+            ops = [d.P2POp(d.isend, send_left, left, self.group), d.P2POp(d.irecv, recv_from_right, right, self.group),
+                   d.P2POp(d.isend, send_right, right, self.group), d.P2POp(d.irecv, recv_from_left, left, self.group)]
+        for req in d.batch_isend_irecv(ops):
+            req.wait()
+
+
+class LoopbackTransport:
+    """All slabs live in this process: collect every rank's send buffers, then deliver."""
+
+    def __init__(self, world):
+        self.world = world
+        self.pending = {}
+
+    def post(self, rank, send_left, send_right):
+        self.pending[rank] = (send_left, send_right)
+
+    def deliver(self, rank, recv_from_left, recv_from_right):
+        left, right = neighbours(rank, self.world)
+        recv_from_left.copy_(self.pending[left][1])    # left neighbour's "send right"
+        recv_from_right.copy_(self.pending[right][0])  # right neighbour's "send left"
+
+
+class SlabSwarm:
+    """One slab of the decomposed swarm on one GPU."""
+
+    def __init__(self, sp, n_global, rank, world, seed=0, device=0, stream=None, own_capacity=None,
+                 ghost_capacity=None, max_records=None):
+        import torch
+        from .swarm import Swarm
+        from . import params as P
+        check_geometry(sp.sizeL, sp.att_range, world)
+        self.torch = torch
+        self.rank, self.world, self.n_global = rank, world, int(n_global)
+        mean_own = n_global / world
+        halo_frac = min(1.0, 2 * sp.att_range * 1.0001 / (sp.sizeL / world))
+        self.own_cap = int(own_capacity or (mean_own * 1.5 + 1024))
+        self.ghost_cap = 0 if world == 1 else int(ghost_capacity or (mean_own * halo_frac * 2 + 1024))
+        self.max_records = int(max_records or max(1024, self.ghost_cap // 2 + 256))
+        sp2 = type(sp).from_buffer_copy(sp)
+        sp2.path = P.PATH_CELLLIST
+        self.sp = sp2
+        self.dev = torch.device('cuda', device)
+        self.swarm = Swarm(sp2, self.own_cap + self.ghost_cap, 0, 1, seed=seed, device=device, stream=stream)
+        lib, h = self.swarm.lib, self.swarm.h
+        self.swarm._check(lib.sbc_domain_config(h, rank, world, self.own_cap))
+        nbytes = lib.sbc_domain_buffer_bytes(self.max_records)
+        mk = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+
+    # ---- state in / out (host arrays indexed by GLOBAL agent id) -------------------------------
+    def scatter_initial(self, state):
+        """Take this rank's agents out of global arrays (x, y, phi, vproj, optional timers...)."""
+        N = self.swarm.N
+        mine = np.where(owner_of(state['x'], self.sp.sizeL, self.world) == self.rank)[0]
+        if mine.size > self.own_cap:
+            raise ValueError('own_capacity %d < %d agents of rank %d' % (self.own_cap, mine.size, self.rank))
+        local = {}
+        for k, v in state.items():
+            a = np.zeros(N, dtype=np.asarray(v).dtype)
+            a[:mine.size] = np.asarray(v)[mine]
+            local[k] = a
+        alive = np.zeros(N, dtype=np.uint8)
+        alive[:mine.size] = 1
+        gid = np.full(N, 0xFFFFFFFF, dtype=np.uint32)
+        gid[:mine.size] = mine.astype(np.uint32)
+        self.swarm.set_state(alive=alive, **local)
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        self.swarm._check(self.swarm.lib.sbc_set_global_ids(self.swarm.h, gid.ctypes.data_as(u32p)))
+
+    def owned_state(self):
+        """(gids, state dict) of the agents this rank owns now."""
+        st = self.swarm.get_state()
+        gid = np.zeros(self.swarm.N, dtype=np.uint32)
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        self.swarm._check(self.swarm.lib.sbc_get_global_ids(self.swarm.h, gid.ctypes.data_as(u32p)))
+        own = np.where(st['alive'][:self.own_cap] == 1)[0]
+        return gid[own], {k: v[own] for k, v in st.items()}
+
+    def counts(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self.swarm._check(self.swarm.lib.sbc_domain_counts(self.swarm.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(owned=a.value, ghosts=b.value, overflow_events=c.value)
+
+    # ---- the two exchange phases around one step ----------------------------------------------
+    def _p(self, t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def pack_halos(self):
+        self.swarm._check(self.swarm.lib.sbc_domain_pack_halos(self.swarm.h, self._p(self.send_l), self._p(self.send_r), self.max_records))
+
+    def unpack_ghosts(self):
+        self.swarm._check(self.swarm.lib.sbc_domain_unpack_ghosts(self.swarm.h, self._p(self.recv_l), self._p(self.recv_r)))
+
+    def pack_migrants(self):
+        self.swarm._check(self.swarm.lib.sbc_domain_pack_migrants(self.swarm.h, self._p(self.send_l), self._p(self.send_r), self.max_records))
+
+    def unpack_migrants(self):
+        self.swarm._check(self.swarm.lib.sbc_domain_unpack_migrants(self.swarm.h, self._p(self.recv_l), self._p(self.recv_r), self.max_records))
+
+    def step_local(self, s):
+        self.swarm.step(s, 1)
+
+    def close(self):
+        self.swarm.close()
+
+
+def step_distributed(slab, transport, s_first, n_steps):
+    """Advance one rank's slab (world > 1: a DistTransport moves the buffers between ranks)."""
+    for s in range(s_first, s_first + n_steps):
+        if slab.world > 1:
+            slab.pack_halos()
+            transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
+            slab.unpack_ghosts()
+        slab.step_local(s)
+        if slab.world > 1:
+            slab.pack_migrants()
+            transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
+            slab.unpack_migrants()
+
+
+def step_loopback(slabs, s_first, n_steps):
+    """Advance all slabs held in this process in lock step (tests / single-GPU emulation)."""
+    world = len(slabs)
+    tr = LoopbackTransport(world)
+    for s in range(s_first, s_first + n_steps):
+        if world > 1:
+            for sl in slabs:
+                sl.pack_halos()
+                tr.post(sl.rank, sl.send_l, sl.send_r)
+            slabs[0].torch.cuda.synchronize()
+            for sl in slabs:
+                tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
+                sl.unpack_ghosts()
+        for sl in slabs:
+            sl.step_local(s)
+        if world > 1:
+            for sl in slabs:
+                sl.pack_migrants()
+                tr.post(sl.rank, sl.send_l, sl.send_r)
+            slabs[0].torch.cuda.synchronize()
+            for sl in slabs:
+                tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
+                sl.unpack_migrants()
+
+
+def gather_global(slabs, n_global):
+    """Global arrays (by agent id) from slabs held in this process."""
+    out = None
+    seen = np.zeros(n_global, dtype=np.int32)
+    for sl in slabs:
+        gid, st = sl.owned_state()
+        if out is None:
+            out = {k: np.zeros(n_global, dtype=v.dtype) for k, v in st.items()}
+        for k, v in st.items():
+            out[k][gid] = v
+        seen[gid] += 1
+    return out, seen
