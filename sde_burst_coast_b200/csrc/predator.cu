@@ -111,7 +111,9 @@ __device__ __forceinline__ void kill_agent(DevState &S, size_t g, float4 p) {
 }
 
 __global__ void __launch_bounds__(PT)
-pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step) {
+pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
+                      const uint32_t *__restrict__ step_dev) {
+    const uint32_t step = step_dev ? *step_dev : step_arg;
     __shared__ double sh[PT / 32];
     __shared__ unsigned long long s_key[PT / 32];
     __shared__ float s_p[4];
@@ -264,6 +266,7 @@ void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step
                            cudaStream_t st) {
     pred_spawn_kernel<<<S.R, PT, 0, st>>>(P, S, (uint32_t)step, (uint32_t)slot);
 }
-void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, cudaStream_t st) {
-    pred_move_kill_kernel<<<S.R, PT, 0, st>>>(P, S, (uint32_t)step);
+void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
+                               cudaStream_t st) {
+    pred_move_kill_kernel<<<S.R, PT, 0, st>>>(P, S, (uint32_t)step, step_dev);
 }

@@ -36,6 +36,12 @@ struct sbc_handle {
     CellScratch cells;
     bool cells_ready, use_cells;
     DomainScratch dom;
+    // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
+    cudaGraphExec_t step_graph[2];
+    bool step_graph_ok[2];
+    uint32_t *step_dev;
+    int64_t step_dev_value;
+    bool use_graphs;
     double *part_dev;           // [R][N][7] rows of particle::out()
     uint8_t *part_alive_dev;
 };
@@ -194,6 +200,10 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->dense_ready = false;
     h->cells_ready = false;
     h->use_cells = false;
+    h->step_graph_ok[0] = h->step_graph_ok[1] = false;
+    h->step_dev = nullptr;
+    h->step_dev_value = -1;
+    h->use_graphs = getenv("SBC_NO_GRAPHS") == nullptr;
     h->part_dev = nullptr;
     h->part_alive_dev = nullptr;
     std::memset(h->host_stats, 0, sizeof(h->host_stats));
@@ -269,6 +279,8 @@ int sbc_destroy(sbc_handle *h) {
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     cudaFree(h->S.gid);
+    for (int k = 0; k < 2; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
+    cudaFree(h->step_dev);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -522,12 +534,52 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     h->host_stats[7]++;
                 }
             }
-            if (int rc = launch_pair_pass(h, 0, false)) return rc;
-            sbc_launch_update(h->P, S, s, pred_phase ? 1 : 0, h->stream);
-            h->host_stats[1]++;
-            if (pred_phase) {
-                sbc_launch_pred_move_kill(h->P, S, s, h->stream);
-                h->host_stats[7]++;
+            // the fixed part of the step (compaction, pair pass, update, predator move + kill) is
+            // replayed from a CUDA graph: one launch instead of ~6-15. The step index then lives in
+            // device memory and is advanced by the graph's last node.
+            const int gk = pred_phase ? 1 : 0;
+            const bool graphable = h->use_graphs && !injected && !S.flags && (!h->use_cells || h->cells_ready) &&
+                                   h->stream != nullptr && h->stream != cudaStreamLegacy &&
+                                   h->stream != cudaStreamPerThread;  // the default streams cannot be captured
+            if (graphable) {
+                if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
+                if (h->step_dev_value != s) {
+                    const uint32_t sv = (uint32_t)s;
+                    SBC_CUDA(cudaMemcpyAsync(h->step_dev, &sv, sizeof(sv), cudaMemcpyHostToDevice, h->stream));
+                    SBC_CUDA(cudaStreamSynchronize(h->stream));  // sv is a stack variable
+                }
+                if (!h->step_graph_ok[gk]) {
+                    cudaGraph_t graph;
+                    unsigned long long keep[8];
+                    std::memcpy(keep, h->host_stats, sizeof(keep));  // the capture pass launches nothing
+                    SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                    int rc = launch_pair_pass(h, 0, false);
+                    sbc_launch_update(h->P, S, 0, h->step_dev, gk, h->stream);
+                    if (gk) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
+                    sbc_launch_step_advance(h->step_dev, h->stream);
+                    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    if (rc) return rc;
+                    if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+                    ce = cudaGraphInstantiate(&h->step_graph[gk], graph, 0);
+                    cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+                    h->step_graph_ok[gk] = true;
+                    std::memcpy(h->host_stats, keep, sizeof(keep));
+                }
+                SBC_CUDA(cudaGraphLaunch(h->step_graph[gk], h->stream));
+                h->step_dev_value = s + 1;
+                h->host_stats[0]++;
+                h->host_stats[1]++;
+                h->host_stats[7] += (h->use_cells ? 7 : 2) + (gk ? 1 : 0);
+                if (h->use_cells) h->host_stats[6]++;
+            } else {
+                if (int rc = launch_pair_pass(h, 0, false)) return rc;
+                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream);
+                h->host_stats[1]++;
+                if (pred_phase) {
+                    sbc_launch_pred_move_kill(h->P, S, s, nullptr, h->stream);
+                    h->host_stats[7]++;
+                }
             }
         }
     }

@@ -112,13 +112,15 @@ void sbc_launch_unpack_migrants(const DevState &S, DomainScratch &D, const void 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
-void sbc_launch_update(const DevParams &P, const DevState &S, long long step, int pred_active,
-                       cudaStream_t st);
+void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
+                       int pred_active, cudaStream_t st);
+void sbc_launch_step_advance(uint32_t *step_dev, cudaStream_t st);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,
                            cudaStream_t st);
-void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, cudaStream_t st);
+void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
+                               cudaStream_t st);
 
 // --- one block per swarm, many steps per launch (swarm_block.cu) -------------------------------
 // returns false when the configuration does not fit this path (N > 1024)

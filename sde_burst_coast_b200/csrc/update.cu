@@ -11,7 +11,10 @@
 namespace {
 
 __global__ void __launch_bounds__(256)
-update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, int pred_active) {
+update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg, const uint32_t *__restrict__ step_dev,
+              int pred_active) {
+    // inside a captured CUDA graph the step index lives in device memory (advanced by step_advance_kernel)
+    const uint32_t step = step_dev ? *step_dev : step_arg;
     const size_t total = (size_t)S.N * S.R;
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= total) return;
@@ -78,8 +81,11 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, in
 
 }  // namespace
 
-void sbc_launch_update(const DevParams &P, const DevState &S, long long step, int pred_active,
-                       cudaStream_t st) {
+__global__ void step_advance_kernel(uint32_t *step_dev) { *step_dev += 1u; }
+
+void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
+                       int pred_active, cudaStream_t st) {
     const size_t total = (size_t)S.N * S.R;
-    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, pred_active);
+    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active);
 }
+void sbc_launch_step_advance(uint32_t *step_dev, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(step_dev); }

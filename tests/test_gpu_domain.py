@@ -8,6 +8,7 @@ from oracle import pyorc
 from sde_burst_coast_b200 import params as PP
 
 pytestmark = pytest.mark.gpu
+_STREAM = None
 
 
 def _setup(N, L, seed):
@@ -21,7 +22,11 @@ def _setup(N, L, seed):
 def _slabs(sp, st, N, world, seed):
     import torch
     from sde_burst_coast_b200.domain import SlabSwarm
-    stream = torch.cuda.current_stream().cuda_stream
+    global _STREAM
+    if _STREAM is None:
+        _STREAM = torch.cuda.Stream()
+    torch.cuda.set_stream(_STREAM)   # one capturable stream for libsbc kernels and torch copies
+    stream = _STREAM.cuda_stream
     slabs = [SlabSwarm(sp, N, r, world, seed=seed, stream=stream) for r in range(world)]
     for sl in slabs:
         sl.scatter_initial(st)
