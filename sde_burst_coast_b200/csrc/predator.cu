@@ -75,7 +75,7 @@ pred_spawn_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step
             sincosf(phi, &s, &c);
             float x = s_com[0] - 0.5f * P.L * c, y = s_com[1] - 0.5f * P.L * s;
             float vx = P.pred_speed * c, vy = P.pred_speed * s;
-            sbc_boundary(x, y, vx, vy, phi, P);
+            sbc_boundary(x, y, vx, vy, phi, P, P.BC);
             pp[0] = make_float4(x, y, vx, vy);
             pphi[0] = phi;
             S.pred_spawned[rep] = 1;
@@ -95,7 +95,7 @@ pred_spawn_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step
         for (int j = threadIdx.x; j < S.Npred; j += PT) {
             float x = sx + px * ((float)j * net_dist), y = sy + py * ((float)j * net_dist);
             float vx = P.pred_speed * c, vy = P.pred_speed * s, ph = phi;
-            sbc_boundary(x, y, vx, vy, ph, P);
+            sbc_boundary(x, y, vx, vy, ph, P, P.BC);
             pp[j] = make_float4(x, y, vx, vy);
             pphi[j] = ph;
         }
@@ -131,7 +131,7 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
             float ph = pphi[j];
             p.x += p.z * P.dt;
             p.y += p.w * P.dt;
-            sbc_boundary(p.x, p.y, p.z, p.w, ph, P);
+            sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
             pp[j] = p;
             pphi[j] = ph;
         }
@@ -201,7 +201,7 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
             float vx = P.pred_speed * c, vy = P.pred_speed * s;
             float x = p0.x + vx * P.dt, y = p0.y + vy * P.dt;
             float ph = lphi;
-            sbc_boundary(x, y, vx, vy, ph, P);
+            sbc_boundary(x, y, vx, vy, ph, P, P.BC);
             pp[0] = make_float4(x, y, vx, vy);
             pphi[0] = ph;
             s_p[0] = x; s_p[1] = y;

@@ -76,6 +76,9 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
     P.alphaTurn = (float)p.alphaTurn;
     P.soc = (float)p.soc_strength;
     P.env = (float)p.env_strength;
+    P.inv_soc = (float)(1.0 / p.soc_strength);
+    P.inv_env = (float)(1.0 / p.env_strength);
+    P.inv_log2q = (float)(1.0 / std::log2(1.0 - p.burst_rate * p.dt));
     P.rep = (float)p.rep_range;
     P.alg = (float)p.alg_range;
     P.att = (float)p.att_range;

@@ -18,7 +18,8 @@ struct DevParams {
     // geometry / dynamics (FP32 copies of sbc_params)
     float L, halfL, invL, L_lo;   // L_lo = sizeL - (double)(float)sizeL
     float dt, beta, alphaTurn;
-    float soc, env;
+    float soc, env, inv_soc, inv_env;
+    float inv_log2q;               // 1 / log2(1 - burst_rate dt): continuous inverse CDF of the inter-burst draw
     float rep, alg, att;           // ranges
     float rep2, alg2, att2;        // squared thresholds for the fast compare
     float band_lo[3], band_hi[3];  // d2 inside [lo,hi] of any threshold => FP64 re-check
@@ -98,15 +99,22 @@ __device__ __forceinline__ uint4 sbc_draw(const DevParams &P, uint32_t replicate
 }
 
 // smallest k >= 1 with r < thr[k-1]; none -> max_steps + 1 (inverse CDF of the rejection loop
-// agents_dynamics.cpp:250-270, integer-exact against the oracle's table)
+// agents_dynamics.cpp:250-270, integer-exact against the oracle's table). The continuous inverse
+// CDF gives the position in the table to within a step or two; the table itself decides.
 __device__ __forceinline__ uint32_t sbc_geometric_k(const uint32_t *__restrict__ thr, uint32_t n,
-                                                    uint32_t r) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (r < __ldg(thr + mid)) hi = mid; else lo = mid + 1;
-    }
+                                                    uint32_t r, float inv_log2q) {
+    const float one_minus_u = fmaxf((float)(~r) * (1.0f / 4294967296.0f), 1e-12f);
+    const float kf = __log2f(one_minus_u) * inv_log2q;
+    uint32_t lo = (uint32_t)fminf(fmaxf(kf, 0.f), (float)n);   // ~ #{j : thr[j] <= r}
+    while (lo < n && __ldg(thr + lo) <= r) lo++;
+    while (lo > 0 && __ldg(thr + lo - 1) > r) lo--;
     return lo + 1;
+}
+
+__device__ __forceinline__ float sbc_rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -284,7 +292,7 @@ __device__ __forceinline__ float sbc_force_change(float px, float py, float R, f
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void sbc_decide(const AgentState &a, const RowAcc &acc, double u_social,
                                            float u_dir, const DevParams &P, float &fx, float &fy,
-                                           float &force_mag, uint32_t &fl) {
+                                           float &force_mag, uint32_t &fl, const int BC) {
     float gx = 0.f, gy = 0.f;
     force_mag = P.soc;
     if (u_social <= P.d_prob_social) {  // :35, taken in FP64: u = r * 2^-32 is exact
@@ -322,7 +330,7 @@ __device__ __forceinline__ void sbc_decide(const AgentState &a, const RowAcc &ac
             sincosf(SBC_TWO_PI_F * u_dir, &gy, &gx);
         }
     }
-    if (P.BC >= 5) {  // :93-117
+    if (BC >= 5) {  // :93-117
         const WallCoef w = sbc_wall_coef(a.stb, P);
         const float px = a.x + w.A * a.vx, py = a.y + w.A * a.vy;
         const float R = w.B * force_mag;
@@ -347,9 +355,9 @@ __device__ __forceinline__ void sbc_decide(const AgentState &a, const RowAcc &ac
 // rounding that x + L would cost in FP32).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool sbc_boundary(float &x, float &y, float &vx, float &vy, float &phi,
-                                             const DevParams &P) {
+                                             const DevParams &P, const int BC) {
     const float L = P.L;
-    switch (P.BC) {
+    switch (BC) {
     case 0: {
         if (x < 0.f) x += L; else if (x >= L) x -= L;
         if (y < 0.f) y += L; else if (y >= L) y -= L;
@@ -365,7 +373,7 @@ __device__ __forceinline__ bool sbc_boundary(float &x, float &y, float &vx, floa
             x -= 2.f * diff * nx;
             y -= 2.f * diff * ny;
             const float vn = nx * vx + ny * vy;
-            const float g = (P.BC == 5) ? 2.f * vn : vn;
+            const float g = (BC == 5) ? 2.f * vn : vn;
             vx -= g * nx;
             vy -= g * ny;
             phi = atan2f(vy, vx);  // u = v/|v|, phi = atan2(u) (:447-449, :467-469)
@@ -425,7 +433,7 @@ __device__ __forceinline__ void sbc_sincos_small(float d, float &s, float &c) {
 }
 
 __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc, double u_social, float u_dir,
-                                               uint32_t k_next, const DevParams &P, uint32_t &fl) {
+                                               uint32_t k_next, const DevParams &P, uint32_t &fl, const int BC) {
     float &cu = a.cu, &su = a.su;
     // (cu, su) = (cos, sin)(a.phi) on entry and on exit. The reference recomputes u from phi at
     // every step (:197,:227-228); here the cached vector is turned by the step's small heading
@@ -438,7 +446,7 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc,
     if (first) {
         fl |= SBC_FL_BURST_START;
         sincosf(a.phi, &su, &cu);
-        sbc_decide(a, acc, u_social, u_dir, P, fx, fy, force_mag, fl);
+        sbc_decide(a, acc, u_social, u_dir, P, fx, fy, force_mag, fl, BC);
         a.fx = fx;
         a.fy = fy;
     } else if (bursting) {
@@ -464,7 +472,7 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc,
         sincosf(lphi, &sl, &cl);
     }
     const float forcep = -fx * sl + fy * cl;
-    const float turn = __fdividef(P.alphaTurn * forcep * P.dt, vproj_old);  // :215 (old vproj)
+    const float turn = P.alphaTurn * forcep * P.dt * sbc_rcp_fast(vproj_old);  // :215 (old vproj)
     lphi += turn;
     float sn, cn;
     if (!hack && fabsf(turn) < 0.25f) {
@@ -481,7 +489,7 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc,
         // through their cosines; an argument outside [-1,1] is NaN in the reference (every
         // comparison false) - reproduced by the `ok` predicates, with a rounding allowance of
         // 1e-6 so that |cos| = 1 + ulp is not mistaken for it.
-        const float inv = 1.f / force_mag;
+        const float inv = (force_mag == P.soc) ? P.inv_soc : P.inv_env;
         const float c0 = (cu * fx + su * fy) * inv;  // cos(angle(u_old, F))
         const float c1 = (cn * fx + sn * fy) * inv;  // cos(angle(u_new, F))
         const float c01 = cn * cu + sn * su;         // cos(angle(u_new, u_old))
@@ -508,8 +516,8 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc,
     a.x += a.vx * P.dt;
     a.y += a.vy * P.dt;
     bool hit = false;
-    if (P.BC != -1) {  // :247
-        hit = sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P);
+    if (BC != -1) {  // :247
+        hit = sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P, BC);
         if (hit) fl |= SBC_FL_BOUNDARY;
     }
     if (a.stb == 0) {  // :250-270
@@ -518,7 +526,7 @@ __device__ __forceinline__ void sbc_agent_step(AgentState &a, const RowAcc &acc,
         a.stb = k_next;
     }
     if (hit) {  // :272 - the second Boundary call can only act when the first one did
-        sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P);
+        sbc_boundary(a.x, a.y, a.vx, a.vy, a.phi, P, BC);
         sincosf(a.phi, &su, &cu);
     }
 }

@@ -41,15 +41,18 @@ __device__ __forceinline__ void draw_decisions(const DevParams &P, const DevStat
     const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
     u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
     u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
-    if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z);
+    if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z, P.inv_log2q);
 }
 
 // ------------------------------------------------------------------------------------------------
 // N <= 32 : swarms inside a warp
 // ------------------------------------------------------------------------------------------------
-template <int TPS>
+constexpr int BC_RUNTIME = -99;   // template value: take the boundary condition from the parameters
+
+template <int TPS, int BCT>
 __global__ void __launch_bounds__(128)
 swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
+    const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
     constexpr int SPW = 32 / TPS;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -83,7 +86,7 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             float ux = 0.f, uy = 0.f;
             if (has && alive && lane != src) {  // pair (row src <- me)
                 float dx = a.x - xi, dy = a.y - yi;
-                if (P.BC == 0) {
+                if (BC == 0) {
                     dx = sbc_delta_pbc(xi, a.x, P);
                     dy = sbc_delta_pbc(yi, a.y, P);
                 }
@@ -131,7 +134,7 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             const bool rearm = a.stb <= 1;
             if (first || rearm) draw_decisions(P, S, g, rep, t, s, rearm, u_social, u_dir, k_next);
             uint32_t fl = 0;
-            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
+            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, BC);
             flags_acc |= fl;
         }
     }
@@ -256,7 +259,7 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
             const bool rearm = a.stb <= 1;
             if (first || rearm) draw_decisions(P, S, g, rep, t, s, rearm, u_social, u_dir, k_next);
             uint32_t fl = 0;
-            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
+            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
             flags_acc |= fl;
         }
     }
@@ -281,9 +284,18 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         const long long warps = ((long long)S.R + spw - 1) / spw;
         const int wpb = 4;
         const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-        if (tps == 8) swarm_warp_kernel<8><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);
-        else if (tps == 16) swarm_warp_kernel<16><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);
-        else swarm_warp_kernel<32><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);
+#define SBC_WARP_LAUNCH(T, B) swarm_warp_kernel<T, B><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns)
+#define SBC_WARP_BC(T)                                                  \
+    do {                                                                \
+        if (P.BC == 6) SBC_WARP_LAUNCH(T, 6);                           \
+        else if (P.BC == 0) SBC_WARP_LAUNCH(T, 0);                      \
+        else SBC_WARP_LAUNCH(T, BC_RUNTIME);                            \
+    } while (0)
+        if (tps == 8) SBC_WARP_BC(8);
+        else if (tps == 16) SBC_WARP_BC(16);
+        else SBC_WARP_BC(32);
+#undef SBC_WARP_BC
+#undef SBC_WARP_LAUNCH
         return true;
     }
     const int nthreads = ((N + 31) / 32) * 32;

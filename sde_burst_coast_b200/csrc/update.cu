@@ -45,7 +45,7 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
         const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
         u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
         u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
-        if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z);
+        if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z, P.inv_log2q);
     }
     if (first) {
         const float4 *ac = reinterpret_cast<const float4 *>(S.acc + g * 8);
@@ -71,7 +71,7 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
         }
     }
     uint32_t fl = 0;
-    sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl);
+    sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
     S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
     S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
     S.force[g] = make_float2(a.fx, a.fy);
