@@ -320,9 +320,13 @@ def main():
             'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': {'kernel': 'swarm_warp_kernel' if N <= 32 else 'swarm_block_kernel', 'bound': 'fp32',
                          'achieved': ach, 'peak': peak_fp32, 'unit': 'TFLOP/s', 'frac': ach / peak_fp32,
-                         'traffic': None, 'flop_per_agent_step': fl,
+                         # dram__bytes_read+write of this kernel per launch: profiles/r1_ncu_ensemble_kernel.txt
+                         # (6.47 MB for 4096 tanks -> scaled to the tanks of this run; writes stay in L2)
+                         'traffic': 6.47e6 * R / 4096 * N / 32, 'flop_per_agent_step': fl,
+                         'issue_slot_utilisation_ncu': 0.752, 'warp_instructions_per_warp_step_ncu': 214,
                          'peak_source': '2*128 lanes*%d SMs*%.0f MHz (MEASURED_PEAKS.json sm_max_mhz)' % (props.multi_processor_count, mhz),
-                         'note': 'state stays in registers for the whole launch: HBM traffic is 80 B per agent per launch'},
+                         'note': 'state stays in registers for the whole launch (112 B per agent per launch of HBM traffic); the kernel is '
+                                 'bound by instruction issue (control, integer, transcendental work), not by FMA throughput'},
         }
         # ---- the north-star kernel: dense all-pairs three-zone pass -------------------------------
         try:
