@@ -16,7 +16,8 @@ import numpy as np
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--n', type=int, default=1 << 20)
+    ap.add_argument('--agents', type=int, default=1 << 20, help='total agents (strong scaling) or agents per GPU with --weak')
+    ap.add_argument('--weak', action='store_true', help='agents scale with the number of GPUs')
     ap.add_argument('--rho', type=float, default=0.01)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
@@ -31,7 +32,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    N = args.n
+    N = args.agents * (world if args.weak else 1)
     L = float(np.sqrt(N / args.rho))
     d = base_dict('natPred', N, BC=0, size=L, Npred=0)
     sp, _ = PP.make_sbc_params(d, path=PP.PATH_CELLLIST)
@@ -74,7 +75,7 @@ def main():
         cand = sum(float(v[1]) for v in allv)
         print(json.dumps({
             'metric': 'agent_steps_per_sec', 'workload': 'C5 single swarm, cell list, x-slabs', 'n_agents': N, 'box': L,
-            'n_gpus': world, 'steps': args.steps, 'scaling': 'strong',
+            'n_gpus': world, 'steps': args.steps, 'scaling': 'weak' if args.weak else 'strong',
             'value': N * args.steps / (ms_max * 1e-3), 'us_per_step': 1e3 * ms_max / args.steps,
             'pair_candidates_per_sec': cand / (ms_max * 1e-3), 'wall_s': wall,
             'owned_per_rank': [int(v[2]) for v in allv], 'ghosts_per_rank': [int(v[3]) for v in allv],
