@@ -36,7 +36,8 @@ typedef enum sbc_status {
 
 /* neighbour rule: which candidate set feeds the three-zone filter */
 enum { SBC_NEIGHBOUR_METRIC = 0 /* = InteractionGlobal, agents_interact.cpp:144-157 */,
-       SBC_NEIGHBOUR_VORONOI = 1 /* = InteractionVoronoiF2F, :26-77; not implemented yet */ };
+       SBC_NEIGHBOUR_VORONOI = 1 /* = InteractionVoronoiF2F, :26-77 (the shipped default): Delaunay
+                                    neighbours; non-periodic swarms of <= 1024 agents, no predators */ };
 /* pair-search path */
 enum { SBC_PATH_AUTO = 0, SBC_PATH_ALLPAIRS = 1, SBC_PATH_CELLLIST = 2 };
 

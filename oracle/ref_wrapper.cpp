@@ -128,7 +128,8 @@ static void ref_metric_step(orc_world *w, int64_t s, uint8_t *flags) {
     }
     for (size_t i = 0; i < a.size(); i++) a[i].NN.resize(0);
     for (size_t j = 0; j < preds.size(); j++) { preds[j].NNset.clear(); preds[j].NN.resize(0); }
-    InteractionGlobal(a, SP);
+    if (w->p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) InteractionVoronoiF2F(a, SP);  // agents_interact.cpp:26
+    else InteractionGlobal(a, SP);                                                  // :144
     if (have_pred && !(s < SP->pred_time / dt)) {
         for (size_t i = 0; i < a.size(); i++)
             for (size_t j = 0; j < preds.size(); j++) {
@@ -319,7 +320,8 @@ int64_t orc_pair_interactions(orc_world *w, int flags, int32_t *c_rep, int32_t *
         saved[i] = pa.bin_step;
         if (flags == SBC_PAIR_ALL_ROWS) pa.bin_step = w->SP.burst_steps;  // open the gate :178
     }
-    InteractionGlobal(a, &w->SP);
+    if (w->p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) InteractionVoronoiF2F(a, &w->SP);
+    else InteractionGlobal(a, &w->SP);
     for (size_t i = 0; i < a.size(); i++) a[i].bin_step = saved[i];
     std::vector<const particle *> by_id(w->N, nullptr);
     for (const particle &pa : a) by_id[pa.id] = &pa;

@@ -436,6 +436,61 @@ void interact_all_pairs(orc_world &w, bool gate) {
     }
 }
 
+// Delaunay edge test between alive agents i and j (Voronoi neighbour mode): some circle through both
+// contains no other agent. Centre m + t n on the perpendicular bisector; every other point bounds t
+// from one side; the edge exists iff max(lower) <= min(upper). Same criterion and arithmetic as the
+// brute-force CGAL stand-in the reference build links against (oracle/shims/CGAL/
+// Delaunay_triangulation_2.h), which is what InteractionVoronoiF2F (agents_interact.cpp:26-77) sees.
+bool delaunay_edge(const orc_world &w, int i, int j) {
+    const double ax = w.a[i].x[0], ay = w.a[i].x[1], bx = w.a[j].x[0], by = w.a[j].x[1];
+    const double dx = bx - ax, dy = by - ay;
+    const double len2 = dx * dx + dy * dy;
+    if (len2 == 0) return false;
+    const double mx = 0.5 * (ax + bx), my = 0.5 * (ay + by);
+    const double nx = -dy, ny = dx;
+    double lo = -INFINITY, hi = INFINITY;
+    for (int k = 0; k < w.N; k++) {
+        if (k == i || k == j || w.a[k].dead) continue;
+        const double qx = w.a[k].x[0] - mx, qy = w.a[k].x[1] - my;
+        const double c = qx * qx + qy * qy - 0.25 * len2;
+        const double s = qx * nx + qy * ny;
+        if (s > 0) {
+            const double b = c / (2 * s);
+            if (b < hi) hi = b;
+        } else if (s < 0) {
+            const double b = c / (2 * s);
+            if (b > lo) lo = b;
+        } else if (c < 0) {
+            return false;
+        }
+        if (lo > hi) return false;
+    }
+    return true;
+}
+
+// agents_interact.cpp:26-77 InteractionVoronoiF2F (non-periodic domains): both directions of every
+// Delaunay edge go through IntCalcPrey; a row receives its partners in ascending id
+void interact_voronoi(orc_world &w, bool gate) {
+    const int N = w.N;
+    for (int i = 0; i < N; i++) {
+        if (w.a[i].dead) continue;
+        for (int j = i + 1; j < N; j++) {
+            if (w.a[j].dead) continue;
+            const bool need_i = !gate || w.a[i].bin_step == w.p.burst_steps;
+            const bool need_j = !gate || w.a[j].bin_step == w.p.burst_steps;
+            if (!need_i && !need_j) continue;
+            if (!delaunay_edge(w, i, j)) continue;
+            pair_term(w, w.a[i], w.a[j], j, gate);
+            pair_term(w, w.a[j], w.a[i], i, gate);
+        }
+    }
+}
+
+void interact(orc_world &w, bool gate) {
+    if (w.p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) interact_voronoi(w, gate);
+    else interact_all_pairs(w, gate);
+}
+
 // agents_interact.cpp:252-292 IntCalcPred
 inline void detect_term(orc_world &w, Agent &ai, const Pred &pr, double u_detect) {
     const sbc_params &p = w.p;
@@ -685,7 +740,7 @@ void one_step(orc_world &w, int64_t s, uint8_t *flags) {
     }
     for (Agent &a : w.a) a.nn.clear();  // :172-173
     // :179-182 interaction
-    interact_all_pairs(w, true);
+    interact(w, true);
     if (have_pred && !(s < p.pred_time / dt)) {
         for (int i = 0; i < N; i++) {
             Agent &a = w.a[i];
@@ -847,7 +902,7 @@ int64_t orc_pair_interactions(orc_world *w, int flags, int32_t *c_rep, int32_t *
         a.c_rep = a.c_alg = a.c_att = 0;
         a.nn.clear();
     }
-    interact_all_pairs(*w, flags == SBC_PAIR_ACTIVE_ROWS);
+    interact(*w, flags == SBC_PAIR_ACTIVE_ROWS);
     int64_t total = 0;
     for (int i = 0; i < w->N; i++) {
         Agent &a = w->a[i];

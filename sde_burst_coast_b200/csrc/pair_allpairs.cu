@@ -12,11 +12,11 @@
 namespace {
 
 // ---- burst-gated rows ------------------------------------------------------------------------
-__global__ void compact_active_kernel(DevState S, uint32_t burst_steps, int *list, int *count) {
+__global__ void compact_active_kernel(DevState S, uint32_t burst_steps, int all_alive, int *list, int *count) {
     const size_t total = (size_t)S.N * S.R;
     for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total;
          g += (size_t)gridDim.x * blockDim.x) {
-        const bool active = S.alive[g] && S.timers[g].x == burst_steps;
+        const bool active = S.alive[g] && (all_alive || S.timers[g].x == burst_steps);
         if (!active) continue;
         const unsigned m = __activemask();
         const int lane = threadIdx.x & 31;
@@ -58,6 +58,15 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__r
             if (amb) {
                 z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
                 n_amb++;
+            }
+            if (P.voronoi && z < 3) {
+                DelaunayEdge e;
+                sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+                for (int k = 0; k < N; k++) {
+                    const float4 pk = pv[k];
+                    if (k != i && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                }
+                if (!sbc_delaunay_end(e)) z = 3;
             }
             const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
             if (z == 0) {
@@ -125,6 +134,15 @@ __global__ void nn_fill_kernel(const __grid_constant__ DevParams P, DevState S, 
         bool amb;
         int z = sbc_zone_fast(d2, P, amb);
         if (amb) z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
+        if (P.voronoi && z < 3) {
+            DelaunayEdge e;
+            sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+            for (int k = 0; k < N; k++) {
+                const float4 pk = pv[k];
+                if (k != i && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+            }
+            if (!sbc_delaunay_end(e)) z = 3;
+        }
         if (z < 3) nn_idx[w++] = j;
     }
 }
@@ -144,12 +162,12 @@ __global__ void clear_acc_kernel(DevState S) {
 
 // compact the rows that start a burst this step into S.active_list / S.active_count; `clear` also
 // zeroes every row's accumulators (only the test hook reads rows that were not active)
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st) {
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive) {
     const size_t total = (size_t)S.N * S.R;
     const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
     cudaMemsetAsync(S.active_count, 0, sizeof(int), st);
     if (clear) clear_acc_kernel<<<blocks, 256, 0, st>>>(S);
-    compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, S.active_list, S.active_count);
+    compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, all_alive ? 1 : 0, S.active_list, S.active_count);
 }
 
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {

@@ -128,6 +128,7 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
     P.pred_kill = p.pred_kill;
     P.pred_move = p.pred_move;
     P.has_alg_zone = p.alg_range > p.rep_range;
+    P.voronoi = (p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) ? 1 : 0;
     P.seed_lo = (uint32_t)seed;
     P.seed_hi = (uint32_t)(seed >> 32);
     P.replicate_offset = (uint32_t)rep_off;
@@ -167,8 +168,12 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     *out = nullptr;
     if (n_agents < 1 || n_replicates < 1 || n_pred < 0)
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need n_agents >= 1, n_replicates >= 1, n_pred >= 0");
-    if (p->neighbour_mode != SBC_NEIGHBOUR_METRIC)
-        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: only the metric neighbour rule is implemented");
+    if (p->neighbour_mode != SBC_NEIGHBOUR_METRIC && p->neighbour_mode != SBC_NEIGHBOUR_VORONOI)
+        return fail(nullptr, SBC_ERR_INVALID, "sbc_create: unknown neighbour_mode");
+    if (p->neighbour_mode == SBC_NEIGHBOUR_VORONOI && (p->BC == 0 || n_pred > 0 || n_agents > 1024))
+        return fail(nullptr, SBC_ERR_INVALID,
+                    "sbc_create: the Voronoi neighbour rule is implemented for non-periodic swarms of up to 1024 "
+                    "agents without predators (InteractionVoronoiF2F on tanks)");
     if (!(p->dt > 0) || !(p->burst_rate > 0) || !(p->burst_rate * p->dt < 1))
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need dt > 0 and 0 < burst_rate*dt < 1");
     if (!(p->rep_range <= p->alg_range && p->alg_range <= p->att_range))
@@ -319,6 +324,13 @@ static int ensure_dense(sbc_handle *h) {
 
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
 static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false) {
+    if (all_rows && h->P.voronoi) {  // Delaunay-filtered candidates: every alive row through the rows kernel
+        sbc_launch_compact_rows(h->P, h->S, true, h->stream, true);
+        sbc_launch_pair_rows(h->P, h->S, h->stream);
+        h->host_stats[0]++;
+        h->host_stats[7] += 2;
+        return SBC_OK;
+    }
     if (all_rows) {
         if (int rc = ensure_dense(h)) return rc;
         if (resort || !h->dense.sorted_valid) {

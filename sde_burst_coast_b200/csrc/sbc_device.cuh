@@ -35,6 +35,7 @@ struct DevParams {
     uint32_t burst_steps, max_steps;
     int32_t BC, N_confu, pred_kill, pred_move;
     int32_t has_alg_zone;          // alg_range > rep_range
+    int32_t voronoi;               // neighbour candidates = Delaunay edges (InteractionVoronoiF2F) instead of all agents
     // Philox key / ids
     uint32_t seed_lo, seed_hi;
     uint32_t replicate_offset;
@@ -165,6 +166,46 @@ static __device__ __noinline__ int sbc_zone_exact(float xi, float yi, float xj, 
     if (d > P.d_alg && d <= P.d_att) return 2;
     return 3;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Voronoi neighbour mode (InteractionVoronoiF2F, agents_interact.cpp:26-77): j is a candidate of row i
+// iff (i, j) is an edge of the Delaunay triangulation of the alive agents. Edge test without building
+// a triangulation: a circle through p_i and p_j with centre m + t n on their perpendicular bisector
+// is empty iff t lies in an interval that every other agent k narrows from one side; the edge exists
+// iff the interval stays non-empty. Evaluated in FP64 with explicitly rounded operations in the
+// order of the CPU oracles, so the decisions are identical to theirs (min / max over k do not
+// depend on the order in which the k arrive).
+// ---------------------------------------------------------------------------------------------
+struct DelaunayEdge {
+    double mx, my, nx, ny, q4, lo, hi;
+    bool ok;
+};
+__device__ __forceinline__ void sbc_delaunay_begin(DelaunayEdge &e, float xi, float yi, float xj, float yj) {
+    const double ax = xi, ay = yi, bx = xj, by = yj;
+    const double dx = __dsub_rn(bx, ax), dy = __dsub_rn(by, ay);
+    const double len2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    e.mx = __dmul_rn(0.5, __dadd_rn(ax, bx));
+    e.my = __dmul_rn(0.5, __dadd_rn(ay, by));
+    e.nx = -dy;
+    e.ny = dx;
+    e.q4 = __dmul_rn(0.25, len2);
+    e.lo = -INFINITY;
+    e.hi = INFINITY;
+    e.ok = (len2 != 0.0);
+}
+__device__ __forceinline__ void sbc_delaunay_add(DelaunayEdge &e, float xk, float yk) {
+    const double qx = __dsub_rn((double)xk, e.mx), qy = __dsub_rn((double)yk, e.my);
+    const double c = __dsub_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), e.q4);
+    const double s = __dadd_rn(__dmul_rn(qx, e.nx), __dmul_rn(qy, e.ny));
+    if (s > 0.0) {
+        e.hi = fmin(e.hi, __ddiv_rn(c, __dmul_rn(2.0, s)));
+    } else if (s < 0.0) {
+        e.lo = fmax(e.lo, __ddiv_rn(c, __dmul_rn(2.0, s)));
+    } else if (c < 0.0) {
+        e.ok = false;
+    }
+}
+__device__ __forceinline__ bool sbc_delaunay_end(const DelaunayEdge &e) { return e.ok && !(e.lo > e.hi); }
 
 // fast zone from the FP32 squared distance; `amb` is set when d2 falls inside the rounding band
 // of any threshold (then the caller must ask sbc_zone_exact)

@@ -49,7 +49,7 @@ void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev
 
 // --- all-pairs three-zone pass -------------------------------------------------------------------
 // burst-gated rows (bin_step == burst_steps), pair_allpairs.cu: compaction, then all-pairs rows
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st);
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive = false);
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st);
 // burst-gated rows through a cell list (celllist.cu), single large swarm
 struct CellScratch {

@@ -49,7 +49,7 @@ __device__ __forceinline__ void draw_decisions(const DevParams &P, const DevStat
 // ------------------------------------------------------------------------------------------------
 constexpr int BC_RUNTIME = -99;   // template value: take the boundary condition from the parameters
 
-template <int TPS, int BCT>
+template <int TPS, int BCT, bool VOR>
 __global__ void __launch_bounds__(128)
 swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
     const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
@@ -101,6 +101,18 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
                 ux = dx * rinv;
                 uy = dy * rinv;
                 n_pairs++;
+            }
+            if (VOR) {  // keep only Delaunay neighbours of the row (warp-uniform loop over the tank)
+                DelaunayEdge e;
+                sbc_delaunay_begin(e, xi, yi, a.x, a.y);
+                const unsigned alive_mask = __ballot_sync(FULL, alive);
+                const int seg0 = seg * TPS;
+                for (int k = 0; k < TPS; k++) {
+                    const int lk = seg0 + k;
+                    const float xk = __shfl_sync(FULL, a.x, lk), yk = __shfl_sync(FULL, a.y, lk);
+                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, xk, yk);
+                }
+                if (z < 3 && !sbc_delaunay_end(e)) z = 3;
             }
             const int cr = __popc(__ballot_sync(FULL, z == 0) & segmask);
             const int ca = __popc(__ballot_sync(FULL, z == 1) & segmask);
@@ -218,6 +230,15 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                             n_amb++;
                         }
                         if (j == row) z = 3;
+                        if (P.voronoi && z < 3) {  // Delaunay edge test against every other agent of the swarm
+                            DelaunayEdge e;
+                            sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+                            for (int k = 0; k < N; k++) {
+                                const float4 pk = pv_s[k];
+                                if (k != row && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                            }
+                            if (!sbc_delaunay_end(e)) z = 3;
+                        }
                         const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
                         if (z == 0) { rx = __fmaf_rn(-dx, rinv, rx); ry = __fmaf_rn(-dy, rinv, ry); cr++; }
                         else if (z == 1) { gx += pj.z; gy += pj.w; ca++; }
@@ -284,7 +305,11 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         const long long warps = ((long long)S.R + spw - 1) / spw;
         const int wpb = 4;
         const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-#define SBC_WARP_LAUNCH(T, B) swarm_warp_kernel<T, B><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns)
+#define SBC_WARP_LAUNCH(T, B)                                                                   \
+    do {                                                                                        \
+        if (P.voronoi) swarm_warp_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns); \
+        else swarm_warp_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);         \
+    } while (0)
 #define SBC_WARP_BC(T)                                                  \
     do {                                                                \
         if (P.BC == 6) SBC_WARP_LAUNCH(T, 6);                           \

@@ -10,7 +10,9 @@
 //                    seeds from the wall clock, swarmdyn.cpp:126-141; 0 or absent = clock)
 //   -y <replicates>  run an ensemble of independent swarms in one process (default 1); replicate r>0
 //                    writes its files with the suffix _<r> after fileID
-// Neighbour rule: METRIC (InteractionGlobal, agents_interact.cpp:144-157) - see DESIGN.md section 2.
+//   -V 1             Voronoi neighbour rule (InteractionVoronoiF2F, agents_interact.cpp:26-77, the shipped
+//                    default of the reference): tanks / open domains of up to 1024 agents without predators
+// Default neighbour rule: METRIC (InteractionGlobal, agents_interact.cpp:144-157) - see DESIGN.md section 2.
 // Output: -J 0 text files exactly as the reference writes them; -J 1 needs libhdf5, which this
 // image does not have: the run then warns once and writes the text files instead.
 #include <algorithm>
@@ -42,6 +44,7 @@ struct HostParams {  // the fields of `params` (src/agents.h:83-148) the host si
     std::string location, fileID;
     uint64_t seed;
     int replicates;
+    int voronoi;
 };
 
 const char *cmd_option(char **begin, char **end, const std::string &opt) {  // input_output.cpp:108-114
@@ -89,6 +92,7 @@ void parse_parameters(int argc, char **argv, HostParams &p) {  // input_output.c
     p.seed = strtoull(cmd_option(b, e, "-Z"), nullptr, 10);
     p.replicates = atoi(cmd_option(b, e, "-y"));
     if (p.replicates < 1) p.replicates = 1;
+    p.voronoi = atoi(cmd_option(b, e, "-V"));
 }
 
 void init_system_parameters(HostParams &p) {  // settings.cpp:79-145
@@ -457,7 +461,7 @@ int main(int argc, char **argv) {
     sp.kill_range = p.kill_range; sp.kill_rate = p.kill_rate; sp.noisep = p.noisep; sp.sim_time = p.sim_time;
     sp.trans_time = p.trans_time; sp.burst_steps = (uint32_t)p.burst_steps; sp.BC = p.BC; sp.N_confu = p.N_confu;
     sp.pred_kill = p.pred_kill; sp.pred_move = p.pred_move;
-    sp.neighbour_mode = SBC_NEIGHBOUR_METRIC; sp.path = SBC_PATH_AUTO;
+    sp.neighbour_mode = p.voronoi ? SBC_NEIGHBOUR_VORONOI : SBC_NEIGHBOUR_METRIC; sp.path = SBC_PATH_AUTO;
 
     sbc_handle *h = nullptr;
     int rc = sbc_create(&sp, N, p.Npred, R, p.seed, 0, 0, &h);

@@ -74,3 +74,16 @@ def test_ensemble_flag_runs_replicates(tmp_path):
     a = _rows(tmp_path / 'swarm_xx.dat')
     b = _rows(tmp_path / 'swarm_xx_3.dat')
     assert a.shape == b.shape and a.shape[1] == 16 and not np.allclose(a[:, 3], b[:, 3])
+
+
+def test_voronoi_flag(tmp_path):
+    d = P.get_base_params(0.2, 1, mode='burst_coast')
+    P.selection_line_parameter(d, 2)
+    d.update(out_h5=0, output_mode=0, N=8)
+    _run(d, tmp_path, ['-Z', '3', '-V', '1'])
+    a = _rows(tmp_path / 'swarm_xx.dat')
+    other = tmp_path / 'metric'
+    other.mkdir()
+    _run(d, other, ['-Z', '3'])
+    b = _rows(other / 'swarm_xx.dat')
+    assert a.shape == b.shape and not np.allclose(a[-1, 3:5], b[-1, 3:5])   # different neighbour rule, different run
