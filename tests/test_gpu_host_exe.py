@@ -87,3 +87,39 @@ def test_voronoi_flag(tmp_path):
     _run(d, other, ['-Z', '3'])
     b = _rows(other / 'swarm_xx.dat')
     assert a.shape == b.shape and not np.allclose(a[-1, 3:5], b[-1, 3:5])   # different neighbour rule, different run
+
+
+def _reference_main(argv, cwd):
+    """Run the reference's own main() (oracle/_ref, swarmdyn.cpp:33-97 with the shipped Voronoi drivers
+    and its clock-seeded mt19937 stream) in a child process."""
+    import sys
+    code = ("import ctypes\nlib = ctypes.CDLL(%r)\nargv = %r\n"
+            "arr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])\n"
+            "lib.orc_ref_swarmdyn_main.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_char_p)]\n"
+            "lib.orc_ref_swarmdyn_main(len(argv), arr)\n") % (os.path.join(ROOT, 'oracle', '_ref', 'liborc_ref.so'), argv)
+    subprocess.run([sys.executable, '-c', code], cwd=cwd, check=True, stdout=subprocess.DEVNULL, timeout=600)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, 'oracle', '_ref', 'liborc_ref.so')), reason='oracle/_ref not built')
+def test_c1_statistics_match_the_shipped_reference_binary(tmp_path):
+    """Config C1 end to end against the reference's OWN main(): same argv, Voronoi neighbour rule on both
+    sides, text output; time- and ensemble-averaged observables of /swarm agree within 4 standard errors."""
+    d = P.get_base_params(5, 15, mode='burst_coast')
+    P.selection_line_parameter(d, 2)
+    d.update(out_h5=0, output_mode=0, N=8)
+    cols = {'pol_order': 1, 'avg_speed': 7, 'NND': 13, 'IID': 14}
+    ref_runs = []
+    for k in range(10):
+        rd = tmp_path / ('ref%d' % k)
+        rd.mkdir()
+        _reference_main(P.dic2swarmdyn_command(d).split(), rd)
+        ref_runs.append(_rows(rd / 'swarm_xx.dat'))
+    R = 96
+    _run(d, tmp_path, ['-Z', '21', '-y', str(R), '-V', '1'])
+    ours = [_rows(tmp_path / ('swarm_xx.dat' if r == 0 else 'swarm_xx_%d.dat' % r)) for r in range(R)]
+    assert ours[0].shape == ref_runs[0].shape
+    for name, c in cols.items():
+        a = np.array([run[:, c].mean() for run in ref_runs])
+        b = np.array([run[:, c].mean() for run in ours])
+        se = np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size)
+        assert abs(a.mean() - b.mean()) <= 4 * se + 0.01 * abs(a.mean()), (name, a.mean(), b.mean(), se)
