@@ -93,21 +93,23 @@ __global__ void cell_bounds_kernel(const uint32_t *__restrict__ key, const int *
     if (r == n - 1 || key[r + 1] != k) cell_end[k] = r + 1;
 }
 
+constexpr int CELLS_THREADS = 128;  // one block per active row
+
 template <bool PERIODIC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                   const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                   const float4 *__restrict__ spv, const int *__restrict__ sidx,
                   const int *__restrict__ list, const int *__restrict__ count) {
+    __shared__ float shf[CELLS_THREADS / 32][6];
+    __shared__ int shi[CELLS_THREADS / 32][3];
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_rows = *count;
     const CellGeom g = *geom;
     unsigned n_amb = 0;
     unsigned long long n_cand = 0;
-    for (int k = warp; k < n_rows; k += n_warps) {
-        const int i = list[k];  // single swarm on this path: g == i
+    for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
+        const int i = list[k];  // single swarm on this path: slot index == global index
         const float4 pi = S.pv[i];
         const int cx = cell_coord(pi.x, g.ox, g.inv_w, g.ncx), cy = cell_coord(pi.y, g.oy, g.inv_h, g.ncy);
         RowAcc A;
@@ -120,8 +122,8 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
                 if (PERIODIC) xx = (xx + g.ncx) % g.ncx; else if (xx < 0 || xx >= g.ncx) continue;
                 const int c = yy * g.ncx + xx;
                 const int r0 = cell_start[c], r1 = cell_end[c];
-                n_cand += (lane == 0) ? (unsigned long long)(r1 - r0) : 0ull;
-                for (int r = r0 + lane; r < r1; r += 32) {
+                n_cand += (threadIdx.x == 0) ? (unsigned long long)(r1 - r0) : 0ull;
+                for (int r = r0 + threadIdx.x; r < r1; r += CELLS_THREADS) {
                     if (sidx[r] == i) continue;
                     const float4 pj = spv[r];
                     float dx = pj.x - pi.x, dy = pj.y - pi.y;
@@ -153,31 +155,18 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
                 }
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o);
-            A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
-            A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o);
-            A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
-            A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o);
-            A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
-        }
-        const int cr = __reduce_add_sync(0xffffffffu, A.c_rep);
-        const int ca = __reduce_add_sync(0xffffffffu, A.c_alg);
-        const int ct = __reduce_add_sync(0xffffffffu, A.c_att);
-        if (lane == 0) {
+        sbc_block_reduce_row<CELLS_THREADS / 32>(A, shf, shi);
+        if (threadIdx.x == 0) {
             float4 *acc = reinterpret_cast<float4 *>(S.acc + (size_t)i * 8);
             acc[0] = make_float4(A.rep_x, A.rep_y, A.alg_x, A.alg_y);
             S.acc[(size_t)i * 8 + 4] = A.att_x;
             S.acc[(size_t)i * 8 + 5] = A.att_y;
-            *reinterpret_cast<int4 *>(S.cnt + (size_t)i * 4) = make_int4(cr, ca, ct, 0);
+            *reinterpret_cast<int4 *>(S.cnt + (size_t)i * 4) = make_int4(A.c_rep, A.c_alg, A.c_att, 0);
         }
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
-    if (lane == 0) {
-        if (n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
-        if (n_cand) atomicAdd(S.stats + 3, n_cand);  // candidates examined on this path
-    }
+    if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
+    if (threadIdx.x == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);  // candidates examined on this path
 }
 
 }  // namespace
@@ -248,11 +237,11 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
 // active rows must have been compacted into S.active_list / S.active_count (sbc_launch_compact_rows)
 void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st) {
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
-    const int blocks = 148 * 8;
+    const int blocks = (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
     if (P.BC == 0)
-        pair_cells_kernel<true><<<blocks, 256, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
+        pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
                                                         S.active_list, S.active_count);
     else
-        pair_cells_kernel<false><<<blocks, 256, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
+        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
                                                          S.active_list, S.active_count);
 }

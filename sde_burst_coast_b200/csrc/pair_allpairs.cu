@@ -28,23 +28,25 @@ __global__ void compact_active_kernel(DevState S, uint32_t burst_steps, int all_
     }
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int ROWS_THREADS = 128;  // one block per active row
+
+__global__ void __launch_bounds__(ROWS_THREADS)
 pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__restrict__ list,
                  const int *__restrict__ count) {
+    __shared__ float shf[ROWS_THREADS / 32][6];
+    __shared__ int shi[ROWS_THREADS / 32][3];
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int n_rows = *count;
     const int N = S.N;
-    unsigned long long n_amb = 0;
-    for (int k = warp; k < n_rows; k += n_warps) {
+    unsigned n_amb = 0;
+    for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
         const int g = list[k];
         const int rep = g / N, i = g - rep * N;
         const float4 *pv = S.pv + (size_t)rep * N;
         const float4 pi = pv[i];
         RowAcc A;
         row_acc_clear(A);
-        for (int j = lane; j < N; j += 32) {
+        for (int j = threadIdx.x; j < N; j += ROWS_THREADS) {
             if (j == i) continue;
             const float4 pj = pv[j];
             float dx = pj.x - pi.x, dy = pj.y - pi.y;
@@ -62,9 +64,9 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__r
             if (P.voronoi && z < 3) {
                 DelaunayEdge e;
                 sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
-                for (int k = 0; k < N; k++) {
-                    const float4 pk = pv[k];
-                    if (k != i && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                for (int kk = 0; kk < N; kk++) {
+                    const float4 pk = pv[kk];
+                    if (kk != i && kk != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
                 }
                 if (!sbc_delaunay_end(e)) z = 3;
             }
@@ -83,28 +85,17 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__r
                 A.c_att++;
             }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o);
-            A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
-            A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o);
-            A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
-            A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o);
-            A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
-        }
-        const int cr = __reduce_add_sync(0xffffffffu, A.c_rep);
-        const int ca = __reduce_add_sync(0xffffffffu, A.c_alg);
-        const int ct = __reduce_add_sync(0xffffffffu, A.c_att);
-        if (lane == 0) {
+        sbc_block_reduce_row<ROWS_THREADS / 32>(A, shf, shi);
+        if (threadIdx.x == 0) {
             float *acc = S.acc + (size_t)g * 8;
             int *cnt = S.cnt + (size_t)g * 4;
             acc[0] = A.rep_x; acc[1] = A.rep_y; acc[2] = A.alg_x; acc[3] = A.alg_y;
             acc[4] = A.att_x; acc[5] = A.att_y;
-            cnt[0] = cr; cnt[1] = ca; cnt[2] = ct;
+            cnt[0] = A.c_rep; cnt[1] = A.c_alg; cnt[2] = A.c_att;
         }
     }
-    n_amb = __reduce_add_sync(0xffffffffu, (unsigned)n_amb);
-    if (lane == 0 && n_amb) atomicAdd(S.stats + 4, n_amb);
+    n_amb = __reduce_add_sync(0xffffffffu, n_amb);
+    if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(S.stats + 3, (unsigned long long)n_rows * (unsigned long long)(N - 1));
 }
@@ -171,7 +162,11 @@ void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, 
 }
 
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {
-    pair_rows_kernel<<<148 * 4, 256, 0, st>>>(P, S, S.active_list, S.active_count);
+    // grid: enough blocks for the synchronised first burst (every row active), few enough to be cheap
+    // to launch when only a handful of rows start a burst
+    const size_t total = (size_t)S.N * S.R;
+    const int blocks = (int)min((size_t)148 * 8, max((size_t)16, total / 64));
+    pair_rows_kernel<<<blocks, ROWS_THREADS, 0, st>>>(P, S, S.active_list, S.active_count);
 }
 
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,

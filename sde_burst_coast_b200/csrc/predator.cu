@@ -110,6 +110,59 @@ __device__ __forceinline__ void kill_agent(DevState &S, size_t g, float4 p) {
     S.pv[g] = make_float4(qnan, qnan, p.z, p.w);
 }
 
+// MoveFishNet (agents_dynamics.cpp:616-624): one block per replicate
+__global__ void __launch_bounds__(PT)
+net_move_kernel(const __grid_constant__ DevParams P, DevState S) {
+    const int rep = blockIdx.x;
+    float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
+    float *pphi = S.pred_phi + (size_t)rep * S.Npred;
+    for (int j = threadIdx.x; j < S.Npred; j += PT) {
+        float4 p = pp[j];
+        float ph = pphi[j];
+        p.x += p.z * P.dt;
+        p.y += p.w * P.dt;
+        sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
+        pp[j] = p;
+        pphi[j] = ph;
+    }
+}
+
+// FishNetKill (agents_dynamics.cpp:780-820): grid (agent chunks, replicates); predicates in FP64
+__global__ void __launch_bounds__(PT)
+net_kill_kernel(const __grid_constant__ DevParams P, DevState S) {
+    __shared__ int s_killed;
+    const int rep = blockIdx.y;
+    const int N = S.N;
+    float4 *pv = S.pv + (size_t)rep * N;
+    const float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
+    if (threadIdx.x == 0) s_killed = 0;
+    __syncthreads();
+    const float4 p0 = pp[0], p1 = pp[1];
+    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
+    if (P.BC == 0) { vn[0] = min_image_d(vn[0], P.dL); vn[1] = min_image_d(vn[1], P.dL); }
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
+    const double net_len = (double)(S.Npred - 1) * dist;
+    float s0, c0;
+    sincosf(S.pred_phi[(size_t)rep * S.Npred], &s0, &c0);
+    const double mv[2] = {(double)c0, (double)s0};
+    int killed = 0;
+    for (int i = blockIdx.x * PT + threadIdx.x; i < N; i += gridDim.x * PT) {
+        const float4 p = pv[i];
+        if (p.x != p.x) continue;
+        double r[2] = {__dsub_rn((double)p.x, (double)p0.x), __dsub_rn((double)p.y, (double)p0.y)};
+        if (P.BC == 0) { r[0] = min_image_d(r[0], P.dL); r[1] = min_image_d(r[1], P.dL); }
+        const double front = __dadd_rn(__dmul_rn(mv[0], r[0]), __dmul_rn(mv[1], r[1]));
+        const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
+        if (front > 0 && front < P.d_kill_range && side > 0 && side <= net_len) {
+            kill_agent(S, (size_t)rep * N + i, p);
+            killed++;
+        }
+    }
+    if (killed) atomicAdd(&s_killed, killed);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_killed) atomicAdd(S.n_dead + rep, s_killed);
+}
+
 __global__ void __launch_bounds__(PT)
 pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
                       const uint32_t *__restrict__ step_dev) {
@@ -125,41 +178,7 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
     float *pphi = S.pred_phi + (size_t)rep * S.Npred;
     if (threadIdx.x == 0) s_killed = 0;
     if (S.Npred > 1) {
-        // MoveFishNet
-        for (int j = threadIdx.x; j < S.Npred; j += PT) {
-            float4 p = pp[j];
-            float ph = pphi[j];
-            p.x += p.z * P.dt;
-            p.y += p.w * P.dt;
-            sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
-            pp[j] = p;
-            pphi[j] = ph;
-        }
-        __syncthreads();
-        if (P.pred_kill != 0) {  // FishNetKill
-            const float4 p0 = pp[0], p1 = pp[1];
-            double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
-            if (P.BC == 0) { vn[0] = min_image_d(vn[0], P.dL); vn[1] = min_image_d(vn[1], P.dL); }
-            const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
-            const double net_len = (double)(S.Npred - 1) * dist;
-            float s0, c0;
-            sincosf(pphi[0], &s0, &c0);
-            const double mv[2] = {(double)c0, (double)s0};
-            int killed = 0;
-            for (int i = threadIdx.x; i < N; i += PT) {
-                const float4 p = pv[i];
-                if (p.x != p.x) continue;
-                double r[2] = {__dsub_rn((double)p.x, (double)p0.x), __dsub_rn((double)p.y, (double)p0.y)};
-                if (P.BC == 0) { r[0] = min_image_d(r[0], P.dL); r[1] = min_image_d(r[1], P.dL); }
-                const double front = __dadd_rn(__dmul_rn(mv[0], r[0]), __dmul_rn(mv[1], r[1]));
-                const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
-                if (front > 0 && front < P.d_kill_range && side > 0 && side <= net_len) {
-                    kill_agent(S, (size_t)rep * N + i, p);
-                    killed++;
-                }
-            }
-            if (killed) atomicAdd(&s_killed, killed);
-        }
+        // fish nets are handled by net_move_kernel + net_kill_kernel (grid over the agents)
     } else {
         // MovePredator
         const float4 p0 = pp[0];
@@ -268,5 +287,13 @@ void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step
 }
 void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
                                cudaStream_t st) {
+    if (S.Npred > 1) {
+        net_move_kernel<<<S.R, PT, 0, st>>>(P, S);
+        if (P.pred_kill != 0) {
+            const int chunks = min(148 * 4, (S.N + PT - 1) / PT);
+            net_kill_kernel<<<dim3(chunks, S.R), PT, 0, st>>>(P, S);
+        }
+        return;
+    }
     pred_move_kill_kernel<<<S.R, PT, 0, st>>>(P, S, (uint32_t)step, step_dev);
 }

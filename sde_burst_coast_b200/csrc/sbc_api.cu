@@ -521,14 +521,28 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     const double dt = p.dt;
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (injected && n_steps != 1) return fail(h, SBC_ERR_STATE, "sbc_step: injected decisions hold for one step");
-    const bool block_path = !h->force_multikernel && S.N <= 1024 && S.Npred == 0 &&
-                            p.path != SBC_PATH_CELLLIST;
+    const bool block_path = !h->force_multikernel && S.N <= 1024 && S.Npred <= 1024 &&
+                            p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
+    // predator schedule in step indices (swarmdyn.cpp:153-170)
+    long long s_pred = -1;
+    int s_trunc = 0, needed = 0;
+    if (S.Npred > 0) {
+        const double x = p.pred_time / dt;
+        s_pred = (long long)std::floor(x);
+        while ((double)s_pred < x) s_pred++;
+        if (s_pred < 0) s_pred = 0;
+        s_trunc = (int)x;
+        if (S.Npred > 1) {
+            if (p.pred_speed0 > 0) needed = (int)(p.sizeL / 2 / (p.pred_speed0 * dt));
+            else needed = (int)((p.sim_time - p.trans_time) / 4 / dt);
+        }
+    }
     if (block_path) {
         // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
         int64_t done = 0;
         while (done < n_steps) {
             const int64_t chunk = (n_steps - done > (1ll << 30)) ? (1ll << 30) : (n_steps - done);
-            sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream);
+            sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed);
             done += chunk;
             h->host_stats[2]++;
         }

@@ -167,6 +167,40 @@ static __device__ __noinline__ int sbc_zone_exact(float xi, float yi, float xj, 
     return 3;
 }
 
+// Sum the zone accumulators of one row over a thread block in a fixed order (lanes by xor tree, then
+// warps in index order): the result does not depend on scheduling. `sh` holds 9 words per warp.
+// Returns the totals in thread 0 (other threads get partial data).
+template <int NWARPS>
+__device__ __forceinline__ void sbc_block_reduce_row(RowAcc &A, float (*shf)[6], int (*shi)[3]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o);
+        A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
+        A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o);
+        A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
+        A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o);
+        A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
+    }
+    A.c_rep = __reduce_add_sync(0xffffffffu, A.c_rep);
+    A.c_alg = __reduce_add_sync(0xffffffffu, A.c_alg);
+    A.c_att = __reduce_add_sync(0xffffffffu, A.c_att);
+    __syncthreads();  // previous row's readers are done with the buffers
+    if (lane == 0) {
+        shf[warp][0] = A.rep_x; shf[warp][1] = A.rep_y; shf[warp][2] = A.alg_x;
+        shf[warp][3] = A.alg_y; shf[warp][4] = A.att_x; shf[warp][5] = A.att_y;
+        shi[warp][0] = A.c_rep; shi[warp][1] = A.c_alg; shi[warp][2] = A.c_att;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < NWARPS; w++) {
+            A.rep_x += shf[w][0]; A.rep_y += shf[w][1]; A.alg_x += shf[w][2];
+            A.alg_y += shf[w][3]; A.att_x += shf[w][4]; A.att_y += shf[w][5];
+            A.c_rep += shi[w][0]; A.c_alg += shi[w][1]; A.c_att += shi[w][2];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Voronoi neighbour mode (InteractionVoronoiF2F, agents_interact.cpp:26-77): j is a candidate of row i
 // iff (i, j) is an edge of the Delaunay triangulation of the alive agents. Edge test without building

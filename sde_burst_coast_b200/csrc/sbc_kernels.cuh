@@ -124,8 +124,10 @@ void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long 
 
 // --- one block per swarm, many steps per launch (swarm_block.cu) -------------------------------
 // returns false when the configuration does not fit this path (N > 1024)
-bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first,
-                            long long n_steps, cudaStream_t st);
+// predators (if any): s_pred = first step with s >= pred_time/dt, s_trunc = (int)(pred_time/dt),
+// needed = fish-net re-spawn period in steps (0 = none)
+bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
+                            cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 
 // --- observables (observables.cu) --------------------------------------------------------------
 void sbc_launch_observables(const DevParams &P, const DevState &S, double *out_dev, cudaStream_t st);

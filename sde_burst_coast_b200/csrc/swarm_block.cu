@@ -167,34 +167,156 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
 // ------------------------------------------------------------------------------------------------
 struct RowResult {
     float v0, v1, v2, v3;
-    int cr, ca, ct, pad;
+    int cr, ca, ct, cf;
 };
 
-__global__ void __launch_bounds__(1024)
-swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
+// block-wide helpers (nwarps <= 32); every thread of the block must call them
+__device__ __forceinline__ double block_sum_d(double v, double *sh, int nwarps) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < nwarps; w++) t += sh[w];
+    return t;
+}
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long *sh, int nwarps) {
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = ~0ull;
+    for (int w = 0; w < nwarps; w++) t = min(t, sh[w]);
+    return t;
+}
+__device__ __forceinline__ double min_image_dd(double r, double L) {  // mathtools.h:64-71 in FP64
+    const double s = (double)((0.0 < r) - (r < 0.0));
+    const double h = __ddiv_rn(__dmul_rn(s, L), 2.0);
+    return __dsub_rn(fmod(__dadd_rn(r, h), L), h);
+}
+
+// CreatePredator / CreateFishNet (agents_dynamics.cpp:534-555, 485-528) by the whole block:
+// GetCenterOfMass (agents_operation.cpp:23-127) of the alive agents, then the predators into pred_s
+__device__ void block_spawn(const DevParams &P, int NP, uint32_t rep, uint32_t step, uint32_t slot, bool alive,
+                            const AgentState &a, float4 *pred_s, float *pphi_s, double *red_s, int nwarps) {
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0, cnt = alive ? 1.0 : 0.0;
+    if (alive) {
+        if (P.BC == 0) {
+            const float scaling = SBC_TWO_PI_F * P.invL;
+            float sn, cs;
+            sincosf(scaling * a.x, &sn, &cs); c0 = cs; c1 = sn;
+            sincosf(scaling * a.y, &sn, &cs); c2 = cs; c3 = sn;
+        } else {
+            c0 = a.x;
+            c2 = a.y;
+        }
+    }
+    c0 = block_sum_d(c0, red_s, nwarps); c1 = block_sum_d(c1, red_s, nwarps);
+    c2 = block_sum_d(c2, red_s, nwarps); c3 = block_sum_d(c3, red_s, nwarps);
+    cnt = block_sum_d(cnt, red_s, nwarps);
+    float comx, comy;
+    if (P.BC == 0) {
+        comx = (float)((atan2(-c1 / cnt, -c0 / cnt) + SBC_PI_D) / (2 * SBC_PI_D / P.dL));
+        comy = (float)((atan2(-c3 / cnt, -c2 / cnt) + SBC_PI_D) / (2 * SBC_PI_D / P.dL));
+    } else {
+        comx = (float)(c0 / cnt);
+        comy = (float)(c2 / cnt);
+    }
+    const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, step, slot);
+    const float u0 = (float)((double)q.x * (1.0 / 4294967296.0));
+    const float u1 = (float)((double)q.y * (1.0 / 4294967296.0));
+    if (NP == 1) {
+        if (threadIdx.x == 0) {
+            float phi = u0 * SBC_TWO_PI_F, sn, cs;
+            sincosf(phi, &sn, &cs);
+            float x = comx - 0.5f * P.L * cs, y = comy - 0.5f * P.L * sn;
+            float vx = P.pred_speed * cs, vy = P.pred_speed * sn;
+            sbc_boundary(x, y, vx, vy, phi, P, P.BC);
+            pred_s[0] = make_float4(x, y, vx, vy);
+            pphi_s[0] = phi;
+        }
+    } else {
+        float phi = SBC_TWO_PI_F * u0, sn, cs;
+        sincosf(phi, &sn, &cs);
+        float sx = comx - 0.25f * P.L * cs, sy = comy - 0.25f * P.L * sn;
+        const float var_noise = SBC_PI_F / 4.f;
+        phi += var_noise * u1 - 0.5f * var_noise;
+        sincosf(phi, &sn, &cs);
+        const float px = sn, py = -cs;  // vec_perp(v_net_move), mathtools.h:183-189
+        const float net_len = 0.25f * P.L;
+        sx -= 0.5f * net_len * px;
+        sy -= 0.5f * net_len * py;
+        const float net_dist = net_len / (float)(NP - 1);
+        for (int j = threadIdx.x; j < NP; j += blockDim.x) {
+            float x = sx + px * ((float)j * net_dist), y = sy + py * ((float)j * net_dist);
+            float vx = P.pred_speed * cs, vy = P.pred_speed * sn, ph = phi;
+            sbc_boundary(x, y, vx, vy, ph, P, P.BC);
+            pred_s[j] = make_float4(x, y, vx, vy);
+            pphi_s[j] = ph;
+        }
+    }
+    __syncthreads();
+}
+
+// when the predators of a swarm appear and re-appear, in step indices (host-evaluated, swarmdyn.cpp:153-170)
+struct PredSchedule {
+    uint32_t s_pred;    // first step with s >= pred_time/dt
+    int32_t s_trunc;    // (int)(pred_time/dt), origin of the net's re-spawn period
+    int32_t needed;     // re-spawn period in steps (fish net), 0 = never
+};
+
+template <bool PRED, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps,
+                   PredSchedule sched) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xffffffffu;
-    const int N = S.N;
+    const int N = S.N, NP = PRED ? S.Npred : 0;
     const int nthreads = blockDim.x;
     const int nwarps = nthreads >> 5;
     float4 *pv_s = reinterpret_cast<float4 *>(smem_raw);                       // [nthreads]
     RowResult *res_s = reinterpret_cast<RowResult *>(pv_s + nthreads);         // [nthreads]
-    unsigned *act_s = reinterpret_cast<unsigned *>(res_s + nthreads);          // [32]
+    float2 *flee_s = reinterpret_cast<float2 *>(res_s + nthreads);             // [nthreads]
+    double *red_s = reinterpret_cast<double *>(flee_s + nthreads);             // [32]
+    unsigned long long *key_s = reinterpret_cast<unsigned long long *>(red_s + 32);  // [32]
+    unsigned *act_s = reinterpret_cast<unsigned *>(key_s + 32);                // [32]
+    int *n_rows_s = reinterpret_cast<int *>(act_s + 32);                       // [4]
+    unsigned short *rows_s = reinterpret_cast<unsigned short *>(n_rows_s + 4); // [nthreads]
+    float4 *pred_s = reinterpret_cast<float4 *>(rows_s + ((nthreads + 7) / 8) * 8);  // [NP], 16-byte aligned
+    float *pphi_s = reinterpret_cast<float *>(pred_s + NP);                    // [NP]
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int rep = blockIdx.x;
     const bool valid = t < N;
     const size_t g = valid ? ((size_t)rep * N + t) : 0;
     AgentState a = {};
-    bool alive = false;
+    bool alive = false, died = false;
     if (valid) {
         load_agent(S, g, a);
         alive = S.alive[g] != 0;
     }
+    if (PRED) {
+        for (int j = t; j < NP; j += nthreads) {
+            pred_s[j] = S.pred_pv[(size_t)rep * NP + j];
+            pphi_s[j] = S.pred_phi[(size_t)rep * NP + j];
+        }
+        __syncthreads();
+    }
     uint32_t flags_acc = 0;
     unsigned long long n_amb = 0, n_pairs = 0;
+    int n_killed = 0;
+    bool spawned = false;
     const float qnan = __int_as_float(0x7fc00000);
 
     for (uint32_t s = s_first; s != s_first + n_steps; s++) {
+        const bool pred_phase = PRED && (s >= sched.s_pred);
+        if (PRED) {
+            if (s == sched.s_pred) {  // swarmdyn.cpp:153-158
+                block_spawn(P, NP, rep, s, 0, alive, a, pred_s, pphi_s, red_s, nwarps);
+                spawned = true;
+            }
+            if (NP > 1 && pred_phase && sched.needed > 0 && ((int)s - sched.s_trunc) % sched.needed == 0)
+                block_spawn(P, NP, rep, s, 1, alive, a, pred_s, pphi_s, red_s, nwarps);  // :160-170
+        }
         const bool first = alive && (a.bin_step == P.burst_steps);
         RowAcc acc;
         row_acc_clear(acc);
@@ -204,14 +326,30 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
             const unsigned m = __ballot_sync(FULL, first);
             if (lane == 0) act_s[warp] = m;
             __syncthreads();
-            int k = 0;
-            for (int ww = 0; ww < nwarps; ww++) {
-                unsigned m2 = act_s[ww];
+            // warp 0 turns the per-warp masks into an ordered list of the rows that start a burst
+            if (warp == 0) {
+                const unsigned mw = (lane < nwarps) ? act_s[lane] : 0u;
+                const int c = __popc(mw);
+                int off = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, off, o);
+                    if (lane >= o) off += v;
+                }
+                if (lane == 31) n_rows_s[0] = off;
+                off -= c;
+                unsigned m2 = mw;
                 while (m2) {
                     const int bit = __ffs(m2) - 1;
                     m2 &= m2 - 1;
-                    if ((k++ % nwarps) != warp) continue;
-                    const int row = ww * 32 + bit;
+                    rows_s[off++] = (unsigned short)(lane * 32 + bit);
+                }
+            }
+            __syncthreads();
+            const int n_first = n_rows_s[0];
+            {
+                for (int kr = warp; kr < n_first; kr += nwarps) {
+                    const int row = rows_s[kr];
                     const float4 pi = pv_s[row];
                     int cr = 0, ca = 0, ct = 0;
                     float rx = 0.f, ry = 0.f, gx = 0.f, gy = 0.f, tx = 0.f, ty = 0.f;
@@ -233,9 +371,9 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                         if (P.voronoi && z < 3) {  // Delaunay edge test against every other agent of the swarm
                             DelaunayEdge e;
                             sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
-                            for (int k = 0; k < N; k++) {
-                                const float4 pk = pv_s[k];
-                                if (k != row && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                            for (int kk = 0; kk < N; kk++) {
+                                const float4 pk = pv_s[kk];
+                                if (kk != row && kk != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
                             }
                             if (!sbc_delaunay_end(e)) z = 3;
                         }
@@ -249,28 +387,53 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                     ca = __reduce_add_sync(FULL, ca);
                     ct = __reduce_add_sync(FULL, ct);
                     float v0 = (cr > 0) ? rx : gx, v1 = (cr > 0) ? ry : gy, v2 = tx, v3 = ty;
+                    float f0 = 0.f, f1 = 0.f;
+                    int cf = 0;
+                    if (pred_phase) {  // IntCalcPred for this row: a lane takes four predators per Philox block
+                        RowAcc fa;
+                        row_acc_clear(fa);
+                        for (int jb = lane; 4 * jb < NP; jb += 32) {
+                            const uint4 q = sbc_draw(P, rep, (uint32_t)row, s, SBC_SLOT_DETECT0 + (uint32_t)jb);
+                            const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int j = 4 * jb + u;
+                                if (j < NP)
+                                    sbc_detect_accumulate(fa, pi.x, pi.y, pred_s[j].x, pred_s[j].y,
+                                                          (double)r4[u] * (1.0 / 4294967296.0), P);
+                            }
+                        }
+                        f0 = fa.flee_x; f1 = fa.flee_y;
+                        cf = __reduce_add_sync(FULL, fa.c_flee);
+                    }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
                         v0 += __shfl_xor_sync(FULL, v0, o);
                         v1 += __shfl_xor_sync(FULL, v1, o);
                         v2 += __shfl_xor_sync(FULL, v2, o);
                         v3 += __shfl_xor_sync(FULL, v3, o);
+                        if (PRED) {
+                            f0 += __shfl_xor_sync(FULL, f0, o);
+                            f1 += __shfl_xor_sync(FULL, f1, o);
+                        }
                     }
                     if (lane == 0) {
                         RowResult r;
                         r.v0 = v0; r.v1 = v1; r.v2 = v2; r.v3 = v3;
-                        r.cr = cr; r.ca = ca; r.ct = ct; r.pad = 0;
+                        r.cr = cr; r.ca = ca; r.ct = ct; r.cf = cf;
                         res_s[row] = r;
+                        flee_s[row] = make_float2(f0, f1);
                     }
                 }
             }
             __syncthreads();
             if (first) {
                 const RowResult r = res_s[t];
-                acc.c_rep = r.cr; acc.c_alg = r.ca; acc.c_att = r.ct;
+                acc.c_rep = r.cr; acc.c_alg = r.ca; acc.c_att = r.ct; acc.c_flee = r.cf;
                 if (r.cr > 0) { acc.rep_x = r.v0; acc.rep_y = r.v1; }
                 else { acc.alg_x = r.v0; acc.alg_y = r.v1; }
                 acc.att_x = r.v2; acc.att_y = r.v3;
+                acc.flee_x = flee_s[t].x; acc.flee_y = flee_s[t].y;
             }
         }
         if (alive) {
@@ -283,10 +446,124 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
             sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
             flags_acc |= fl;
         }
+        if (pred_phase) {  // swarmdyn.cpp:192-203
+            bool die = false;
+            if (NP > 1) {
+                __syncthreads();
+                for (int j = t; j < NP; j += nthreads) {  // MoveFishNet :616-624
+                    float4 p = pred_s[j];
+                    float ph = pphi_s[j];
+                    p.x += p.z * P.dt;
+                    p.y += p.w * P.dt;
+                    sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
+                    pred_s[j] = p;
+                    pphi_s[j] = ph;
+                }
+                __syncthreads();
+                if (P.pred_kill != 0 && alive) {  // FishNetKill :780-820
+                    const float4 p0 = pred_s[0], p1 = pred_s[1];
+                    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
+                    if (P.BC == 0) { vn[0] = min_image_dd(vn[0], P.dL); vn[1] = min_image_dd(vn[1], P.dL); }
+                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
+                    const double net_len = (double)(NP - 1) * dist;
+                    float s0, c0;
+                    sincosf(pphi_s[0], &s0, &c0);
+                    double r[2] = {__dsub_rn((double)a.x, (double)p0.x), __dsub_rn((double)a.y, (double)p0.y)};
+                    if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
+                    const double front = __dadd_rn(__dmul_rn((double)c0, r[0]), __dmul_rn((double)s0, r[1]));
+                    const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
+                    die = front > 0 && front < P.d_kill_range && side > 0 && side <= net_len;
+                }
+            } else {
+                // MovePredator :567-613
+                const float4 p0 = pred_s[0];
+                float lphi = pphi_s[0];
+                if (P.pred_move == 0) {
+                    const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, s, 2u);
+                    const float u1 = (float)(((double)q.x + 1.0) * (1.0 / 4294967296.0));
+                    const float u2 = (float)((double)q.y * (1.0 / 4294967296.0));
+                    const float gss = sqrtf(-2.f * logf(u1)) * cosf(SBC_TWO_PI_F * u2);
+                    lphi = fmodf(pphi_s[0] + P.noisep * gss * sqrtf(P.pred_speed), SBC_TWO_PI_F);
+                } else {
+                    unsigned long long key = ~0ull;
+                    float dx = 0.f, dy = 0.f;
+                    if (alive) {
+                        dx = a.x - p0.x; dy = a.y - p0.y;
+                        if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, a.x, P); dy = sbc_delta_pbc(p0.y, a.y, P); }
+                        key = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)t;
+                    }
+                    const unsigned long long best = block_min_u64(key, key_s, nwarps);
+                    __syncthreads();
+                    if (best != ~0ull && (unsigned)(best & 0xffffffffu) == (unsigned)t) red_s[0] = (double)atan2f(dy, dx);
+                    __syncthreads();
+                    if (best != ~0ull) lphi = (float)red_s[0];
+                }
+                __syncthreads();
+                if (t == 0) {
+                    float sn, cs;
+                    sincosf(lphi, &sn, &cs);
+                    float vx = P.pred_speed * cs, vy = P.pred_speed * sn;
+                    float x = p0.x + vx * P.dt, y = p0.y + vy * P.dt;
+                    float ph = lphi;
+                    sbc_boundary(x, y, vx, vy, ph, P, P.BC);
+                    pred_s[0] = make_float4(x, y, vx, vy);
+                    pphi_s[0] = ph;
+                }
+                __syncthreads();
+                if (P.pred_kill != 0) {  // PredKill :826-915
+                    const double px = (double)pred_s[0].x, py = (double)pred_s[0].y;
+                    const double r_sense = 4 * P.d_kill_range;
+                    double d = INFINITY;
+                    if (alive) {
+                        double r[2] = {__dsub_rn((double)a.x, px), __dsub_rn((double)a.y, py)};
+                        if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
+                        d = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
+                    }
+                    if (P.pred_kill == 1) {
+                        die = alive && d <= P.d_kill_range;
+                    } else {
+                        const bool sensed = alive && d <= r_sense;
+                        const bool cand = sensed && d < P.d_kill_range;
+                        const double n_sensed = block_sum_d(sensed ? 1.0 : 0.0, red_s, nwarps);
+                        const double total = block_sum_d(cand ? (P.d_kill_range - d) / P.d_kill_range : 0.0, red_s, nwarps);
+                        const double eff = (n_sensed > 0)
+                                               ? (double)P.kill_rate * 0.5 * (tanh(-1.0 * (n_sensed - (double)P.N_confu)) + 1.0)
+                                               : 0.0;
+                        if (cand) {
+                            double pk = 0;
+                            if (P.pred_kill == 2) pk = (double)P.kill_rate * (double)P.dt;
+                            else if (P.pred_kill == 3) pk = eff * (double)P.dt;
+                            else if (P.pred_kill == 4) pk = eff * (double)P.dt * (((P.d_kill_range - d) / P.d_kill_range) / total);
+                            const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DECISION);
+                            die = pk > (double)q.w * (1.0 / 4294967296.0);
+                        }
+                    }
+                }
+            }
+            if (die) {
+                alive = false;
+                died = true;
+                n_killed++;
+            }
+        }
     }
-    if (valid && alive) {
+    if (valid && (alive || died)) {
         store_agent(S, g, a);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
+        if (died) {  // split_dead (agents_operation.cpp:209-218): the agent leaves the active set
+            S.alive[g] = 0;
+            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
+            S.pv[g] = make_float4(qnan, qnan, a.vx, a.vy);
+        }
+    }
+    if (PRED) {
+        __syncthreads();
+        for (int j = t; j < NP; j += nthreads) {
+            S.pred_pv[(size_t)rep * NP + j] = pred_s[j];
+            S.pred_phi[(size_t)rep * NP + j] = pphi_s[j];
+        }
+        if (n_killed) atomicAdd(S.n_dead + rep, n_killed);
+        if (t == 0 && spawned) S.pred_spawned[rep] = 1;
     }
     if (n_amb) atomicAdd(S.stats + 4, n_amb);
     if (n_pairs) atomicAdd(S.stats + 3, n_pairs);
@@ -294,12 +571,12 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
 
 }  // namespace
 
-bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first,
-                            long long n_steps, cudaStream_t st) {
+bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
+                            cudaStream_t st, long long s_pred, int s_trunc, int needed) {
     const int N = S.N;
-    if (N > 1024 || N < 1) return false;
+    if (N > 1024 || N < 1 || S.Npred > 1024) return false;
     const uint32_t s0 = (uint32_t)s_first, ns = (uint32_t)n_steps;
-    if (N <= 32) {
+    if (N <= 32 && S.Npred == 0) {
         const int tps = (N <= 8) ? 8 : (N <= 16) ? 16 : 32;
         const int spw = 32 / tps;
         const long long warps = ((long long)S.R + spw - 1) / spw;
@@ -324,12 +601,27 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         return true;
     }
     const int nthreads = ((N + 31) / 32) * 32;
-    const size_t smem = (size_t)nthreads * (sizeof(float4) + sizeof(RowResult)) + 32 * sizeof(unsigned);
+    const size_t smem = (size_t)nthreads * (sizeof(float4) + sizeof(RowResult) + sizeof(float2)) + 32 * sizeof(double) +
+                        32 * sizeof(unsigned long long) + 32 * sizeof(unsigned) + 4 * sizeof(int) + (size_t)((nthreads + 7) / 8) * 8 * sizeof(unsigned short) + (size_t)S.Npred * (sizeof(float4) + sizeof(float)) + 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(swarm_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(swarm_block_kernel<false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(swarm_block_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(swarm_block_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(swarm_block_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_set = true;
     }
-    swarm_block_kernel<<<S.R, nthreads, smem, st>>>(P, S, s0, ns);
+    PredSchedule sched;
+    sched.s_pred = (s_pred < 0 || s_pred > 0xffffffffll) ? 0xffffffffu : (uint32_t)s_pred;
+    sched.s_trunc = s_trunc;
+    sched.needed = needed;
+    // two register budgets: swarms of up to 256 agents get the larger one
+    if (nthreads <= 256) {
+        if (S.Npred > 0) swarm_block_kernel<true, 256><<<S.R, nthreads, smem, st>>>(P, S, s0, ns, sched);
+        else swarm_block_kernel<false, 256><<<S.R, nthreads, smem, st>>>(P, S, s0, ns, sched);
+    } else {
+        if (S.Npred > 0) swarm_block_kernel<true, 1024><<<S.R, nthreads, smem, st>>>(P, S, s0, ns, sched);
+        else swarm_block_kernel<false, 1024><<<S.R, nthreads, smem, st>>>(P, S, s0, ns, sched);
+    }
     return true;
 }

@@ -10,6 +10,53 @@
 
 namespace {
 
+// prey<-predator detection (IntCalcPred, agents_interact.cpp:252-292) for the rows that start a burst
+// this step (the only rows that read the result): one warp per active row, a lane takes
+// four predators per Philox block; flee sums and counter go to acc[6..7] / cnt[3] of the row.
+__global__ void __launch_bounds__(256)
+detect_rows_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
+                   const uint32_t *__restrict__ step_dev, const int *__restrict__ list,
+                   const int *__restrict__ count) {
+    const uint32_t step = step_dev ? *step_dev : step_arg;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_rows = *count;
+    const int N = S.N, NP = S.Npred;
+    for (int k = warp; k < n_rows; k += n_warps) {
+        const int g = list[k];
+        const uint32_t rep = (uint32_t)(g / N);
+        const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
+        const float4 pi = S.pv[g];
+        const float4 *pp = S.pred_pv + (size_t)rep * NP;
+        RowAcc acc;
+        row_acc_clear(acc);
+        for (int jb = lane; 4 * jb < NP; jb += 32) {
+            const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DETECT0 + (uint32_t)jb);
+            const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = 4 * jb + u;
+                if (j < NP) {
+                    const float4 pr = pp[j];
+                    sbc_detect_accumulate(acc, pi.x, pi.y, pr.x, pr.y, (double)r[u] * (1.0 / 4294967296.0), P);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.flee_x += __shfl_xor_sync(0xffffffffu, acc.flee_x, o);
+            acc.flee_y += __shfl_xor_sync(0xffffffffu, acc.flee_y, o);
+        }
+        const int cf = __reduce_add_sync(0xffffffffu, acc.c_flee);
+        if (lane == 0) {
+            S.acc[(size_t)g * 8 + 6] = acc.flee_x;
+            S.acc[(size_t)g * 8 + 7] = acc.flee_y;
+            S.cnt[(size_t)g * 4 + 3] = cf;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg, const uint32_t *__restrict__ step_dev,
               int pred_active) {
@@ -54,20 +101,10 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
         acc.rep_x = a0.x; acc.rep_y = a0.y; acc.alg_x = a0.z; acc.alg_y = a0.w;
         acc.att_x = a1.x; acc.att_y = a1.y;
         acc.c_rep = c.x; acc.c_alg = c.y; acc.c_att = c.z;
-        if (pred_active) {
-            const float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
-            for (int j = 0; j < S.Npred; j += 4) {
-                const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DETECT0 + (uint32_t)(j >> 2));
-                const uint32_t r[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (j + k < S.Npred) {
-                        const float4 pr = pp[j + k];
-                        sbc_detect_accumulate(acc, a.x, a.y, pr.x, pr.y,
-                                              (double)r[k] * (1.0 / 4294967296.0), P);
-                    }
-                }
-            }
+        if (pred_active) {  // prey<-predator detection of this row was evaluated by detect_rows_kernel
+            acc.flee_x = a1.z;
+            acc.flee_y = a1.w;
+            acc.c_flee = c.w;
         }
     }
     uint32_t fl = 0;
@@ -86,6 +123,8 @@ __global__ void step_advance_kernel(uint32_t *step_dev) { *step_dev += 1u; }
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
                        int pred_active, cudaStream_t st) {
     const size_t total = (size_t)S.N * S.R;
+    if (pred_active)  // needs the compacted active rows of this step (sbc_launch_compact_rows)
+        detect_rows_kernel<<<148 * 2, 256, 0, st>>>(P, S, (uint32_t)step, step_dev, S.active_list, S.active_count);
     update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active);
 }
 void sbc_launch_step_advance(uint32_t *step_dev, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(step_dev); }

@@ -28,7 +28,8 @@ def _setup(mode, N, npred, kill, move, L=100.0, seed=1, **over):
 
 @pytest.mark.parametrize('kill,move,npred,mode', [(1, 1, 1, 'natPred'), (2, 1, 1, 'natPredNoConfu'), (3, 1, 1, 'natPred'),
                                                    (4, 1, 1, 'natPred'), (1, 0, 1, 'sinFisher'), (1, 0, 50, 'mulFisher')])
-def test_one_step_with_predator_present(kill, move, npred, mode):
+@pytest.mark.parametrize('multikernel', [True, False])
+def test_one_step_with_predator_present(kill, move, npred, mode, multikernel):
     """Predator(s) placed inside the swarm: one step = detection for burst-starting rows, update,
     predator move, kill. Alive sets exact, everything else within tolerance."""
     N = 200
@@ -70,8 +71,9 @@ def test_one_step_with_predator_present(kill, move, npred, mode):
     assert mism <= 3, mism   # detection / decision flips at FP32 resolution are rare
 
 
+@pytest.mark.parametrize('multikernel', [True, False])
 @pytest.mark.parametrize('npred', [1, 50])
-def test_spawn_step_places_predator_like_oracle(npred):
+def test_spawn_step_places_predator_like_oracle(npred, multikernel):
     N = 120
     mode = 'natPred' if npred == 1 else 'mulFisher'
     sp, np_, _ = make_params(mode, N, BC=0, size=100.0, Npred=npred, pred_kill=0, pred_move=1 if npred == 1 else 0,
@@ -80,7 +82,7 @@ def test_spawn_step_places_predator_like_oracle(npred):
     st = random_state(N, sp, rng, spread=30.0)
     w = pyorc.World(sp, N, npred, seed=9, replicate=4)
     g = _swarm(sp, N, npred, seed=9, replicate_offset=4)
-    g.force_multikernel(True)
+    g.force_multikernel(multikernel)
     for obj in (w, g):
         obj.set_state(**st)
     w.step(0, 12)
@@ -116,3 +118,28 @@ def test_survival_curve_matches_oracle_statistically():
     se = np.sqrt(np.var(dead_o) / R + np.var(dead_g) / R) + 1e-9
     assert mo > 0.5 and mg > 0.5, (mo, mg)
     assert abs(mo - mg) <= 4 * se + 0.5, (mo, mg, se)
+
+
+def test_block_and_multikernel_paths_agree_over_a_predator_run():
+    """Same swarm, same seed, 4000 steps through the predator phase on both schedules: identical burst
+    timers and kill counts, predator tracks within tolerance."""
+    N = 300
+    sp, _, _ = make_params('natPred', N, BC=0, size=100.0, Npred=1, pred_kill=1, pred_move=1, pred_time=0.05,
+                           time=50.0, pred_speed0=20.0)
+    rng = np.random.default_rng(12)
+    st = random_state(N, sp, rng, spread=30.0)
+    out = []
+    for mk in (False, True):
+        g = _swarm(sp, N, 1, seed=5)
+        g.force_multikernel(mk)
+        g.set_state(**st)
+        g.step(0, 4000)
+        out.append((g.get_state(), g.get_predators(), g.counts(), g.stats()))
+        g.close()
+    a, b = out
+    assert a[3]['block_launches'] == 1 and b[3]['update_launches'] == 4000
+    al = a[0]['alive'].astype(bool) & b[0]['alive'].astype(bool)
+    assert np.array_equal(a[0]['steps_till_burst'][al], b[0]['steps_till_burst'][al])
+    # trajectories are chaotic over 4000 steps, kill counts agree statistically only
+    assert int(a[2][1][0]) > 0 and int(b[2][1][0]) > 0
+    assert abs(int(a[2][1][0]) - int(b[2][1][0])) <= 0.5 * max(int(a[2][1][0]), int(b[2][1][0])) + 5
