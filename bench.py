@@ -277,8 +277,6 @@ def main():
         g.set_state(**host)                      # H2D: x, y, phi, vproj (doubles, the ABI layout)
         g.step(s, args.chunk)
         g._check(g.lib.sbc_get_particles(g.h, part.ctypes.data_as(dp), alive.ctypes.data_as(u8p)))  # D2H
-        host['x'][...] = part[:, :, 0]           # the host keeps the loop state, as swarmdyn's main does
-        host['y'][...] = part[:, :, 1]
 
     for _ in range(2):
         e2e_step(s_now)

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(DT, 6)
 pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float4 *__restrict__ spv_all,
                   int nsplit, float *__restrict__ part_f, int *__restrict__ part_i,
                   unsigned long long *__restrict__ stats) {
-    __shared__ __align__(16) float2 tA[TILE];   // tile positions for the far test (block-relative hi part if periodic)
+    __shared__ float4 tA[TILE];                 // far-test tile: block-relative {x', y', w = -(x'^2+y'^2)(1-8u), 0}
     __shared__ __align__(16) float2 tL[TILE];   // periodic: lo parts of the block-relative tile positions
     __shared__ float4 tB[TILE];                 // tile agents as stored
     __shared__ int s_ref;
@@ -213,7 +213,9 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
     const float4 c = any_alive ? spv[s_ref] : nan4;
     Acc9 A0 = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0, 0, 0}, A1 = A0;
     unsigned n_amb = 0;
-    float x0 = p0.x, y0 = p0.y, x1 = p1.x, y1 = p1.y;
+    // block-relative row coordinates: two-floats (hi, lo) of the minimum image in a periodic box,
+    // plain differences to the reference point otherwise
+    float x0 = p0.x - c.x, y0 = p0.y - c.y, x1 = p1.x - c.x, y1 = p1.y - c.y;
     float l0x = 0.f, l0y = 0.f, l1x = 0.f, l1y = 0.f;
     int generic = 0;
     if (PERIODIC) {
@@ -223,7 +225,15 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
         const float m = fmaxf(fmaxf(fabsf(x0), fabsf(y0)), fmaxf(fabsf(x1), fabsf(y1)));
         generic = __syncthreads_or(m > P.compact_lim);   // NaN rows compare false
     }
+    // Far test in expanded form: |p_j - p_i|^2 <= far2  <=>  (|p_i|^2 - far2) - 2 p_i.p_j <= -|p_j|^2.
+    // Two FFMAs per pair; the FP32 rounding of the three terms (<= 4u(2|p_i|^2 + |p_j|^2 + far2)) is
+    // covered by shifting both sides: the test may pass a pair that is not near, never the reverse.
+    const float u8 = 8.f * 5.9604645e-8f;
+    const float n0 = __fmaf_rn(y0, y0, x0 * x0), n1 = __fmaf_rn(y1, y1, x1 * x1);
+    const float c0 = (n0 - P.far2) - u8 * (n0 + P.far2), c1 = (n1 - P.far2) - u8 * (n1 + P.far2);
+    const float m2x0 = -2.f * x0, m2y0 = -2.f * y0, m2x1 = -2.f * x1, m2y1 = -2.f * y1;
     const float far2 = P.far2;
+    (void)far2;
     if (any_alive) {
         // tiles are dealt to the splits round-robin: a split's tiles are spread over the whole
         // curve, so every block sees about the same share of near pairs
@@ -233,51 +243,43 @@ pair_dense_kernel(const __grid_constant__ DevParams P, int N, int R, const float
                 const int j = j0 + t;
                 const float4 pj = (j < N) ? spv[j] : nan4;
                 tB[t] = pj;
+                float hx = pj.x - c.x, hy = pj.y - c.y;
                 if (PERIODIC) {
                     float lx, ly;
-                    const float hx = sbc_delta_pbc2(c.x, pj.x, P, lx), hy = sbc_delta_pbc2(c.y, pj.y, P, ly);
-                    tA[t] = make_float2(hx, hy);
+                    hx = sbc_delta_pbc2(c.x, pj.x, P, lx);
+                    hy = sbc_delta_pbc2(c.y, pj.y, P, ly);
                     tL[t] = make_float2(lx, ly);
-                } else {
-                    tA[t] = make_float2(pj.x, pj.y);
                 }
+                tA[t] = make_float4(hx, hy, -__fmaf_rn(hy, hy, hx * hx) * (1.f - 8.f * 5.9604645e-8f), 0.f);
             }
             __syncthreads();
             if (!generic) {
-                const float4 *tA2 = reinterpret_cast<const float4 *>(tA);  // two j per LDS.128
 #pragma unroll 2
-                for (int jj = 0; jj < TILE / 2; jj++) {
-                    const float4 q = tA2[jj];
-                    const float ax0 = q.x - x0, ay0 = q.y - y0, ax1 = q.x - x1, ay1 = q.y - y1;
-                    const float bx0 = q.z - x0, by0 = q.w - y0, bx1 = q.z - x1, by1 = q.w - y1;
-                    const float da0 = __fmaf_rn(ay0, ay0, __fmul_rn(ax0, ax0)), da1 = __fmaf_rn(ay1, ay1, __fmul_rn(ax1, ax1));
-                    const float db0 = __fmaf_rn(by0, by0, __fmul_rn(bx0, bx0)), db1 = __fmaf_rn(by1, by1, __fmul_rn(bx1, bx1));
-                    const float ma = fminf(da0, da1), mb = fminf(db0, db1);
-                    if (fminf(ma, mb) <= far2) {  // NaN (dead or padding) never passes
-                        if (ma <= far2) {
-                            const float4 *pjp = &tB[2 * jj];
-                            if (PERIODIC) {
-                                const float2 l = tL[2 * jj];
-                                const float dx0 = ax0 + (l.x - l0x), dy0 = ay0 + (l.y - l0y);
-                                const float dx1 = ax1 + (l.x - l1x), dy1 = ay1 + (l.y - l1y);
+                for (int jj = 0; jj < TILE; jj += 2) {
+                    const float4 qa = tA[jj], qb = tA[jj + 1];
+                    const float ea0 = __fmaf_rn(m2x0, qa.x, __fmaf_rn(m2y0, qa.y, c0));
+                    const float ea1 = __fmaf_rn(m2x1, qa.x, __fmaf_rn(m2y1, qa.y, c1));
+                    const float eb0 = __fmaf_rn(m2x0, qb.x, __fmaf_rn(m2y0, qb.y, c0));
+                    const float eb1 = __fmaf_rn(m2x1, qb.x, __fmaf_rn(m2y1, qb.y, c1));
+                    const float ta = fminf(ea0, ea1) - qa.z, tb = fminf(eb0, eb1) - qb.z;
+                    if (fminf(ta, tb) <= 0.f) {  // NaN (dead or padding) never passes
+#pragma unroll
+                        for (int u = 0; u < 2; u++) {
+                            if ((u ? tb : ta) <= 0.f) {
+                                const float4 q = u ? qb : qa;
+                                const float4 *pjp = &tB[jj + u];
+                                float dx0, dy0, dx1, dy1;
+                                if (PERIODIC) {
+                                    const float2 l = tL[jj + u];
+                                    dx0 = (q.x - x0) + (l.x - l0x); dy0 = (q.y - y0) + (l.y - l0y);
+                                    dx1 = (q.x - x1) + (l.x - l1x); dy1 = (q.y - y1) + (l.y - l1y);
+                                } else {
+                                    const float4 pj = *pjp;   // stored coordinates: one rounding per difference
+                                    dx0 = pj.x - p0.x; dy0 = pj.y - p0.y;
+                                    dx1 = pj.x - p1.x; dy1 = pj.y - p1.y;
+                                }
                                 near_pair<HAS_ALG>(A0, n_amb, dx0, dy0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)), p0.x, p0.y, pjp, P);
                                 near_pair<HAS_ALG>(A1, n_amb, dx1, dy1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)), p1.x, p1.y, pjp, P);
-                            } else {
-                                near_pair<HAS_ALG>(A0, n_amb, ax0, ay0, da0, p0.x, p0.y, pjp, P);
-                                near_pair<HAS_ALG>(A1, n_amb, ax1, ay1, da1, p1.x, p1.y, pjp, P);
-                            }
-                        }
-                        if (mb <= far2) {
-                            const float4 *pjp = &tB[2 * jj + 1];
-                            if (PERIODIC) {
-                                const float2 l = tL[2 * jj + 1];
-                                const float dx0 = bx0 + (l.x - l0x), dy0 = by0 + (l.y - l0y);
-                                const float dx1 = bx1 + (l.x - l1x), dy1 = by1 + (l.y - l1y);
-                                near_pair<HAS_ALG>(A0, n_amb, dx0, dy0, __fmaf_rn(dy0, dy0, __fmul_rn(dx0, dx0)), p0.x, p0.y, pjp, P);
-                                near_pair<HAS_ALG>(A1, n_amb, dx1, dy1, __fmaf_rn(dy1, dy1, __fmul_rn(dx1, dx1)), p1.x, p1.y, pjp, P);
-                            } else {
-                                near_pair<HAS_ALG>(A0, n_amb, bx0, by0, db0, p0.x, p0.y, pjp, P);
-                                near_pair<HAS_ALG>(A1, n_amb, bx1, by1, db1, p1.x, p1.y, pjp, P);
                             }
                         }
                     }
