@@ -174,19 +174,21 @@ int sbc_get_stats(sbc_handle *h, uint64_t out[8]);
  * the start of the step, every agent is updated once, decisions depend on (seed, GLOBAL id, step).
  * A handle's n_agents is its slot capacity: slots [0, own_capacity) hold owned agents or free slots,
  * the rest hold ghosts (copies of the neighbours' agents within att_range of a slab edge).
- * Buffers are DEVICE pointers of sbc_domain_buffer_bytes(max_records) bytes: a header record with the
- * count followed by 64-byte records, so messages have a fixed size and no host round trip is needed.
- * Per step the host does: pack_halos -> exchange -> unpack_ghosts -> sbc_step(h, s, 1) ->
- * pack_migrants -> exchange -> unpack_migrants (sde_burst_coast_b200/domain.py; transport = NCCL
- * send/recv over NVLink through torch.distributed). */
+ * Buffers are DEVICE pointers of sbc_domain_buffer_bytes(max_migrants, max_halo) bytes:
+ * [header | migrant records | halo records], 64-byte records, fixed size - no host round trip sizes a
+ * message. ONE exchange per step: after sbc_set_state and after every sbc_step(h, s, 1) the host does
+ * sbc_domain_pack -> exchange with the two ring neighbours -> sbc_domain_unpack
+ * (sde_burst_coast_b200/domain.py; transport = NCCL send/recv over NVLink through torch.distributed). */
 int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid /* [n_agents] */);
 int sbc_get_global_ids(sbc_handle *h, uint32_t *gid /* [n_agents]; 0xFFFFFFFF for empty ghost slots */);
-int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity);
-size_t sbc_domain_buffer_bytes(int max_records);
-int sbc_domain_pack_halos(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records);
-int sbc_domain_unpack_ghosts(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev);
-int sbc_domain_pack_migrants(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records);
-int sbc_domain_unpack_migrants(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev, int max_records);
+int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int max_migrants, int max_halo);
+size_t sbc_domain_buffer_bytes(int max_migrants, int max_halo);
+/* classify the owned agents (left the slab / inside a halo band), write both buffers, free leavers' slots */
+int sbc_domain_pack(sbc_handle *h, void *send_left_dev, void *send_right_dev);
+/* recv_a / recv_b: what the left / right neighbour sent to this rank; sent_*: this rank's own send buffers
+ * (its outgoing migrants become its ghosts) */
+int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
+                      const void *sent_right_dev);
 int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t *overflow_events);
 
 /* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on

@@ -1,22 +1,26 @@
 // domain.cu - spatial domain decomposition of ONE large periodic swarm over several handles (one per
-// GPU): slabs along x, per-step halo of the agents within att_range of a slab edge, migration of
-// agents that crossed an edge (BASELINE config C5). The reference has no
-// counterpart (single process); what must be preserved is Step()'s semantics
-// (/root/reference/src/swarmdyn.cpp:143-204): interactions see every agent's position at the start of
-// the step, every agent is updated once, decisions depend on (seed, GLOBAL agent id, step) only.
+// GPU): slabs along x, halo of the agents within att_range of a slab edge, migration of agents that
+// crossed an edge (BASELINE config C5). The reference has no counterpart (single
+// process); what must be preserved is Step()'s semantics (/root/reference/src/swarmdyn.cpp:143-204):
+// interactions see every agent's position at the start of the step, every agent is updated once,
+// decisions depend on (seed, GLOBAL agent id, step) only.
 //
 // Slots of a handle: [0, own_cap) owned agents (alive) or free slots (alive = 0, x = NaN);
 // [own_cap, N) ghosts = copies of neighbours' edge agents (alive = 0 but x valid: visible as
-// interaction partners j, never rows, never updated). Records travel in fixed-size device buffers
-// (header record with the count, then 64-byte records), so no host round trip is needed to size a
-// message; the transport itself (NCCL send/recv over NVLink, or a loop-back copy in tests) belongs to
-// the host side (sde_burst_coast_b200/domain.py).
+// interaction partners j, never rows, never updated).
 //
-// Packing order is by slot index (CUB DeviceSelect, stable), arrival order is (left buffer, right
-// buffer): results do not depend on thread scheduling.
-#include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-
+// ONE exchange per step, after the update:
+//   pack   : every owned agent is classified in one ordered pass - it LEFT the slab through the left /
+//            right edge (full-state record, slot freed) or it stays and lies within the halo band of
+//            an edge (position record). Both kinds go into one fixed-size buffer per side
+//            [header | migrants | halo], so no host round trip sizes a message.
+//   unpack : incoming migrants take free slots (a device-resident stack, lowest slot first), incoming
+//            halo records become ghosts, and so do the agents this rank just sent away - they sit just
+//            across the edge, exactly where the neighbour's halo band would report them.
+// Packing order is by slot index (block counts -> scan -> ordered write) and arrival order is fixed
+// (left buffer, right buffer), so results do not depend on thread scheduling. The transport itself
+// (NCCL send/recv over NVLink, or a loop-back copy in tests) belongs to the host side
+// (sde_burst_coast_b200/domain.py).
 #include "sbc_kernels.cuh"
 
 namespace {
@@ -31,102 +35,248 @@ struct __align__(16) DomRecord {  // 64 bytes
 };
 static_assert(sizeof(DomRecord) == 64, "DomRecord must be 64 bytes");
 
-// which side an agent at x has to go to / be visible from. Slabs are [rank w, (rank+1) w) of a
-// periodic box; an owned agent outside its slab belongs to the neighbour it is closer to.
-struct HaloPred {
-    const float4 *pv;
-    const uint8_t *alive;
-    float lo, hi;   // select alive owned agents with lo <= x < hi (a band next to one slab edge)
-    __device__ bool operator()(int g) const {
-        if (!alive[g]) return false;
-        const float x = pv[g].x;
-        return x >= lo && x < hi;
-    }
-};
-struct LeaverPred {
-    const float4 *pv;
-    const uint8_t *alive;
-    float x_lo, x_hi, L;
-    int side;  // 0: leaves through the left edge, 1: through the right edge
-    __device__ bool operator()(int g) const {
-        if (!alive[g]) return false;
-        const float x = pv[g].x;
-        if (x >= x_lo && x < x_hi) return false;
-        // circular distance to the two edges decides the side
-        float dl = x_lo - x; if (dl < 0.f) dl += L;      // how far left of the left edge
-        float dr = x - x_hi; if (dr < 0.f) dr += L;      // how far right of the right edge
-        return (side == 0) ? (dl <= dr) : (dr < dl);
-    }
-};
-struct FreePred {
-    const uint8_t *alive;
-    __device__ bool operator()(int g) const { return alive[g] == 0; }
-};
+constexpr int CLS_THREADS = 256;
+constexpr int CLS_PER_BLOCK = 1024;  // slots per block
+enum { CAT_LEAVE_L = 0, CAT_LEAVE_R = 1, CAT_HALO_L = 2, CAT_HALO_R = 3, CAT_FREE = 4, NCAT = 5 };
 
-__global__ void gather_records_kernel(DevState S, const int *__restrict__ sel, const int *__restrict__ n_sel,
-                                      int max_records, int full_state, int free_slots, DomRecord *__restrict__ buf,
-                                      int *overflow) {
-    const int n = *n_sel;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0) {
-        DomRecord hdr = {};
-        hdr.gid = (uint32_t)min(n, max_records);
-        hdr.pad[0] = (uint32_t)n;  // what was wanted; > max_records means overflow
-        buf[0] = hdr;
-        if (n > max_records) atomicAdd(overflow, 1);
+// category mask of one owned slot: bit c set = the slot belongs to category c
+__device__ __forceinline__ unsigned classify(const DevState &S, int g, float x_lo, float x_hi, float L, float halo) {
+    if (!S.alive[g]) return 0u;
+    const float x = S.pv[g].x;
+    if (x >= x_lo && x < x_hi) {
+        unsigned m = 0;
+        if (x < x_lo + halo) m |= 1u << CAT_HALO_L;
+        if (x >= x_hi - halo) m |= 1u << CAT_HALO_R;
+        return m;
     }
-    if (k >= n || k >= max_records) return;
-    const int g = sel[k];
-    DomRecord r = {};
-    r.pv = S.pv[g];
-    r.gid = S.gid ? S.gid[g] : (uint32_t)g;
-    if (full_state) {
-        r.hv = S.hv[g];
-        r.force = S.force[g];
-        r.timers = S.timers[g];
+    // outside the slab: the neighbour it is closer to along the ring gets it
+    float dl = x_lo - x; if (dl < 0.f) dl += L;
+    float dr = x - x_hi; if (dr < 0.f) dr += L;
+    return (dl <= dr) ? (1u << CAT_LEAVE_L) : (1u << CAT_LEAVE_R);
+}
+
+__global__ void __launch_bounds__(CLS_THREADS)
+dom_count_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float halo, int *__restrict__ block_counts) {
+    __shared__ int sh[4];
+    if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+    __syncthreads();
+    int c[4] = {0, 0, 0, 0};
+    const int base = blockIdx.x * CLS_PER_BLOCK;
+    for (int k = threadIdx.x; k < CLS_PER_BLOCK; k += CLS_THREADS) {
+        const int g = base + k;
+        if (g >= own_cap) break;
+        const unsigned m = classify(S, g, x_lo, x_hi, L, halo);
+#pragma unroll
+        for (int q = 0; q < 4; q++) c[q] += (m >> q) & 1u;
     }
-    buf[1 + k] = r;
-    if (free_slots) {  // the agent now lives on the neighbour
-        const float qnan = __int_as_float(0x7fc00000);
-        S.alive[g] = 0;
-        S.pv[g] = make_float4(qnan, qnan, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int v = __reduce_add_sync(0xffffffffu, c[q]);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[q], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) block_counts[blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of the per-block counts (one block), headers of the two send buffers, free-stack base
+__global__ void __launch_bounds__(1024)
+dom_scan_kernel(int nblk, const int *__restrict__ block_counts, int *__restrict__ block_off, int *__restrict__ ctl,
+                DomRecord *__restrict__ send_l, DomRecord *__restrict__ send_r, int max_mig, int max_halo) {
+    __shared__ int warp_tot[32][4];
+    __shared__ int carry[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) carry[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        int v[4], inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            v[q] = (b < nblk) ? block_counts[b * 4 + q] : 0;
+            inc[q] = v[q];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc[q], o);
+                if (lane >= o) inc[q] += t;
+            }
+            if (lane == 31) warp_tot[warp][q] = inc[q];
+        }
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                int t = warp_tot[lane][q], s = t;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, s, o);
+                    if (lane >= o) s += u;
+                }
+                warp_tot[lane][q] = s - t;  // exclusive prefix of the warp totals
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int excl = carry[q] + warp_tot[warp][q] + inc[q] - v[q];
+            if (b < nblk) block_off[b * 4 + q] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) carry[q] += warp_tot[31][q] + inc[q];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        // ctl: [0] free_top, [1] free_base for this pack, [2..5] totals, [6] overflow events
+        const int nl = carry[CAT_LEAVE_L], nr = carry[CAT_LEAVE_R], hl = carry[CAT_HALO_L], hr = carry[CAT_HALO_R];
+        ctl[2] = nl; ctl[3] = nr; ctl[4] = hl; ctl[5] = hr;
+        if (nl > max_mig || nr > max_mig || hl > max_halo || hr > max_halo) ctl[6] += 1;
+        ctl[1] = ctl[0];
+        ctl[0] += min(nl, max_mig) + min(nr, max_mig);  // leavers free their slots
+        DomRecord h = {};
+        h.gid = (uint32_t)min(nl, max_mig); h.pad[0] = (uint32_t)min(hl, max_halo);
+        send_l[0] = h;
+        h.gid = (uint32_t)min(nr, max_mig); h.pad[0] = (uint32_t)min(hr, max_halo);
+        send_r[0] = h;
     }
 }
 
-__global__ void unpack_ghosts_kernel(DevState S, int ghost_first, const DomRecord *__restrict__ a,
-                                     const DomRecord *__restrict__ b, int *overflow) {
-    const int na = a ? (int)a[0].gid : 0, nb = b ? (int)b[0].gid : 0;
-    const int cap = S.N - ghost_first;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0 && na + nb > cap) atomicAdd(overflow, 1);
-    if (k >= cap) return;
-    const int g = ghost_first + k;
+// ordered write of the records: within a block by a ballot prefix, between blocks by the scanned offsets
+__global__ void __launch_bounds__(CLS_THREADS)
+dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float halo, const int *__restrict__ block_off,
+                const int *__restrict__ ctl, int *__restrict__ free_stack, DomRecord *__restrict__ send_l,
+                DomRecord *__restrict__ send_r, int max_mig, int max_halo) {
+    __shared__ int run[4];       // running offsets of this block, advanced chunk by chunk
+    __shared__ int wcnt[CLS_THREADS / 32][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 4) run[threadIdx.x] = block_off[blockIdx.x * 4 + threadIdx.x];
+    __syncthreads();
+    const int base = blockIdx.x * CLS_PER_BLOCK;
+    const int free_base = ctl[1], n_leave_l = min(ctl[2], max_mig);
     const float qnan = __int_as_float(0x7fc00000);
-    float4 pv = make_float4(qnan, qnan, 0.f, 0.f);
-    uint32_t gid = 0xffffffffu;
-    if (k < na) { pv = a[1 + k].pv; gid = a[1 + k].gid; }
-    else if (k < na + nb) { pv = b[1 + (k - na)].pv; gid = b[1 + (k - na)].gid; }
-    S.pv[g] = pv;
-    S.alive[g] = 0;
-    if (S.gid) S.gid[g] = gid;
+    for (int k0 = 0; k0 < CLS_PER_BLOCK; k0 += CLS_THREADS) {
+        const int g = base + k0 + threadIdx.x;
+        const unsigned m = (g < own_cap) ? classify(S, g, x_lo, x_hi, L, halo) : 0u;
+        int pos[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned bal = __ballot_sync(0xffffffffu, (m >> q) & 1u);
+            pos[q] = __popc(bal & ((1u << lane) - 1u));
+            if (lane == 0) wcnt[warp][q] = __popc(bal);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            int off = run[q];
+            for (int w = 0; w < warp; w++) off += wcnt[w][q];
+            pos[q] += off;
+        }
+        if (m) {
+            DomRecord r = {};
+            r.pv = S.pv[g];
+            r.gid = S.gid ? S.gid[g] : (uint32_t)g;
+            if (m & ((1u << CAT_LEAVE_L) | (1u << CAT_LEAVE_R))) {
+                const bool left = (m >> CAT_LEAVE_L) & 1u;
+                const int p = left ? pos[CAT_LEAVE_L] : pos[CAT_LEAVE_R];
+                if (p < max_mig) {
+                    r.hv = S.hv[g];
+                    r.force = S.force[g];
+                    r.timers = S.timers[g];
+                    (left ? send_l : send_r)[1 + p] = r;
+                    // the agent now lives on the neighbour: free the slot (ordered push on the stack)
+                    S.alive[g] = 0;
+                    S.pv[g] = make_float4(qnan, qnan, 0.f, 0.f);
+                    free_stack[free_base + (left ? p : n_leave_l + p)] = g;
+                }
+            } else {
+                if ((m >> CAT_HALO_L) & 1u) { const int p = pos[CAT_HALO_L]; if (p < max_halo) send_l[1 + max_mig + p] = r; }
+                if ((m >> CAT_HALO_R) & 1u) { const int p = pos[CAT_HALO_R]; if (p < max_halo) send_r[1 + max_mig + p] = r; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            int t = 0;
+            for (int w = 0; w < CLS_THREADS / 32; w++) t += wcnt[w][threadIdx.x];
+            run[threadIdx.x] += t;
+        }
+        __syncthreads();
+    }
 }
 
-__global__ void unpack_migrants_kernel(DevState S, const int *__restrict__ free_list, const int *__restrict__ n_free,
-                                       const DomRecord *__restrict__ a, const DomRecord *__restrict__ b,
-                                       int *overflow) {
-    const int na = a ? (int)a[0].gid : 0, nb = b ? (int)b[0].gid : 0;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k == 0 && na + nb > *n_free) atomicAdd(overflow, 1);
-    if (k >= na + nb || k >= *n_free) return;
-    const DomRecord r = (k < na) ? a[1 + k] : b[1 + (k - na)];
-    const int g = free_list[k];
-    S.pv[g] = r.pv;
-    S.pv_dead[g] = r.pv;
-    S.hv[g] = r.hv;
-    S.force[g] = r.force;
-    S.timers[g] = r.timers;
-    S.alive[g] = 1;
-    if (S.gid) S.gid[g] = r.gid;
+// incoming migrants -> free owned slots; ghosts = incoming halo (left, right) + my own outgoing migrants
+__global__ void __launch_bounds__(256)
+dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a, const DomRecord *__restrict__ recv_b,
+                  const DomRecord *__restrict__ sent_l, const DomRecord *__restrict__ sent_r, int max_mig,
+                  int *__restrict__ ctl, const int *__restrict__ free_stack) {
+    const int ma = recv_a ? (int)recv_a[0].gid : 0, mb = recv_b ? (int)recv_b[0].gid : 0;
+    const int ha = recv_a ? (int)recv_a[0].pad[0] : 0, hb = recv_b ? (int)recv_b[0].pad[0] : 0;
+    const int sl = sent_l ? (int)sent_l[0].gid : 0, sr = sent_r ? (int)sent_r[0].gid : 0;
+    const int free_top = ctl[0];
+    const int ghost_cap = S.N - own_cap;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        if (ma + mb > free_top || ha + hb + sl + sr > ghost_cap) ctl[6] += 1;
+        ctl[7] = ma + mb;  // consumed by dom_commit_kernel
+    }
+    if (t < ma + mb && t < free_top) {  // migrants
+        const DomRecord r = (t < ma) ? recv_a[1 + t] : recv_b[1 + (t - ma)];
+        const int g = free_stack[free_top - 1 - t];
+        S.pv[g] = r.pv;
+        S.pv_dead[g] = r.pv;
+        S.hv[g] = r.hv;
+        S.force[g] = r.force;
+        S.timers[g] = r.timers;
+        S.alive[g] = 1;
+        if (S.gid) S.gid[g] = r.gid;
+    }
+    if (t < ghost_cap) {  // ghosts
+        const float qnan = __int_as_float(0x7fc00000);
+        float4 pv = make_float4(qnan, qnan, 0.f, 0.f);
+        uint32_t gid = 0xffffffffu;
+        int k = t;
+        if (k < ha) { pv = recv_a[1 + max_mig + k].pv; gid = recv_a[1 + max_mig + k].gid; }
+        else if ((k -= ha) < hb) { pv = recv_b[1 + max_mig + k].pv; gid = recv_b[1 + max_mig + k].gid; }
+        else if ((k -= hb) < sl) { pv = sent_l[1 + k].pv; gid = sent_l[1 + k].gid; }
+        else if ((k -= sl) < sr) { pv = sent_r[1 + k].pv; gid = sent_r[1 + k].gid; }
+        const int g = own_cap + t;
+        S.pv[g] = pv;
+        S.alive[g] = 0;
+        if (S.gid) S.gid[g] = gid;
+    }
+}
+__global__ void dom_commit_kernel(int *ctl) { ctl[0] = max(ctl[0] - ctl[7], 0); }
+
+// free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
+// slot first. One block walks the slots from the top down, 1024 at a time, with an ordered compaction.
+__global__ void __launch_bounds__(1024)
+dom_init_stack_kernel(DevState S, int own_cap, int *free_stack, int *ctl) {
+    __shared__ int wsum[32];
+    __shared__ int top_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) top_s = 0;
+    __syncthreads();
+    for (int hi = own_cap - 1; hi >= 0; hi -= 1024) {
+        const int g = hi - (int)threadIdx.x;
+        const bool fr = (g >= 0) && !S.alive[g];
+        const unsigned bal = __ballot_sync(0xffffffffu, fr);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int off = top_s;
+        for (int w = 0; w < warp; w++) off += wsum[w];
+        if (fr) free_stack[off + __popc(bal & ((1u << lane) - 1u))] = g;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; w++) t += wsum[w];
+            top_s += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ctl[0] = top_s;
+        ctl[6] = 0;
+    }
 }
 
 __global__ void count_owned_kernel(DevState S, int own_cap, int *out) {
@@ -143,76 +293,51 @@ __global__ void count_owned_kernel(DevState S, int own_cap, int *out) {
     }
 }
 
-template <class Pred>
-void select_slots(DomainScratch &D, int n_slots, Pred pred, cudaStream_t st) {
-    cub::CountingInputIterator<int> it(0);
-    cub::DeviceSelect::If(D.cub_tmp, D.cub_bytes, it, D.sel, D.n_sel, n_slots, pred, st);
-}
-
 }  // namespace
 
 size_t sbc_domain_record_bytes(void) { return sizeof(DomRecord); }
 
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int n_slots) {
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap) {
     cudaError_t e;
-    if ((e = cudaMalloc((void **)&D.sel, (size_t)n_slots * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&D.n_sel, 4 * sizeof(int))) != cudaSuccess) return e;
-    cudaMemset(D.n_sel, 0, 4 * sizeof(int));  // [0] selection count, [1..2] owned / ghost counts, [3] overflow events
-    cub::CountingInputIterator<int> it(0);
-    D.cub_bytes = 0;
-    FreePred fp{nullptr};
-    cub::DeviceSelect::If(nullptr, D.cub_bytes, it, D.sel, D.n_sel, n_slots, fp);
-    D.cub_bytes += 256;
-    return cudaMalloc(&D.cub_tmp, D.cub_bytes);
+    D.nblk = (own_cap + CLS_PER_BLOCK - 1) / CLS_PER_BLOCK;
+    if ((e = cudaMalloc((void **)&D.block_counts, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.block_off, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.free_stack, (size_t)own_cap * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.ctl, 16 * sizeof(int))) != cudaSuccess) return e;
+    return cudaMemset(D.ctl, 0, 16 * sizeof(int));
 }
 void sbc_domain_scratch_free(DomainScratch &D) {
-    cudaFree(D.sel); cudaFree(D.n_sel); cudaFree(D.cub_tmp);
+    cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl);
     D = DomainScratch();
 }
 
-// halo bands: agents within `halo` of the left edge go into buf_left, of the right edge into buf_right
-void sbc_launch_pack_halos(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
-                           void *buf_right, int max_records, cudaStream_t st) {
+void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t st) {
+    dom_init_stack_kernel<<<1, 1024, 0, st>>>(S, D.own_cap, D.free_stack, D.ctl);
+}
+
+void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
+                            cudaStream_t st) {
     const float halo = P.att * 1.0001f;
-    void *bufs[2] = {buf_left, buf_right};
-    for (int side = 0; side < 2; side++) {
-        if (!bufs[side]) continue;
-        HaloPred pr{S.pv, S.alive, side == 0 ? D.x_lo : D.x_hi - halo, side == 0 ? D.x_lo + halo : D.x_hi};
-        select_slots(D, D.own_cap, pr, st);
-        gather_records_kernel<<<(max_records + 255) / 256, 256, 0, st>>>(S, D.sel, D.n_sel, max_records, 0, 0,
-                                                                        static_cast<DomRecord *>(bufs[side]), D.n_sel + 3);
-    }
+    dom_count_kernel<<<D.nblk, CLS_THREADS, 0, st>>>(S, D.own_cap, D.x_lo, D.x_hi, P.L, halo, D.block_counts);
+    dom_scan_kernel<<<1, 1024, 0, st>>>(D.nblk, D.block_counts, D.block_off, D.ctl, static_cast<DomRecord *>(send_l),
+                                        static_cast<DomRecord *>(send_r), D.max_mig, D.max_halo);
+    dom_pack_kernel<<<D.nblk, CLS_THREADS, 0, st>>>(S, D.own_cap, D.x_lo, D.x_hi, P.L, halo, D.block_off, D.ctl,
+                                                    D.free_stack, static_cast<DomRecord *>(send_l),
+                                                    static_cast<DomRecord *>(send_r), D.max_mig, D.max_halo);
 }
 
-void sbc_launch_unpack_ghosts(const DevState &S, DomainScratch &D, const void *a, const void *b, cudaStream_t st) {
-    const int cap = S.N - D.own_cap;
-    if (cap <= 0) return;
-    unpack_ghosts_kernel<<<(cap + 255) / 256, 256, 0, st>>>(S, D.own_cap, static_cast<const DomRecord *>(a),
-                                                           static_cast<const DomRecord *>(b), D.n_sel + 3);
-}
-
-void sbc_launch_pack_migrants(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
-                              void *buf_right, int max_records, cudaStream_t st) {
-    void *bufs[2] = {buf_left, buf_right};
-    for (int side = 0; side < 2; side++) {
-        if (!bufs[side]) continue;
-        LeaverPred pr{S.pv, S.alive, D.x_lo, D.x_hi, P.L, side};
-        select_slots(D, D.own_cap, pr, st);
-        gather_records_kernel<<<(max_records + 255) / 256, 256, 0, st>>>(S, D.sel, D.n_sel, max_records, 1, 1,
-                                                                        static_cast<DomRecord *>(bufs[side]), D.n_sel + 3);
-    }
-}
-
-void sbc_launch_unpack_migrants(const DevState &S, DomainScratch &D, const void *a, const void *b, int max_records,
-                                cudaStream_t st) {
-    FreePred fp{S.alive};
-    select_slots(D, D.own_cap, fp, st);
-    unpack_migrants_kernel<<<(2 * max_records + 255) / 256, 256, 0, st>>>(S, D.sel, D.n_sel,
-                                                                         static_cast<const DomRecord *>(a),
-                                                                         static_cast<const DomRecord *>(b), D.n_sel + 3);
+void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
+                              const void *sent_l, const void *sent_r, cudaStream_t st) {
+    const int ghost_cap = S.N - D.own_cap;
+    const int n = max(ghost_cap, 2 * D.max_mig);
+    dom_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(S, D.own_cap, static_cast<const DomRecord *>(recv_a),
+                                                      static_cast<const DomRecord *>(recv_b),
+                                                      static_cast<const DomRecord *>(sent_l),
+                                                      static_cast<const DomRecord *>(sent_r), D.max_mig, D.ctl, D.free_stack);
+    dom_commit_kernel<<<1, 1, 0, st>>>(D.ctl);
 }
 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st) {
-    cudaMemsetAsync(D.n_sel + 1, 0, 2 * sizeof(int), st);
-    count_owned_kernel<<<148, 256, 0, st>>>(S, D.own_cap, D.n_sel + 1);
+    cudaMemsetAsync(D.ctl + 8, 0, 2 * sizeof(int), st);
+    count_owned_kernel<<<148, 256, 0, st>>>(S, D.own_cap, D.ctl + 8);
 }

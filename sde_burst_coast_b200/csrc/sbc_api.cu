@@ -407,6 +407,7 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
     }
     sbc_launch_pack_state(S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
     h->dense.sorted_valid = false;
+    if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
     h->host_stats[7]++;
     // the caller's buffers may be reused as soon as we return
     SBC_CUDA(cudaStreamSynchronize(h->stream));
@@ -808,23 +809,25 @@ int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid) {
     return SBC_OK;
 }
 
-int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity) {
+int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int max_migrants, int max_halo) {
     if (!h || world < 1 || rank < 0 || rank >= world) return SBC_ERR_INVALID;
     if (h->S.R != 1) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: one swarm per handle");
     if (h->hp.BC != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: periodic boundary (BC 0) only");
     if (h->S.Npred != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators are not decomposed yet");
-    if (own_capacity < 1 || own_capacity > h->S.N) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad own_capacity");
+    if (own_capacity < 1 || own_capacity > h->S.N || max_migrants < 1 || max_halo < 1)
+        return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad capacities");
     const double w = h->hp.sizeL / world, halo = h->hp.att_range * 1.0001;
-    if (world > 1 && w < (world == 2 ? 2 * halo : halo))
+    if (world > 1 && w < (world == 2 ? 2.1 * halo : 1.05 * halo))
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: slabs narrower than the halo");
     if (!h->use_cells) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: needs the cell-list path");
     SBC_CUDA(cudaSetDevice(h->device));
-    if (!h->dom.enabled) {
-        cudaError_t e = sbc_domain_scratch_alloc(h->dom, h->S.N);
-        if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
-        h->dom.enabled = true;
-    }
+    if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
+    cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity);
+    if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
+    h->dom.enabled = true;
     h->dom.own_cap = own_capacity;
+    h->dom.max_mig = max_migrants;
+    h->dom.max_halo = max_halo;
     h->dom.x_lo = (float)(w * rank);
     h->dom.x_hi = (rank == world - 1) ? (float)h->hp.sizeL : (float)(w * (rank + 1));
     if (!h->S.gid) {  // default ids = slot index
@@ -832,36 +835,27 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity) {
         for (size_t k = 0; k < ids.size(); k++) ids[k] = (uint32_t)k;
         if (int rc = sbc_set_global_ids(h, ids.data())) return rc;
     }
+    sbc_launch_domain_reset(h->S, h->dom, h->stream);
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
     return SBC_OK;
 }
 
-size_t sbc_domain_buffer_bytes(int max_records) { return (size_t)(max_records + 1) * sbc_domain_record_bytes(); }
+size_t sbc_domain_buffer_bytes(int max_migrants, int max_halo) {
+    return (size_t)(1 + max_migrants + max_halo) * sbc_domain_record_bytes();
+}
 
-int sbc_domain_pack_halos(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records) {
-    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+int sbc_domain_pack(sbc_handle *h, void *send_left_dev, void *send_right_dev) {
+    if (!h || !h->dom.enabled || !send_left_dev || !send_right_dev) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_pack_halos(h->P, h->S, h->dom, buf_left_dev, buf_right_dev, max_records, h->stream);
-    h->host_stats[7] += 4;
+    sbc_launch_domain_pack(h->P, h->S, h->dom, send_left_dev, send_right_dev, h->stream);
+    h->host_stats[7] += 3;
     return SBC_OK;
 }
-int sbc_domain_unpack_ghosts(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev) {
+int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
+                      const void *sent_right_dev) {
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_unpack_ghosts(h->S, h->dom, buf_a_dev, buf_b_dev, h->stream);
-    h->host_stats[7] += 1;
-    return SBC_OK;
-}
-int sbc_domain_pack_migrants(sbc_handle *h, void *buf_left_dev, void *buf_right_dev, int max_records) {
-    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
-    SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_pack_migrants(h->P, h->S, h->dom, buf_left_dev, buf_right_dev, max_records, h->stream);
-    h->host_stats[7] += 4;
-    return SBC_OK;
-}
-int sbc_domain_unpack_migrants(sbc_handle *h, const void *buf_a_dev, const void *buf_b_dev, int max_records) {
-    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
-    SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_unpack_migrants(h->S, h->dom, buf_a_dev, buf_b_dev, max_records, h->stream);
+    sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
     h->host_stats[7] += 2;
     return SBC_OK;
 }
@@ -869,12 +863,12 @@ int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
     sbc_launch_count_owned(h->S, h->dom, h->stream);
-    int v[4];
-    SBC_CUDA(cudaMemcpyAsync(v, h->dom.n_sel, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    int v[16];
+    SBC_CUDA(cudaMemcpyAsync(v, h->dom.ctl, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
     SBC_CUDA(cudaStreamSynchronize(h->stream));
-    if (n_owned) *n_owned = v[1];
-    if (n_ghost) *n_ghost = v[2];
-    if (overflow_events) *overflow_events = v[3];
+    if (n_owned) *n_owned = v[8];
+    if (n_ghost) *n_ghost = v[9];
+    if (overflow_events) *overflow_events = v[6];
     return SBC_OK;
 }
 int sbc_get_global_ids(sbc_handle *h, uint32_t *gid) {

@@ -91,24 +91,24 @@ void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, con
 
 // --- domain decomposition of one large swarm (domain.cu) --------------------------------------------
 struct DomainScratch {
-    int *sel = nullptr;      // selected slot indices
-    int *n_sel = nullptr;    // [0] selection count, [1] owned, [2] ghosts, [3] overflow events
-    void *cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    int *block_counts = nullptr, *block_off = nullptr;  // [nblk][4] per-block category counts / offsets
+    int *free_stack = nullptr;                          // free owned slots, popped from the top
+    int *ctl = nullptr;  // [0] free_top [1] free_base [2..5] totals (leave L/R, halo L/R) [6] overflow events
+                         // [7] migrants taken by the last unpack [8] owned [9] ghosts
+    int nblk = 0;
     int own_cap = 0;         // slots [0, own_cap) are owned / free, [own_cap, N) ghosts
+    int max_mig = 0, max_halo = 0;  // record capacities of one buffer: [header | max_mig | max_halo]
     float x_lo = 0.f, x_hi = 0.f;
     bool enabled = false;
 };
 size_t sbc_domain_record_bytes(void);
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int n_slots);
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap);
 void sbc_domain_scratch_free(DomainScratch &D);
-void sbc_launch_pack_halos(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
-                           void *buf_right, int max_records, cudaStream_t st);
-void sbc_launch_unpack_ghosts(const DevState &S, DomainScratch &D, const void *a, const void *b, cudaStream_t st);
-void sbc_launch_pack_migrants(const DevParams &P, const DevState &S, DomainScratch &D, void *buf_left,
-                              void *buf_right, int max_records, cudaStream_t st);
-void sbc_launch_unpack_migrants(const DevState &S, DomainScratch &D, const void *a, const void *b, int max_records,
-                                cudaStream_t st);
+void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t st);
+void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
+                            cudaStream_t st);
+void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
+                              const void *sent_l, const void *sent_r, cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------

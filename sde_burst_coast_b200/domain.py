@@ -36,7 +36,7 @@ def neighbours(rank, world):
 def check_geometry(L, att_range, world):
     """Slabs must be at least one halo wide (two when both neighbours are the same rank)."""
     w, halo = L / world, att_range * 1.0001
-    if world > 1 and w < (2 * halo if world == 2 else halo):
+    if world > 1 and w < (2.1 * halo if world == 2 else 1.05 * halo):
         raise ValueError('slab width %.3f is narrower than the halo requirement for att_range %.3f' % (w, att_range))
 
 
@@ -95,20 +95,22 @@ class SlabSwarm:
         self.torch = torch
         self.rank, self.world, self.n_global = rank, world, int(n_global)
         mean_own = n_global / world
-        halo_frac = min(1.0, 2 * sp.att_range * 1.0001 / (sp.sizeL / world))
+        halo_frac = min(1.0, sp.att_range * 1.0001 / (sp.sizeL / world))
         self.own_cap = int(own_capacity or (mean_own * 1.5 + 1024))
-        self.ghost_cap = 0 if world == 1 else int(ghost_capacity or (mean_own * halo_frac * 2 + 1024))
-        self.max_records = int(max_records or max(1024, self.ghost_cap // 2 + 256))
+        self.max_halo = int(max_records or (mean_own * halo_frac * 2 + 1024))      # records per edge band
+        self.max_mig = int(max(256, self.max_halo // 8))                            # migrants per edge per step
+        self.ghost_cap = 0 if world == 1 else int(ghost_capacity or (2 * self.max_halo + 2 * self.max_mig))
         sp2 = type(sp).from_buffer_copy(sp)
         sp2.path = P.PATH_CELLLIST
         self.sp = sp2
         self.dev = torch.device('cuda', device)
         self.swarm = Swarm(sp2, self.own_cap + self.ghost_cap, 0, 1, seed=seed, device=device, stream=stream)
         lib, h = self.swarm.lib, self.swarm.h
-        self.swarm._check(lib.sbc_domain_config(h, rank, world, self.own_cap))
-        nbytes = lib.sbc_domain_buffer_bytes(self.max_records)
+        self.swarm._check(lib.sbc_domain_config(h, rank, world, self.own_cap, self.max_mig, self.max_halo))
+        nbytes = lib.sbc_domain_buffer_bytes(self.max_mig, self.max_halo)
         mk = lambda: torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
         self.send_l, self.send_r, self.recv_l, self.recv_r = mk(), mk(), mk(), mk()
+        self.primed = False   # ghosts of the current positions are in place
 
     # ---- state in / out (host arrays indexed by GLOBAL agent id) -------------------------------
     def scatter_initial(self, state):
@@ -129,6 +131,7 @@ class SlabSwarm:
         self.swarm.set_state(alive=alive, **local)
         u32p = ctypes.POINTER(ctypes.c_uint32)
         self.swarm._check(self.swarm.lib.sbc_set_global_ids(self.swarm.h, gid.ctypes.data_as(u32p)))
+        self.primed = False
 
     def owned_state(self):
         """(gids, state dict) of the agents this rank owns now."""
@@ -144,21 +147,18 @@ class SlabSwarm:
         self.swarm._check(self.swarm.lib.sbc_domain_counts(self.swarm.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return dict(owned=a.value, ghosts=b.value, overflow_events=c.value)
 
-    # ---- the two exchange phases around one step ----------------------------------------------
+    # ---- the exchange: once before the first step, then after every step -------------------------
     def _p(self, t):
         return ctypes.c_void_p(t.data_ptr())
 
-    def pack_halos(self):
-        self.swarm._check(self.swarm.lib.sbc_domain_pack_halos(self.swarm.h, self._p(self.send_l), self._p(self.send_r), self.max_records))
+    def pack(self):
+        """Classify the owned agents and fill both send buffers ([header | migrants | halo])."""
+        self.swarm._check(self.swarm.lib.sbc_domain_pack(self.swarm.h, self._p(self.send_l), self._p(self.send_r)))
 
-    def unpack_ghosts(self):
-        self.swarm._check(self.swarm.lib.sbc_domain_unpack_ghosts(self.swarm.h, self._p(self.recv_l), self._p(self.recv_r)))
-
-    def pack_migrants(self):
-        self.swarm._check(self.swarm.lib.sbc_domain_pack_migrants(self.swarm.h, self._p(self.send_l), self._p(self.send_r), self.max_records))
-
-    def unpack_migrants(self):
-        self.swarm._check(self.swarm.lib.sbc_domain_unpack_migrants(self.swarm.h, self._p(self.recv_l), self._p(self.recv_r), self.max_records))
+    def unpack(self):
+        """Insert the incoming migrants, rebuild the ghosts (incoming halo + my own outgoing migrants)."""
+        self.swarm._check(self.swarm.lib.sbc_domain_unpack(self.swarm.h, self._p(self.recv_l), self._p(self.recv_r),
+                                                           self._p(self.send_l), self._p(self.send_r)))
 
     def step_local(self, s):
         self.swarm.step(s, 1)
@@ -168,42 +168,43 @@ class SlabSwarm:
 
 
 def step_distributed(slab, transport, s_first, n_steps):
-    """Advance one rank's slab (world > 1: a DistTransport moves the buffers between ranks)."""
+    """Advance one rank's slab (world > 1: a DistTransport moves the buffers between ranks). One exchange per
+    step: [pack -> exchange -> unpack] once before the first step, then after every step."""
+    def exchange():
+        slab.pack()
+        transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
+        slab.unpack()
+    if slab.world > 1 and not slab.primed:
+        exchange()
+        slab.primed = True
     for s in range(s_first, s_first + n_steps):
-        if slab.world > 1:
-            slab.pack_halos()
-            transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
-            slab.unpack_ghosts()
         slab.step_local(s)
         if slab.world > 1:
-            slab.pack_migrants()
-            transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
-            slab.unpack_migrants()
+            exchange()
 
 
 def step_loopback(slabs, s_first, n_steps):
     """Advance all slabs held in this process in lock step (tests / single-GPU emulation)."""
     world = len(slabs)
     tr = LoopbackTransport(world)
+
+    def exchange():
+        for sl in slabs:
+            sl.pack()
+            tr.post(sl.rank, sl.send_l, sl.send_r)
+        slabs[0].torch.cuda.synchronize()
+        for sl in slabs:
+            tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
+            sl.unpack()
+    if world > 1 and not all(sl.primed for sl in slabs):
+        exchange()
+        for sl in slabs:
+            sl.primed = True
     for s in range(s_first, s_first + n_steps):
-        if world > 1:
-            for sl in slabs:
-                sl.pack_halos()
-                tr.post(sl.rank, sl.send_l, sl.send_r)
-            slabs[0].torch.cuda.synchronize()
-            for sl in slabs:
-                tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
-                sl.unpack_ghosts()
         for sl in slabs:
             sl.step_local(s)
         if world > 1:
-            for sl in slabs:
-                sl.pack_migrants()
-                tr.post(sl.rank, sl.send_l, sl.send_r)
-            slabs[0].torch.cuda.synchronize()
-            for sl in slabs:
-                tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
-                sl.unpack_migrants()
+            exchange()
 
 
 def gather_global(slabs, n_global):

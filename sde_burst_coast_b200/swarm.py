@@ -53,12 +53,10 @@ ABI = [
     ('sbc_bench_pair_pass', ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     ('sbc_set_global_ids', ctypes.c_int, [_vp, _u32p]),
     ('sbc_get_global_ids', ctypes.c_int, [_vp, _u32p]),
-    ('sbc_domain_config', ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
-    ('sbc_domain_buffer_bytes', ctypes.c_size_t, [ctypes.c_int]),
-    ('sbc_domain_pack_halos', ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
-    ('sbc_domain_unpack_ghosts', ctypes.c_int, [_vp, _vp, _vp]),
-    ('sbc_domain_pack_migrants', ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
-    ('sbc_domain_unpack_migrants', ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int]),
+    ('sbc_domain_config', ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    ('sbc_domain_buffer_bytes', ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    ('sbc_domain_pack', ctypes.c_int, [_vp, _vp, _vp]),
+    ('sbc_domain_unpack', ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ('sbc_domain_counts', ctypes.c_int, [_vp, _i32p, _i32p, _i32p]),
 ]
 

@@ -47,13 +47,13 @@ def test_halo_makes_zone_counts_exact(world):
     slabs = _slabs(sp, st, N, world, seed=3)
     tr = LoopbackTransport(world)
     for sl in slabs:
-        sl.pack_halos()
+        sl.pack()
         tr.post(sl.rank, sl.send_l, sl.send_r)
     torch.cuda.synchronize()
     total_owned = 0
     for sl in slabs:
         tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
-        sl.unpack_ghosts()
+        sl.unpack()
         got = sl.swarm.pair_interactions(PP.PAIR_ACTIVE_ROWS, want_nn=False)
         gid, own = sl.owned_state()
         slots = np.where(sl.swarm.get_state()['alive'][:sl.own_cap] == 1)[0]
