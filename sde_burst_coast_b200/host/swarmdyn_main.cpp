@@ -13,8 +13,11 @@
 //   -V 1             Voronoi neighbour rule (InteractionVoronoiF2F, agents_interact.cpp:26-77, the shipped
 //                    default of the reference): tanks / open domains of up to 1024 agents without predators
 // Default neighbour rule: METRIC (InteractionGlobal, agents_interact.cpp:144-157) - see DESIGN.md section 2.
-// Output: -J 0 text files exactly as the reference writes them; -J 1 needs libhdf5, which this
-// image does not have: the run then warns once and writes the text files instead.
+// Output: -J 0 text files exactly as the reference writes them; -J 1 writes out_<fileID>.h5 with the
+// reference's datasets (/part, /pred, /swarm, /swarm_fishNet; under /<fileID>/ when fileID != "xx") through
+// the dependency-free writer h5mini.hpp (contiguous float64 datasets; no libhdf5 in this image). The
+// reference's "extend" mode (append a run to an existing file, h5tools.cpp:174-178) is not reproduced:
+// every run writes a fresh file.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -31,6 +34,7 @@
 #include <vector>
 
 #include "../../include/sbc.h"
+#include "h5mini.hpp"
 
 namespace {
 
@@ -483,14 +487,15 @@ int main(int argc, char **argv) {
     SBC_CHECK(sbc_set_state(h, X.data(), Y.data(), nullptr, nullptr, PHI.data(), VP.data(), nullptr, nullptr,
                             nullptr, nullptr, nullptr));
     std::cout << "Go";  // swarmdyn.cpp:61
-    if (p.out_h5 && (p.out_mean || p.out_particle))
-        fprintf(stderr, "\nswarmdyn: built without libhdf5 - writing the -J 0 text files instead of out_%s.h5\n", p.fileID.c_str());
 
     auto suffix = [&](int r) { return r == 0 ? p.fileID : p.fileID + "_" + std::to_string(r); };
     std::vector<double> part((size_t)R * N * 7), preds((size_t)R * std::max(p.Npred, 1) * 6);
     std::vector<uint8_t> alive((size_t)R * N);
     std::vector<int32_t> n_alive(R), n_dead(R);
     std::vector<std::vector<std::vector<double>>> swarm_rows(R), net_rows(R);
+    // -J 1: /part and /pred are collected in memory and written once at the end
+    std::vector<std::vector<double>> h5_part(R), h5_pred(R);
+    std::vector<int> h5_pred_first(R, -1);
     const int s_trans = (int)(p.trans_time / p.dt), s_pred = (int)(p.pred_time / p.dt);
     int outstep = 0;
     const bool want_output = p.out_mean || p.out_particle;
@@ -520,10 +525,23 @@ int main(int argc, char **argv) {
                     if (pred_phase)
                         net_rows[r].push_back(out_swarm_fishnet(rows, al, preds.data() + (size_t)r * p.Npred * 6, p, n_dead[r]));
                 }
-                if (p.out_particle) {
+                if (p.out_particle && !p.out_h5) {
                     append_particles(p.location + "part_" + suffix(r) + ".dat", rows, al, N, 7);
                     if (pred_phase && p.Npred > 0)
                         append_particles(p.location + "pred_" + suffix(r) + ".dat", preds.data() + (size_t)r * p.Npred * 6, nullptr, p.Npred, 6);
+                }
+                if (p.out_particle && p.out_h5 && outstep < p.total_outstep) {
+                    // /part: (total_outstep, N, 7), rows by agent id, dead agents stay zero (swarmdyn.cpp:561-600)
+                    if (h5_part[r].empty()) h5_part[r].assign((size_t)p.total_outstep * N * 7, 0.0);
+                    std::copy(rows, rows + (size_t)N * 7, h5_part[r].begin() + (size_t)outstep * N * 7);
+                    if (pred_phase && p.Npred > 0) {  // /pred: (outsteps left at its first output, Npred, 6)
+                        if (h5_pred_first[r] < 0) {
+                            h5_pred_first[r] = outstep;
+                            h5_pred[r].assign((size_t)(p.total_outstep - outstep) * p.Npred * 6, 0.0);
+                        }
+                        std::copy(preds.data() + (size_t)r * p.Npred * 6, preds.data() + (size_t)(r + 1) * p.Npred * 6,
+                                  h5_pred[r].begin() + (size_t)(outstep - h5_pred_first[r]) * p.Npred * 6);
+                    }
                 }
             }
             outstep++;
@@ -532,8 +550,29 @@ int main(int argc, char **argv) {
     }
     (void)s_pred;
     for (int r = 0; r < R; r++) {  // DataCreateSaveWrite :453-461 writes once, at the last output step
-        write_rows(p.location + "swarm_" + suffix(r) + ".dat", swarm_rows[r]);
-        write_rows(p.location + "swarm_fishNet_" + suffix(r) + ".dat", net_rows[r]);
+        if (!p.out_h5) {
+            write_rows(p.location + "swarm_" + suffix(r) + ".dat", swarm_rows[r]);
+            write_rows(p.location + "swarm_fishNet_" + suffix(r) + ".dat", net_rows[r]);
+            continue;
+        }
+        // out_<fileID>.h5 (h5tools.cpp:181-217): datasets at the root for fileID "xx", else under /<fileID>/
+        h5mini::Writer w(p.fileID == "xx" ? "" : p.fileID);
+        auto flat = [](const std::vector<std::vector<double>> &rows, size_t n_rows, size_t width) {
+            std::vector<double> out(n_rows * width, 0.0);
+            for (size_t k = 0; k < rows.size() && k < n_rows; k++) std::copy(rows[k].begin(), rows[k].end(), out.begin() + k * width);
+            return out;
+        };
+        int n_sets = 0;
+        if (!h5_part[r].empty()) { w.add("part", {(uint64_t)p.total_outstep, (uint64_t)N, 7}, h5_part[r]); n_sets++; }
+        if (!h5_pred[r].empty()) { w.add("pred", {(uint64_t)(p.total_outstep - h5_pred_first[r]), (uint64_t)p.Npred, 6}, h5_pred[r]); n_sets++; }
+        if (!swarm_rows[r].empty()) { w.add("swarm", {(uint64_t)p.total_outstep, 16}, flat(swarm_rows[r], p.total_outstep, 16)); n_sets++; }
+        if (!net_rows[r].empty()) {
+            const size_t n_net = (size_t)p.total_outstep - (swarm_rows[r].size() - net_rows[r].size());
+            w.add("swarm_fishNet", {(uint64_t)n_net, 4}, flat(net_rows[r], n_net, 4));
+            n_sets++;
+        }
+        if (n_sets && !w.write(p.location + "out_" + suffix(r) + ".h5"))
+            fprintf(stderr, "swarmdyn: cannot write %sout_%s.h5\n", p.location.c_str(), suffix(r).c_str());
     }
     if (outstep == 1) {  // swarmdyn.cpp:93-95 "equilibration run": final positions and velocities
         SBC_CHECK(sbc_get_particles(h, part.data(), alive.data()));

@@ -123,3 +123,34 @@ def test_c1_statistics_match_the_shipped_reference_binary(tmp_path):
         b = np.array([run[:, c].mean() for run in ours])
         se = np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size)
         assert abs(a.mean() - b.mean()) <= 4 * se + 0.01 * abs(a.mean()), (name, a.mean(), b.mean(), se)
+
+
+def test_h5_output_matches_text_output(tmp_path):
+    """-J 1 (out_xx.h5 through the built-in writer) holds exactly what -J 0 writes as text, in the
+    reference's dataset layout: /part (outsteps, N, 7), /pred, /swarm (outsteps, 16), /swarm_fishNet."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import h5mini_read
+    d = P.get_base_params(0.5, 2, mode='natPred')
+    P.selection_line_parameter(d, 2)
+    d.update(output_mode=1, N=30, pred_speed0=20, kill_rate=50, N_confu=40)
+    a, b = tmp_path / 'h5', tmp_path / 'txt'
+    a.mkdir()
+    b.mkdir()
+    _run(dict(d, out_h5=1), a, ['-Z', '9'])
+    _run(dict(d, out_h5=0), b, ['-Z', '9'])
+    f = h5mini_read.File(str(a / 'out_xx.h5'))
+    assert sorted(f.links()) == ['part', 'pred', 'swarm', 'swarm_fishNet']
+    part, pred, swarm, net = (f.read('/' + k) for k in ('part', 'pred', 'swarm', 'swarm_fishNet'))
+    sw_txt = _rows(b / 'swarm_xx.dat')
+    assert swarm.shape == sw_txt.shape and part.shape == (swarm.shape[0], 30, 7)
+    assert np.allclose(swarm[:, :15], sw_txt[:, :15], rtol=2e-5, atol=1e-6, equal_nan=True)   # text has 6 digits
+    assert pred.shape[1:] == (1, 6) and net.shape == (pred.shape[0], 4)
+    pred_txt = _rows(b / 'pred_xx.dat')
+    assert np.allclose(pred[:, 0, :], pred_txt, rtol=2e-5, atol=1e-6)
+    # fileID other than "xx": datasets under /<fileID>/
+    c = tmp_path / 'grp'
+    c.mkdir()
+    _run(dict(d, out_h5=1, fileID='run3'), c, ['-Z', '9'])
+    g = h5mini_read.File(str(c / 'out_run3.h5'))
+    assert list(g.links()) == ['run3'] and np.array_equal(g.read('/run3/part'), part)

@@ -121,3 +121,33 @@ def test_geometric_table_matches_rejection_loop():
     assert ks.min() >= 1 and ks.max() <= max_steps + 1
     assert abs(ks.mean() - (1 - (1 - p) ** (max_steps + 1)) / p) < 3 * (1 / p) / np.sqrt(ks.size)
     assert abs((ks == max_steps + 1).mean() - (1 - p) ** max_steps) < 2e-3
+
+
+def test_h5_writer_round_trip(tmp_path):
+    """h5mini.hpp (the executable's -J 1 writer) against the independent reader tests/h5mini_read.py: version-0
+    superblock, old-style groups (B-tree + heap + symbol node), contiguous IEEE F64LE datasets."""
+    import h5mini_read
+    host = os.path.dirname(EXE)
+    subprocess.run(['make', '-C', host, 'h5mini_selftest'], check=True, stdout=subprocess.DEVNULL)
+    tool = os.path.join(host, 'h5mini_selftest')
+    for group in ('', 'run7'):
+        path = str(tmp_path / ('t%s.h5' % group))
+        subprocess.run([tool, path] + ([group] if group else []), check=True)
+        f = h5mini_read.File(path)
+        root = f.links()
+        if group:
+            assert list(root) == [group]
+            names = sorted(f.links(root[group]))
+        else:
+            names = sorted(root)
+        assert names == ['part', 'pred', 'swarm', 'swarm_fishNet']
+        pre = '/' + group + '/' if group else '/'
+        part = f.read(pre + 'part')
+        assert part.shape == (3, 4, 7) and np.array_equal(part.ravel(), 0.5 * np.arange(84) - 3.25)
+        assert np.array_equal(f.read(pre + 'swarm').ravel(), 1.0 / (1.0 + np.arange(48)))
+        assert f.read(pre + 'pred').shape == (2, 1, 6) and np.all(f.read(pre + 'swarm_fishNet') == 2.5)
+    # a truncated file is rejected by the reader (end-of-file address check)
+    raw = open(path, 'rb').read()
+    open(path, 'wb').write(raw[:-8])
+    with pytest.raises(h5mini_read.H5Error):
+        h5mini_read.File(path)
