@@ -4,11 +4,14 @@
 // 172-250): a pair farther apart than att_range contributes nothing, and every agent within
 // att_range of row i lies in the 3 x 3 block of cells around i's cell.
 //
-// Build (every call; stable, hence deterministic): cell key per agent -> CUB radix sort of
-// (key, agent id) -> first/last sorted position per cell -> agents gathered in cell order.
-// Pass: rows that start a burst are compacted (pair_allpairs.cu), one warp per active row, the lanes
-// stride over the agents of the nine cells (coalesced float4 reads of the gathered copy), zone
-// decisions exactly as on the all-pairs path (FP32 band + FP64 re-decision), warp-shuffle reduction.
+// Build (stable, hence deterministic): cell key per agent -> CUB radix sort of (key, agent id) ->
+// first/last sorted position per cell. Cells are att_range + skin wide, so one build serves several
+// steps (Verlet skin): a pass looks around the row's BUILD-TIME cell and reads the candidates' CURRENT
+// positions, which is exact as long as nobody moved more than skin/2 since the build - the host side
+// bounds that by (steps since build) x (largest possible speed) x dt and rebuilds in time.
+// Pass: rows that start a burst are compacted (pair_allpairs.cu), one block per active row, threads
+// stride over the agents of the nine cells, zone decisions exactly as on the all-pairs path (FP32
+// band + FP64 re-decision), fixed-order block reduction.
 #include <cub/device/device_radix_sort.cuh>
 
 #include "sbc_kernels.cuh"
@@ -81,13 +84,10 @@ __global__ void cell_key_kernel(const float4 *__restrict__ pv, int n, const Cell
 }
 
 __global__ void cell_bounds_kernel(const uint32_t *__restrict__ key, const int *__restrict__ idx, int n,
-                                   uint32_t dead_key, const float4 *__restrict__ pv,
-                                   int *__restrict__ cell_start, int *__restrict__ cell_end,
-                                   float4 *__restrict__ spv) {
+                                   uint32_t dead_key, int *__restrict__ cell_start, int *__restrict__ cell_end) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t k = key[r];
-    spv[r] = pv[idx[r]];
     if (k == dead_key) return;
     if (r == 0 || key[r - 1] != k) cell_start[k] = r;
     if (r == n - 1 || key[r + 1] != k) cell_end[k] = r + 1;
@@ -99,7 +99,7 @@ template <bool PERIODIC>
 __global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                   const int *__restrict__ cell_start, const int *__restrict__ cell_end,
-                  const float4 *__restrict__ spv, const int *__restrict__ sidx,
+                  const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
                   const int *__restrict__ list, const int *__restrict__ count) {
     __shared__ float shf[CELLS_THREADS / 32][6];
     __shared__ int shi[CELLS_THREADS / 32][3];
@@ -111,7 +111,9 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
     for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
         const int i = list[k];  // single swarm on this path: slot index == global index
         const float4 pi = S.pv[i];
-        const int cx = cell_coord(pi.x, g.ox, g.inv_w, g.ncx), cy = cell_coord(pi.y, g.oy, g.inv_h, g.ncy);
+        // the row's cell at build time (agents alive now were alive then: nobody is born between builds)
+        const int ck = (int)build_key[i];
+        const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
         RowAcc A;
         row_acc_clear(A);
         for (int oy = -1; oy <= 1; oy++) {
@@ -124,8 +126,9 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
                 const int r0 = cell_start[c], r1 = cell_end[c];
                 n_cand += (threadIdx.x == 0) ? (unsigned long long)(r1 - r0) : 0ull;
                 for (int r = r0 + threadIdx.x; r < r1; r += CELLS_THREADS) {
-                    if (sidx[r] == i) continue;
-                    const float4 pj = spv[r];
+                    const int j = sidx[r];
+                    if (j == i) continue;
+                    const float4 pj = S.pv[j];   // current position (NaN if the agent died since the build)
                     float dx = pj.x - pi.x, dy = pj.y - pi.y;
                     if (PERIODIC) {
                         dx = sbc_delta_pbc(pi.x, pj.x, P);
@@ -178,12 +181,19 @@ bool sbc_cells_supported(const DevParams &P, int N, int R) {
     return true;
 }
 
+// widest skin (up to `want`) that still leaves three cells per axis in a periodic box
+float sbc_cells_skin(const DevParams &P, float want) {
+    if (P.BC != 0) return want;
+    const double room = (double)P.L / 3.0 / 1.00001 - (double)P.att;
+    return (float)fmax(0.0, fmin((double)want, room));
+}
+
 cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
     cudaError_t e;
     C.max_per_axis = 2048;
     CellGeom hg;
     if (P.BC == 0) {
-        const int n = (int)floor((double)P.L / ((double)P.att * 1.00001));
+        const int n = (int)floor((double)P.L / (((double)P.att + (double)C.skin) * 1.00001));
         hg.ox = hg.oy = 0.f;
         hg.inv_w = hg.inv_h = (float)((double)n / (double)P.L);
         hg.ncx = hg.ncy = n;
@@ -196,7 +206,6 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
     if ((e = cudaMalloc((void **)&C.key_out, (size_t)N * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.idx_in, (size_t)N * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.idx_out, (size_t)N * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&C.spv, (size_t)N * sizeof(float4))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.cell_start, C.ncells * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.cell_end, C.ncells * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.bbox, 4 * sizeof(int))) != cudaSuccess) return e;
@@ -211,7 +220,7 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
 }
 
 void sbc_cell_scratch_free(CellScratch &C) {
-    cudaFree(C.key_in); cudaFree(C.key_out); cudaFree(C.idx_in); cudaFree(C.idx_out); cudaFree(C.spv);
+    cudaFree(C.key_in); cudaFree(C.key_out); cudaFree(C.idx_in); cudaFree(C.idx_out);
     cudaFree(C.cell_start); cudaFree(C.cell_end); cudaFree(C.bbox); cudaFree(C.geom); cudaFree(C.cub_tmp);
     C = CellScratch();
 }
@@ -223,7 +232,7 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
     if (P.BC != 0) {
         bbox_init_kernel2<<<1, 1, 0, st>>>(C.bbox);
         bbox_kernel2<<<148, 256, 0, st>>>(S.pv, N, C.bbox);
-        cell_geom_kernel<<<1, 1, 0, st>>>(C.bbox, P.att * 1.00001f, C.max_per_axis, geom);
+        cell_geom_kernel<<<1, 1, 0, st>>>(C.bbox, (P.att + C.skin) * 1.00001f, C.max_per_axis, geom);
     }
     const uint32_t dead_key = (uint32_t)C.ncells;
     cell_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, geom, dead_key, C.key_in, C.idx_in);
@@ -231,7 +240,7 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
                                     C.key_bits, st);
     cudaMemsetAsync(C.cell_start, 0, C.ncells * sizeof(int), st);
     cudaMemsetAsync(C.cell_end, 0, C.ncells * sizeof(int), st);
-    cell_bounds_kernel<<<blocks, 256, 0, st>>>(C.key_out, C.idx_out, N, dead_key, S.pv, C.cell_start, C.cell_end, C.spv);
+    cell_bounds_kernel<<<blocks, 256, 0, st>>>(C.key_out, C.idx_out, N, dead_key, C.cell_start, C.cell_end);
 }
 
 // active rows must have been compacted into S.active_list / S.active_count (sbc_launch_compact_rows)
@@ -239,9 +248,9 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
     const int blocks = (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
     if (P.BC == 0)
-        pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
+        pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out,
                                                         S.active_list, S.active_count);
     else
-        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.spv, C.idx_out,
+        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out,
                                                          S.active_list, S.active_count);
 }

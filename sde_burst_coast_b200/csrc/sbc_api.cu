@@ -35,10 +35,13 @@ struct sbc_handle {
     bool dense_ready;
     CellScratch cells;
     bool cells_ready, use_cells;
+    bool cells_valid;        // the cell order on the device belongs to the current agents
+    int cells_age, cells_max_age;  // steps since the build / steps one build may serve (Verlet skin)
+    double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
     // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
-    cudaGraphExec_t step_graph[2];
-    bool step_graph_ok[2];
+    cudaGraphExec_t step_graph[4];   // [2 * rebuild + pred_phase]
+    bool step_graph_ok[4];
     uint32_t *step_dev;
     int64_t step_dev_value;
     bool use_graphs;
@@ -208,7 +211,11 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->dense_ready = false;
     h->cells_ready = false;
     h->use_cells = false;
-    h->step_graph_ok[0] = h->step_graph_ok[1] = false;
+    h->cells_valid = false;
+    h->cells_age = 0;
+    h->cells_max_age = 1;
+    h->v0_max = 1.0;
+    for (int k = 0; k < 4; k++) h->step_graph_ok[k] = false;
     h->step_dev = nullptr;
     h->step_dev_value = -1;
     h->use_graphs = getenv("SBC_NO_GRAPHS") == nullptr;
@@ -287,7 +294,7 @@ int sbc_destroy(sbc_handle *h) {
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     cudaFree(h->S.gid);
-    for (int k = 0; k < 2; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
+    for (int k = 0; k < 4; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
     cudaFree(h->step_dev);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
@@ -322,8 +329,19 @@ static int ensure_dense(sbc_handle *h) {
     return SBC_OK;
 }
 
+// How many steps one cell build may serve: nobody moves faster than max(initial speed, largest force /
+// friction) (vproj' = vproj (1 - beta dt) + f dt), a wall reflection can add twice the overshoot
+// (agents_dynamics.cpp:432-470); every agent must stay within skin/2 of where the build saw it.
+static void set_cells_max_age(sbc_handle *h) {
+    const double vmax = std::fmax(h->v0_max, std::fmax(h->hp.soc_strength, h->hp.env_strength) / h->hp.beta);
+    const double per_step = (h->hp.BC == 0 ? 1.0 : 3.0) * vmax * h->hp.dt * 1.01;
+    const double k = (h->cells.skin > 0.f && per_step > 0) ? std::floor(0.5 * h->cells.skin / per_step) : 0.0;
+    h->cells_max_age = (int)std::fmin(std::fmax(k, 0.0), 64.0);
+}
+
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
-static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false) {
+static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false,
+                            bool rebuild_cells = true) {
     if (all_rows && h->P.voronoi) {  // Delaunay-filtered candidates: every alive row through the rows kernel
         sbc_launch_compact_rows(h->P, h->S, true, h->stream, true);
         sbc_launch_pair_rows(h->P, h->S, h->stream);
@@ -346,17 +364,23 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
         h->host_stats[7] += clear_inactive ? 2 : 1;
         if (h->use_cells) {
             if (!h->cells_ready) {
+                // skin: a fifth of att_range when the box allows; one build then serves several steps
+                h->cells.skin = h->dom.enabled ? 0.f : sbc_cells_skin(h->P, 0.2f * h->P.att);
                 cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
                 if (e != cudaSuccess) {
                     sbc_cell_scratch_free(h->cells);
                     return fail(h, SBC_ERR_NOMEM, std::string("cell list scratch: ") + cudaGetErrorString(e));
                 }
                 h->cells_ready = true;
+                set_cells_max_age(h);
             }
-            sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
+            if (rebuild_cells) {
+                sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
+                h->host_stats[6]++;
+                h->host_stats[7] += 4;
+            }
             sbc_launch_pair_cells(h->P, h->S, h->cells, h->stream);
-            h->host_stats[6]++;
-            h->host_stats[7] += 5;
+            h->host_stats[7] += 1;
         } else {
             sbc_launch_pair_rows(h->P, h->S, h->stream);
         }
@@ -407,6 +431,11 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
     }
     sbc_launch_pack_state(S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
     h->dense.sorted_valid = false;
+    h->cells_valid = false;
+    if (vproj)
+        for (size_t g = 0; g < total; g++)
+            if (vproj[g] > h->v0_max) h->v0_max = vproj[g];
+    if (h->cells_ready) set_cells_max_age(h);
     if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
     h->host_stats[7]++;
     // the caller's buffers may be reused as soon as we return
@@ -567,7 +596,11 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             // the fixed part of the step (compaction, pair pass, update, predator move + kill) is
             // replayed from a CUDA graph: one launch instead of ~6-15. The step index then lives in
             // device memory and is advanced by the graph's last node.
-            const int gk = pred_phase ? 1 : 0;
+            // cell order: rebuilt when stale (Verlet skin used up), after a state change, and always in
+            // decomposed mode (ghosts change every step)
+            const bool rebuild = !h->use_cells || !h->cells_ready || !h->cells_valid || h->dom.enabled ||
+                                 h->cells_age > h->cells_max_age;
+            const int gk = (pred_phase ? 1 : 0) + (rebuild ? 2 : 0);
             const bool graphable = h->use_graphs && !injected && !S.flags && (!h->use_cells || h->cells_ready) &&
                                    h->stream != nullptr && h->stream != cudaStreamLegacy &&
                                    h->stream != cudaStreamPerThread;  // the default streams cannot be captured
@@ -583,9 +616,9 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     unsigned long long keep[8];
                     std::memcpy(keep, h->host_stats, sizeof(keep));  // the capture pass launches nothing
                     SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                    int rc = launch_pair_pass(h, 0, false);
-                    sbc_launch_update(h->P, S, 0, h->step_dev, gk, h->stream);
-                    if (gk) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
+                    int rc = launch_pair_pass(h, 0, false, false, rebuild);
+                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream);
+                    if (pred_phase) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
                     sbc_launch_step_advance(h->step_dev, h->stream);
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     if (rc) return rc;
@@ -600,16 +633,20 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                 h->step_dev_value = s + 1;
                 h->host_stats[0]++;
                 h->host_stats[1]++;
-                h->host_stats[7] += (h->use_cells ? 7 : 2) + (gk ? 1 : 0);
-                if (h->use_cells) h->host_stats[6]++;
+                h->host_stats[7] += (h->use_cells ? (rebuild ? 7 : 3) : 2) + (pred_phase ? 2 : 0);
+                if (h->use_cells && rebuild) h->host_stats[6]++;
             } else {
-                if (int rc = launch_pair_pass(h, 0, false)) return rc;
+                if (int rc = launch_pair_pass(h, 0, false, false, rebuild)) return rc;
                 sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream);
                 h->host_stats[1]++;
                 if (pred_phase) {
                     sbc_launch_pred_move_kill(h->P, S, s, nullptr, h->stream);
                     h->host_stats[7]++;
                 }
+            }
+            if (h->use_cells) {
+                if (rebuild) { h->cells_valid = true; h->cells_age = 0; }
+                h->cells_age++;   // the agents moved once more since the build
             }
         }
     }
@@ -641,6 +678,7 @@ int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_a
     const size_t total = (size_t)S.N * S.R;
     const int all_rows = (flags & SBC_PAIR_ALL_ROWS) != 0;
     if (int rc = launch_pair_pass(h, all_rows, true, true)) return rc;
+    if (!all_rows && h->use_cells) { h->cells_valid = true; h->cells_age = 0; }
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     SBC_CUDA(cudaGetLastError());
     std::vector<float> acc(total * 8);
@@ -856,6 +894,7 @@ int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
     sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
+    h->cells_valid = false;
     h->host_stats[7] += 2;
     return SBC_OK;
 }

