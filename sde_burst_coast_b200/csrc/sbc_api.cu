@@ -71,7 +71,6 @@ static float next_up(float v) { return std::nextafterf(v, INFINITY); }
 static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off, DevParams &P) {
     std::memset(&P, 0, sizeof(P));
     P.L = (float)p.sizeL;
-    P.halfL = (float)(p.sizeL / 2);
     P.invL = (float)(1.0 / p.sizeL);
     P.L_lo = (float)(p.sizeL - (double)(float)p.sizeL);
     P.dt = (float)p.dt;

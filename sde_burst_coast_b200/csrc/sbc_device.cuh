@@ -16,7 +16,7 @@
 // ---------------------------------------------------------------------------------------------
 struct DevParams {
     // geometry / dynamics (FP32 copies of sbc_params)
-    float L, halfL, invL, L_lo;   // L_lo = sizeL - (double)(float)sizeL
+    float L, invL, L_lo;   // L_lo = sizeL - (double)(float)sizeL
     float dt, beta, alphaTurn;
     float soc, env, inv_soc, inv_env;
     float inv_log2q;               // 1 / log2(1 - burst_rate dt): continuous inverse CDF of the inter-burst draw
@@ -247,27 +247,6 @@ __device__ __forceinline__ int sbc_zone_fast(float d2, const DevParams &P, bool 
     amb = (d2 >= P.band_lo[0] && d2 <= P.band_hi[0]) || (d2 >= P.band_lo[1] && d2 <= P.band_hi[1]) ||
           (d2 >= P.band_lo[2] && d2 <= P.band_hi[2]);
     return (d2 <= P.rep2) ? 0 : (d2 <= P.alg2) ? 1 : (d2 <= P.att2) ? 2 : 3;
-}
-
-// one directed pair (row i <- j) in the straightforward form used by the block kernel and the
-// exact re-do paths; the tiled all-pairs kernel has its own instruction-tuned inner loop
-__device__ __forceinline__ void sbc_pair_accumulate(RowAcc &acc, float xi, float yi, float4 pj,
-                                                    const DevParams &P, int &zone_out) {
-    float dx = pj.x - xi, dy = pj.y - yi;
-    if (P.BC == 0) {
-        dx = sbc_delta_pbc(xi, pj.x, P);
-        dy = sbc_delta_pbc(yi, pj.y, P);
-    }
-    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-    bool amb;
-    int z = sbc_zone_fast(d2, P, amb);
-    if (amb) z = sbc_zone_exact(xi, yi, pj.x, pj.y, P);
-    const float rinv = (d2 > 0.f) ? rsqrtf(d2) : 0.f;  // u_ji = 0 when d = 0, agents_interact.cpp:199
-    const float ux = dx * rinv, uy = dy * rinv;
-    if (z == 0) { acc.rep_x -= ux; acc.rep_y -= uy; acc.c_rep++; }
-    else if (z == 1) { acc.alg_x += pj.z; acc.alg_y += pj.w; acc.c_alg++; }
-    else if (z == 2) { acc.att_x += ux; acc.att_y += uy; acc.c_att++; }
-    zone_out = z;
 }
 
 // prey <- predator detection, agents_interact.cpp:252-292; u_detect from the agent's own draw
