@@ -159,8 +159,10 @@ int sbc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]
  * bit5 boundary hit, bit6 flee cue, bit7 re-armed. enable!=0 starts collecting; out!=NULL reads
  * ([R][N]) and clears. */
 int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out);
-/* Route swarms of <= 1024 agents through the multi-kernel path (pair pass + update kernels)
- * instead of the one-block-per-swarm kernel, so that both paths can be checked on one state. */
+/* on = 1: route swarms of <= 1024 agents through the multi-kernel path (pair pass + update kernels)
+ * instead of the persistent one-swarm-per-block / per-cluster kernels; on = 2: keep swarms of 257..1024
+ * agents on the one-block kernel instead of the thread-block-cluster kernel; 0: automatic. Lets the
+ * tests check every schedule on one state. */
 int sbc_debug_force_multikernel(sbc_handle *h, int on);
 
 /* Kernel statistics since creation: [0] pair-kernel launches, [1] update launches,

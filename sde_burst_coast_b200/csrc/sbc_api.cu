@@ -29,6 +29,7 @@ struct sbc_handle {
     uint32_t *inj_k_dev;
     unsigned long long host_stats[8];
     bool force_multikernel;
+    bool force_block;        // test hook: keep swarms of 257..2048 agents on the one-block kernel
     unsigned char *stage_raw;   // device staging of the ABI-layout arrays (state_io.cu)
     StateStage stage;
     DenseScratch dense;
@@ -206,6 +207,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->inj_dir_dev = nullptr;
     h->inj_k_dev = nullptr;
     h->force_multikernel = false;
+    h->force_block = false;
     h->stage_raw = nullptr;
     h->dense_ready = false;
     h->cells_ready = false;
@@ -550,7 +552,8 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     const double dt = p.dt;
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (injected && n_steps != 1) return fail(h, SBC_ERR_STATE, "sbc_step: injected decisions hold for one step");
-    const bool block_path = !h->force_multikernel && S.N <= 1024 && S.Npred <= 1024 &&
+    const bool cluster_ok = !h->force_block && sbc_cluster_supported(h->P, S.N, S.Npred);
+    const bool block_path = !h->force_multikernel && (S.N <= 1024 || cluster_ok) && S.Npred <= 1024 &&
                             p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
     // predator schedule in step indices (swarmdyn.cpp:153-170)
     long long s_pred = -1;
@@ -566,12 +569,16 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             else needed = (int)((p.sim_time - p.trans_time) / 4 / dt);
         }
     }
+    const bool cluster_path = block_path && cluster_ok;
     if (block_path) {
         // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
         int64_t done = 0;
         while (done < n_steps) {
             const int64_t chunk = (n_steps - done > (1ll << 30)) ? (1ll << 30) : (n_steps - done);
-            sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed);
+            if (cluster_path)  // 257..2048 agents: one swarm on a cluster of up to 8 CTAs (DSMEM)
+                SBC_CUDA(sbc_launch_swarm_cluster(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed));
+            else
+                sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed);
             done += chunk;
             h->host_stats[2]++;
         }
@@ -797,7 +804,8 @@ int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out) {
 /* test hook: route swarms of <= 1024 agents through the multi-kernel path as well */
 int sbc_debug_force_multikernel(sbc_handle *h, int on) {
     if (!h) return SBC_ERR_INVALID;
-    h->force_multikernel = on != 0;
+    h->force_multikernel = (on == 1);
+    h->force_block = (on == 2);
     return SBC_OK;
 }
 

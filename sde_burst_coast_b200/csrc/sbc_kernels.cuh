@@ -130,5 +130,10 @@ void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long 
 bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
                             cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 
+// --- one swarm per thread-block cluster, positions shared through DSMEM (swarm_cluster.cu) ---------
+bool sbc_cluster_supported(const DevParams &P, int N, int Npred);
+cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
+                                     cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
+
 // --- observables (observables.cu) --------------------------------------------------------------
 void sbc_launch_observables(const DevParams &P, const DevState &S, double *out_dev, cudaStream_t st);

@@ -234,7 +234,8 @@ class Swarm:
         return out
 
     def force_multikernel(self, on=True):
-        self._check(self.lib.sbc_debug_force_multikernel(self.h, 1 if on else 0))
+        """True / 1: multi-kernel path; 2: one-block kernel instead of the cluster kernel; False / 0: automatic."""
+        self._check(self.lib.sbc_debug_force_multikernel(self.h, int(on)))
 
     def stats(self):
         out = np.zeros(8, dtype=np.uint64)

@@ -143,3 +143,65 @@ def test_block_and_multikernel_paths_agree_over_a_predator_run():
     # trajectories are chaotic over 4000 steps, kill counts agree statistically only
     assert int(a[2][1][0]) > 0 and int(b[2][1][0]) > 0
     assert abs(int(a[2][1][0]) - int(b[2][1][0])) <= 0.5 * max(int(a[2][1][0]), int(b[2][1][0])) + 5
+
+
+@pytest.mark.parametrize('kill,move,npred,mode', [(1, 1, 1, 'natPred'), (3, 1, 1, 'natPred'), (4, 1, 1, 'natPred'),
+                                                   (1, 0, 1, 'sinFisher'), (1, 0, 50, 'mulFisher')])
+def test_cluster_kernel_one_step_with_predator(kill, move, npred, mode):
+    """Swarms of 257..2048 agents run on a thread-block cluster (swarm_cluster.cu): same checks as above."""
+    N = 700
+    sp, st, rng = _setup(mode, N, npred, kill, move, seed=kill * 5 + npred, N_confu=2000,
+                         kill_rate=4000.0 if kill == 4 else 400.0)
+    st['bin_step'] = np.where(rng.random(N) < 0.4, sp.burst_steps, st['bin_step']).astype(np.uint32)
+    if npred == 1:
+        px, py, pphi = np.array([50.0]), np.array([50.0]), np.array([0.3])
+    else:
+        px = 40.0 + 0.5 * np.arange(npred, dtype=np.float64)
+        py = np.full(npred, 48.0)
+        pphi = np.full(npred, np.pi / 2)
+    killed = 0
+    for trial in range(2):
+        w = pyorc.World(sp, N, npred, seed=200 + trial, replicate=0)
+        g = _swarm(sp, N, npred, seed=200 + trial)
+        for obj in (w, g):
+            obj.set_state(**st)
+            obj.set_predators(px, py, pphi, 1)
+        w.step(7 + trial, 1)
+        g.step(7 + trial, 1)
+        o, gs = w.get_state(), g.get_state()
+        assert g.stats()['block_launches'] == 1
+        assert np.array_equal(o['alive'], gs['alive']), np.where(o['alive'] != gs['alive'])[0]
+        killed += N - int(o['alive'].sum())
+        al = o['alive'].astype(bool)
+        assert np.array_equal(o['bin_step'][al], gs['bin_step'][al])
+        ok = (np.abs(o['x'] - gs['x']) <= 1e-5 * np.maximum(1, np.abs(o['x']))) & \
+             (np.abs(o['y'] - gs['y']) <= 1e-5 * np.maximum(1, np.abs(o['y'])))
+        assert (~ok[al]).sum() <= 4
+        assert np.allclose(w.get_predators(), g.get_predators()[0], rtol=1e-5, atol=1e-4)
+        w.close()
+        g.close()
+    assert killed > 0
+
+
+def test_cluster_kernel_spawn_and_long_run():
+    N = 1200
+    sp, _, _ = make_params('natPred', N, BC=0, size=200.0, Npred=1, pred_kill=1, pred_move=1, pred_time=0.01,
+                           time=50.0, pred_speed0=20.0)
+    rng = np.random.default_rng(4)
+    st = random_state(N, sp, rng, spread=60.0)
+    w = pyorc.World(sp, N, 1, seed=9, replicate=0)
+    g = _swarm(sp, N, 1, seed=9)
+    for obj in (w, g):
+        obj.set_state(**st)
+    w.step(0, 12)
+    g.step(0, 12)
+    assert np.allclose(w.get_predators()[:, :2] % 200.0, g.get_predators()[0][:, :2] % 200.0, atol=2e-3)
+    g.step(12, 3000)
+    gs = g.get_state()
+    w.step(12, 3000)
+    o = w.get_state()
+    both = o['alive'].astype(bool) & gs['alive'].astype(bool)
+    assert np.array_equal(o['steps_till_burst'][both], gs['steps_till_burst'][both])
+    assert int(g.counts()[1][0]) > 0
+    w.close()
+    g.close()

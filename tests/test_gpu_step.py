@@ -43,7 +43,7 @@ def _close_state(o, g, sp, what=''):
     ('natPred', dict(BC=0, size=200.0, Npred=0), 2000),
     ('burst_coast', dict(BC=2, size=60.0), 50), ('burst_coast', dict(BC=3, size=60.0), 50),
 ])
-@pytest.mark.parametrize('multikernel', [False, True])
+@pytest.mark.parametrize('multikernel', [False, True, 2])   # automatic (warp / block / cluster kernel), multi-kernel, block kernel
 def test_one_step_injected(mode, over, N, multikernel):
     sp, _, _ = make_params(mode, N, **over)
     rng = np.random.default_rng(N * 3 + sp.BC + 100)
@@ -63,7 +63,7 @@ def test_one_step_injected(mode, over, N, multikernel):
         o = w.get_state()
         g = _swarm(sp, N)
         if multikernel:
-            g.force_multikernel(True)
+            g.force_multikernel(multikernel)
         g.debug_flags(True)
         g.set_state(**st)
         g.inject(us, ud, kn)
@@ -148,7 +148,7 @@ def test_split_launches_equal_one_launch():
     b.close()
 
 
-@pytest.mark.parametrize('N', [30, 64, 300])
+@pytest.mark.parametrize('N', [30, 64, 300, 1500])
 def test_block_path_matches_multikernel_path(N):
     """The one-block-per-swarm kernel and the pair-pass + update kernels are two schedules of the same
     arithmetic: identical timers, states within the one-step tolerance for a short run."""
@@ -169,6 +169,15 @@ def test_block_path_matches_multikernel_path(N):
     ok = _close_state(sa, sb, sp)
     assert ok.mean() >= 0.97, ok.mean()
     assert a.stats()['block_launches'] == 1 and b.stats()['update_launches'] == 3
+    if N > 256:   # the automatic path is the cluster kernel there: check the one-block kernel as well
+        c = _swarm(sp, N, seed=11)
+        c.force_multikernel(2)
+        c.set_state(**st)
+        c.step(0, 3)
+        sc = c.get_state()
+        assert np.array_equal(sa['steps_till_burst'], sc['steps_till_burst'])
+        assert _close_state(sa, sc, sp).mean() >= 0.97
+        c.close()
     a.close()
     b.close()
 
