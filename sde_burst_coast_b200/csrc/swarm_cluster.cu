@@ -70,7 +70,9 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
     unsigned *act_s = reinterpret_cast<unsigned *>(wkey_s + NW);          // [NW]
     int *n_rows_s = reinterpret_cast<int *>(act_s + NW);                  // [4]
     unsigned short *rows_s = reinterpret_cast<unsigned short *>(n_rows_s + 4);  // [CT]
-    float4 *all_s = reinterpret_cast<float4 *>(rows_s + CT);              // [C * CT] local copy of every CTA's positions
+    float *wsum_f = reinterpret_cast<float *>(rows_s + CT);               // [NW][8] warp partials of one row
+    int *wsum_i = reinterpret_cast<int *>(wsum_f + NW * 8);                // [NW][4]
+    float4 *all_s = reinterpret_cast<float4 *>(wsum_i + NW * 4);          // [C * CT] local copy of every CTA's positions
     float4 *pred_s = all_s + C * CT;                                      // [NP]
     float *pphi_s = reinterpret_cast<float *>(pred_s + NP);               // [NP]
 
@@ -224,43 +226,42 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
                 all_s[c * CT + tid] = (cluster.map_shared_rank(pv_s, c) + (s & 1u) * CT)[tid];
             __syncthreads();
         }
-        for (int kr = warp; kr < n_first; kr += NW) {
+        // every burst-starting row is swept by ALL warps of the CTA (a warp takes every NW-th group of 32
+        // partners), so the step's critical path is N / (32 NW) iterations instead of N / 32; the warp
+        // partials are combined in warp order by one thread - a fixed order, independent of scheduling
+        for (int kr = 0; kr < n_first; kr++) {
             const int row_l = rows_s[kr];             // index inside this CTA
             const int row = crank * CT + row_l;       // index inside the swarm
             const float4 pi = my_pv[row_l];
             int cr = 0, ca = 0, ct = 0;
             float rx = 0.f, ry = 0.f, gx = 0.f, gy = 0.f, tx = 0.f, ty = 0.f;
-            {
-                const int c = 0;
-                for (int jl = lane; jl < N; jl += 32) {
-                    const float4 pj = all_s[jl];
-                    float dx = pj.x - pi.x, dy = pj.y - pi.y;
-                    if (P.BC == 0) {
-                        dx = sbc_delta_pbc(pi.x, pj.x, P);
-                        dy = sbc_delta_pbc(pi.y, pj.y, P);
-                    }
-                    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-                    bool amb;
-                    int z = sbc_zone_fast(d2, P, amb);
-                    if (amb) {
-                        z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
-                        n_amb++;
-                    }
-                    if (c * CT + jl == row) z = 3;
-                    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
-                    if (z == 0) { rx = __fmaf_rn(-dx, rinv, rx); ry = __fmaf_rn(-dy, rinv, ry); cr++; }
-                    else if (z == 1) { gx += pj.z; gy += pj.w; ca++; }
-                    else if (z == 2) { tx = __fmaf_rn(dx, rinv, tx); ty = __fmaf_rn(dy, rinv, ty); ct++; }
+            for (int jl = tid; jl < N; jl += CT) {
+                const float4 pj = all_s[jl];
+                float dx = pj.x - pi.x, dy = pj.y - pi.y;
+                if (P.BC == 0) {
+                    dx = sbc_delta_pbc(pi.x, pj.x, P);
+                    dy = sbc_delta_pbc(pi.y, pj.y, P);
                 }
+                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                bool amb;
+                int z = sbc_zone_fast(d2, P, amb);
+                if (amb) {
+                    z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
+                    n_amb++;
+                }
+                if (jl == row) z = 3;
+                const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+                if (z == 0) { rx = __fmaf_rn(-dx, rinv, rx); ry = __fmaf_rn(-dy, rinv, ry); cr++; }
+                else if (z == 1) { gx += pj.z; gy += pj.w; ca++; }
+                else if (z == 2) { tx = __fmaf_rn(dx, rinv, tx); ty = __fmaf_rn(dy, rinv, ty); ct++; }
             }
-            n_pairs += (lane == 0) ? (unsigned long long)(N - 1) : 0ull;
+            n_pairs += (tid == 0) ? (unsigned long long)(N - 1) : 0ull;
             cr = __reduce_add_sync(FULL, cr);
             ca = __reduce_add_sync(FULL, ca);
             ct = __reduce_add_sync(FULL, ct);
-            float v0 = (cr > 0) ? rx : gx, v1 = (cr > 0) ? ry : gy, v2 = tx, v3 = ty;
             float f0 = 0.f, f1 = 0.f;
             int cf = 0;
-            if (pred_phase) {  // IntCalcPred (agents_interact.cpp:252-292) for this row
+            if (pred_phase && warp == (kr % NW)) {  // IntCalcPred (agents_interact.cpp:252-292): one warp per row
                 RowAcc fa;
                 row_acc_clear(fa);
                 for (int jb = lane; 4 * jb < NP; jb += 32) {
@@ -279,22 +280,37 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                v0 += __shfl_xor_sync(FULL, v0, o);
-                v1 += __shfl_xor_sync(FULL, v1, o);
-                v2 += __shfl_xor_sync(FULL, v2, o);
-                v3 += __shfl_xor_sync(FULL, v3, o);
+                rx += __shfl_xor_sync(FULL, rx, o); ry += __shfl_xor_sync(FULL, ry, o);
+                gx += __shfl_xor_sync(FULL, gx, o); gy += __shfl_xor_sync(FULL, gy, o);
+                tx += __shfl_xor_sync(FULL, tx, o); ty += __shfl_xor_sync(FULL, ty, o);
                 if (PRED) {
                     f0 += __shfl_xor_sync(FULL, f0, o);
                     f1 += __shfl_xor_sync(FULL, f1, o);
                 }
             }
             if (lane == 0) {
-                RowResult r;
-                r.v0 = v0; r.v1 = v1; r.v2 = v2; r.v3 = v3;
-                r.cr = cr; r.ca = ca; r.ct = ct; r.cf = cf;
-                res_s[row_l] = r;
-                flee_s[row_l] = make_float2(f0, f1);
+                float *wf = wsum_f + warp * 8;
+                int *wi = wsum_i + warp * 4;
+                wf[0] = rx; wf[1] = ry; wf[2] = gx; wf[3] = gy; wf[4] = tx; wf[5] = ty;
+                wi[0] = cr; wi[1] = ca; wi[2] = ct;
+                if (pred_phase && warp == (kr % NW)) { flee_s[row_l] = make_float2(f0, f1); wi[3] = cf; }
             }
+            __syncthreads();
+            if (tid == 0) {
+                float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                int c3[3] = {0, 0, 0};
+                for (int w = 0; w < NW; w++) {
+                    for (int q = 0; q < 6; q++) v[q] += wsum_f[w * 8 + q];
+                    for (int q = 0; q < 3; q++) c3[q] += wsum_i[w * 4 + q];
+                }
+                RowResult r;
+                r.v0 = (c3[0] > 0) ? v[0] : v[2]; r.v1 = (c3[0] > 0) ? v[1] : v[3]; r.v2 = v[4]; r.v3 = v[5];
+                r.cr = c3[0]; r.ca = c3[1]; r.ct = c3[2];
+                r.cf = pred_phase ? wsum_i[(kr % NW) * 4 + 3] : 0;
+                res_s[row_l] = r;
+                if (!pred_phase) flee_s[row_l] = make_float2(0.f, 0.f);
+            }
+            __syncthreads();
         }
         __syncthreads();
         if (first) {
@@ -474,7 +490,7 @@ cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long
     const size_t smem = 2 * CT * sizeof(float4) + CT * sizeof(RowResult) + CT * sizeof(float2) + 8 * sizeof(double) +
                         sizeof(ChaseEntry) + (CT / 32) * 5 * sizeof(double) + (CT / 32) * sizeof(unsigned long long) +
                         (CT / 32) * sizeof(unsigned) + 4 * sizeof(int) + CT * sizeof(unsigned short) +
-                        (size_t)C * CT * sizeof(float4) + (size_t)S.Npred * (sizeof(float4) + sizeof(float)) + 64;
+                        (CT / 32) * 8 * sizeof(float) + (CT / 32) * 4 * sizeof(int) + (size_t)C * CT * sizeof(float4) + (size_t)S.Npred * (sizeof(float4) + sizeof(float)) + 64;
     PredSchedule sched;
     sched.s_pred = (s_pred < 0 || s_pred > 0xffffffffll) ? 0xffffffffu : (uint32_t)s_pred;
     sched.s_trunc = s_trunc;
