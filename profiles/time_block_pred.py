@@ -22,6 +22,10 @@ t("N=1024 pred kill1 walk (auto)", 1024, 1, 1, 0)
 t("N=256 pred kill3 chase (auto)", 256, 1, 3, 1)
 t("N=30 pred kill3 chase x4096 (auto)", 30, 1, 3, 1, R=4096, steps=2000)
 t("N=30 no pred x4096 (warp kernel)", 30, 0, 0, 0, R=4096, steps=2000)
+t("N=30 pred kill3 chase x4096 (block, forced)", 30, 1, 3, 1, R=4096, steps=2000, mk=2)
+t("N=30 pred kill3 chase x16384 (auto)", 30, 1, 3, 1, R=16384, steps=2000)
+t("N=30 pred kill1 walk x16384 (auto)", 30, 1, 1, 0, R=16384, steps=2000)
+t("N=30 no pred x16384 (warp kernel)", 30, 0, 0, 0, R=16384, steps=2000)
 t("N=1024 pred kill3 chase (multikernel)", 1024, 1, 3, 1, mk=True, steps=2000)
 t("N=1024 no predator (block, forced)", 1024, 0, 0, 0, mk=2)
 t("N=2048 pred kill3 chase (cluster)", 2048, 1, 3, 1)

@@ -21,12 +21,6 @@ __device__ __forceinline__ double block_sum(double v, double *sh) {
     return t;
 }
 
-__device__ __forceinline__ double min_image_d(double r, double L) {
-    const double s = (double)((0.0 < r) - (r < 0.0));
-    const double h = __ddiv_rn(__dmul_rn(s, L), 2.0);
-    return __dsub_rn(fmod(__dadd_rn(r, h), L), h);
-}
-
 __global__ void __launch_bounds__(PT)
 pred_spawn_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step, uint32_t slot) {
     __shared__ double sh[PT / 32];
@@ -138,22 +132,12 @@ net_kill_kernel(const __grid_constant__ DevParams P, DevState S) {
     if (threadIdx.x == 0) s_killed = 0;
     __syncthreads();
     const float4 p0 = pp[0], p1 = pp[1];
-    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
-    if (P.BC == 0) { vn[0] = min_image_d(vn[0], P.dL); vn[1] = min_image_d(vn[1], P.dL); }
-    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
-    const double net_len = (double)(S.Npred - 1) * dist;
-    float s0, c0;
-    sincosf(S.pred_phi[(size_t)rep * S.Npred], &s0, &c0);
-    const double mv[2] = {(double)c0, (double)s0};
+    const float ph0 = S.pred_phi[(size_t)rep * S.Npred];
     int killed = 0;
     for (int i = blockIdx.x * PT + threadIdx.x; i < N; i += gridDim.x * PT) {
         const float4 p = pv[i];
         if (p.x != p.x) continue;
-        double r[2] = {__dsub_rn((double)p.x, (double)p0.x), __dsub_rn((double)p.y, (double)p0.y)};
-        if (P.BC == 0) { r[0] = min_image_d(r[0], P.dL); r[1] = min_image_d(r[1], P.dL); }
-        const double front = __dadd_rn(__dmul_rn(mv[0], r[0]), __dmul_rn(mv[1], r[1]));
-        const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
-        if (front > 0 && front < P.d_kill_range && side > 0 && side <= net_len) {
+        if (sbc_net_kills(p.x, p.y, p0, p1, ph0, S.Npred, P)) {
             kill_agent(S, (size_t)rep * N + i, p);
             killed++;
         }
@@ -227,43 +211,32 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
         }
         __syncthreads();
         if (P.pred_kill != 0) {  // PredKill
-            const double px = (double)s_p[0], py = (double)s_p[1];
-            const double r_sense = 4 * P.d_kill_range;
+            const float px = s_p[0], py = s_p[1];
             double n_sensed = 0, total = 0;
             // pass 1: N_sensed and the normalisation of the selection weights (:861-877)
-            for (int i = threadIdx.x; i < N; i += PT) {
-                const float4 p = pv[i];
-                if (p.x != p.x) continue;
-                double r[2] = {__dsub_rn((double)p.x, px), __dsub_rn((double)p.y, py)};
-                if (P.BC == 0) { r[0] = min_image_d(r[0], P.dL); r[1] = min_image_d(r[1], P.dL); }
-                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
-                if (d <= r_sense) {
-                    n_sensed += 1;
-                    if (d < P.d_kill_range) total += (P.d_kill_range - d) / P.d_kill_range;
-                }
-            }
             if (P.pred_kill > 1) {
+                for (int i = threadIdx.x; i < N; i += PT) {
+                    const float4 p = pv[i];
+                    if (p.x != p.x) continue;
+                    const KillClass kc = sbc_kill_classify(p.x, p.y, px, py, P);
+                    if (kc.sensed) {
+                        n_sensed += 1;
+                        if (kc.cand && P.pred_kill == 4) total += sbc_kill_weight(p.x, p.y, px, py, P);
+                    }
+                }
                 n_sensed = block_sum(n_sensed, sh);
                 total = block_sum(total, sh);
             }
-            const double eff = (n_sensed > 0)
-                                   ? (double)P.kill_rate * 0.5 * (tanh(-1.0 * (n_sensed - (double)P.N_confu)) + 1.0)
-                                   : 0.0;
             int killed = 0;
             for (int i = threadIdx.x; i < N; i += PT) {
                 const float4 p = pv[i];
                 if (p.x != p.x) continue;
-                double r[2] = {__dsub_rn((double)p.x, px), __dsub_rn((double)p.y, py)};
-                if (P.BC == 0) { r[0] = min_image_d(r[0], P.dL); r[1] = min_image_d(r[1], P.dL); }
-                const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
+                const KillClass kc = sbc_kill_classify(p.x, p.y, px, py, P);
                 bool die = false;
                 if (P.pred_kill == 1) {
-                    die = d <= P.d_kill_range;
-                } else if (d <= r_sense && d < P.d_kill_range) {
-                    double pk = 0;
-                    if (P.pred_kill == 2) pk = (double)P.kill_rate * (double)P.dt;
-                    else if (P.pred_kill == 3) pk = eff * (double)P.dt;
-                    else if (P.pred_kill == 4) pk = eff * (double)P.dt * (((P.d_kill_range - d) / P.d_kill_range) / total);
+                    die = kc.within;
+                } else if (kc.cand) {
+                    const double pk = sbc_kill_probability(p.x, p.y, px, py, (int)n_sensed, total, S.kill_eff, P);
                     const uint4 q = sbc_draw(P, rep, (uint32_t)i, step, SBC_SLOT_DECISION);
                     die = pk > (double)q.w * (1.0 / 4294967296.0);
                 }

@@ -245,6 +245,8 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
     uint32_t *geo_dev = nullptr;
     ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
+    double *eff_dev = nullptr;
+    ok = ok && dev_alloc(&eff_dev, (size_t)n_agents + 1) == cudaSuccess;
     ok = ok && dev_alloc(&h->obs_dev, (size_t)n_replicates * 8) == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("sbc_create: CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -252,6 +254,13 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
         return SBC_ERR_NOMEM;
     }
     S.geo = geo_dev;
+    {   // kill_rate * SigmoidFunction(N_sensed, N_confu, -1) (mathtools.cpp:22-33) for every possible N_sensed
+        std::vector<double> eff((size_t)n_agents + 1, 0.0);
+        for (int n = 1; n <= n_agents; n++)
+            eff[n] = p->kill_rate * (0.5 * (std::tanh(-1.0 * ((double)n - (double)p->N_confu)) + 1.0));
+        cudaMemcpy(eff_dev, eff.data(), eff.size() * sizeof(double), cudaMemcpyHostToDevice);
+        S.kill_eff = eff_dev;
+    }
     cudaMemcpy(geo_dev, h->geo_host.data(), h->geo_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaMemset(S.stats, 0, 8 * sizeof(unsigned long long));
     cudaMemset(S.n_dead, 0, n_replicates * sizeof(int));
@@ -289,7 +298,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.pv); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.force); cudaFree(S.timers);
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list); cudaFree(S.active_count);
-    cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo));
+    cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
@@ -578,7 +587,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             if (cluster_path)  // 257..2048 agents: one swarm on a cluster of up to 8 CTAs (DSMEM)
                 SBC_CUDA(sbc_launch_swarm_cluster(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed));
             else
-                sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed);
+                sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed, h->force_block);
             done += chunk;
             h->host_stats[2]++;
         }

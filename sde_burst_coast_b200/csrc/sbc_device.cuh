@@ -145,19 +145,29 @@ __device__ __forceinline__ float sbc_delta_pbc(float xi, float xj, const DevPara
     return __fmaf_rn(-n, P.L_lo, a - b);
 }
 
+// FP64 minimum image exactly as mathtools.h:64-71 computes it: fmod(r + sgn(r) L/2, L) - sgn(r) L/2.
+// For |t| < 2 L the fmod is one exact subtraction (Sterbenz), so the slow library path is only kept
+// for arguments the simulation never produces.
+__device__ __forceinline__ double sbc_fmod_near(double t, double L) {
+    const double at = fabs(t);
+    if (at < L) return t;
+    if (at < 2.0 * L) return (t > 0.0) ? __dsub_rn(t, L) : __dadd_rn(t, L);
+    return fmod(t, L);
+}
+__device__ __forceinline__ double sbc_min_image_dd(double r, double L) {
+    const double s = (double)((0.0 < r) - (r < 0.0));
+    const double h = __ddiv_rn(__dmul_rn(s, L), 2.0);
+    return __dsub_rn(sbc_fmod_near(__dadd_rn(r, h), L), h);
+}
+
 // FP64 replay of CalcDistVec + vec_length + SFM_4Zone in the reference's operation order
 // (mathtools.h:54-83, social_forces.cpp:33-47): returns 0,1,2 or 3 (= none).
 static __device__ __noinline__ int sbc_zone_exact(float xi, float yi, float xj, float yj,
                                            const DevParams &P) {
     double r[2] = {__dsub_rn((double)xj, (double)xi), __dsub_rn((double)yj, (double)yi)};
     if (P.BC == 0) {
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const double s = (double)((0.0 < r[d]) - (r[d] < 0.0));
-            const double h = __ddiv_rn(__dmul_rn(s, P.dL), 2.0);
-            const double t = fmod(__dadd_rn(r[d], h), P.dL);
-            r[d] = __dsub_rn(t, h);
-        }
+        r[0] = sbc_min_image_dd(r[0], P.dL);
+        r[1] = sbc_min_image_dd(r[1], P.dL);
     }
     const double len = __dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1]));
     const double d = __dsqrt_rn(len);
@@ -266,12 +276,8 @@ __device__ __forceinline__ void sbc_detect_accumulate(RowAcc &acc, float xi, flo
     if (fabsf((float)u_detect - fs) <= 4e-6f * fmaxf(fs, 1.f)) {
         double r[2] = {__dsub_rn((double)px, (double)xi), __dsub_rn((double)py, (double)yi)};
         if (P.BC == 0) {
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                const double s = (double)((0.0 < r[k]) - (r[k] < 0.0));
-                const double h = __ddiv_rn(__dmul_rn(s, P.dL), 2.0);
-                r[k] = __dsub_rn(fmod(__dadd_rn(r[k], h), P.dL), h);
-            }
+            r[0] = sbc_min_image_dd(r[0], P.dL);
+            r[1] = sbc_min_image_dd(r[1], P.dL);
         }
         const double dd = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
         const double fsd = __ddiv_rn(2.0, __dadd_rn(1.0, __ddiv_rn(dd, P.d_flee_range)));
@@ -283,6 +289,89 @@ __device__ __forceinline__ void sbc_detect_accumulate(RowAcc &acc, float xi, flo
         acc.flee_x -= dx * rinv;
         acc.flee_y -= dy * rinv;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PredKill / FishNetKill predicates (agents_dynamics.cpp:780-915), shared by every kernel that kills.
+// The comparisons run in FP64 in the reference's operation order, but only for agents an FP32 estimate
+// cannot rule out: the estimate's error (a few ulp of L) is far below the margin used here.
+// ---------------------------------------------------------------------------------------------
+// distance prey - predator in FP64, the reference's operation order
+__device__ __forceinline__ double sbc_kill_distance(float ax, float ay, float px, float py, const DevParams &P) {
+    double r[2] = {__dsub_rn((double)ax, (double)px), __dsub_rn((double)ay, (double)py)};
+    if (P.BC == 0) {
+        r[0] = sbc_min_image_dd(r[0], P.dL);
+        r[1] = sbc_min_image_dd(r[1], P.dL);
+    }
+    return __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
+}
+// where a prey stands relative to the predator: sensed (d <= 4 kill_range, :861-870), candidate
+// (d < kill_range, :872) and within (d <= kill_range, the radial kill :845-850). Decided on the FP32
+// squared distance; only a distance within a few ulp of a threshold is re-decided in FP64.
+struct KillClass {
+    bool sensed, cand, within;
+};
+__device__ __forceinline__ KillClass sbc_kill_classify(float ax, float ay, float px, float py, const DevParams &P) {
+    float dx = ax - px, dy = ay - py;
+    if (P.BC == 0) {
+        dx = sbc_delta_pbc(px, ax, P);
+        dy = sbc_delta_pbc(py, ay, P);
+    }
+    const float d2 = __fmaf_rn(dy, dy, dx * dx);
+    const float kr2 = P.kill_range * P.kill_range, rs2 = 16.f * kr2;
+    KillClass k;
+    k.sensed = d2 <= rs2;
+    k.cand = d2 < kr2;
+    k.within = d2 <= kr2;
+    if (fabsf(d2 - kr2) <= 8e-6f * kr2 || fabsf(d2 - rs2) <= 8e-6f * rs2) {
+        const double d = sbc_kill_distance(ax, ay, px, py, P);
+        k.sensed = d <= 4 * P.d_kill_range;
+        k.cand = k.sensed && d < P.d_kill_range;
+        k.within = d <= P.d_kill_range;
+    }
+    return k;
+}
+// kill probability of a candidate (d < kill_range, sensed), :879-905. eff_table[n] is the confusion-
+// modulated rate kill_rate / 2 (tanh(-(n - N_confu)) + 1) for n sensed prey, tabulated by the host in FP64.
+__device__ __forceinline__ double sbc_kill_probability(float ax, float ay, float px, float py, int n_sensed,
+                                                       double total, const double *eff_table, const DevParams &P) {
+    if (P.pred_kill == 2) return (double)P.kill_rate * (double)P.dt;
+    const double eff = eff_table[n_sensed];
+    if (P.pred_kill == 3) return eff * (double)P.dt;
+    if (P.pred_kill == 4) {
+        const double d = sbc_kill_distance(ax, ay, px, py, P);
+        return eff * (double)P.dt * (((P.d_kill_range - d) / P.d_kill_range) / total);
+    }
+    return 0.0;
+}
+// selection weight of a candidate for kill rule 4, :872-877
+__device__ __forceinline__ double sbc_kill_weight(float ax, float ay, float px, float py, const DevParams &P) {
+    return (P.d_kill_range - sbc_kill_distance(ax, ay, px, py, P)) / P.d_kill_range;
+}
+// FishNetKill :780-820 for one agent: the net's first two nodes p0, p1, heading phi0 of node 0
+__device__ __forceinline__ bool sbc_net_kills(float ax, float ay, float4 p0, float4 p1, float phi0, int NP,
+                                              const DevParams &P) {
+    float s0, c0;
+    sincosf(phi0, &s0, &c0);
+    {   // FP32 estimate of the distance in front of the net
+        float rx = ax - p0.x, ry = ay - p0.y;
+        if (P.BC == 0) {
+            rx = sbc_delta_pbc(p0.x, ax, P);
+            ry = sbc_delta_pbc(p0.y, ay, P);
+        }
+        const float front = __fmaf_rn(c0, rx, s0 * ry);
+        const float slack = __fmaf_rn(0.01f, P.kill_range, 1e-5f * P.L);
+        if (front < -slack || front > P.kill_range + slack) return false;
+    }
+    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
+    if (P.BC == 0) { vn[0] = sbc_min_image_dd(vn[0], P.dL); vn[1] = sbc_min_image_dd(vn[1], P.dL); }
+    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
+    const double net_len = (double)(NP - 1) * dist;
+    double r[2] = {__dsub_rn((double)ax, (double)p0.x), __dsub_rn((double)ay, (double)p0.y)};
+    if (P.BC == 0) { r[0] = sbc_min_image_dd(r[0], P.dL); r[1] = sbc_min_image_dd(r[1], P.dL); }
+    const double front = __dadd_rn(__dmul_rn((double)c0, r[0]), __dmul_rn((double)s0, r[1]));
+    const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
+    return front > 0 && front < P.d_kill_range && side > 0 && side <= net_len;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ struct DevState {
     float *pred_phi;   // [R][Npred]
     int *n_dead;       // [R]
     int *pred_spawned; // [R]
+    const double *kill_eff; // [N+1] effective kill rate for n sensed prey (PredKill, agents_dynamics.cpp:879-884)
     // decisions
     const uint32_t *geo; // inter-burst table, max_steps entries
     double *inj_social;  // [R*N] or nullptr
@@ -128,7 +129,8 @@ void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long 
 // predators (if any): s_pred = first step with s >= pred_time/dt, s_trunc = (int)(pred_time/dt),
 // needed = fish-net re-spawn period in steps (0 = none)
 bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
-                            cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
+                            cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0,
+                            bool force_block = false);
 
 // --- one swarm per thread-block cluster, positions shared through DSMEM (swarm_cluster.cu) ---------
 bool sbc_cluster_supported(const DevParams &P, int N, int Npred);

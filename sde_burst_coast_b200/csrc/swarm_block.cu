@@ -47,11 +47,19 @@ __device__ __forceinline__ void draw_decisions(const DevParams &P, const DevStat
 // ------------------------------------------------------------------------------------------------
 // N <= 32 : swarms inside a warp
 // ------------------------------------------------------------------------------------------------
+// when the predators of a swarm appear and re-appear, in step indices (host-evaluated, swarmdyn.cpp:153-170)
+struct PredSchedule {
+    uint32_t s_pred;    // first step with s >= pred_time/dt
+    int32_t s_trunc;    // (int)(pred_time/dt), origin of the net's re-spawn period
+    int32_t needed;     // re-spawn period in steps (fish net), 0 = never
+};
+
 constexpr int BC_RUNTIME = -99;   // template value: take the boundary condition from the parameters
 
-template <int TPS, int BCT, bool VOR>
+template <int TPS, int BCT, bool VOR, bool PRED>
 __global__ void __launch_bounds__(128)
-swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
+swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps,
+                  PredSchedule sched) {
     const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
     constexpr int SPW = 32 / TPS;
     constexpr unsigned FULL = 0xffffffffu;
@@ -64,15 +72,59 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
     const size_t g = valid ? ((size_t)rep * N + t) : 0;
     const unsigned segmask = (TPS == 32) ? FULL : (((1u << TPS) - 1u) << (seg * TPS));
     AgentState a = {};
-    bool alive = false;
+    bool alive = false, died = false;
     if (valid) {
         load_agent(S, g, a);
         alive = S.alive[g] != 0;
     }
     uint32_t flags_acc = 0;
     unsigned long long n_amb = 0, n_pairs = 0;
+    // PRED: the swarm's single predator (Npred == 1), replicated in every lane of the segment
+    float4 pred = make_float4(0.f, 0.f, 0.f, 0.f);
+    float pred_phi = 0.f;
+    bool spawned = false, phi_stale = false;
+    if (PRED && rep < S.R) {
+        pred = S.pred_pv[rep];
+        pred_phi = S.pred_phi[rep];
+    }
 
     for (uint32_t s = s_first; s != s_first + n_steps; s++) {
+        const bool pred_phase = PRED && (s >= sched.s_pred);
+        if (PRED && s == sched.s_pred) {  // CreatePredator (agents_dynamics.cpp:534-555, swarmdyn.cpp:153-158)
+            double c[5] = {0, 0, 0, 0, alive ? 1.0 : 0.0};
+            if (alive) {
+                if (BC == 0) {
+                    const float scaling = SBC_TWO_PI_F * P.invL;
+                    float sn, cs;
+                    sincosf(scaling * a.x, &sn, &cs); c[0] = cs; c[1] = sn;
+                    sincosf(scaling * a.y, &sn, &cs); c[2] = cs; c[3] = sn;
+                } else {
+                    c[0] = a.x;
+                    c[2] = a.y;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++)
+                for (int o = TPS / 2; o > 0; o >>= 1) c[k] += __shfl_xor_sync(FULL, c[k], o);
+            float comx, comy;
+            if (BC == 0) {
+                comx = (float)((atan2(-c[1] / c[4], -c[0] / c[4]) + SBC_PI_D) / (2 * SBC_PI_D / P.dL));
+                comy = (float)((atan2(-c[3] / c[4], -c[2] / c[4]) + SBC_PI_D) / (2 * SBC_PI_D / P.dL));
+            } else {
+                comx = (float)(c[0] / c[4]);
+                comy = (float)(c[2] / c[4]);
+            }
+            const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, s, 0u);
+            float phi = (float)((double)q.x * (1.0 / 4294967296.0)) * SBC_TWO_PI_F, sn, cs;
+            sincosf(phi, &sn, &cs);
+            pred.x = comx - 0.5f * P.L * cs;
+            pred.y = comy - 0.5f * P.L * sn;
+            pred.z = P.pred_speed * cs;
+            pred.w = P.pred_speed * sn;
+            sbc_boundary(pred.x, pred.y, pred.z, pred.w, phi, P, BC);
+            pred_phi = phi;
+            spawned = true;
+        }
         const bool first = alive && (a.bin_step == P.burst_steps);
         RowAcc acc;
         row_acc_clear(acc);
@@ -139,6 +191,15 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             }
             rem &= ~__ballot_sync(FULL, is_row);
         }
+        if (PRED && pred_phase && first) {  // IntCalcPred (agents_interact.cpp:252-292): the row's own draw
+            const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DETECT0);
+            RowAcc fa;
+            row_acc_clear(fa);
+            sbc_detect_accumulate(fa, a.x, a.y, pred.x, pred.y, (double)q.x * (1.0 / 4294967296.0), P);
+            acc.c_flee = fa.c_flee;
+            acc.flee_x = fa.flee_x;
+            acc.flee_y = fa.flee_y;
+        }
         if (alive) {
             double u_social = 0.0;
             float u_dir = 0.f;
@@ -149,10 +210,103 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, BC);
             flags_acc |= fl;
         }
+        if (PRED && pred_phase) {  // swarmdyn.cpp:192-203, every lane of the segment moves its copy of the predator
+            float lphi = pred_phi;
+            bool chase_hit = false;
+            float chase_cs = 1.f, chase_sn = 0.f;
+            if (P.pred_move == 0) {  // MovePredator :567-613, random walk
+                const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, s, 2u);
+                const float u1 = (float)(((double)q.x + 1.0) * (1.0 / 4294967296.0));
+                const float u2 = (float)((double)q.y * (1.0 / 4294967296.0));
+                const float gss = sqrtf(-2.f * logf(u1)) * cosf(SBC_TWO_PI_F * u2);
+                lphi = fmodf(pred_phi + P.noisep * gss * sqrtf(P.pred_speed), SBC_TWO_PI_F);
+            } else {  // chase the closest prey: arg-min of (d2, index) over the segment
+                unsigned key = 0xffffffffu;   // d2 >= 0: its bit pattern orders like the value
+                float dx = 0.f, dy = 0.f;
+                if (alive) {
+                    dx = a.x - pred.x; dy = a.y - pred.y;
+                    if (BC == 0) { dx = sbc_delta_pbc(pred.x, a.x, P); dy = sbc_delta_pbc(pred.y, a.y, P); }
+                    key = __float_as_uint(dx * dx + dy * dy);
+                }
+                const unsigned best = __reduce_min_sync(segmask, key);
+                const unsigned winners = __ballot_sync(FULL, key == best) & segmask;   // lowest index wins a tie
+                const int wl = __ffs(winners) - 1;
+                const float wdx = __shfl_sync(FULL, dx, wl), wdy = __shfl_sync(FULL, dy, wl);
+                chase_hit = best != 0xffffffffu;
+                if (BCT == 0) {
+                    // periodic box: the heading never changes at the boundary, so the velocity
+                    // speed * (cos, sin)(atan2(dy, dx)) is taken as speed * (dx, dy) / |d| and the angle
+                    // itself is only formed when the launch ends
+                    const float d2w = wdx * wdx + wdy * wdy;
+                    const float rinv = rsqrtf(d2w);
+                    chase_cs = (d2w > 0.f) ? wdx * rinv : 1.f;
+                    chase_sn = (d2w > 0.f) ? wdy * rinv : 0.f;
+                } else if (chase_hit) {
+                    lphi = atan2f(wdy, wdx);
+                }
+            }
+            if (BCT == 0 && P.pred_move != 0) {
+                if (chase_hit) {
+                    pred.z = P.pred_speed * chase_cs;
+                    pred.w = P.pred_speed * chase_sn;
+                    phi_stale = true;
+                }
+                pred.x += pred.z * P.dt;
+                pred.y += pred.w * P.dt;
+                float ph = 0.f;
+                sbc_boundary(pred.x, pred.y, pred.z, pred.w, ph, P, BC);
+            } else {
+                float sn, cs;
+                sincosf(lphi, &sn, &cs);
+                pred.z = P.pred_speed * cs;
+                pred.w = P.pred_speed * sn;
+                pred.x += pred.z * P.dt;
+                pred.y += pred.w * P.dt;
+                pred_phi = lphi;
+                sbc_boundary(pred.x, pred.y, pred.z, pred.w, pred_phi, P, BC);
+            }
+            if (P.pred_kill != 0) {  // PredKill :826-915
+                bool die = false;
+                KillClass kc = {false, false, false};
+                if (alive) kc = sbc_kill_classify(a.x, a.y, pred.x, pred.y, P);
+                if (P.pred_kill == 1) {
+                    die = kc.within;
+                } else {
+                    const int n_sensed = __popc(__ballot_sync(FULL, kc.sensed) & segmask);
+                    double total = 0.0;
+                    if (P.pred_kill == 4) {
+                        total = kc.cand ? sbc_kill_weight(a.x, a.y, pred.x, pred.y, P) : 0.0;
+#pragma unroll
+                        for (int o = TPS / 2; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+                    }
+                    if (kc.cand) {
+                        const double pk = sbc_kill_probability(a.x, a.y, pred.x, pred.y, n_sensed, total, S.kill_eff, P);
+                        const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DECISION);
+                        die = pk > (double)q.w * (1.0 / 4294967296.0);
+                    }
+                }
+                if (die) {
+                    alive = false;
+                    died = true;
+                }
+            }
+        }
     }
-    if (valid && alive) {
+    if (valid && (alive || died)) {
         store_agent(S, g, a);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
+        if (died) {  // split_dead (agents_operation.cpp:209-218)
+            S.alive[g] = 0;
+            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
+            S.pv[g] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), a.vx, a.vy);
+            atomicAdd(S.n_dead + rep, 1);
+        }
+    }
+    if (PRED && rep < S.R && t == 0) {
+        if (phi_stale) pred_phi = atan2f(pred.w, pred.z);
+        S.pred_pv[rep] = pred;
+        S.pred_phi[rep] = pred_phi;
+        if (spawned) S.pred_spawned[rep] = 1;
     }
     n_amb = __reduce_add_sync(FULL, (unsigned)n_amb);
     const unsigned np = __reduce_add_sync(FULL, (unsigned)n_pairs);
@@ -188,11 +342,6 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     unsigned long long t = ~0ull;
     for (int w = 0; w < nwarps; w++) t = min(t, sh[w]);
     return t;
-}
-__device__ __forceinline__ double min_image_dd(double r, double L) {  // mathtools.h:64-71 in FP64
-    const double s = (double)((0.0 < r) - (r < 0.0));
-    const double h = __ddiv_rn(__dmul_rn(s, L), 2.0);
-    return __dsub_rn(fmod(__dadd_rn(r, h), L), h);
 }
 
 // CreatePredator / CreateFishNet (agents_dynamics.cpp:534-555, 485-528) by the whole block:
@@ -257,13 +406,6 @@ __device__ void block_spawn(const DevParams &P, int NP, uint32_t rep, uint32_t s
     }
     __syncthreads();
 }
-
-// when the predators of a swarm appear and re-appear, in step indices (host-evaluated, swarmdyn.cpp:153-170)
-struct PredSchedule {
-    uint32_t s_pred;    // first step with s >= pred_time/dt
-    int32_t s_trunc;    // (int)(pred_time/dt), origin of the net's re-spawn period
-    int32_t needed;     // re-spawn period in steps (fish net), 0 = never
-};
 
 template <bool PRED, int MAXT>
 __global__ void __launch_bounds__(MAXT)
@@ -460,20 +602,8 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                     pphi_s[j] = ph;
                 }
                 __syncthreads();
-                if (P.pred_kill != 0 && alive) {  // FishNetKill :780-820
-                    const float4 p0 = pred_s[0], p1 = pred_s[1];
-                    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
-                    if (P.BC == 0) { vn[0] = min_image_dd(vn[0], P.dL); vn[1] = min_image_dd(vn[1], P.dL); }
-                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
-                    const double net_len = (double)(NP - 1) * dist;
-                    float s0, c0;
-                    sincosf(pphi_s[0], &s0, &c0);
-                    double r[2] = {__dsub_rn((double)a.x, (double)p0.x), __dsub_rn((double)a.y, (double)p0.y)};
-                    if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
-                    const double front = __dadd_rn(__dmul_rn((double)c0, r[0]), __dmul_rn((double)s0, r[1]));
-                    const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
-                    die = front > 0 && front < P.d_kill_range && side > 0 && side <= net_len;
-                }
+                if (P.pred_kill != 0 && alive)  // FishNetKill :780-820
+                    die = sbc_net_kills(a.x, a.y, pred_s[0], pred_s[1], pphi_s[0], NP, P);
             } else {
                 // MovePredator :567-613
                 const float4 p0 = pred_s[0];
@@ -511,29 +641,18 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                 }
                 __syncthreads();
                 if (P.pred_kill != 0) {  // PredKill :826-915
-                    const double px = (double)pred_s[0].x, py = (double)pred_s[0].y;
-                    const double r_sense = 4 * P.d_kill_range;
-                    double d = INFINITY;
-                    if (alive) {
-                        double r[2] = {__dsub_rn((double)a.x, px), __dsub_rn((double)a.y, py)};
-                        if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
-                        d = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
-                    }
+                    const float4 pp = pred_s[0];
+                    KillClass kc = {false, false, false};
+                    if (alive) kc = sbc_kill_classify(a.x, a.y, pp.x, pp.y, P);
                     if (P.pred_kill == 1) {
-                        die = alive && d <= P.d_kill_range;
+                        die = kc.within;
                     } else {
-                        const bool sensed = alive && d <= r_sense;
-                        const bool cand = sensed && d < P.d_kill_range;
-                        const double n_sensed = block_sum_d(sensed ? 1.0 : 0.0, red_s, nwarps);
-                        const double total = block_sum_d(cand ? (P.d_kill_range - d) / P.d_kill_range : 0.0, red_s, nwarps);
-                        const double eff = (n_sensed > 0)
-                                               ? (double)P.kill_rate * 0.5 * (tanh(-1.0 * (n_sensed - (double)P.N_confu)) + 1.0)
-                                               : 0.0;
-                        if (cand) {
-                            double pk = 0;
-                            if (P.pred_kill == 2) pk = (double)P.kill_rate * (double)P.dt;
-                            else if (P.pred_kill == 3) pk = eff * (double)P.dt;
-                            else if (P.pred_kill == 4) pk = eff * (double)P.dt * (((P.d_kill_range - d) / P.d_kill_range) / total);
+                        const int n_sensed = __syncthreads_count(kc.sensed ? 1 : 0);
+                        double total = 0.0;
+                        if (P.pred_kill == 4)
+                            total = block_sum_d(kc.cand ? sbc_kill_weight(a.x, a.y, pp.x, pp.y, P) : 0.0, red_s, nwarps);
+                        if (kc.cand) {
+                            const double pk = sbc_kill_probability(a.x, a.y, pp.x, pp.y, n_sensed, total, S.kill_eff, P);
                             const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DECISION);
                             die = pk > (double)q.w * (1.0 / 4294967296.0);
                         }
@@ -572,26 +691,33 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
 }  // namespace
 
 bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
-                            cudaStream_t st, long long s_pred, int s_trunc, int needed) {
+                            cudaStream_t st, long long s_pred, int s_trunc, int needed, bool force_block) {
     const int N = S.N;
     if (N > 1024 || N < 1 || S.Npred > 1024) return false;
     const uint32_t s0 = (uint32_t)s_first, ns = (uint32_t)n_steps;
-    if (N <= 32 && S.Npred == 0) {
+    PredSchedule sched;
+    sched.s_pred = (s_pred < 0 || s_pred > 0xffffffffll) ? 0xffffffffu : (uint32_t)s_pred;
+    sched.s_trunc = s_trunc;
+    sched.needed = needed;
+    if (N <= 32 && S.Npred <= 1 && !(force_block && S.Npred == 1)) {
         const int tps = (N <= 8) ? 8 : (N <= 16) ? 16 : 32;
         const int spw = 32 / tps;
         const long long warps = ((long long)S.R + spw - 1) / spw;
         const int wpb = 4;
         const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-#define SBC_WARP_LAUNCH(T, B)                                                                   \
-    do {                                                                                        \
-        if (P.voronoi) swarm_warp_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns); \
-        else swarm_warp_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);         \
+#define SBC_WARP_LAUNCH(T, B, PR)                                                                          \
+    do {                                                                                                   \
+        if (P.voronoi) swarm_warp_kernel<T, B, true, PR><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched); \
+        else swarm_warp_kernel<T, B, false, PR><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched);         \
     } while (0)
-#define SBC_WARP_BC(T)                                                  \
-    do {                                                                \
-        if (P.BC == 6) SBC_WARP_LAUNCH(T, 6);                           \
-        else if (P.BC == 0) SBC_WARP_LAUNCH(T, 0);                      \
-        else SBC_WARP_LAUNCH(T, BC_RUNTIME);                            \
+#define SBC_WARP_BC(T)                                                                     \
+    do {                                                                                   \
+        if (S.Npred == 1) {  /* predator variants: periodic box or run-time boundary */    \
+            if (P.BC == 0) SBC_WARP_LAUNCH(T, 0, true);                                    \
+            else SBC_WARP_LAUNCH(T, BC_RUNTIME, true);                                     \
+        } else if (P.BC == 6) SBC_WARP_LAUNCH(T, 6, false);                                \
+        else if (P.BC == 0) SBC_WARP_LAUNCH(T, 0, false);                                  \
+        else SBC_WARP_LAUNCH(T, BC_RUNTIME, false);                                        \
     } while (0)
         if (tps == 8) SBC_WARP_BC(8);
         else if (tps == 16) SBC_WARP_BC(16);
@@ -611,10 +737,6 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         cudaFuncSetAttribute(swarm_block_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_set = true;
     }
-    PredSchedule sched;
-    sched.s_pred = (s_pred < 0 || s_pred > 0xffffffffll) ? 0xffffffffu : (uint32_t)s_pred;
-    sched.s_trunc = s_trunc;
-    sched.needed = needed;
     // two register budgets: swarms of up to 256 agents get the larger one
     if (nthreads <= 256) {
         if (S.Npred > 0) swarm_block_kernel<true, 256><<<S.R, nthreads, smem, st>>>(P, S, s0, ns, sched);

@@ -3,16 +3,18 @@
 // other's agent positions through distributed shared memory (DSMEM). The whole Step()
 // (/root/reference/src/swarmdyn.cpp:143-204) - interaction of the rows that start a burst, predator
 // detection, burst decision, burst-coast update, boundary, predator spawn / move / kill - runs inside one
-// persistent launch for many steps, with ONE cluster barrier per step (two or three in the predator
-// phase). This is the Blackwell answer to swarms that are too large for one SM to step quickly
-// (swarm_block.cu: ~13 us/step at N = 1024) and too small to amortise kernel launches (update.cu path).
+// persistent launch for many steps, with ONE cluster barrier per step, predators included. This is the
+// Blackwell answer to swarms that are too large for one SM to step quickly (swarm_block.cu: ~13 us/step
+// at N = 1024) and too small to amortise kernel launches (update.cu path).
 //
 // Data flow per step: every CTA publishes {x, y, vx, vy} of its agents in its own shared memory
 // (double-buffered by step parity) -> cluster.sync() -> the warps of a CTA process the CTA's
-// burst-starting rows, streaming the N partners out of all CTAs' shared memory -> thread-local update.
-// Cluster-wide reductions (centre of mass at spawn, closest prey for the chasing predator, sensed /
-// weight sums for the kill rules) publish one partial per CTA, synchronise, and every CTA combines the
-// partials in rank order - all CTAs hold identical copies of the predators.
+// burst-starting rows against a local copy of the N partners (one bulk DSMEM read) -> thread-local update.
+// The predator's move and kill of step s need the positions after that step's update, i.e. exactly what
+// the exchange of step s + 1 publishes: they are evaluated there, by every CTA on its own copy of the
+// whole swarm (centre of mass at spawn, closest prey, sensed / weight sums, dead set), so all CTAs hold
+// identical predators and dead sets without a second barrier; a launch ends with one extra exchange
+// for the predator phase of its last step.
 #include <cooperative_groups.h>
 
 #include "sbc_kernels.cuh"
@@ -32,19 +34,10 @@ struct PredSchedule {
     int32_t s_trunc;
     int32_t needed;
 };
-struct ChaseEntry {  // one CTA's closest prey
-    unsigned long long key;
-    float dx, dy;
-};
 
 __device__ __forceinline__ double warp_sum_d(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-__device__ __forceinline__ double min_image_dd(double r, double L) {
-    const double s = (double)((0.0 < r) - (r < 0.0));
-    const double h = __ddiv_rn(__dmul_rn(s, L), 2.0);
-    return __dsub_rn(fmod(__dadd_rn(r, h), L), h);
 }
 
 template <bool PRED>
@@ -63,9 +56,7 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
     float4 *pv_s = reinterpret_cast<float4 *>(smem_raw);                  // [2][CT]
     RowResult *res_s = reinterpret_cast<RowResult *>(pv_s + 2 * CT);      // [CT]
     float2 *flee_s = reinterpret_cast<float2 *>(res_s + CT);              // [CT]
-    double *part_s = reinterpret_cast<double *>(flee_s + CT);             // [8] this CTA's partial sums (DSMEM-read by the others)
-    ChaseEntry *chase_s = reinterpret_cast<ChaseEntry *>(part_s + 8);     // [1]
-    double *wred_s = reinterpret_cast<double *>(chase_s + 1);             // [NW][5] warp partials
+    double *wred_s = reinterpret_cast<double *>(flee_s + CT);             // [NW][5] warp partials
     unsigned long long *wkey_s = reinterpret_cast<unsigned long long *>(wred_s + NW * 5);  // [NW]
     unsigned *act_s = reinterpret_cast<unsigned *>(wkey_s + NW);          // [NW]
     int *n_rows_s = reinterpret_cast<int *>(act_s + NW);                  // [4]
@@ -105,41 +96,40 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
     bool spawned = false;
     const float qnan = __int_as_float(0x7fc00000);
 
-    // sum of up to 5 doubles per thread over the whole cluster; every CTA gets the same totals
-    auto cluster_sum = [&](double *v, int n) {
+    // sums of n <= 5 doubles per thread over this CTA (every thread gets the totals)
+    auto cta_sum = [&](double *v, int n) {
         for (int k = 0; k < n; k++) {
             const double w = warp_sum_d(v[k]);
             if (lane == 0) wred_s[warp * 5 + k] = w;
         }
         __syncthreads();
-        if (tid < n) {
-            double tot = 0;
-            for (int w = 0; w < NW; w++) tot += wred_s[w * 5 + tid];
-            part_s[tid] = tot;
-        }
-        cluster.sync();
         for (int k = 0; k < n; k++) {
             double tot = 0;
-            for (int c = 0; c < C; c++) tot += cluster.map_shared_rank(part_s, c)[k];
+            for (int w = 0; w < NW; w++) tot += wred_s[w * 5 + k];
             v[k] = tot;
         }
-        cluster.sync();   // nobody overwrites part_s while a neighbour still reads it
+        __syncthreads();
     };
 
-    auto spawn = [&](uint32_t step, uint32_t slot) {  // CreatePredator / CreateFishNet, agents_dynamics.cpp:485-555
-        double v[5] = {0, 0, 0, 0, alive ? 1.0 : 0.0};
-        if (alive) {
+    // CreatePredator / CreateFishNet (agents_dynamics.cpp:485-555) from the swarm copy in all_s; every CTA
+    // computes the same predators
+    auto spawn = [&](uint32_t step, uint32_t slot) {
+        double v[5] = {0, 0, 0, 0, 0};
+        const float scaling = SBC_TWO_PI_F * P.invL;
+        for (int c = 0; c < C; c++) {
+            const float4 p = all_s[c * CT + tid];
+            if (p.x != p.x) continue;
+            v[4] += 1.0;
             if (P.BC == 0) {
-                const float scaling = SBC_TWO_PI_F * P.invL;
                 float sn, cs;
-                sincosf(scaling * a.x, &sn, &cs); v[0] = cs; v[1] = sn;
-                sincosf(scaling * a.y, &sn, &cs); v[2] = cs; v[3] = sn;
+                sincosf(scaling * p.x, &sn, &cs); v[0] += cs; v[1] += sn;
+                sincosf(scaling * p.y, &sn, &cs); v[2] += cs; v[3] += sn;
             } else {
-                v[0] = a.x;
-                v[2] = a.y;
+                v[0] += p.x;
+                v[2] += p.y;
             }
         }
-        cluster_sum(v, 5);
+        cta_sum(v, 5);
         float comx, comy;
         if (P.BC == 0) {
             comx = (float)((atan2(-v[1] / v[4], -v[0] / v[4]) + SBC_PI_D) / (2 * SBC_PI_D / P.dL));
@@ -184,18 +174,140 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
         __syncthreads();
     };
 
-    for (uint32_t s = s_first; s != s_first + n_steps; s++) {
-        const bool pred_phase = PRED && (s >= sched.s_pred);
-        if (PRED) {
-            if (s == sched.s_pred) { spawn(s, 0); spawned = true; }
-            if (NP > 1 && pred_phase && sched.needed > 0 && ((int)s - sched.s_trunc) % sched.needed == 0) spawn(s, 1);
+    // Predator move + kill of step sp (swarmdyn.cpp:192-203), evaluated on the positions AFTER that step's
+    // agent update - which are exactly what the next exchange publishes. Every CTA therefore runs this
+    // phase on its own full copy of the swarm (all_s) right after the exchange: identical predators and
+    // identical dead sets in every CTA without any further cluster barrier. A thread looks after the
+    // agents c * CT + tid, c < C; the one with c == crank is its own.
+    auto predator_phase = [&](uint32_t sp) {
+        unsigned dead_mask = 0;   // bit c: agent c * CT + tid dies
+        if (NP > 1) {
+            for (int j = tid; j < NP; j += CT) {  // MoveFishNet :616-624
+                float4 p = pred_s[j];
+                float ph = pphi_s[j];
+                p.x += p.z * P.dt;
+                p.y += p.w * P.dt;
+                sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
+                pred_s[j] = p;
+                pphi_s[j] = ph;
+            }
+            __syncthreads();
+            if (P.pred_kill != 0) {  // FishNetKill :780-820
+                const float4 p0 = pred_s[0], p1 = pred_s[1];
+                const float ph0 = pphi_s[0];
+                for (int c = 0; c < C; c++) {
+                    const float4 p = all_s[c * CT + tid];
+                    if (p.x == p.x && sbc_net_kills(p.x, p.y, p0, p1, ph0, NP, P)) dead_mask |= 1u << c;
+                }
+            }
+        } else {
+            const float4 p0 = pred_s[0];
+            float lphi = pphi_s[0];
+            if (P.pred_move == 0) {  // MovePredator :567-613, random walk
+                const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, sp, 2u);
+                const float u1 = (float)(((double)q.x + 1.0) * (1.0 / 4294967296.0));
+                const float u2 = (float)((double)q.y * (1.0 / 4294967296.0));
+                const float gss = sqrtf(-2.f * logf(u1)) * cosf(SBC_TWO_PI_F * u2);
+                lphi = fmodf(lphi + P.noisep * gss * sqrtf(P.pred_speed), SBC_TWO_PI_F);
+            } else {  // chase the closest prey: arg-min over the whole swarm inside the CTA
+                unsigned long long best = ~0ull;
+                for (int c = 0; c < C; c++) {
+                    const float4 p = all_s[c * CT + tid];
+                    if (p.x != p.x) continue;
+                    float dx = p.x - p0.x, dy = p.y - p0.y;
+                    if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, p.x, P); dy = sbc_delta_pbc(p0.y, p.y, P); }
+                    best = min(best, ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)(c * CT + tid));
+                }
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
+                if (lane == 0) wkey_s[warp] = best;
+                __syncthreads();
+                best = ~0ull;
+                for (int w = 0; w < NW; w++) best = min(best, wkey_s[w]);
+                if (best != ~0ull) {
+                    const float4 p = all_s[(unsigned)(best & 0xffffffffu)];
+                    float dx = p.x - p0.x, dy = p.y - p0.y;
+                    if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, p.x, P); dy = sbc_delta_pbc(p0.y, p.y, P); }
+                    lphi = atan2f(dy, dx);
+                }
+            }
+            // every thread moves its own copy of the predator; thread 0 stores it
+            float sn, cs;
+            sincosf(lphi, &sn, &cs);
+            float vx = P.pred_speed * cs, vy = P.pred_speed * sn;
+            float x = p0.x + vx * P.dt, y = p0.y + vy * P.dt;
+            float ph = lphi;
+            sbc_boundary(x, y, vx, vy, ph, P, P.BC);
+            __syncthreads();   // every thread has read pred_s[0]
+            if (tid == 0) {
+                pred_s[0] = make_float4(x, y, vx, vy);
+                pphi_s[0] = ph;
+            }
+            if (P.pred_kill != 0) {  // PredKill :826-915
+                unsigned cand_mask = 0;
+                double v[2] = {0.0, 0.0};   // N_sensed, sum of the selection weights
+                for (int c = 0; c < C; c++) {
+                    const float4 p = all_s[c * CT + tid];
+                    if (p.x != p.x) continue;
+                    const KillClass kc = sbc_kill_classify(p.x, p.y, x, y, P);
+                    if (P.pred_kill == 1) {
+                        if (kc.within) dead_mask |= 1u << c;
+                    } else if (kc.sensed) {
+                        v[0] += 1.0;
+                        if (kc.cand) {
+                            cand_mask |= 1u << c;
+                            if (P.pred_kill == 4) v[1] += sbc_kill_weight(p.x, p.y, x, y, P);
+                        }
+                    }
+                }
+                if (P.pred_kill > 1) {
+                    cta_sum(v, 2);
+                    for (int c = 0; c < C; c++) {
+                        if (!((cand_mask >> c) & 1u)) continue;
+                        const float4 p = all_s[c * CT + tid];
+                        const double pk = sbc_kill_probability(p.x, p.y, x, y, (int)v[0], v[1], S.kill_eff, P);
+                        const uint4 q = sbc_draw(P, rep, (uint32_t)(c * CT + tid), sp, SBC_SLOT_DECISION);
+                        if (pk > (double)q.w * (1.0 / 4294967296.0)) dead_mask |= 1u << c;
+                    }
+                }
+            }
         }
+        for (int c = 0; c < C; c++)   // split_dead: the dead leave every CTA's copy of the swarm
+            if ((dead_mask >> c) & 1u) all_s[c * CT + tid] = make_float4(qnan, qnan, 0.f, 0.f);
+        if ((dead_mask >> crank) & 1u) {
+            alive = false;
+            died = true;
+            n_killed++;
+        }
+        __syncthreads();
+    };
+
+    const uint32_t s_end = s_first + n_steps;
+    for (uint32_t s = s_first;; s++) {
+        // the predator phase of step s - 1 is still to do when this launch has run that step
+        const bool pending = PRED && s != s_first && s != 0 && (s - 1 >= sched.s_pred);
+        if (s == s_end && !pending) break;
+        const bool pred_phase = PRED && (s >= sched.s_pred);
+        const bool spawn0 = PRED && s != s_end && s == sched.s_pred;
+        const bool spawn1 = PRED && s != s_end && NP > 1 && pred_phase && sched.needed > 0 &&
+                            ((int)s - sched.s_trunc) % sched.needed == 0;
         float4 *my_pv = pv_s + (s & 1u) * CT;
         my_pv[tid] = alive ? make_float4(a.x, a.y, a.vx, a.vy) : make_float4(qnan, qnan, 0.f, 0.f);
+        cluster.sync();   // the one cluster barrier of the step: everybody's positions are visible
+        bool have_all = false;
+        if (pending || spawn0 || spawn1) {
+            for (int c = 0; c < C; c++)
+                all_s[c * CT + tid] = (cluster.map_shared_rank(pv_s, c) + (s & 1u) * CT)[tid];
+            __syncthreads();
+            have_all = true;
+            if (pending) predator_phase(s - 1);
+            if (s == s_end) break;
+            if (spawn0) { spawn(s, 0); spawned = true; }   // swarmdyn.cpp:153-158
+            if (spawn1) spawn(s, 1);                        // :160-170
+        }
         const bool first = alive && (a.bin_step == P.burst_steps);
         const unsigned m = __ballot_sync(FULL, first);
         if (lane == 0) act_s[warp] = m;
-        cluster.sync();   // (A) the positions of this step are visible cluster-wide
+        __syncthreads();
         RowAcc acc;
         row_acc_clear(acc);
         // ordered list of this CTA's burst-starting rows
@@ -219,7 +331,7 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
         }
         __syncthreads();
         const int n_first = n_rows_s[0];
-        if (n_first > 0) {
+        if (n_first > 0 && !have_all) {
             // one bulk read of every CTA's positions through DSMEM (all loads of a thread in flight at once),
             // so that the row sweeps below run out of local shared memory
             for (int c = 0; c < C; c++)
@@ -229,6 +341,9 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
         // every burst-starting row is swept by ALL warps of the CTA (a warp takes every NW-th group of 32
         // partners), so the step's critical path is N / (32 NW) iterations instead of N / 32; the warp
         // partials are combined in warp order by one thread - a fixed order, independent of scheduling
+        // predator detection: up to four predators share one Philox block and are handled by the row's own
+        // thread after the sweeps (all rows in parallel); larger nets are spread over the lanes of a warp
+        const bool row_detect = pred_phase && NP > 4;
         for (int kr = 0; kr < n_first; kr++) {
             const int row_l = rows_s[kr];             // index inside this CTA
             const int row = crank * CT + row_l;       // index inside the swarm
@@ -261,7 +376,7 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
             ct = __reduce_add_sync(FULL, ct);
             float f0 = 0.f, f1 = 0.f;
             int cf = 0;
-            if (pred_phase && warp == (kr % NW)) {  // IntCalcPred (agents_interact.cpp:252-292): one warp per row
+            if (row_detect && warp == (kr % NW)) {  // IntCalcPred (agents_interact.cpp:252-292): one warp per row
                 RowAcc fa;
                 row_acc_clear(fa);
                 for (int jb = lane; 4 * jb < NP; jb += 32) {
@@ -293,7 +408,7 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
                 int *wi = wsum_i + warp * 4;
                 wf[0] = rx; wf[1] = ry; wf[2] = gx; wf[3] = gy; wf[4] = tx; wf[5] = ty;
                 wi[0] = cr; wi[1] = ca; wi[2] = ct;
-                if (pred_phase && warp == (kr % NW)) { flee_s[row_l] = make_float2(f0, f1); wi[3] = cf; }
+                if (row_detect && warp == (kr % NW)) { flee_s[row_l] = make_float2(f0, f1); wi[3] = cf; }
             }
             __syncthreads();
             if (tid == 0) {
@@ -306,9 +421,9 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
                 RowResult r;
                 r.v0 = (c3[0] > 0) ? v[0] : v[2]; r.v1 = (c3[0] > 0) ? v[1] : v[3]; r.v2 = v[4]; r.v3 = v[5];
                 r.cr = c3[0]; r.ca = c3[1]; r.ct = c3[2];
-                r.cf = pred_phase ? wsum_i[(kr % NW) * 4 + 3] : 0;
+                r.cf = row_detect ? wsum_i[(kr % NW) * 4 + 3] : 0;
                 res_s[row_l] = r;
-                if (!pred_phase) flee_s[row_l] = make_float2(0.f, 0.f);
+                if (!row_detect) flee_s[row_l] = make_float2(0.f, 0.f);
             }
             __syncthreads();
         }
@@ -320,6 +435,19 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
             else { acc.alg_x = r.v0; acc.alg_y = r.v1; }
             acc.att_x = r.v2; acc.att_y = r.v3;
             acc.flee_x = flee_s[tid].x; acc.flee_y = flee_s[tid].y;
+            if (pred_phase && !row_detect) {  // IntCalcPred, agents_interact.cpp:252-292
+                const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DETECT0);
+                const uint32_t r4[4] = {q.x, q.y, q.z, q.w};
+                RowAcc fa;
+                row_acc_clear(fa);
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (j < NP)
+                        sbc_detect_accumulate(fa, a.x, a.y, pred_s[j].x, pred_s[j].y, (double)r4[j] * (1.0 / 4294967296.0), P);
+                acc.c_flee = fa.c_flee;
+                acc.flee_x = fa.flee_x;
+                acc.flee_y = fa.flee_y;
+            }
         }
         if (alive) {
             double u_social = 0.0;
@@ -335,119 +463,6 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
             uint32_t fl = 0;
             sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
             flags_acc |= fl;
-        }
-        if (pred_phase) {  // swarmdyn.cpp:192-203; every CTA keeps an identical copy of the predators
-            bool die = false;
-            if (NP > 1) {
-                __syncthreads();
-                for (int j = tid; j < NP; j += CT) {  // MoveFishNet :616-624
-                    float4 p = pred_s[j];
-                    float ph = pphi_s[j];
-                    p.x += p.z * P.dt;
-                    p.y += p.w * P.dt;
-                    sbc_boundary(p.x, p.y, p.z, p.w, ph, P, P.BC);
-                    pred_s[j] = p;
-                    pphi_s[j] = ph;
-                }
-                __syncthreads();
-                if (P.pred_kill != 0 && alive) {  // FishNetKill :780-820
-                    const float4 p0 = pred_s[0], p1 = pred_s[1];
-                    double vn[2] = {__dsub_rn((double)p1.x, (double)p0.x), __dsub_rn((double)p1.y, (double)p0.y)};
-                    if (P.BC == 0) { vn[0] = min_image_dd(vn[0], P.dL); vn[1] = min_image_dd(vn[1], P.dL); }
-                    const double dist = __dsqrt_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])));
-                    const double net_len = (double)(NP - 1) * dist;
-                    float s0, c0;
-                    sincosf(pphi_s[0], &s0, &c0);
-                    double r[2] = {__dsub_rn((double)a.x, (double)p0.x), __dsub_rn((double)a.y, (double)p0.y)};
-                    if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
-                    const double front = __dadd_rn(__dmul_rn((double)c0, r[0]), __dmul_rn((double)s0, r[1]));
-                    const double side = __dadd_rn(__dmul_rn(vn[0], r[0]), __dmul_rn(vn[1], r[1]));
-                    die = front > 0 && front < P.d_kill_range && side > 0 && side <= net_len;
-                }
-            } else {
-                const float4 p0 = pred_s[0];
-                float lphi = pphi_s[0];
-                if (P.pred_move == 0) {  // MovePredator :567-613, random walk
-                    const uint4 q = sbc_draw(P, rep, SBC_PREDATOR_AGENT_ID, s, 2u);
-                    const float u1 = (float)(((double)q.x + 1.0) * (1.0 / 4294967296.0));
-                    const float u2 = (float)((double)q.y * (1.0 / 4294967296.0));
-                    const float gss = sqrtf(-2.f * logf(u1)) * cosf(SBC_TWO_PI_F * u2);
-                    lphi = fmodf(pphi_s[0] + P.noisep * gss * sqrtf(P.pred_speed), SBC_TWO_PI_F);
-                } else {  // chase the closest prey: block arg-min, then the best of the CTAs
-                    unsigned long long key = ~0ull;
-                    float dx = 0.f, dy = 0.f;
-                    if (alive) {
-                        dx = a.x - p0.x; dy = a.y - p0.y;
-                        if (P.BC == 0) { dx = sbc_delta_pbc(p0.x, a.x, P); dy = sbc_delta_pbc(p0.y, a.y, P); }
-                        key = ((unsigned long long)__float_as_uint(dx * dx + dy * dy) << 32) | (unsigned)t;
-                    }
-                    unsigned long long best = key;
-                    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULL, best, o));
-                    if (lane == 0) wkey_s[warp] = best;
-                    __syncthreads();
-                    best = ~0ull;
-                    for (int w = 0; w < NW; w++) best = min(best, wkey_s[w]);
-                    if (tid == 0) chase_s->key = ~0ull;
-                    __syncthreads();
-                    if (best != ~0ull && key == best) { chase_s->key = key; chase_s->dx = dx; chase_s->dy = dy; }
-                    cluster.sync();   // (B)
-                    ChaseEntry win;
-                    win.key = ~0ull; win.dx = 0.f; win.dy = 0.f;
-                    for (int c = 0; c < C; c++) {
-                        const ChaseEntry e = *cluster.map_shared_rank(chase_s, c);
-                        if (e.key < win.key) win = e;
-                    }
-                    if (win.key != ~0ull) lphi = atan2f(win.dy, win.dx);
-                    cluster.sync();   // chase_s may be rewritten next step
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    float sn, cs;
-                    sincosf(lphi, &sn, &cs);
-                    float vx = P.pred_speed * cs, vy = P.pred_speed * sn;
-                    float x = p0.x + vx * P.dt, y = p0.y + vy * P.dt;
-                    float ph = lphi;
-                    sbc_boundary(x, y, vx, vy, ph, P, P.BC);
-                    pred_s[0] = make_float4(x, y, vx, vy);
-                    pphi_s[0] = ph;
-                }
-                __syncthreads();
-                if (P.pred_kill != 0) {  // PredKill :826-915
-                    const double px = (double)pred_s[0].x, py = (double)pred_s[0].y;
-                    const double r_sense = 4 * P.d_kill_range;
-                    double d = INFINITY;
-                    if (alive) {
-                        double r[2] = {__dsub_rn((double)a.x, px), __dsub_rn((double)a.y, py)};
-                        if (P.BC == 0) { r[0] = min_image_dd(r[0], P.dL); r[1] = min_image_dd(r[1], P.dL); }
-                        d = __dsqrt_rn(__dadd_rn(__dmul_rn(r[0], r[0]), __dmul_rn(r[1], r[1])));
-                    }
-                    if (P.pred_kill == 1) {
-                        die = alive && d <= P.d_kill_range;
-                    } else {
-                        const bool sensed = alive && d <= r_sense;
-                        const bool cand = sensed && d < P.d_kill_range;
-                        double v[2] = {sensed ? 1.0 : 0.0, cand ? (P.d_kill_range - d) / P.d_kill_range : 0.0};
-                        cluster_sum(v, 2);
-                        const double n_sensed = v[0], total = v[1];
-                        const double eff = (n_sensed > 0)
-                                               ? (double)P.kill_rate * 0.5 * (tanh(-1.0 * (n_sensed - (double)P.N_confu)) + 1.0)
-                                               : 0.0;
-                        if (cand) {
-                            double pk = 0;
-                            if (P.pred_kill == 2) pk = (double)P.kill_rate * (double)P.dt;
-                            else if (P.pred_kill == 3) pk = eff * (double)P.dt;
-                            else if (P.pred_kill == 4) pk = eff * (double)P.dt * (((P.d_kill_range - d) / P.d_kill_range) / total);
-                            const uint4 q = sbc_draw(P, rep, (uint32_t)t, s, SBC_SLOT_DECISION);
-                            die = pk > (double)q.w * (1.0 / 4294967296.0);
-                        }
-                    }
-                }
-            }
-            if (die) {
-                alive = false;
-                died = true;
-                n_killed++;
-            }
         }
     }
     if (valid && (alive || died)) {
@@ -487,8 +502,8 @@ bool sbc_cluster_supported(const DevParams &P, int N, int Npred) {
 cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
                                      cudaStream_t st, long long s_pred, int s_trunc, int needed) {
     const int C = (S.N + CT - 1) / CT;
-    const size_t smem = 2 * CT * sizeof(float4) + CT * sizeof(RowResult) + CT * sizeof(float2) + 8 * sizeof(double) +
-                        sizeof(ChaseEntry) + (CT / 32) * 5 * sizeof(double) + (CT / 32) * sizeof(unsigned long long) +
+    const size_t smem = 2 * CT * sizeof(float4) + CT * sizeof(RowResult) + CT * sizeof(float2) +
+                        (CT / 32) * 5 * sizeof(double) + (CT / 32) * sizeof(unsigned long long) +
                         (CT / 32) * sizeof(unsigned) + 4 * sizeof(int) + CT * sizeof(unsigned short) +
                         (CT / 32) * 8 * sizeof(float) + (CT / 32) * 4 * sizeof(int) + (size_t)C * CT * sizeof(float4) + (size_t)S.Npred * (sizeof(float4) + sizeof(float)) + 64;
     PredSchedule sched;

@@ -46,7 +46,7 @@ def test_one_step_with_predator_present(kill, move, npred, mode, multikernel):
     for trial in range(3):
         w = pyorc.World(sp, N, npred, seed=100 + trial, replicate=0)
         g = _swarm(sp, N, npred, seed=100 + trial)
-        g.force_multikernel(True)
+        g.force_multikernel(multikernel)
         for obj in (w, g):
             obj.set_state(**st)
             obj.set_predators(px, py, pphi, 1)
@@ -205,3 +205,111 @@ def test_cluster_kernel_spawn_and_long_run():
     assert int(g.counts()[1][0]) > 0
     w.close()
     g.close()
+
+
+@pytest.mark.parametrize('N', [8, 13, 30])
+@pytest.mark.parametrize('kill,move,mode', [(1, 1, 'natPred'), (2, 1, 'natPredNoConfu'), (3, 1, 'natPred'),
+                                            (4, 1, 'natPred'), (1, 0, 'sinFisher')])
+def test_warp_kernel_one_step_with_predator(N, kill, move, mode):
+    """Ensembles of small swarms with one predator each run inside warps (swarm_warp_kernel<.., PRED>):
+    every replicate against its own oracle world."""
+    R = 24
+    sp, _, _ = make_params(mode, N, BC=0, size=100.0, Npred=1, pred_kill=kill, pred_move=move, pred_time=0.0,
+                           time=50.0, N_confu=50, kill_rate=4000.0 if kill == 4 else 400.0)
+    rng = np.random.default_rng(N * 11 + kill)
+    sts = []
+    for r in range(R):
+        st = random_state(N, sp, rng, spread=12.0)
+        st['bin_step'] = np.where(rng.random(N) < 0.4, sp.burst_steps, st['bin_step']).astype(np.uint32)
+        sts.append(st)
+    px = np.full((R, 1), 50.0) + rng.uniform(-3, 3, (R, 1))
+    py = np.full((R, 1), 50.0) + rng.uniform(-3, 3, (R, 1))
+    pphi = rng.uniform(0, 2 * np.pi, (R, 1))
+    g = _swarm(sp, N, 1, n_replicates=R, seed=300)
+    g.set_state(**{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    g.set_predators(px, py, pphi, 1)
+    g.step(6, 1)
+    assert g.stats()['block_launches'] == 1
+    gs = g.get_state()
+    gp = g.get_predators()
+    gc = g.counts()
+    killed = mism = 0
+    for r in range(R):
+        w = pyorc.World(sp, N, 1, seed=300, replicate=r)
+        w.set_state(**sts[r])
+        w.set_predators(px[r], py[r], pphi[r], 1)
+        w.step(6, 1)
+        o = w.get_state()
+        assert np.array_equal(o['alive'], gs['alive'][r]), (r, np.where(o['alive'] != gs['alive'][r])[0])
+        al = o['alive'].astype(bool)
+        killed += N - int(al.sum())
+        assert np.array_equal(o['bin_step'][al], gs['bin_step'][r][al])
+        assert np.array_equal(o['steps_till_burst'][al], gs['steps_till_burst'][r][al])
+        ok = (np.abs(o['x'] - gs['x'][r]) <= 1e-5 * np.maximum(1, np.abs(o['x']))) & \
+             (np.abs(o['y'] - gs['y'][r]) <= 1e-5 * np.maximum(1, np.abs(o['y']))) & \
+             (np.hypot(o['fx'] - gs['fx'][r], o['fy'] - gs['fy'][r]) <= 2e-5 * np.maximum(1, np.hypot(o['fx'], o['fy'])))
+        mism += int((~ok[al]).sum())
+        po = w.get_predators()
+        # position to the one-step tolerance; the chase heading comes from an FP32 difference of positions
+        # (|d| ~ 1 at coordinates ~ 50), so speed * (cos, sin) carries ~1e-5 rad * speed
+        assert np.allclose(po[:, :2], gp[r][:, :2], rtol=1e-5, atol=1e-4), (r, po, gp[r])
+        assert np.allclose(po[:, 2:4], gp[r][:, 2:4], atol=2e-3), (r, po, gp[r])
+        assert w.counts() == (int(gc[0][r]), int(gc[1][r]))
+        w.close()
+    g.close()
+    assert killed > 0
+    assert mism <= 3, mism
+
+
+def test_warp_kernel_spawn_like_oracle():
+    N, R = 30, 6
+    sp, _, _ = make_params('natPred', N, BC=0, size=100.0, Npred=1, pred_kill=0, pred_move=1, pred_time=0.01, time=50.0)
+    rng = np.random.default_rng(8)
+    sts = [random_state(N, sp, rng, spread=20.0) for _ in range(R)]
+    g = _swarm(sp, N, 1, n_replicates=R, seed=9, replicate_offset=2)
+    g.set_state(**{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    g.step(0, 12)   # spawn at s = 10
+    gp = g.get_predators()
+    for r in range(R):
+        w = pyorc.World(sp, N, 1, seed=9, replicate=2 + r)
+        w.set_state(**sts[r])
+        w.step(0, 12)
+        po = w.get_predators()
+        assert np.allclose(po[:, :2] % 100.0, gp[r][:, :2] % 100.0, atol=2e-3), (r, po, gp[r])
+        assert np.allclose(po[:, 2:4], gp[r][:, 2:4], atol=2e-3)
+        w.close()
+    g.close()
+
+
+@pytest.mark.parametrize('N,bc', [(30, 0), (16, 0), (30, 5)])
+def test_warp_and_block_predator_kernels_agree(N, bc):
+    """The in-warp predator path and the one-block-per-swarm kernel (test hook 2) run the same arithmetic:
+    same dead sets and timers over a run through spawn, chase and kills."""
+    R = 32
+    L = 100.0 if bc == 0 else 60.0
+    sp, _, _ = make_params('natPred', N, BC=bc, size=L, Npred=1, pred_kill=3, pred_move=1,
+                           pred_time=0.0, time=50.0, pred_speed0=20.0, kill_rate=50.0, N_confu=100)
+    rng = np.random.default_rng(N + bc)
+    sts = [random_state(N, sp, rng, spread=15.0) for _ in range(R)]
+    state = {k: np.stack([s[k] for s in sts]) for k in sts[0]}
+    c = 50.0 if bc == 0 else 0.0
+    px, py = c + rng.uniform(-4, 4, (R, 1)), c + rng.uniform(-4, 4, (R, 1))
+    pphi = rng.uniform(0, 2 * np.pi, (R, 1))
+    out = []
+    for hook in (0, 2):
+        g = _swarm(sp, N, 1, n_replicates=R, seed=17)
+        g.force_multikernel(hook)
+        g.set_state(**state)
+        g.set_predators(px, py, pphi, 1)
+        g.step(3, 150)
+        out.append((g.get_state(), g.get_predators(), g.counts()))
+        g.close()
+    a, b = out
+    assert int(a[2][1].sum()) > 0, 'nobody was killed'
+    same = np.array_equal(a[0]['alive'], b[0]['alive'])
+    frac = (a[0]['alive'] == b[0]['alive']).mean()
+    assert frac >= 0.98, frac
+    if same:
+        al = a[0]['alive'].astype(bool)
+        assert np.array_equal(a[0]['steps_till_burst'][al], b[0]['steps_till_burst'][al])
+        assert np.allclose(a[0]['x'][al], b[0]['x'][al], atol=5e-2)
