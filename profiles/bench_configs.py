@@ -20,7 +20,7 @@ def state(N, L, BC, seed):
     return dict(x=f32(x), y=f32(y), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=np.ones(N))
 
 
-def run(name, d, npred_expected, steps, cpu_steps, neighbour=PP.NEIGHBOUR_METRIC, voronoi_cpu=False):
+def run(name, d, npred_expected, steps, cpu_steps, neighbour=PP.NEIGHBOUR_METRIC, voronoi_cpu=False, R=1):
     import torch
     from sde_burst_coast_b200.swarm import Swarm
     from oracle import pyorc
@@ -28,8 +28,8 @@ def run(name, d, npred_expected, steps, cpu_steps, neighbour=PP.NEIGHBOUR_METRIC
     N = int(d['N'])
     st = state(N, sp.sizeL, sp.BC, 7)
     ts = torch.cuda.Stream()
-    g = Swarm(sp, N, npred, seed=1, stream=ts.cuda_stream)
-    g.set_state(**st)
+    g = Swarm(sp, N, npred, n_replicates=R, seed=1, stream=ts.cuda_stream)
+    g.set_state(**({k: np.tile(v, (R, 1)) for k, v in st.items()} if R > 1 else st))
     with torch.cuda.stream(ts):
         g.step(0, 50)
         torch.cuda.synchronize()
@@ -49,9 +49,9 @@ def run(name, d, npred_expected, steps, cpu_steps, neighbour=PP.NEIGHBOUR_METRIC
     w.step(0, 2)
     t = w.timed_steps(2, cpu_steps)
     w.close()
-    out = {'config': name, 'n_agents': N, 'n_pred': npred, 'box': sp.sizeL, 'BC': sp.BC,
+    out = {'config': name, 'n_agents': N, 'replicates': R, 'n_pred': npred, 'box': sp.sizeL, 'BC': sp.BC,
            'neighbour_rule': 'voronoi' if neighbour else 'metric', 'gpu_steps': steps,
-           'gpu_agent_steps_per_s': N * steps / (ms * 1e-3), 'gpu_us_per_step': 1e3 * ms / steps,
+           'gpu_agent_steps_per_s': N * R * steps / (ms * 1e-3), 'gpu_us_per_step': 1e3 * ms / steps,
            'gpu_pairs_or_candidates_per_s': (s1['pairs'] - s0['pairs']) / (ms * 1e-3),
            'gpu_launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'block_launches', 'other_launches')) / steps,
            'alive_at_end': alive,
@@ -67,6 +67,11 @@ def main():
         d = base_dict('burst_coast', N)
         run('C1 tank N=%d (metric)' % N, d, 0, 40000, 40000)
         run('C1 tank N=%d (voronoi)' % N, d, 0, 40000, 40000, neighbour=PP.NEIGHBOUR_VORONOI)
+    # the reference's default run (RunSingle.py: natPred, N = 30, L = 100, chasing predator, kill rule 3): one swarm
+    # and an ensemble of 16,384 replicates in one launch
+    d = base_dict('natPred', 30, BC=0, size=100.0, Npred=1, pred_move=1, pred_kill=3, pred_time=0.02, time=12.0)
+    run('natPred default N=30', d, 1, 40000, 20000)
+    run('natPred default N=30 x 16384 replicates', d, 1, 2000, 20000, R=16384)
     # C3: natPred N = 1024, sparse (L = 584) and dense (L = 100)
     for L in (584.0, 100.0):
         d = base_dict('natPred', 1024, BC=0, size=L, Npred=1, pred_move=1, pred_kill=3, pred_time=0.02, time=12.0, pred_speed0=20)

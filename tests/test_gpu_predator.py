@@ -313,3 +313,42 @@ def test_warp_and_block_predator_kernels_agree(N, bc):
         al = a[0]['alive'].astype(bool)
         assert np.array_equal(a[0]['steps_till_burst'][al], b[0]['steps_till_burst'][al])
         assert np.allclose(a[0]['x'][al], b[0]['x'][al], atol=5e-2)
+
+
+@pytest.mark.parametrize('N,R,hook', [(30, 8, 0), (30, 8, 2), (200, 3, 0), (520, 4, 0), (1100, 2, 0)])
+def test_predator_run_independent_of_launch_splits_and_sharding(N, R, hook):
+    """natPred through spawn, chase and kills on the warp (N=30), block (hook 2, N=200) and cluster (N>256)
+    kernels: (a) one launch == many short launches, bit for bit - the cluster kernel finishes the predator phase
+    of a launch's last step before it returns; (b) replicate r of an ensemble == a one-replicate handle
+    created with replicate_offset = r."""
+    sp, _, _ = make_params('natPred', N, BC=0, size=100.0, Npred=1, pred_kill=3, pred_move=1, pred_time=0.01,
+                           time=50.0, pred_speed0=40.0, kill_rate=200.0, N_confu=5000)
+    rng = np.random.default_rng(N)
+    sts = [random_state(N, sp, rng, spread=30.0) for _ in range(R)]
+    state = {k: np.stack([s[k] for s in sts]) for k in sts[0]}
+
+    def run(chunks, r0=0, r1=R):
+        g = _swarm(sp, N, 1, n_replicates=r1 - r0, seed=23, replicate_offset=r0)
+        g.force_multikernel(hook)
+        g.set_state(**{k: v[r0:r1] for k, v in state.items()})
+        s = 0
+        for c in chunks:
+            g.step(s, c)
+            s += c
+        out = (g.get_state(), g.get_predators(), g.counts())
+        g.close()
+        return out
+
+    total = 600
+    one = run([total])
+    many = run([7, 1, 92] + [50] * 10)
+    assert int(one[2][1].sum()) > 0, 'nobody was killed'
+    for k in one[0]:
+        assert np.array_equal(one[0][k], many[0][k], equal_nan=True), k
+    assert np.array_equal(one[1], many[1])
+    assert np.array_equal(one[2][1], many[2][1])
+    r = R - 1
+    single = run([total], r, r + 1)
+    for k in one[0]:
+        assert np.array_equal(np.atleast_2d(one[0][k])[r], np.atleast_2d(single[0][k])[0], equal_nan=True), k
+    assert np.array_equal(one[1][r], single[1][0])
