@@ -175,12 +175,15 @@ int sbc_get_stats(sbc_handle *h, uint64_t out[8]);
  * has no counterpart; Step()'s semantics (swarmdyn.cpp:143-204) are kept: interactions see positions at
  * the start of the step, every agent is updated once, decisions depend on (seed, GLOBAL id, step).
  * A handle's n_agents is its slot capacity: slots [0, own_capacity) hold owned agents or free slots,
- * the rest hold ghosts (copies of the neighbours' agents within att_range of a slab edge).
+ * the rest hold ghosts (copies of the neighbours' agents within att_range + skin of a slab edge).
  * Buffers are DEVICE pointers of sbc_domain_buffer_bytes(max_migrants, max_halo) bytes:
  * [header | migrant records | halo records], 64-byte records, fixed size - no host round trip sizes a
  * message. ONE exchange per step: after sbc_set_state and after every sbc_step(h, s, 1) the host does
  * sbc_domain_pack -> exchange with the two ring neighbours -> sbc_domain_unpack
- * (sde_burst_coast_b200/domain.py; transport = NCCL send/recv over NVLink through torch.distributed). */
+ * (sde_burst_coast_b200/domain.py; transport = NCCL send/recv over NVLink through torch.distributed).
+ * The exchange is FULL (migration, new ghost sets, new cell order in the next step) every period + 1
+ * steps and a position REFRESH of the ghosts in place otherwise - the library picks the kind, the same on
+ * every rank; see sbc_domain_rebuild_period. */
 int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid /* [n_agents] */);
 int sbc_get_global_ids(sbc_handle *h, uint32_t *gid /* [n_agents]; 0xFFFFFFFF for empty ghost slots */);
 int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int max_migrants, int max_halo);
@@ -192,6 +195,11 @@ int sbc_domain_pack(sbc_handle *h, void *send_left_dev, void *send_right_dev);
 int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
                       const void *sent_right_dev);
 int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t *overflow_events);
+/* period < 0: returns how many refresh exchanges this rank's own agents allow between two full ones (the
+ * Verlet-skin bound of the cell list, from the largest speed in its state). period >= 0: sets the number
+ * all ranks agreed on (the minimum of the above; 0 = every exchange is full, the default) and returns the
+ * value in effect. Call after sbc_set_state, before the first sbc_domain_pack. */
+int sbc_domain_rebuild_period(sbc_handle *h, int period);
 
 /* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on
  * the handle's stream; returns mean milliseconds per launch in *ms. */

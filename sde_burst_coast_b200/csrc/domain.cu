@@ -17,6 +17,13 @@
 //   unpack : incoming migrants take free slots (a device-resident stack, lowest slot first), incoming
 //            halo records become ghosts, and so do the agents this rank just sent away - they sit just
 //            across the edge, exactly where the neighbour's halo band would report them.
+// REFRESH exchanges. The cell order of a handle serves several steps (Verlet skin, celllist.cu), and so
+// does the slot layout: between two cell builds no agent changes rank and no ghost changes slot. The
+// band mirrored on the neighbour is att_range + skin wide, the full exchange records which slots it sent
+// to each side (plus the migrants it received from that side - the sender keeps those as ghosts), and
+// the exchanges in between only carry the current {x, y, vx, vy} of exactly those slots, in the same
+// order, into the same ghost slots. An agent that crosses an edge meanwhile stays with its old owner
+// (at most skin/2 outside the slab) until the next full exchange.
 // Packing order is by slot index (block counts -> scan -> ordered write) and arrival order is fixed
 // (left buffer, right buffer), so results do not depend on thread scheduling. The transport itself
 // (NCCL send/recv over NVLink, or a loop-back copy in tests) belongs to the host side
@@ -146,7 +153,7 @@ dom_scan_kernel(int nblk, const int *__restrict__ block_counts, int *__restrict_
 __global__ void __launch_bounds__(CLS_THREADS)
 dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float halo, const int *__restrict__ block_off,
                 const int *__restrict__ ctl, int *__restrict__ free_stack, DomRecord *__restrict__ send_l,
-                DomRecord *__restrict__ send_r, int max_mig, int max_halo) {
+                DomRecord *__restrict__ send_r, int max_mig, int max_halo, int *__restrict__ halo_list) {
     __shared__ int run[4];       // running offsets of this block, advanced chunk by chunk
     __shared__ int wcnt[CLS_THREADS / 32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -190,8 +197,15 @@ dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float 
                     free_stack[free_base + (left ? p : n_leave_l + p)] = g;
                 }
             } else {
-                if ((m >> CAT_HALO_L) & 1u) { const int p = pos[CAT_HALO_L]; if (p < max_halo) send_l[1 + max_mig + p] = r; }
-                if ((m >> CAT_HALO_R) & 1u) { const int p = pos[CAT_HALO_R]; if (p < max_halo) send_r[1 + max_mig + p] = r; }
+                const int list_cap = max_halo + max_mig;
+                if ((m >> CAT_HALO_L) & 1u) {
+                    const int p = pos[CAT_HALO_L];
+                    if (p < max_halo) { send_l[1 + max_mig + p] = r; halo_list[p] = g; }
+                }
+                if ((m >> CAT_HALO_R) & 1u) {
+                    const int p = pos[CAT_HALO_R];
+                    if (p < max_halo) { send_r[1 + max_mig + p] = r; halo_list[list_cap + p] = g; }
+                }
             }
         }
         __syncthreads();
@@ -207,21 +221,28 @@ dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float 
 // incoming migrants -> free owned slots; ghosts = incoming halo (left, right) + my own outgoing migrants
 __global__ void __launch_bounds__(256)
 dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a, const DomRecord *__restrict__ recv_b,
-                  const DomRecord *__restrict__ sent_l, const DomRecord *__restrict__ sent_r, int max_mig,
-                  int *__restrict__ ctl, const int *__restrict__ free_stack) {
+                  const DomRecord *__restrict__ sent_l, const DomRecord *__restrict__ sent_r, int max_mig, int max_halo,
+                  int *__restrict__ ctl, const int *__restrict__ free_stack, int *__restrict__ halo_list) {
     const int ma = recv_a ? (int)recv_a[0].gid : 0, mb = recv_b ? (int)recv_b[0].gid : 0;
     const int ha = recv_a ? (int)recv_a[0].pad[0] : 0, hb = recv_b ? (int)recv_b[0].pad[0] : 0;
     const int sl = sent_l ? (int)sent_l[0].gid : 0, sr = sent_r ? (int)sent_r[0].gid : 0;
     const int free_top = ctl[0];
     const int ghost_cap = S.N - own_cap;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int own_l = min(ctl[4], max_halo), own_r = min(ctl[5], max_halo);   // my own halo lists
     if (t == 0) {
         if (ma + mb > free_top || ha + hb + sl + sr > ghost_cap) ctl[6] += 1;
+        if ((recv_a && recv_a[0].pad[1] != 0u) || (recv_b && recv_b[0].pad[1] != 0u)) ctl[6] += 1;  // not a full record set
         ctl[7] = ma + mb;  // consumed by dom_commit_kernel
+        ctl[10] = ha; ctl[11] = hb; ctl[12] = sl; ctl[13] = sr;
+        ctl[14] = own_l + ma;   // the migrants from the left sit in my left band: the left neighbour mirrors them
+        ctl[15] = own_r + mb;
     }
     if (t < ma + mb && t < free_top) {  // migrants
         const DomRecord r = (t < ma) ? recv_a[1 + t] : recv_b[1 + (t - ma)];
         const int g = free_stack[free_top - 1 - t];
+        if (t < ma) halo_list[own_l + t] = g;
+        else halo_list[(max_halo + max_mig) + own_r + (t - ma)] = g;
         S.pv[g] = r.pv;
         S.pv_dead[g] = r.pv;
         S.hv[g] = r.hv;
@@ -246,6 +267,42 @@ dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a,
     }
 }
 __global__ void dom_commit_kernel(int *ctl) { ctl[0] = max(ctl[0] - ctl[7], 0); }
+
+// refresh exchange: current {x, y, vx, vy} of the slots listed by the last full exchange, same order
+__global__ void __launch_bounds__(256)
+dom_refresh_pack_kernel(DevState S, const int *__restrict__ ctl, const int *__restrict__ halo_list, int list_cap,
+                        DomRecord *__restrict__ send_l, DomRecord *__restrict__ send_r) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
+    if (t == 0) {
+        DomRecord h = {};
+        h.pad[1] = 1u;   // marks a refresh buffer
+        h.pad[0] = (uint32_t)nl; send_l[0] = h;
+        h.pad[0] = (uint32_t)nr; send_r[0] = h;
+    }
+    if (t < nl) send_l[1 + t].pv = S.pv[halo_list[t]];
+    if (t < nr) send_r[1 + t].pv = S.pv[halo_list[list_cap + t]];
+}
+// ghosts keep the slots the last full unpack gave them: [halo from a][halo from b][sent left][sent right];
+// the agents I sent left now live on the left neighbour, which lists them behind its own right band
+__global__ void __launch_bounds__(256)
+dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const DomRecord *__restrict__ recv_a,
+                          const DomRecord *__restrict__ recv_b) {
+    const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        const bool ok_a = recv_a ? (recv_a[0].pad[1] == 1u && (int)recv_a[0].pad[0] == ha + sl) : (ha + sl == 0);
+        const bool ok_b = recv_b ? (recv_b[0].pad[1] == 1u && (int)recv_b[0].pad[0] == hb + sr) : (hb + sr == 0);
+        if (!ok_a || !ok_b) ctl[6] += 1;   // the ranks disagree about the kind or the content of this exchange
+    }
+    int k = t;
+    const DomRecord *src = nullptr;
+    if (k < ha) src = recv_a + 1 + k;
+    else if ((k -= ha) < hb) src = recv_b + 1 + k;
+    else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
+    else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
+    if (src && t < S.N - own_cap) S.pv[own_cap + t] = src->pv;
+}
 
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
 // slot first. One block walks the slots from the top down, 1024 at a time, with an ordered compaction.
@@ -297,17 +354,19 @@ __global__ void count_owned_kernel(DevState S, int own_cap, int *out) {
 
 size_t sbc_domain_record_bytes(void) { return sizeof(DomRecord); }
 
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap) {
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo) {
     cudaError_t e;
     D.nblk = (own_cap + CLS_PER_BLOCK - 1) / CLS_PER_BLOCK;
+    if ((e = cudaMalloc((void **)&D.halo_list, (size_t)2 * (max_mig + max_halo) * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.block_counts, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.block_off, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.free_stack, (size_t)own_cap * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.ctl, 16 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMemset(D.halo_list, 0, (size_t)2 * (max_mig + max_halo) * sizeof(int))) != cudaSuccess) return e;
     return cudaMemset(D.ctl, 0, 16 * sizeof(int));
 }
 void sbc_domain_scratch_free(DomainScratch &D) {
-    cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl);
+    cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl); cudaFree(D.halo_list);
     D = DomainScratch();
 }
 
@@ -317,13 +376,13 @@ void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t s
 
 void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
                             cudaStream_t st) {
-    const float halo = P.att * 1.0001f;
+    const float halo = D.halo;
     dom_count_kernel<<<D.nblk, CLS_THREADS, 0, st>>>(S, D.own_cap, D.x_lo, D.x_hi, P.L, halo, D.block_counts);
     dom_scan_kernel<<<1, 1024, 0, st>>>(D.nblk, D.block_counts, D.block_off, D.ctl, static_cast<DomRecord *>(send_l),
                                         static_cast<DomRecord *>(send_r), D.max_mig, D.max_halo);
     dom_pack_kernel<<<D.nblk, CLS_THREADS, 0, st>>>(S, D.own_cap, D.x_lo, D.x_hi, P.L, halo, D.block_off, D.ctl,
                                                     D.free_stack, static_cast<DomRecord *>(send_l),
-                                                    static_cast<DomRecord *>(send_r), D.max_mig, D.max_halo);
+                                                    static_cast<DomRecord *>(send_r), D.max_mig, D.max_halo, D.halo_list);
 }
 
 void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
@@ -333,8 +392,22 @@ void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *r
     dom_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(S, D.own_cap, static_cast<const DomRecord *>(recv_a),
                                                       static_cast<const DomRecord *>(recv_b),
                                                       static_cast<const DomRecord *>(sent_l),
-                                                      static_cast<const DomRecord *>(sent_r), D.max_mig, D.ctl, D.free_stack);
+                                                      static_cast<const DomRecord *>(sent_r), D.max_mig, D.max_halo, D.ctl,
+                                                      D.free_stack, D.halo_list);
     dom_commit_kernel<<<1, 1, 0, st>>>(D.ctl);
+}
+
+void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *send_l, void *send_r, cudaStream_t st) {
+    const int cap = D.max_halo + D.max_mig;
+    dom_refresh_pack_kernel<<<(cap + 255) / 256, 256, 0, st>>>(S, D.ctl, D.halo_list, cap, static_cast<DomRecord *>(send_l),
+                                                             static_cast<DomRecord *>(send_r));
+}
+void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
+                                      cudaStream_t st) {
+    const int ghost_cap = S.N - D.own_cap;
+    if (ghost_cap <= 0) return;
+    dom_refresh_unpack_kernel<<<(ghost_cap + 255) / 256, 256, 0, st>>>(S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a),
+                                                                      static_cast<const DomRecord *>(recv_b));
 }
 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st) {

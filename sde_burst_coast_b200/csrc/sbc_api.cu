@@ -38,6 +38,9 @@ struct sbc_handle {
     bool cells_ready, use_cells;
     bool cells_valid;        // the cell order on the device belongs to the current agents
     int cells_age, cells_max_age;  // steps since the build / steps one build may serve (Verlet skin)
+    int cells_local_max_age;       // what this handle's own agents allow (domain mode: the ranks agree on the minimum)
+    int dom_period;                // domain mode: agreed number of refresh exchanges between two full ones
+    bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
     double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
     // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
@@ -215,6 +218,9 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->cells_valid = false;
     h->cells_age = 0;
     h->cells_max_age = 1;
+    h->cells_local_max_age = 0;
+    h->dom_period = 0;
+    h->dom_last_full = true;
     h->v0_max = 1.0;
     for (int k = 0; k < 4; k++) h->step_graph_ok[k] = false;
     h->step_dev = nullptr;
@@ -346,7 +352,9 @@ static void set_cells_max_age(sbc_handle *h) {
     const double vmax = std::fmax(h->v0_max, std::fmax(h->hp.soc_strength, h->hp.env_strength) / h->hp.beta);
     const double per_step = (h->hp.BC == 0 ? 1.0 : 3.0) * vmax * h->hp.dt * 1.01;
     const double k = (h->cells.skin > 0.f && per_step > 0) ? std::floor(0.5 * h->cells.skin / per_step) : 0.0;
-    h->cells_max_age = (int)std::fmin(std::fmax(k, 0.0), 64.0);
+    h->cells_local_max_age = (int)std::fmin(std::fmax(k, 0.0), 64.0);
+    // a decomposed swarm rebuilds on every rank in the same step: the agreed period, never more than is safe here
+    h->cells_max_age = h->dom.enabled ? std::min(h->cells_local_max_age, h->dom_period) : h->cells_local_max_age;
 }
 
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
@@ -375,7 +383,7 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
         if (h->use_cells) {
             if (!h->cells_ready) {
                 // skin: a fifth of att_range when the box allows; one build then serves several steps
-                h->cells.skin = h->dom.enabled ? 0.f : sbc_cells_skin(h->P, 0.2f * h->P.att);
+                h->cells.skin = sbc_cells_skin(h->P, 0.2f * h->P.att);
                 cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
                 if (e != cudaSuccess) {
                     sbc_cell_scratch_free(h->cells);
@@ -445,7 +453,7 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
     if (vproj)
         for (size_t g = 0; g < total; g++)
             if (vproj[g] > h->v0_max) h->v0_max = vproj[g];
-    if (h->cells_ready) set_cells_max_age(h);
+    if (h->cells_ready || h->dom.enabled) set_cells_max_age(h);
     if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
     h->host_stats[7]++;
     // the caller's buffers may be reused as soon as we return
@@ -613,8 +621,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             // device memory and is advanced by the graph's last node.
             // cell order: rebuilt when stale (Verlet skin used up), after a state change, and always in
             // decomposed mode (ghosts change every step)
-            const bool rebuild = !h->use_cells || !h->cells_ready || !h->cells_valid || h->dom.enabled ||
-                                 h->cells_age > h->cells_max_age;
+            const bool rebuild = !h->use_cells || !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
             const int gk = (pred_phase ? 1 : 0) + (rebuild ? 2 : 0);
             const bool graphable = h->use_graphs && !injected && !S.flags && (!h->use_cells || h->cells_ready) &&
                                    h->stream != nullptr && h->stream != cudaStreamLegacy &&
@@ -870,15 +877,21 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     if (h->S.Npred != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators are not decomposed yet");
     if (own_capacity < 1 || own_capacity > h->S.N || max_migrants < 1 || max_halo < 1)
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad capacities");
-    const double w = h->hp.sizeL / world, halo = h->hp.att_range * 1.0001;
+    const float skin = sbc_cells_skin(h->P, 0.2f * h->P.att);
+    const double w = h->hp.sizeL / world, halo = (h->hp.att_range + (double)skin) * 1.0001;
     if (world > 1 && w < (world == 2 ? 2.1 * halo : 1.05 * halo))
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: slabs narrower than the halo");
     if (!h->use_cells) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: needs the cell-list path");
     SBC_CUDA(cudaSetDevice(h->device));
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
-    cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity);
+    cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity, max_migrants, max_halo);
     if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
     h->dom.enabled = true;
+    h->dom.halo = (float)halo;
+    h->dom_period = 0;
+    h->dom_last_full = true;
+    h->cells.skin = skin;
+    set_cells_max_age(h);
     h->dom.own_cap = own_capacity;
     h->dom.max_mig = max_migrants;
     h->dom.max_halo = max_halo;
@@ -901,17 +914,40 @@ size_t sbc_domain_buffer_bytes(int max_migrants, int max_halo) {
 int sbc_domain_pack(sbc_handle *h, void *send_left_dev, void *send_right_dev) {
     if (!h || !h->dom.enabled || !send_left_dev || !send_right_dev) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_domain_pack(h->P, h->S, h->dom, send_left_dev, send_right_dev, h->stream);
-    h->host_stats[7] += 3;
+    // the kind of this exchange follows the cell list: full (migration + new ghost sets) when the next step
+    // rebuilds the cell order, otherwise a position refresh of the ghosts already in place
+    h->dom_last_full = !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
+    if (h->dom_last_full) {
+        sbc_launch_domain_pack(h->P, h->S, h->dom, send_left_dev, send_right_dev, h->stream);
+        h->host_stats[7] += 3;
+    } else {
+        sbc_launch_domain_refresh_pack(h->S, h->dom, send_left_dev, send_right_dev, h->stream);
+        h->host_stats[7] += 1;
+    }
     return SBC_OK;
+}
+int sbc_domain_rebuild_period(sbc_handle *h, int period) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    if (period >= 0) {
+        h->dom_period = period;
+        set_cells_max_age(h);
+        h->cells_valid = false;   // the next exchange is a full one on every rank
+        return h->cells_max_age;
+    }
+    return h->cells_local_max_age;
 }
 int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
                       const void *sent_right_dev) {
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
-    h->cells_valid = false;
-    h->host_stats[7] += 2;
+    if (h->dom_last_full) {
+        sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
+        h->cells_valid = false;   // slots changed hands: the next step rebuilds the cell order
+        h->host_stats[7] += 2;
+    } else {
+        sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, h->stream);
+        h->host_stats[7] += 1;
+    }
     return SBC_OK;
 }
 int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t *overflow_events) {

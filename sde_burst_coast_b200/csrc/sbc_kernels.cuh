@@ -97,6 +97,10 @@ struct DomainScratch {
     int *free_stack = nullptr;                          // free owned slots, popped from the top
     int *ctl = nullptr;  // [0] free_top [1] free_base [2..5] totals (leave L/R, halo L/R) [6] overflow events
                          // [7] migrants taken by the last unpack [8] owned [9] ghosts
+                         // [10..13] ghost segment sizes of the last full unpack (halo from a, from b, sent l, sent r)
+                         // [14] [15] length of the refresh list towards the left / right neighbour
+    int *halo_list = nullptr;  // [2][max_halo + max_mig] slots whose positions a refresh exchange sends left / right
+    float halo = 0.f;          // width of the edge band that is mirrored on the neighbour (att_range + skin)
     int nblk = 0;
     int own_cap = 0;         // slots [0, own_cap) are owned / free, [own_cap, N) ghosts
     int max_mig = 0, max_halo = 0;  // record capacities of one buffer: [header | max_mig | max_halo]
@@ -104,13 +108,16 @@ struct DomainScratch {
     bool enabled = false;
 };
 size_t sbc_domain_record_bytes(void);
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap);
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo);
 void sbc_domain_scratch_free(DomainScratch &D);
 void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t st);
 void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
                             cudaStream_t st);
 void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
                               const void *sent_l, const void *sent_r, cudaStream_t st);
+void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *send_l, void *send_r, cudaStream_t st);
+void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
+                                      cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------

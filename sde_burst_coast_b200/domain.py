@@ -66,6 +66,16 @@ class DistTransport:
         for req in d.batch_isend_irecv(ops):
             req.wait()
 
+    def min_int(self, v):
+        """Minimum of one integer over the ranks (the rebuild period all slabs can afford)."""
+        if self.world == 1:
+            return int(v)
+        import torch
+        dev = 'cuda' if self.dist.get_backend(self.group) == 'nccl' else 'cpu'
+        t = torch.tensor([int(v)], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(t.item())
+
 
 class LoopbackTransport:
     """All slabs live in this process: collect every rank's send buffers, then deliver."""
@@ -95,7 +105,7 @@ class SlabSwarm:
         self.torch = torch
         self.rank, self.world, self.n_global = rank, world, int(n_global)
         mean_own = n_global / world
-        halo_frac = min(1.0, sp.att_range * 1.0001 / (sp.sizeL / world))
+        halo_frac = min(1.0, sp.att_range * 1.2001 / (sp.sizeL / world))   # band = att_range + skin (<= att_range / 5)
         self.own_cap = int(own_capacity or (mean_own * 1.15 + 4096))   # slack for density fluctuations; every slot costs sort time
         self.max_halo = int(max_records or (mean_own * halo_frac * 2 + 1024))      # records per edge band
         self.max_mig = int(max(256, self.max_halo // 8))                            # migrants per edge per step
@@ -132,6 +142,21 @@ class SlabSwarm:
         u32p = ctypes.POINTER(ctypes.c_uint32)
         self.swarm._check(self.swarm.lib.sbc_set_global_ids(self.swarm.h, gid.ctypes.data_as(u32p)))
         self.primed = False
+
+    def local_rebuild_period(self):
+        """Refresh exchanges this rank's agents allow between two full exchanges (sbc_domain_rebuild_period)."""
+        v = self.swarm.lib.sbc_domain_rebuild_period(self.swarm.h, -1)
+        if v < 0:
+            self.swarm._check(v)
+        return int(v)
+
+    def set_rebuild_period(self, period):
+        """The number every rank agreed on (the minimum over the ranks)."""
+        v = self.swarm.lib.sbc_domain_rebuild_period(self.swarm.h, int(period))
+        if v < 0:
+            self.swarm._check(v)
+        self.primed = False
+        return int(v)
 
     def owned_state(self):
         """(gids, state dict) of the agents this rank owns now."""
@@ -174,8 +199,10 @@ def step_distributed(slab, transport, s_first, n_steps):
         slab.pack()
         transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
         slab.unpack()
-    if slab.world > 1 and not slab.primed:
-        exchange()
+    if not slab.primed:
+        slab.set_rebuild_period(transport.min_int(slab.local_rebuild_period()))
+        if slab.world > 1:
+            exchange()
         slab.primed = True
     for s in range(s_first, s_first + n_steps):
         slab.step_local(s)
@@ -196,8 +223,12 @@ def step_loopback(slabs, s_first, n_steps):
         for sl in slabs:
             tr.deliver(sl.rank, sl.recv_l, sl.recv_r)
             sl.unpack()
-    if world > 1 and not all(sl.primed for sl in slabs):
-        exchange()
+    if not all(sl.primed for sl in slabs):
+        period = min(sl.local_rebuild_period() for sl in slabs)
+        for sl in slabs:
+            sl.set_rebuild_period(period)
+        if world > 1:
+            exchange()
         for sl in slabs:
             sl.primed = True
     for s in range(s_first, s_first + n_steps):

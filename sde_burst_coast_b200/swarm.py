@@ -58,6 +58,7 @@ ABI = [
     ('sbc_domain_pack', ctypes.c_int, [_vp, _vp, _vp]),
     ('sbc_domain_unpack', ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ('sbc_domain_counts', ctypes.c_int, [_vp, _i32p, _i32p, _i32p]),
+    ('sbc_domain_rebuild_period', ctypes.c_int, [_vp, ctypes.c_int]),
 ]
 
 _lib = None

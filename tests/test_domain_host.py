@@ -43,6 +43,7 @@ for it in range(3):
     left, right = neighbours(rank, world)
     assert int(recv_l[0]) == 10 * left + 2 + 100 * it and bool((recv_l == recv_l[0]).all()), (rank, 'from left', int(recv_l[0]))
     assert int(recv_r[0]) == 10 * right + 1 + 100 * it and bool((recv_r == recv_r[0]).all()), (rank, 'from right', int(recv_r[0]))
+assert tr.min_int(7 + 3 * ((rank + 1) %% world)) == 7   # the rebuild period every rank can afford
 dist.barrier()
 dist.destroy_process_group()
 sys.stdout.write('rank-' + str(rank) + '-ok\n'); sys.stdout.flush()
@@ -68,6 +69,7 @@ def test_world_one_is_a_self_exchange():
     rl, rr = torch.zeros(8, dtype=a.dtype), torch.zeros(8, dtype=a.dtype)
     tr.exchange(a, b, rl, rr)
     assert rr.equal(a) and rl.equal(b)
+    assert tr.min_int(5) == 5
 
 
 def test_reference_arm_runs_on_rank_zero_only():

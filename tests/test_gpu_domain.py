@@ -93,8 +93,16 @@ def test_decomposed_run_matches_whole_swarm(world):
     assert np.array_equal(got['bin_step'], ws['bin_step'])
     close = (np.abs(((got['x'] - ws['x'] + L / 2) % L) - L / 2) < 1e-3) & (np.abs(((got['y'] - ws['y'] + L / 2) % L) - L / 2) < 1e-3)
     assert close.mean() > 0.995, close.mean()
-    from sde_burst_coast_b200.domain import owner_of
-    for sl in slabs:   # everybody is at home after migration
+    from sde_burst_coast_b200.domain import slab_bounds
+    period = slabs[0].local_rebuild_period()
+    assert period >= 1, 'this configuration should allow refresh exchanges'
+    builds = slabs[0].swarm.stats()['cell_builds']
+    assert builds <= K // 2, builds     # most exchanges were position refreshes of the ghosts in place
+    skin = 0.2 * sp.att_range
+    for sl in slabs:   # everybody is at home, or on the way there (at most skin/2 outside until the next full exchange)
         gid, own = sl.owned_state()
-        assert np.all(owner_of(own['x'], L, world) == sl.rank)
+        lo, hi = slab_bounds(L, world)[sl.rank]
+        inside = (own['x'] >= lo) & (own['x'] < hi)
+        out = np.where(inside, 0.0, np.minimum((lo - own['x']) % L, (own['x'] - hi) % L))   # distance along the ring
+        assert np.all(out <= 0.5 * skin + 1e-3), out.max()
         sl.close()
