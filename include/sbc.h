@@ -201,6 +201,24 @@ int sbc_domain_counts(sbc_handle *h, int32_t *n_owned, int32_t *n_ghost, int32_t
  * value in effect. Call after sbc_set_state, before the first sbc_domain_pack. */
 int sbc_domain_rebuild_period(sbc_handle *h, int period);
 
+/* Exchange through PEER MEMORY instead of a message library: every rank owns an inbox in device memory
+ * (two buffers per side, by parity of the exchange count, plus arrival flags); a rank's push kernel stores
+ * the used part of its send buffers directly into its neighbours' inboxes over NVLink and then publishes
+ * the exchange count in their flags; the receiver's stream holds in a one-thread kernel until both flags
+ * show it. No host synchronisation and no collective call per step.
+ *   sbc_domain_inbox      : allocate the inbox (once); returns its device address, size and - if asked - the
+ *                           64-byte CUDA IPC handle another process opens with sbc_domain_open_peer
+ *   sbc_domain_attach_peers: the inboxes of the left / right ring neighbour, as device pointers valid here
+ *   sbc_domain_post       : pack + push to both neighbours;  sbc_domain_complete : wait + unpack
+ *   sbc_domain_step       : n_steps x { sbc_step(h, s, 1); post; complete }
+ * Every rank must make the same sequence of post / complete calls. */
+int sbc_domain_inbox(sbc_handle *h, void **base_dev, size_t *bytes, void *ipc_handle_64 /* or NULL */);
+int sbc_domain_open_peer(sbc_handle *h, const void *ipc_handle_64, void **mapped_dev);
+int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inbox_dev);
+int sbc_domain_post(sbc_handle *h);
+int sbc_domain_complete(sbc_handle *h);
+int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps);
+
 /* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on
  * the handle's stream; returns mean milliseconds per launch in *ms. */
 int sbc_bench_pair_pass(sbc_handle *h, int flags, int iters, float *ms);

@@ -21,13 +21,15 @@ def main():
     ap.add_argument('--rho', type=float, default=0.01)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--transport', choices=['peer', 'nccl'], default='peer',
+                    help='peer: libsbc kernels store into the neighbours\' inboxes over NVLink; nccl: torch.distributed send/recv')
     args = ap.parse_args()
     import faulthandler
     faulthandler.dump_traceback_later(280, exit=True)
     import torch, torch.distributed as dist
     from helpers import base_dict, f32
     from sde_burst_coast_b200 import params as PP
-    from sde_burst_coast_b200.domain import SlabSwarm, DistTransport, step_distributed
+    from sde_burst_coast_b200.domain import SlabSwarm, DistTransport, PeerTransport, step_distributed
     world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
     if world > 1:
@@ -43,7 +45,7 @@ def main():
     stream = tstream.cuda_stream
     slab = SlabSwarm(sp, N, rank, world, seed=20261019, device=local, stream=stream)
     slab.scatter_initial(st)
-    tr = DistTransport(rank, world)
+    tr = PeerTransport(slab) if args.transport == 'peer' else DistTransport(rank, world)
 
     def barrier():
         if world > 1:
@@ -75,7 +77,7 @@ def main():
         cand = sum(float(v[1]) for v in allv)
         print(json.dumps({
             'metric': 'agent_steps_per_sec', 'workload': 'C5 single swarm, cell list, x-slabs', 'n_agents': N, 'box': L,
-            'n_gpus': world, 'steps': args.steps, 'scaling': 'weak' if args.weak else 'strong',
+            'n_gpus': world, 'transport': args.transport if world > 1 else 'none', 'steps': args.steps, 'scaling': 'weak' if args.weak else 'strong',
             'value': N * args.steps / (ms_max * 1e-3), 'us_per_step': 1e3 * ms_max / args.steps,
             'pair_candidates_per_sec': cand / (ms_max * 1e-3), 'wall_s': wall,
             'owned_per_rank': [int(v[2]) for v in allv], 'ghosts_per_rank': [int(v[3]) for v in allv],

@@ -93,8 +93,96 @@ __global__ void cell_bounds_kernel(const uint32_t *__restrict__ key, const int *
     if (r == n - 1 || key[r + 1] != k) cell_end[k] = r + 1;
 }
 
-constexpr int CELLS_THREADS = 128;  // one block per active row
+constexpr int CELLS_THREADS = 128;
 
+// One active row against the agents of its 3 x 3 cell neighbourhood, swept by a GROUP of TPR threads
+// (a warp when the neighbourhood holds a few dozen agents, a whole block when it holds thousands).
+// The nine cell ranges are fetched at once by nine threads and laid end to end, so that the group walks ONE
+// candidate range: the dependent chain per row is key -> cell bounds -> sorted index -> position (four
+// memory round trips) instead of three per cell.
+template <bool PERIODIC, int TPR>
+__device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevState &S, const CellGeom &g,
+                                                const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, int i,
+                                                int t /* thread in group */, int *pref /* [10] shared, per group */,
+                                                int *first /* [9] shared, per group */, RowAcc &A, unsigned &n_amb,
+                                                unsigned long long &n_cand) {
+    const float4 pi = S.pv[i];
+    // the row's cell at build time (agents alive now were alive then: nobody is born between builds)
+    const int ck = (int)build_key[i];
+    const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
+    if (t < 9) {
+        int yy = cy + t / 3 - 1, xx = cx + t % 3 - 1;
+        bool ok = true;
+        if (PERIODIC) {
+            yy = (yy + g.ncy) % g.ncy;
+            xx = (xx + g.ncx) % g.ncx;
+        } else {
+            ok = yy >= 0 && yy < g.ncy && xx >= 0 && xx < g.ncx;
+        }
+        int r0 = 0, r1 = 0;
+        if (ok) {
+            const int c = yy * g.ncx + xx;
+            r0 = cell_start[c];
+            r1 = cell_end[c];
+        }
+        first[t] = r0;
+        pref[t + 1] = r1 - r0;
+    }
+    if (TPR == 32) __syncwarp(); else __syncthreads();
+    if (t == 0) {
+        int run = 0;
+        pref[0] = 0;
+        for (int c = 0; c < 9; c++) { run += pref[c + 1]; pref[c + 1] = run; }
+        n_cand += (unsigned long long)run;
+    }
+    if (TPR == 32) __syncwarp(); else __syncthreads();
+    const int total = pref[9];
+    row_acc_clear(A);
+    for (int q = t; q < total; q += TPR) {
+        int c = 0;
+#pragma unroll
+        for (int k = 1; k < 9; k++) c += (q >= pref[k]) ? 1 : 0;
+        const int j = sidx[first[c] + (q - pref[c])];
+        if (j == i) continue;
+        const float4 pj = S.pv[j];   // current position (NaN if the agent died since the build)
+        float dx = pj.x - pi.x, dy = pj.y - pi.y;
+        if (PERIODIC) {
+            dx = sbc_delta_pbc(pi.x, pj.x, P);
+            dy = sbc_delta_pbc(pi.y, pj.y, P);
+        }
+        const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+        bool amb;
+        int z = sbc_zone_fast(d2, P, amb);
+        if (amb) {
+            z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
+            n_amb++;
+        }
+        const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+        if (z == 0) {
+            A.rep_x = __fmaf_rn(-dx, rinv, A.rep_x);
+            A.rep_y = __fmaf_rn(-dy, rinv, A.rep_y);
+            A.c_rep++;
+        } else if (z == 1) {
+            A.alg_x += pj.z;
+            A.alg_y += pj.w;
+            A.c_alg++;
+        } else if (z == 2) {
+            A.att_x = __fmaf_rn(dx, rinv, A.att_x);
+            A.att_y = __fmaf_rn(dy, rinv, A.att_y);
+            A.c_att++;
+        }
+    }
+}
+__device__ __forceinline__ void cells_row_store(const DevState &S, int i, const RowAcc &A) {
+    float4 *acc = reinterpret_cast<float4 *>(S.acc + (size_t)i * 8);
+    acc[0] = make_float4(A.rep_x, A.rep_y, A.alg_x, A.alg_y);
+    S.acc[(size_t)i * 8 + 4] = A.att_x;
+    S.acc[(size_t)i * 8 + 5] = A.att_y;
+    *reinterpret_cast<int4 *>(S.cnt + (size_t)i * 4) = make_int4(A.c_rep, A.c_alg, A.c_att, 0);
+}
+
+// dense neighbourhoods: one block per active row
 template <bool PERIODIC>
 __global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
@@ -103,6 +191,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
                   const int *__restrict__ list, const int *__restrict__ count) {
     __shared__ float shf[CELLS_THREADS / 32][6];
     __shared__ int shi[CELLS_THREADS / 32][3];
+    __shared__ int pref[10], first[9];
     const int lane = threadIdx.x & 31;
     const int n_rows = *count;
     const CellGeom g = *geom;
@@ -110,66 +199,52 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
     unsigned long long n_cand = 0;
     for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
         const int i = list[k];  // single swarm on this path: slot index == global index
-        const float4 pi = S.pv[i];
-        // the row's cell at build time (agents alive now were alive then: nobody is born between builds)
-        const int ck = (int)build_key[i];
-        const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
         RowAcc A;
-        row_acc_clear(A);
-        for (int oy = -1; oy <= 1; oy++) {
-            int yy = cy + oy;
-            if (PERIODIC) yy = (yy + g.ncy) % g.ncy; else if (yy < 0 || yy >= g.ncy) continue;
-            for (int ox = -1; ox <= 1; ox++) {
-                int xx = cx + ox;
-                if (PERIODIC) xx = (xx + g.ncx) % g.ncx; else if (xx < 0 || xx >= g.ncx) continue;
-                const int c = yy * g.ncx + xx;
-                const int r0 = cell_start[c], r1 = cell_end[c];
-                n_cand += (threadIdx.x == 0) ? (unsigned long long)(r1 - r0) : 0ull;
-                for (int r = r0 + threadIdx.x; r < r1; r += CELLS_THREADS) {
-                    const int j = sidx[r];
-                    if (j == i) continue;
-                    const float4 pj = S.pv[j];   // current position (NaN if the agent died since the build)
-                    float dx = pj.x - pi.x, dy = pj.y - pi.y;
-                    if (PERIODIC) {
-                        dx = sbc_delta_pbc(pi.x, pj.x, P);
-                        dy = sbc_delta_pbc(pi.y, pj.y, P);
-                    }
-                    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-                    bool amb;
-                    int z = sbc_zone_fast(d2, P, amb);
-                    if (amb) {
-                        z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
-                        n_amb++;
-                    }
-                    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
-                    if (z == 0) {
-                        A.rep_x = __fmaf_rn(-dx, rinv, A.rep_x);
-                        A.rep_y = __fmaf_rn(-dy, rinv, A.rep_y);
-                        A.c_rep++;
-                    } else if (z == 1) {
-                        A.alg_x += pj.z;
-                        A.alg_y += pj.w;
-                        A.c_alg++;
-                    } else if (z == 2) {
-                        A.att_x = __fmaf_rn(dx, rinv, A.att_x);
-                        A.att_y = __fmaf_rn(dy, rinv, A.att_y);
-                        A.c_att++;
-                    }
-                }
-            }
-        }
+        cells_row_sweep<PERIODIC, CELLS_THREADS>(P, S, g, cell_start, cell_end, build_key, sidx, i, threadIdx.x, pref, first, A,
+                                                 n_amb, n_cand);
         sbc_block_reduce_row<CELLS_THREADS / 32>(A, shf, shi);
-        if (threadIdx.x == 0) {
-            float4 *acc = reinterpret_cast<float4 *>(S.acc + (size_t)i * 8);
-            acc[0] = make_float4(A.rep_x, A.rep_y, A.alg_x, A.alg_y);
-            S.acc[(size_t)i * 8 + 4] = A.att_x;
-            S.acc[(size_t)i * 8 + 5] = A.att_y;
-            *reinterpret_cast<int4 *>(S.cnt + (size_t)i * 4) = make_int4(A.c_rep, A.c_alg, A.c_att, 0);
-        }
+        if (threadIdx.x == 0) cells_row_store(S, i, A);
+        __syncthreads();   // pref / first are rewritten by the next row
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (threadIdx.x == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);  // candidates examined on this path
+}
+
+// sparse neighbourhoods (a few dozen candidates): one WARP per active row, reduction by shuffles only
+template <bool PERIODIC>
+__global__ void __launch_bounds__(CELLS_THREADS)
+pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
+                       const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                       const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
+                       const int *__restrict__ list, const int *__restrict__ count) {
+    constexpr int WPB = CELLS_THREADS / 32;
+    __shared__ int pref[WPB][10], first[WPB][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_rows = *count;
+    const CellGeom g = *geom;
+    unsigned n_amb = 0;
+    unsigned long long n_cand = 0;
+    for (int k = blockIdx.x * WPB + warp; k < n_rows; k += gridDim.x * WPB) {
+        const int i = list[k];
+        RowAcc A;
+        cells_row_sweep<PERIODIC, 32>(P, S, g, cell_start, cell_end, build_key, sidx, i, lane, pref[warp], first[warp], A, n_amb,
+                                      n_cand);
+        A.c_rep = __reduce_add_sync(0xffffffffu, A.c_rep);
+        A.c_alg = __reduce_add_sync(0xffffffffu, A.c_alg);
+        A.c_att = __reduce_add_sync(0xffffffffu, A.c_att);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o); A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
+            A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o); A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
+            A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o); A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
+        }
+        if (lane == 0) cells_row_store(S, i, A);
+        __syncwarp();
+    }
+    n_amb = __reduce_add_sync(0xffffffffu, n_amb);
+    if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
+    if (lane == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);
 }
 
 }  // namespace
@@ -247,10 +322,15 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
 void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st) {
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
     const int blocks = (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
-    if (P.BC == 0)
-        pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out,
-                                                        S.active_list, S.active_count);
-    else
-        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out,
-                                                         S.active_list, S.active_count);
+    // mean number of candidates a row meets in its nine cells decides between a warp and a block per row
+    const double per_row = 9.0 * (double)S.N / (double)(C.ncells > 0 ? C.ncells : 1);
+    const bool warp_rows = P.BC == 0 && per_row < 512.0;
+#define SBC_CELLS_ARGS P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, S.active_list, S.active_count
+    if (P.BC == 0) {
+        if (warp_rows) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        else pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+    } else {
+        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+    }
+#undef SBC_CELLS_ARGS
 }

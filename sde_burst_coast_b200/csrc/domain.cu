@@ -286,8 +286,10 @@ dom_refresh_pack_kernel(DevState S, const int *__restrict__ ctl, const int *__re
 // ghosts keep the slots the last full unpack gave them: [halo from a][halo from b][sent left][sent right];
 // the agents I sent left now live on the left neighbour, which lists them behind its own right band
 __global__ void __launch_bounds__(256)
-dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const DomRecord *__restrict__ recv_a,
-                          const DomRecord *__restrict__ recv_b) {
+dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
+                          const DomRecord *recv_b0, const DomRecord *recv_b1) {
+    const int par = ctl[16] & 1;   // buffers by parity of the exchange count (the same pointer twice without an inbox)
+    const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
     const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t == 0) {
@@ -302,6 +304,57 @@ dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const 
     else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
     else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
     if (src && t < S.N - own_cap) S.pv[own_cap + t] = src->pv;
+}
+
+// ---- exchange through peer memory (NVLink) ---------------------------------------------------------
+// Every rank owns an INBOX: per side (from left / from right) two buffers (parity of the exchange epoch)
+// and one arrival flag each. A rank pushes the used part of its send buffers straight into its
+// neighbours' inboxes (16-byte stores over NVLink), then a one-thread kernel publishes the epoch in the
+// neighbours' flags; the receiver's one-thread wait kernel holds its stream until both flags show the
+// epoch. Producers never wait, so the ring cannot deadlock; two parities suffice because a rank can
+// only push epoch e + 2 after it has consumed e + 1, which the neighbour sent after consuming e.
+// The exchange count lives in device memory (ctl[16]) so that a whole refresh exchange can be replayed from a
+// CUDA graph: push and flag act on count + 1, the flag kernel commits it, wait and unpack read it back.
+__global__ void __launch_bounds__(256)
+dom_push_kernel(const DomRecord *__restrict__ send_l, const DomRecord *__restrict__ send_r, DomRecord *dst_l0,
+                DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, const int *__restrict__ ctl, int max_mig,
+                int max_halo) {
+    const int par = (ctl[16] + 1) & 1;
+    DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
+    const int per_side = (1 + max_mig + max_halo) * 4;   // 16-byte quarters
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 2 * per_side; q += gridDim.x * blockDim.x) {
+        const int side = q >= per_side;
+        const int k = q - side * per_side, rec = k >> 2;
+        const DomRecord *src = side ? send_r : send_l;
+        const DomRecord h = src[0];
+        bool used;
+        if (h.pad[1] == 1u) used = rec < 1 + (int)h.pad[0];                       // refresh: [header | n records]
+        else used = rec < 1 + (int)h.gid || (rec >= 1 + max_mig && rec < 1 + max_mig + (int)h.pad[0]);
+        if (used) reinterpret_cast<uint4 *>(side ? dst_r : dst_l)[k] = reinterpret_cast<const uint4 *>(src)[k];
+    }
+}
+__global__ void dom_flag_kernel(volatile int *flag_l0, volatile int *flag_l1, volatile int *flag_r0, volatile int *flag_r1,
+                                int *ctl) {
+    const int epoch = ctl[16] + 1, par = epoch & 1;
+    __threadfence_system();
+    *(par ? flag_l1 : flag_l0) = epoch;
+    *(par ? flag_r1 : flag_r0) = epoch;
+    __threadfence_system();
+    ctl[16] = epoch;
+}
+__global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
+                                const volatile int *flag_b1, int *ctl) {
+    const int epoch = ctl[16], par = epoch & 1;
+    const volatile int *fa = par ? flag_a1 : flag_a0, *fb = par ? flag_b1 : flag_b0;
+    const long long t0 = clock64();
+    while (*fa < epoch || *fb < epoch) {
+        if (clock64() - t0 > 6000000000ll) {   // ~3 s: a neighbour is gone; report instead of hanging the GPU
+            ctl[6] += 1000;
+            break;
+        }
+        __nanosleep(200);
+    }
+    __threadfence_system();
 }
 
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
@@ -361,9 +414,9 @@ cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig,
     if ((e = cudaMalloc((void **)&D.block_counts, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.block_off, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.free_stack, (size_t)own_cap * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&D.ctl, 16 * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&D.ctl, 32 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMemset(D.halo_list, 0, (size_t)2 * (max_mig + max_halo) * sizeof(int))) != cudaSuccess) return e;
-    return cudaMemset(D.ctl, 0, 16 * sizeof(int));
+    return cudaMemset(D.ctl, 0, 32 * sizeof(int));
 }
 void sbc_domain_scratch_free(DomainScratch &D) {
     cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl); cudaFree(D.halo_list);
@@ -402,12 +455,24 @@ void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *s
     dom_refresh_pack_kernel<<<(cap + 255) / 256, 256, 0, st>>>(S, D.ctl, D.halo_list, cap, static_cast<DomRecord *>(send_l),
                                                              static_cast<DomRecord *>(send_r));
 }
-void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
-                                      cudaStream_t st) {
+void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a0, const void *recv_a1,
+                                      const void *recv_b0, const void *recv_b1, cudaStream_t st) {
     const int ghost_cap = S.N - D.own_cap;
     if (ghost_cap <= 0) return;
-    dom_refresh_unpack_kernel<<<(ghost_cap + 255) / 256, 256, 0, st>>>(S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a),
-                                                                      static_cast<const DomRecord *>(recv_b));
+    dom_refresh_unpack_kernel<<<(ghost_cap + 255) / 256, 256, 0, st>>>(
+        S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a0), static_cast<const DomRecord *>(recv_a1),
+        static_cast<const DomRecord *>(recv_b0), static_cast<const DomRecord *>(recv_b1));
+}
+void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
+                            int *const flag_l[2], int *const flag_r[2], cudaStream_t st) {
+    dom_push_kernel<<<64, 256, 0, st>>>(static_cast<const DomRecord *>(send_l), static_cast<const DomRecord *>(send_r),
+                                        static_cast<DomRecord *>(dst_l[0]), static_cast<DomRecord *>(dst_l[1]),
+                                        static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), D.ctl, D.max_mig,
+                                        D.max_halo);
+    dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], D.ctl);
+}
+void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
+    dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl);
 }
 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st) {

@@ -12,19 +12,51 @@
 namespace {
 
 // ---- burst-gated rows ------------------------------------------------------------------------
-__global__ void compact_active_kernel(DevState S, uint32_t burst_steps, int all_alive, int *list, int *count) {
+// four consecutive agents per thread (one 4-byte load of the alive flags, two 16-byte loads of the timers):
+// the pass is a plain stream over 9 bytes per agent. The order of the list does not matter - every row
+// writes only its own accumulators.
+__global__ void __launch_bounds__(256)
+compact_active_kernel(DevState S, uint32_t burst_steps, int all_alive, int *list, int *count) {
     const size_t total = (size_t)S.N * S.R;
-    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total;
-         g += (size_t)gridDim.x * blockDim.x) {
-        const bool active = S.alive[g] && (all_alive || S.timers[g].x == burst_steps);
-        if (!active) continue;
-        const unsigned m = __activemask();
-        const int lane = threadIdx.x & 31;
-        const int leader = __ffs(m) - 1;
+    const size_t quads = (total + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // whole warps iterate together, so the scan below may use the full mask
+    for (size_t qb = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31u); qb < quads; qb += stride) {
+        const size_t q = qb + lane, g0 = 4 * q;
+        unsigned act = 0;   // bit k: agent g0 + k starts a burst
+        if (q < quads) {
+            if (g0 + 3 < total) {
+                const uint32_t al = *reinterpret_cast<const uint32_t *>(S.alive + g0);
+                if (al && all_alive) {
+                    for (int k = 0; k < 4; k++) act |= ((al >> (8 * k)) & 0xffu) ? (1u << k) : 0u;
+                } else if (al) {
+                    const uint4 t01 = *reinterpret_cast<const uint4 *>(S.timers + g0);
+                    const uint4 t23 = *reinterpret_cast<const uint4 *>(S.timers + g0 + 2);
+                    act |= ((al & 0xffu) && t01.x == burst_steps) ? 1u : 0u;
+                    act |= ((al & 0xff00u) && t01.z == burst_steps) ? 2u : 0u;
+                    act |= ((al & 0xff0000u) && t23.x == burst_steps) ? 4u : 0u;
+                    act |= ((al & 0xff000000u) && t23.z == burst_steps) ? 8u : 0u;
+                }
+            } else {
+                for (int k = 0; k < 4 && g0 + k < total; k++)
+                    if (S.alive[g0 + k] && (all_alive || S.timers[g0 + k].x == burst_steps)) act |= 1u << k;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, act != 0) == 0) continue;
+        // warp-aggregated append: one atomic per warp iteration
+        const int n_mine = __popc(act);
+        int incl = n_mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
         int base = 0;
-        if (lane == leader) base = atomicAdd(count, __popc(m));
-        base = __shfl_sync(m, base, leader);
-        list[base + __popc(m & ((1u << lane) - 1))] = (int)g;
+        if (lane == 31) base = atomicAdd(count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - n_mine;
+        for (int k = 0; k < 4; k++)
+            if ((act >> k) & 1u) list[base++] = (int)(g0 + k);
     }
 }
 

@@ -4,6 +4,7 @@
 // of the hot path runs on the host; without a usable CUDA device every call fails loudly.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,15 @@ struct sbc_handle {
     bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
     double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
+    // exchange through peer memory: own inbox [flags 256 B | from-left p0 | from-left p1 | from-right p0 | from-right p1]
+    unsigned char *inbox;
+    size_t inbox_buf_bytes;
+    unsigned char *peer_l, *peer_r;        // the neighbours' inboxes (mapped through CUDA IPC, or plain pointers in-process)
+    std::vector<void *> ipc_opened;
+    unsigned char *send_own[2];            // this rank's send buffers (left, right)
+    int dom_epoch;
+    cudaGraphExec_t refresh_graph;         // one refresh exchange (pack, push, flag, wait, unpack)
+    bool refresh_graph_ok;
     // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
     cudaGraphExec_t step_graph[4];   // [2 * rebuild + pred_phase]
     bool step_graph_ok[4];
@@ -309,6 +319,9 @@ int sbc_destroy(sbc_handle *h) {
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
+    if (h->refresh_graph_ok) cudaGraphExecDestroy(h->refresh_graph);
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
     cudaFree(h->S.gid);
     for (int k = 0; k < 4; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
     cudaFree(h->step_dev);
@@ -348,6 +361,12 @@ static int ensure_dense(sbc_handle *h) {
 // How many steps one cell build may serve: nobody moves faster than max(initial speed, largest force /
 // friction) (vproj' = vproj (1 - beta dt) + f dt), a wall reflection can add twice the overshoot
 // (agents_dynamics.cpp:432-470); every agent must stay within skin/2 of where the build saw it.
+// skin of the cell list as a fraction of att_range (SBC_SKIN_FRAC overrides the default for tuning runs)
+static float cells_skin_for(const sbc_handle *h) {
+    float frac = 0.2f;
+    if (const char *e = std::getenv("SBC_SKIN_FRAC")) frac = (float)std::atof(e);
+    return sbc_cells_skin(h->P, frac * h->P.att);
+}
 static void set_cells_max_age(sbc_handle *h) {
     const double vmax = std::fmax(h->v0_max, std::fmax(h->hp.soc_strength, h->hp.env_strength) / h->hp.beta);
     const double per_step = (h->hp.BC == 0 ? 1.0 : 3.0) * vmax * h->hp.dt * 1.01;
@@ -383,7 +402,7 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
         if (h->use_cells) {
             if (!h->cells_ready) {
                 // skin: a fifth of att_range when the box allows; one build then serves several steps
-                h->cells.skin = sbc_cells_skin(h->P, 0.2f * h->P.att);
+                h->cells.skin = cells_skin_for(h);
                 cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
                 if (e != cudaSuccess) {
                     sbc_cell_scratch_free(h->cells);
@@ -877,7 +896,7 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     if (h->S.Npred != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators are not decomposed yet");
     if (own_capacity < 1 || own_capacity > h->S.N || max_migrants < 1 || max_halo < 1)
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad capacities");
-    const float skin = sbc_cells_skin(h->P, 0.2f * h->P.att);
+    const float skin = cells_skin_for(h);
     const double w = h->hp.sizeL / world, halo = (h->hp.att_range + (double)skin) * 1.0001;
     if (world > 1 && w < (world == 2 ? 2.1 * halo : 1.05 * halo))
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: slabs narrower than the halo");
@@ -936,6 +955,131 @@ int sbc_domain_rebuild_period(sbc_handle *h, int period) {
     }
     return h->cells_local_max_age;
 }
+// ---- exchange through peer memory -----------------------------------------------------------------
+static unsigned char *inbox_buf(unsigned char *base, size_t bytes, int side, int parity) {
+    return base + 256 + (size_t)(side * 2 + parity) * bytes;
+}
+static int *inbox_flag(unsigned char *base, int side, int parity) { return reinterpret_cast<int *>(base) + side * 2 + parity; }
+
+int sbc_domain_inbox(sbc_handle *h, void **base_dev, size_t *bytes, void *ipc_handle_64) {
+    if (!h || !h->dom.enabled) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    if (!h->inbox) {
+        h->inbox_buf_bytes = sbc_domain_buffer_bytes(h->dom.max_mig, h->dom.max_halo);
+        const size_t total = 256 + 4 * h->inbox_buf_bytes;
+        SBC_CUDA(cudaMalloc((void **)&h->inbox, total));
+        SBC_CUDA(cudaMemset(h->inbox, 0, total));
+        for (int k = 0; k < 2; k++) {
+            SBC_CUDA(cudaMalloc((void **)&h->send_own[k], h->inbox_buf_bytes));
+            SBC_CUDA(cudaMemset(h->send_own[k], 0, h->inbox_buf_bytes));
+        }
+        h->dom_epoch = 0;
+    }
+    if (base_dev) *base_dev = h->inbox;
+    if (bytes) *bytes = 256 + 4 * h->inbox_buf_bytes;
+    if (ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        SBC_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(ipc_handle_64), h->inbox));
+    }
+    return SBC_OK;
+}
+int sbc_domain_open_peer(sbc_handle *h, const void *ipc_handle_64, void **mapped_dev) {
+    if (!h || !ipc_handle_64 || !mapped_dev) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, ipc_handle_64, sizeof(hd));
+    void *p = nullptr;
+    SBC_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(p);
+    *mapped_dev = p;
+    return SBC_OK;
+}
+int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inbox_dev) {
+    if (!h || !h->dom.enabled || !h->inbox) return SBC_ERR_STATE;
+    if (!left_inbox_dev || !right_inbox_dev) return SBC_ERR_INVALID;
+    h->peer_l = static_cast<unsigned char *>(left_inbox_dev);
+    h->peer_r = static_cast<unsigned char *>(right_inbox_dev);
+    return SBC_OK;
+}
+static void domain_launch_push(sbc_handle *h) {
+    // what I send left arrives at the left neighbour as data "from its right" (side 1), and vice versa
+    void *dst_l[2], *dst_r[2];
+    int *flag_l[2], *flag_r[2];
+    for (int par = 0; par < 2; par++) {
+        dst_l[par] = inbox_buf(h->peer_l, h->inbox_buf_bytes, 1, par);
+        dst_r[par] = inbox_buf(h->peer_r, h->inbox_buf_bytes, 0, par);
+        flag_l[par] = inbox_flag(h->peer_l, 1, par);
+        flag_r[par] = inbox_flag(h->peer_r, 0, par);
+    }
+    sbc_launch_domain_push(h->dom, h->send_own[0], h->send_own[1], dst_l, dst_r, flag_l, flag_r, h->stream);
+}
+static void domain_launch_wait(sbc_handle *h) {
+    int *flag_a[2] = {inbox_flag(h->inbox, 0, 0), inbox_flag(h->inbox, 0, 1)};
+    int *flag_b[2] = {inbox_flag(h->inbox, 1, 0), inbox_flag(h->inbox, 1, 1)};
+    sbc_launch_domain_wait(h->dom, flag_a, flag_b, h->stream);
+}
+static void domain_launch_refresh_unpack(sbc_handle *h) {
+    sbc_launch_domain_refresh_unpack(h->S, h->dom, inbox_buf(h->inbox, h->inbox_buf_bytes, 0, 0),
+                                     inbox_buf(h->inbox, h->inbox_buf_bytes, 0, 1), inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 0),
+                                     inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 1), h->stream);
+}
+int sbc_domain_post(sbc_handle *h) {
+    if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
+    if (int rc = sbc_domain_pack(h, h->send_own[0], h->send_own[1])) return rc;
+    h->dom_epoch++;   // mirrors ctl[16], which the flag kernel advances
+    domain_launch_push(h);
+    h->host_stats[7] += 2;
+    return SBC_OK;
+}
+int sbc_domain_complete(sbc_handle *h) {
+    if (!h || !h->dom.enabled || !h->inbox) return SBC_ERR_STATE;
+    SBC_CUDA(cudaSetDevice(h->device));
+    domain_launch_wait(h);
+    h->host_stats[7] += 1;
+    if (!h->dom_last_full) {
+        domain_launch_refresh_unpack(h);
+        h->host_stats[7] += 1;
+        return SBC_OK;
+    }
+    const int par = h->dom_epoch & 1;
+    return sbc_domain_unpack(h, inbox_buf(h->inbox, h->inbox_buf_bytes, 0, par), inbox_buf(h->inbox, h->inbox_buf_bytes, 1, par),
+                             h->send_own[0], h->send_own[1]);
+}
+int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
+    if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
+    const bool graphable = h->use_graphs && h->stream != nullptr && h->stream != cudaStreamLegacy &&
+                           h->stream != cudaStreamPerThread;
+    for (int64_t s = s_first; s < s_first + n_steps; s++) {
+        if (int rc = sbc_step(h, s, 1)) return rc;
+        const bool full = !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
+        if (full || !graphable) {
+            if (int rc = sbc_domain_post(h)) return rc;
+            if (int rc = sbc_domain_complete(h)) return rc;
+            continue;
+        }
+        // refresh exchange: refresh-pack, push, flag, wait, refresh-unpack replayed as one graph launch
+        if (!h->refresh_graph_ok) {
+            cudaGraph_t graph;
+            SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            sbc_launch_domain_refresh_pack(h->S, h->dom, h->send_own[0], h->send_own[1], h->stream);
+            domain_launch_push(h);
+            domain_launch_wait(h);
+            domain_launch_refresh_unpack(h);
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("exchange graph capture: ") + cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&h->refresh_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("exchange graph instantiate: ") + cudaGetErrorString(ce));
+            h->refresh_graph_ok = true;
+        }
+        SBC_CUDA(cudaGraphLaunch(h->refresh_graph, h->stream));
+        h->dom_last_full = false;
+        h->dom_epoch++;
+        h->host_stats[7] += 5;
+    }
+    return SBC_OK;
+}
+
 int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
                       const void *sent_right_dev) {
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
@@ -945,7 +1089,7 @@ int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_
         h->cells_valid = false;   // slots changed hands: the next step rebuilds the cell order
         h->host_stats[7] += 2;
     } else {
-        sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, h->stream);
+        sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_a_dev, recv_b_dev, recv_b_dev, h->stream);
         h->host_stats[7] += 1;
     }
     return SBC_OK;

@@ -7,6 +7,9 @@ which rank is left / right, who gets which buffer, and the transport - `DistTran
 fixed-size record buffers with torch.distributed point-to-point operations (NCCL over NVLink between
 GPUs; the same code runs on CPU tensors with gloo, which is how the routing is tested without GPUs),
 `LoopbackTransport` wires several slabs inside one process (single-GPU emulation in the tests).
+`PeerTransport` is the fast path between GPUs: it only runs at set-up (the ranks swap the CUDA IPC handles
+of their inboxes); afterwards libsbc's own kernels store the records into the neighbours' device memory
+over NVLink and no message-library call is made per step (include/sbc.h, sbc_domain_post / _complete).
 
 Nothing here computes the hot path; the reference has no counterpart (it is a single process).
 """
@@ -75,6 +78,40 @@ class DistTransport:
         t = torch.tensor([int(v)], dtype=torch.int32, device=dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
         return int(t.item())
+
+
+class PeerTransport:
+    """Set-up of the peer-memory exchange: every rank exports its inbox (CUDA IPC), the handles travel once
+    through torch.distributed, each rank maps the inboxes of its two ring neighbours. The per-step traffic
+    then never touches this class (sbc_domain_step)."""
+
+    def __init__(self, slab, group=None):
+        import torch
+        import torch.distributed as dist
+        self.dist, self.rank, self.world, self.group = dist, slab.rank, slab.world, group
+        lib, h = slab.swarm.lib, slab.swarm.h
+        base, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        handle = (ctypes.c_ubyte * 64)()
+        slab.swarm._check(lib.sbc_domain_inbox(h, ctypes.byref(base), ctypes.byref(nbytes), handle))
+        if self.world == 1:
+            slab.swarm._check(lib.sbc_domain_attach_peers(h, base, base))
+            return
+        dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        left, right = neighbours(self.rank, self.world)
+        mapped = {}
+        for peer in {left, right}:
+            raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
+            p = ctypes.c_void_p()
+            slab.swarm._check(lib.sbc_domain_open_peer(h, raw, ctypes.byref(p)))
+            mapped[peer] = p
+        slab.swarm._check(lib.sbc_domain_attach_peers(h, mapped[left], mapped[right]))
+        dist.barrier(group=group)   # every inbox is mapped before anybody pushes
+
+    def min_int(self, v):
+        return DistTransport.min_int(self, v)
 
 
 class LoopbackTransport:
@@ -194,7 +231,23 @@ class SlabSwarm:
 
 def step_distributed(slab, transport, s_first, n_steps):
     """Advance one rank's slab (world > 1: a DistTransport moves the buffers between ranks). One exchange per
-    step: [pack -> exchange -> unpack] once before the first step, then after every step."""
+    step: [pack -> exchange -> unpack] once before the first step, then after every step. With a
+    PeerTransport the whole loop runs inside libsbc (sbc_domain_step): the records go straight into the
+    neighbours' device memory."""
+    if isinstance(transport, PeerTransport):
+        lib, h = slab.swarm.lib, slab.swarm.h
+        if not slab.primed:
+            slab.set_rebuild_period(transport.min_int(slab.local_rebuild_period()))
+            if slab.world > 1:
+                slab.swarm._check(lib.sbc_domain_post(h))
+                slab.swarm._check(lib.sbc_domain_complete(h))
+            slab.primed = True
+        if slab.world > 1:
+            slab.swarm._check(lib.sbc_domain_step(h, int(s_first), int(n_steps)))
+        else:
+            slab.swarm.step(s_first, n_steps)
+        return
+
     def exchange():
         slab.pack()
         transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
@@ -210,10 +263,45 @@ def step_distributed(slab, transport, s_first, n_steps):
             exchange()
 
 
-def step_loopback(slabs, s_first, n_steps):
-    """Advance all slabs held in this process in lock step (tests / single-GPU emulation)."""
+def attach_loopback_peers(slabs):
+    """Slabs of one process on one GPU: the neighbours' inboxes are ordinary device pointers."""
+    world = len(slabs)
+    bases = []
+    for sl in slabs:
+        base, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        sl.swarm._check(sl.swarm.lib.sbc_domain_inbox(sl.swarm.h, ctypes.byref(base), ctypes.byref(nbytes), None))
+        bases.append(base)
+    for sl in slabs:
+        left, right = neighbours(sl.rank, world)
+        sl.swarm._check(sl.swarm.lib.sbc_domain_attach_peers(sl.swarm.h, bases[left], bases[right]))
+
+
+def step_loopback(slabs, s_first, n_steps, peer=False):
+    """Advance all slabs held in this process in lock step (tests / single-GPU emulation). peer=True uses the
+    peer-memory exchange (after attach_loopback_peers): every slab posts, then every slab completes - all on
+    one stream, so no wait kernel ever spins."""
     world = len(slabs)
     tr = LoopbackTransport(world)
+    if peer:
+        def exchange():
+            for sl in slabs:
+                sl.swarm._check(sl.swarm.lib.sbc_domain_post(sl.swarm.h))
+            for sl in slabs:
+                sl.swarm._check(sl.swarm.lib.sbc_domain_complete(sl.swarm.h))
+        if not all(sl.primed for sl in slabs):
+            period = min(sl.local_rebuild_period() for sl in slabs)
+            for sl in slabs:
+                sl.set_rebuild_period(period)
+            if world > 1:
+                exchange()
+            for sl in slabs:
+                sl.primed = True
+        for s in range(s_first, s_first + n_steps):
+            for sl in slabs:
+                sl.step_local(s)
+            if world > 1:
+                exchange()
+        return
 
     def exchange():
         for sl in slabs:

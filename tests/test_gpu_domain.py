@@ -106,3 +106,28 @@ def test_decomposed_run_matches_whole_swarm(world):
         out = np.where(inside, 0.0, np.minimum((lo - own['x']) % L, (own['x'] - hi) % L))   # distance along the ring
         assert np.all(out <= 0.5 * skin + 1e-3), out.max()
         sl.close()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_peer_memory_exchange_equals_buffer_exchange(world):
+    """The push-into-the-neighbour's-inbox exchange (sbc_domain_post / _complete) moves exactly the records
+    the buffer exchange moves: identical states after a run with migration and refresh exchanges."""
+    from sde_burst_coast_b200.domain import step_loopback, gather_global, attach_loopback_peers
+    N, L, K = 6000, 400.0, 45
+    sp, st = _setup(N, L, 21)
+    st['vproj'] = st['vproj'] * 4
+    st['vx'], st['vy'] = st['vx'] * 4, st['vy'] * 4
+    out = []
+    for peer in (False, True):
+        slabs = _slabs(sp, st, N, world, seed=5)
+        if peer:
+            attach_loopback_peers(slabs)
+        step_loopback(slabs, 0, K, peer=peer)
+        got, seen = gather_global(slabs, N)
+        assert np.all(seen == 1)
+        assert sum(sl.counts()['overflow_events'] for sl in slabs) == 0
+        out.append(got)
+        for sl in slabs:
+            sl.close()
+    for k in out[0]:
+        assert np.array_equal(out[0][k], out[1][k]), k
