@@ -51,6 +51,7 @@ struct sbc_handle {
     std::vector<void *> ipc_opened;
     unsigned char *send_own[2];            // this rank's send buffers (left, right)
     int dom_epoch;
+    float4 *grid_pos;                      // [2][N padded] positions published by the cooperative kernel (swarm_grid.cu)
     cudaGraphExec_t refresh_graph;         // one refresh exchange (pack, push, flag, wait, unpack)
     bool refresh_graph_ok;
     // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
@@ -299,7 +300,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
         }
         h->use_cells = true;
     } else if (p->path == SBC_PATH_AUTO) {
-        h->use_cells = n_agents >= 8192 && sbc_cells_supported(h->P, n_agents, n_replicates);
+        h->use_cells = n_agents > 2048 && sbc_cells_supported(h->P, n_agents, n_replicates);
     }
     *out = h;
     // InitSystem defaults (settings.cpp:168-193)
@@ -321,7 +322,7 @@ int sbc_destroy(sbc_handle *h) {
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     if (h->refresh_graph_ok) cudaGraphExecDestroy(h->refresh_graph);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
+    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]); cudaFree(h->grid_pos);
     cudaFree(h->S.gid);
     for (int k = 0; k < 4; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
     cudaFree(h->step_dev);
@@ -589,8 +590,14 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (injected && n_steps != 1) return fail(h, SBC_ERR_STATE, "sbc_step: injected decisions hold for one step");
     const bool cluster_ok = !h->force_block && sbc_cluster_supported(h->P, S.N, S.Npred);
-    const bool block_path = !h->force_multikernel && (S.N <= 1024 || cluster_ok) && S.Npred <= 1024 &&
-                            p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
+    // 2,049 .. 4,096 agents, no single predator: one persistent cooperative launch, a grid barrier per step.
+    // (Measured: 13.7 us/step at N = 4096 against 28.7 on the multi-kernel path; from ~6,000 agents on the
+    // all-pairs sweep of the cooperative kernel loses to the cell-list kernels, 22 vs 16 us/step at N = 8192; with the
+    // cell list the multi-kernel path needs 14.8 us/step at N = 4096, so the gain is modest.)
+    const bool grid_ok = !h->force_block && !cluster_ok && S.N > 1024 && S.N <= 4096 && p.path == SBC_PATH_AUTO &&
+                         sbc_grid_supported(h->P, S.N, S.R, S.Npred);
+    const bool block_path = !h->force_multikernel && (S.N <= 1024 || cluster_ok || grid_ok) && S.Npred <= 2048 &&
+                            (S.Npred <= 1024 || grid_ok) && p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
     // predator schedule in step indices (swarmdyn.cpp:153-170)
     long long s_pred = -1;
     int s_trunc = 0, needed = 0;
@@ -606,6 +613,11 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         }
     }
     const bool cluster_path = block_path && cluster_ok;
+    const bool grid_path = block_path && grid_ok;
+    if (grid_path && !h->grid_pos) {
+        const size_t npad = ((size_t)S.N + 255) / 256 * 256;
+        SBC_CUDA(cudaMalloc((void **)&h->grid_pos, 2 * npad * sizeof(float4)));
+    }
     if (block_path) {
         // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
         int64_t done = 0;
@@ -613,6 +625,8 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             const int64_t chunk = (n_steps - done > (1ll << 30)) ? (1ll << 30) : (n_steps - done);
             if (cluster_path)  // 257..2048 agents: one swarm on a cluster of up to 8 CTAs (DSMEM)
                 SBC_CUDA(sbc_launch_swarm_cluster(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed));
+            else if (grid_path)
+                SBC_CUDA(sbc_launch_swarm_grid(h->P, S, s_first + done, chunk, h->grid_pos, h->stream, s_pred, s_trunc, needed));
             else
                 sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed, h->force_block);
             done += chunk;

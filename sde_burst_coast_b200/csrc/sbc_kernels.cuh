@@ -145,6 +145,9 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
 
 // --- one swarm per thread-block cluster, positions shared through DSMEM (swarm_cluster.cu) ---------
 bool sbc_cluster_supported(const DevParams &P, int N, int Npred);
+bool sbc_grid_supported(const DevParams &P, int N, int R, int Npred);
+cudaError_t sbc_launch_swarm_grid(const DevParams &P, const DevState &S, long long s_first, long long n_steps, float4 *pos,
+                                  cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
                                      cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 

@@ -24,14 +24,30 @@ def _swarm(*a, **k):
     return Swarm(*a, **k)
 
 
-def _close_state(o, g, sp, what=''):
-    """o: oracle state, g: GPU state (same shapes). Returns the mask of agents that agree."""
-    okx = (np.abs(o['x'] - g['x']) <= TOL_X * np.maximum(1, np.abs(o['x']))) & \
-          (np.abs(o['y'] - g['y']) <= TOL_X * np.maximum(1, np.abs(o['y'])))
-    okv = np.abs(o['vproj'] - g['vproj']) <= TOL_V * np.maximum(1, np.abs(o['vproj']))
-    okp = ang_diff(o['phi'], g['phi']) <= TOL_PHI
+def _cancellation(pairs):
+    """Relative error FP32 may leave in the DIRECTION of a zone sum: c unit vectors summed in FP32 carry an
+    absolute error of about c * 2^-23, which matters when they nearly cancel (|sum| << 1). Per row, the worst
+    of the zones that have members."""
+    cond = np.zeros(len(pairs['c_rep']))
+    for c, f in (('c_rep', 'f_rep'), ('c_alg', 'f_alg'), ('c_att', 'f_att')):
+        n = pairs[c].astype(np.float64)
+        mag = np.hypot(pairs[f][:, 0], pairs[f][:, 1])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            cond = np.maximum(cond, np.where(n > 0, n * 2.4e-7 / np.maximum(mag, 1e-30), 0.0))
+    return np.minimum(cond, 1.0)
+
+
+def _close_state(o, g, sp, what='', cond=None):
+    """o: oracle state, g: GPU state (same shapes). Returns the mask of agents that agree. `cond` (from
+    _cancellation) widens the bars of rows whose social force is an ill-conditioned sum."""
     fmag = np.maximum(1.0, np.hypot(o['fx'], o['fy']))
-    okf = np.hypot(o['fx'] - g['fx'], o['fy'] - g['fy']) <= TOL_F * fmag
+    extra = np.zeros_like(fmag) if cond is None else cond
+    kick = extra * fmag * sp.dt     # what the force error does to speed / heading / position within one step
+    okx = (np.abs(o['x'] - g['x']) <= TOL_X * np.maximum(1, np.abs(o['x'])) + kick) & \
+          (np.abs(o['y'] - g['y']) <= TOL_X * np.maximum(1, np.abs(o['y'])) + kick)
+    okv = np.abs(o['vproj'] - g['vproj']) <= TOL_V * np.maximum(1, np.abs(o['vproj'])) + kick
+    okp = ang_diff(o['phi'], g['phi']) <= TOL_PHI + kick
+    okf = np.hypot(o['fx'] - g['fx'], o['fy'] - g['fy']) <= (TOL_F + extra) * fmag
     return okx & okv & okp & okf
 
 
@@ -41,6 +57,8 @@ def _close_state(o, g, sp, what=''):
     ('natPred', dict(BC=0, size=100.0, Npred=0), 300),
     ('natPred', dict(BC=0, size=100.0, Npred=0, alg_range=10.0), 1024),
     ('natPred', dict(BC=0, size=200.0, Npred=0), 2000),
+    ('natPred', dict(BC=0, size=300.0, Npred=0), 3000),            # cooperative grid kernel (swarm_grid.cu)
+    ('burst_coast', dict(BC=5, size=120.0), 2500),
     ('burst_coast', dict(BC=2, size=60.0), 50), ('burst_coast', dict(BC=3, size=60.0), 50),
 ])
 @pytest.mark.parametrize('multikernel', [False, True, 2])   # automatic (warp / block / cluster kernel), multi-kernel, block kernel
@@ -58,6 +76,7 @@ def test_one_step_injected(mode, over, N, multikernel):
         kn = rng.integers(1, 600, N).astype(np.uint32)
         w = pyorc.World(sp, N)
         w.set_state(**st)
+        cond = _cancellation(w.pair_interactions(0, want_nn=False))   # burst-starting rows of this state
         w.inject(us, ud, kn)
         fo = w.step(0, 1, want_flags=True)
         o = w.get_state()
@@ -72,7 +91,7 @@ def test_one_step_injected(mode, over, N, multikernel):
         fg = g.debug_flags(True, read=True)
         assert np.array_equal(o['bin_step'], gs['bin_step'])
         assert np.array_equal(o['steps_till_burst'], gs['steps_till_burst'])
-        ok = _close_state(o, gs, sp)
+        ok = _close_state(o, gs, sp, cond=cond)
         same_flags = (fo == fg)
         # an agent may only disagree if one of its branch decisions flipped (guard band)
         assert np.all(ok | ~same_flags), 'state differs although every branch agreed: %s' % np.where(~ok & same_flags)[0]
@@ -148,7 +167,7 @@ def test_split_launches_equal_one_launch():
     b.close()
 
 
-@pytest.mark.parametrize('N', [30, 64, 300, 1500])
+@pytest.mark.parametrize('N', [30, 64, 300, 1500, 3500])
 def test_block_path_matches_multikernel_path(N):
     """The one-block-per-swarm kernel and the pair-pass + update kernels are two schedules of the same
     arithmetic: identical timers, states within the one-step tolerance for a short run."""
