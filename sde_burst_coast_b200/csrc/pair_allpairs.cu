@@ -16,7 +16,9 @@ namespace {
 // the pass is a plain stream over 9 bytes per agent. The order of the list does not matter - every row
 // writes only its own accumulators.
 __global__ void __launch_bounds__(256)
-compact_active_kernel(DevState S, uint32_t burst_steps, int all_alive, int *list, int *count) {
+compact_active_kernel(DevState S, uint32_t burst_steps, int all_alive, int *list, int *count, uint32_t *step_inc) {
+    // first kernel of a graph-replayed step: advance the device-resident step index for the kernels behind it
+    if (step_inc && blockIdx.x == 0 && threadIdx.x == 0) *step_inc += 1u;
     const size_t total = (size_t)S.N * S.R;
     const size_t quads = (total + 3) / 4;
     const int lane = threadIdx.x & 31;
@@ -185,12 +187,13 @@ __global__ void clear_acc_kernel(DevState S) {
 
 // compact the rows that start a burst this step into S.active_list / S.active_count; `clear` also
 // zeroes every row's accumulators (only the test hook reads rows that were not active)
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive) {
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive,
+                             bool count_is_zero, uint32_t *step_inc) {
     const size_t total = (size_t)S.N * S.R;
     const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
-    cudaMemsetAsync(S.active_count, 0, sizeof(int), st);
+    if (!count_is_zero) cudaMemsetAsync(S.active_count, 0, sizeof(int), st);
     if (clear) clear_acc_kernel<<<blocks, 256, 0, st>>>(S);
-    compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, all_alive ? 1 : 0, S.active_list, S.active_count);
+    compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, all_alive ? 1 : 0, S.active_list, S.active_count, step_inc);
 }
 
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {

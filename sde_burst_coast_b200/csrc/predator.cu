@@ -121,32 +121,6 @@ net_move_kernel(const __grid_constant__ DevParams P, DevState S) {
     }
 }
 
-// FishNetKill (agents_dynamics.cpp:780-820): grid (agent chunks, replicates); predicates in FP64
-__global__ void __launch_bounds__(PT)
-net_kill_kernel(const __grid_constant__ DevParams P, DevState S) {
-    __shared__ int s_killed;
-    const int rep = blockIdx.y;
-    const int N = S.N;
-    float4 *pv = S.pv + (size_t)rep * N;
-    const float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
-    if (threadIdx.x == 0) s_killed = 0;
-    __syncthreads();
-    const float4 p0 = pp[0], p1 = pp[1];
-    const float ph0 = S.pred_phi[(size_t)rep * S.Npred];
-    int killed = 0;
-    for (int i = blockIdx.x * PT + threadIdx.x; i < N; i += gridDim.x * PT) {
-        const float4 p = pv[i];
-        if (p.x != p.x) continue;
-        if (sbc_net_kills(p.x, p.y, p0, p1, ph0, S.Npred, P)) {
-            kill_agent(S, (size_t)rep * N + i, p);
-            killed++;
-        }
-    }
-    if (killed) atomicAdd(&s_killed, killed);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_killed) atomicAdd(S.n_dead + rep, s_killed);
-}
-
 __global__ void __launch_bounds__(PT)
 pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
                       const uint32_t *__restrict__ step_dev) {
@@ -260,12 +234,8 @@ void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step
 }
 void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
                                cudaStream_t st) {
-    if (S.Npred > 1) {
+    if (S.Npred > 1) {  // the net kill was evaluated by update_kernel against the moved first two nodes
         net_move_kernel<<<S.R, PT, 0, st>>>(P, S);
-        if (P.pred_kill != 0) {
-            const int chunks = min(148 * 4, (S.N + PT - 1) / PT);
-            net_kill_kernel<<<dim3(chunks, S.R), PT, 0, st>>>(P, S);
-        }
         return;
     }
     pred_move_kill_kernel<<<S.R, PT, 0, st>>>(P, S, (uint32_t)step, step_dev);

@@ -42,6 +42,7 @@ struct sbc_handle {
     int cells_local_max_age;       // what this handle's own agents allow (domain mode: the ranks agree on the minimum)
     int dom_period;                // domain mode: agreed number of refresh exchanges between two full ones
     bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
+    bool active_count_zero;        // S.active_count is known to be zero (left so by the last update kernel)
     double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
     // exchange through peer memory: own inbox [flags 256 B | from-left p0 | from-left p1 | from-right p0 | from-right p1]
@@ -51,7 +52,6 @@ struct sbc_handle {
     std::vector<void *> ipc_opened;
     unsigned char *send_own[2];            // this rank's send buffers (left, right)
     int dom_epoch;
-    float4 *grid_pos;                      // [2][N padded] positions published by the cooperative kernel (swarm_grid.cu)
     cudaGraphExec_t refresh_graph;         // one refresh exchange (pack, push, flag, wait, unpack)
     bool refresh_graph_ok;
     // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
@@ -322,7 +322,7 @@ int sbc_destroy(sbc_handle *h) {
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     if (h->refresh_graph_ok) cudaGraphExecDestroy(h->refresh_graph);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]); cudaFree(h->grid_pos);
+    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
     cudaFree(h->S.gid);
     for (int k = 0; k < 4; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
     cudaFree(h->step_dev);
@@ -379,9 +379,10 @@ static void set_cells_max_age(sbc_handle *h) {
 
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
 static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false,
-                            bool rebuild_cells = true) {
+                            bool rebuild_cells = true, uint32_t *step_inc = nullptr) {
     if (all_rows && h->P.voronoi) {  // Delaunay-filtered candidates: every alive row through the rows kernel
-        sbc_launch_compact_rows(h->P, h->S, true, h->stream, true);
+        sbc_launch_compact_rows(h->P, h->S, true, h->stream, true, h->active_count_zero);
+        h->active_count_zero = false;
         sbc_launch_pair_rows(h->P, h->S, h->stream);
         h->host_stats[0]++;
         h->host_stats[7] += 2;
@@ -398,7 +399,8 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
         h->host_stats[7] += 2;
         h->host_stats[3] += (unsigned long long)h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
     } else {
-        sbc_launch_compact_rows(h->P, h->S, clear_inactive, h->stream);
+        sbc_launch_compact_rows(h->P, h->S, clear_inactive, h->stream, false, h->active_count_zero, step_inc);
+        h->active_count_zero = false;
         h->host_stats[7] += clear_inactive ? 2 : 1;
         if (h->use_cells) {
             if (!h->cells_ready) {
@@ -590,14 +592,8 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (injected && n_steps != 1) return fail(h, SBC_ERR_STATE, "sbc_step: injected decisions hold for one step");
     const bool cluster_ok = !h->force_block && sbc_cluster_supported(h->P, S.N, S.Npred);
-    // 2,049 .. 4,096 agents, no single predator: one persistent cooperative launch, a grid barrier per step.
-    // (Measured: 13.7 us/step at N = 4096 against 28.7 on the multi-kernel path; from ~6,000 agents on the
-    // all-pairs sweep of the cooperative kernel loses to the cell-list kernels, 22 vs 16 us/step at N = 8192; with the
-    // cell list the multi-kernel path needs 14.8 us/step at N = 4096, so the gain is modest.)
-    const bool grid_ok = !h->force_block && !cluster_ok && S.N > 1024 && S.N <= 4096 && p.path == SBC_PATH_AUTO &&
-                         sbc_grid_supported(h->P, S.N, S.R, S.Npred);
-    const bool block_path = !h->force_multikernel && (S.N <= 1024 || cluster_ok || grid_ok) && S.Npred <= 2048 &&
-                            (S.Npred <= 1024 || grid_ok) && p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
+    const bool block_path = !h->force_multikernel && (S.N <= 1024 || cluster_ok) && S.Npred <= 1024 &&
+                            p.path != SBC_PATH_CELLLIST && !h->dom.enabled;
     // predator schedule in step indices (swarmdyn.cpp:153-170)
     long long s_pred = -1;
     int s_trunc = 0, needed = 0;
@@ -613,11 +609,6 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         }
     }
     const bool cluster_path = block_path && cluster_ok;
-    const bool grid_path = block_path && grid_ok;
-    if (grid_path && !h->grid_pos) {
-        const size_t npad = ((size_t)S.N + 255) / 256 * 256;
-        SBC_CUDA(cudaMalloc((void **)&h->grid_pos, 2 * npad * sizeof(float4)));
-    }
     if (block_path) {
         // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
         int64_t done = 0;
@@ -625,8 +616,6 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             const int64_t chunk = (n_steps - done > (1ll << 30)) ? (1ll << 30) : (n_steps - done);
             if (cluster_path)  // 257..2048 agents: one swarm on a cluster of up to 8 CTAs (DSMEM)
                 SBC_CUDA(sbc_launch_swarm_cluster(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed));
-            else if (grid_path)
-                SBC_CUDA(sbc_launch_swarm_grid(h->P, S, s_first + done, chunk, h->grid_pos, h->stream, s_pred, s_trunc, needed));
             else
                 sbc_launch_swarm_block(h->P, S, s_first + done, chunk, h->stream, s_pred, s_trunc, needed, h->force_block);
             done += chunk;
@@ -661,8 +650,9 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                                    h->stream != cudaStreamPerThread;  // the default streams cannot be captured
             if (graphable) {
                 if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
+                // the device holds s - 1 between steps: the graph's first kernel (the compaction) advances it
                 if (h->step_dev_value != s) {
-                    const uint32_t sv = (uint32_t)s;
+                    const uint32_t sv = (uint32_t)s - 1u;
                     SBC_CUDA(cudaMemcpyAsync(h->step_dev, &sv, sizeof(sv), cudaMemcpyHostToDevice, h->stream));
                     SBC_CUDA(cudaStreamSynchronize(h->stream));  // sv is a stack variable
                 }
@@ -671,11 +661,12 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     unsigned long long keep[8];
                     std::memcpy(keep, h->host_stats, sizeof(keep));  // the capture pass launches nothing
                     SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                    int rc = launch_pair_pass(h, 0, false, false, rebuild);
-                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream);
+                    h->active_count_zero = true;   // precondition of a replay, established below
+                    int rc = launch_pair_pass(h, 0, false, false, rebuild, h->step_dev);
+                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true);
                     if (pred_phase) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
-                    sbc_launch_step_advance(h->step_dev, h->stream);
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                    h->active_count_zero = false;  // nothing ran during the capture
                     if (rc) return rc;
                     if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
                     ce = cudaGraphInstantiate(&h->step_graph[gk], graph, 0);
@@ -684,7 +675,9 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     h->step_graph_ok[gk] = true;
                     std::memcpy(h->host_stats, keep, sizeof(keep));
                 }
+                if (!h->active_count_zero) SBC_CUDA(cudaMemsetAsync(S.active_count, 0, sizeof(int), h->stream));
                 SBC_CUDA(cudaGraphLaunch(h->step_graph[gk], h->stream));
+                h->active_count_zero = true;   // the graph's update kernel left the counter at zero
                 h->step_dev_value = s + 1;
                 h->host_stats[0]++;
                 h->host_stats[1]++;
@@ -692,7 +685,8 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                 if (h->use_cells && rebuild) h->host_stats[6]++;
             } else {
                 if (int rc = launch_pair_pass(h, 0, false, false, rebuild)) return rc;
-                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream);
+                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true);
+                h->active_count_zero = true;
                 h->host_stats[1]++;
                 if (pred_phase) {
                     sbc_launch_pred_move_kill(h->P, S, s, nullptr, h->stream);

@@ -50,7 +50,8 @@ void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev
 
 // --- all-pairs three-zone pass -------------------------------------------------------------------
 // burst-gated rows (bin_step == burst_steps), pair_allpairs.cu: compaction, then all-pairs rows
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive = false);
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive = false,
+                             bool count_is_zero = false, uint32_t *step_inc = nullptr);
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st);
 // burst-gated rows through a cell list (celllist.cu), single large swarm
 struct CellScratch {
@@ -125,9 +126,10 @@ void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const f
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
+// pred_active: the rows' flee sums are valid (detection ran); zero_count: reset the active-row counter for the next
+// step's compaction once nobody reads it any more; the fish-net kill is evaluated here when a net is present
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st);
-void sbc_launch_step_advance(uint32_t *step_dev, cudaStream_t st);
+                       int pred_active, cudaStream_t st, bool zero_count = false);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,
@@ -145,9 +147,7 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
 
 // --- one swarm per thread-block cluster, positions shared through DSMEM (swarm_cluster.cu) ---------
 bool sbc_cluster_supported(const DevParams &P, int N, int Npred);
-bool sbc_grid_supported(const DevParams &P, int N, int R, int Npred);
-cudaError_t sbc_launch_swarm_grid(const DevParams &P, const DevState &S, long long s_first, long long n_steps, float4 *pos,
-                                  cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
+
 cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long long s_first, long long n_steps,
                                      cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 

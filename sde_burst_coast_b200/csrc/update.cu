@@ -59,7 +59,9 @@ detect_rows_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t ste
 
 __global__ void __launch_bounds__(256)
 update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg, const uint32_t *__restrict__ step_dev,
-              int pred_active) {
+              int pred_active, int *zero_count, int net_kill) {
+    // the pair pass and the detection of this step are done: the next compaction may start from zero
+    if (zero_count && blockIdx.x == 0 && threadIdx.x == 0) *zero_count = 0;
     // inside a captured CUDA graph the step index lives in device memory (advanced by step_advance_kernel)
     const uint32_t step = step_dev ? *step_dev : step_arg;
     const size_t total = (size_t)S.N * S.R;
@@ -114,17 +116,34 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
     S.force[g] = make_float2(a.fx, a.fy);
     S.timers[g] = make_uint2(a.bin_step, a.stb);
     if (S.flags) S.flags[g] |= (uint8_t)fl;
+    if (net_kill) {
+        // FishNetKill (agents_dynamics.cpp:780-820) against the net AFTER this step's MoveFishNet (:616-624): the
+        // test reads the first two nodes only, so every thread moves its own copy of them (net_move_kernel, which
+        // runs behind this kernel, moves the stored net with the same arithmetic)
+        const int NP = S.Npred;
+        float4 n0 = S.pred_pv[(size_t)rep * NP], n1 = S.pred_pv[(size_t)rep * NP + 1];
+        float ph0 = S.pred_phi[(size_t)rep * NP], ph1 = S.pred_phi[(size_t)rep * NP + 1];
+        n0.x += n0.z * P.dt; n0.y += n0.w * P.dt;
+        sbc_boundary(n0.x, n0.y, n0.z, n0.w, ph0, P, P.BC);
+        n1.x += n1.z * P.dt; n1.y += n1.w * P.dt;
+        sbc_boundary(n1.x, n1.y, n1.z, n1.w, ph1, P, P.BC);
+        if (sbc_net_kills(a.x, a.y, n0, n1, ph0, NP, P)) {  // split_dead (agents_operation.cpp:209-218)
+            S.alive[g] = 0;
+            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
+            S.pv[g] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), a.vx, a.vy);
+            atomicAdd(S.n_dead + rep, 1);
+        }
+    }
 }
 
 }  // namespace
 
-__global__ void step_advance_kernel(uint32_t *step_dev) { *step_dev += 1u; }
-
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st) {
+                       int pred_active, cudaStream_t st, bool zero_count) {
     const size_t total = (size_t)S.N * S.R;
     if (pred_active)  // needs the compacted active rows of this step (sbc_launch_compact_rows)
         detect_rows_kernel<<<148 * 2, 256, 0, st>>>(P, S, (uint32_t)step, step_dev, S.active_list, S.active_count);
-    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active);
+    const int net_kill = (pred_active && S.Npred > 1 && P.pred_kill != 0) ? 1 : 0;
+    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active,
+                                                                  zero_count ? S.active_count : nullptr, net_kill);
 }
-void sbc_launch_step_advance(uint32_t *step_dev, cudaStream_t st) { step_advance_kernel<<<1, 1, 0, st>>>(step_dev); }
