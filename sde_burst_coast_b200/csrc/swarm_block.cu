@@ -56,10 +56,127 @@ struct PredSchedule {
 
 constexpr int BC_RUNTIME = -99;   // template value: take the boundary condition from the parameters
 
-template <int TPS, int BCT, bool VOR, bool PRED>
+template <int TPS, int BCT, bool VOR>
 __global__ void __launch_bounds__(128)
-swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps,
+swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
+    const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
+    constexpr int SPW = 32 / TPS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int seg = lane / TPS, t = lane % TPS;
+    const int rep = warp_global * SPW + seg;
+    const int N = S.N;
+    const bool valid = (rep < S.R) && (t < N);
+    const size_t g = valid ? ((size_t)rep * N + t) : 0;
+    const unsigned segmask = (TPS == 32) ? FULL : (((1u << TPS) - 1u) << (seg * TPS));
+    AgentState a = {};
+    bool alive = false;
+    if (valid) {
+        load_agent(S, g, a);
+        alive = S.alive[g] != 0;
+    }
+    uint32_t flags_acc = 0;
+    unsigned long long n_amb = 0, n_pairs = 0;
+
+    for (uint32_t s = s_first; s != s_first + n_steps; s++) {
+        const bool first = alive && (a.bin_step == P.burst_steps);
+        RowAcc acc;
+        row_acc_clear(acc);
+        unsigned rem = __ballot_sync(FULL, first);
+        while (rem) {  // warp-uniform: every segment serves its lowest pending row
+            const unsigned mine = rem & segmask;
+            const bool has = mine != 0;
+            const int src = has ? (__ffs(mine) - 1) : lane;
+            const float xi = __shfl_sync(FULL, a.x, src), yi = __shfl_sync(FULL, a.y, src);
+            int z = 3;
+            float ux = 0.f, uy = 0.f;
+            if (has && alive && lane != src) {  // pair (row src <- me)
+                float dx = a.x - xi, dy = a.y - yi;
+                if (BC == 0) {
+                    dx = sbc_delta_pbc(xi, a.x, P);
+                    dy = sbc_delta_pbc(yi, a.y, P);
+                }
+                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                bool amb;
+                z = sbc_zone_fast(d2, P, amb);
+                if (amb) {
+                    z = sbc_zone_exact(xi, yi, a.x, a.y, P);
+                    n_amb++;
+                }
+                const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+                ux = dx * rinv;
+                uy = dy * rinv;
+                n_pairs++;
+            }
+            if (VOR) {  // keep only Delaunay neighbours of the row (warp-uniform loop over the tank)
+                DelaunayEdge e;
+                sbc_delaunay_begin(e, xi, yi, a.x, a.y);
+                const unsigned alive_mask = __ballot_sync(FULL, alive);
+                const int seg0 = seg * TPS;
+                for (int k = 0; k < TPS; k++) {
+                    const int lk = seg0 + k;
+                    const float xk = __shfl_sync(FULL, a.x, lk), yk = __shfl_sync(FULL, a.y, lk);
+                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, xk, yk);
+                }
+                if (z < 3 && !sbc_delaunay_end(e)) z = 3;
+            }
+            const int cr = __popc(__ballot_sync(FULL, z == 0) & segmask);
+            const int ca = __popc(__ballot_sync(FULL, z == 1) & segmask);
+            const int ct = __popc(__ballot_sync(FULL, z == 2) & segmask);
+            // the decision reads force_rep when c_rep > 0 and force_alg/force_att otherwise
+            // (agents_dynamics.cpp:40-58): reduce only what will be read
+            float v0 = (cr > 0) ? ((z == 0) ? -ux : 0.f) : ((z == 1) ? a.vx : 0.f);
+            float v1 = (cr > 0) ? ((z == 0) ? -uy : 0.f) : ((z == 1) ? a.vy : 0.f);
+            float v2 = (z == 2) ? ux : 0.f;
+            float v3 = (z == 2) ? uy : 0.f;
+#pragma unroll
+            for (int o = TPS / 2; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(FULL, v0, o);
+                v1 += __shfl_xor_sync(FULL, v1, o);
+                v2 += __shfl_xor_sync(FULL, v2, o);
+                v3 += __shfl_xor_sync(FULL, v3, o);
+            }
+            const bool is_row = has && (lane == src);
+            if (is_row) {
+                acc.c_rep = cr; acc.c_alg = ca; acc.c_att = ct;
+                if (cr > 0) { acc.rep_x = v0; acc.rep_y = v1; }
+                else { acc.alg_x = v0; acc.alg_y = v1; }
+                acc.att_x = v2; acc.att_y = v3;
+            }
+            rem &= ~__ballot_sync(FULL, is_row);
+        }
+        if (alive) {
+            double u_social = 0.0;
+            float u_dir = 0.f;
+            uint32_t k_next = 1;
+            const bool rearm = a.stb <= 1;
+            if (first || rearm) draw_decisions(P, S, g, rep, t, s, rearm, u_social, u_dir, k_next);
+            uint32_t fl = 0;
+            sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, BC);
+            flags_acc |= fl;
+        }
+    }
+    if (valid && alive) {
+        store_agent(S, g, a);
+        if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
+    }
+    n_amb = __reduce_add_sync(FULL, (unsigned)n_amb);
+    const unsigned np = __reduce_add_sync(FULL, (unsigned)n_pairs);
+    if (lane == 0) {
+        if (n_amb) atomicAdd(S.stats + 4, n_amb);
+        if (np) atomicAdd(S.stats + 3, (unsigned long long)np);
+    }
+}
+
+// The same with ONE predator per swarm (natPred, sinFisher: Npred == 1) carried in registers by every lane of the
+// segment: spawn, detection by the burst-starting rows, chase / random walk, the four kill rules. Kept apart
+// from the kernel above, whose code generation must not depend on it (it is the headline kernel of bench.py).
+template <int TPS, int BCT, bool VOR>
+__global__ void __launch_bounds__(128)
+swarm_warp_pred_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps,
                   PredSchedule sched) {
+    constexpr bool PRED = true;
     const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
     constexpr int SPW = 32 / TPS;
     constexpr unsigned FULL = 0xffffffffu;
@@ -705,10 +822,15 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         const long long warps = ((long long)S.R + spw - 1) / spw;
         const int wpb = 4;
         const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
-#define SBC_WARP_LAUNCH(T, B, PR)                                                                          \
-    do {                                                                                                   \
-        if (P.voronoi) swarm_warp_kernel<T, B, true, PR><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched); \
-        else swarm_warp_kernel<T, B, false, PR><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched);         \
+#define SBC_WARP_LAUNCH(T, B, PR)                                                                         \
+    do {                                                                                                  \
+        if (PR) {                                                                                         \
+            if (P.voronoi) swarm_warp_pred_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched); \
+            else swarm_warp_pred_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched);  \
+        } else {                                                                                          \
+            if (P.voronoi) swarm_warp_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);     \
+            else swarm_warp_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);              \
+        }                                                                                                 \
     } while (0)
 #define SBC_WARP_BC(T)                                                                     \
     do {                                                                                   \
