@@ -357,6 +357,78 @@ __global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int 
     __threadfence_system();
 }
 
+// One refresh exchange in two kernels (the graph-replayed form): SEND gathers the listed positions straight into
+// the neighbours' inboxes and the last block to finish publishes the exchange count; RECV holds every block until
+// both flags show the count, then scatters the incoming positions into the ghost slots.
+__global__ void __launch_bounds__(256)
+dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list, int list_cap, DomRecord *dst_l0,
+                        DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, volatile int *flag_l0, volatile int *flag_l1,
+                        volatile int *flag_r0, volatile int *flag_r1, unsigned *ticket) {
+    const int epoch = ctl[16] + 1, par = epoch & 1;
+    DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
+    if (t == 0) {
+        DomRecord h = {};
+        h.pad[1] = 1u;   // marks a refresh buffer
+        h.pad[0] = (uint32_t)nl; dst_l[0] = h;
+        h.pad[0] = (uint32_t)nr; dst_r[0] = h;
+    }
+    if (t < nl) dst_l[1 + t].pv = S.pv[halo_list[t]];
+    if (t < nr) dst_r[1 + t].pv = S.pv[halo_list[list_cap + t]];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(ticket, 1u);
+        if (done == gridDim.x - 1) {   // every block has stored its records (and read ctl[16])
+            *ticket = 0u;
+            __threadfence_system();
+            *(par ? flag_l1 : flag_l0) = epoch;
+            *(par ? flag_r1 : flag_r0) = epoch;
+            __threadfence_system();
+            ctl[16] = epoch;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
+                        const DomRecord *recv_b0, const DomRecord *recv_b1, const volatile int *flag_a0,
+                        const volatile int *flag_a1, const volatile int *flag_b0, const volatile int *flag_b1) {
+    const int epoch = ctl[16], par = epoch & 1;
+    if (threadIdx.x == 0) {
+        const volatile int *fa = par ? flag_a1 : flag_a0, *fb = par ? flag_b1 : flag_b0;
+        const long long t0 = clock64();
+        while (*fa < epoch || *fb < epoch) {
+            if (clock64() - t0 > 6000000000ll) {   // ~3 s: a neighbour is gone; report instead of hanging the GPU
+                if (blockIdx.x == 0) ctl[6] += 1000;
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
+    const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        const bool ok_a = recv_a[0].pad[1] == 1u && (int)recv_a[0].pad[0] == ha + sl;
+        const bool ok_b = recv_b[0].pad[1] == 1u && (int)recv_b[0].pad[0] == hb + sr;
+        if (!ok_a || !ok_b) ctl[6] += 1;
+    }
+    int k = t;
+    const DomRecord *src = nullptr;
+    if (k < ha) src = recv_a + 1 + k;
+    else if ((k -= ha) < hb) src = recv_b + 1 + k;
+    else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
+    else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
+    if (src && t < S.N - own_cap) {
+        // the records were written by another GPU: read them past L1
+        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(&src->pv));
+        S.pv[own_cap + t] = pv;
+    }
+}
+
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
 // slot first. One block walks the slots from the top down, 1024 at a time, with an ordered compaction.
 __global__ void __launch_bounds__(1024)
@@ -470,6 +542,20 @@ void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *se
                                         static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), D.ctl, D.max_mig,
                                         D.max_halo);
     dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], D.ctl);
+}
+void sbc_launch_domain_refresh_fused(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
+                                     int *const flag_l[2], int *const flag_r[2], const void *const recv_a[2],
+                                     const void *const recv_b[2], int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
+    const int cap = D.max_halo + D.max_mig;
+    unsigned *ticket = reinterpret_cast<unsigned *>(D.ctl + 20);
+    dom_refresh_send_kernel<<<(cap + 255) / 256, 256, 0, st>>>(
+        S, D.ctl, D.halo_list, cap, static_cast<DomRecord *>(dst_l[0]), static_cast<DomRecord *>(dst_l[1]),
+        static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), flag_l[0], flag_l[1], flag_r[0], flag_r[1], ticket);
+    const int ghost_cap = S.N - D.own_cap;
+    dom_refresh_recv_kernel<<<(max(ghost_cap, 1) + 255) / 256, 256, 0, st>>>(
+        S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a[0]), static_cast<const DomRecord *>(recv_a[1]),
+        static_cast<const DomRecord *>(recv_b[0]), static_cast<const DomRecord *>(recv_b[1]), flag_a[0], flag_a[1], flag_b[0],
+        flag_b[1]);
 }
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
     dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl);

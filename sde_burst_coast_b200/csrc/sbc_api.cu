@@ -1069,10 +1069,23 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         if (!h->refresh_graph_ok) {
             cudaGraph_t graph;
             SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            sbc_launch_domain_refresh_pack(h->S, h->dom, h->send_own[0], h->send_own[1], h->stream);
-            domain_launch_push(h);
-            domain_launch_wait(h);
-            domain_launch_refresh_unpack(h);
+            {   // two kernels: gather + store into the neighbours' inboxes + publish | wait + scatter into the ghosts
+                void *dst_l[2], *dst_r[2];
+                const void *recv_a[2], *recv_b[2];
+                int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
+                for (int par = 0; par < 2; par++) {
+                    dst_l[par] = inbox_buf(h->peer_l, h->inbox_buf_bytes, 1, par);
+                    dst_r[par] = inbox_buf(h->peer_r, h->inbox_buf_bytes, 0, par);
+                    flag_l[par] = inbox_flag(h->peer_l, 1, par);
+                    flag_r[par] = inbox_flag(h->peer_r, 0, par);
+                    recv_a[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 0, par);
+                    recv_b[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 1, par);
+                    flag_a[par] = inbox_flag(h->inbox, 0, par);
+                    flag_b[par] = inbox_flag(h->inbox, 1, par);
+                }
+                sbc_launch_domain_refresh_fused(h->S, h->dom, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b,
+                                                h->stream);
+            }
             cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("exchange graph capture: ") + cudaGetErrorString(ce));
             ce = cudaGraphInstantiate(&h->refresh_graph, graph, 0);
@@ -1083,7 +1096,7 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         SBC_CUDA(cudaGraphLaunch(h->refresh_graph, h->stream));
         h->dom_last_full = false;
         h->dom_epoch++;
-        h->host_stats[7] += 5;
+        h->host_stats[7] += 2;
     }
     return SBC_OK;
 }

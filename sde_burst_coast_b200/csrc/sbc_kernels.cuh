@@ -100,7 +100,7 @@ struct DomainScratch {
                          // [7] migrants taken by the last unpack [8] owned [9] ghosts
                          // [10..13] ghost segment sizes of the last full unpack (halo from a, from b, sent l, sent r)
                          // [14] [15] length of the refresh list towards the left / right neighbour
-                         // [16] number of peer-memory exchanges posted so far
+                         // [16] number of peer-memory exchanges posted so far [20] block ticket of the fused refresh send
     int *halo_list = nullptr;  // [2][max_halo + max_mig] slots whose positions a refresh exchange sends left / right
     float halo = 0.f;          // width of the edge band that is mirrored on the neighbour (att_range + skin)
     int nblk = 0;
@@ -123,6 +123,9 @@ void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const
 void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
                             int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
+void sbc_launch_domain_refresh_fused(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
+                                     int *const flag_l[2], int *const flag_r[2], const void *const recv_a[2],
+                                     const void *const recv_b[2], int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
