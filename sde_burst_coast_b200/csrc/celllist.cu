@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                   const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                   const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
-                  const int *__restrict__ list, const int *__restrict__ count) {
+                  const int *__restrict__ list, const int *__restrict__ count, int detect, uint32_t step_arg,
+                  const uint32_t *__restrict__ step_dev) {
+    const uint32_t step = step_dev ? *step_dev : step_arg;
     __shared__ float shf[CELLS_THREADS / 32][6];
     __shared__ int shi[CELLS_THREADS / 32][3];
     __shared__ int pref[10], first[9];
@@ -204,6 +206,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
                                                  n_amb, n_cand);
         sbc_block_reduce_row<CELLS_THREADS / 32>(A, shf, shi);
         if (threadIdx.x == 0) cells_row_store(S, i, A);
+        if (detect && threadIdx.x < 32) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane);
         __syncthreads();   // pref / first are rewritten by the next row
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
@@ -217,7 +220,9 @@ __global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                        const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                        const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
-                       const int *__restrict__ list, const int *__restrict__ count) {
+                       const int *__restrict__ list, const int *__restrict__ count, int detect, uint32_t step_arg,
+                       const uint32_t *__restrict__ step_dev) {
+    const uint32_t step = step_dev ? *step_dev : step_arg;
     constexpr int WPB = CELLS_THREADS / 32;
     __shared__ int pref[WPB][10], first[WPB][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,6 +246,7 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
         }
         if (lane == 0) cells_row_store(S, i, A);
         __syncwarp();
+        if (detect) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane);
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
@@ -319,13 +325,15 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
 }
 
 // active rows must have been compacted into S.active_list / S.active_count (sbc_launch_compact_rows)
-void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st) {
+void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st, int detect, long long step,
+                           const uint32_t *step_dev) {
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
     const int blocks = (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
     // mean number of candidates a row meets in its nine cells decides between a warp and a block per row
     const double per_row = 9.0 * (double)S.N / (double)(C.ncells > 0 ? C.ncells : 1);
     const bool warp_rows = P.BC == 0 && per_row < 512.0;
-#define SBC_CELLS_ARGS P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, S.active_list, S.active_count
+#define SBC_CELLS_ARGS \
+    P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, S.active_list, S.active_count, detect, (uint32_t)step, step_dev
     if (P.BC == 0) {
         if (warp_rows) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
         else pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);

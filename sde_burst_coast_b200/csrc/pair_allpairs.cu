@@ -66,7 +66,8 @@ constexpr int ROWS_THREADS = 128;  // one block per active row
 
 __global__ void __launch_bounds__(ROWS_THREADS)
 pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__restrict__ list,
-                 const int *__restrict__ count) {
+                 const int *__restrict__ count, int detect, uint32_t step_arg, const uint32_t *__restrict__ step_dev) {
+    const uint32_t step = step_dev ? *step_dev : step_arg;
     __shared__ float shf[ROWS_THREADS / 32][6];
     __shared__ int shi[ROWS_THREADS / 32][3];
     const int lane = threadIdx.x & 31;
@@ -127,6 +128,7 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, const int *__r
             acc[4] = A.att_x; acc[5] = A.att_y;
             cnt[0] = A.c_rep; cnt[1] = A.c_alg; cnt[2] = A.c_att;
         }
+        if (detect && threadIdx.x < 32) sbc_detect_row_warp(P, S, (size_t)g, pi, step, lane);
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
@@ -196,12 +198,13 @@ void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, 
     compact_active_kernel<<<blocks, 256, 0, st>>>(S, P.burst_steps, all_alive ? 1 : 0, S.active_list, S.active_count, step_inc);
 }
 
-void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st) {
+void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st, int detect, long long step,
+                          const uint32_t *step_dev) {
     // grid: enough blocks for the synchronised first burst (every row active), few enough to be cheap
     // to launch when only a handful of rows start a burst
     const size_t total = (size_t)S.N * S.R;
     const int blocks = (int)min((size_t)148 * 8, max((size_t)16, total / 64));
-    pair_rows_kernel<<<blocks, ROWS_THREADS, 0, st>>>(P, S, S.active_list, S.active_count);
+    pair_rows_kernel<<<blocks, ROWS_THREADS, 0, st>>>(P, S, S.active_list, S.active_count, detect, (uint32_t)step, step_dev);
 }
 
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,

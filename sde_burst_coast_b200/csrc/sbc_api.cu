@@ -379,7 +379,7 @@ static void set_cells_max_age(sbc_handle *h) {
 
 // one three-zone pass over the current state: dense (all rows) or burst-gated rows
 static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false,
-                            bool rebuild_cells = true, uint32_t *step_inc = nullptr) {
+                            bool rebuild_cells = true, uint32_t *step_inc = nullptr, int detect = 0, long long step = 0) {
     if (all_rows && h->P.voronoi) {  // Delaunay-filtered candidates: every alive row through the rows kernel
         sbc_launch_compact_rows(h->P, h->S, true, h->stream, true, h->active_count_zero);
         h->active_count_zero = false;
@@ -419,10 +419,10 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
                 h->host_stats[6]++;
                 h->host_stats[7] += 4;
             }
-            sbc_launch_pair_cells(h->P, h->S, h->cells, h->stream);
+            sbc_launch_pair_cells(h->P, h->S, h->cells, h->stream, detect, step, step_inc);
             h->host_stats[7] += 1;
         } else {
-            sbc_launch_pair_rows(h->P, h->S, h->stream);
+            sbc_launch_pair_rows(h->P, h->S, h->stream, detect, step, step_inc);
         }
         h->host_stats[0]++;
     }
@@ -662,8 +662,8 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     std::memcpy(keep, h->host_stats, sizeof(keep));  // the capture pass launches nothing
                     SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                     h->active_count_zero = true;   // precondition of a replay, established below
-                    int rc = launch_pair_pass(h, 0, false, false, rebuild, h->step_dev);
-                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true);
+                    int rc = launch_pair_pass(h, 0, false, false, rebuild, h->step_dev, pred_phase ? 1 : 0, 0);
+                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true, true);
                     if (pred_phase) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     h->active_count_zero = false;  // nothing ran during the capture
@@ -681,11 +681,11 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                 h->step_dev_value = s + 1;
                 h->host_stats[0]++;
                 h->host_stats[1]++;
-                h->host_stats[7] += (h->use_cells ? (rebuild ? 7 : 3) : 2) + (pred_phase ? 2 : 0);
+                h->host_stats[7] += (h->use_cells ? (rebuild ? 7 : 3) : 2) + (pred_phase ? 1 : 0);
                 if (h->use_cells && rebuild) h->host_stats[6]++;
             } else {
-                if (int rc = launch_pair_pass(h, 0, false, false, rebuild)) return rc;
-                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true);
+                if (int rc = launch_pair_pass(h, 0, false, false, rebuild, nullptr, pred_phase ? 1 : 0, s)) return rc;
+                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true, true);
                 h->active_count_zero = true;
                 h->host_stats[1]++;
                 if (pred_phase) {

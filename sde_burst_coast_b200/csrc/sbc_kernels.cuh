@@ -34,6 +34,44 @@ struct DevState {
     unsigned long long *stats; // [8] see sbc_get_stats
 };
 
+// prey<-predator detection (IntCalcPred, /root/reference/src/agents_interact.cpp:252-292) of ONE burst-starting row by
+// ONE warp: a lane takes four predators per Philox block; flee sums and counter go to acc[6..7] / cnt[3] of the row.
+// Called by the pair kernels right after the row's zone sums (every lane of the warp must call it).
+#ifdef __CUDACC__
+__device__ __forceinline__ void sbc_detect_row_warp(const DevParams &P, const DevState &S, size_t g, float4 pi, uint32_t step,
+                                                    int lane) {
+    const int N = S.N, NP = S.Npred;
+    const uint32_t rep = (uint32_t)(g / N);
+    const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
+    const float4 *pp = S.pred_pv + (size_t)rep * NP;
+    RowAcc acc;
+    row_acc_clear(acc);
+    for (int jb = lane; 4 * jb < NP; jb += 32) {
+        const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DETECT0 + (uint32_t)jb);
+        const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = 4 * jb + u;
+            if (j < NP) {
+                const float4 pr = pp[j];
+                sbc_detect_accumulate(acc, pi.x, pi.y, pr.x, pr.y, (double)r[u] * (1.0 / 4294967296.0), P);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.flee_x += __shfl_xor_sync(0xffffffffu, acc.flee_x, o);
+        acc.flee_y += __shfl_xor_sync(0xffffffffu, acc.flee_y, o);
+    }
+    const int cf = __reduce_add_sync(0xffffffffu, acc.c_flee);
+    if (lane == 0) {
+        S.acc[g * 8 + 6] = acc.flee_x;
+        S.acc[g * 8 + 7] = acc.flee_y;
+        S.cnt[g * 4 + 3] = cf;
+    }
+}
+#endif
+
 // --- host <-> device state conversion (state_io.cu) ------------------------------------------
 // staging area in device memory holding the caller's arrays in the ABI's own layout
 struct StateStage {
@@ -52,7 +90,9 @@ void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev
 // burst-gated rows (bin_step == burst_steps), pair_allpairs.cu: compaction, then all-pairs rows
 void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive = false,
                              bool count_is_zero = false, uint32_t *step_inc = nullptr);
-void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st);
+// detect != 0: the rows also evaluate the prey<-predator detection of step `step` (*step_dev when given)
+void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st, int detect = 0, long long step = 0,
+                          const uint32_t *step_dev = nullptr);
 // burst-gated rows through a cell list (celllist.cu), single large swarm
 struct CellScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
@@ -70,7 +110,8 @@ float sbc_cells_skin(const DevParams &P, float want);
 cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N);
 void sbc_cell_scratch_free(CellScratch &C);
 void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
-void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
+void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st, int detect = 0,
+                           long long step = 0, const uint32_t *step_dev = nullptr);
 // dense pass (every alive row), pair_dense.cu: Morton order + tiled all pairs + split combine
 struct DenseScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
@@ -132,7 +173,7 @@ void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st
 // pred_active: the rows' flee sums are valid (detection ran); zero_count: reset the active-row counter for the next
 // step's compaction once nobody reads it any more; the fish-net kill is evaluated here when a net is present
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count = false);
+                       int pred_active, cudaStream_t st, bool zero_count = false, bool detect_done = false);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,

@@ -25,35 +25,7 @@ detect_rows_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t ste
     const int N = S.N, NP = S.Npred;
     for (int k = warp; k < n_rows; k += n_warps) {
         const int g = list[k];
-        const uint32_t rep = (uint32_t)(g / N);
-        const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
-        const float4 pi = S.pv[g];
-        const float4 *pp = S.pred_pv + (size_t)rep * NP;
-        RowAcc acc;
-        row_acc_clear(acc);
-        for (int jb = lane; 4 * jb < NP; jb += 32) {
-            const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DETECT0 + (uint32_t)jb);
-            const uint32_t r[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int j = 4 * jb + u;
-                if (j < NP) {
-                    const float4 pr = pp[j];
-                    sbc_detect_accumulate(acc, pi.x, pi.y, pr.x, pr.y, (double)r[u] * (1.0 / 4294967296.0), P);
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc.flee_x += __shfl_xor_sync(0xffffffffu, acc.flee_x, o);
-            acc.flee_y += __shfl_xor_sync(0xffffffffu, acc.flee_y, o);
-        }
-        const int cf = __reduce_add_sync(0xffffffffu, acc.c_flee);
-        if (lane == 0) {
-            S.acc[(size_t)g * 8 + 6] = acc.flee_x;
-            S.acc[(size_t)g * 8 + 7] = acc.flee_y;
-            S.cnt[(size_t)g * 4 + 3] = cf;
-        }
+        sbc_detect_row_warp(P, S, (size_t)g, S.pv[g], step, lane);
     }
 }
 
@@ -139,9 +111,9 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
 }  // namespace
 
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count) {
+                       int pred_active, cudaStream_t st, bool zero_count, bool detect_done) {
     const size_t total = (size_t)S.N * S.R;
-    if (pred_active)  // needs the compacted active rows of this step (sbc_launch_compact_rows)
+    if (pred_active && !detect_done)  // needs the compacted active rows of this step (sbc_launch_compact_rows)
         detect_rows_kernel<<<148 * 2, 256, 0, st>>>(P, S, (uint32_t)step, step_dev, S.active_list, S.active_count);
     const int net_kill = (pred_active && S.Npred > 1 && P.pred_kill != 0) ? 1 : 0;
     update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active,
