@@ -13,7 +13,8 @@ one launch of the one-swarm-per-warp kernel. Replicates are independent: ranks s
 Printed JSON line: `value` = agent-steps/s with the state resident in HBM (CUDA events on the
 handle's stream, L2 flushed between timed launches, max over ranks); `e2e` = the same metric through
 the C ABI with HOST buffers (sbc_set_state from pinned memory -> sbc_step -> sbc_get_particles),
-copies inside the timed region; `roofline` = the ensemble kernel against the FP32 peak; `pair_kernel`
+copies inside the timed region, the ensemble cut into four handles on their own streams / host threads so
+that uploads, kernels and downloads of different parts overlap; `roofline` = the ensemble kernel against the FP32 peak; `pair_kernel`
 = the dense all-pairs three-zone kernel (north-star kernel) against the FP32 peak;
 `cpu_baseline` = the CPU oracle (the reference's own translation units when oracle/_ref is
 present) on a bounded sample of the same workload.
@@ -267,24 +268,47 @@ def main():
     pairs = stats1['pairs'] - stats0['pairs']
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in st.items()}
+    # The tanks are independent, so the public API is driven the way a user with host data would drive it: the
+    # ensemble is cut into E2E_PARTS handles, each on its own stream and host thread (ctypes releases the GIL), so
+    # that the upload of one part, the kernel of another and the download of a third overlap. Every bench step
+    # still uploads every tank's state from pinned host memory and downloads every tank's particle rows.
+    # The state every e2e step uploads is the ensemble as the timed region above left it (steady state, timers
+    # included), so that both figures describe the same regime of the dynamics.
+    snap = g.get_state()
+    g.close()
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in snap.items()}
     part = torch.empty((R, N, 7), dtype=torch.float64).pin_memory().numpy()
     alive = torch.empty((R, N), dtype=torch.uint8).pin_memory().numpy()
     import ctypes
     dp, u8p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint8)
+    E2E_PARTS = max(1, min(4, R // 1024))
+    cuts = [R * k // E2E_PARTS for k in range(E2E_PARTS + 1)]
+    parts = []
+    for k in range(E2E_PARTS):
+        r0, r1 = cuts[k], cuts[k + 1]
+        sk = torch.cuda.Stream()
+        hk = Swarm(sp, N, n_replicates=r1 - r0, seed=SEED, replicate_offset=rank * R + r0, device=local, stream=sk.cuda_stream)
+        parts.append((hk, sk, r0, r1))
 
-    def e2e_step(s):
-        g.set_state(**host)                      # H2D: x, y, phi, vproj (doubles, the ABI layout)
-        g.step(s, args.chunk)
-        g._check(g.lib.sbc_get_particles(g.h, part.ctypes.data_as(dp), alive.ctypes.data_as(u8p)))  # D2H
+    def e2e_run(hk, r0, r1, s_first, n):
+        sub = {k: v[r0:r1] for k, v in host.items()}
+        for q in range(n):
+            hk.set_state(**sub)                      # H2D: the full state in the ABI layout (8 doubles, 2 timers, alive)
+            hk.step(s_first + q * args.chunk, args.chunk)
+            hk._check(hk.lib.sbc_get_particles(hk.h, part[r0:r1].ctypes.data_as(dp), alive[r0:r1].ctypes.data_as(u8p)))  # D2H
 
-    for _ in range(2):
-        e2e_step(s_now)
+    def e2e_all(s_first, n):
+        th = [threading.Thread(target=e2e_run, args=(hk, r0, r1, s_first, n)) for hk, _, r0, r1 in parts]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+
+    e2e_all(s_now, 2)
     log('e2e warm-up done')
     barrier()
     t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(s_now + k * args.chunk)
+    e2e_all(s_now, args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
@@ -294,7 +318,8 @@ def main():
     h2d = sum(v.nbytes for v in host.values())
     d2h = part.nbytes + alive.nbytes
     log('e2e done: %.3f s' % e2e_s)
-    g.close()
+    for hk, _, _, _ in parts:
+        hk.close()
 
     out = None
     if rank == 0:
@@ -314,7 +339,10 @@ def main():
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': workload_config(args, N),
             'pair_interactions_per_sec': world * pairs / (ms_max * 1e-3),
-            'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'note': 'four handles on their own streams and host threads: uploads, kernels and downloads of different '
+                            'parts of the ensemble overlap, and no L2 flush separates the launches - which is why this can '
+                            'reach the device-resident figure'},
             'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': {'kernel': 'swarm_warp_kernel' if N <= 32 else 'swarm_block_kernel', 'bound': 'fp32',
                          'achieved': ach, 'peak': peak_fp32, 'unit': 'TFLOP/s', 'frac': ach / peak_fp32,
