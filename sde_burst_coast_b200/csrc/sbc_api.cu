@@ -663,7 +663,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
                     h->active_count_zero = true;   // precondition of a replay, established below
                     int rc = launch_pair_pass(h, 0, false, false, rebuild, h->step_dev, pred_phase ? 1 : 0, 0);
-                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true, true);
+                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true);
                     if (pred_phase) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
                     cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
                     h->active_count_zero = false;  // nothing ran during the capture
@@ -685,7 +685,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                 if (h->use_cells && rebuild) h->host_stats[6]++;
             } else {
                 if (int rc = launch_pair_pass(h, 0, false, false, rebuild, nullptr, pred_phase ? 1 : 0, s)) return rc;
-                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true, true);
+                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true);
                 h->active_count_zero = true;
                 h->host_stats[1]++;
                 if (pred_phase) {

@@ -170,10 +170,10 @@ void sbc_launch_domain_refresh_fused(const DevState &S, DomainScratch &D, void *
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
-// pred_active: the rows' flee sums are valid (detection ran); zero_count: reset the active-row counter for the next
+// pred_active: the rows' flee sums are valid (the pair kernel ran the detection); zero_count: reset the active-row counter for the next
 // step's compaction once nobody reads it any more; the fish-net kill is evaluated here when a net is present
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count = false, bool detect_done = false);
+                       int pred_active, cudaStream_t st, bool zero_count = false);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,

@@ -1,33 +1,15 @@
 // update.cu - per-agent burst-coast update for swarms that do not fit one thread block:
 // ParticleBurstCoast with the burst decision, wall avoidance, Euler step, boundary and burst
-// re-arm (/root/reference/src/agents_dynamics.cpp:150-273), preceded - for rows that start a
-// burst while a predator is present - by the prey<-predator detection of IntCalcPred
-// (agents_interact.cpp:252-292; only rows that read the result evaluate it).
+// re-arm (/root/reference/src/agents_dynamics.cpp:150-273). For rows that start a burst while a
+// predator is present, the prey<-predator detection of IntCalcPred (agents_interact.cpp:252-292; only
+// rows that read the result evaluate it) has been evaluated by the pair kernel that swept
+// the row (sbc_detect_row_warp, sbc_kernels.cuh).
 //
 // One thread per agent, coalesced SoA traffic: 48 B read + 48 B written per agent-step
 // (pv float4, hv float4, force float2, timers uint2) -> HBM-bound.
 #include "sbc_kernels.cuh"
 
 namespace {
-
-// prey<-predator detection (IntCalcPred, agents_interact.cpp:252-292) for the rows that start a burst
-// this step (the only rows that read the result): one warp per active row, a lane takes
-// four predators per Philox block; flee sums and counter go to acc[6..7] / cnt[3] of the row.
-__global__ void __launch_bounds__(256)
-detect_rows_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
-                   const uint32_t *__restrict__ step_dev, const int *__restrict__ list,
-                   const int *__restrict__ count) {
-    const uint32_t step = step_dev ? *step_dev : step_arg;
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    const int n_rows = *count;
-    const int N = S.N, NP = S.Npred;
-    for (int k = warp; k < n_rows; k += n_warps) {
-        const int g = list[k];
-        sbc_detect_row_warp(P, S, (size_t)g, S.pv[g], step, lane);
-    }
-}
 
 __global__ void __launch_bounds__(256)
 update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg, const uint32_t *__restrict__ step_dev,
@@ -111,10 +93,8 @@ update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg
 }  // namespace
 
 void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count, bool detect_done) {
+                       int pred_active, cudaStream_t st, bool zero_count) {
     const size_t total = (size_t)S.N * S.R;
-    if (pred_active && !detect_done)  // needs the compacted active rows of this step (sbc_launch_compact_rows)
-        detect_rows_kernel<<<148 * 2, 256, 0, st>>>(P, S, (uint32_t)step, step_dev, S.active_list, S.active_count);
     const int net_kill = (pred_active && S.Npred > 1 && P.pred_kill != 0) ? 1 : 0;
     update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active,
                                                                   zero_count ? S.active_count : nullptr, net_kill);
