@@ -93,7 +93,8 @@ __global__ void cell_bounds_kernel(const uint32_t *__restrict__ key, const int *
     if (r == n - 1 || key[r + 1] != k) cell_end[k] = r + 1;
 }
 
-constexpr int CELLS_THREADS = 128;
+constexpr int CELLS_THREADS = 128;        // warp-per-row kernel: four rows per block
+constexpr int CELLS_BLOCK_THREADS = 512;  // block-per-row kernel: a dense neighbourhood holds thousands of candidates
 
 // One active row against the agents of its 3 x 3 cell neighbourhood, swept by a GROUP of TPR threads
 // (a warp when the neighbourhood holds a few dozen agents, a whole block when it holds thousands).
@@ -184,15 +185,15 @@ __device__ __forceinline__ void cells_row_store(const DevState &S, int i, const 
 
 // dense neighbourhoods: one block per active row
 template <bool PERIODIC>
-__global__ void __launch_bounds__(CELLS_THREADS)
+__global__ void __launch_bounds__(CELLS_BLOCK_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                   const int *__restrict__ cell_start, const int *__restrict__ cell_end,
                   const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
                   const int *__restrict__ list, const int *__restrict__ count, int detect, uint32_t step_arg,
                   const uint32_t *__restrict__ step_dev) {
     const uint32_t step = step_dev ? *step_dev : step_arg;
-    __shared__ float shf[CELLS_THREADS / 32][6];
-    __shared__ int shi[CELLS_THREADS / 32][3];
+    __shared__ float shf[CELLS_BLOCK_THREADS / 32][6];
+    __shared__ int shi[CELLS_BLOCK_THREADS / 32][3];
     __shared__ int pref[10], first[9];
     const int lane = threadIdx.x & 31;
     const int n_rows = *count;
@@ -202,9 +203,9 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
     for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
         const int i = list[k];  // single swarm on this path: slot index == global index
         RowAcc A;
-        cells_row_sweep<PERIODIC, CELLS_THREADS>(P, S, g, cell_start, cell_end, build_key, sidx, i, threadIdx.x, pref, first, A,
+        cells_row_sweep<PERIODIC, CELLS_BLOCK_THREADS>(P, S, g, cell_start, cell_end, build_key, sidx, i, threadIdx.x, pref, first, A,
                                                  n_amb, n_cand);
-        sbc_block_reduce_row<CELLS_THREADS / 32>(A, shf, shi);
+        sbc_block_reduce_row<CELLS_BLOCK_THREADS / 32>(A, shf, shi);
         if (threadIdx.x == 0) cells_row_store(S, i, A);
         if (detect && threadIdx.x < 32) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane);
         __syncthreads();   // pref / first are rewritten by the next row
@@ -336,9 +337,9 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
     P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, S.active_list, S.active_count, detect, (uint32_t)step, step_dev
     if (P.BC == 0) {
         if (warp_rows) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
-        else pair_cells_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        else pair_cells_kernel<true><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);
     } else {
-        pair_cells_kernel<false><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        pair_cells_kernel<false><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);
     }
 #undef SBC_CELLS_ARGS
 }
