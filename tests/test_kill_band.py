@@ -68,3 +68,23 @@ def test_fp32_decisions_agree_outside_a_quarter_of_the_band(periodic, L, kill_ra
         assert np.array_equal(lt32[clear], lt64[clear]), int((lt32 != lt64)[clear].sum())
         checked += int(clear.sum())
     assert checked > 10000
+
+
+@pytest.mark.parametrize('L', [100.0, 584.0, 10240.0, 14481.546878700494])
+def test_periodic_difference_is_accurate_to_one_rounding(L):
+    """sbc_delta_pbc (emulated above) against the exact minimum image of the same FP32 coordinates: the fold
+    happens before the subtraction, so the result carries one rounding of the difference itself, not an ulp of L."""
+    rng = np.random.default_rng(int(L))
+    xi = (rng.random(500000) * L).astype(f32)
+    xj = (rng.random(500000) * L).astype(f32)
+    xi, xj = np.where(xi >= f32(L), f32(0), xi), np.where(xj >= f32(L), f32(0), xj)
+    got = _delta_pbc32(xi, xj, L).astype(np.float64)
+    r = xj.astype(np.float64) - xi.astype(np.float64)
+    exact = r - L * np.rint(r / L)
+    away_from_tie = np.abs(np.abs(r) - L / 2) > 1e-3 * L          # at |r| = L/2 either image is a minimum image
+    err = np.abs(got - exact)[away_from_tie]
+    bound = 2.0 ** -23 * np.abs(exact[away_from_tie]) + 2.0 ** -24 * np.abs(L - float(f32(L))) + 1e-30
+    assert np.all(err <= bound), float((err / bound).max())
+    # near neighbours (the pairs the zone tests care about) come out EXACT: both coordinates within a factor two
+    close = away_from_tie & (np.abs(exact) < 0.25 * np.minimum(xi, xj).astype(np.float64)) & (np.rint(r / L) == 0)
+    assert close.sum() > 1000 and np.all(got[close] == exact[close])
