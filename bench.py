@@ -16,8 +16,15 @@ the C ABI with HOST buffers (sbc_set_state from pinned memory -> sbc_step -> sbc
 copies inside the timed region, the ensemble cut into four handles on their own streams / host threads so
 that uploads, kernels and downloads of different parts overlap; `roofline` = the ensemble kernel against the FP32 peak; `pair_kernel`
 = the dense all-pairs three-zone kernel (north-star kernel) against the FP32 peak;
+`c5_step` (1 GPU) = one large periodic swarm on the cell-list path against the HBM roofline of SURVEY 8(d);
+`domain_swarm` (N > 1 GPUs) = that swarm decomposed into x-slabs with the peer-memory halo exchange, 1,048,576 agents
+per GPU, plus a small decomposed run whose burst timers are compared bit for bit with the undecomposed swarm;
 `cpu_baseline` = the CPU oracle (the reference's own translation units when oracle/_ref is
 present) on a bounded sample of the same workload.
+
+Numbers that only a profiler can give (DRAM traffic, issue-slot utilisation, instructions per pair) are NOT literals in
+this file: they are read at run time from the ncu summaries committed under profiles/ (named in the output), and
+only used when the summary was taken on the same configuration and its kernel duration agrees with this run's.
 """
 import argparse
 import json
@@ -41,6 +48,7 @@ def log(msg):
     if os.environ.get('RANK', '0') == '0':
         print('[bench %.1fs] %s' % (time.time() - _T0, msg), file=sys.stderr, flush=True)
 FLOP_PER_PAIR_OPEN, FLOP_PER_PAIR_PERIODIC = 13, 21
+STATE_BYTES_ENSEMBLE = 56   # pv 16 + hv 16 (phi, vproj, cos, sin) + force 8 + timers 8 + (alive 1, rounded) per agent
 # Algorithmic FP32 work of one agent-step of the ensemble kernel:
 #   coasting step 16 FLOP, bursting step 58 FLOP, burst start + (N-1) pairs * 13 FLOP;
 #   weights = measured branch fractions of the tank (bursting 0.366, burst start 0.0047).
@@ -50,6 +58,79 @@ def flop_per_agent_step(n_agents):
 
 def fp32_peak_tflops(sm_count, mhz):
     return 2 * 128 * sm_count * mhz * 1e6 / 1e12
+
+
+def read_ncu_summary(name):
+    """Parse profiles/<name> (written by profiles/summarize.py report): a `# config: k=v ...` line, then per captured
+    launch a `## kernel` header and `metric value unit` rows. Returns (config dict, [ {kernel, metrics...} ]) or None."""
+    path = os.path.join(ROOT, 'profiles', name)
+    if not os.path.exists(path):
+        return None
+    cfg, launches, cur = {}, [], None
+    for line in open(path):
+        line = line.rstrip()
+        if line.startswith('# config:'):
+            for tok in line[len('# config:'):].split():
+                if '=' in tok:
+                    k, v = tok.split('=', 1)
+                    cfg[k] = v
+        elif line.startswith('## '):
+            cur = {'kernel': line[3:].strip()}
+            launches.append(cur)
+        elif cur is not None and line and not line.startswith('#'):
+            tok = line.split()
+            if len(tok) >= 2:
+                try:
+                    val = float(tok[1].replace(',', ''))
+                except ValueError:
+                    continue
+                unit = tok[2] if len(tok) > 2 else ''
+                scale = {'ms': 1e-3, 'us': 1e-6, 'ns': 1e-9, 'msecond': 1e-3, 'usecond': 1e-6, 'nsecond': 1e-9, 'second': 1.0,
+                         'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}.get(unit, 1.0)
+                cur[tok[0]] = val * scale
+    return cfg, launches
+
+
+def recorded_profile(name, want_cfg, kernel_substr, my_seconds_per_launch, tol=0.10):
+    """The committed ncu summary `name`, if it belongs to this configuration (every key of want_cfg equal) and its
+    kernel duration agrees with this run's own timing within `tol`. Returns a dict for the JSON line (always names
+    the file and says why it was or was not used)."""
+    got = read_ncu_summary(name)
+    out = {'file': 'profiles/' + name}
+    if got is None:
+        out['used'] = False
+        out['why'] = 'no such summary committed'
+        return out
+    cfg, launches = got
+    out['config'] = cfg
+    mism = [k for k, v in want_cfg.items() if str(cfg.get(k)) != str(v)]
+    rows = [l for l in launches if kernel_substr in l['kernel']]
+    if mism or not rows:
+        out['used'] = False
+        out['why'] = 'summary is for another configuration (%s)' % ', '.join(mism) if mism else 'kernel not in the summary'
+        return out
+    r = rows[0]
+    dur = r.get('gpu__time_duration.sum')
+    out['kernel'] = r['kernel'][:80]
+    out['ncu_seconds_per_launch'] = dur
+    out['bench_seconds_per_launch'] = my_seconds_per_launch
+    ok = dur is not None and my_seconds_per_launch > 0 and abs(dur / my_seconds_per_launch - 1.0) <= tol
+    out['used'] = bool(ok)
+    if not ok:
+        out['why'] = 'ncu kernel duration differs from this run by more than %d %%: the summary is stale' % int(tol * 100)
+        print('[bench] WARNING: %s does not describe the kernel this run timed (%.4g s vs %.4g s per launch)' %
+              (name, dur or float('nan'), my_seconds_per_launch), file=sys.stderr)
+        return out
+    for k_out, k_in in (('dram_bytes_read', 'dram__bytes_read.sum'), ('dram_bytes_write', 'dram__bytes_write.sum'),
+                        ('issue_slot_utilisation', 'smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                        ('warp_instructions', 'smsp__inst_executed.sum'),
+                        ('threads_per_warp_instruction', 'smsp__thread_inst_executed_per_inst_executed.ratio'),
+                        ('fma_pipe_pct', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'),
+                        ('registers_per_thread', 'launch__registers_per_thread'),
+                        ('waves_per_sm', 'launch__waves_per_multiprocessor')):
+        if k_in in r:
+            out[k_out] = r[k_in]
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -193,6 +274,9 @@ def main():
     ap.add_argument('--chunk', type=int, default=1000, help='time steps per bench step')
     ap.add_argument('--pair-n', type=int, default=65536, help='swarm size of the dense pair-kernel measurement')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-c5', action='store_true', help='skip the single-GPU large-swarm leg (c5_step)')
+    ap.add_argument('--no-domain', action='store_true', help='skip the decomposed-swarm leg of a multi-GPU run (domain_swarm)')
+    ap.add_argument('--c5-agents', type=int, default=1 << 20, help='agents per GPU of the large-swarm legs')
     args = ap.parse_args()
 
     from helpers import make_params
@@ -203,7 +287,7 @@ def main():
         return
 
     import faulthandler
-    faulthandler.dump_traceback_later(240, exit=True)   # a hung rank prints where and dies instead of idling
+    faulthandler.dump_traceback_later(420, exit=True)   # a hung rank prints where and dies instead of idling
     local = int(os.environ.get('LOCAL_RANK', '0'))
     sampler = ClockSampler(local)   # nvidia-smi child is started before CUDA / NCCL are initialised
     sampler.start()
@@ -304,6 +388,9 @@ def main():
         for x in th:
             x.join()
 
+    e2e_abi = 'double (reference layout): sbc_set_state / sbc_get_particles'
+    e2e_note = ('%d handles on their own streams and host threads: uploads, kernels and downloads of different parts of the '
+                'ensemble overlap, and no L2 flush separates the launches' % E2E_PARTS)
     e2e_all(s_now, 2)
     log('e2e warm-up done')
     barrier()
@@ -333,6 +420,15 @@ def main():
         peak_fp32 = fp32_peak_tflops(props.multi_processor_count, mhz)
         fl = flop_per_agent_step(N)
         ach = (R * N * args.chunk * args.steps) * fl / (ms * 1e-3) / 1e12   # this rank's kernel
+        kname = 'swarm_warp_kernel' if N <= 32 else 'swarm_block_kernel'
+        prof = recorded_profile('r2_ncu_ensemble_kernel.txt', {'tanks': R, 'agents': N, 'chunk': args.chunk}, kname,
+                                ms * 1e-3 / args.steps)
+        traffic = None
+        if prof.get('used') and 'dram_bytes_read' in prof:
+            traffic = prof['dram_bytes_read'] + prof.get('dram_bytes_write', 0.0)
+            wi = prof.get('warp_instructions')
+            if wi:
+                prof['warp_instructions_per_warp_step'] = wi / (R * N / 32.0 * args.chunk)
         out = {
             'metric': 'agent_steps_per_sec', 'value': value, 'unit': 'agent-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_max / args.steps,
@@ -340,77 +436,266 @@ def main():
             'data': 'synthetic', 'config': workload_config(args, N),
             'pair_interactions_per_sec': world * pairs / (ms_max * 1e-3),
             'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'note': 'four handles on their own streams and host threads: uploads, kernels and downloads of different '
-                            'parts of the ensemble overlap, and no L2 flush separates the launches - which is why this can '
-                            'reach the device-resident figure'},
+                    'abi': e2e_abi, 'parts': E2E_PARTS, 'note': e2e_note},
             'gpu_launches': int(launches), 'clocks': clocks,
-            'roofline': {'kernel': 'swarm_warp_kernel' if N <= 32 else 'swarm_block_kernel', 'bound': 'fp32',
+            'roofline': {'kernel': kname, 'bound': 'fp32',
                          'achieved': ach, 'peak': peak_fp32, 'unit': 'TFLOP/s', 'frac': ach / peak_fp32,
-                         # dram__bytes_read+write of this kernel per launch: profiles/r1_ncu_ensemble_kernel.txt
-                         # (6.47 MB for 4096 tanks -> scaled to the tanks of this run; writes stay in L2)
-                         'traffic': 6.47e6 * R / 4096 * N / 32, 'flop_per_agent_step': fl,
-                         'issue_slot_utilisation_ncu': 0.752, 'warp_instructions_per_warp_step_ncu': 214,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu summary
+                         # named in recorded_profile - null unless that summary is of this configuration and its kernel
+                         # duration agrees with this run's
+                         'traffic': traffic, 'flop_per_agent_step': fl, 'recorded_profile': prof,
+                         'algorithmic_hbm_bytes_per_launch': 2 * STATE_BYTES_ENSEMBLE * R * N,
                          'peak_source': '2*128 lanes*%d SMs*%.0f MHz (MEASURED_PEAKS.json sm_max_mhz)' % (props.multi_processor_count, mhz),
-                         'note': 'state stays in registers for the whole launch (112 B per agent per launch of HBM traffic); the kernel is '
+                         'note': 'state stays in registers for the whole launch (HBM is touched at entry and exit only); the kernel is '
                                  'bound by instruction issue (control, integer, transcendental work), not by FMA throughput'},
         }
         # ---- the north-star kernel: dense all-pairs three-zone pass -------------------------------
         try:
-            out['pair_kernel'] = pair_kernel_roofline(args.pair_n, local, peak_fp32)
+            out['pair_kernel'] = pair_kernel_roofline(args.pair_n, local, peak_fp32, props.multi_processor_count, mhz)
         except Exception as e:  # keep the headline line even if this leg fails
             out['pair_kernel'] = {'error': str(e)}
         log('pair kernel leg done')
+        if world == 1 and not args.no_c5:
+            try:
+                out['c5_step'] = c5_single_gpu(local, peaks.get('hbm_gbs', 6563.2), args.c5_agents)
+            except Exception as e:
+                out['c5_step'] = {'error': str(e)}
+            log('C5 leg done')
         if world == 1 and not args.no_cpu:
             kind = oracle_kind()
             rate, secs, n = cpu_sample(sp, N, 40, args.chunk * 8, kind, 1, SEED)
             out['cpu_baseline'] = {'value': rate, 'unit': 'agent-steps/s', 'cores': 1, 'kind': kind,
                                    'sample': '40 tanks x N=%d x %d steps, single thread, %.1f s' % (N, args.chunk * 8, secs)}
+    if world > 1 and not args.no_domain:
+        # every rank takes part; rank 0 gets the result
+        try:
+            dom = domain_swarm_leg(rank, world, local, args.c5_agents)
+        except Exception as e:
+            dom = {'error': repr(e)} if rank == 0 else None
+        if rank == 0:
+            out['domain_swarm'] = dom
+        log('decomposed-swarm leg done')
+    if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def pair_kernel_roofline(n, device, peak_fp32):
+def pair_kernel_roofline(n, device, peak_fp32, sm_count, mhz):
     """Dense state (every row active, the reference state at s = 1): N(N-1) directed pairs/launch.
     Timed by sbc_bench_pair_pass with CUDA events on the handle's stream (gather + all-pairs kernel +
     split combine; the Hilbert sort of the positions is timed separately as `with_sort`). Cases:
     the probe density of SURVEY section 6 (N=16384 in L=100: ~1960 neighbours inside att_range) in an
-    open and a periodic domain, and the sparse density of config C4 (rho = 0.01: ~12 neighbours)."""
+    open and a periodic domain at N = 65536 / 16384 / 4096 / 1024 (the small sizes also as ensembles of
+    replicates, so that a launch holds enough pairs to time), the sparse density of config C4 (rho = 0.01:
+    ~12 neighbours), and an ALL-NEAR blob (diameter < att_range: every pair executes the full zone arithmetic).
+    `frac` is ALWAYS the 13-FLOP figure of SURVEY 8(d) (a periodic pair costs more - `frac_at_21_flop` - but
+    a far pair leaves after the distance test, so the larger convention can exceed 1)."""
     from helpers import make_params, f32
     from sde_burst_coast_b200.swarm import Swarm
     from sde_burst_coast_b200.params import PAIR_ALL_ROWS
     res = {'bound': 'fp32', 'kernel': 'pair_dense_kernel', 'unit': 'TFLOP/s', 'peak': peak_fp32, 'cases': []}
-    cases = [('open, dense', n, 'burst_coast', dict(BC=-1), 1.6384, FLOP_PER_PAIR_OPEN),
-             ('periodic, dense', n, 'natPred', dict(BC=0, Npred=0), 1.6384, FLOP_PER_PAIR_PERIODIC),
-             ('periodic, sparse (C4 density)', n, 'natPred', dict(BC=0, Npred=0), 0.01, FLOP_PER_PAIR_PERIODIC),
-             ('open, dense', 16384, 'burst_coast', dict(BC=-1), 1.6384, FLOP_PER_PAIR_OPEN)]
-    for name, nn, mode, over, rho, flop in cases:
-        L = float(np.sqrt(nn / rho))
+    dense = 1.6384
+    cases = [('open, dense', n, 1, 'burst_coast', dict(BC=-1), dense, None),
+             ('periodic, dense', n, 1, 'natPred', dict(BC=0, Npred=0), dense, None),
+             ('periodic, sparse (C4 density)', n, 1, 'natPred', dict(BC=0, Npred=0), 0.01, None),
+             ('open, dense', 16384, 1, 'burst_coast', dict(BC=-1), dense, None),
+             ('open, dense', 4096, 1, 'burst_coast', dict(BC=-1), dense, None),
+             ('open, dense', 4096, 16, 'burst_coast', dict(BC=-1), dense, None),
+             ('open, dense', 1024, 1, 'burst_coast', dict(BC=-1), dense, None),
+             ('open, dense', 1024, 64, 'burst_coast', dict(BC=-1), dense, None),
+             ('periodic, dense', 4096, 16, 'natPred', dict(BC=0, Npred=0), dense, None),
+             ('open, all near', 4096, 16, 'burst_coast', dict(BC=-1), None, 0.95)]
+    issue_peak = 128.0 * sm_count * mhz * 1e6     # thread-instructions per second the FP32-class pipes can issue
+    for name, nn, reps, mode, over, rho, blob in cases:
         if over.get('BC') == 0:
+            L = float(np.sqrt(nn / rho))
             over = dict(over, size=L)
         sp, _, _ = make_params(mode, nn, **over)
         rng = np.random.default_rng(SEED)
-        st = dict(x=f32(L * rng.random(nn)), y=f32(L * rng.random(nn)), phi=f32(2 * np.pi * rng.random(nn)),
-                  vproj=np.ones(nn))
-        g = Swarm(sp, nn, device=device)
+        if blob is not None:     # a disc of diameter blob * att_range: no far pair at all
+            L = blob * sp.att_range
+            rad, th = 0.5 * L * np.sqrt(rng.random((reps, nn))), 2 * np.pi * rng.random((reps, nn))
+            x, y = rad * np.cos(th), rad * np.sin(th)
+        else:
+            L = float(np.sqrt(nn / rho))
+            x, y = L * rng.random((reps, nn)), L * rng.random((reps, nn))
+        st = dict(x=f32(x), y=f32(y), phi=f32(2 * np.pi * rng.random((reps, nn))), vproj=np.ones((reps, nn)))
+        g = Swarm(sp, nn, n_replicates=reps, device=device)
         g.set_state(**st)
+        s0 = g.stats()
         ms = g.bench_pair_pass(PAIR_ALL_ROWS, iters=10)
+        s1 = g.stats()
         ms_sort = g.bench_pair_pass(PAIR_ALL_ROWS | 2, iters=10)
-        stats = g.stats()
         g.close()
-        pairs = nn * (nn - 1)
-        ach = pairs * flop / (ms * 1e-3) / 1e12
-        res['cases'].append({'case': name, 'n_agents': nn, 'box': L, 'pairs_per_launch': pairs, 'ms_per_launch': ms,
-                             'ms_per_launch_with_sort': ms_sort, 'pairs_per_sec': pairs / (ms * 1e-3),
-                             'flop_per_pair': flop, 'achieved': ach, 'frac': ach / peak_fp32,
-                             'frac_at_13_flop': pairs * 13 / (ms * 1e-3) / 1e12 / peak_fp32,
-                             'ambiguous_pairs_rechecked_per_launch': stats['ambiguous_pairs'] // 22})
+        pairs = reps * nn * (nn - 1)
+        pps = pairs / (ms * 1e-3)
+        case = {'case': name, 'n_agents': nn, 'replicates': reps, 'box': L, 'pairs_per_launch': pairs, 'ms_per_launch': ms,
+                'ms_per_launch_with_sort': ms_sort, 'pairs_per_sec': pps,
+                'flop_per_pair': FLOP_PER_PAIR_OPEN, 'achieved': pps * FLOP_PER_PAIR_OPEN / 1e12,
+                'frac': pps * FLOP_PER_PAIR_OPEN / 1e12 / peak_fp32,
+                'ambiguous_pairs_rechecked_per_launch': (s1['ambiguous_pairs'] - s0['ambiguous_pairs']) // 11}
+        if over.get('BC') == 0:
+            case['frac_at_21_flop'] = pps * FLOP_PER_PAIR_PERIODIC / 1e12 / peak_fp32
+        # issue-slot fraction of SURVEY 8(d): pairs/s * instructions per pair / (128 * SMs * f); the instruction count
+        # per pair comes from smsp__thread_inst_executed of the committed ncu capture of this very case
+        tag = '%s_n%d_r%d' % (name.split(',')[0] + ('_allnear' if blob else ('_sparse' if rho == 0.01 else '')), nn, reps)
+        prof = recorded_profile('r2_ncu_pair_dense_%s.txt' % tag, {'n': nn, 'replicates': reps}, 'pair_dense', ms * 1e-3, tol=0.25)
+        if prof.get('used') and prof.get('warp_instructions') and prof.get('threads_per_warp_instruction'):
+            ipp = prof['warp_instructions'] * prof['threads_per_warp_instruction'] / pairs
+            case['thread_instructions_per_pair'] = ipp
+            case['issue_slot_fraction'] = pps * ipp / issue_peak
+        if prof.get('used') or 'why' in prof and 'no such' not in prof['why']:
+            case['recorded_profile'] = prof
+        res['cases'].append(case)
     # headline of this object: the open-domain dense case at the requested N
     res.update({k: res['cases'][0][k] for k in ('n_agents', 'pairs_per_sec', 'achieved', 'frac', 'ms_per_launch')})
     res['note'] = ('every directed pair has its distance evaluated; the zone arithmetic runs only for pairs that '
-                   'pass d2 <= att2 (warp-uniform early-out on Hilbert-sorted rows), so sparse states and the '
-                   'periodic 21-FLOP convention can read above 1.0; frac_at_13_flop is the conservative figure')
+                   'pass d2 <= att2 (warp-uniform early-out on Hilbert-sorted rows). frac counts 13 FLOP for every '
+                   'pair, near or far, periodic or not; the all-near case is the only one where all 13 are executed')
+    return res
+
+
+C5_RHO = 0.01          # BASELINE config C5: N = 1,048,576 in L = 10,240
+C5_BYTES_PER_AGENT_STEP = 72   # SURVEY 8(d): read + write of the 36-byte persistent state
+
+
+def c5_state(N, L, seed=SEED):
+    from helpers import f32
+    rng = np.random.default_rng(seed)
+    return dict(x=f32(L * rng.random(N)), y=f32(L * rng.random(N)), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=np.ones(N))
+
+
+def c5_single_gpu(device, hbm_gbs, n_agents, steps=400, warmup=60):
+    """Config C5 on ONE GPU: a periodic swarm of n_agents at rho = 0.01 on the cell-list path, `steps` time steps after
+    the synchronised first burst, CUDA events on the handle's stream. HBM roofline: 72 B per agent-step."""
+    import torch
+    from helpers import base_dict
+    from sde_burst_coast_b200 import params as PP
+    from sde_burst_coast_b200.swarm import Swarm
+    N = int(n_agents)
+    L = float(np.sqrt(N / C5_RHO))
+    sp, _ = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, Npred=0), path=PP.PATH_CELLLIST)
+    ts = torch.cuda.Stream()
+    g = Swarm(sp, N, seed=SEED, device=device, stream=ts.cuda_stream)
+    g.set_state(**c5_state(N, L))
+    with torch.cuda.stream(ts):
+        g.step(0, warmup)
+        ts.synchronize()
+        s0 = g.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ts)
+        g.step(warmup, steps)
+        e1.record(ts)
+        ts.synchronize()
+        ms = e0.elapsed_time(e1)
+        s1 = g.stats()
+    g.close()
+    us = 1e3 * ms / steps
+    gbs = C5_BYTES_PER_AGENT_STEP * N / (us * 1e-6) / 1e9
+    return {'workload': 'C5 single periodic swarm, cell list, rho = 0.01', 'n_agents': N, 'box': L, 'steps': steps,
+            'us_per_step': us, 'agent_steps_per_sec': N * steps / (ms * 1e-3),
+            'pair_candidates_per_sec': (s1['pairs'] - s0['pairs']) / (ms * 1e-3),
+            'cell_builds': s1['cell_builds'] - s0['cell_builds'],
+            'launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'other_launches')) / steps,
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': gbs / hbm_gbs,
+                         'bytes_per_agent_step': C5_BYTES_PER_AGENT_STEP, 'traffic': None,
+                         'note': 'whole step (pair pass + update + amortised cell build) against the HBM figure of the update alone'}}
+
+
+def domain_swarm_leg(rank, world, device, agents_per_gpu, steps=200, warmup=40):
+    """The only multi-GPU path that communicates: ONE periodic swarm cut into x-slabs, one rank per GPU, halo /
+    migration records stored straight into the neighbours' device memory (CUDA IPC over NVLink, sbc_domain_step).
+      (1) parity: a 120,000-agent swarm stepped 130 times decomposed over all ranks vs undecomposed on rank 0 -
+          burst timers bit for bit, positions to FP32 summation order (the body of tests/multi_gpu_worker.py);
+      (2) weak scaling of config C5: agents_per_gpu agents per GPU (L grows with the GPU count, rho = 0.01)."""
+    import torch
+    import torch.distributed as dist
+    from helpers import base_dict, f32
+    from sde_burst_coast_b200 import params as PP
+    from sde_burst_coast_b200.domain import SlabSwarm, PeerTransport, step_distributed
+    from sde_burst_coast_b200.swarm import Swarm
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    res = {}
+    # ---- (1) parity ----------------------------------------------------------------------------------------------
+    N, L, K = 120000, 3400.0, 130
+    sp, _ = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, Npred=0), path=PP.PATH_CELLLIST)
+    rng = np.random.default_rng(99)
+    st = dict(x=f32(L * rng.random(N)), y=f32(L * rng.random(N)), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=4.0 * np.ones(N))
+    slab = SlabSwarm(sp, N, rank, world, seed=7, device=device, stream=ts.cuda_stream)
+    slab.scatter_initial(st)
+    tr = PeerTransport(slab)
+    step_distributed(slab, tr, 0, 40)
+    step_distributed(slab, tr, 40, K - 40)
+    torch.cuda.synchronize()
+    gid, own = slab.owned_state()
+    cnt = slab.counts()
+    gathered = [None] * world
+    dist.gather_object((gid, {k: own[k] for k in ('x', 'y', 'bin_step', 'steps_till_burst')}, cnt), gathered if rank == 0 else None, dst=0)
+    slab.close()
+    if rank == 0:
+        whole = Swarm(sp, N, seed=7, device=device)
+        whole.set_state(**st)
+        whole.step(0, K)
+        ws = whole.get_state()
+        whole.close()
+        seen = np.zeros(N, dtype=np.int32)
+        got = {k: np.zeros(N, dtype=v.dtype) for k, v in gathered[0][1].items()}
+        for g_, o_, _c in gathered:
+            seen[g_] += 1
+            for k, v in o_.items():
+                got[k][g_] = v
+        dx = np.abs(((got['x'] - ws['x'] + L / 2) % L) - L / 2)
+        dy = np.abs(((got['y'] - ws['y'] + L / 2) % L) - L / 2)
+        checks = {'every_agent_owned_once': bool(np.all(seen == 1)),
+                  'steps_till_burst_bit_exact': bool(np.array_equal(got['steps_till_burst'], ws['steps_till_burst'])),
+                  'bin_step_bit_exact': bool(np.array_equal(got['bin_step'], ws['bin_step'])),
+                  'positions_within_1e-3': float(((dx < 1e-3) & (dy < 1e-3)).mean()),
+                  'overflow_events': int(sum(c_['overflow_events'] for _, _, c_ in gathered))}
+        ok = (checks['every_agent_owned_once'] and checks['steps_till_burst_bit_exact'] and checks['bin_step_bit_exact'] and
+              checks['positions_within_1e-3'] > 0.995 and checks['overflow_events'] == 0)
+        res['parity'] = 'ok' if ok else 'FAIL'
+        res['parity_detail'] = dict(checks, n_agents=N, steps=K, against='undecomposed swarm on rank 0 (same seed, global agent ids)')
+    dist.barrier()
+    # ---- (2) C5, weak scaling -------------------------------------------------------------------------------------
+    N = int(agents_per_gpu) * world
+    L = float(np.sqrt(N / C5_RHO))
+    sp, _ = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, Npred=0), path=PP.PATH_CELLLIST)
+    slab = SlabSwarm(sp, N, rank, world, seed=SEED, device=device, stream=ts.cuda_stream)
+    slab.scatter_initial(c5_state(N, L))
+    tr = PeerTransport(slab)
+    step_distributed(slab, tr, 0, warmup)        # includes the synchronised first burst at s = 1
+    dist.barrier()
+    torch.cuda.synchronize()
+    s0 = slab.swarm.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ts)
+    step_distributed(slab, tr, warmup, steps)
+    e1.record(ts)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    s1 = slab.swarm.stats()
+    c = slab.counts()
+    t = torch.tensor([ms, float(s1['pairs'] - s0['pairs']), float(c['owned']), float(c['ghosts']), float(c['overflow_events']),
+                      float(s1['cell_builds'] - s0['cell_builds'])], dtype=torch.float64, device='cuda')
+    allv = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allv, t)
+    slab.close()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    if rank != 0:
+        return None
+    ms_max = max(float(v[0]) for v in allv)
+    res.update({'workload': 'C5 single periodic swarm decomposed into x-slabs, peer-memory halo exchange (no NCCL in the step loop)',
+                'scaling': 'weak', 'n_gpus': world, 'n_agents': N, 'agents_per_gpu': int(agents_per_gpu), 'box': L, 'steps': steps,
+                'value': N * steps / (ms_max * 1e-3), 'unit': 'agent-steps/s', 'us_per_step': 1e3 * ms_max / steps,
+                'us_per_step_per_rank': [1e3 * float(v[0]) / steps for v in allv],
+                'pair_candidates_per_sec': sum(float(v[1]) for v in allv) / (ms_max * 1e-3),
+                'owned_per_rank': [int(v[2]) for v in allv], 'ghosts_per_rank': [int(v[3]) for v in allv],
+                'overflow_events': int(sum(float(v[4]) for v in allv)), 'full_exchanges': int(allv[0][5]),
+                'launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'other_launches')) / steps})
     return res
 
 

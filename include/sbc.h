@@ -218,6 +218,11 @@ int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inb
 int sbc_domain_post(sbc_handle *h);
 int sbc_domain_complete(sbc_handle *h);
 int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps);
+/* How long a wait kernel holds for a neighbour's records (wall clock, default 10 s; the environment variable
+ * SBC_DOMAIN_TIMEOUT_S overrides the default at sbc_domain_config). A wait that runs out does NOT apply the stale
+ * inbox: the handle is marked failed and sbc_domain_step / sbc_domain_complete return SBC_ERR_STATE. The same
+ * status reports record-buffer overflows and header mismatches between neighbours. */
+int sbc_domain_set_timeout(sbc_handle *h, double seconds);
 
 /* ---- micro-benchmark hook: time `iters` launches of the dense pair pass with CUDA events on
  * the handle's stream; returns mean milliseconds per launch in *ms. */

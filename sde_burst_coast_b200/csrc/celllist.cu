@@ -188,15 +188,17 @@ template <bool PERIODIC>
 __global__ void __launch_bounds__(CELLS_BLOCK_THREADS)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                   const int *__restrict__ cell_start, const int *__restrict__ cell_end,
-                  const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
-                  const int *__restrict__ list, const int *__restrict__ count, int detect, uint32_t step_arg,
-                  const uint32_t *__restrict__ step_dev) {
-    const uint32_t step = step_dev ? *step_dev : step_arg;
+                  const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
+    const uint32_t step = SA.step_dev ? *SA.step_dev : SA.step;
+    const int par = (int)(step & 1u);
+    const int *__restrict__ list = S.active_list[par];
     __shared__ float shf[CELLS_BLOCK_THREADS / 32][6];
     __shared__ int shi[CELLS_BLOCK_THREADS / 32][3];
     __shared__ int pref[10], first[9];
+    __shared__ float s_flee[2];
+    __shared__ int s_cflee;
     const int lane = threadIdx.x & 31;
-    const int n_rows = *count;
+    const int n_rows = S.active_count[par];
     const CellGeom g = *geom;
     unsigned n_amb = 0;
     unsigned long long n_cand = 0;
@@ -206,13 +208,28 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
         cells_row_sweep<PERIODIC, CELLS_BLOCK_THREADS>(P, S, g, cell_start, cell_end, build_key, sidx, i, threadIdx.x, pref, first, A,
                                                  n_amb, n_cand);
         sbc_block_reduce_row<CELLS_BLOCK_THREADS / 32>(A, shf, shi);
-        if (threadIdx.x == 0) cells_row_store(S, i, A);
-        if (detect && threadIdx.x < 32) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane);
+        if (SA.pred_active) {   // IntCalcPred of this row by the last warp (thread 0 holds the zone sums)
+            if (threadIdx.x >= CELLS_BLOCK_THREADS - 32) {
+                RowAcc F;
+                row_acc_clear(F);
+                sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane, F);
+                if (lane == 0) { s_flee[0] = F.flee_x; s_flee[1] = F.flee_y; s_cflee = F.c_flee; }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            cells_row_store(S, i, A);
+            if (SA.finish) {
+                if (SA.pred_active) { A.flee_x = s_flee[0]; A.flee_y = s_flee[1]; A.c_flee = s_cflee; }
+                sbc_finish_row(P, S, (size_t)i, A, step, SA);
+            }
+        }
         __syncthreads();   // pref / first are rewritten by the next row
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (threadIdx.x == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);  // candidates examined on this path
+    sbc_step_close(S, SA, step);
 }
 
 // sparse neighbourhoods (a few dozen candidates): one WARP per active row, reduction by shuffles only
@@ -220,14 +237,14 @@ template <bool PERIODIC>
 __global__ void __launch_bounds__(CELLS_THREADS)
 pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
                        const int *__restrict__ cell_start, const int *__restrict__ cell_end,
-                       const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
-                       const int *__restrict__ list, const int *__restrict__ count, int detect, uint32_t step_arg,
-                       const uint32_t *__restrict__ step_dev) {
-    const uint32_t step = step_dev ? *step_dev : step_arg;
+                       const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
+    const uint32_t step = SA.step_dev ? *SA.step_dev : SA.step;
+    const int par = (int)(step & 1u);
+    const int *__restrict__ list = S.active_list[par];
     constexpr int WPB = CELLS_THREADS / 32;
     __shared__ int pref[WPB][10], first[WPB][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_rows = *count;
+    const int n_rows = S.active_count[par];
     const CellGeom g = *geom;
     unsigned n_amb = 0;
     unsigned long long n_cand = 0;
@@ -247,11 +264,14 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
         }
         if (lane == 0) cells_row_store(S, i, A);
         __syncwarp();
-        if (detect) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane);
+        if (SA.pred_active) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane, A);
+        if (SA.finish && lane == 0) sbc_finish_row(P, S, (size_t)i, A, step, SA);
+        __syncwarp();
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (lane == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);
+    sbc_step_close(S, SA, step);
 }
 
 }  // namespace
@@ -325,18 +345,22 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
     cell_bounds_kernel<<<blocks, 256, 0, st>>>(C.key_out, C.idx_out, N, dead_key, C.cell_start, C.cell_end);
 }
 
-// active rows must have been compacted into S.active_list / S.active_count (sbc_launch_compact_rows)
-void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st, int detect, long long step,
-                           const uint32_t *step_dev) {
-    const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
-    const int blocks = (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
-    // mean number of candidates a row meets in its nine cells decides between a warp and a block per row
+// mean number of candidates a row meets in its nine cells decides between a warp and a block per row
+static bool cells_warp_rows(const DevParams &P, const DevState &S, const CellScratch &C) {
     const double per_row = 9.0 * (double)S.N / (double)(C.ncells > 0 ? C.ncells : 1);
-    const bool warp_rows = P.BC == 0 && per_row < 512.0;
-#define SBC_CELLS_ARGS \
-    P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, S.active_list, S.active_count, detect, (uint32_t)step, step_dev
+    return P.BC == 0 && per_row < 512.0;
+}
+int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C) {
+    return (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
+}
+
+// the rows are S.active_list[step & 1] (kept by the steps themselves, or compacted by sbc_launch_compact_rows)
+void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, const StepArgs &A, cudaStream_t st) {
+    const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
+    const int blocks = sbc_pair_cells_blocks(P, S, C);
+#define SBC_CELLS_ARGS P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, A
     if (P.BC == 0) {
-        if (warp_rows) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        if (cells_warp_rows(P, S, C)) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
         else pair_cells_kernel<true><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);
     } else {
         pair_cells_kernel<false><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);

@@ -34,9 +34,10 @@ namespace {
 
 struct __align__(16) DomRecord {  // 64 bytes
     float4 pv;
-    float4 hv;
+    float2 hv;       // phi, vproj
     float2 force;
-    uint2 timers;
+    uint32_t tm;     // packed burst timers
+    uint32_t spare[3];
     uint32_t gid;
     uint32_t pad[3];
 };
@@ -189,7 +190,7 @@ dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float 
                 if (p < max_mig) {
                     r.hv = S.hv[g];
                     r.force = S.force[g];
-                    r.timers = S.timers[g];
+                    r.tm = S.tm[g];
                     (left ? send_l : send_r)[1 + p] = r;
                     // the agent now lives on the neighbour: free the slot (ordered push on the stack)
                     S.alive[g] = 0;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(256)
 dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a, const DomRecord *__restrict__ recv_b,
                   const DomRecord *__restrict__ sent_l, const DomRecord *__restrict__ sent_r, int max_mig, int max_halo,
                   int *__restrict__ ctl, const int *__restrict__ free_stack, int *__restrict__ halo_list) {
+    if (ctl[21]) return;   // the wait for these records timed out: leave the slots alone
     const int ma = recv_a ? (int)recv_a[0].gid : 0, mb = recv_b ? (int)recv_b[0].gid : 0;
     const int ha = recv_a ? (int)recv_a[0].pad[0] : 0, hb = recv_b ? (int)recv_b[0].pad[0] : 0;
     const int sl = sent_l ? (int)sent_l[0].gid : 0, sr = sent_r ? (int)sent_r[0].gid : 0;
@@ -247,7 +249,7 @@ dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a,
         S.pv_dead[g] = r.pv;
         S.hv[g] = r.hv;
         S.force[g] = r.force;
-        S.timers[g] = r.timers;
+        S.tm[g] = r.tm;
         S.alive[g] = 1;
         if (S.gid) S.gid[g] = r.gid;
     }
@@ -266,7 +268,10 @@ dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a,
         if (S.gid) S.gid[g] = gid;
     }
 }
-__global__ void dom_commit_kernel(int *ctl) { ctl[0] = max(ctl[0] - ctl[7], 0); }
+__global__ void dom_commit_kernel(int *ctl) {
+    if (ctl[21]) return;
+    ctl[0] = max(ctl[0] - ctl[7], 0);
+}
 
 // refresh exchange: current {x, y, vx, vy} of the slots listed by the last full exchange, same order
 __global__ void __launch_bounds__(256)
@@ -288,6 +293,7 @@ dom_refresh_pack_kernel(DevState S, const int *__restrict__ ctl, const int *__re
 __global__ void __launch_bounds__(256)
 dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
                           const DomRecord *recv_b0, const DomRecord *recv_b1) {
+    if (ctl[21]) return;
     const int par = ctl[16] & 1;   // buffers by parity of the exchange count (the same pointer twice without an inbox)
     const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
     const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
@@ -342,19 +348,33 @@ __global__ void dom_flag_kernel(volatile int *flag_l0, volatile int *flag_l1, vo
     __threadfence_system();
     ctl[16] = epoch;
 }
-__global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
-                                const volatile int *flag_b1, int *ctl) {
-    const int epoch = ctl[16], par = epoch & 1;
-    const volatile int *fa = par ? flag_a1 : flag_a0, *fb = par ? flag_b1 : flag_b0;
-    const long long t0 = clock64();
+// Wall-clock nanoseconds (independent of the SM clock).
+__device__ __forceinline__ unsigned long long dom_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Hold until both flags show `epoch`. A neighbour that does not answer within timeout_ns is reported, not waited
+// for: ctl[21] (sticky) marks the handle's exchange as failed, every later unpack is skipped and the host
+// side turns the mark into SBC_ERR_STATE (sbc_domain_step / sbc_domain_complete).
+__device__ __forceinline__ bool dom_wait_flags(const volatile int *fa, const volatile int *fb, int epoch,
+                                               unsigned long long timeout_ns) {
+    const unsigned long long t0 = dom_now_ns();
     while (*fa < epoch || *fb < epoch) {
-        if (clock64() - t0 > 6000000000ll) {   // ~3 s: a neighbour is gone; report instead of hanging the GPU
-            ctl[6] += 1000;
-            break;
-        }
-        __nanosleep(200);
+        if (dom_now_ns() - t0 > timeout_ns) return false;
+        __nanosleep(100);
     }
     __threadfence_system();
+    return true;
+}
+__global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
+                                const volatile int *flag_b1, int *ctl, unsigned long long timeout_ns) {
+    const int epoch = ctl[16], par = epoch & 1;
+    if (ctl[21]) return;   // an earlier exchange already failed
+    if (!dom_wait_flags(par ? flag_a1 : flag_a0, par ? flag_b1 : flag_b0, epoch, timeout_ns)) {
+        ctl[6] += 1000;
+        ctl[21] = 1;
+    }
 }
 
 // One refresh exchange in two kernels (the graph-replayed form): SEND gathers the listed positions straight into
@@ -393,21 +413,22 @@ dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list,
 __global__ void __launch_bounds__(256)
 dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
                         const DomRecord *recv_b0, const DomRecord *recv_b1, const volatile int *flag_a0,
-                        const volatile int *flag_a1, const volatile int *flag_b0, const volatile int *flag_b1) {
+                        const volatile int *flag_a1, const volatile int *flag_b0, const volatile int *flag_b1,
+                        unsigned long long timeout_ns) {
     const int epoch = ctl[16], par = epoch & 1;
+    __shared__ int arrived;
     if (threadIdx.x == 0) {
-        const volatile int *fa = par ? flag_a1 : flag_a0, *fb = par ? flag_b1 : flag_b0;
-        const long long t0 = clock64();
-        while (*fa < epoch || *fb < epoch) {
-            if (clock64() - t0 > 6000000000ll) {   // ~3 s: a neighbour is gone; report instead of hanging the GPU
-                if (blockIdx.x == 0) ctl[6] += 1000;
-                break;
-            }
-            __nanosleep(100);
+        // ctl[21] of an earlier failure is read through volatile: block 0 of THIS launch may be setting it right now,
+        // which is fine - every block runs its own wait and comes to the same verdict
+        arrived = (*(volatile int *)(ctl + 21) == 0) &&
+                  dom_wait_flags(par ? flag_a1 : flag_a0, par ? flag_b1 : flag_b0, epoch, timeout_ns);
+        if (!arrived && blockIdx.x == 0 && *(volatile int *)(ctl + 21) == 0) {
+            ctl[6] += 1000;
+            *(volatile int *)(ctl + 21) = 1;
         }
-        __threadfence_system();
     }
     __syncthreads();
+    if (!arrived) return;   // stale or partial records are never unpacked
     const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
     const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,6 +479,7 @@ dom_init_stack_kernel(DevState S, int own_cap, int *free_stack, int *ctl) {
     if (threadIdx.x == 0) {
         ctl[0] = top_s;
         ctl[6] = 0;
+        ctl[21] = 0;
     }
 }
 
@@ -543,22 +565,24 @@ void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *se
                                         D.max_halo);
     dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], D.ctl);
 }
-void sbc_launch_domain_refresh_fused(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
-                                     int *const flag_l[2], int *const flag_r[2], const void *const recv_a[2],
-                                     const void *const recv_b[2], int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
+void sbc_launch_domain_refresh_send(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
+                                    int *const flag_l[2], int *const flag_r[2], cudaStream_t st) {
     const int cap = D.max_halo + D.max_mig;
     unsigned *ticket = reinterpret_cast<unsigned *>(D.ctl + 20);
     dom_refresh_send_kernel<<<(cap + 255) / 256, 256, 0, st>>>(
         S, D.ctl, D.halo_list, cap, static_cast<DomRecord *>(dst_l[0]), static_cast<DomRecord *>(dst_l[1]),
         static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), flag_l[0], flag_l[1], flag_r[0], flag_r[1], ticket);
+}
+void sbc_launch_domain_refresh_recv(const DevState &S, DomainScratch &D, const void *const recv_a[2], const void *const recv_b[2],
+                                    int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
     const int ghost_cap = S.N - D.own_cap;
     dom_refresh_recv_kernel<<<(max(ghost_cap, 1) + 255) / 256, 256, 0, st>>>(
         S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a[0]), static_cast<const DomRecord *>(recv_a[1]),
         static_cast<const DomRecord *>(recv_b[0]), static_cast<const DomRecord *>(recv_b[1]), flag_a[0], flag_a[1], flag_b[0],
-        flag_b[1]);
+        flag_b[1], D.timeout_ns);
 }
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
-    dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl);
+    dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl, D.timeout_ns);
 }
 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st) {

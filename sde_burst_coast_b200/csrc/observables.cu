@@ -13,13 +13,14 @@ observables_kernel(const __grid_constant__ DevParams P, DevState S, double *out)
     __shared__ double sh[8][OT / 32];
     const int rep = blockIdx.x, N = S.N;
     const float4 *pv = S.pv + (size_t)rep * N;
-    const float4 *hv = S.hv + (size_t)rep * N;
+    const float2 *hv = S.hv + (size_t)rep * N;
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // n, ux, uy, x, y, vx, vy, speed ; nnd separately
     double nnd = 0;
     for (int i = threadIdx.x; i < N; i += OT) {
         const float4 p = pv[i];
         if (p.x != p.x) continue;
-        const float c = hv[i].z, s = hv[i].w;
+        float c, s;
+        sincosf(hv[i].x, &s, &c);
         acc[0] += 1; acc[1] += c; acc[2] += s; acc[3] += p.x; acc[4] += p.y;
         acc[5] += p.z; acc[6] += p.w; acc[7] += sqrtf(p.z * p.z + p.w * p.w);
         float best = -1.f;

@@ -97,17 +97,22 @@ pred_spawn_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step
     }
 }
 
-__device__ __forceinline__ void kill_agent(DevState &S, size_t g, float4 p) {
-    S.alive[g] = 0;
-    S.pv_dead[g] = p;
-    const float qnan = __int_as_float(0x7fc00000);
-    S.pv[g] = make_float4(qnan, qnan, p.z, p.w);
-}
-
-// MoveFishNet (agents_dynamics.cpp:616-624): one block per replicate
+// MoveFishNet (agents_dynamics.cpp:616-624): one block per replicate; block 0 first applies the kills the step's
+// kernels recorded (FishNetKill was evaluated per agent against the moved net, sbc_update_agent): S.pv holds the
+// positions after this step's update here
 __global__ void __launch_bounds__(PT)
 net_move_kernel(const __grid_constant__ DevParams P, DevState S) {
     const int rep = blockIdx.x;
+    if (blockIdx.x == 0 && S.kill_count) {
+        const int nk = *S.kill_count;
+        for (int k = threadIdx.x; k < nk; k += PT) {
+            const size_t g = (size_t)S.kill_list[k];
+            sbc_kill_agent(S, g, S.pv[g]);
+            atomicAdd(S.n_dead + g / S.N, 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *S.kill_count = 0;
+    }
     float4 *pp = S.pred_pv + (size_t)rep * S.Npred;
     float *pphi = S.pred_phi + (size_t)rep * S.Npred;
     for (int j = threadIdx.x; j < S.Npred; j += PT) {
@@ -124,7 +129,8 @@ net_move_kernel(const __grid_constant__ DevParams P, DevState S) {
 __global__ void __launch_bounds__(PT)
 pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
                       const uint32_t *__restrict__ step_dev) {
-    const uint32_t step = step_dev ? *step_dev : step_arg;
+    // behind the step's two kernels the device-resident step index has already moved on
+    const uint32_t step = step_dev ? *step_dev - 1u : step_arg;
     __shared__ double sh[PT / 32];
     __shared__ unsigned long long s_key[PT / 32];
     __shared__ float s_p[4];
@@ -211,11 +217,12 @@ pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t 
                     die = kc.within;
                 } else if (kc.cand) {
                     const double pk = sbc_kill_probability(p.x, p.y, px, py, (int)n_sensed, total, S.kill_eff, P);
-                    const uint4 q = sbc_draw(P, rep, (uint32_t)i, step, SBC_SLOT_DECISION);
+                    const uint32_t id = S.gid ? S.gid[(size_t)rep * N + i] : (uint32_t)i;
+                    const uint4 q = sbc_draw(P, rep, id, step, SBC_SLOT_DECISION);
                     die = pk > (double)q.w * (1.0 / 4294967296.0);
                 }
                 if (die) {
-                    kill_agent(S, (size_t)rep * N + i, p);
+                    sbc_kill_agent(S, (size_t)rep * N + i, p);
                     killed++;
                 }
             }

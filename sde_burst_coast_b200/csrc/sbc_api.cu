@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -42,7 +43,15 @@ struct sbc_handle {
     int cells_local_max_age;       // what this handle's own agents allow (domain mode: the ranks agree on the minimum)
     int dom_period;                // domain mode: agreed number of refresh exchanges between two full ones
     bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
-    bool active_count_zero;        // S.active_count is known to be zero (left so by the last update kernel)
+    // multi-kernel path bookkeeping
+    bool list_valid;               // S.active_list[list_step & 1] holds the rows (bin_step == burst_steps) of step list_step
+    int64_t list_step;
+    bool nxt_synced;               // S.pv_nxt carries the dead / free marks of S.pv (needed before a step writes into it)
+    bool cs_valid;                 // S.cs == (cos, sin)(phi): true after set_state / ensemble launches, false after multi-kernel steps
+    int pv_parity;                 // which of the two position buffers S.pv currently is (captured graphs bake the pointers)
+    bool recv_pending;             // domain mode: the neighbours' refresh records of the last step are not in the ghosts yet
+    cudaStream_t stream2;          // second branch of a captured step (rows kernel next to the bulk update)
+    cudaEvent_t ev_fork, ev_join;
     double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
     // exchange through peer memory: own inbox [flags 256 B | from-left p0 | from-left p1 | from-right p0 | from-right p1]
@@ -52,11 +61,8 @@ struct sbc_handle {
     std::vector<void *> ipc_opened;
     unsigned char *send_own[2];            // this rank's send buffers (left, right)
     int dom_epoch;
-    cudaGraphExec_t refresh_graph;         // one refresh exchange (pack, push, flag, wait, unpack)
-    bool refresh_graph_ok;
-    // CUDA graphs of one multi-kernel step ([0] before, [1] during the predator phase)
-    cudaGraphExec_t step_graph[4];   // [2 * rebuild + pred_phase]
-    bool step_graph_ok[4];
+    // CUDA graphs of one multi-kernel step, keyed by MK_* bits | position-buffer parity
+    std::map<unsigned, cudaGraphExec_t> graphs;
     uint32_t *step_dev;
     int64_t step_dev_value;
     bool use_graphs;
@@ -78,6 +84,16 @@ static std::string g_create_error;
 static int fail(sbc_handle *h, int code, const std::string &msg) {
     if (h) h->err = msg; else g_create_error = msg;
     return code;
+}
+
+// Captured graphs bake device pointers (S.gid, dom.ctl, halo_list, inbox addresses of the peers ...) by value:
+// whoever changes one of them throws the graphs away; they are re-captured on the next step.
+static void invalidate_graphs(sbc_handle *h) {
+    if (h->graphs.empty()) return;
+    cudaStreamSynchronize(h->stream);   // a replay may still be in flight
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    h->graphs.clear();
+    h->step_dev_value = -1;
 }
 
 static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
@@ -140,6 +156,10 @@ static void fill_dev_params(const sbc_params &p, uint64_t seed, uint64_t rep_off
     P.d_kill_range = p.kill_range;
     P.burst_steps = p.burst_steps;
     P.max_steps = (uint32_t)(5 / (p.burst_rate * p.dt));
+    P.tm_bits = 1;
+    while ((1ull << P.tm_bits) <= (unsigned long long)p.burst_steps) P.tm_bits++;
+    P.tm_mask = (1u << P.tm_bits) - 1u;
+    P.tm_stb_max = (P.tm_bits >= 32) ? 0u : (uint32_t)((1ull << (32 - P.tm_bits)) - 1ull);
     P.BC = p.BC;
     P.N_confu = p.N_confu;
     P.pred_kill = p.pred_kill;
@@ -200,6 +220,14 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     if (p->BC < -1 || p->BC > 6) return fail(nullptr, SBC_ERR_INVALID, "sbc_create: BC must be -1..6");
     if ((size_t)n_agents * (size_t)n_replicates > (size_t)1 << 30)
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: more than 2^30 agents per handle");
+    {   // both burst timers of an agent share one 32-bit word (bin_step <= burst_steps, steps_till_burst <= max_steps + 1)
+        unsigned bits = 1;
+        while ((1ull << bits) <= (unsigned long long)p->burst_steps) bits++;
+        const double max_stb = 5.0 / (p->burst_rate * p->dt) + 2.0;
+        if (bits >= 31 || max_stb >= (double)(1ull << (32 - bits)))
+            return fail(nullptr, SBC_ERR_INVALID, "sbc_create: burst_steps and 5/(burst_rate dt) do not fit one 32-bit timer word "
+                                                  "(dt far below 1e-5)");
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -233,7 +261,14 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->dom_period = 0;
     h->dom_last_full = true;
     h->v0_max = 1.0;
-    for (int k = 0; k < 4; k++) h->step_graph_ok[k] = false;
+    h->list_valid = false;
+    h->list_step = -1;
+    h->nxt_synced = false;
+    h->cs_valid = true;
+    h->pv_parity = 0;
+    h->recv_pending = false;
+    h->stream2 = nullptr;
+    h->ev_fork = h->ev_join = nullptr;
     h->step_dev = nullptr;
     h->step_dev_value = -1;
     h->use_graphs = getenv("SBC_NO_GRAPHS") == nullptr;
@@ -251,14 +286,24 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     const size_t npt = (size_t)(n_pred > 0 ? n_pred : 1) * n_replicates;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    {   // the rows kernel of a captured step runs on its own branch, ahead of the bulk update in the block scheduler
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        ok = ok && cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && dev_alloc(&S.pv, total) == cudaSuccess && dev_alloc(&S.pv_dead, total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.pv_nxt, total) == cudaSuccess && dev_alloc(&S.cs, total) == cudaSuccess;
     ok = ok && dev_alloc(&S.hv, total) == cudaSuccess && dev_alloc(&S.force, total) == cudaSuccess;
-    ok = ok && dev_alloc(&S.timers, total) == cudaSuccess && dev_alloc(&S.alive, total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.tm, total + 4) == cudaSuccess && dev_alloc(&S.alive, total + 4) == cudaSuccess;
+    if (n_pred > 1) ok = ok && dev_alloc(&S.kill_list, total) == cudaSuccess && dev_alloc(&S.kill_count, 1) == cudaSuccess;
     ok = ok && dev_alloc(&S.acc, total * 8) == cudaSuccess && dev_alloc(&S.cnt, total * 4) == cudaSuccess;
     ok = ok && dev_alloc(&S.pred_pv, npt) == cudaSuccess && dev_alloc(&S.pred_phi, npt) == cudaSuccess;
     ok = ok && dev_alloc(&S.n_dead, (size_t)n_replicates) == cudaSuccess;
     ok = ok && dev_alloc(&S.pred_spawned, (size_t)n_replicates) == cudaSuccess;
-    ok = ok && dev_alloc(&S.active_list, total) == cudaSuccess && dev_alloc(&S.active_count, 1) == cudaSuccess;
+    ok = ok && dev_alloc(&S.active_list[0], total) == cudaSuccess && dev_alloc(&S.active_list[1], total) == cudaSuccess;
+    ok = ok && dev_alloc(&S.active_count, 4) == cudaSuccess;
     ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
     uint32_t *geo_dev = nullptr;
     ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
@@ -280,6 +325,8 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     }
     cudaMemcpy(geo_dev, h->geo_host.data(), h->geo_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaMemset(S.stats, 0, 8 * sizeof(unsigned long long));
+    cudaMemset(S.active_count, 0, 4 * sizeof(int));
+    if (S.kill_count) cudaMemset(S.kill_count, 0, sizeof(int));
     cudaMemset(S.n_dead, 0, n_replicates * sizeof(int));
     cudaMemset(S.pred_spawned, 0, n_replicates * sizeof(int));
     cudaMemset(S.acc, 0, total * 8 * sizeof(float));
@@ -312,19 +359,22 @@ int sbc_destroy(sbc_handle *h) {
     if (!h) return SBC_OK;
     cudaSetDevice(h->device);
     DevState &S = h->S;
-    cudaFree(S.pv); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.force); cudaFree(S.timers);
+    cudaFree(S.pv); cudaFree(S.pv_nxt); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.cs); cudaFree(S.force); cudaFree(S.tm);
+    cudaFree(S.kill_list); cudaFree(S.kill_count);
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
-    cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list); cudaFree(S.active_count);
+    cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_count);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
-    if (h->refresh_graph_ok) cudaGraphExecDestroy(h->refresh_graph);
+    for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
     cudaFree(h->S.gid);
-    for (int k = 0; k < 4; k++) if (h->step_graph_ok[k]) cudaGraphExecDestroy(h->step_graph[k]);
     cudaFree(h->step_dev);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
@@ -370,25 +420,40 @@ static float cells_skin_for(const sbc_handle *h) {
 }
 static void set_cells_max_age(sbc_handle *h) {
     const double vmax = std::fmax(h->v0_max, std::fmax(h->hp.soc_strength, h->hp.env_strength) / h->hp.beta);
-    const double per_step = (h->hp.BC == 0 ? 1.0 : 3.0) * vmax * h->hp.dt * 1.01;
+    // BC 1 puts an agent that left the box at 0.9999 L / 0.0001 (agents_dynamics.cpp:300-356): a jump of up to 1e-4 L
+    const double clamp_jump = (h->hp.BC == 1) ? 1.0001e-4 * h->hp.sizeL : 0.0;
+    const double per_step = (h->hp.BC == 0 ? 1.0 : 3.0) * vmax * h->hp.dt * 1.01 + clamp_jump;
     const double k = (h->cells.skin > 0.f && per_step > 0) ? std::floor(0.5 * h->cells.skin / per_step) : 0.0;
     h->cells_local_max_age = (int)std::fmin(std::fmax(k, 0.0), 64.0);
     // a decomposed swarm rebuilds on every rank in the same step: the agreed period, never more than is safe here
     h->cells_max_age = h->dom.enabled ? std::min(h->cells_local_max_age, h->dom_period) : h->cells_local_max_age;
 }
 
-// one three-zone pass over the current state: dense (all rows) or burst-gated rows
-static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false,
-                            bool rebuild_cells = true, uint32_t *step_inc = nullptr, int detect = 0, long long step = 0) {
-    if (all_rows && h->P.voronoi) {  // Delaunay-filtered candidates: every alive row through the rows kernel
-        sbc_launch_compact_rows(h->P, h->S, true, h->stream, true, h->active_count_zero);
-        h->active_count_zero = false;
-        sbc_launch_pair_rows(h->P, h->S, h->stream);
-        h->host_stats[0]++;
-        h->host_stats[7] += 2;
-        return SBC_OK;
+static int ensure_cells(sbc_handle *h) {
+    if (h->cells_ready) return SBC_OK;
+    // skin: a fifth of att_range when the box allows; one build then serves several steps
+    h->cells.skin = cells_skin_for(h);
+    cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
+    if (e != cudaSuccess) {
+        sbc_cell_scratch_free(h->cells);
+        return fail(h, SBC_ERR_NOMEM, std::string("cell list scratch: ") + cudaGetErrorString(e));
     }
-    if (all_rows) {
+    h->cells_ready = true;
+    set_cells_max_age(h);
+    return SBC_OK;
+}
+
+// slots that can hold an agent the update moves: a slab's owned range, otherwise everything
+static int n_update_of(const sbc_handle *h) {
+    return h->dom.enabled ? h->dom.own_cap : (int)((size_t)h->S.N * h->S.R);
+}
+
+// one three-zone pass over the current state WITHOUT advancing it (test hook, dense-pass benchmark): dense (all rows)
+// or the burst-gated rows, compacted into list 0
+static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false) {
+    StepArgs A = {};
+    A.n_update = n_update_of(h);
+    if (all_rows && !h->P.voronoi) {
         if (int rc = ensure_dense(h)) return rc;
         if (resort || !h->dense.sorted_valid) {
             sbc_launch_dense_sort(h->P, h->S, h->dense, h->stream);
@@ -398,34 +463,25 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
         h->host_stats[0]++;
         h->host_stats[7] += 2;
         h->host_stats[3] += (unsigned long long)h->S.R * h->S.N * (unsigned long long)(h->S.N - 1);
-    } else {
-        sbc_launch_compact_rows(h->P, h->S, clear_inactive, h->stream, false, h->active_count_zero, step_inc);
-        h->active_count_zero = false;
-        h->host_stats[7] += clear_inactive ? 2 : 1;
-        if (h->use_cells) {
-            if (!h->cells_ready) {
-                // skin: a fifth of att_range when the box allows; one build then serves several steps
-                h->cells.skin = cells_skin_for(h);
-                cudaError_t e = sbc_cell_scratch_alloc(h->cells, h->P, h->S.N);
-                if (e != cudaSuccess) {
-                    sbc_cell_scratch_free(h->cells);
-                    return fail(h, SBC_ERR_NOMEM, std::string("cell list scratch: ") + cudaGetErrorString(e));
-                }
-                h->cells_ready = true;
-                set_cells_max_age(h);
-            }
-            if (rebuild_cells) {
-                sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
-                h->host_stats[6]++;
-                h->host_stats[7] += 4;
-            }
-            sbc_launch_pair_cells(h->P, h->S, h->cells, h->stream, detect, step, step_inc);
-            h->host_stats[7] += 1;
-        } else {
-            sbc_launch_pair_rows(h->P, h->S, h->stream, detect, step, step_inc);
-        }
-        h->host_stats[0]++;
+        return SBC_OK;
     }
+    // rows into list 0 (the kernels pick the list by the parity of the step: 0 here)
+    h->list_valid = false;
+    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 4 * sizeof(int), h->stream));
+    const bool every = all_rows != 0;   // Delaunay-filtered candidates: every alive row through the rows kernel
+    sbc_launch_compact_rows(h->P, h->S, every || clear_inactive, every, A.n_update, h->S.active_list[0], h->S.active_count, h->stream);
+    h->host_stats[7] += (every || clear_inactive) ? 2 : 1;
+    if (h->use_cells && !every) {
+        if (int rc = ensure_cells(h)) return rc;
+        sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
+        h->host_stats[6]++;
+        h->host_stats[7] += 4;
+        sbc_launch_pair_cells(h->P, h->S, h->cells, A, h->stream);
+        h->host_stats[7] += 1;
+    } else {
+        sbc_launch_pair_rows(h->P, h->S, A, h->stream);
+    }
+    h->host_stats[0]++;
     return SBC_OK;
 }
 
@@ -469,12 +525,20 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
         mask |= SBC_ST_ALIVE;
         SBC_CUDA(cudaMemcpyAsync(h->stage.al, alive, total, cudaMemcpyHostToDevice, h->stream));
     }
-    sbc_launch_pack_state(S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
+    if (h->state_set && !h->cs_valid) sbc_launch_refresh_cs(S, h->stream);   // a partial upload keeps the other fields
+    sbc_launch_pack_state(h->P, S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
     h->dense.sorted_valid = false;
     h->cells_valid = false;
+    h->list_valid = false;
+    h->nxt_synced = true;    // the pack kernel writes both position buffers
+    h->cs_valid = true;
+    h->recv_pending = false;
     if (vproj)
         for (size_t g = 0; g < total; g++)
             if (vproj[g] > h->v0_max) h->v0_max = vproj[g];
+    // a decomposed swarm rebuilds on every rank in the same step: a new state voids the agreed period (every exchange is
+    // a full one until sbc_domain_rebuild_period is called again on all ranks)
+    if (h->dom.enabled) h->dom_period = 0;
     if (h->cells_ready || h->dom.enabled) set_cells_max_age(h);
     if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
     h->host_stats[7]++;
@@ -499,7 +563,7 @@ int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, d
     if (bin_step) mask |= SBC_ST_BIN;
     if (stb) mask |= SBC_ST_STB;
     if (alive) mask |= SBC_ST_ALIVE;
-    sbc_launch_unpack_state(S, h->stage, mask, h->stream);
+    sbc_launch_unpack_state(h->P, S, h->stage, mask, h->stream);
     h->host_stats[7]++;
     for (int k = 0; k < 8; k++)
         if (ddst[k]) SBC_CUDA(cudaMemcpyAsync(ddst[k], h->stage.d[k], total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -581,6 +645,119 @@ int sbc_get_counts(sbc_handle *h, int32_t *n_alive, int32_t *n_dead) {
     return SBC_OK;
 }
 
+// ---- one step of the multi-kernel path ---------------------------------------------------------------------------
+// Step() (swarmdyn.cpp:143-204) as TWO independent kernels - the rows kernel (agents that start a burst: pair sweep,
+// detection, their own update) and the bulk update of everybody else - plus, when due, the cell build in front, the
+// predator move + kill behind, and in a decomposed swarm the receipt of the neighbours' records in front of the rows
+// kernel and the dispatch of this rank's records at the end. Replayed from a CUDA graph whose two branches run side
+// by side; the graph bakes pointers, so there is one per combination of the MK_* bits and the position-buffer parity.
+enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_RECV = 8, MK_SEND = 16 };
+
+static void domain_launch_refresh_send(sbc_handle *h, const DevState &S, cudaStream_t st);
+static void domain_launch_refresh_recv(sbc_handle *h, const DevState &S, cudaStream_t st);
+
+static int ensure_rows(sbc_handle *h, int64_t s) {
+    if (h->list_valid && h->list_step == s) return SBC_OK;
+    const int par = (int)(s & 1);
+    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 4 * sizeof(int), h->stream));
+    sbc_launch_compact_rows(h->P, h->S, false, false, n_update_of(h), h->S.active_list[par], h->S.active_count + par, h->stream);
+    h->host_stats[7] += 1;
+    h->list_valid = true;
+    h->list_step = s;
+    return SBC_OK;
+}
+
+// the kernels of one step in launch order; aux == nullptr: everything on `main`
+static void record_step(sbc_handle *h, unsigned key, const StepArgs &A, cudaStream_t main, cudaStream_t aux) {
+    DevState &S = h->S;
+    if (key & MK_REBUILD) sbc_launch_cell_build(h->P, S, h->cells, main);
+    cudaStream_t rows_st = main;
+    if (aux) {
+        cudaEventRecord(h->ev_fork, main);
+        cudaStreamWaitEvent(aux, h->ev_fork, 0);
+        rows_st = aux;
+    }
+    if (key & MK_RECV) domain_launch_refresh_recv(h, S, rows_st);   // ghosts of this step's start-of-step positions
+    if (h->use_cells) sbc_launch_pair_cells(h->P, S, h->cells, A, rows_st);
+    else sbc_launch_pair_rows(h->P, S, A, rows_st);
+    sbc_launch_update_bulk(h->P, S, A, main);
+    if (aux) {
+        cudaEventRecord(h->ev_join, aux);
+        cudaStreamWaitEvent(main, h->ev_join, 0);
+    }
+    DevState Sn = S;   // what the host sees after the step: the new positions are the current ones
+    Sn.pv = S.pv_nxt;
+    Sn.pv_nxt = S.pv;
+    if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
+    if (key & MK_SEND) domain_launch_refresh_send(h, Sn, main);
+}
+
+static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, bool send_after) {
+    DevState &S = h->S;
+    const bool injected = S.inj_social || S.inj_dir || S.inj_k;
+    if (h->use_cells) if (int rc = ensure_cells(h)) return rc;
+    // cell order: rebuilt when stale (Verlet skin used up) and after a state change
+    const bool rebuild = h->use_cells && (!h->cells_valid || h->cells_age > h->cells_max_age);
+    if (int rc = ensure_rows(h, s)) return rc;
+    if (!h->nxt_synced) {
+        SBC_CUDA(cudaMemcpyAsync(S.pv_nxt, S.pv, (size_t)S.N * S.R * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+        h->nxt_synced = true;
+    }
+    const unsigned key = (h->pv_parity ? MK_PARITY : 0) | (rebuild ? MK_REBUILD : 0) | (pred_phase ? MK_PRED : 0) |
+                         (recv_first ? MK_RECV : 0) | (send_after ? MK_SEND : 0);
+    StepArgs A = {};
+    A.step = (uint32_t)s;
+    A.n_update = n_update_of(h);
+    A.pred_active = pred_phase ? 1 : 0;
+    A.net_kill = (pred_phase && S.Npred > 1 && h->hp.pred_kill != 0) ? 1 : 0;
+    A.finish = 1;
+    A.ticket_total = (unsigned)(sbc_update_bulk_blocks(A.n_update) +
+                                (h->use_cells ? sbc_pair_cells_blocks(h->P, S, h->cells) : sbc_pair_rows_blocks(S)));
+    const bool graphable = h->use_graphs && !injected && !S.flags && h->stream != nullptr && h->stream != cudaStreamLegacy &&
+                           h->stream != cudaStreamPerThread;  // the default streams cannot be captured
+    if (graphable) {
+        if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
+        if (h->step_dev_value != s) {   // the step index lives on the device and is advanced by the step itself
+            const uint32_t sv = (uint32_t)s;
+            SBC_CUDA(cudaMemcpyAsync(h->step_dev, &sv, sizeof(sv), cudaMemcpyHostToDevice, h->stream));
+            SBC_CUDA(cudaStreamSynchronize(h->stream));  // sv is a stack variable
+        }
+        auto it = h->graphs.find(key);
+        if (it == h->graphs.end()) {
+            cudaGraph_t graph;
+            A.step_dev = h->step_dev;
+            SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            record_step(h, key, A, h->stream, h->stream2);
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
+            cudaGraphExec_t exec;
+            ce = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+            it = h->graphs.emplace(key, exec).first;
+        }
+        SBC_CUDA(cudaGraphLaunch(it->second, h->stream));
+        h->step_dev_value = s + 1;
+    } else {
+        record_step(h, key, A, h->stream, nullptr);
+        h->step_dev_value = -1;
+    }
+    // the new positions are the current ones from here on
+    std::swap(S.pv, S.pv_nxt);
+    h->pv_parity ^= 1;
+    h->list_step = s + 1;    // the step's kernels appended the agents they re-armed
+    h->cs_valid = false;
+    h->dense.sorted_valid = false;
+    h->host_stats[0]++;
+    h->host_stats[1]++;
+    h->host_stats[7] += (rebuild ? 4 : 0) + (pred_phase ? 1 : 0) + (recv_first ? 1 : 0) + (send_after ? 1 : 0);
+    if (h->use_cells) {
+        if (rebuild) { h->cells_valid = true; h->cells_age = 0; h->host_stats[6]++; }
+        h->cells_age++;   // the agents moved once more since the build
+    }
+    return SBC_OK;
+}
+
 int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     if (!h || n_steps < 0) return SBC_ERR_INVALID;
     if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_step: no state");
@@ -610,6 +787,10 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     }
     const bool cluster_path = block_path && cluster_ok;
     if (block_path) {
+        if (!h->cs_valid) {   // steps on the multi-kernel path do not maintain the cached heading vector
+            sbc_launch_refresh_cs(S, h->stream);
+            h->cs_valid = true;
+        }
         // one launch covers up to 2^31 steps; split only to keep the step counter in 32 bits
         int64_t done = 0;
         while (done < n_steps) {
@@ -621,6 +802,9 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             done += chunk;
             h->host_stats[2]++;
         }
+        h->list_valid = false;    // timers changed behind the row lists' back
+        h->nxt_synced = false;    // kills and moves went to S.pv only
+        h->dense.sorted_valid = false;
     } else {
         for (int64_t s = s_first; s < s_first + n_steps; s++) {
             const bool pred_phase = S.Npred > 0 && (double)s >= p.pred_time / dt;
@@ -630,73 +814,12 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             }
             if (S.Npred > 1 && pred_phase) {  // swarmdyn.cpp:160-170
                 const int since = (int)s - (int)(p.pred_time / dt);
-                int needed;
-                if (p.pred_speed0 > 0) needed = (int)(p.sizeL / 2 / (p.pred_speed0 * dt));
-                else needed = (int)((p.sim_time - p.trans_time) / 4 / dt);
                 if (needed > 0 && since % needed == 0) {
                     sbc_launch_pred_spawn(h->P, S, s, 1, h->stream);
                     h->host_stats[7]++;
                 }
             }
-            // the fixed part of the step (compaction, pair pass, update, predator move + kill) is
-            // replayed from a CUDA graph: one launch instead of ~6-15. The step index then lives in
-            // device memory and is advanced by the graph's last node.
-            // cell order: rebuilt when stale (Verlet skin used up), after a state change, and always in
-            // decomposed mode (ghosts change every step)
-            const bool rebuild = !h->use_cells || !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
-            const int gk = (pred_phase ? 1 : 0) + (rebuild ? 2 : 0);
-            const bool graphable = h->use_graphs && !injected && !S.flags && (!h->use_cells || h->cells_ready) &&
-                                   h->stream != nullptr && h->stream != cudaStreamLegacy &&
-                                   h->stream != cudaStreamPerThread;  // the default streams cannot be captured
-            if (graphable) {
-                if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
-                // the device holds s - 1 between steps: the graph's first kernel (the compaction) advances it
-                if (h->step_dev_value != s) {
-                    const uint32_t sv = (uint32_t)s - 1u;
-                    SBC_CUDA(cudaMemcpyAsync(h->step_dev, &sv, sizeof(sv), cudaMemcpyHostToDevice, h->stream));
-                    SBC_CUDA(cudaStreamSynchronize(h->stream));  // sv is a stack variable
-                }
-                if (!h->step_graph_ok[gk]) {
-                    cudaGraph_t graph;
-                    unsigned long long keep[8];
-                    std::memcpy(keep, h->host_stats, sizeof(keep));  // the capture pass launches nothing
-                    SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-                    h->active_count_zero = true;   // precondition of a replay, established below
-                    int rc = launch_pair_pass(h, 0, false, false, rebuild, h->step_dev, pred_phase ? 1 : 0, 0);
-                    sbc_launch_update(h->P, S, 0, h->step_dev, pred_phase ? 1 : 0, h->stream, true);
-                    if (pred_phase) sbc_launch_pred_move_kill(h->P, S, 0, h->step_dev, h->stream);
-                    cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-                    h->active_count_zero = false;  // nothing ran during the capture
-                    if (rc) return rc;
-                    if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
-                    ce = cudaGraphInstantiate(&h->step_graph[gk], graph, 0);
-                    cudaGraphDestroy(graph);
-                    if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
-                    h->step_graph_ok[gk] = true;
-                    std::memcpy(h->host_stats, keep, sizeof(keep));
-                }
-                if (!h->active_count_zero) SBC_CUDA(cudaMemsetAsync(S.active_count, 0, sizeof(int), h->stream));
-                SBC_CUDA(cudaGraphLaunch(h->step_graph[gk], h->stream));
-                h->active_count_zero = true;   // the graph's update kernel left the counter at zero
-                h->step_dev_value = s + 1;
-                h->host_stats[0]++;
-                h->host_stats[1]++;
-                h->host_stats[7] += (h->use_cells ? (rebuild ? 7 : 3) : 2) + (pred_phase ? 1 : 0);
-                if (h->use_cells && rebuild) h->host_stats[6]++;
-            } else {
-                if (int rc = launch_pair_pass(h, 0, false, false, rebuild, nullptr, pred_phase ? 1 : 0, s)) return rc;
-                sbc_launch_update(h->P, S, s, nullptr, pred_phase ? 1 : 0, h->stream, true);
-                h->active_count_zero = true;
-                h->host_stats[1]++;
-                if (pred_phase) {
-                    sbc_launch_pred_move_kill(h->P, S, s, nullptr, h->stream);
-                    h->host_stats[7]++;
-                }
-            }
-            if (h->use_cells) {
-                if (rebuild) { h->cells_valid = true; h->cells_age = 0; }
-                h->cells_age++;   // the agents moved once more since the build
-            }
+            if (int rc = mk_step(h, s, pred_phase, false, false)) return rc;
         }
     }
     h->host_stats[5] += (unsigned long long)n_steps * (unsigned long long)S.N * (unsigned long long)S.R;
@@ -891,7 +1014,10 @@ int sbc_set_global_ids(sbc_handle *h, const uint32_t *gid) {
     if (!h || !gid) return SBC_ERR_INVALID;
     SBC_CUDA(cudaSetDevice(h->device));
     const size_t total = (size_t)h->S.N * h->S.R;
-    if (!h->S.gid) SBC_CUDA(dev_alloc(&h->S.gid, total));
+    if (!h->S.gid) {
+        invalidate_graphs(h);   // graphs captured so far keyed the Philox draws by slot (S.gid == nullptr baked in)
+        SBC_CUDA(dev_alloc(&h->S.gid, total));
+    }
     SBC_CUDA(cudaMemcpyAsync(h->S.gid, gid, total * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     return SBC_OK;
@@ -910,8 +1036,17 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: slabs narrower than the halo");
     if (!h->use_cells) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: needs the cell-list path");
     SBC_CUDA(cudaSetDevice(h->device));
+    if (h->inbox)   // the neighbours hold this handle's exchange count and buffer sizes: they cannot be reset from here
+        return fail(h, SBC_ERR_STATE, "sbc_domain_config: the inbox of this handle is already exported; create a new handle");
+    invalidate_graphs(h);
+    const unsigned long long keep_timeout = h->dom.timeout_ns;
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity, max_migrants, max_halo);
+    h->dom.timeout_ns = keep_timeout;
+    if (const char *ev = std::getenv("SBC_DOMAIN_TIMEOUT_S")) {
+        const double sec = std::atof(ev);
+        if (sec > 0) h->dom.timeout_ns = (unsigned long long)(sec * 1e9);
+    }
     if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
     h->dom.enabled = true;
     h->dom.halo = (float)halo;
@@ -946,6 +1081,8 @@ int sbc_domain_pack(sbc_handle *h, void *send_left_dev, void *send_right_dev) {
     h->dom_last_full = !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
     if (h->dom_last_full) {
         sbc_launch_domain_pack(h->P, h->S, h->dom, send_left_dev, send_right_dev, h->stream);
+        h->nxt_synced = false;   // leavers' slots were freed in S.pv only
+        h->list_valid = false;
         h->host_stats[7] += 3;
     } else {
         sbc_launch_domain_refresh_pack(h->S, h->dom, send_left_dev, send_right_dev, h->stream);
@@ -1005,6 +1142,7 @@ int sbc_domain_open_peer(sbc_handle *h, const void *ipc_handle_64, void **mapped
 int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inbox_dev) {
     if (!h || !h->dom.enabled || !h->inbox) return SBC_ERR_STATE;
     if (!left_inbox_dev || !right_inbox_dev) return SBC_ERR_INVALID;
+    invalidate_graphs(h);
     h->peer_l = static_cast<unsigned char *>(left_inbox_dev);
     h->peer_r = static_cast<unsigned char *>(right_inbox_dev);
     return SBC_OK;
@@ -1031,6 +1169,28 @@ static void domain_launch_refresh_unpack(sbc_handle *h) {
                                      inbox_buf(h->inbox, h->inbox_buf_bytes, 0, 1), inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 0),
                                      inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 1), h->stream);
 }
+// Turn what the exchange kernels recorded into a status: a wait that timed out (ctl[21]), record overflows and
+// header mismatches (ctl[6]) all mean that some rank stepped with wrong ghosts.
+static int domain_check(sbc_handle *h, const char *where) {
+    int v[24];
+    SBC_CUDA(cudaMemcpyAsync(v, h->dom.ctl, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (v[21])
+        return fail(h, SBC_ERR_STATE, std::string(where) + ": a neighbour's records did not arrive within " +
+                                          std::to_string(h->dom.timeout_ns / 1000000ull) + " ms (sbc_domain_set_timeout); "
+                                          "the exchange was not applied, the state of this handle is no longer valid");
+    if (v[6])
+        return fail(h, SBC_ERR_STATE, std::string(where) + ": " + std::to_string(v[6]) +
+                                          " exchange events overflowed a record buffer or disagreed with the neighbour's header");
+    return SBC_OK;
+}
+int sbc_domain_set_timeout(sbc_handle *h, double seconds) {
+    if (!h || !(seconds > 0)) return SBC_ERR_INVALID;
+    invalidate_graphs(h);   // the limit is a kernel argument of the captured wait
+    h->dom.timeout_ns = (unsigned long long)(seconds * 1e9);
+    return SBC_OK;
+}
+
 int sbc_domain_post(sbc_handle *h) {
     if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
     if (int rc = sbc_domain_pack(h, h->send_own[0], h->send_own[1])) return rc;
@@ -1039,7 +1199,7 @@ int sbc_domain_post(sbc_handle *h) {
     h->host_stats[7] += 2;
     return SBC_OK;
 }
-int sbc_domain_complete(sbc_handle *h) {
+static int domain_complete_async(sbc_handle *h) {
     if (!h || !h->dom.enabled || !h->inbox) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
     domain_launch_wait(h);
@@ -1053,52 +1213,75 @@ int sbc_domain_complete(sbc_handle *h) {
     return sbc_domain_unpack(h, inbox_buf(h->inbox, h->inbox_buf_bytes, 0, par), inbox_buf(h->inbox, h->inbox_buf_bytes, 1, par),
                              h->send_own[0], h->send_own[1]);
 }
+int sbc_domain_complete(sbc_handle *h) {
+    if (int rc = domain_complete_async(h)) return rc;
+    // several handles of one process on one stream (loop-back tests) post first and complete afterwards: the status of
+    // this handle is known once its own wait ran, which the stream order guarantees here
+    return domain_check(h, "sbc_domain_complete");
+}
+// the two halves of a refresh exchange (domain.cu): SEND gathers the listed positions straight into the neighbours'
+// inboxes and publishes the exchange count; RECV holds until both neighbours' counts arrived and scatters their
+// records into the ghost slots
+static void domain_peer_pointers(sbc_handle *h, void *dst_l[2], void *dst_r[2], int *flag_l[2], int *flag_r[2],
+                                 const void *recv_a[2], const void *recv_b[2], int *flag_a[2], int *flag_b[2]) {
+    for (int par = 0; par < 2; par++) {
+        dst_l[par] = inbox_buf(h->peer_l, h->inbox_buf_bytes, 1, par);
+        dst_r[par] = inbox_buf(h->peer_r, h->inbox_buf_bytes, 0, par);
+        flag_l[par] = inbox_flag(h->peer_l, 1, par);
+        flag_r[par] = inbox_flag(h->peer_r, 0, par);
+        recv_a[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 0, par);
+        recv_b[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 1, par);
+        flag_a[par] = inbox_flag(h->inbox, 0, par);
+        flag_b[par] = inbox_flag(h->inbox, 1, par);
+    }
+}
+static void domain_launch_refresh_send(sbc_handle *h, const DevState &S, cudaStream_t st) {
+    void *dst_l[2], *dst_r[2];
+    const void *recv_a[2], *recv_b[2];
+    int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
+    domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
+    sbc_launch_domain_refresh_send(S, h->dom, dst_l, dst_r, flag_l, flag_r, st);
+}
+static void domain_launch_refresh_recv(sbc_handle *h, const DevState &S, cudaStream_t st) {
+    void *dst_l[2], *dst_r[2];
+    const void *recv_a[2], *recv_b[2];
+    int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
+    domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
+    sbc_launch_domain_refresh_recv(S, h->dom, recv_a, recv_b, flag_a, flag_b, st);
+}
+
+// n_steps x { step ; exchange }. A refresh exchange is part of the step's graph: this rank's records leave at the end
+// of step s, the neighbours' records are awaited at the START of step s + 1 on the rows kernel's branch - the bulk
+// update of step s + 1 (which reads no ghost) runs meanwhile, so a rank that is a little ahead does not idle.
 int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
-    const bool graphable = h->use_graphs && h->stream != nullptr && h->stream != cudaStreamLegacy &&
-                           h->stream != cudaStreamPerThread;
+    if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_domain_step: no state");
+    SBC_CUDA(cudaSetDevice(h->device));
     for (int64_t s = s_first; s < s_first + n_steps; s++) {
-        if (int rc = sbc_step(h, s, 1)) return rc;
-        const bool full = !h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age;
-        if (full || !graphable) {
+        if (int rc = ensure_cells(h)) return rc;
+        // the exchange behind this step is a full one when the NEXT step rebuilds the cell order
+        const bool rebuild_now = !h->cells_valid || h->cells_age > h->cells_max_age;
+        const int age_after = (rebuild_now ? 0 : h->cells_age) + 1;
+        const bool full_after = age_after > h->cells_max_age;
+        if (int rc = mk_step(h, s, false, h->recv_pending, !full_after)) return rc;
+        h->recv_pending = false;
+        if (full_after) {
             if (int rc = sbc_domain_post(h)) return rc;
-            if (int rc = sbc_domain_complete(h)) return rc;
-            continue;
+            if (int rc = domain_complete_async(h)) return rc;
+        } else {
+            h->dom_last_full = false;
+            h->dom_epoch++;
+            h->recv_pending = true;
         }
-        // refresh exchange: refresh-pack, push, flag, wait, refresh-unpack replayed as one graph launch
-        if (!h->refresh_graph_ok) {
-            cudaGraph_t graph;
-            SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            {   // two kernels: gather + store into the neighbours' inboxes + publish | wait + scatter into the ghosts
-                void *dst_l[2], *dst_r[2];
-                const void *recv_a[2], *recv_b[2];
-                int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
-                for (int par = 0; par < 2; par++) {
-                    dst_l[par] = inbox_buf(h->peer_l, h->inbox_buf_bytes, 1, par);
-                    dst_r[par] = inbox_buf(h->peer_r, h->inbox_buf_bytes, 0, par);
-                    flag_l[par] = inbox_flag(h->peer_l, 1, par);
-                    flag_r[par] = inbox_flag(h->peer_r, 0, par);
-                    recv_a[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 0, par);
-                    recv_b[par] = inbox_buf(h->inbox, h->inbox_buf_bytes, 1, par);
-                    flag_a[par] = inbox_flag(h->inbox, 0, par);
-                    flag_b[par] = inbox_flag(h->inbox, 1, par);
-                }
-                sbc_launch_domain_refresh_fused(h->S, h->dom, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b,
-                                                h->stream);
-            }
-            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("exchange graph capture: ") + cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&h->refresh_graph, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("exchange graph instantiate: ") + cudaGetErrorString(ce));
-            h->refresh_graph_ok = true;
-        }
-        SBC_CUDA(cudaGraphLaunch(h->refresh_graph, h->stream));
-        h->dom_last_full = false;
-        h->dom_epoch++;
-        h->host_stats[7] += 2;
     }
-    return SBC_OK;
+    if (h->recv_pending) {   // leave the handle with its ghosts in place
+        domain_launch_refresh_recv(h, h->S, h->stream);
+        h->host_stats[7]++;
+        h->recv_pending = false;
+    }
+    h->host_stats[5] += (unsigned long long)n_steps * (unsigned long long)h->S.N;
+    // one host synchronisation per call (not per step): did every exchange of this call arrive and fit?
+    return domain_check(h, "sbc_domain_step");
 }
 
 int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_dev, const void *sent_left_dev,
@@ -1108,6 +1291,8 @@ int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_
     if (h->dom_last_full) {
         sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
         h->cells_valid = false;   // slots changed hands: the next step rebuilds the cell order
+        h->nxt_synced = false;    // ... and both position buffers and the row list start afresh
+        h->list_valid = false;
         h->host_stats[7] += 2;
     } else {
         sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_a_dev, recv_b_dev, recv_b_dev, h->stream);

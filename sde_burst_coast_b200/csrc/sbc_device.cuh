@@ -33,6 +33,7 @@ struct DevParams {
     double dL, d_rep, d_alg, d_att, d_prob_social, d_flee_range, d_kill_range;
     // integers
     uint32_t burst_steps, max_steps;
+    uint32_t tm_bits, tm_mask, tm_stb_max;   // packed burst timers: bin_step in the low tm_bits, steps_till_burst above
     int32_t BC, N_confu, pred_kill, pred_move;
     int32_t has_alg_zone;          // alg_range > rep_range
     int32_t voronoi;               // neighbour candidates = Delaunay edges (InteractionVoronoiF2F) instead of all agents
@@ -49,6 +50,14 @@ struct AgentState {
     float fx, fy;
     uint32_t bin_step, stb;
 };
+
+// burst timers of one agent in one word (agents.h:50-51: bin_step <= burst_steps, steps_till_burst <= max_steps + 1;
+// the split is chosen at sbc_create so that both fit)
+__device__ __forceinline__ uint32_t sbc_tm_pack(uint32_t bin_step, uint32_t stb, const DevParams &P) {
+    return bin_step | (min(stb, P.tm_stb_max) << P.tm_bits);
+}
+__device__ __forceinline__ uint32_t sbc_tm_bin(uint32_t t, const DevParams &P) { return t & P.tm_mask; }
+__device__ __forceinline__ uint32_t sbc_tm_stb(uint32_t t, const DevParams &P) { return t >> P.tm_bits; }
 
 // accumulators of one row (agents_interact.cpp:211-225, :286-290)
 struct RowAcc {

@@ -3,13 +3,19 @@
 #include "sbc_device.cuh"
 
 // device-resident state of one handle: R replicates x N agents, index g = r*N + i
+// Persistent state of the multi-kernel path: pv 16 + hv 8 + force 8 + tm 4 = 36 B per agent. The
+// ensemble kernels additionally keep the heading vector `cs` they turn incrementally, so that a launch can be split
+// anywhere bit-exactly; the multi-kernel path derives it from phi and never touches `cs`.
 struct DevState {
     int N, R, Npred;
     float4 *pv;        // {x, y, vx, vy}; x = y = NaN for dead agents (their last pv is in pv_dead)
+    float4 *pv_nxt;    // multi-kernel path: the update writes the next positions here while the pair pass still reads
+                       // pv (start-of-step positions); the host swaps the two after every step
     float4 *pv_dead;   // last {x,y,vx,vy} of killed agents
-    float4 *hv;        // {phi, vproj, cos phi, sin phi}
+    float2 *hv;        // {phi, vproj}
+    float2 *cs;        // {cos phi, sin phi} as the ensemble kernels carry it (valid when the host says so)
     float2 *force;     // {fx, fy}
-    uint2 *timers;     // {bin_step, steps_till_burst}
+    uint32_t *tm;      // burst timers, sbc_tm_pack(bin_step, steps_till_burst)
     uint8_t *alive;
     uint32_t *gid;     // global agent id per slot (domain decomposition), nullptr = slot index
     // row accumulators written by the pair pass, consumed by the update
@@ -21,25 +27,72 @@ struct DevState {
     int *n_dead;       // [R]
     int *pred_spawned; // [R]
     const double *kill_eff; // [N+1] effective kill rate for n sensed prey (PredKill, agents_dynamics.cpp:879-884)
+    int *kill_list;         // [R*N] agents the fish net caught during the running step (only with a net), kill_count [1]
+    int *kill_count;
     // decisions
     const uint32_t *geo; // inter-burst table, max_steps entries
     double *inj_social;  // [R*N] or nullptr
     float *inj_dir;
     uint32_t *inj_k;
     uint8_t *flags;      // [R*N] branch flags OR-ed over steps (test hook), may be nullptr
-    // scratch of the burst-gated pair pass
-    int *active_list;    // [R*N]
-    int *active_count;   // [1]
+    // burst-gated rows: two lists by parity of the step. The rows of step s are in active_list[s & 1] - written by the
+    // update of step s - 1 (the agents it re-armed), or by the compaction kernel after a state change
+    int *active_list[2];   // [R*N] each
+    int *active_count;     // [2] + [2] block ticket of the step's two kernels
     // counters
     unsigned long long *stats; // [8] see sbc_get_stats
+};
+
+// per-launch constants of one multi-kernel step (rows kernel + update_bulk_kernel, update.cu)
+struct StepArgs {
+    uint32_t step;           // step index when step_dev == nullptr
+    uint32_t *step_dev;      // device-resident step index of a graph-replayed step (advanced by sbc_step_close)
+    int n_update;            // slots [0, n_update) can hold agents that are updated (a slab: own_cap; otherwise R * N)
+    int net_kill;            // a fish net is present and kills: FishNetKill is evaluated per agent
+    int pred_active;         // predator phase: burst-starting rows evaluate IntCalcPred
+    int finish;              // rows kernel: 1 = update the rows (a step), 0 = only write acc / cnt (test hook)
+    unsigned ticket_total;   // blocks of the step's two kernels together; 0 = nobody closes the step
 };
 
 // prey<-predator detection (IntCalcPred, /root/reference/src/agents_interact.cpp:252-292) of ONE burst-starting row by
 // ONE warp: a lane takes four predators per Philox block; flee sums and counter go to acc[6..7] / cnt[3] of the row.
 // Called by the pair kernels right after the row's zone sums (every lane of the warp must call it).
 #ifdef __CUDACC__
+// agent state in / out of the SoA arrays. `with_cs`: the ensemble kernels' cached heading vector
+__device__ __forceinline__ void sbc_load_agent(const DevParams &P, const DevState &S, size_t g, AgentState &a, bool with_cs) {
+    const float4 p = S.pv[g];
+    const float2 h = S.hv[g];
+    const float2 f = S.force[g];
+    const uint32_t t = S.tm[g];
+    a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
+    a.phi = h.x; a.vproj = h.y;
+    if (with_cs) {
+        const float2 c = S.cs[g];
+        a.cu = c.x; a.su = c.y;
+    }
+    a.fx = f.x; a.fy = f.y;
+    a.bin_step = sbc_tm_bin(t, P); a.stb = sbc_tm_stb(t, P);
+}
+__device__ __forceinline__ void sbc_store_agent(const DevParams &P, const DevState &S, size_t g, const AgentState &a, bool with_cs) {
+    S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
+    S.hv[g] = make_float2(a.phi, a.vproj);
+    if (with_cs) S.cs[g] = make_float2(a.cu, a.su);
+    S.force[g] = make_float2(a.fx, a.fy);
+    S.tm[g] = sbc_tm_pack(a.bin_step, a.stb, P);
+}
+// split_dead (agents_operation.cpp:209-218): the agent leaves the active set. NaN positions drop out of every distance
+// compare; both position buffers are marked so that the flip of the multi-kernel path cannot resurrect it
+__device__ __forceinline__ void sbc_kill_agent(const DevState &S, size_t g, float4 p) {
+    S.alive[g] = 0;
+    S.pv_dead[g] = p;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float4 dead = make_float4(qnan, qnan, p.z, p.w);
+    S.pv[g] = dead;
+    S.pv_nxt[g] = dead;
+}
+
 __device__ __forceinline__ void sbc_detect_row_warp(const DevParams &P, const DevState &S, size_t g, float4 pi, uint32_t step,
-                                                    int lane) {
+                                                    int lane, RowAcc &row) {
     const int N = S.N, NP = S.Npred;
     const uint32_t rep = (uint32_t)(g / N);
     const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
@@ -64,10 +117,104 @@ __device__ __forceinline__ void sbc_detect_row_warp(const DevParams &P, const De
         acc.flee_y += __shfl_xor_sync(0xffffffffu, acc.flee_y, o);
     }
     const int cf = __reduce_add_sync(0xffffffffu, acc.c_flee);
+    row.flee_x = acc.flee_x;   // every lane holds the totals
+    row.flee_y = acc.flee_y;
+    row.c_flee = cf;
     if (lane == 0) {
         S.acc[g * 8 + 6] = acc.flee_x;
         S.acc[g * 8 + 7] = acc.flee_y;
         S.cnt[g * 4 + 3] = cf;
+    }
+}
+
+// ParticleBurstCoast (agents_dynamics.cpp:150-273) of ONE agent of the multi-kernel path by one thread: state in from
+// S.pv (start-of-step position) / hv / force, decisions from the agent's Philox block (or injected), state out to
+// S.pv_nxt / hv / force / tm. `acc` are the row's zone and flee sums (only read when the agent starts a burst).
+// Returns true when the agent starts a burst in the NEXT step (it was re-armed and is still alive).
+__device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, uint32_t tm,
+                                                 uint32_t step, const StepArgs &A) {
+    const int N = S.N;
+    const uint32_t rep = (uint32_t)(g / N);
+    // Philox counters use the GLOBAL agent id, so a decomposed swarm draws what the whole swarm would
+    const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
+    AgentState a;
+    {
+        const float4 p = S.pv[g];
+        const float2 h = S.hv[g];
+        const float2 f = S.force[g];
+        a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
+        a.phi = h.x; a.vproj = h.y;
+        sincosf(a.phi, &a.su, &a.cu);
+        a.fx = f.x; a.fy = f.y;
+        a.bin_step = sbc_tm_bin(tm, P); a.stb = sbc_tm_stb(tm, P);
+    }
+    const bool first = (a.bin_step == P.burst_steps);
+    const bool rearm = (a.stb <= 1);
+    double u_social = 0.0;
+    float u_dir = 0.f;
+    uint32_t k_next = 1;
+    if (first || rearm) {
+        const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
+        u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
+        u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
+        if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z, P.inv_log2q);
+    }
+    uint32_t fl = 0;
+    sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
+    S.pv_nxt[g] = make_float4(a.x, a.y, a.vx, a.vy);
+    S.hv[g] = make_float2(a.phi, a.vproj);
+    S.force[g] = make_float2(a.fx, a.fy);
+    S.tm[g] = sbc_tm_pack(a.bin_step, a.stb, P);
+    if (S.flags) S.flags[g] |= (uint8_t)fl;
+    bool alive = true;
+    if (A.net_kill) {
+        // FishNetKill (agents_dynamics.cpp:780-820) against the net AFTER this step's MoveFishNet (:616-624): the
+        // test reads the first two nodes only, so every thread moves its own copy of them (net_move_kernel, which
+        // runs behind the step's kernels, moves the stored net with the same arithmetic)
+        const int NP = S.Npred;
+        float4 n0 = S.pred_pv[(size_t)rep * NP], n1 = S.pred_pv[(size_t)rep * NP + 1];
+        float ph0 = S.pred_phi[(size_t)rep * NP], ph1 = S.pred_phi[(size_t)rep * NP + 1];
+        n0.x += n0.z * P.dt; n0.y += n0.w * P.dt;
+        sbc_boundary(n0.x, n0.y, n0.z, n0.w, ph0, P, P.BC);
+        n1.x += n1.z * P.dt; n1.y += n1.w * P.dt;
+        sbc_boundary(n1.x, n1.y, n1.z, n1.w, ph1, P, P.BC);
+        if (sbc_net_kills(a.x, a.y, n0, n1, ph0, NP, P)) {
+            // other rows may still be reading this agent's start-of-step position: the kill itself (split_dead,
+            // agents_operation.cpp:209-218) is applied by net_move_kernel behind the step's two kernels
+            S.kill_list[atomicAdd(S.kill_count, 1)] = (int)g;
+            alive = false;
+        }
+    }
+    return alive && a.bin_step == P.burst_steps;
+}
+
+// Every block of the step's two kernels ends here; the block that arrives last closes the step: the rows of this step
+// are consumed (their counter is cleared for the update of step + 1, which appends the rows of step + 2 there) and the
+// device-resident step index of a graph-replayed step moves on. Every thread of the block must call it.
+__device__ __forceinline__ void sbc_step_close(const DevState &S, const StepArgs &A, uint32_t step) {
+    if (A.ticket_total == 0u) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned *ticket = reinterpret_cast<unsigned *>(S.active_count + 2);
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == A.ticket_total - 1u) {
+            *ticket = 0u;
+            S.active_count[step & 1u] = 0;
+            if (A.step_dev) *A.step_dev = step + 1u;
+            __threadfence();
+        }
+    }
+}
+// rows kernel, lane / thread 0 of the group that swept row g: update the row and pass it on if it re-armed
+__device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, uint32_t step,
+                                               const StepArgs &A) {
+    if (!S.alive[g]) return;   // killed after it was listed
+    const uint32_t tm = S.tm[g];
+    if (sbc_update_agent(P, S, g, acc, tm, step, A)) {
+        const int par = (int)(step & 1u);
+        const int at = atomicAdd(S.active_count + (par ^ 1), 1);
+        S.active_list[par ^ 1][at] = (int)g;
     }
 }
 #endif
@@ -81,18 +228,19 @@ struct StateStage {
 };
 enum { SBC_ST_X = 1, SBC_ST_Y = 2, SBC_ST_VX = 4, SBC_ST_VY = 8, SBC_ST_PHI = 16, SBC_ST_VPROJ = 32,
        SBC_ST_FX = 64, SBC_ST_FY = 128, SBC_ST_BIN = 256, SBC_ST_STB = 512, SBC_ST_ALIVE = 1024 };
-void sbc_launch_pack_state(const DevState &S, const StateStage &st, unsigned mask, int have_prev,
+void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, int have_prev,
                            cudaStream_t stream);
-void sbc_launch_unpack_state(const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
+void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
 
 // --- all-pairs three-zone pass -------------------------------------------------------------------
-// burst-gated rows (bin_step == burst_steps), pair_allpairs.cu: compaction, then all-pairs rows
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, cudaStream_t st, bool all_alive = false,
-                             bool count_is_zero = false, uint32_t *step_inc = nullptr);
-// detect != 0: the rows also evaluate the prey<-predator detection of step `step` (*step_dev when given)
-void sbc_launch_pair_rows(const DevParams &P, const DevState &S, cudaStream_t st, int detect = 0, long long step = 0,
-                          const uint32_t *step_dev = nullptr);
+// rows of a fresh state into list / count (update.cu); the steps themselves keep the lists up to date
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int *list, int *count,
+                             cudaStream_t st);
+// burst-gated rows (bin_step == burst_steps) against all agents of their swarm, pair_allpairs.cu. The rows are
+// S.active_list[step & 1]; A.finish: the rows are updated as well (one of the two kernels of a step)
+int sbc_pair_rows_blocks(const DevState &S);
+void sbc_launch_pair_rows(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st);
 // burst-gated rows through a cell list (celllist.cu), single large swarm
 struct CellScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
@@ -110,8 +258,8 @@ float sbc_cells_skin(const DevParams &P, float want);
 cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N);
 void sbc_cell_scratch_free(CellScratch &C);
 void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
-void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st, int detect = 0,
-                           long long step = 0, const uint32_t *step_dev = nullptr);
+int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C);
+void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, const StepArgs &A, cudaStream_t st);
 // dense pass (every alive row), pair_dense.cu: Morton order + tiled all pairs + split combine
 struct DenseScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
@@ -142,12 +290,14 @@ struct DomainScratch {
                          // [10..13] ghost segment sizes of the last full unpack (halo from a, from b, sent l, sent r)
                          // [14] [15] length of the refresh list towards the left / right neighbour
                          // [16] number of peer-memory exchanges posted so far [20] block ticket of the fused refresh send
+                         // [21] a wait for the neighbours' records timed out (sticky until the next sbc_set_state)
     int *halo_list = nullptr;  // [2][max_halo + max_mig] slots whose positions a refresh exchange sends left / right
     float halo = 0.f;          // width of the edge band that is mirrored on the neighbour (att_range + skin)
     int nblk = 0;
     int own_cap = 0;         // slots [0, own_cap) are owned / free, [own_cap, N) ghosts
     int max_mig = 0, max_halo = 0;  // record capacities of one buffer: [header | max_mig | max_halo]
     float x_lo = 0.f, x_hi = 0.f;
+    unsigned long long timeout_ns = 10000000000ull;  // how long a wait kernel holds for a neighbour (wall clock)
     bool enabled = false;
 };
 size_t sbc_domain_record_bytes(void);
@@ -164,20 +314,21 @@ void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const
 void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
                             int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
-void sbc_launch_domain_refresh_fused(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
-                                     int *const flag_l[2], int *const flag_r[2], const void *const recv_a[2],
-                                     const void *const recv_b[2], int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
+void sbc_launch_domain_refresh_send(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
+                                    int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
+void sbc_launch_domain_refresh_recv(const DevState &S, DomainScratch &D, const void *const recv_a[2], const void *const recv_b[2],
+                                    int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
-// --- per-agent update incl. prey<-predator detection (update.cu) -------------------------------
-// pred_active: the rows' flee sums are valid (the pair kernel ran the detection); zero_count: reset the active-row counter for the next
-// step's compaction once nobody reads it any more; the fish-net kill is evaluated here when a net is present
-void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count = false);
+// --- per-agent update of everybody who does not start a burst this step (update.cu) --------------
+int sbc_update_bulk_blocks(int n_update);
+void sbc_launch_update_bulk(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st);
+void sbc_launch_refresh_cs(const DevState &S, cudaStream_t st);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,
                            cudaStream_t st);
+// step_back: the device-resident step index has already moved on (the kernel runs behind the step's two kernels)
 void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
                                cudaStream_t st);
 

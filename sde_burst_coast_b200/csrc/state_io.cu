@@ -7,37 +7,41 @@
 namespace {
 
 __global__ void __launch_bounds__(256)
-pack_state_kernel(DevState S, StateStage st, unsigned mask, int have_prev) {
+pack_state_kernel(const __grid_constant__ DevParams P, DevState S, StateStage st, unsigned mask, int have_prev) {
     const size_t total = (size_t)S.N * S.R;
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= total) return;
     float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 hv = make_float4(0.f, 1.f, 1.f, 0.f);  // InitSystem: phi = 0, vproj = 1 (settings.cpp:168-193)
+    float2 hv = make_float2(0.f, 1.f);  // InitSystem: phi = 0, vproj = 1 (settings.cpp:168-193)
+    float2 cs = make_float2(1.f, 0.f);
     float2 fo = make_float2(0.f, 0.f);
-    uint2 tm = make_uint2(0u, 0u);
+    uint32_t bin = 0u, stb = 0u;
     uint8_t al = 1;
     if (have_prev) {
         al = S.alive[g];
         pv = al ? S.pv[g] : S.pv_dead[g];
         hv = S.hv[g];
+        cs = S.cs[g];
         fo = S.force[g];
-        tm = S.timers[g];
+        const uint32_t t = S.tm[g];
+        bin = sbc_tm_bin(t, P);
+        stb = sbc_tm_stb(t, P);
     }
     if (mask & SBC_ST_X) pv.x = (float)st.d[0][g];
     if (mask & SBC_ST_Y) pv.y = (float)st.d[1][g];
     if (mask & SBC_ST_PHI) {
         hv.x = (float)st.d[4][g];
-        sincosf(hv.x, &hv.w, &hv.z);
+        sincosf(hv.x, &cs.y, &cs.x);
     }
     if (mask & SBC_ST_VPROJ) hv.y = (float)st.d[5][g];
     if (mask & SBC_ST_VX) pv.z = (float)st.d[2][g];
-    else if (mask & SBC_ST_PHI) pv.z = hv.y * hv.z;  // v = vproj u(phi), settings.cpp:374-377
+    else if (mask & SBC_ST_PHI) pv.z = hv.y * cs.x;  // v = vproj u(phi), settings.cpp:374-377
     if (mask & SBC_ST_VY) pv.w = (float)st.d[3][g];
-    else if (mask & SBC_ST_PHI) pv.w = hv.y * hv.w;
+    else if (mask & SBC_ST_PHI) pv.w = hv.y * cs.y;
     if (mask & SBC_ST_FX) fo.x = (float)st.d[6][g];
     if (mask & SBC_ST_FY) fo.y = (float)st.d[7][g];
-    if (mask & SBC_ST_BIN) tm.x = st.u[0][g];
-    if (mask & SBC_ST_STB) tm.y = st.u[1][g];
+    if (mask & SBC_ST_BIN) bin = min(st.u[0][g], P.tm_mask);
+    if (mask & SBC_ST_STB) stb = st.u[1][g];
     if (mask & SBC_ST_ALIVE) al = st.al[g] ? 1 : 0;
     S.pv_dead[g] = pv;
     if (!al) {
@@ -47,22 +51,24 @@ pack_state_kernel(DevState S, StateStage st, unsigned mask, int have_prev) {
         atomicAdd(S.n_dead + g / S.N, 1);
     }
     S.pv[g] = pv;
+    S.pv_nxt[g] = pv;
     S.hv[g] = hv;
+    S.cs[g] = cs;
     S.force[g] = fo;
-    S.timers[g] = tm;
+    S.tm[g] = sbc_tm_pack(bin, stb, P);
     S.alive[g] = al;
 }
 
 __global__ void __launch_bounds__(256)
-unpack_state_kernel(DevState S, StateStage st, unsigned mask) {
+unpack_state_kernel(const __grid_constant__ DevParams P, DevState S, StateStage st, unsigned mask) {
     const size_t total = (size_t)S.N * S.R;
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= total) return;
     const uint8_t al = S.alive[g];
     const float4 pv = al ? S.pv[g] : S.pv_dead[g];
-    const float4 hv = S.hv[g];
+    const float2 hv = S.hv[g];
     const float2 fo = S.force[g];
-    const uint2 tm = S.timers[g];
+    const uint32_t tm = S.tm[g];
     if (mask & SBC_ST_X) st.d[0][g] = pv.x;
     if (mask & SBC_ST_Y) st.d[1][g] = pv.y;
     if (mask & SBC_ST_VX) st.d[2][g] = pv.z;
@@ -71,8 +77,8 @@ unpack_state_kernel(DevState S, StateStage st, unsigned mask) {
     if (mask & SBC_ST_VPROJ) st.d[5][g] = hv.y;
     if (mask & SBC_ST_FX) st.d[6][g] = fo.x;
     if (mask & SBC_ST_FY) st.d[7][g] = fo.y;
-    if (mask & SBC_ST_BIN) st.u[0][g] = tm.x;
-    if (mask & SBC_ST_STB) st.u[1][g] = tm.y;
+    if (mask & SBC_ST_BIN) st.u[0][g] = sbc_tm_bin(tm, P);
+    if (mask & SBC_ST_STB) st.u[1][g] = sbc_tm_stb(tm, P);
     if (mask & SBC_ST_ALIVE) st.al[g] = al;
 }
 
@@ -102,15 +108,15 @@ particles_kernel(DevState S, double *__restrict__ out, uint8_t *__restrict__ ali
 
 }  // namespace
 
-void sbc_launch_pack_state(const DevState &S, const StateStage &st, unsigned mask, int have_prev,
+void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, int have_prev,
                            cudaStream_t stream) {
     const size_t total = (size_t)S.N * S.R;
     cudaMemsetAsync(S.n_dead, 0, (size_t)S.R * sizeof(int), stream);
-    pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(S, st, mask, have_prev);
+    pack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, S, st, mask, have_prev);
 }
-void sbc_launch_unpack_state(const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream) {
+void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream) {
     const size_t total = (size_t)S.N * S.R;
-    unpack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(S, st, mask);
+    unpack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, S, st, mask);
 }
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream) {
     const size_t n = (size_t)S.N * S.R * 7;

@@ -18,23 +18,6 @@
 
 namespace {
 
-__device__ __forceinline__ void load_agent(const DevState &S, size_t g, AgentState &a) {
-    const float4 p = S.pv[g];
-    const float4 h = S.hv[g];
-    const float2 f = S.force[g];
-    const uint2 t = S.timers[g];
-    a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-    a.phi = h.x; a.vproj = h.y; a.cu = h.z; a.su = h.w;
-    a.fx = f.x; a.fy = f.y;
-    a.bin_step = t.x; a.stb = t.y;
-}
-__device__ __forceinline__ void store_agent(const DevState &S, size_t g, const AgentState &a) {
-    S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
-    S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
-    S.force[g] = make_float2(a.fx, a.fy);
-    S.timers[g] = make_uint2(a.bin_step, a.stb);
-}
-
 __device__ __forceinline__ void draw_decisions(const DevParams &P, const DevState &S, size_t g,
                                                uint32_t rep, uint32_t i, uint32_t step, bool rearm,
                                                double &u_social, float &u_dir, uint32_t &k_next) {
@@ -73,7 +56,7 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
     AgentState a = {};
     bool alive = false;
     if (valid) {
-        load_agent(S, g, a);
+        sbc_load_agent(P, S, g, a, true);
         alive = S.alive[g] != 0;
     }
     uint32_t flags_acc = 0;
@@ -158,7 +141,7 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
         }
     }
     if (valid && alive) {
-        store_agent(S, g, a);
+        sbc_store_agent(P, S, g, a, true);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
     }
     n_amb = __reduce_add_sync(FULL, (unsigned)n_amb);
@@ -191,7 +174,7 @@ swarm_warp_pred_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t
     AgentState a = {};
     bool alive = false, died = false;
     if (valid) {
-        load_agent(S, g, a);
+        sbc_load_agent(P, S, g, a, true);
         alive = S.alive[g] != 0;
     }
     uint32_t flags_acc = 0;
@@ -410,12 +393,10 @@ swarm_warp_pred_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t
         }
     }
     if (valid && (alive || died)) {
-        store_agent(S, g, a);
+        sbc_store_agent(P, S, g, a, true);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
         if (died) {  // split_dead (agents_operation.cpp:209-218)
-            S.alive[g] = 0;
-            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
-            S.pv[g] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), a.vx, a.vy);
+            sbc_kill_agent(S, g, make_float4(a.x, a.y, a.vx, a.vy));
             atomicAdd(S.n_dead + rep, 1);
         }
     }
@@ -550,7 +531,7 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
     AgentState a = {};
     bool alive = false, died = false;
     if (valid) {
-        load_agent(S, g, a);
+        sbc_load_agent(P, S, g, a, true);
         alive = S.alive[g] != 0;
     }
     if (PRED) {
@@ -784,13 +765,9 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
         }
     }
     if (valid && (alive || died)) {
-        store_agent(S, g, a);
+        sbc_store_agent(P, S, g, a, true);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
-        if (died) {  // split_dead (agents_operation.cpp:209-218): the agent leaves the active set
-            S.alive[g] = 0;
-            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
-            S.pv[g] = make_float4(qnan, qnan, a.vx, a.vy);
-        }
+        if (died) sbc_kill_agent(S, g, make_float4(a.x, a.y, a.vx, a.vy));
     }
     if (PRED) {
         __syncthreads();

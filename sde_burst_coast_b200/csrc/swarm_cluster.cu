@@ -73,14 +73,7 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
     AgentState a = {};
     bool alive = false, died = false;
     if (valid) {
-        const float4 p = S.pv[g];
-        const float4 h = S.hv[g];
-        const float2 f = S.force[g];
-        const uint2 tm = S.timers[g];
-        a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-        a.phi = h.x; a.vproj = h.y; a.cu = h.z; a.su = h.w;
-        a.fx = f.x; a.fy = f.y;
-        a.bin_step = tm.x; a.stb = tm.y;
+        sbc_load_agent(P, S, g, a, true);
         alive = S.alive[g] != 0;
     }
     if (PRED) {
@@ -466,16 +459,9 @@ swarm_cluster_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s
         }
     }
     if (valid && (alive || died)) {
-        S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
-        S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
-        S.force[g] = make_float2(a.fx, a.fy);
-        S.timers[g] = make_uint2(a.bin_step, a.stb);
+        sbc_store_agent(P, S, g, a, true);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
-        if (died) {
-            S.alive[g] = 0;
-            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
-            S.pv[g] = make_float4(qnan, qnan, a.vx, a.vy);
-        }
+        if (died) sbc_kill_agent(S, g, make_float4(a.x, a.y, a.vx, a.vy));
     }
     if (PRED) {
         __syncthreads();

@@ -1,101 +1,133 @@
 // update.cu - per-agent burst-coast update for swarms that do not fit one thread block:
 // ParticleBurstCoast with the burst decision, wall avoidance, Euler step, boundary and burst
-// re-arm (/root/reference/src/agents_dynamics.cpp:150-273). For rows that start a burst while a
-// predator is present, the prey<-predator detection of IntCalcPred (agents_interact.cpp:252-292; only
-// rows that read the result evaluate it) has been evaluated by the pair kernel that swept
-// the row (sbc_detect_row_warp, sbc_kernels.cuh).
+// re-arm (/root/reference/src/agents_dynamics.cpp:150-273).
 //
-// One thread per agent, coalesced SoA traffic: 48 B read + 48 B written per agent-step
-// (pv float4, hv float4, force float2, timers uint2) -> HBM-bound.
+// One multi-kernel step is TWO kernels that do not depend on each other:
+//   * the rows kernel (pair_allpairs.cu / celllist.cu): the agents that start a burst this step - the only ones that
+//     read the three-zone sums (IntCalcPrey's gate, agents_interact.cpp:178) - are swept against their candidates
+//     and updated right there by sbc_update_agent (sbc_kernels.cuh);
+//   * update_bulk_kernel (here): every other agent, one thread each, a plain stream over the 36-byte state
+//     (pv 16 + hv 8 + force 8 + timers 4 read and written: 72 B per agent-step, HBM-bound).
+// Both read start-of-step positions from S.pv and write the new ones to S.pv_nxt (Step()'s semantics,
+// swarmdyn.cpp:143-204: interactions see the positions at the start of the step), both append the agents they
+// re-arm to the row list of the NEXT step, and whichever block of the two kernels finishes last closes the step
+// (sbc_step_close): no compaction pass, no dependent launch between pair pass and update.
 #include "sbc_kernels.cuh"
 
 namespace {
 
 __global__ void __launch_bounds__(256)
-update_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg, const uint32_t *__restrict__ step_dev,
-              int pred_active, int *zero_count, int net_kill) {
-    // the pair pass and the detection of this step are done: the next compaction may start from zero
-    if (zero_count && blockIdx.x == 0 && threadIdx.x == 0) *zero_count = 0;
-    // inside a captured CUDA graph the step index lives in device memory (advanced by step_advance_kernel)
-    const uint32_t step = step_dev ? *step_dev : step_arg;
+update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) {
+    const uint32_t step = A.step_dev ? *A.step_dev : A.step;
+    const int par = (int)(step & 1u);
+    const int lane = threadIdx.x & 31;
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool rearmed = false;
+    if (g < (size_t)A.n_update && S.alive[g]) {
+        const uint32_t tm = S.tm[g];
+        if (sbc_tm_bin(tm, P) != P.burst_steps) {   // rows that start a burst belong to the rows kernel
+            RowAcc acc;
+            row_acc_clear(acc);
+            rearmed = sbc_update_agent(P, S, g, acc, tm, step, A);
+        }
+    }
+    // warp-aggregated append to the rows of the next step
+    const unsigned m = __ballot_sync(0xffffffffu, rearmed);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(S.active_count + (par ^ 1), __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (rearmed) S.active_list[par ^ 1][base + __popc(m & ((1u << lane) - 1u))] = (int)g;
+    }
+    sbc_step_close(S, A, step);
+}
+
+// rows of a fresh state (after sbc_set_state, a full domain exchange, an ensemble launch ...): the agents with
+// bin_step == burst_steps, four per thread, warp-aggregated append. The order of the list does not matter - every
+// row writes only its own state.
+__global__ void __launch_bounds__(256)
+compact_active_kernel(const __grid_constant__ DevParams P, DevState S, int all_alive, int n_scan, int *list, int *count) {
+    const size_t total = (size_t)n_scan;
+    const size_t quads = (total + 3) / 4;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // whole warps iterate together, so the scan below may use the full mask
+    for (size_t qb = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31u); qb < quads; qb += stride) {
+        const size_t q = qb + lane, g0 = 4 * q;
+        unsigned act = 0;   // bit k: agent g0 + k starts a burst
+        if (q < quads) {
+            if (g0 + 3 < total) {
+                const uint32_t al = *reinterpret_cast<const uint32_t *>(S.alive + g0);
+                if (al && all_alive) {
+                    for (int k = 0; k < 4; k++) act |= ((al >> (8 * k)) & 0xffu) ? (1u << k) : 0u;
+                } else if (al) {
+                    const uint4 t = *reinterpret_cast<const uint4 *>(S.tm + g0);
+                    act |= ((al & 0xffu) && sbc_tm_bin(t.x, P) == P.burst_steps) ? 1u : 0u;
+                    act |= ((al & 0xff00u) && sbc_tm_bin(t.y, P) == P.burst_steps) ? 2u : 0u;
+                    act |= ((al & 0xff0000u) && sbc_tm_bin(t.z, P) == P.burst_steps) ? 4u : 0u;
+                    act |= ((al & 0xff000000u) && sbc_tm_bin(t.w, P) == P.burst_steps) ? 8u : 0u;
+                }
+            } else {
+                for (int k = 0; k < 4 && g0 + k < total; k++)
+                    if (S.alive[g0 + k] && (all_alive || sbc_tm_bin(S.tm[g0 + k], P) == P.burst_steps)) act |= 1u << k;
+            }
+        }
+        if (__ballot_sync(0xffffffffu, act != 0) == 0) continue;
+        const int n_mine = __popc(act);
+        int incl = n_mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int base = 0;
+        if (lane == 31) base = atomicAdd(count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - n_mine;
+        for (int k = 0; k < 4; k++)
+            if ((act >> k) & 1u) list[base++] = (int)(g0 + k);
+    }
+}
+
+__global__ void clear_acc_kernel(DevState S) {
+    const size_t total = (size_t)S.N * S.R;
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total;
+         g += (size_t)gridDim.x * blockDim.x) {
+        float4 *a = reinterpret_cast<float4 *>(S.acc + g * 8);
+        a[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<int4 *>(S.cnt + g * 4) = make_int4(0, 0, 0, 0);
+    }
+}
+
+// the ensemble kernels' heading vector from phi (after steps on the multi-kernel path, which does not maintain it)
+__global__ void refresh_cs_kernel(DevState S) {
     const size_t total = (size_t)S.N * S.R;
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (g >= total) return;
-    if (!S.alive[g]) return;
-    const int N = S.N;
-    const uint32_t rep = (uint32_t)(g / N);
-    // Philox counters use the GLOBAL agent id, so a decomposed swarm draws what the whole swarm would
-    const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
-    AgentState a;
-    {
-        const float4 p = S.pv[g];
-        const float4 h = S.hv[g];
-        const float2 f = S.force[g];
-        const uint2 t = S.timers[g];
-        a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-        a.phi = h.x; a.vproj = h.y; a.cu = h.z; a.su = h.w;
-        a.fx = f.x; a.fy = f.y;
-        a.bin_step = t.x; a.stb = t.y;
-    }
-    const bool first = (a.bin_step == P.burst_steps);
-    const bool rearm = (a.stb <= 1);
-    RowAcc acc;
-    row_acc_clear(acc);
-    double u_social = 0.0;
-    float u_dir = 0.f;
-    uint32_t k_next = 1;
-    if (first || rearm) {
-        const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
-        u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
-        u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
-        if (rearm) k_next = S.inj_k ? S.inj_k[g] : sbc_geometric_k(S.geo, P.max_steps, q.z, P.inv_log2q);
-    }
-    if (first) {
-        const float4 *ac = reinterpret_cast<const float4 *>(S.acc + g * 8);
-        const float4 a0 = ac[0], a1 = ac[1];
-        const int4 c = *reinterpret_cast<const int4 *>(S.cnt + g * 4);
-        acc.rep_x = a0.x; acc.rep_y = a0.y; acc.alg_x = a0.z; acc.alg_y = a0.w;
-        acc.att_x = a1.x; acc.att_y = a1.y;
-        acc.c_rep = c.x; acc.c_alg = c.y; acc.c_att = c.z;
-        if (pred_active) {  // prey<-predator detection of this row was evaluated by detect_rows_kernel
-            acc.flee_x = a1.z;
-            acc.flee_y = a1.w;
-            acc.c_flee = c.w;
-        }
-    }
-    uint32_t fl = 0;
-    sbc_agent_step(a, acc, u_social, u_dir, k_next, P, fl, P.BC);
-    S.pv[g] = make_float4(a.x, a.y, a.vx, a.vy);
-    S.hv[g] = make_float4(a.phi, a.vproj, a.cu, a.su);
-    S.force[g] = make_float2(a.fx, a.fy);
-    S.timers[g] = make_uint2(a.bin_step, a.stb);
-    if (S.flags) S.flags[g] |= (uint8_t)fl;
-    if (net_kill) {
-        // FishNetKill (agents_dynamics.cpp:780-820) against the net AFTER this step's MoveFishNet (:616-624): the
-        // test reads the first two nodes only, so every thread moves its own copy of them (net_move_kernel, which
-        // runs behind this kernel, moves the stored net with the same arithmetic)
-        const int NP = S.Npred;
-        float4 n0 = S.pred_pv[(size_t)rep * NP], n1 = S.pred_pv[(size_t)rep * NP + 1];
-        float ph0 = S.pred_phi[(size_t)rep * NP], ph1 = S.pred_phi[(size_t)rep * NP + 1];
-        n0.x += n0.z * P.dt; n0.y += n0.w * P.dt;
-        sbc_boundary(n0.x, n0.y, n0.z, n0.w, ph0, P, P.BC);
-        n1.x += n1.z * P.dt; n1.y += n1.w * P.dt;
-        sbc_boundary(n1.x, n1.y, n1.z, n1.w, ph1, P, P.BC);
-        if (sbc_net_kills(a.x, a.y, n0, n1, ph0, NP, P)) {  // split_dead (agents_operation.cpp:209-218)
-            S.alive[g] = 0;
-            S.pv_dead[g] = make_float4(a.x, a.y, a.vx, a.vy);
-            S.pv[g] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), a.vx, a.vy);
-            atomicAdd(S.n_dead + rep, 1);
-        }
-    }
+    float s, c;
+    sincosf(S.hv[g].x, &s, &c);
+    S.cs[g] = make_float2(c, s);
 }
 
 }  // namespace
 
-void sbc_launch_update(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
-                       int pred_active, cudaStream_t st, bool zero_count) {
+int sbc_update_bulk_blocks(int n_update) { return (n_update + 255) / 256; }
+
+void sbc_launch_update_bulk(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st) {
+    update_bulk_kernel<<<(unsigned)sbc_update_bulk_blocks(A.n_update), 256, 0, st>>>(P, S, A);
+}
+
+// compact the rows that start a burst (or, all_alive, every alive agent) of slots [0, n_scan) into list / count
+// (count must be zero); `clear` also zeroes every row's accumulators (the test hook reads rows that were not active)
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int *list, int *count,
+                             cudaStream_t st) {
     const size_t total = (size_t)S.N * S.R;
-    const int net_kill = (pred_active && S.Npred > 1 && P.pred_kill != 0) ? 1 : 0;
-    update_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, S, (uint32_t)step, step_dev, pred_active,
-                                                                  zero_count ? S.active_count : nullptr, net_kill);
+    const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
+    if (clear) clear_acc_kernel<<<blocks, 256, 0, st>>>(S);
+    compact_active_kernel<<<blocks, 256, 0, st>>>(P, S, all_alive ? 1 : 0, n_scan, list, count);
+}
+
+void sbc_launch_refresh_cs(const DevState &S, cudaStream_t st) {
+    const size_t total = (size_t)S.N * S.R;
+    refresh_cs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(S);
 }

@@ -151,6 +151,7 @@ class SlabSwarm:
         sp2.path = P.PATH_CELLLIST
         self.sp = sp2
         self.dev = torch.device('cuda', device)
+        self.stream = stream   # cudaStream_t (int) the handle's kernels run on; None = the handle's private stream
         self.swarm = Swarm(sp2, self.own_cap + self.ghost_cap, 0, 1, seed=seed, device=device, stream=stream)
         lib, h = self.swarm.lib, self.swarm.h
         self.swarm._check(lib.sbc_domain_config(h, rank, world, self.own_cap, self.max_mig, self.max_halo))
@@ -248,9 +249,21 @@ def step_distributed(slab, transport, s_first, n_steps):
             slab.swarm.step(s_first, n_steps)
         return
 
+    # pack / unpack run on the handle's stream, the message library on torch's current stream. When the two are the
+    # same stream (the fast set-up: torch.cuda.set_stream(ts); SlabSwarm(..., stream=ts.cuda_stream)) stream order does
+    # the job; otherwise the host orders them: the buffers are complete before they are sent and landed before they
+    # are unpacked, and the next pack cannot overwrite a buffer still in flight.
+    torch = slab.torch
+    is_cuda = slab.send_l.is_cuda
+    shared = is_cuda and slab.stream is not None and torch.cuda.current_stream(slab.dev).cuda_stream == slab.stream
+
     def exchange():
         slab.pack()
+        if is_cuda and not shared:
+            slab.swarm.synchronize()
         transport.exchange(slab.send_l, slab.send_r, slab.recv_l, slab.recv_r)
+        if is_cuda and not shared:
+            torch.cuda.current_stream(slab.dev).synchronize()
         slab.unpack()
     if not slab.primed:
         slab.set_rebuild_period(transport.min_int(slab.local_rebuild_period()))

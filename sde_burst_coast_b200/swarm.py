@@ -65,6 +65,7 @@ ABI = [
     ('sbc_domain_post', ctypes.c_int, [_vp]),
     ('sbc_domain_complete', ctypes.c_int, [_vp]),
     ('sbc_domain_step', ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64]),
+    ('sbc_domain_set_timeout', ctypes.c_int, [_vp, ctypes.c_double]),
 ]
 
 _lib = None

@@ -74,3 +74,16 @@ def nn_sets(res, N):
 def ang_diff(a, b):
     d = (np.asarray(a) - np.asarray(b) + np.pi) % (2 * np.pi) - np.pi
     return np.abs(d)
+
+
+def cancellation(pairs):
+    """Relative error FP32 may leave in the DIRECTION of a zone sum: c unit vectors summed in FP32 carry an
+    absolute error of about c * 2^-23, which matters when they nearly cancel (|sum| << 1). Per row, the worst
+    of the zones that have members."""
+    cond = np.zeros(len(pairs['c_rep']))
+    for c, f in (('c_rep', 'f_rep'), ('c_alg', 'f_alg'), ('c_att', 'f_att')):
+        n = pairs[c].astype(np.float64)
+        mag = np.hypot(pairs[f][:, 0], pairs[f][:, 1])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            cond = np.maximum(cond, np.where(n > 0, n * 2.4e-7 / np.maximum(mag, 1e-30), 0.0))
+    return np.minimum(cond, 1.0)

@@ -57,15 +57,31 @@ def test_gpu_against_reference_vectors(name):
         for k in ('f_rep', 'f_alg', 'f_att'):
             ref = G['%s/pair%d/%s' % (name, flags, k)]
             assert np.allclose(res[k], ref, rtol=1e-5, atol=2e-5), (flags, k)
+    # branch flags of this very step from the restatement (the committed vectors hold states only): an agent may differ
+    # from the reference vector only where the GPU took another branch than the CPU inside a guard band
+    w = pyorc.World(sp, N, seed=77, replicate=2, kind='port')
+    w.set_state(**_state(name))
+    from helpers import cancellation
+    cond = cancellation(w.pair_interactions(0, want_nn=False))   # rows whose zone sum nearly cancels (see test_gpu_step)
+    w.inject(G[name + '/inj/us'], G[name + '/inj/ud'], G[name + '/inj/kn'])
+    f_cpu = w.step(0, 1, want_flags=True)
+    w.close()
+    g.debug_flags(True)
     g.inject(G[name + '/inj/us'], G[name + '/inj/ud'], G[name + '/inj/kn'])
     g.step(0, 1)
+    f_gpu = g.debug_flags(True, read=True)
+    g.debug_flags(False)
     s = g.get_state()
     ref = {k: G['%s/step1/%s' % (name, k)] for k in s}
     assert np.array_equal(s['bin_step'], ref['bin_step']) and np.array_equal(s['steps_till_burst'], ref['steps_till_burst'])
-    ok = (np.abs(s['x'] - ref['x']) <= 1e-5 * np.maximum(1, np.abs(ref['x']))) & \
-         (np.abs(s['y'] - ref['y']) <= 1e-5 * np.maximum(1, np.abs(ref['y']))) & \
-         (np.abs(s['vproj'] - ref['vproj']) <= 1e-5 * np.maximum(1, ref['vproj'])) & (ang_diff(s['phi'], ref['phi']) <= 2e-5)
-    assert ok.mean() >= 0.97, 'more than a guard-band share of agents differ: %s' % np.where(~ok)[0]
+    kick = cond * np.maximum(1.0, np.hypot(ref['fx'], ref['fy'])) * sp.dt
+    ok = (np.abs(s['x'] - ref['x']) <= 1e-5 * np.maximum(1, np.abs(ref['x'])) + kick) & \
+         (np.abs(s['y'] - ref['y']) <= 1e-5 * np.maximum(1, np.abs(ref['y'])) + kick) & \
+         (np.abs(s['vproj'] - ref['vproj']) <= 1e-5 * np.maximum(1, ref['vproj']) + kick) & \
+         (ang_diff(s['phi'], ref['phi']) <= 2e-5 + kick)
+    flipped = f_cpu != f_gpu
+    assert np.all(ok | flipped), 'agents differ although every branch agreed: %s' % np.where(~ok & ~flipped)[0]
+    assert flipped.sum() <= max(1, N // 100), 'too many branch flips: %s' % np.where(flipped)[0]
     g.step(1, 199)
     s = g.get_state()
     assert np.array_equal(s['steps_till_burst'], G['%s/step200/steps_till_burst' % name])

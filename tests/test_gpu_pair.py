@@ -13,9 +13,20 @@ from sde_burst_coast_b200.params import PAIR_ACTIVE_ROWS, PAIR_ALL_ROWS
 pytestmark = pytest.mark.gpu
 
 
-def _compare(sp, N, st, flags, alive=None):
+KINDS = ['port', 'reference']
+
+
+def _need(kind):
+    if kind == 'reference' and not pyorc.have_reference():
+        pytest.skip('oracle/_ref/liborc_ref.so not built (needs /root/reference at build time)')
+
+
+def _compare(sp, N, st, flags, alive=None, kind='port'):
+    """CUDA path against the CPU side of `kind`: the restatement, or the reference's own IntCalcPrey / SFM_4Zone
+    driven by InteractionGlobal (oracle/_ref)."""
     from sde_burst_coast_b200.swarm import Swarm
-    w = pyorc.World(sp, N, 0, kind='port')
+    _need(kind)
+    w = pyorc.World(sp, N, 0, kind=kind)
     if alive is not None:
         st = dict(st, alive=alive)
     w.set_state(**st)
@@ -45,7 +56,8 @@ def _compare(sp, N, st, flags, alive=None):
 ])
 @pytest.mark.parametrize('alg', [None, 10.0])
 @pytest.mark.parametrize('flags', [PAIR_ALL_ROWS, PAIR_ACTIVE_ROWS])
-def test_pair_parity(mode, BC, L, N, alg, flags):
+@pytest.mark.parametrize('kind', KINDS)
+def test_pair_parity(mode, BC, L, N, alg, flags, kind):
     over = dict(BC=BC, Npred=0)
     if L:
         over['size'] = L
@@ -54,18 +66,19 @@ def test_pair_parity(mode, BC, L, N, alg, flags):
     sp, _, _ = make_params(mode, N, **over)
     rng = np.random.default_rng(1000 + N + BC)
     st = random_state(N, sp, rng, spread=60.0 if BC == -1 else None)
-    ref = _compare(sp, N, st, flags)
+    ref = _compare(sp, N, st, flags, kind=kind)
     if flags == PAIR_ALL_ROWS:
         assert ref['c_rep'].sum() + ref['c_att'].sum() > 0
 
 
-def test_pair_threshold_ties_and_coincident():
+@pytest.mark.parametrize('kind', KINDS)
+def test_pair_threshold_ties_and_coincident(kind):
     """Distances exactly on the closed upper bounds, coincident agents, a lone agent."""
     sp, _, _ = make_params('burst_coast', 8, BC=-1, rep_range=4.0, alg_range=8.0, att_range=16.0)
     x = np.array([0.0, 4.0, 8.0, 16.0, 0.0, -4.0000005, 8.000001, 1000.0])
     y = np.zeros(8)
     st = dict(x=f32(x), y=f32(y), phi=np.zeros(8), vproj=np.ones(8))
-    ref = _compare(sp, 8, st, PAIR_ALL_ROWS)
+    ref = _compare(sp, 8, st, PAIR_ALL_ROWS, kind=kind)
     assert ref['c_rep'][0] == 2 and ref['c_alg'][0] == 2 and ref['c_att'][0] == 2  # ties are inside
     assert ref['c_rep'][7] + ref['c_alg'][7] + ref['c_att'][7] == 0
 

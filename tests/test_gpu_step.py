@@ -11,7 +11,7 @@ Stated tolerances (FP32 device vs FP64 oracle on FP32-representable states, SURV
 import numpy as np
 import pytest
 
-from helpers import make_params, random_state, ang_diff
+from helpers import make_params, random_state, ang_diff, cancellation as _cancellation
 from oracle import pyorc
 
 pytestmark = pytest.mark.gpu
@@ -22,19 +22,6 @@ TOL_X, TOL_V, TOL_PHI, TOL_F = 1e-5, 1e-5, 2e-5, 2e-5
 def _swarm(*a, **k):
     from sde_burst_coast_b200.swarm import Swarm
     return Swarm(*a, **k)
-
-
-def _cancellation(pairs):
-    """Relative error FP32 may leave in the DIRECTION of a zone sum: c unit vectors summed in FP32 carry an
-    absolute error of about c * 2^-23, which matters when they nearly cancel (|sum| << 1). Per row, the worst
-    of the zones that have members."""
-    cond = np.zeros(len(pairs['c_rep']))
-    for c, f in (('c_rep', 'f_rep'), ('c_alg', 'f_alg'), ('c_att', 'f_att')):
-        n = pairs[c].astype(np.float64)
-        mag = np.hypot(pairs[f][:, 0], pairs[f][:, 1])
-        with np.errstate(divide='ignore', invalid='ignore'):
-            cond = np.maximum(cond, np.where(n > 0, n * 2.4e-7 / np.maximum(mag, 1e-30), 0.0))
-    return np.minimum(cond, 1.0)
 
 
 def _close_state(o, g, sp, what='', cond=None):
@@ -48,7 +35,39 @@ def _close_state(o, g, sp, what='', cond=None):
     okv = np.abs(o['vproj'] - g['vproj']) <= TOL_V * np.maximum(1, np.abs(o['vproj'])) + kick
     okp = ang_diff(o['phi'], g['phi']) <= TOL_PHI + kick
     okf = np.hypot(o['fx'] - g['fx'], o['fy'] - g['fy']) <= (TOL_F + extra) * fmag
-    return okx & okv & okp & okf
+    # the lab-frame velocity (what Boundary<> edits at a wall and particle::out() reports): heading error times speed
+    vmag = np.maximum(1.0, np.hypot(o['vx'], o['vy']))
+    okw = np.hypot(o['vx'] - g['vx'], o['vy'] - g['vy']) <= (TOL_PHI + TOL_V) * vmag + kick * (1 + vmag)
+    return okx & okv & okp & okf & okw
+
+
+def _send_through_walls(st, sp, rng):
+    """Box boundaries (Boundary<> cases 1-4, /root/reference/src/agents_dynamics.cpp:300-430): put a third of the agents
+    a fraction of one step's travel inside a wall (or a corner), heading outwards, so that this step crosses it."""
+    from helpers import f32
+    N, L = st['x'].size, sp.sizeL
+    pick = np.where(rng.random(N) < 0.34)[0]
+    for i in pick:
+        walls = rng.integers(0, 4, size=1 + (rng.random() < 0.25))   # sometimes two walls: a corner
+        vp = 8.0 + 10 * rng.random()
+        reach = vp * sp.dt
+        ang = None
+        for w_ in walls:
+            if w_ == 0: st['x'][i] = L - 0.3 * reach; ang = 0.0
+            if w_ == 1: st['x'][i] = 0.3 * reach; ang = np.pi
+            if w_ == 2: st['y'][i] = L - 0.3 * reach; ang = 0.5 * np.pi
+            if w_ == 3: st['y'][i] = 0.3 * reach; ang = -0.5 * np.pi
+        if len(walls) == 2 and walls[0] // 2 != walls[1] // 2:
+            ang = np.arctan2(1.0 if walls[1] == 2 else -1.0, 1.0 if walls[0] == 0 else -1.0)
+        st['phi'][i] = ang + 0.4 * (rng.random() - 0.5)
+        st['vproj'][i] = vp
+        st['bin_step'][i] = 0         # coasting: the heading does not turn during this step
+        st['fx'][i] = st['fy'][i] = 0.0
+        st['steps_till_burst'][i] = max(int(st['steps_till_burst'][i]), 5)
+    for k in ('x', 'y', 'phi', 'vproj'):
+        st[k] = f32(st[k])
+    st['vx'] = f32(st['vproj'] * np.cos(st['phi']))
+    st['vy'] = f32(st['vproj'] * np.sin(st['phi']))
 
 
 @pytest.mark.parametrize('mode,over,N', [
@@ -60,17 +79,27 @@ def _close_state(o, g, sp, what='', cond=None):
     ('natPred', dict(BC=0, size=300.0, Npred=0), 3000),            # cell-list pair pass from N > 2048
     ('burst_coast', dict(BC=5, size=120.0), 2500),
     ('burst_coast', dict(BC=2, size=60.0), 50), ('burst_coast', dict(BC=3, size=60.0), 50),
+    ('burst_coast', dict(BC=1, size=60.0), 50), ('burst_coast', dict(BC=4, size=60.0), 50),   # inelastic box / x periodic + y inelastic
+    ('burst_coast', dict(BC=1, size=60.0), 300), ('burst_coast', dict(BC=4, size=60.0), 300),
 ])
 @pytest.mark.parametrize('multikernel', [False, True, 2])   # automatic (warp / block / cluster kernel), multi-kernel, block kernel
-def test_one_step_injected(mode, over, N, multikernel):
+@pytest.mark.parametrize('kind', ['port', 'reference'])
+def test_one_step_injected(mode, over, N, multikernel, kind):
+    """kind: the CPU side is the restatement (`port`) or the reference's own translation units compiled in place
+    (`reference`, oracle/_ref - present wherever build() ran with /root/reference mounted; the library travels)."""
+    if kind == 'reference' and not pyorc.have_reference():
+        pytest.skip('oracle/_ref/liborc_ref.so not built (needs /root/reference at build time)')
     sp, _, _ = make_params(mode, N, **over)
     rng = np.random.default_rng(N * 3 + sp.BC + 100)
     bad_total = 0
     flag_mismatch = 0
+    hits_total = 0
     trials = 6
     for t in range(trials):
         wide = sp.BC in (5, 6) and t % 2 == 1
-        st = random_state(N, sp, rng, spread=(0.97 * sp.sizeL if wide else (50.0 if sp.BC in (-1, 2, 3) else None)))
+        st = random_state(N, sp, rng, spread=(0.97 * sp.sizeL if wide else (50.0 if sp.BC in (-1, 1, 2, 3, 4) else None)))
+        if sp.BC in (1, 2, 3, 4):
+            _send_through_walls(st, sp, rng)
         us, ud = rng.random(N), rng.random(N)
         ud = np.asarray(ud, dtype=np.float32).astype(np.float64)
         kn = rng.integers(1, 600, N).astype(np.uint32)
@@ -80,6 +109,20 @@ def test_one_step_injected(mode, over, N, multikernel):
         w.inject(us, ud, kn)
         fo = w.step(0, 1, want_flags=True)
         o = w.get_state()
+        if kind == 'reference':
+            # the reference's ParticleBurstCoast does not tell which internal branch it took (wall redirect, clamp,
+            # boundary hit): the branch flags come from the restatement, the STATE the GPU is held to comes from the
+            # reference's own translation units - and the two must be the same doubles
+            wr = pyorc.World(sp, N, kind='reference')
+            wr.set_state(**st)
+            wr.inject(us, ud, kn)
+            fr = wr.step(0, 1, want_flags=True)
+            o_ref = wr.get_state()
+            wr.close()
+            assert np.array_equal(fr, fo & 195)   # burst start, social cue, flee cue, re-arm: the observable flags
+            for k in o:
+                assert np.array_equal(o[k], o_ref[k], equal_nan=True), 'port and reference differ in ' + k
+            o = o_ref
         g = _swarm(sp, N)
         if multikernel:
             g.force_multikernel(multikernel)
@@ -93,6 +136,7 @@ def test_one_step_injected(mode, over, N, multikernel):
         assert np.array_equal(o['steps_till_burst'], gs['steps_till_burst'])
         ok = _close_state(o, gs, sp, cond=cond)
         same_flags = (fo == fg)
+        hits_total += int(((fo & 32) != 0).sum())
         # an agent may only disagree if one of its branch decisions flipped (guard band)
         assert np.all(ok | ~same_flags), 'state differs although every branch agreed: %s' % np.where(~ok & same_flags)[0]
         bad_total += int((~ok).sum())
@@ -101,6 +145,8 @@ def test_one_step_injected(mode, over, N, multikernel):
         w.close()
     # branch flips are rare events (ties within FP32 rounding of a threshold)
     assert flag_mismatch <= max(1, trials * N // 200), (flag_mismatch, bad_total)
+    if sp.BC in (1, 2, 3, 4):
+        assert hits_total >= trials * N // 10, 'the wall cases of Boundary<> were not exercised'
 
 
 @pytest.mark.parametrize('N,R', [(8, 64), (16, 32), (30, 16), (64, 8), (200, 3)])
