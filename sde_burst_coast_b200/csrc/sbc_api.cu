@@ -297,6 +297,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     ok = ok && dev_alloc(&S.pv_nxt, total) == cudaSuccess && dev_alloc(&S.cs, total) == cudaSuccess;
     ok = ok && dev_alloc(&S.hv, total) == cudaSuccess && dev_alloc(&S.force, total) == cudaSuccess;
     ok = ok && dev_alloc(&S.tm, total + 4) == cudaSuccess && dev_alloc(&S.alive, total + 4) == cudaSuccess;
+    ok = ok && dev_alloc(&S.tm_nxt, total + 4) == cudaSuccess;
     if (n_pred > 1) ok = ok && dev_alloc(&S.kill_list, total) == cudaSuccess && dev_alloc(&S.kill_count, 1) == cudaSuccess;
     ok = ok && dev_alloc(&S.acc, total * 8) == cudaSuccess && dev_alloc(&S.cnt, total * 4) == cudaSuccess;
     ok = ok && dev_alloc(&S.pred_pv, npt) == cudaSuccess && dev_alloc(&S.pred_phi, npt) == cudaSuccess;
@@ -359,7 +360,7 @@ int sbc_destroy(sbc_handle *h) {
     if (!h) return SBC_OK;
     cudaSetDevice(h->device);
     DevState &S = h->S;
-    cudaFree(S.pv); cudaFree(S.pv_nxt); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.cs); cudaFree(S.force); cudaFree(S.tm);
+    cudaFree(S.pv); cudaFree(S.pv_nxt); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.cs); cudaFree(S.force); cudaFree(S.tm); cudaFree(S.tm_nxt);
     cudaFree(S.kill_list); cudaFree(S.kill_count);
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_count);
@@ -688,6 +689,8 @@ static void record_step(sbc_handle *h, unsigned key, const StepArgs &A, cudaStre
     DevState Sn = S;   // what the host sees after the step: the new positions are the current ones
     Sn.pv = S.pv_nxt;
     Sn.pv_nxt = S.pv;
+    Sn.tm = S.tm_nxt;
+    Sn.tm_nxt = S.tm;
     if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
     if (key & MK_SEND) domain_launch_refresh_send(h, Sn, main);
 }
@@ -744,6 +747,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
     }
     // the new positions are the current ones from here on
     std::swap(S.pv, S.pv_nxt);
+    std::swap(S.tm, S.tm_nxt);
     h->pv_parity ^= 1;
     h->list_step = s + 1;    // the step's kernels appended the agents they re-armed
     h->cs_valid = false;

@@ -556,15 +556,15 @@ __device__ __forceinline__ bool sbc_boundary(float &x, float &y, float &vx, floa
         if (y > L) { y -= 2.f * (y - L); vy = -vy; hit = true; } else if (y < 0.f) { y -= 2.f * y; vy = -vy; hit = true; }
         return hit;
     }
-    case 3: {  // x periodic, y elastic :386-406
+    case 3: {  // x periodic, y elastic :386-406 (the wrap counts as a boundary event, as in the oracle's flag)
         bool hit = false;
-        if (x < 0.f) x += L; else if (x >= L) x -= L;
+        if (x < 0.f) { x += L; hit = true; } else if (x >= L) { x -= L; hit = true; }
         if (y > L) { y -= 2.f * (y - L); vy = -vy; hit = true; } else if (y < 0.f) { y -= 2.f * y; vy = -vy; hit = true; }
         return hit;
     }
     case 4: {  // x periodic, y inelastic :407-430
         bool hit = false;
-        if (x < 0.f) x += L; else if (x >= L) x -= L;
+        if (x < 0.f) { x += L; hit = true; } else if (x >= L) { x -= L; hit = true; }
         if (y > L) { y = L - 0.0001f; vy = 0.f; hit = true; } else if (y < 0.f) { y = 0.0001f; vy = 0.f; hit = true; }
         return hit;
     }

@@ -16,6 +16,9 @@ struct DevState {
     float2 *cs;        // {cos phi, sin phi} as the ensemble kernels carry it (valid when the host says so)
     float2 *force;     // {fx, fy}
     uint32_t *tm;      // burst timers, sbc_tm_pack(bin_step, steps_till_burst)
+    uint32_t *tm_nxt;  // multi-kernel path: written by the step, swapped with tm together with pv / pv_nxt - the bulk
+                       // update tells the rows (bin_step == burst_steps) by the START-of-step timers while the rows
+                       // kernel is already writing theirs
     uint8_t *alive;
     uint32_t *gid;     // global agent id per slot (domain decomposition), nullptr = slot index
     // row accumulators written by the pair pass, consumed by the update
@@ -129,7 +132,7 @@ __device__ __forceinline__ void sbc_detect_row_warp(const DevParams &P, const De
 
 // ParticleBurstCoast (agents_dynamics.cpp:150-273) of ONE agent of the multi-kernel path by one thread: state in from
 // S.pv (start-of-step position) / hv / force, decisions from the agent's Philox block (or injected), state out to
-// S.pv_nxt / hv / force / tm. `acc` are the row's zone and flee sums (only read when the agent starts a burst).
+// S.pv_nxt / hv / force / tm_nxt. `acc` are the row's zone and flee sums (only read when the agent starts a burst).
 // Returns true when the agent starts a burst in the NEXT step (it was re-armed and is still alive).
 __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, uint32_t tm,
                                                  uint32_t step, const StepArgs &A) {
@@ -164,7 +167,7 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
     S.pv_nxt[g] = make_float4(a.x, a.y, a.vx, a.vy);
     S.hv[g] = make_float2(a.phi, a.vproj);
     S.force[g] = make_float2(a.fx, a.fy);
-    S.tm[g] = sbc_tm_pack(a.bin_step, a.stb, P);
+    S.tm_nxt[g] = sbc_tm_pack(a.bin_step, a.stb, P);
     if (S.flags) S.flags[g] |= (uint8_t)fl;
     bool alive = true;
     if (A.net_kill) {
