@@ -165,6 +165,13 @@ int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out);
  * tests check every schedule on one state. */
 int sbc_debug_force_multikernel(sbc_handle *h, int on);
 
+/* Timeline of the multi-kernel step (profiling hook): while enabled, every step records for each of its kernels
+ * (0 rows kernel, 1 bulk update, 2 exchange receive, 3 exchange send) the wall-clock nanoseconds (%globaltimer) at
+ * which its first block started and its last block ended. out (may be NULL): uint64 [1024][8][2] = {start, end} by
+ * (step mod 1024, kernel); exchanges are indexed by their running count instead of the step. Untouched entries read
+ * {UINT64_MAX, 0}. enable != 0 (re)starts the recording, 0 stops it. */
+int sbc_debug_trace(sbc_handle *h, int enable, uint64_t *out);
+
 /* Kernel statistics since creation: [0] pair-kernel launches, [1] update launches,
  * [2] ensemble launches, [3] directed pairs evaluated, [4] ambiguous (FP64 re-checked) pairs,
  * [5] agent-steps, [6] cell-list builds, [7] other launches. */

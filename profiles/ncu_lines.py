@@ -15,9 +15,11 @@ for r in rows:
         kernels += 1
         if kernels > 1: break
         continue
-    if r[0] == 'File Name': cur_file = r[1].split('/')[-1]; continue
+    if r[0] in ('File Name', 'File Path'): cur_file = r[1].split('/')[-1]; continue
+    if r[0] == 'Function Name': continue
     if r[0] == 'Line No': hdr = r; continue
     if hdr is None or len(r) < len(hdr): continue
+    if not r[0].strip().isdigit(): continue   # SASS rows repeat what their source line already aggregates
     try:
         ie = float(r[hdr.index('Instructions Executed')] or 0)
         ns = float(r[hdr.index('# Samples')] or 0)

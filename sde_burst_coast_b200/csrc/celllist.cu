@@ -13,6 +13,7 @@
 // stride over the agents of the nine cells, zone decisions exactly as on the all-pairs path (FP32
 // band + FP64 re-decision), fixed-order block reduction.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "sbc_kernels.cuh"
 
@@ -84,13 +85,51 @@ __global__ void cell_key_kernel(const float4 *__restrict__ pv, int n, const Cell
 }
 
 __global__ void cell_bounds_kernel(const uint32_t *__restrict__ key, const int *__restrict__ idx, int n,
-                                   uint32_t dead_key, int *__restrict__ cell_start, int *__restrict__ cell_end) {
+                                   uint32_t dead_key, int2 *__restrict__ cell_range) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const uint32_t k = key[r];
     if (k == dead_key) return;
-    if (r == 0 || key[r - 1] != k) cell_start[k] = r;
-    if (r == n - 1 || key[r + 1] != k) cell_end[k] = r + 1;
+    if (r == 0 || key[r - 1] != k) cell_range[k].x = r;
+    if (r == n - 1 || key[r + 1] != k) cell_range[k].y = r + 1;
+}
+
+// ---- counting-sort build for sparse grids (a few agents per cell, e.g. config C5) ---------------------------------
+// key + count (atomic per agent), exclusive scan of the counts, scatter (the counters run back down to zero), then one
+// thread per cell puts its handful of agents into ascending index order - the same order the stable radix sort gives,
+// so results stay reproducible - and writes the cell's range. Four light passes instead of a three-pass radix sort.
+__global__ void cell_count_kernel(const float4 *__restrict__ pv, int n, const CellGeom *__restrict__ geom, uint32_t dead_key,
+                                  uint32_t *__restrict__ key, int *__restrict__ cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const CellGeom g = *geom;
+    const float4 p = pv[i];
+    uint32_t k = dead_key;
+    if (p.x == p.x) {
+        k = (uint32_t)(cell_coord(p.y, g.oy, g.inv_h, g.ncy) * g.ncx + cell_coord(p.x, g.ox, g.inv_w, g.ncx));
+        atomicAdd(cnt + k, 1);
+    }
+    key[i] = k;
+}
+__global__ void cell_scatter_kernel(const uint32_t *__restrict__ key, int n, uint32_t dead_key, const int *__restrict__ start,
+                                    int *__restrict__ cnt, int *__restrict__ sidx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t k = key[i];
+    if (k == dead_key) return;
+    sidx[start[k] + atomicSub(cnt + k, 1) - 1] = i;
+}
+__global__ void cell_finish_kernel(int ncells, const int *__restrict__ start, int *__restrict__ sidx, int2 *__restrict__ cell_range) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncells) return;
+    const int r0 = start[c], r1 = start[c + 1];
+    cell_range[c] = make_int2(r0, r1);
+    for (int a = r0 + 1; a < r1; a++) {   // insertion sort of a handful of indices
+        const int v = sidx[a];
+        int b = a - 1;
+        while (b >= r0 && sidx[b] > v) { sidx[b + 1] = sidx[b]; b--; }
+        sidx[b + 1] = v;
+    }
 }
 
 constexpr int CELLS_THREADS = 128;        // warp-per-row kernel: four rows per block
@@ -103,7 +142,7 @@ constexpr int CELLS_BLOCK_THREADS = 512;  // block-per-row kernel: a dense neigh
 // memory round trips) instead of three per cell.
 template <bool PERIODIC, int TPR>
 __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevState &S, const CellGeom &g,
-                                                const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                                                const int2 *__restrict__ cell_range,
                                                 const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, int i,
                                                 int t /* thread in group */, int *pref /* [10] shared, per group */,
                                                 int *first /* [9] shared, per group */, RowAcc &A, unsigned &n_amb,
@@ -113,7 +152,8 @@ __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevSta
     const int ck = (int)build_key[i];
     const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
     if (t < 9) {
-        int yy = cy + t / 3 - 1, xx = cx + t % 3 - 1;
+        const int tc = t;
+        int yy = cy + tc / 3 - 1, xx = cx + tc % 3 - 1;
         bool ok = true;
         if (PERIODIC) {
             yy = (yy + g.ncy) % g.ncy;
@@ -123,23 +163,24 @@ __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevSta
         }
         int r0 = 0, r1 = 0;
         if (ok) {
-            const int c = yy * g.ncx + xx;
-            r0 = cell_start[c];
-            r1 = cell_end[c];
+            const int2 cr = cell_range[yy * g.ncx + xx];
+            r0 = cr.x;
+            r1 = cr.y;
         }
-        first[t] = r0;
-        pref[t + 1] = r1 - r0;
+        first[tc] = r0;
+        pref[tc + 1] = r1 - r0;
     }
-    if (TPR == 32) __syncwarp(); else __syncthreads();
+    if (TPR <= 32) __syncwarp(); else __syncthreads();
     if (t == 0) {
         int run = 0;
         pref[0] = 0;
         for (int c = 0; c < 9; c++) { run += pref[c + 1]; pref[c + 1] = run; }
         n_cand += (unsigned long long)run;
     }
-    if (TPR == 32) __syncwarp(); else __syncthreads();
+    if (TPR <= 32) __syncwarp(); else __syncthreads();
     const int total = pref[9];
     row_acc_clear(A);
+#pragma unroll 2
     for (int q = t; q < total; q += TPR) {
         int c = 0;
 #pragma unroll
@@ -185,13 +226,13 @@ __device__ __forceinline__ void cells_row_store(const DevState &S, int i, const 
 
 // dense neighbourhoods: one block per active row
 template <bool PERIODIC>
-__global__ void __launch_bounds__(CELLS_BLOCK_THREADS)
+__global__ void __launch_bounds__(CELLS_BLOCK_THREADS, 2)
 pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
-                  const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                  const int2 *__restrict__ cell_range,
                   const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
-    const uint32_t step = SA.step_dev ? *SA.step_dev : SA.step;
-    const int par = (int)(step & 1u);
-    const int *__restrict__ list = S.active_list[par];
+    const uint32_t step = sbc_step_of(SA);
+    const int par = (int)(step % 3u);
+    const int2 *__restrict__ list = S.active_list[par];
     __shared__ float shf[CELLS_BLOCK_THREADS / 32][6];
     __shared__ int shi[CELLS_BLOCK_THREADS / 32][3];
     __shared__ int pref[10], first[9];
@@ -202,10 +243,13 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
     const CellGeom g = *geom;
     unsigned n_amb = 0;
     unsigned long long n_cand = 0;
+    sbc_trace(S, step, SBC_TR_ROWS, true);
     for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
-        const int i = list[k];  // single swarm on this path: slot index == global index
+        const int i = list[k].x;  // single swarm on this path: slot index == global index
+        RowState rs = {};
+        if (SA.finish && threadIdx.x == 0) rs = sbc_row_prefetch(S, (size_t)i);
         RowAcc A;
-        cells_row_sweep<PERIODIC, CELLS_BLOCK_THREADS>(P, S, g, cell_start, cell_end, build_key, sidx, i, threadIdx.x, pref, first, A,
+        cells_row_sweep<PERIODIC, CELLS_BLOCK_THREADS>(P, S, g, cell_range, build_key, sidx, i, threadIdx.x, pref, first, A,
                                                  n_amb, n_cand);
         sbc_block_reduce_row<CELLS_BLOCK_THREADS / 32>(A, shf, shi);
         if (SA.pred_active) {   // IntCalcPred of this row by the last warp (thread 0 holds the zone sums)
@@ -221,7 +265,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
             cells_row_store(S, i, A);
             if (SA.finish) {
                 if (SA.pred_active) { A.flee_x = s_flee[0]; A.flee_y = s_flee[1]; A.c_flee = s_cflee; }
-                sbc_finish_row(P, S, (size_t)i, A, step, SA);
+                sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
             }
         }
         __syncthreads();   // pref / first are rewritten by the next row
@@ -229,18 +273,151 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (threadIdx.x == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);  // candidates examined on this path
-    sbc_step_close(S, SA, step);
+    __syncthreads();
+    sbc_trace(S, step, SBC_TR_ROWS, false);
 }
 
-// sparse neighbourhoods (a few dozen candidates): one WARP per active row, reduction by shuffles only
+// one candidate of a row: zone decision as on the all-pairs path (FP32 band + FP64 re-decision), accumulation
 template <bool PERIODIC>
-__global__ void __launch_bounds__(CELLS_THREADS)
+__device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, const float4 pj, RowAcc &A, unsigned &n_amb) {
+    float dx = pj.x - pi.x, dy = pj.y - pi.y;
+    if (PERIODIC) {
+        dx = sbc_delta_pbc(pi.x, pj.x, P);
+        dy = sbc_delta_pbc(pi.y, pj.y, P);
+    }
+    const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));   // NaN for a dead or skipped candidate: no zone
+    bool amb;
+    int z = sbc_zone_fast(d2, P, amb);
+    if (amb) {
+        z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
+        n_amb++;
+    }
+    const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
+    if (z == 0) {
+        A.rep_x = __fmaf_rn(-dx, rinv, A.rep_x);
+        A.rep_y = __fmaf_rn(-dy, rinv, A.rep_y);
+        A.c_rep++;
+    } else if (z == 1) {
+        A.alg_x += pj.z;
+        A.alg_y += pj.w;
+        A.c_alg++;
+    } else if (z == 2) {
+        A.att_x = __fmaf_rn(dx, rinv, A.att_x);
+        A.att_y = __fmaf_rn(dy, rinv, A.att_y);
+        A.c_att++;
+    }
+}
+
+// sparse neighbourhoods (a few agents per cell): EIGHT lanes per active row, four rows per warp. Lane t walks cell t of
+// the row's 3 x 3 block (lane 0 also the ninth), four candidates at a time: the sorted indices of a batch are loaded
+// together, then their positions together, so the dependent chain of a row is list -> key -> cell bounds -> indices ->
+// positions, five memory round trips whatever the cell holds. Few warps carry a step's rows (about 0.5 % of the
+// agents), which leaves the register file to the bulk update that runs beside this kernel.
+template <bool PERIODIC>
+__global__ void __launch_bounds__(CELLS_THREADS, 8)   // 64 registers: the whole grid is resident on a quarter of the register file
+pair_cells_lanes_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
+                        const int2 *__restrict__ cell_range,
+                        const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
+    const uint32_t step = sbc_step_of(SA);
+    const int par = (int)(step % 3u);
+    const int2 *__restrict__ list = S.active_list[par];
+    constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / TPR, t = lane % TPR;
+    const unsigned gmask = ((1u << TPR) - 1u) << (grp * TPR);
+    // the first list entry is fetched together with the row count, not after it
+    const int k_first = (blockIdx.x * WPB + warp) * GPW + grp;
+    const int cap = S.N * S.R;
+    int2 e_next = (k_first < cap) ? list[k_first] : make_int2(0, 0);
+    const int n_rows = S.active_count[par];
+    const CellGeom g = *geom;
+    const float qnan = __int_as_float(0x7fc00000);
+    unsigned n_amb = 0, n_cand = 0;
+    sbc_trace(S, step, SBC_TR_ROWS, true);
+    // warp-uniform loop: the groups of a warp take GPW consecutive rows per pass
+    for (int k0 = (blockIdx.x * WPB + warp) * GPW; k0 < n_rows; k0 += gridDim.x * GPB) {
+        const int k = k0 + grp;
+        const bool has = k < n_rows;
+        const int2 e = e_next;
+        const int k_nxt = k + gridDim.x * GPB;
+        if (k_nxt < n_rows) e_next = list[k_nxt];
+        const int i = has ? e.x : 0;
+        RowState rs = {};
+        if (SA.finish && t == 0 && has) rs = sbc_row_prefetch(S, (size_t)i);
+        const float4 pi = has ? S.pv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // the row's cell at build time (agents alive now were alive then: nobody is born between builds); the key
+        // travelled with the list entry unless the cell order was rebuilt since
+        const int ck = !has ? 0 : ((SA.fresh_cells || e.y < 0) ? (int)build_key[i] : e.y);
+        const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
+        int r0[2] = {0, 0}, r1[2] = {0, 0};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int tc = t + u * TPR;   // lane 0 owns cells 0 and 8
+            if (has && tc < 9) {
+                int yy = cy + tc / 3 - 1, xx = cx + tc % 3 - 1;
+                bool ok = true;
+                if (PERIODIC) {
+                    yy += (yy < 0) ? g.ncy : 0; yy -= (yy >= g.ncy) ? g.ncy : 0;
+                    xx += (xx < 0) ? g.ncx : 0; xx -= (xx >= g.ncx) ? g.ncx : 0;
+                } else {
+                    ok = yy >= 0 && yy < g.ncy && xx >= 0 && xx < g.ncx;
+                }
+                if (ok) {
+                    const int2 cr = cell_range[yy * g.ncx + xx];
+                    r0[u] = cr.x;
+                    r1[u] = cr.y;
+                }
+            }
+        }
+        RowAcc A;
+        row_acc_clear(A);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            n_cand += (unsigned)(r1[u] - r0[u]);
+            for (int r = r0[u]; r < r1[u]; r += 4) {
+                int jj[4];
+                float4 pj[4];
+#pragma unroll
+                for (int b = 0; b < 4; b++) jj[b] = (r + b < r1[u]) ? sidx[r + b] : -1;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    pj[b] = (jj[b] >= 0 && jj[b] != i) ? S.pv[jj[b]] : make_float4(qnan, qnan, 0.f, 0.f);
+#pragma unroll
+                for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
+            }
+        }
+        A.c_rep = __reduce_add_sync(gmask, A.c_rep);
+        A.c_alg = __reduce_add_sync(gmask, A.c_alg);
+        A.c_att = __reduce_add_sync(gmask, A.c_att);
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) {
+            A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o); A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
+            A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o); A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
+            A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o); A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
+        }
+        if (t == 0 && has) {
+            cells_row_store(S, i, A);
+            if (SA.finish) sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
+        }
+        __syncwarp();
+    }
+    n_amb = __reduce_add_sync(0xffffffffu, n_amb);
+    if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
+    n_cand = __reduce_add_sync(0xffffffffu, n_cand);
+    if (lane == 0 && n_cand) atomicAdd(S.stats + 3, (unsigned long long)n_cand);
+    __syncthreads();
+    sbc_trace(S, step, SBC_TR_ROWS, false);
+}
+
+// the same neighbourhoods in the predator phase: one WARP per active row, which also evaluates IntCalcPred for it
+template <bool PERIODIC>
+__global__ void __launch_bounds__(CELLS_THREADS, 4)
 pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
-                       const int *__restrict__ cell_start, const int *__restrict__ cell_end,
+                       const int2 *__restrict__ cell_range,
                        const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
-    const uint32_t step = SA.step_dev ? *SA.step_dev : SA.step;
-    const int par = (int)(step & 1u);
-    const int *__restrict__ list = S.active_list[par];
+    const uint32_t step = sbc_step_of(SA);
+    const int par = (int)(step % 3u);
+    const int2 *__restrict__ list = S.active_list[par];
     constexpr int WPB = CELLS_THREADS / 32;
     __shared__ int pref[WPB][10], first[WPB][9];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -248,10 +425,13 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
     const CellGeom g = *geom;
     unsigned n_amb = 0;
     unsigned long long n_cand = 0;
+    sbc_trace(S, step, SBC_TR_ROWS, true);
     for (int k = blockIdx.x * WPB + warp; k < n_rows; k += gridDim.x * WPB) {
-        const int i = list[k];
+        const int i = list[k].x;
+        RowState rs = {};
+        if (SA.finish && lane == 0) rs = sbc_row_prefetch(S, (size_t)i);
         RowAcc A;
-        cells_row_sweep<PERIODIC, 32>(P, S, g, cell_start, cell_end, build_key, sidx, i, lane, pref[warp], first[warp], A, n_amb,
+        cells_row_sweep<PERIODIC, 32>(P, S, g, cell_range, build_key, sidx, i, lane, pref[warp], first[warp], A, n_amb,
                                       n_cand);
         A.c_rep = __reduce_add_sync(0xffffffffu, A.c_rep);
         A.c_alg = __reduce_add_sync(0xffffffffu, A.c_alg);
@@ -265,13 +445,14 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
         if (lane == 0) cells_row_store(S, i, A);
         __syncwarp();
         if (SA.pred_active) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane, A);
-        if (SA.finish && lane == 0) sbc_finish_row(P, S, (size_t)i, A, step, SA);
+        if (SA.finish && lane == 0) sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
         __syncwarp();
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (lane == 0 && n_cand) atomicAdd(S.stats + 3, n_cand);
-    sbc_step_close(S, SA, step);
+    __syncthreads();
+    sbc_trace(S, step, SBC_TR_ROWS, false);
 }
 
 }  // namespace
@@ -308,8 +489,7 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
     if ((e = cudaMalloc((void **)&C.key_out, (size_t)N * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.idx_in, (size_t)N * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.idx_out, (size_t)N * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&C.cell_start, C.ncells * sizeof(int))) != cudaSuccess) return e;
-    if ((e = cudaMalloc((void **)&C.cell_end, C.ncells * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&C.cell_range, C.ncells * sizeof(int2))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&C.bbox, 4 * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc(&C.geom, sizeof(CellGeom))) != cudaSuccess) return e;
     if (P.BC == 0) cudaMemcpy(C.geom, &hg, sizeof(hg), cudaMemcpyHostToDevice);
@@ -317,13 +497,23 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
     while (((size_t)1 << C.key_bits) <= C.ncells) C.key_bits++;
     C.cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, C.cub_bytes, C.key_in, C.key_out, C.idx_in, C.idx_out, N, 0, C.key_bits);
+    // sparse grids (periodic box, at most 32 agents per cell on average) are built by a counting sort
+    C.counting = P.BC == 0 && (double)N / (double)C.ncells <= 32.0;
+    if (C.counting) {
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, C.cnt, C.start, (int)C.ncells + 1);
+        if (scan_bytes > C.cub_bytes) C.cub_bytes = scan_bytes;
+        if ((e = cudaMalloc((void **)&C.cnt, (C.ncells + 1) * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&C.start, (C.ncells + 1) * sizeof(int))) != cudaSuccess) return e;
+        if ((e = cudaMemset(C.cnt, 0, (C.ncells + 1) * sizeof(int))) != cudaSuccess) return e;
+    }
     if ((e = cudaMalloc(&C.cub_tmp, C.cub_bytes ? C.cub_bytes : 16)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 void sbc_cell_scratch_free(CellScratch &C) {
     cudaFree(C.key_in); cudaFree(C.key_out); cudaFree(C.idx_in); cudaFree(C.idx_out);
-    cudaFree(C.cell_start); cudaFree(C.cell_end); cudaFree(C.bbox); cudaFree(C.geom); cudaFree(C.cub_tmp);
+    cudaFree(C.cell_range); cudaFree(C.bbox); cudaFree(C.geom); cudaFree(C.cub_tmp); cudaFree(C.cnt); cudaFree(C.start);
     C = CellScratch();
 }
 
@@ -337,12 +527,19 @@ void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C
         cell_geom_kernel<<<1, 1, 0, st>>>(C.bbox, (P.att + C.skin) * 1.00001f, C.max_per_axis, geom);
     }
     const uint32_t dead_key = (uint32_t)C.ncells;
+    if (C.counting) {
+        cell_count_kernel<<<blocks, 256, 0, st>>>(S.pv, N, geom, dead_key, C.key_in, C.cnt);
+        size_t bytes = C.cub_bytes;
+        cub::DeviceScan::ExclusiveSum(C.cub_tmp, bytes, C.cnt, C.start, (int)C.ncells + 1, st);
+        cell_scatter_kernel<<<blocks, 256, 0, st>>>(C.key_in, N, dead_key, C.start, C.cnt, C.idx_out);
+        cell_finish_kernel<<<(unsigned)((C.ncells + 255) / 256), 256, 0, st>>>((int)C.ncells, C.start, C.idx_out, C.cell_range);
+        return;
+    }
     cell_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, geom, dead_key, C.key_in, C.idx_in);
     cub::DeviceRadixSort::SortPairs(C.cub_tmp, C.cub_bytes, C.key_in, C.key_out, C.idx_in, C.idx_out, N, 0,
                                     C.key_bits, st);
-    cudaMemsetAsync(C.cell_start, 0, C.ncells * sizeof(int), st);
-    cudaMemsetAsync(C.cell_end, 0, C.ncells * sizeof(int), st);
-    cell_bounds_kernel<<<blocks, 256, 0, st>>>(C.key_out, C.idx_out, N, dead_key, C.cell_start, C.cell_end);
+    cudaMemsetAsync(C.cell_range, 0, C.ncells * sizeof(int2), st);
+    cell_bounds_kernel<<<blocks, 256, 0, st>>>(C.key_out, C.idx_out, N, dead_key, C.cell_range);
 }
 
 // mean number of candidates a row meets in its nine cells decides between a warp and a block per row
@@ -350,20 +547,31 @@ static bool cells_warp_rows(const DevParams &P, const DevState &S, const CellScr
     const double per_row = 9.0 * (double)S.N / (double)(C.ncells > 0 ? C.ncells : 1);
     return P.BC == 0 && per_row < 512.0;
 }
+// The rows kernel is the first of the step's two kernels; the bulk update's blocks are only dispatched once every
+// block of this grid has been, so the grid must be resident at once: 4 blocks of four warps per SM in the
+// lanes-per-row kernel (four rows per warp: 9472 rows in flight cover the ~0.5 % of a million agents that start a
+// burst in a step; warps without a row exit at once), 2 blocks of 512 threads per SM in the block-per-row kernel.
 int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C) {
-    return (int)min((size_t)148 * 16, max((size_t)16, (size_t)S.N / 64));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const size_t cap = (size_t)sms * (cells_warp_rows(P, S, C) ? 4 : 2);
+    return (int)min(cap, max((size_t)16, (size_t)S.N / 64));
 }
 
-// the rows are S.active_list[step & 1] (kept by the steps themselves, or compacted by sbc_launch_compact_rows)
+// the rows are S.active_list[step % 3] (kept by the steps themselves, or compacted by sbc_launch_compact_rows)
 void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, const StepArgs &A, cudaStream_t st) {
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
     const int blocks = sbc_pair_cells_blocks(P, S, C);
-#define SBC_CELLS_ARGS P, S, geom, C.cell_start, C.cell_end, C.key_in, C.idx_out, A
+#define SBC_CELLS_ARGS P, S, geom, C.cell_range, C.key_in, C.idx_out, A
     if (P.BC == 0) {
-        if (cells_warp_rows(P, S, C)) pair_cells_warp_kernel<true><<<blocks, CELLS_THREADS, 0, st>>>(SBC_CELLS_ARGS);
-        else pair_cells_kernel<true><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        if (cells_warp_rows(P, S, C)) {
+            if (A.pred_active) sbc_launch_prio(pair_cells_warp_kernel<true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else sbc_launch_prio(pair_cells_lanes_kernel<true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+        } else {
+            sbc_launch_prio(pair_cells_kernel<true>, blocks, CELLS_BLOCK_THREADS, 0, st, SBC_CELLS_ARGS);
+        }
     } else {
-        pair_cells_kernel<false><<<blocks, CELLS_BLOCK_THREADS, 0, st>>>(SBC_CELLS_ARGS);
+        sbc_launch_prio(pair_cells_kernel<false>, blocks, CELLS_BLOCK_THREADS, 0, st, SBC_CELLS_ARGS);
     }
 #undef SBC_CELLS_ARGS
 }

@@ -385,6 +385,7 @@ dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list,
                         DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, volatile int *flag_l0, volatile int *flag_l1,
                         volatile int *flag_r0, volatile int *flag_r1, unsigned *ticket) {
     const int epoch = ctl[16] + 1, par = epoch & 1;
+    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, true);   // exchanges are indexed by their count, not by the step
     DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
@@ -398,6 +399,7 @@ dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list,
     if (t < nr) dst_r[1 + t].pv = S.pv[halo_list[list_cap + t]];
     __threadfence_system();
     __syncthreads();
+    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, false);
     if (threadIdx.x == 0) {
         const unsigned done = atomicAdd(ticket, 1u);
         if (done == gridDim.x - 1) {   // every block has stored its records (and read ctl[16])
@@ -417,6 +419,7 @@ dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv
                         unsigned long long timeout_ns) {
     const int epoch = ctl[16], par = epoch & 1;
     __shared__ int arrived;
+    sbc_trace(S, (uint32_t)epoch, SBC_TR_RECV, true);
     if (threadIdx.x == 0) {
         // ctl[21] of an earlier failure is read through volatile: block 0 of THIS launch may be setting it right now,
         // which is fine - every block runs its own wait and comes to the same verdict
@@ -448,6 +451,7 @@ dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv
         const float4 pv = __ldcg(reinterpret_cast<const float4 *>(&src->pv));
         S.pv[own_cap + t] = pv;
     }
+    sbc_trace(S, (uint32_t)epoch, SBC_TR_RECV, false);
 }
 
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest

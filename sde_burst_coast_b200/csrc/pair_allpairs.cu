@@ -13,11 +13,11 @@ namespace {
 
 constexpr int ROWS_THREADS = 128;  // one block per active row
 
-__global__ void __launch_bounds__(ROWS_THREADS)
+__global__ void __launch_bounds__(ROWS_THREADS, 4)
 pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs SA) {
-    const uint32_t step = SA.step_dev ? *SA.step_dev : SA.step;
-    const int par = (int)(step & 1u);
-    const int *__restrict__ list = S.active_list[par];
+    const uint32_t step = sbc_step_of(SA);
+    const int par = (int)(step % 3u);
+    const int2 *__restrict__ list = S.active_list[par];
     __shared__ float shf[ROWS_THREADS / 32][6];
     __shared__ int shi[ROWS_THREADS / 32][3];
     __shared__ float s_flee[2];
@@ -26,11 +26,14 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs SA) {
     const int n_rows = S.active_count[par];
     const int N = S.N;
     unsigned n_amb = 0;
+    sbc_trace(S, step, SBC_TR_ROWS, true);
     for (int k = blockIdx.x; k < n_rows; k += gridDim.x) {
-        const int g = list[k];
+        const int g = list[k].x;
         const int rep = g / N, i = g - rep * N;
         const float4 *pv = S.pv + (size_t)rep * N;
         const float4 pi = pv[i];
+        RowState rs = {};
+        if (SA.finish && threadIdx.x == 0) rs = sbc_row_prefetch(S, (size_t)g);
         RowAcc A;
         row_acc_clear(A);
         for (int j = threadIdx.x; j < N; j += ROWS_THREADS) {
@@ -90,7 +93,7 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs SA) {
             cnt[0] = A.c_rep; cnt[1] = A.c_alg; cnt[2] = A.c_att;
             if (SA.finish) {
                 if (SA.pred_active) { A.flee_x = s_flee[0]; A.flee_y = s_flee[1]; A.c_flee = s_cflee; }
-                sbc_finish_row(P, S, (size_t)g, A, step, SA);
+                sbc_finish_row(P, S, (size_t)g, A, rs, step, SA);
             }
         }
     }
@@ -98,7 +101,8 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs SA) {
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(S.stats + 3, (unsigned long long)n_rows * (unsigned long long)(N - 1));
-    sbc_step_close(S, SA, step);
+    __syncthreads();
+    sbc_trace(S, step, SBC_TR_ROWS, false);
 }
 
 // test hook: neighbour ids of every row in ascending j (same zone functions as the kernels above)
@@ -144,12 +148,13 @@ __global__ void nn_fill_kernel(const __grid_constant__ DevParams P, DevState S, 
 int sbc_pair_rows_blocks(const DevState &S) {
     // grid: enough blocks for the synchronised first burst (every row active), few enough to be cheap
     // to launch when only a handful of rows start a burst
+    // resident at once (see sbc_pair_cells_blocks): the bulk update's blocks follow this grid's in the dispatch order
     const size_t total = (size_t)S.N * S.R;
-    return (int)min((size_t)148 * 8, max((size_t)16, total / 64));
+    return (int)min((size_t)148 * 4, max((size_t)16, total / 64));
 }
 
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st) {
-    pair_rows_kernel<<<sbc_pair_rows_blocks(S), ROWS_THREADS, 0, st>>>(P, S, A);
+    sbc_launch_prio(pair_rows_kernel, sbc_pair_rows_blocks(S), ROWS_THREADS, 0, st, P, S, A);
 }
 
 void sbc_launch_nn_fill(const DevParams &P, const DevState &S, int all_rows, const long long *nn_ptr,

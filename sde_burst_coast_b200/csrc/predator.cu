@@ -129,8 +129,7 @@ net_move_kernel(const __grid_constant__ DevParams P, DevState S) {
 __global__ void __launch_bounds__(PT)
 pred_move_kill_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t step_arg,
                       const uint32_t *__restrict__ step_dev) {
-    // behind the step's two kernels the device-resident step index has already moved on
-    const uint32_t step = step_dev ? *step_dev - 1u : step_arg;
+    const uint32_t step = step_dev ? *step_dev + step_arg : step_arg;   // graph-replayed: base + offset inside the launch
     __shared__ double sh[PT / 32];
     __shared__ unsigned long long s_key[PT / 32];
     __shared__ float s_p[4];

@@ -44,7 +44,7 @@ struct sbc_handle {
     int dom_period;                // domain mode: agreed number of refresh exchanges between two full ones
     bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
     // multi-kernel path bookkeeping
-    bool list_valid;               // S.active_list[list_step & 1] holds the rows (bin_step == burst_steps) of step list_step
+    bool list_valid;               // S.active_list[list_step % 3] holds the rows (bin_step == burst_steps) of step list_step
     int64_t list_step;
     bool nxt_synced;               // S.pv_nxt carries the dead / free marks of S.pv (needed before a step writes into it)
     bool cs_valid;                 // S.cs == (cos, sin)(phi): true after set_state / ensemble launches, false after multi-kernel steps
@@ -66,6 +66,7 @@ struct sbc_handle {
     uint32_t *step_dev;
     int64_t step_dev_value;
     bool use_graphs;
+    unsigned long long *trace_dev;
     double *part_dev;           // [R][N][7] rows of particle::out()
     uint8_t *part_alive_dev;
 };
@@ -303,7 +304,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     ok = ok && dev_alloc(&S.pred_pv, npt) == cudaSuccess && dev_alloc(&S.pred_phi, npt) == cudaSuccess;
     ok = ok && dev_alloc(&S.n_dead, (size_t)n_replicates) == cudaSuccess;
     ok = ok && dev_alloc(&S.pred_spawned, (size_t)n_replicates) == cudaSuccess;
-    ok = ok && dev_alloc(&S.active_list[0], total) == cudaSuccess && dev_alloc(&S.active_list[1], total) == cudaSuccess;
+    for (int k = 0; k < 3; k++) ok = ok && dev_alloc(&S.active_list[k], total) == cudaSuccess;
     ok = ok && dev_alloc(&S.active_count, 4) == cudaSuccess;
     ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
     uint32_t *geo_dev = nullptr;
@@ -363,7 +364,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.pv); cudaFree(S.pv_nxt); cudaFree(S.pv_dead); cudaFree(S.hv); cudaFree(S.cs); cudaFree(S.force); cudaFree(S.tm); cudaFree(S.tm_nxt);
     cudaFree(S.kill_list); cudaFree(S.kill_count);
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
-    cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_count);
+    cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_list[2]); cudaFree(S.active_count);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
@@ -377,6 +378,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
     cudaFree(h->S.gid);
     cudaFree(h->step_dev);
+    cudaFree(h->trace_dev);
     cudaFree(h->stage_raw); cudaFree(h->part_dev); cudaFree(h->part_alive_dev);
     cudaFree(h->inj_social_dev); cudaFree(h->inj_dir_dev); cudaFree(h->inj_k_dev);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -440,6 +442,8 @@ static int ensure_cells(sbc_handle *h) {
         return fail(h, SBC_ERR_NOMEM, std::string("cell list scratch: ") + cudaGetErrorString(e));
     }
     h->cells_ready = true;
+    h->S.cell_key = h->cells.key_in;
+    invalidate_graphs(h);   // (nothing captured yet on this path, but the pointer is baked into captured steps)
     set_cells_max_age(h);
     return SBC_OK;
 }
@@ -474,6 +478,7 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
     h->host_stats[7] += (every || clear_inactive) ? 2 : 1;
     if (h->use_cells && !every) {
         if (int rc = ensure_cells(h)) return rc;
+        A.fresh_cells = 1;   // the build below comes after the compaction above
         sbc_launch_cell_build(h->P, h->S, h->cells, h->stream);
         h->host_stats[6]++;
         h->host_stats[7] += 4;
@@ -659,7 +664,7 @@ static void domain_launch_refresh_recv(sbc_handle *h, const DevState &S, cudaStr
 
 static int ensure_rows(sbc_handle *h, int64_t s) {
     if (h->list_valid && h->list_step == s) return SBC_OK;
-    const int par = (int)(s & 1);
+    const int par = (int)((uint32_t)s % 3u);
     SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 4 * sizeof(int), h->stream));
     sbc_launch_compact_rows(h->P, h->S, false, false, n_update_of(h), h->S.active_list[par], h->S.active_count + par, h->stream);
     h->host_stats[7] += 1;
@@ -668,16 +673,17 @@ static int ensure_rows(sbc_handle *h, int64_t s) {
     return SBC_OK;
 }
 
-// the kernels of one step in launch order; aux == nullptr: everything on `main`
-static void record_step(sbc_handle *h, unsigned key, const StepArgs &A, cudaStream_t main, cudaStream_t aux) {
-    DevState &S = h->S;
-    if (key & MK_REBUILD) sbc_launch_cell_build(h->P, S, h->cells, main);
+// the kernels of one step in launch order on the state S (positions in S.pv, new ones into S.pv_nxt);
+// aux == nullptr: everything on `main`
+static void record_step(sbc_handle *h, const DevState &S, unsigned key, const StepArgs &A, cudaStream_t main, cudaStream_t aux) {
     cudaStream_t rows_st = main;
     if (aux) {
         cudaEventRecord(h->ev_fork, main);
         cudaStreamWaitEvent(aux, h->ev_fork, 0);
         rows_st = aux;
     }
+    // the cell order is only read by the rows kernel: it is built on that branch, next to the bulk update
+    if (key & MK_REBUILD) sbc_launch_cell_build(h->P, S, h->cells, rows_st);
     if (key & MK_RECV) domain_launch_refresh_recv(h, S, rows_st);   // ghosts of this step's start-of-step positions
     if (h->use_cells) sbc_launch_pair_cells(h->P, S, h->cells, A, rows_st);
     else sbc_launch_pair_rows(h->P, S, A, rows_st);
@@ -687,15 +693,15 @@ static void record_step(sbc_handle *h, unsigned key, const StepArgs &A, cudaStre
         cudaStreamWaitEvent(main, h->ev_join, 0);
     }
     DevState Sn = S;   // what the host sees after the step: the new positions are the current ones
-    Sn.pv = S.pv_nxt;
-    Sn.pv_nxt = S.pv;
-    Sn.tm = S.tm_nxt;
-    Sn.tm_nxt = S.tm;
+    std::swap(Sn.pv, Sn.pv_nxt);
+    std::swap(Sn.tm, Sn.tm_nxt);
     if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
     if (key & MK_SEND) domain_launch_refresh_send(h, Sn, main);
 }
 
-static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, bool send_after) {
+// `count` consecutive steps s, s + 1, ... with the same ingredients (count > 1: no cell build among them) as ONE graph
+// launch: inside a graph the next step's kernels follow at node-to-node latency instead of a launch gap.
+static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, bool send_after, int count = 1) {
     DevState &S = h->S;
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (h->use_cells) if (int rc = ensure_cells(h)) return rc;
@@ -707,17 +713,17 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
         h->nxt_synced = true;
     }
     const unsigned key = (h->pv_parity ? MK_PARITY : 0) | (rebuild ? MK_REBUILD : 0) | (pred_phase ? MK_PRED : 0) |
-                         (recv_first ? MK_RECV : 0) | (send_after ? MK_SEND : 0);
+                         (recv_first ? MK_RECV : 0) | (send_after ? MK_SEND : 0) | ((unsigned)count << 8);
     StepArgs A = {};
     A.step = (uint32_t)s;
     A.n_update = n_update_of(h);
     A.pred_active = pred_phase ? 1 : 0;
     A.net_kill = (pred_phase && S.Npred > 1 && h->hp.pred_kill != 0) ? 1 : 0;
     A.finish = 1;
-    A.ticket_total = (unsigned)(sbc_update_bulk_blocks(A.n_update) +
-                                (h->use_cells ? sbc_pair_cells_blocks(h->P, S, h->cells) : sbc_pair_rows_blocks(S)));
+    A.fresh_cells = rebuild ? 1 : 0;
     const bool graphable = h->use_graphs && !injected && !S.flags && h->stream != nullptr && h->stream != cudaStreamLegacy &&
                            h->stream != cudaStreamPerThread;  // the default streams cannot be captured
+    if (count > 1 && (!graphable || rebuild)) return fail(h, SBC_ERR_STATE, "mk_step: a batch needs graph replay and no cell build");
     if (graphable) {
         if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
         if (h->step_dev_value != s) {   // the step index lives on the device and is advanced by the step itself
@@ -730,7 +736,14 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
             cudaGraph_t graph;
             A.step_dev = h->step_dev;
             SBC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            record_step(h, key, A, h->stream, h->stream2);
+            DevState Sc = S;
+            for (int k = 0; k < count; k++) {
+                A.step = (uint32_t)k;   // offset inside the launch; the base lives in *step_dev
+                record_step(h, Sc, key, A, h->stream, h->stream2);
+                std::swap(Sc.pv, Sc.pv_nxt);
+                std::swap(Sc.tm, Sc.tm_nxt);
+            }
+            sbc_launch_step_advance(h->step_dev, count, h->stream);
             cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
             cudaGraphExec_t exec;
@@ -740,26 +753,40 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
             it = h->graphs.emplace(key, exec).first;
         }
         SBC_CUDA(cudaGraphLaunch(it->second, h->stream));
-        h->step_dev_value = s + 1;
+        h->step_dev_value = s + count;
     } else {
-        record_step(h, key, A, h->stream, nullptr);
+        record_step(h, S, key, A, h->stream, nullptr);
         h->step_dev_value = -1;
     }
     // the new positions are the current ones from here on
-    std::swap(S.pv, S.pv_nxt);
-    std::swap(S.tm, S.tm_nxt);
-    h->pv_parity ^= 1;
-    h->list_step = s + 1;    // the step's kernels appended the agents they re-armed
+    if (count & 1) {
+        std::swap(S.pv, S.pv_nxt);
+        std::swap(S.tm, S.tm_nxt);
+        h->pv_parity ^= 1;
+    }
+    h->list_step = s + count;    // the steps' kernels appended the agents they re-armed
     h->cs_valid = false;
     h->dense.sorted_valid = false;
-    h->host_stats[0]++;
-    h->host_stats[1]++;
-    h->host_stats[7] += (rebuild ? 4 : 0) + (pred_phase ? 1 : 0) + (recv_first ? 1 : 0) + (send_after ? 1 : 0);
+    h->host_stats[0] += count;
+    h->host_stats[1] += count;
+    h->host_stats[7] += (rebuild ? 4 : 0) + count * ((pred_phase ? 1 : 0) + (recv_first ? 1 : 0) + (send_after ? 1 : 0));
     if (h->use_cells) {
         if (rebuild) { h->cells_valid = true; h->cells_age = 0; h->host_stats[6]++; }
-        h->cells_age++;   // the agents moved once more since the build
+        h->cells_age += count;   // the agents moved once more per step since the build
     }
     return SBC_OK;
+}
+
+// how many of the next `want` steps can go into one graph launch: no cell build among them
+static int mk_batch(const sbc_handle *h, int64_t want) {
+    if (!h->use_graphs || h->S.flags || h->S.inj_social || h->S.inj_dir || h->S.inj_k) return 1;
+    if (h->stream == nullptr || h->stream == cudaStreamLegacy || h->stream == cudaStreamPerThread) return 1;
+    int64_t room = want;
+    if (h->use_cells) {
+        if (!h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age) return 1;   // this step rebuilds
+        room = std::min<int64_t>(room, (int64_t)h->cells_max_age - h->cells_age + 1);
+    }
+    return room >= 4 ? 4 : 1;
 }
 
 int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
@@ -823,7 +850,19 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     h->host_stats[7]++;
                 }
             }
-            if (int rc = mk_step(h, s, pred_phase, false, false)) return rc;
+            // plain steps go four to a graph launch: none of them spawns (the spawn kernels above are launched eagerly)
+            int count = mk_batch(h, s_first + n_steps - s);
+            if (count > 1 && S.Npred > 0) {
+                for (int k = 1; k < count; k++) {
+                    const int64_t sk = s + k;
+                    const bool ph = (double)sk >= p.pred_time / dt;
+                    const bool spawn0 = ph && (double)(sk - 1) < p.pred_time / dt;
+                    const bool spawn1 = S.Npred > 1 && ph && needed > 0 && ((int)sk - (int)(p.pred_time / dt)) % needed == 0;
+                    if (ph != pred_phase || spawn0 || spawn1) { count = 1; break; }
+                }
+            }
+            if (int rc = mk_step(h, s, pred_phase, false, false, count)) return rc;
+            s += count - 1;
         }
     }
     h->host_stats[5] += (unsigned long long)n_steps * (unsigned long long)S.N * (unsigned long long)S.R;
@@ -968,6 +1007,27 @@ int sbc_debug_flags(sbc_handle *h, int enable, uint8_t *out) {
         SBC_CUDA(cudaMemset(h->flags_dev, 0, total));
     }
     S.flags = enable ? h->flags_dev : nullptr;
+    return SBC_OK;
+}
+
+/* profiling hook: timeline of the multi-kernel step (see include/sbc.h) */
+int sbc_debug_trace(sbc_handle *h, int enable, uint64_t *out) {
+    if (!h) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    const size_t n = (size_t)SBC_TRACE_STEPS * SBC_TR_KERNELS * 2;
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    if (out && h->S.trace) SBC_CUDA(cudaMemcpy(out, h->S.trace, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (enable) {
+        if (!h->trace_dev) SBC_CUDA(dev_alloc(&h->trace_dev, n));
+        std::vector<unsigned long long> init(n);
+        for (size_t k = 0; k < n; k++) init[k] = (k & 1) ? 0ull : ~0ull;   // min of the entries, max of the exits
+        SBC_CUDA(cudaMemcpy(h->trace_dev, init.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    unsigned long long *want = enable ? h->trace_dev : nullptr;
+    if (want != h->S.trace) {
+        invalidate_graphs(h);   // the pointer is baked into captured steps
+        h->S.trace = want;
+    }
     return SBC_OK;
 }
 
@@ -1265,6 +1325,16 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         if (int rc = ensure_cells(h)) return rc;
         // the exchange behind this step is a full one when the NEXT step rebuilds the cell order
         const bool rebuild_now = !h->cells_valid || h->cells_age > h->cells_max_age;
+        // four refresh steps (receive ... send) in one graph launch when none of them ends in a full exchange
+        int count = h->recv_pending ? mk_batch(h, s_first + n_steps - s) : 1;
+        if (count > 1 && h->cells_age + count > h->cells_max_age) count = 1;
+        if (count > 1) {
+            if (int rc = mk_step(h, s, false, true, true, count)) return rc;
+            h->dom_last_full = false;
+            h->dom_epoch += count;
+            s += count - 1;
+            continue;   // recv_pending stays set: the last step's records are still on their way
+        }
         const int age_after = (rebuild_now ? 0 : h->cells_age) + 1;
         const bool full_after = age_after > h->cells_max_age;
         if (int rc = mk_step(h, s, false, h->recv_pending, !full_after)) return rc;

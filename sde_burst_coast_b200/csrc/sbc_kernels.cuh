@@ -38,29 +38,59 @@ struct DevState {
     float *inj_dir;
     uint32_t *inj_k;
     uint8_t *flags;      // [R*N] branch flags OR-ed over steps (test hook), may be nullptr
-    // burst-gated rows: two lists by parity of the step. The rows of step s are in active_list[s & 1] - written by the
-    // update of step s - 1 (the agents it re-armed), or by the compaction kernel after a state change
-    int *active_list[2];   // [R*N] each
-    int *active_count;     // [2] + [2] block ticket of the step's two kernels
+    // burst-gated rows: three lists in rotation. The rows of step s are in active_list[s % 3] - written by the update of
+    // step s - 1 (the agents it re-armed), or by the compaction kernel after a state change; step s appends the rows of
+    // step s + 1 to list (s + 1) % 3 and clears the counter of list (s + 2) % 3, which nobody touches during step s
+    int2 *active_list[3];  // [R*N] each: {slot, the slot's cell key at list time (0 without a cell list)}
+    int *active_count;     // [3] (+ 1 pad)
+    const uint32_t *cell_key;  // cell key of every slot as of the last cell build (nullptr without a cell list)
     // counters
     unsigned long long *stats; // [8] see sbc_get_stats
+    // timeline of the multi-kernel step (test / profiling hook, sbc_debug_trace): per step (mod SBC_TRACE_STEPS) and kernel
+    // id the wall-clock time the first block started and the last block ended, nullptr = off
+    unsigned long long *trace;
 };
+#define SBC_TRACE_STEPS 1024
+enum { SBC_TR_ROWS = 0, SBC_TR_BULK = 1, SBC_TR_RECV = 2, SBC_TR_SEND = 3, SBC_TR_LASTSTART = 4, SBC_TR_KERNELS = 8 };
 
 // per-launch constants of one multi-kernel step (rows kernel + update_bulk_kernel, update.cu)
 struct StepArgs {
-    uint32_t step;           // step index when step_dev == nullptr
-    uint32_t *step_dev;      // device-resident step index of a graph-replayed step (advanced by sbc_step_close)
+    uint32_t step;           // step index; with step_dev the offset of this step inside its graph launch
+    const uint32_t *step_dev;  // graph-replayed steps: device-resident index of the launch's first step (the last node of
+                             // the graph moves it on)
     int n_update;            // slots [0, n_update) can hold agents that are updated (a slab: own_cap; otherwise R * N)
     int net_kill;            // a fish net is present and kills: FishNetKill is evaluated per agent
     int pred_active;         // predator phase: burst-starting rows evaluate IntCalcPred
     int finish;              // rows kernel: 1 = update the rows (a step), 0 = only write acc / cnt (test hook)
-    unsigned ticket_total;   // blocks of the step's two kernels together; 0 = nobody closes the step
+    int fresh_cells;         // the cell order was rebuilt after the rows were listed: their cached cell keys are stale
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t sbc_step_of(const StepArgs &A) { return A.step_dev ? *A.step_dev + A.step : A.step; }
+#endif
 
 // prey<-predator detection (IntCalcPred, /root/reference/src/agents_interact.cpp:252-292) of ONE burst-starting row by
 // ONE warp: a lane takes four predators per Philox block; flee sums and counter go to acc[6..7] / cnt[3] of the row.
 // Called by the pair kernels right after the row's zone sums (every lane of the warp must call it).
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long sbc_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// every block calls this at entry (begin) and exit: min of the entries, max of the exits
+__device__ __forceinline__ void sbc_trace(const DevState &S, uint32_t step, int kid, bool begin) {
+    if (!S.trace || threadIdx.x != 0) return;
+    unsigned long long *slot = S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + kid) * 2;
+    const unsigned long long now = sbc_now_ns();
+    if (begin) {
+        atomicMin(slot, now);
+        // when the LAST block of the kernel started (kernel id + SBC_TR_LASTSTART, entry 1): tells a late dispatch of
+        // the grid from a slow kernel
+        atomicMax(S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + kid + SBC_TR_LASTSTART) * 2 + 1, now);
+    } else {
+        atomicMax(slot + 1, now);
+    }
+}
 // agent state in / out of the SoA arrays. `with_cs`: the ensemble kernels' cached heading vector
 __device__ __forceinline__ void sbc_load_agent(const DevParams &P, const DevState &S, size_t g, AgentState &a, bool with_cs) {
     const float4 p = S.pv[g];
@@ -135,28 +165,37 @@ __device__ __forceinline__ void sbc_detect_row_warp(const DevParams &P, const De
 // S.pv_nxt / hv / force / tm_nxt. `acc` are the row's zone and flee sums (only read when the agent starts a burst).
 // Returns true when the agent starts a burst in the NEXT step (it was re-armed and is still alive).
 __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, uint32_t tm,
-                                                 uint32_t step, const StepArgs &A) {
-    const int N = S.N;
-    const uint32_t rep = (uint32_t)(g / N);
-    // Philox counters use the GLOBAL agent id, so a decomposed swarm draws what the whole swarm would
-    const uint32_t i = S.gid ? S.gid[g] : (uint32_t)(g - (size_t)rep * N);
+                                                 float4 p, float2 h, float2 f, uint32_t step, const StepArgs &A) {
     AgentState a;
+    a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
+    a.phi = h.x; a.vproj = h.y;
+    a.fx = f.x; a.fy = f.y;
+    a.bin_step = sbc_tm_bin(tm, P); a.stb = sbc_tm_stb(tm, P);
     {
-        const float4 p = S.pv[g];
-        const float2 h = S.hv[g];
-        const float2 f = S.force[g];
-        a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
-        a.phi = h.x; a.vproj = h.y;
-        sincosf(a.phi, &a.su, &a.cu);
-        a.fx = f.x; a.fy = f.y;
-        a.bin_step = sbc_tm_bin(tm, P); a.stb = sbc_tm_stb(tm, P);
+        // heading vector. Where no wall ever edits the velocity (open and periodic domains) v = vproj (cos, sin)(phi)
+        // holds at every step boundary (:227-233), so u = v / |v| saves the sincosf; otherwise, and for an agent at
+        // rest, it comes from phi as in the reference (:197)
+        const float v2 = __fmaf_rn(a.vx, a.vx, a.vy * a.vy);
+        if (P.BC <= 0 && v2 > 1e-30f) {
+            const float rinv = rsqrtf(v2);
+            a.cu = a.vx * rinv;
+            a.su = a.vy * rinv;
+        } else {
+            sincosf(a.phi, &a.su, &a.cu);
+        }
     }
     const bool first = (a.bin_step == P.burst_steps);
     const bool rearm = (a.stb <= 1);
     double u_social = 0.0;
     float u_dir = 0.f;
     uint32_t k_next = 1;
+    uint32_t rep = 0;
+    if (first || rearm || A.net_kill) {   // (the replicate index costs an integer division: only where it is used)
+        rep = (S.R > 1) ? (uint32_t)g / (uint32_t)S.N : 0u;
+    }
     if (first || rearm) {
+        // Philox counters use the GLOBAL agent id, so a decomposed swarm draws what the whole swarm would
+        const uint32_t i = S.gid ? S.gid[g] : (uint32_t)g - rep * (uint32_t)S.N;
         const uint4 q = sbc_draw(P, rep, i, step, SBC_SLOT_DECISION);
         u_social = S.inj_social ? S.inj_social[g] : (double)q.x * (1.0 / 4294967296.0);
         u_dir = S.inj_dir ? S.inj_dir[g] : (float)(q.y >> 8) * (1.0f / 16777216.0f);
@@ -191,34 +230,36 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
     return alive && a.bin_step == P.burst_steps;
 }
 
-// Every block of the step's two kernels ends here; the block that arrives last closes the step: the rows of this step
-// are consumed (their counter is cleared for the update of step + 1, which appends the rows of step + 2 there) and the
-// device-resident step index of a graph-replayed step moves on. Every thread of the block must call it.
-__device__ __forceinline__ void sbc_step_close(const DevState &S, const StepArgs &A, uint32_t step) {
-    if (A.ticket_total == 0u) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        unsigned *ticket = reinterpret_cast<unsigned *>(S.active_count + 2);
-        const unsigned t = atomicAdd(ticket, 1u);
-        if (t == A.ticket_total - 1u) {
-            *ticket = 0u;
-            S.active_count[step & 1u] = 0;
-            if (A.step_dev) *A.step_dev = step + 1u;
-            __threadfence();
-        }
-    }
+// rows kernel, lane / thread 0 of the group that sweeps row g: the row's own state is fetched BEFORE the sweep (the loads
+// overlap the sweep's dependent chain), the row is updated after it and passed on if it re-armed
+struct RowState {
+    float4 p;
+    float2 hv, f;
+    uint32_t tm;
+    uint8_t al;
+};
+__device__ __forceinline__ RowState sbc_row_prefetch(const DevState &S, size_t g) {
+    RowState r;
+    r.al = S.alive[g];
+    r.tm = S.tm[g];
+    r.p = S.pv[g];
+    r.hv = S.hv[g];
+    r.f = S.force[g];
+    return r;
 }
-// rows kernel, lane / thread 0 of the group that swept row g: update the row and pass it on if it re-armed
-__device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, uint32_t step,
-                                               const StepArgs &A) {
-    if (!S.alive[g]) return;   // killed after it was listed
-    const uint32_t tm = S.tm[g];
-    if (sbc_update_agent(P, S, g, acc, tm, step, A)) {
-        const int par = (int)(step & 1u);
-        const int at = atomicAdd(S.active_count + (par ^ 1), 1);
-        S.active_list[par ^ 1][at] = (int)g;
-    }
+// An agent whose steps_till_burst reads <= 1 at the start of a step is re-armed by that step (agents_dynamics.cpp:
+// 184-188, 250-252) and starts a burst in the next one: it can be put on the next step's row list before it is
+// updated, so that the latency of the list counter's atomic hides behind the update arithmetic.
+__device__ __forceinline__ bool sbc_will_rearm(uint32_t tm, const DevParams &P) { return sbc_tm_stb(tm, P) <= 1u; }
+__device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, const RowState &r,
+                                               uint32_t step, const StepArgs &A) {
+    if (!r.al) return;   // killed after it was listed
+    int at = -1;
+    const int nxt = (int)((step + 1u) % 3u);
+    if (sbc_will_rearm(r.tm, P)) at = atomicAdd(S.active_count + nxt, 1);
+    sbc_update_agent(P, S, g, acc, r.tm, r.p, r.hv, r.f, step, A);
+    // (an agent the net caught this step is dropped by the next rows kernel)
+    if (at >= 0) S.active_list[nxt][at] = make_int2((int)g, S.cell_key ? (int)S.cell_key[g] : 0);   // (after the build, if any)
 }
 #endif
 
@@ -236,24 +277,51 @@ void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateSta
 void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
 
+// Launch with the highest stream priority as a LAUNCH ATTRIBUTE: it is recorded in the kernel node of a captured graph,
+// so the rows kernel's few blocks are dispatched ahead of the thousands of blocks of the bulk update that is launched
+// beside it (a stream's own priority does not survive capture).
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+static inline cudaError_t sbc_launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static int hi = 1 << 30;
+    if (hi == (1 << 30)) {
+        int lo = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = hi;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // --- all-pairs three-zone pass -------------------------------------------------------------------
 // rows of a fresh state into list / count (update.cu); the steps themselves keep the lists up to date
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int *list, int *count,
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int2 *list, int *count,
                              cudaStream_t st);
 // burst-gated rows (bin_step == burst_steps) against all agents of their swarm, pair_allpairs.cu. The rows are
-// S.active_list[step & 1]; A.finish: the rows are updated as well (one of the two kernels of a step)
+// S.active_list[step % 3]; A.finish: the rows are updated as well (one of the two kernels of a step)
 int sbc_pair_rows_blocks(const DevState &S);
 void sbc_launch_pair_rows(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st);
 // burst-gated rows through a cell list (celllist.cu), single large swarm
 struct CellScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
     int *idx_in = nullptr, *idx_out = nullptr;   // idx_out[r] = agent id at sorted position r
-    int *cell_start = nullptr, *cell_end = nullptr;
+    int2 *cell_range = nullptr;                   // [ncells] {first, one past last} sorted position of the cell's agents
     int *bbox = nullptr;
     void *geom = nullptr;                         // CellGeom on the device
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0, ncells = 0;
     int key_bits = 0, max_per_axis = 0;
+    bool counting = false;                        // sparse grid: counting-sort build (cnt / start: [ncells + 1])
+    int *cnt = nullptr, *start = nullptr;
     float skin = 0.f;                             // cells are att_range + skin wide
 };
 bool sbc_cells_supported(const DevParams &P, int N, int R);
@@ -327,6 +395,7 @@ void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st
 int sbc_update_bulk_blocks(int n_update);
 void sbc_launch_update_bulk(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st);
 void sbc_launch_refresh_cs(const DevState &S, cudaStream_t st);
+void sbc_launch_step_advance(uint32_t *step_dev, int count, cudaStream_t st);
 
 // --- predator spawn / move / kill (predator.cu) ------------------------------------------------
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,

@@ -10,43 +10,64 @@
 //     (pv 16 + hv 8 + force 8 + timers 4 read and written: 72 B per agent-step, HBM-bound).
 // Both read start-of-step positions from S.pv and write the new ones to S.pv_nxt (Step()'s semantics,
 // swarmdyn.cpp:143-204: interactions see the positions at the start of the step), both append the agents they
-// re-arm to the row list of the NEXT step, and whichever block of the two kernels finishes last closes the step
-// (sbc_step_close): no compaction pass, no dependent launch between pair pass and update.
+// re-arm to the row list of the NEXT step (three lists in rotation, so nobody has to wait for a list to be consumed):
+// no compaction pass, no dependent launch between pair pass and update.
 #include "sbc_kernels.cuh"
 
 namespace {
 
 __global__ void __launch_bounds__(256)
 update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) {
-    const uint32_t step = A.step_dev ? *A.step_dev : A.step;
-    const int par = (int)(step & 1u);
+    const uint32_t step = sbc_step_of(A);
+    const int nxt = (int)((step + 1u) % 3u);
     const int lane = threadIdx.x & 31;
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    bool rearmed = false;
-    if (g < (size_t)A.n_update && S.alive[g]) {
-        const uint32_t tm = S.tm[g];
-        if (sbc_tm_bin(tm, P) != P.burst_steps) {   // rows that start a burst belong to the rows kernel
-            RowAcc acc;
-            row_acc_clear(acc);
-            rearmed = sbc_update_agent(P, S, g, acc, tm, step, A);
-        }
+    sbc_trace(S, step, SBC_TR_BULK, true);
+    // the list after next is idle during this step: clear its counter for the step that appends to it
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.active_count[(step + 2u) % 3u] = 0;
+    bool mine = false, rearm = false;
+    uint8_t al = 0;
+    uint32_t tm = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 hv = make_float2(0.f, 0.f), f = make_float2(0.f, 0.f);
+    if (g < (size_t)A.n_update) {
+        // every load is issued before the first one is looked at: one memory round trip per agent instead of three
+        al = S.alive[g];
+        tm = S.tm[g];
+        p = S.pv[g];
+        hv = S.hv[g];
+        f = S.force[g];
+        mine = al && sbc_tm_bin(tm, P) != P.burst_steps;   // rows that start a burst belong to the rows kernel
+        rearm = mine && sbc_will_rearm(tm, P);
     }
-    // warp-aggregated append to the rows of the next step
-    const unsigned m = __ballot_sync(0xffffffffu, rearmed);
+    // warp-aggregated append to the rows of the next step, issued before the update: the counter's atomic returns
+    // while the warp computes
+    const unsigned m = __ballot_sync(0xffffffffu, rearm);
+    int base = 0, key = 0;
+    if (m && lane == 0) base = atomicAdd(S.active_count + nxt, __popc(m));
+    // the agent's cell key travels with the list entry (one round trip less for the row) - unless the cell order is
+    // being rebuilt beside this kernel: -1 sends the row to the key array
+    if (rearm && S.cell_key) key = A.fresh_cells ? -1 : (int)S.cell_key[g];
+    if (mine) {
+        RowAcc acc;
+        row_acc_clear(acc);
+        sbc_update_agent(P, S, g, acc, tm, p, hv, f, step, A);
+    }
     if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(S.active_count + (par ^ 1), __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (rearmed) S.active_list[par ^ 1][base + __popc(m & ((1u << lane) - 1u))] = (int)g;
+        if (rearm) S.active_list[nxt][base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)g, key);
     }
-    sbc_step_close(S, A, step);
+    sbc_trace(S, step, SBC_TR_BULK, false);
 }
+
+// last node of a graph-replayed launch of `count` steps: the device-resident step index moves on
+__global__ void step_advance_kernel(uint32_t *step_dev, uint32_t count) { *step_dev += count; }
 
 // rows of a fresh state (after sbc_set_state, a full domain exchange, an ensemble launch ...): the agents with
 // bin_step == burst_steps, four per thread, warp-aggregated append. The order of the list does not matter - every
 // row writes only its own state.
 __global__ void __launch_bounds__(256)
-compact_active_kernel(const __grid_constant__ DevParams P, DevState S, int all_alive, int n_scan, int *list, int *count) {
+compact_active_kernel(const __grid_constant__ DevParams P, DevState S, int all_alive, int n_scan, int2 *list, int *count) {
     const size_t total = (size_t)n_scan;
     const size_t quads = (total + 3) / 4;
     const int lane = threadIdx.x & 31;
@@ -84,7 +105,7 @@ compact_active_kernel(const __grid_constant__ DevParams P, DevState S, int all_a
         if (lane == 31) base = atomicAdd(count, incl);
         base = __shfl_sync(0xffffffffu, base, 31) + incl - n_mine;
         for (int k = 0; k < 4; k++)
-            if ((act >> k) & 1u) list[base++] = (int)(g0 + k);
+            if ((act >> k) & 1u) list[base++] = make_int2((int)(g0 + k), S.cell_key ? (int)S.cell_key[g0 + k] : 0);
     }
 }
 
@@ -119,12 +140,16 @@ void sbc_launch_update_bulk(const DevParams &P, const DevState &S, const StepArg
 
 // compact the rows that start a burst (or, all_alive, every alive agent) of slots [0, n_scan) into list / count
 // (count must be zero); `clear` also zeroes every row's accumulators (the test hook reads rows that were not active)
-void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int *list, int *count,
+void sbc_launch_compact_rows(const DevParams &P, const DevState &S, bool clear, bool all_alive, int n_scan, int2 *list, int *count,
                              cudaStream_t st) {
     const size_t total = (size_t)S.N * S.R;
     const int blocks = (int)min((size_t)148 * 8, (total + 255) / 256);
     if (clear) clear_acc_kernel<<<blocks, 256, 0, st>>>(S);
     compact_active_kernel<<<blocks, 256, 0, st>>>(P, S, all_alive ? 1 : 0, n_scan, list, count);
+}
+
+void sbc_launch_step_advance(uint32_t *step_dev, int count, cudaStream_t st) {
+    step_advance_kernel<<<1, 1, 0, st>>>(step_dev, (uint32_t)count);
 }
 
 void sbc_launch_refresh_cs(const DevState &S, cudaStream_t st) {

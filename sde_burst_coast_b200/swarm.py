@@ -50,6 +50,7 @@ ABI = [
     ('sbc_debug_flags', ctypes.c_int, [_vp, ctypes.c_int, _u8p]),
     ('sbc_debug_force_multikernel', ctypes.c_int, [_vp, ctypes.c_int]),
     ('sbc_get_stats', ctypes.c_int, [_vp, _u64p]),
+    ('sbc_debug_trace', ctypes.c_int, [_vp, ctypes.c_int, _u64p]),
     ('sbc_bench_pair_pass', ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
     ('sbc_set_global_ids', ctypes.c_int, [_vp, _u32p]),
     ('sbc_get_global_ids', ctypes.c_int, [_vp, _u32p]),
@@ -244,6 +245,12 @@ class Swarm:
     def force_multikernel(self, on=True):
         """True / 1: multi-kernel path; 2: one-block kernel instead of the cluster kernel; False / 0: automatic."""
         self._check(self.lib.sbc_debug_force_multikernel(self.h, int(on)))
+
+    def trace(self, enable=True, read=False):
+        """Timeline hook (sbc_debug_trace): returns uint64 [1024][8][2] {start, end} ns by (step mod 1024, kernel) when read."""
+        out = np.zeros((1024, 8, 2), dtype=np.uint64) if read else None
+        self._check(self.lib.sbc_debug_trace(self.h, 1 if enable else 0, _ptr(out, _u64p)))
+        return out
 
     def stats(self):
         out = np.zeros(8, dtype=np.uint64)
