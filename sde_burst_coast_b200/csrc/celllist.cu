@@ -146,7 +146,7 @@ __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevSta
                                                 const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, int i,
                                                 int t /* thread in group */, int *pref /* [10] shared, per group */,
                                                 int *first /* [9] shared, per group */, RowAcc &A, unsigned &n_amb,
-                                                unsigned long long &n_cand) {
+                                                unsigned long long &n_cand, const StepArgs &SA, uint32_t step) {
     const float4 pi = S.pv[i];
     // the row's cell at build time (agents alive now were alive then: nobody is born between builds)
     const int ck = (int)build_key[i];
@@ -180,6 +180,7 @@ __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevSta
     if (TPR <= 32) __syncwarp(); else __syncthreads();
     const int total = pref[9];
     row_acc_clear(A);
+    if (SA.ghost_ready && (cx <= SA.edge_lo || cx >= SA.edge_hi)) sbc_wait_ghosts(SA, step);   // a row next to a slab edge
 #pragma unroll 2
     for (int q = t; q < total; q += TPR) {
         int c = 0;
@@ -187,7 +188,8 @@ __device__ __forceinline__ void cells_row_sweep(const DevParams &P, const DevSta
         for (int k = 1; k < 9; k++) c += (q >= pref[k]) ? 1 : 0;
         const int j = sidx[first[c] + (q - pref[c])];
         if (j == i) continue;
-        const float4 pj = S.pv[j];   // current position (NaN if the agent died since the build)
+        const float4 pj = __ldcg(S.pv + j);   // current position (NaN if the agent died since the build); past L1: a ghost's
+                                              // slot may have been written by the exchange while this kernel runs
         float dx = pj.x - pi.x, dy = pj.y - pi.y;
         if (PERIODIC) {
             dx = sbc_delta_pbc(pi.x, pj.x, P);
@@ -250,7 +252,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
         if (SA.finish && threadIdx.x == 0) rs = sbc_row_prefetch(S, (size_t)i);
         RowAcc A;
         cells_row_sweep<PERIODIC, CELLS_BLOCK_THREADS>(P, S, g, cell_range, build_key, sidx, i, threadIdx.x, pref, first, A,
-                                                 n_amb, n_cand);
+                                                 n_amb, n_cand, SA, step);
         sbc_block_reduce_row<CELLS_BLOCK_THREADS / 32>(A, shf, shi);
         if (SA.pred_active) {   // IntCalcPred of this row by the last warp (thread 0 holds the zone sums)
             if (threadIdx.x >= CELLS_BLOCK_THREADS - 32) {
@@ -313,35 +315,36 @@ __device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, 
 // together, then their positions together, so the dependent chain of a row is list -> key -> cell bounds -> indices ->
 // positions, five memory round trips whatever the cell holds. Few warps carry a step's rows (about 0.5 % of the
 // agents), which leaves the register file to the bulk update that runs beside this kernel.
-template <bool PERIODIC>
-__global__ void __launch_bounds__(CELLS_THREADS, 8)   // 64 registers: the whole grid is resident on a quarter of the register file
-pair_cells_lanes_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeom *__restrict__ geom,
-                        const int2 *__restrict__ cell_range,
-                        const uint32_t *__restrict__ build_key, const int *__restrict__ sidx, StepArgs SA) {
-    const uint32_t step = sbc_step_of(SA);
-    const int par = (int)(step % 3u);
-    const int2 *__restrict__ list = S.active_list[par];
-    constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW;
+// The row's own update, NOT inlined: the interior and the edge blocks of the lanes kernel must run the very same
+// instructions - an inlined copy per call site may contract floating-point expressions differently, and a row's
+// result must not depend on which list it was on. (P, S, A are __grid_constant__ kernel parameters: no copies.)
+static __device__ __noinline__ void cells_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc,
+                                                     const RowState &r, uint32_t step, const StepArgs &A) {
+    sbc_finish_row(P, S, g, acc, r, step, A);
+}
+
+// One pass of a group of eight lanes over the rows of `list`: lane t walks cell t of the row's 3 x 3 block (lane 0 also
+// the ninth). The sorted indices of up to eight candidates per cell are loaded together, then their positions together,
+// so the dependent chain of a row is list -> (key) -> cell bounds -> indices -> positions whatever the cell holds.
+// EDGE: the rows next to a slab edge of a decomposed swarm - everything up to the indices goes on while the ghosts
+// are on their way; the group holds right before it reads positions (past L1: the exchange writes them meanwhile).
+template <bool PERIODIC, bool EDGE>
+__device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevState &S, const CellGeom &g,
+                                                 const int2 *__restrict__ cell_range, const uint32_t *__restrict__ build_key,
+                                                 const int *__restrict__ sidx, const StepArgs &SA, uint32_t step,
+                                                 const int2 *__restrict__ list, int n_rows, int bid, int nblk, unsigned &n_amb,
+                                                 unsigned &n_cand) {
+    constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW, NB = 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / TPR, t = lane % TPR;
     const unsigned gmask = ((1u << TPR) - 1u) << (grp * TPR);
-    // the first list entry is fetched together with the row count, not after it
-    const int k_first = (blockIdx.x * WPB + warp) * GPW + grp;
-    const int cap = S.N * S.R;
-    int2 e_next = (k_first < cap) ? list[k_first] : make_int2(0, 0);
-    const int n_rows = S.active_count[par];
-    const CellGeom g = *geom;
     const float qnan = __int_as_float(0x7fc00000);
-    unsigned n_amb = 0, n_cand = 0;
-    sbc_trace(S, step, SBC_TR_ROWS, true);
     // warp-uniform loop: the groups of a warp take GPW consecutive rows per pass
-    for (int k0 = (blockIdx.x * WPB + warp) * GPW; k0 < n_rows; k0 += gridDim.x * GPB) {
+    for (int k0 = (bid * WPB + warp) * GPW; k0 < n_rows; k0 += nblk * GPB) {
         const int k = k0 + grp;
         const bool has = k < n_rows;
-        const int2 e = e_next;
-        const int k_nxt = k + gridDim.x * GPB;
-        if (k_nxt < n_rows) e_next = list[k_nxt];
-        const int i = has ? e.x : 0;
+        const int2 e = has ? list[k] : make_int2(0, 0);
+        const int i = e.x;
         RowState rs = {};
         if (SA.finish && t == 0 && has) rs = sbc_row_prefetch(S, (size_t)i);
         const float4 pi = has ? S.pv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -374,16 +377,21 @@ pair_cells_lanes_kernel(const __grid_constant__ DevParams P, DevState S, const C
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             n_cand += (unsigned)(r1[u] - r0[u]);
-            for (int r = r0[u]; r < r1[u]; r += 4) {
-                int jj[4];
-                float4 pj[4];
+            for (int r = r0[u]; r < r1[u]; r += NB) {
+                int jj[NB];
 #pragma unroll
-                for (int b = 0; b < 4; b++) jj[b] = (r + b < r1[u]) ? sidx[r + b] : -1;
+                for (int b = 0; b < NB; b++) jj[b] = (r + b < r1[u]) ? sidx[r + b] : -1;
+                if (EDGE) sbc_wait_ghosts(SA, step);
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    pj[b] = (jj[b] >= 0 && jj[b] != i) ? S.pv[jj[b]] : make_float4(qnan, qnan, 0.f, 0.f);
+                for (int h = 0; h < NB; h += 4) {
+                    float4 pj[4];
 #pragma unroll
-                for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
+                    for (int b = 0; b < 4; b++)
+                        pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
+                                : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
+                }
             }
         }
         A.c_rep = __reduce_add_sync(gmask, A.c_rep);
@@ -397,16 +405,128 @@ pair_cells_lanes_kernel(const __grid_constant__ DevParams P, DevState S, const C
         }
         if (t == 0 && has) {
             cells_row_store(S, i, A);
-            if (SA.finish) sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
+            if (SA.finish) cells_finish_row(P, S, (size_t)i, A, rs, step, SA);
         }
         __syncwarp();
+    }
+}
+
+// The rows next to a slab edge while the exchange is in flight (GHOSTS): a whole WARP per row, three lanes per cell of
+// the 3 x 3 block, so that a lane holds at most four candidates of a cell of up to twelve agents. Everything up to the
+// candidates' indices goes on while the ghosts are on their way; after the wait ONE round of position loads (past L1:
+// the exchange wrote them meanwhile) is all that is left before the row's update. These rows are few (two cell columns
+// per slab edge); their sums are accumulated in another - equally fixed - order than the eight-lane sweep's.
+template <bool PERIODIC>
+__device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const DevState &S, const CellGeom &g,
+                                                     const int2 *__restrict__ cell_range, const uint32_t *__restrict__ build_key,
+                                                     const int *__restrict__ sidx, const StepArgs &SA, uint32_t step,
+                                                     const int2 *__restrict__ list, int n_rows, int bid, int nblk, unsigned &n_amb,
+                                                     unsigned &n_cand) {
+    constexpr int WPB = CELLS_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tc = lane / 3, sub = lane % 3;   // cell of the 3 x 3 block (lanes 27..31 idle), place among its three lanes
+    const float qnan = __int_as_float(0x7fc00000);
+    for (int k = bid * WPB + warp; k < n_rows; k += nblk * WPB) {
+        const int2 e = list[k];
+        const int i = e.x;
+        RowState rs = {};
+        if (SA.finish && lane == 0) rs = sbc_row_prefetch(S, (size_t)i);
+        const float4 pi = S.pv[i];
+        const int ck = (SA.fresh_cells || e.y < 0) ? (int)build_key[i] : e.y;
+        const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
+        int r0 = 0, r1 = 0;
+        if (tc < 9) {
+            int yy = cy + tc / 3 - 1, xx = cx + tc % 3 - 1;
+            bool ok = true;
+            if (PERIODIC) {
+                yy += (yy < 0) ? g.ncy : 0; yy -= (yy >= g.ncy) ? g.ncy : 0;
+                xx += (xx < 0) ? g.ncx : 0; xx -= (xx >= g.ncx) ? g.ncx : 0;
+            } else {
+                ok = yy >= 0 && yy < g.ncy && xx >= 0 && xx < g.ncx;
+            }
+            if (ok) {
+                const int2 cr = cell_range[yy * g.ncx + xx];
+                r0 = cr.x;
+                r1 = cr.y;
+            }
+        }
+        if (sub == 0) n_cand += (unsigned)(r1 - r0);
+        RowAcc A;
+        row_acc_clear(A);
+        for (int r = r0 + sub; r < r1; r += 12) {
+            int jj[4];
+            float4 pj[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) jj[b] = (r + 3 * b < r1) ? sidx[r + 3 * b] : -1;
+            sbc_wait_ghosts(SA, step);
+            if (S.trace) {   // when the first / last waiting lane of the step got through (kernel id 7)
+                unsigned long long *w = S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + 7) * 2;
+                const unsigned long long now = sbc_now_ns();
+                atomicMin(w, now);
+                atomicMax(w + 1, now);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                pj[b] = (jj[b] >= 0 && jj[b] != i) ? __ldcg(S.pv + jj[b]) : make_float4(qnan, qnan, 0.f, 0.f);
+#pragma unroll
+            for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
+        }
+        A.c_rep = __reduce_add_sync(0xffffffffu, A.c_rep);
+        A.c_alg = __reduce_add_sync(0xffffffffu, A.c_alg);
+        A.c_att = __reduce_add_sync(0xffffffffu, A.c_att);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A.rep_x += __shfl_xor_sync(0xffffffffu, A.rep_x, o); A.rep_y += __shfl_xor_sync(0xffffffffu, A.rep_y, o);
+            A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o); A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
+            A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o); A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
+        }
+        if (lane == 0) {
+            cells_row_store(S, i, A);
+            if (SA.finish) cells_finish_row(P, S, (size_t)i, A, rs, step, SA);
+        }
+        __syncwarp();
+    }
+}
+
+// sparse neighbourhoods (a few agents per cell): EIGHT lanes per active row, four rows per warp. Few warps carry a step's
+// rows (about 0.5 % of the agents), which leaves the register file to the bulk update that runs beside this kernel.
+// Decomposed swarm: the last SA.edge_blocks blocks of the grid take the rows next to a slab edge (listed apart by
+// whoever re-armed them); with GHOSTS they wait for the exchange that runs beside this kernel. The other blocks never
+// see a ghost and never wait.
+template <bool PERIODIC, bool GHOSTS>
+__global__ void __launch_bounds__(CELLS_THREADS, 8)   // 64 registers: the whole grid is resident on a quarter of the register file
+pair_cells_lanes_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
+                        const CellGeom *__restrict__ geom, const int2 *__restrict__ cell_range,
+                        const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
+                        const __grid_constant__ StepArgs SA) {
+    const uint32_t step = sbc_step_of(SA);
+    const int par = (int)(step % 3u);
+    const int n_main = (int)gridDim.x - SA.edge_blocks;
+    const bool edge_part = (int)blockIdx.x >= n_main;
+    const CellGeom g = *geom;
+    const int lane = threadIdx.x & 31;
+    unsigned n_amb = 0, n_cand = 0;
+    if (!edge_part) {
+        sbc_trace(S, step, SBC_TR_ROWS, true);
+        cells_lanes_rows<PERIODIC, false>(P, S, g, cell_range, build_key, sidx, SA, step, S.active_list[par], S.active_count[par],
+                                          (int)blockIdx.x, n_main, n_amb, n_cand);
+    } else if (GHOSTS) {
+        if (S.trace && threadIdx.x == 0)
+            atomicMin(S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + SBC_TR_EDGE) * 2, sbc_now_ns());
+        cells_warp_edge_rows<PERIODIC>(P, S, g, cell_range, build_key, sidx, SA, step, S.edge_list[par], S.active_count[4 + par],
+                                       (int)blockIdx.x - n_main, SA.edge_blocks, n_amb, n_cand);
+    } else {
+        cells_lanes_rows<PERIODIC, false>(P, S, g, cell_range, build_key, sidx, SA, step, S.edge_list[par], S.active_count[4 + par],
+                                          (int)blockIdx.x - n_main, SA.edge_blocks, n_amb, n_cand);
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
     if (lane == 0 && n_amb) atomicAdd(S.stats + 4, (unsigned long long)n_amb);
     n_cand = __reduce_add_sync(0xffffffffu, n_cand);
     if (lane == 0 && n_cand) atomicAdd(S.stats + 3, (unsigned long long)n_cand);
     __syncthreads();
-    sbc_trace(S, step, SBC_TR_ROWS, false);
+    if (!edge_part) sbc_trace(S, step, SBC_TR_ROWS, false);
+    else if (S.trace && threadIdx.x == 0)   // the edge blocks' last exit, apart (kernel id SBC_TR_EDGE, entry 1)
+        atomicMax(S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + SBC_TR_EDGE) * 2 + 1, sbc_now_ns());
 }
 
 // the same neighbourhoods in the predator phase: one WARP per active row, which also evaluates IntCalcPred for it
@@ -432,7 +552,7 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
         if (SA.finish && lane == 0) rs = sbc_row_prefetch(S, (size_t)i);
         RowAcc A;
         cells_row_sweep<PERIODIC, 32>(P, S, g, cell_range, build_key, sidx, i, lane, pref[warp], first[warp], A, n_amb,
-                                      n_cand);
+                                      n_cand, SA, step);
         A.c_rep = __reduce_add_sync(0xffffffffu, A.c_rep);
         A.c_alg = __reduce_add_sync(0xffffffffu, A.c_alg);
         A.c_att = __reduce_add_sync(0xffffffffu, A.c_att);
@@ -482,6 +602,7 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N) {
         hg.ncx = hg.ncy = n;
         hg.periodic = 1;
         C.ncells = (size_t)n * n;
+        C.ncx = n;
     } else {
         C.ncells = (size_t)C.max_per_axis * C.max_per_axis;
     }
@@ -551,6 +672,9 @@ static bool cells_warp_rows(const DevParams &P, const DevState &S, const CellScr
 // block of this grid has been, so the grid must be resident at once: 4 blocks of four warps per SM in the
 // lanes-per-row kernel (four rows per warp: 9472 rows in flight cover the ~0.5 % of a million agents that start a
 // burst in a step; warps without a row exit at once), 2 blocks of 512 threads per SM in the block-per-row kernel.
+bool sbc_pair_cells_lanes(const DevParams &P, const DevState &S, const CellScratch &C, int pred_active) {
+    return P.BC == 0 && cells_warp_rows(P, S, C) && !pred_active;
+}
 int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
@@ -561,12 +685,13 @@ int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScrat
 // the rows are S.active_list[step % 3] (kept by the steps themselves, or compacted by sbc_launch_compact_rows)
 void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, const StepArgs &A, cudaStream_t st) {
     const CellGeom *geom = static_cast<const CellGeom *>(C.geom);
-    const int blocks = sbc_pair_cells_blocks(P, S, C);
+    const int blocks = sbc_pair_cells_blocks(P, S, C) + A.edge_blocks;   // (edge_blocks > 0 only with the lanes kernel)
 #define SBC_CELLS_ARGS P, S, geom, C.cell_range, C.key_in, C.idx_out, A
     if (P.BC == 0) {
         if (cells_warp_rows(P, S, C)) {
             if (A.pred_active) sbc_launch_prio(pair_cells_warp_kernel<true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
-            else sbc_launch_prio(pair_cells_lanes_kernel<true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else if (A.ghost_ready) sbc_launch_prio(pair_cells_lanes_kernel<true, true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else sbc_launch_prio(pair_cells_lanes_kernel<true, false>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
         } else {
             sbc_launch_prio(pair_cells_kernel<true>, blocks, CELLS_BLOCK_THREADS, 0, st, SBC_CELLS_ARGS);
         }

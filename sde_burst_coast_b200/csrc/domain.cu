@@ -268,9 +268,10 @@ dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a,
         if (S.gid) S.gid[g] = gid;
     }
 }
-__global__ void dom_commit_kernel(int *ctl) {
+__global__ void dom_commit_kernel(int *ctl, int epoch) {
     if (ctl[21]) return;
     ctl[0] = max(ctl[0] - ctl[7], 0);
+    if (epoch >= 0) ctl[17] = epoch;   // the ghosts hold the records of this exchange
 }
 
 // refresh exchange: current {x, y, vx, vy} of the slots listed by the last full exchange, same order
@@ -292,9 +293,9 @@ dom_refresh_pack_kernel(DevState S, const int *__restrict__ ctl, const int *__re
 // the agents I sent left now live on the left neighbour, which lists them behind its own right band
 __global__ void __launch_bounds__(256)
 dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
-                          const DomRecord *recv_b0, const DomRecord *recv_b1) {
+                          const DomRecord *recv_b0, const DomRecord *recv_b1, int epoch) {
     if (ctl[21]) return;
-    const int par = ctl[16] & 1;   // buffers by parity of the exchange count (the same pointer twice without an inbox)
+    const int par = epoch & 1;   // buffers by parity of the exchange count (the same pointer twice without an inbox)
     const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
     const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,6 +311,7 @@ dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const 
     else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
     else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
     if (src && t < S.N - own_cap) S.pv[own_cap + t] = src->pv;
+    if (t == 0) ctl[17] = epoch;   // (read by kernels launched behind this one)
 }
 
 // ---- exchange through peer memory (NVLink) ---------------------------------------------------------
@@ -319,13 +321,14 @@ dom_refresh_unpack_kernel(DevState S, int own_cap, int *__restrict__ ctl, const 
 // neighbours' flags; the receiver's one-thread wait kernel holds its stream until both flags show the
 // epoch. Producers never wait, so the ring cannot deadlock; two parities suffice because a rank can
 // only push epoch e + 2 after it has consumed e + 1, which the neighbour sent after consuming e.
-// The exchange count lives in device memory (ctl[16]) so that a whole refresh exchange can be replayed from a
-// CUDA graph: push and flag act on count + 1, the flag kernel commits it, wait and unpack read it back.
+// Exchanges are numbered (one per step, full or refresh). The host passes the number to the kernels it launches
+// eagerly; inside a replayed graph it is the device-resident step index plus a shift the host keeps in ctl[18].
+// ctl[17] holds the number of the last exchange whose records are in the ghost slots.
 __global__ void __launch_bounds__(256)
 dom_push_kernel(const DomRecord *__restrict__ send_l, const DomRecord *__restrict__ send_r, DomRecord *dst_l0,
-                DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, const int *__restrict__ ctl, int max_mig,
+                DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, int epoch, int max_mig,
                 int max_halo) {
-    const int par = (ctl[16] + 1) & 1;
+    const int par = epoch & 1;
     DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
     const int per_side = (1 + max_mig + max_halo) * 4;   // 16-byte quarters
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < 2 * per_side; q += gridDim.x * blockDim.x) {
@@ -340,13 +343,11 @@ dom_push_kernel(const DomRecord *__restrict__ send_l, const DomRecord *__restric
     }
 }
 __global__ void dom_flag_kernel(volatile int *flag_l0, volatile int *flag_l1, volatile int *flag_r0, volatile int *flag_r1,
-                                int *ctl) {
-    const int epoch = ctl[16] + 1, par = epoch & 1;
+                                int epoch) {
+    const int par = epoch & 1;
     __threadfence_system();
     *(par ? flag_l1 : flag_l0) = epoch;
     *(par ? flag_r1 : flag_r0) = epoch;
-    __threadfence_system();
-    ctl[16] = epoch;
 }
 // Wall-clock nanoseconds (independent of the SM clock).
 __device__ __forceinline__ unsigned long long dom_now_ns() {
@@ -368,8 +369,8 @@ __device__ __forceinline__ bool dom_wait_flags(const volatile int *fa, const vol
     return true;
 }
 __global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
-                                const volatile int *flag_b1, int *ctl, unsigned long long timeout_ns) {
-    const int epoch = ctl[16], par = epoch & 1;
+                                const volatile int *flag_b1, int *ctl, int epoch, unsigned long long timeout_ns) {
+    const int par = epoch & 1;
     if (ctl[21]) return;   // an earlier exchange already failed
     if (!dom_wait_flags(par ? flag_a1 : flag_a0, par ? flag_b1 : flag_b0, epoch, timeout_ns)) {
         ctl[6] += 1000;
@@ -378,16 +379,29 @@ __global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int 
 }
 
 // One refresh exchange in two kernels (the graph-replayed form): SEND gathers the listed positions straight into
-// the neighbours' inboxes and the last block to finish publishes the exchange count; RECV holds every block until
-// both flags show the count, then scatters the incoming positions into the ghost slots.
-__global__ void __launch_bounds__(256)
-dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list, int list_cap, DomRecord *dst_l0,
-                        DomRecord *dst_l1, DomRecord *dst_r0, DomRecord *dst_r1, volatile int *flag_l0, volatile int *flag_l1,
-                        volatile int *flag_r0, volatile int *flag_r1, unsigned *ticket) {
-    const int epoch = ctl[16] + 1, par = epoch & 1;
-    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, true);   // exchanges are indexed by their count, not by the step
+// the neighbours' inboxes and the last block to finish publishes the exchange number; RECV holds every block until
+// both neighbours' numbers arrived, scatters their positions into the ghost slots, and its last block announces in
+// ctl[17] that the ghosts are in place - which is what the rows kernel of the running step waits for before it reads
+// a candidate near a slab edge. `step_dev` / `step_off`: the exchange belongs to step (*step_dev + step_off) - 1, the
+// one BEFORE the step in whose graph these kernels sit (nullptr: step_off is that number itself, eager launch).
+__device__ __forceinline__ int dom_epoch_of(const int *ctl, const uint32_t *step_dev, uint32_t step_off) {
+    const uint32_t step = step_dev ? *step_dev + step_off : step_off;
+    return (int)step - 1 + ctl[18];
+}
+struct DomPeers {   // where a refresh exchange writes (the neighbours' inboxes) and reads (this rank's own)
+    DomRecord *dst_l[2], *dst_r[2];
+    volatile int *flag_l[2], *flag_r[2];
+    const DomRecord *recv_a[2], *recv_b[2];
+    const volatile int *flag_a[2], *flag_b[2];
+};
+__device__ __forceinline__ void dom_send_body(const DevState &S, int *ctl, int epoch, const int *__restrict__ halo_list, int list_cap,
+                                              const DomPeers &X, unsigned *ticket, int bid, int nblk) {
+    const int par = epoch & 1;
+    DomRecord *dst_l0 = X.dst_l[0], *dst_l1 = X.dst_l[1], *dst_r0 = X.dst_r[0], *dst_r1 = X.dst_r[1];
+    volatile int *flag_l0 = X.flag_l[0], *flag_l1 = X.flag_l[1], *flag_r0 = X.flag_r[0], *flag_r1 = X.flag_r[1];
+    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, true);   // exchanges are indexed by their number, not by the step
     DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = bid * blockDim.x + threadIdx.x;
     const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
     if (t == 0) {
         DomRecord h = {};
@@ -397,27 +411,24 @@ dom_refresh_send_kernel(DevState S, int *ctl, const int *__restrict__ halo_list,
     }
     if (t < nl) dst_l[1 + t].pv = S.pv[halo_list[t]];
     if (t < nr) dst_r[1 + t].pv = S.pv[halo_list[list_cap + t]];
-    __threadfence_system();
+    __threadfence_system();   // this block's records are at the neighbours before its ticket is
     __syncthreads();
     sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, false);
     if (threadIdx.x == 0) {
         const unsigned done = atomicAdd(ticket, 1u);
-        if (done == gridDim.x - 1) {   // every block has stored its records (and read ctl[16])
+        if (done == (unsigned)nblk - 1u) {   // every block has stored its records
             *ticket = 0u;
             __threadfence_system();
             *(par ? flag_l1 : flag_l0) = epoch;
             *(par ? flag_r1 : flag_r0) = epoch;
-            __threadfence_system();
-            ctl[16] = epoch;
         }
     }
 }
-__global__ void __launch_bounds__(256)
-dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv_a0, const DomRecord *recv_a1,
-                        const DomRecord *recv_b0, const DomRecord *recv_b1, const volatile int *flag_a0,
-                        const volatile int *flag_a1, const volatile int *flag_b0, const volatile int *flag_b1,
-                        unsigned long long timeout_ns) {
-    const int epoch = ctl[16], par = epoch & 1;
+__device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, int *ctl, int epoch, const DomPeers &X,
+                                              unsigned long long timeout_ns, unsigned *ticket, int bid, int nblk) {
+    const int par = epoch & 1;
+    const DomRecord *recv_a0 = X.recv_a[0], *recv_a1 = X.recv_a[1], *recv_b0 = X.recv_b[0], *recv_b1 = X.recv_b[1];
+    const volatile int *flag_a0 = X.flag_a[0], *flag_a1 = X.flag_a[1], *flag_b0 = X.flag_b[0], *flag_b1 = X.flag_b[1];
     __shared__ int arrived;
     sbc_trace(S, (uint32_t)epoch, SBC_TR_RECV, true);
     if (threadIdx.x == 0) {
@@ -425,33 +436,58 @@ dom_refresh_recv_kernel(DevState S, int own_cap, int *ctl, const DomRecord *recv
         // which is fine - every block runs its own wait and comes to the same verdict
         arrived = (*(volatile int *)(ctl + 21) == 0) &&
                   dom_wait_flags(par ? flag_a1 : flag_a0, par ? flag_b1 : flag_b0, epoch, timeout_ns);
-        if (!arrived && blockIdx.x == 0 && *(volatile int *)(ctl + 21) == 0) {
+        if (!arrived && bid == 0 && *(volatile int *)(ctl + 21) == 0) {
             ctl[6] += 1000;
             *(volatile int *)(ctl + 21) = 1;
         }
     }
     __syncthreads();
-    if (!arrived) return;   // stale or partial records are never unpacked
-    const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
-    const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t == 0) {
-        const bool ok_a = recv_a[0].pad[1] == 1u && (int)recv_a[0].pad[0] == ha + sl;
-        const bool ok_b = recv_b[0].pad[1] == 1u && (int)recv_b[0].pad[0] == hb + sr;
-        if (!ok_a || !ok_b) ctl[6] += 1;
-    }
-    int k = t;
-    const DomRecord *src = nullptr;
-    if (k < ha) src = recv_a + 1 + k;
-    else if ((k -= ha) < hb) src = recv_b + 1 + k;
-    else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
-    else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
-    if (src && t < S.N - own_cap) {
-        // the records were written by another GPU: read them past L1
-        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(&src->pv));
-        S.pv[own_cap + t] = pv;
+    if (arrived) {   // stale or partial records are never unpacked
+        const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
+        const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
+        const int t = bid * blockDim.x + threadIdx.x;
+        if (t == 0) {
+            const bool ok_a = recv_a[0].pad[1] == 1u && (int)recv_a[0].pad[0] == ha + sl;
+            const bool ok_b = recv_b[0].pad[1] == 1u && (int)recv_b[0].pad[0] == hb + sr;
+            if (!ok_a || !ok_b) ctl[6] += 1;
+        }
+        int k = t;
+        const DomRecord *src = nullptr;
+        if (k < ha) src = recv_a + 1 + k;
+        else if ((k -= ha) < hb) src = recv_b + 1 + k;
+        else if ((k -= hb) < sl) src = recv_a + 1 + ha + k;
+        else if ((k -= sl) < sr) src = recv_b + 1 + hb + k;
+        if (src && t < S.N - own_cap) {
+            // the records were written by another GPU: read them past L1
+            const float4 pv = __ldcg(reinterpret_cast<const float4 *>(&src->pv));
+            S.pv[own_cap + t] = pv;
+        }
     }
     sbc_trace(S, (uint32_t)epoch, SBC_TR_RECV, false);
+    // the last block tells the rows kernel that runs beside this one that the ghosts are in place (also after a
+    // time-out: the step must not hang; the failure is on record in ctl[21])
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(ticket, 1u);
+        if (done == (unsigned)nblk - 1u) {
+            *ticket = 0u;
+            __threadfence();
+            *(volatile int *)(ctl + 17) = epoch;
+        }
+    }
+}
+// ONE launch for both halves: the first n_send blocks send, the others receive (they are resident and waiting while
+// the records travel; nobody in this grid waits for anything inside this grid, so co-residency is not required)
+__global__ void __launch_bounds__(256)
+dom_refresh_exchange_kernel(DevState S, int own_cap, int *ctl, const uint32_t *step_dev, uint32_t step_off,
+                            const int *__restrict__ halo_list, int list_cap, DomPeers X, unsigned long long timeout_ns, int n_send) {
+    const int epoch = dom_epoch_of(ctl, step_dev, step_off);
+    if ((int)blockIdx.x < n_send)
+        dom_send_body(S, ctl, epoch, halo_list, list_cap, X, reinterpret_cast<unsigned *>(ctl + 20), blockIdx.x, n_send);
+    else
+        dom_recv_body(S, own_cap, ctl, epoch, X, timeout_ns, reinterpret_cast<unsigned *>(ctl + 22), blockIdx.x - n_send,
+                      gridDim.x - n_send);
 }
 
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
@@ -537,7 +573,7 @@ void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch
 }
 
 void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
-                              const void *sent_l, const void *sent_r, cudaStream_t st) {
+                              const void *sent_l, const void *sent_r, int epoch, cudaStream_t st) {
     const int ghost_cap = S.N - D.own_cap;
     const int n = max(ghost_cap, 2 * D.max_mig);
     dom_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(S, D.own_cap, static_cast<const DomRecord *>(recv_a),
@@ -545,7 +581,7 @@ void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *r
                                                       static_cast<const DomRecord *>(sent_l),
                                                       static_cast<const DomRecord *>(sent_r), D.max_mig, D.max_halo, D.ctl,
                                                       D.free_stack, D.halo_list);
-    dom_commit_kernel<<<1, 1, 0, st>>>(D.ctl);
+    dom_commit_kernel<<<1, 1, 0, st>>>(D.ctl, epoch);
 }
 
 void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *send_l, void *send_r, cudaStream_t st) {
@@ -554,39 +590,39 @@ void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *s
                                                              static_cast<DomRecord *>(send_r));
 }
 void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a0, const void *recv_a1,
-                                      const void *recv_b0, const void *recv_b1, cudaStream_t st) {
+                                      const void *recv_b0, const void *recv_b1, int epoch, cudaStream_t st) {
     const int ghost_cap = S.N - D.own_cap;
     if (ghost_cap <= 0) return;
     dom_refresh_unpack_kernel<<<(ghost_cap + 255) / 256, 256, 0, st>>>(
         S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a0), static_cast<const DomRecord *>(recv_a1),
-        static_cast<const DomRecord *>(recv_b0), static_cast<const DomRecord *>(recv_b1));
+        static_cast<const DomRecord *>(recv_b0), static_cast<const DomRecord *>(recv_b1), epoch);
 }
 void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
-                            int *const flag_l[2], int *const flag_r[2], cudaStream_t st) {
+                            int *const flag_l[2], int *const flag_r[2], int epoch, cudaStream_t st) {
     dom_push_kernel<<<64, 256, 0, st>>>(static_cast<const DomRecord *>(send_l), static_cast<const DomRecord *>(send_r),
                                         static_cast<DomRecord *>(dst_l[0]), static_cast<DomRecord *>(dst_l[1]),
-                                        static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), D.ctl, D.max_mig,
+                                        static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), epoch, D.max_mig,
                                         D.max_halo);
-    dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], D.ctl);
+    dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], epoch);
 }
-void sbc_launch_domain_refresh_send(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
-                                    int *const flag_l[2], int *const flag_r[2], cudaStream_t st) {
+void sbc_launch_domain_refresh_exchange(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
+                                        void *const dst_l[2], void *const dst_r[2], int *const flag_l[2], int *const flag_r[2],
+                                        const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
+                                        int *const flag_b[2], cudaStream_t st) {
+    DomPeers X;
+    for (int k = 0; k < 2; k++) {
+        X.dst_l[k] = static_cast<DomRecord *>(dst_l[k]); X.dst_r[k] = static_cast<DomRecord *>(dst_r[k]);
+        X.flag_l[k] = flag_l[k]; X.flag_r[k] = flag_r[k];
+        X.recv_a[k] = static_cast<const DomRecord *>(recv_a[k]); X.recv_b[k] = static_cast<const DomRecord *>(recv_b[k]);
+        X.flag_a[k] = flag_a[k]; X.flag_b[k] = flag_b[k];
+    }
     const int cap = D.max_halo + D.max_mig;
-    unsigned *ticket = reinterpret_cast<unsigned *>(D.ctl + 20);
-    dom_refresh_send_kernel<<<(cap + 255) / 256, 256, 0, st>>>(
-        S, D.ctl, D.halo_list, cap, static_cast<DomRecord *>(dst_l[0]), static_cast<DomRecord *>(dst_l[1]),
-        static_cast<DomRecord *>(dst_r[0]), static_cast<DomRecord *>(dst_r[1]), flag_l[0], flag_l[1], flag_r[0], flag_r[1], ticket);
+    const int n_send = (cap + 255) / 256, n_recv = (max(S.N - D.own_cap, 1) + 255) / 256;
+    sbc_launch_prio(dom_refresh_exchange_kernel, n_send + n_recv, 256, 0, st, S, D.own_cap, D.ctl, step_dev, step_off,
+                    (const int *)D.halo_list, cap, X, D.timeout_ns, n_send);
 }
-void sbc_launch_domain_refresh_recv(const DevState &S, DomainScratch &D, const void *const recv_a[2], const void *const recv_b[2],
-                                    int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
-    const int ghost_cap = S.N - D.own_cap;
-    dom_refresh_recv_kernel<<<(max(ghost_cap, 1) + 255) / 256, 256, 0, st>>>(
-        S, D.own_cap, D.ctl, static_cast<const DomRecord *>(recv_a[0]), static_cast<const DomRecord *>(recv_a[1]),
-        static_cast<const DomRecord *>(recv_b[0]), static_cast<const DomRecord *>(recv_b[1]), flag_a[0], flag_a[1], flag_b[0],
-        flag_b[1], D.timeout_ns);
-}
-void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st) {
-    dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl, D.timeout_ns);
+void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], int epoch, cudaStream_t st) {
+    dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl, epoch, D.timeout_ns);
 }
 
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st) {

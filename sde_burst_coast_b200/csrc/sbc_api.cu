@@ -49,9 +49,10 @@ struct sbc_handle {
     bool nxt_synced;               // S.pv_nxt carries the dead / free marks of S.pv (needed before a step writes into it)
     bool cs_valid;                 // S.cs == (cos, sin)(phi): true after set_state / ensemble launches, false after multi-kernel steps
     int pv_parity;                 // which of the two position buffers S.pv currently is (captured graphs bake the pointers)
-    bool recv_pending;             // domain mode: the neighbours' refresh records of the last step are not in the ghosts yet
     cudaStream_t stream2;          // second branch of a captured step (rows kernel next to the bulk update)
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t stream3;          // third branch: a decomposed swarm's refresh exchange of the previous step
+    cudaEvent_t ev_fork, ev_join, ev_join2;
+    int dom_shift;                 // ctl[18] as last uploaded: exchange number minus step index
     double v0_max;           // largest speed handed in through sbc_set_state
     DomainScratch dom;
     // exchange through peer memory: own inbox [flags 256 B | from-left p0 | from-left p1 | from-right p0 | from-right p1]
@@ -267,9 +268,9 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->nxt_synced = false;
     h->cs_valid = true;
     h->pv_parity = 0;
-    h->recv_pending = false;
-    h->stream2 = nullptr;
-    h->ev_fork = h->ev_join = nullptr;
+    h->stream2 = h->stream3 = nullptr;
+    h->ev_fork = h->ev_join = h->ev_join2 = nullptr;
+    h->dom_shift = 0x7fffffff;
     h->step_dev = nullptr;
     h->step_dev_value = -1;
     h->use_graphs = getenv("SBC_NO_GRAPHS") == nullptr;
@@ -291,6 +292,8 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         ok = ok && cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
     }
@@ -305,7 +308,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     ok = ok && dev_alloc(&S.n_dead, (size_t)n_replicates) == cudaSuccess;
     ok = ok && dev_alloc(&S.pred_spawned, (size_t)n_replicates) == cudaSuccess;
     for (int k = 0; k < 3; k++) ok = ok && dev_alloc(&S.active_list[k], total) == cudaSuccess;
-    ok = ok && dev_alloc(&S.active_count, 4) == cudaSuccess;
+    ok = ok && dev_alloc(&S.active_count, 8) == cudaSuccess;
     ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
     uint32_t *geo_dev = nullptr;
     ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
@@ -327,7 +330,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     }
     cudaMemcpy(geo_dev, h->geo_host.data(), h->geo_host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     cudaMemset(S.stats, 0, 8 * sizeof(unsigned long long));
-    cudaMemset(S.active_count, 0, 4 * sizeof(int));
+    cudaMemset(S.active_count, 0, 8 * sizeof(int));
     if (S.kill_count) cudaMemset(S.kill_count, 0, sizeof(int));
     cudaMemset(S.n_dead, 0, n_replicates * sizeof(int));
     cudaMemset(S.pred_spawned, 0, n_replicates * sizeof(int));
@@ -365,6 +368,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.kill_list); cudaFree(S.kill_count);
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_list[2]); cudaFree(S.active_count);
+    cudaFree(S.edge_list[0]); cudaFree(S.edge_list[1]); cudaFree(S.edge_list[2]);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
@@ -372,6 +376,8 @@ int sbc_destroy(sbc_handle *h) {
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
     for (auto &kv : h->graphs) cudaGraphExecDestroy(kv.second);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream3) cudaStreamDestroy(h->stream3);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
@@ -458,6 +464,7 @@ static int n_update_of(const sbc_handle *h) {
 static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear_inactive = false) {
     StepArgs A = {};
     A.n_update = n_update_of(h);
+    A.edge_hi = -1;
     if (all_rows && !h->P.voronoi) {
         if (int rc = ensure_dense(h)) return rc;
         if (resort || !h->dense.sorted_valid) {
@@ -472,7 +479,7 @@ static int launch_pair_pass(sbc_handle *h, int all_rows, bool resort, bool clear
     }
     // rows into list 0 (the kernels pick the list by the parity of the step: 0 here)
     h->list_valid = false;
-    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 4 * sizeof(int), h->stream));
+    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 8 * sizeof(int), h->stream));
     const bool every = all_rows != 0;   // Delaunay-filtered candidates: every alive row through the rows kernel
     sbc_launch_compact_rows(h->P, h->S, every || clear_inactive, every, A.n_update, h->S.active_list[0], h->S.active_count, h->stream);
     h->host_stats[7] += (every || clear_inactive) ? 2 : 1;
@@ -538,7 +545,6 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
     h->list_valid = false;
     h->nxt_synced = true;    // the pack kernel writes both position buffers
     h->cs_valid = true;
-    h->recv_pending = false;
     if (vproj)
         for (size_t g = 0; g < total; g++)
             if (vproj[g] > h->v0_max) h->v0_max = vproj[g];
@@ -657,15 +663,15 @@ int sbc_get_counts(sbc_handle *h, int32_t *n_alive, int32_t *n_dead) {
 // predator move + kill behind, and in a decomposed swarm the receipt of the neighbours' records in front of the rows
 // kernel and the dispatch of this rank's records at the end. Replayed from a CUDA graph whose two branches run side
 // by side; the graph bakes pointers, so there is one per combination of the MK_* bits and the position-buffer parity.
-enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_RECV = 8, MK_SEND = 16 };
+enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_XCHG = 8 };
 
-static void domain_launch_refresh_send(sbc_handle *h, const DevState &S, cudaStream_t st);
-static void domain_launch_refresh_recv(sbc_handle *h, const DevState &S, cudaStream_t st);
+static void domain_launch_refresh_exchange(sbc_handle *h, const DevState &S, const uint32_t *step_dev, uint32_t step_off,
+                                           cudaStream_t st);
 
 static int ensure_rows(sbc_handle *h, int64_t s) {
     if (h->list_valid && h->list_step == s) return SBC_OK;
     const int par = (int)((uint32_t)s % 3u);
-    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 4 * sizeof(int), h->stream));
+    SBC_CUDA(cudaMemsetAsync(h->S.active_count, 0, 8 * sizeof(int), h->stream));
     sbc_launch_compact_rows(h->P, h->S, false, false, n_update_of(h), h->S.active_list[par], h->S.active_count + par, h->stream);
     h->host_stats[7] += 1;
     h->list_valid = true;
@@ -674,34 +680,45 @@ static int ensure_rows(sbc_handle *h, int64_t s) {
 }
 
 // the kernels of one step in launch order on the state S (positions in S.pv, new ones into S.pv_nxt);
-// aux == nullptr: everything on `main`
-static void record_step(sbc_handle *h, const DevState &S, unsigned key, const StepArgs &A, cudaStream_t main, cudaStream_t aux) {
-    cudaStream_t rows_st = main;
+// aux == nullptr: everything on `main`. Three branches that do not depend on each other:
+//   aux2 : a decomposed swarm's refresh exchange of the PREVIOUS step (send this rank's edge positions, receive the
+//          neighbours' into the ghost slots) - only the rows next to a slab edge wait for it, inside the rows kernel
+//   aux  : cell build when due, rows kernel          main : bulk update
+static void record_step(sbc_handle *h, const DevState &S, unsigned key, const StepArgs &A, cudaStream_t main, cudaStream_t aux,
+                        cudaStream_t aux2) {
+    cudaStream_t rows_st = main, x_st = main;
     if (aux) {
         cudaEventRecord(h->ev_fork, main);
         cudaStreamWaitEvent(aux, h->ev_fork, 0);
         rows_st = aux;
+        if (key & MK_XCHG) {
+            cudaStreamWaitEvent(aux2, h->ev_fork, 0);
+            x_st = aux2;
+        }
     }
+    if (key & MK_XCHG) domain_launch_refresh_exchange(h, S, A.step_dev, A.step, x_st);
     // the cell order is only read by the rows kernel: it is built on that branch, next to the bulk update
     if (key & MK_REBUILD) sbc_launch_cell_build(h->P, S, h->cells, rows_st);
-    if (key & MK_RECV) domain_launch_refresh_recv(h, S, rows_st);   // ghosts of this step's start-of-step positions
     if (h->use_cells) sbc_launch_pair_cells(h->P, S, h->cells, A, rows_st);
     else sbc_launch_pair_rows(h->P, S, A, rows_st);
     sbc_launch_update_bulk(h->P, S, A, main);
     if (aux) {
         cudaEventRecord(h->ev_join, aux);
         cudaStreamWaitEvent(main, h->ev_join, 0);
+        if (key & MK_XCHG) {
+            cudaEventRecord(h->ev_join2, aux2);
+            cudaStreamWaitEvent(main, h->ev_join2, 0);
+        }
     }
     DevState Sn = S;   // what the host sees after the step: the new positions are the current ones
     std::swap(Sn.pv, Sn.pv_nxt);
     std::swap(Sn.tm, Sn.tm_nxt);
     if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
-    if (key & MK_SEND) domain_launch_refresh_send(h, Sn, main);
 }
 
 // `count` consecutive steps s, s + 1, ... with the same ingredients (count > 1: no cell build among them) as ONE graph
 // launch: inside a graph the next step's kernels follow at node-to-node latency instead of a launch gap.
-static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, bool send_after, int count = 1) {
+static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, int count = 1) {
     DevState &S = h->S;
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (h->use_cells) if (int rc = ensure_cells(h)) return rc;
@@ -713,7 +730,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
         h->nxt_synced = true;
     }
     const unsigned key = (h->pv_parity ? MK_PARITY : 0) | (rebuild ? MK_REBUILD : 0) | (pred_phase ? MK_PRED : 0) |
-                         (recv_first ? MK_RECV : 0) | (send_after ? MK_SEND : 0) | ((unsigned)count << 8);
+                         (xchg_first ? MK_XCHG : 0) | ((unsigned)count << 8);
     StepArgs A = {};
     A.step = (uint32_t)s;
     A.n_update = n_update_of(h);
@@ -721,6 +738,21 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
     A.net_kill = (pred_phase && S.Npred > 1 && h->hp.pred_kill != 0) ? 1 : 0;
     A.finish = 1;
     A.fresh_cells = rebuild ? 1 : 0;
+    A.edge_hi = -1;
+    if (h->use_cells && h->cells.ncx > 0) {   // periodic box: fixed grid
+        A.cell_ncx = h->cells.ncx;
+        A.cell_inv_w = (float)((double)h->cells.ncx / (double)h->P.L);   // == CellGeom::inv_w (celllist.cu), bit for bit
+    }
+    if (h->dom.enabled && h->peer_l && h->use_cells && sbc_pair_cells_lanes(h->P, S, h->cells, A.pred_active)) {
+        // slab with the peer-memory exchange: rows whose 3 x 3 cells can hold a ghost are listed apart and swept by
+        // their own blocks, which wait (inside the rows kernel) for the exchange that runs beside the step
+        const double inv_w = (double)h->cells.ncx / h->hp.sizeL;   // cell columns per unit length
+        A.edge_lo = (int)std::floor((double)h->dom.x_lo * inv_w) + 1;
+        A.edge_hi = (int)std::floor((double)h->dom.x_hi * inv_w) - 1;
+        A.edge_blocks = 148;
+        A.wait_ns = h->dom.timeout_ns;
+        if (xchg_first) A.ghost_ready = h->dom.ctl + 17;
+    }
     const bool graphable = h->use_graphs && !injected && !S.flags && h->stream != nullptr && h->stream != cudaStreamLegacy &&
                            h->stream != cudaStreamPerThread;  // the default streams cannot be captured
     if (count > 1 && (!graphable || rebuild)) return fail(h, SBC_ERR_STATE, "mk_step: a batch needs graph replay and no cell build");
@@ -739,7 +771,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
             DevState Sc = S;
             for (int k = 0; k < count; k++) {
                 A.step = (uint32_t)k;   // offset inside the launch; the base lives in *step_dev
-                record_step(h, Sc, key, A, h->stream, h->stream2);
+                record_step(h, Sc, key, A, h->stream, h->stream2, h->stream3);
                 std::swap(Sc.pv, Sc.pv_nxt);
                 std::swap(Sc.tm, Sc.tm_nxt);
             }
@@ -747,7 +779,8 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
             cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
             if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(ce));
             cudaGraphExec_t exec;
-            ce = cudaGraphInstantiate(&exec, graph, 0);
+            // node priorities (sbc_launch_prio) only count when the graph is instantiated with this flag
+            ce = cudaGraphInstantiateWithFlags(&exec, graph, cudaGraphInstantiateFlagUseNodePriority);
             cudaGraphDestroy(graph);
             if (ce != cudaSuccess) return fail(h, SBC_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
             it = h->graphs.emplace(key, exec).first;
@@ -755,7 +788,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
         SBC_CUDA(cudaGraphLaunch(it->second, h->stream));
         h->step_dev_value = s + count;
     } else {
-        record_step(h, S, key, A, h->stream, nullptr);
+        record_step(h, S, key, A, h->stream, nullptr, nullptr);
         h->step_dev_value = -1;
     }
     // the new positions are the current ones from here on
@@ -769,7 +802,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool recv_first, b
     h->dense.sorted_valid = false;
     h->host_stats[0] += count;
     h->host_stats[1] += count;
-    h->host_stats[7] += (rebuild ? 4 : 0) + count * ((pred_phase ? 1 : 0) + (recv_first ? 1 : 0) + (send_after ? 1 : 0));
+    h->host_stats[7] += (rebuild ? 4 : 0) + count * ((pred_phase ? 1 : 0) + (xchg_first ? 1 : 0));
     if (h->use_cells) {
         if (rebuild) { h->cells_valid = true; h->cells_age = 0; h->host_stats[6]++; }
         h->cells_age += count;   // the agents moved once more per step since the build
@@ -861,7 +894,7 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     if (ph != pred_phase || spawn0 || spawn1) { count = 1; break; }
                 }
             }
-            if (int rc = mk_step(h, s, pred_phase, false, false, count)) return rc;
+            if (int rc = mk_step(h, s, pred_phase, false, count)) return rc;
             s += count - 1;
         }
     }
@@ -1113,6 +1146,8 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     }
     if (e != cudaSuccess) return fail(h, SBC_ERR_NOMEM, std::string("domain scratch: ") + cudaGetErrorString(e));
     h->dom.enabled = true;
+    for (int k = 0; k < 3; k++)   // rows next to a slab edge are listed apart (worst case: every owned agent)
+        if (!h->S.edge_list[k]) SBC_CUDA(dev_alloc(&h->S.edge_list[k], (size_t)h->S.N));
     h->dom.halo = (float)halo;
     h->dom_period = 0;
     h->dom_last_full = true;
@@ -1221,17 +1256,17 @@ static void domain_launch_push(sbc_handle *h) {
         flag_l[par] = inbox_flag(h->peer_l, 1, par);
         flag_r[par] = inbox_flag(h->peer_r, 0, par);
     }
-    sbc_launch_domain_push(h->dom, h->send_own[0], h->send_own[1], dst_l, dst_r, flag_l, flag_r, h->stream);
+    sbc_launch_domain_push(h->dom, h->send_own[0], h->send_own[1], dst_l, dst_r, flag_l, flag_r, h->dom_epoch, h->stream);
 }
 static void domain_launch_wait(sbc_handle *h) {
     int *flag_a[2] = {inbox_flag(h->inbox, 0, 0), inbox_flag(h->inbox, 0, 1)};
     int *flag_b[2] = {inbox_flag(h->inbox, 1, 0), inbox_flag(h->inbox, 1, 1)};
-    sbc_launch_domain_wait(h->dom, flag_a, flag_b, h->stream);
+    sbc_launch_domain_wait(h->dom, flag_a, flag_b, h->dom_epoch, h->stream);
 }
 static void domain_launch_refresh_unpack(sbc_handle *h) {
     sbc_launch_domain_refresh_unpack(h->S, h->dom, inbox_buf(h->inbox, h->inbox_buf_bytes, 0, 0),
                                      inbox_buf(h->inbox, h->inbox_buf_bytes, 0, 1), inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 0),
-                                     inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 1), h->stream);
+                                     inbox_buf(h->inbox, h->inbox_buf_bytes, 1, 1), h->dom_epoch, h->stream);
 }
 // Turn what the exchange kernels recorded into a status: a wait that timed out (ctl[21]), record overflows and
 // header mismatches (ctl[6]) all mean that some rank stepped with wrong ghosts.
@@ -1258,7 +1293,7 @@ int sbc_domain_set_timeout(sbc_handle *h, double seconds) {
 int sbc_domain_post(sbc_handle *h) {
     if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
     if (int rc = sbc_domain_pack(h, h->send_own[0], h->send_own[1])) return rc;
-    h->dom_epoch++;   // mirrors ctl[16], which the flag kernel advances
+    h->dom_epoch++;   // exchanges are numbered; the neighbours count along
     domain_launch_push(h);
     h->host_stats[7] += 2;
     return SBC_OK;
@@ -1299,59 +1334,66 @@ static void domain_peer_pointers(sbc_handle *h, void *dst_l[2], void *dst_r[2], 
         flag_b[par] = inbox_flag(h->inbox, 1, par);
     }
 }
-static void domain_launch_refresh_send(sbc_handle *h, const DevState &S, cudaStream_t st) {
+// the refresh exchange of the step BEFORE step (*step_dev + step_off): send, then receive, on one stream
+static void domain_launch_refresh_exchange(sbc_handle *h, const DevState &S, const uint32_t *step_dev, uint32_t step_off,
+                                           cudaStream_t st) {
     void *dst_l[2], *dst_r[2];
     const void *recv_a[2], *recv_b[2];
     int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
     domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
-    sbc_launch_domain_refresh_send(S, h->dom, dst_l, dst_r, flag_l, flag_r, st);
-}
-static void domain_launch_refresh_recv(sbc_handle *h, const DevState &S, cudaStream_t st) {
-    void *dst_l[2], *dst_r[2];
-    const void *recv_a[2], *recv_b[2];
-    int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
-    domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
-    sbc_launch_domain_refresh_recv(S, h->dom, recv_a, recv_b, flag_a, flag_b, st);
+    sbc_launch_domain_refresh_exchange(S, h->dom, step_dev, step_off, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a,
+                                       flag_b, st);
 }
 
-// n_steps x { step ; exchange }. A refresh exchange is part of the step's graph: this rank's records leave at the end
-// of step s, the neighbours' records are awaited at the START of step s + 1 on the rows kernel's branch - the bulk
-// update of step s + 1 (which reads no ghost) runs meanwhile, so a rank that is a little ahead does not idle.
+// n_steps x { step ; exchange }. A refresh exchange does not sit between two steps: this rank's edge positions of step
+// s leave, and the neighbours' arrive, on a branch of step s + 1's graph that runs BESIDE its bulk update and its rows
+// kernel; only the rows next to a slab edge hold (inside the rows kernel, right before they read candidate
+// positions) until the ghosts are in place. A rank that is a little ahead or behind costs its neighbours nothing.
 int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     if (!h || !h->dom.enabled || !h->peer_l || !h->peer_r) return SBC_ERR_STATE;
     if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_domain_step: no state");
     SBC_CUDA(cudaSetDevice(h->device));
-    for (int64_t s = s_first; s < s_first + n_steps; s++) {
+    if (n_steps <= 0) return SBC_OK;
+    {   // exchange number of the exchange behind step s: s + shift (the next one is dom_epoch + 1, behind s_first)
+        const int shift = h->dom_epoch + 1 - (int)s_first;
+        if (shift != h->dom_shift) {
+            SBC_CUDA(cudaMemcpyAsync(h->dom.ctl + 18, &shift, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+            SBC_CUDA(cudaStreamSynchronize(h->stream));   // `shift` is a stack variable
+            h->dom_shift = shift;
+        }
+    }
+    bool pending = false;   // the refresh exchange behind the last step has not run yet
+    int64_t s = s_first;
+    for (; s < s_first + n_steps; s++) {
         if (int rc = ensure_cells(h)) return rc;
         // the exchange behind this step is a full one when the NEXT step rebuilds the cell order
         const bool rebuild_now = !h->cells_valid || h->cells_age > h->cells_max_age;
-        // four refresh steps (receive ... send) in one graph launch when none of them ends in a full exchange
-        int count = h->recv_pending ? mk_batch(h, s_first + n_steps - s) : 1;
+        // four refresh steps in one graph launch when none of them ends in a full exchange
+        int count = pending ? mk_batch(h, s_first + n_steps - s) : 1;
         if (count > 1 && h->cells_age + count > h->cells_max_age) count = 1;
         if (count > 1) {
-            if (int rc = mk_step(h, s, false, true, true, count)) return rc;
+            if (int rc = mk_step(h, s, false, true, count)) return rc;
             h->dom_last_full = false;
             h->dom_epoch += count;
             s += count - 1;
-            continue;   // recv_pending stays set: the last step's records are still on their way
+            continue;   // still pending: the exchange behind the last of these steps
         }
         const int age_after = (rebuild_now ? 0 : h->cells_age) + 1;
         const bool full_after = age_after > h->cells_max_age;
-        if (int rc = mk_step(h, s, false, h->recv_pending, !full_after)) return rc;
-        h->recv_pending = false;
+        if (int rc = mk_step(h, s, false, pending)) return rc;
+        pending = false;
         if (full_after) {
             if (int rc = sbc_domain_post(h)) return rc;
             if (int rc = domain_complete_async(h)) return rc;
         } else {
             h->dom_last_full = false;
             h->dom_epoch++;
-            h->recv_pending = true;
+            pending = true;
         }
     }
-    if (h->recv_pending) {   // leave the handle with its ghosts in place
-        domain_launch_refresh_recv(h, h->S, h->stream);
-        h->host_stats[7]++;
-        h->recv_pending = false;
+    if (pending) {   // leave the handle with its ghosts in place: the exchange behind the last step, eagerly
+        domain_launch_refresh_exchange(h, h->S, nullptr, (uint32_t)s, h->stream);
+        h->host_stats[7] += 2;
     }
     h->host_stats[5] += (unsigned long long)n_steps * (unsigned long long)h->S.N;
     // one host synchronisation per call (not per step): did every exchange of this call arrive and fit?
@@ -1363,13 +1405,14 @@ int sbc_domain_unpack(sbc_handle *h, const void *recv_a_dev, const void *recv_b_
     if (!h || !h->dom.enabled) return SBC_ERR_STATE;
     SBC_CUDA(cudaSetDevice(h->device));
     if (h->dom_last_full) {
-        sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev, h->stream);
+        sbc_launch_domain_unpack(h->S, h->dom, recv_a_dev, recv_b_dev, sent_left_dev, sent_right_dev,
+                                 h->inbox ? h->dom_epoch : -1, h->stream);
         h->cells_valid = false;   // slots changed hands: the next step rebuilds the cell order
         h->nxt_synced = false;    // ... and both position buffers and the row list start afresh
         h->list_valid = false;
         h->host_stats[7] += 2;
     } else {
-        sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_a_dev, recv_b_dev, recv_b_dev, h->stream);
+        sbc_launch_domain_refresh_unpack(h->S, h->dom, recv_a_dev, recv_a_dev, recv_b_dev, recv_b_dev, h->dom_epoch, h->stream);
         h->host_stats[7] += 1;
     }
     return SBC_OK;

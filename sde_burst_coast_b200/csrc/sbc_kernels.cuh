@@ -42,7 +42,8 @@ struct DevState {
     // step s - 1 (the agents it re-armed), or by the compaction kernel after a state change; step s appends the rows of
     // step s + 1 to list (s + 1) % 3 and clears the counter of list (s + 2) % 3, which nobody touches during step s
     int2 *active_list[3];  // [R*N] each: {slot, the slot's cell key at list time (0 without a cell list)}
-    int *active_count;     // [3] (+ 1 pad)
+    int2 *edge_list[3];    // decomposed swarm: the rows next to a slab edge are listed apart (they wait for the ghosts)
+    int *active_count;     // [3] (+ 1 pad) of active_list, [4..6] of edge_list
     const uint32_t *cell_key;  // cell key of every slot as of the last cell build (nullptr without a cell list)
     // counters
     unsigned long long *stats; // [8] see sbc_get_stats
@@ -51,7 +52,7 @@ struct DevState {
     unsigned long long *trace;
 };
 #define SBC_TRACE_STEPS 1024
-enum { SBC_TR_ROWS = 0, SBC_TR_BULK = 1, SBC_TR_RECV = 2, SBC_TR_SEND = 3, SBC_TR_LASTSTART = 4, SBC_TR_KERNELS = 8 };
+enum { SBC_TR_ROWS = 0, SBC_TR_BULK = 1, SBC_TR_RECV = 2, SBC_TR_SEND = 3, SBC_TR_LASTSTART = 4, SBC_TR_EDGE = 6, SBC_TR_KERNELS = 8 };
 
 // per-launch constants of one multi-kernel step (rows kernel + update_bulk_kernel, update.cu)
 struct StepArgs {
@@ -63,7 +64,24 @@ struct StepArgs {
     int pred_active;         // predator phase: burst-starting rows evaluate IntCalcPred
     int finish;              // rows kernel: 1 = update the rows (a step), 0 = only write acc / cnt (test hook)
     int fresh_cells;         // the cell order was rebuilt after the rows were listed: their cached cell keys are stale
+    // decomposed swarm: the neighbours' records of the previous step arrive WHILE this step's kernels run. Rows whose
+    // 3 x 3 cells can hold a ghost (cell column <= edge_lo or >= edge_hi) hold before they read candidate positions
+    // until ghost_ready[0] shows exchange number step - 1 + ghost_ready[1]; nullptr: nothing to wait for
+    const int *ghost_ready;
+    int edge_lo, edge_hi;    // edge_hi < 0: not a decomposed swarm, nobody is listed apart
+    int edge_blocks;         // rows kernel: the last edge_blocks blocks of the grid take the edge list
+    int cell_ncx;            // cells per axis (to tell a row's cell column from its key)
+    float cell_inv_w;        // cells per unit length (a rebuild step derives the new key of a listed agent itself)
+    unsigned long long wait_ns;
 };
+#ifdef __CUDACC__
+// is the cell with this key next to a slab edge (its 3 x 3 block can hold a ghost)?
+__device__ __forceinline__ bool sbc_edge_cell(int key, const StepArgs &A) {
+    if (A.edge_hi < 0) return false;
+    const int cx = key % A.cell_ncx;
+    return cx <= A.edge_lo || cx >= A.edge_hi;
+}
+#endif
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t sbc_step_of(const StepArgs &A) { return A.step_dev ? *A.step_dev + A.step : A.step; }
 #endif
@@ -230,6 +248,21 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
     return alive && a.bin_step == P.burst_steps;
 }
 
+// Decomposed swarm: hold until the ghost slots carry the neighbours' positions of the previous step (the exchange
+// runs on another branch of the step's graph; StepArgs::ghost_ready). Called by the rows next to a slab edge right
+// before they read candidate positions. Gives up after wait_ns (the exchange itself has put the failure on record).
+__device__ __forceinline__ void sbc_wait_ghosts(const StepArgs &A, uint32_t step) {
+    const volatile int *r = A.ghost_ready;
+    const int need = (int)step - 1 + r[1];
+    if (r[0] >= need) return;
+    const unsigned long long t0 = sbc_now_ns();
+    while (r[0] < need) {
+        if (sbc_now_ns() - t0 > A.wait_ns) break;
+        __nanosleep(100);
+    }
+    __threadfence();
+}
+
 // rows kernel, lane / thread 0 of the group that sweeps row g: the row's own state is fetched BEFORE the sweep (the loads
 // overlap the sweep's dependent chain), the row is updated after it and passed on if it re-armed
 struct RowState {
@@ -256,10 +289,12 @@ __device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevStat
     if (!r.al) return;   // killed after it was listed
     int at = -1;
     const int nxt = (int)((step + 1u) % 3u);
-    if (sbc_will_rearm(r.tm, P)) at = atomicAdd(S.active_count + nxt, 1);
+    const int key = S.cell_key ? (int)S.cell_key[g] : 0;   // (this kernel runs behind the cell build, if there was one)
+    const bool edge = sbc_edge_cell(key, A);
+    if (sbc_will_rearm(r.tm, P)) at = atomicAdd(S.active_count + nxt + (edge ? 4 : 0), 1);
     sbc_update_agent(P, S, g, acc, r.tm, r.p, r.hv, r.f, step, A);
     // (an agent the net caught this step is dropped by the next rows kernel)
-    if (at >= 0) S.active_list[nxt][at] = make_int2((int)g, S.cell_key ? (int)S.cell_key[g] : 0);   // (after the build, if any)
+    if (at >= 0) (edge ? S.edge_list : S.active_list)[nxt][at] = make_int2((int)g, key);
 }
 #endif
 
@@ -319,6 +354,7 @@ struct CellScratch {
     void *geom = nullptr;                         // CellGeom on the device
     void *cub_tmp = nullptr;
     size_t cub_bytes = 0, ncells = 0;
+    int ncx = 0;                                  // cells per axis of a periodic box
     int key_bits = 0, max_per_axis = 0;
     bool counting = false;                        // sparse grid: counting-sort build (cnt / start: [ncells + 1])
     int *cnt = nullptr, *start = nullptr;
@@ -330,6 +366,7 @@ cudaError_t sbc_cell_scratch_alloc(CellScratch &C, const DevParams &P, int N);
 void sbc_cell_scratch_free(CellScratch &C);
 void sbc_launch_cell_build(const DevParams &P, const DevState &S, CellScratch &C, cudaStream_t st);
 int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C);
+bool sbc_pair_cells_lanes(const DevParams &P, const DevState &S, const CellScratch &C, int pred_active);
 void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C, const StepArgs &A, cudaStream_t st);
 // dense pass (every alive row), pair_dense.cu: Morton order + tiled all pairs + split combine
 struct DenseScratch {
@@ -360,7 +397,8 @@ struct DomainScratch {
                          // [7] migrants taken by the last unpack [8] owned [9] ghosts
                          // [10..13] ghost segment sizes of the last full unpack (halo from a, from b, sent l, sent r)
                          // [14] [15] length of the refresh list towards the left / right neighbour
-                         // [16] number of peer-memory exchanges posted so far [20] block ticket of the fused refresh send
+                         // [17] number of the last exchange whose records are in the ghost slots [18] exchange number minus
+                         // step index inside sbc_domain_step [20] / [22] block tickets of the refresh send / receive
                          // [21] a wait for the neighbours' records timed out (sticky until the next sbc_set_state)
     int *halo_list = nullptr;  // [2][max_halo + max_mig] slots whose positions a refresh exchange sends left / right
     float halo = 0.f;          // width of the edge band that is mirrored on the neighbour (att_range + skin)
@@ -378,17 +416,17 @@ void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t s
 void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
                             cudaStream_t st);
 void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *recv_a, const void *recv_b,
-                              const void *sent_l, const void *sent_r, cudaStream_t st);
+                              const void *sent_l, const void *sent_r, int epoch, cudaStream_t st);
 void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *send_l, void *send_r, cudaStream_t st);
 void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const void *recv_a0, const void *recv_a1,
-                                      const void *recv_b0, const void *recv_b1, cudaStream_t st);
+                                      const void *recv_b0, const void *recv_b1, int epoch, cudaStream_t st);
 void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
-                            int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
-void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
-void sbc_launch_domain_refresh_send(const DevState &S, DomainScratch &D, void *const dst_l[2], void *const dst_r[2],
-                                    int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
-void sbc_launch_domain_refresh_recv(const DevState &S, DomainScratch &D, const void *const recv_a[2], const void *const recv_b[2],
-                                    int *const flag_a[2], int *const flag_b[2], cudaStream_t st);
+                            int *const flag_l[2], int *const flag_r[2], int epoch, cudaStream_t st);
+void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], int epoch, cudaStream_t st);
+void sbc_launch_domain_refresh_exchange(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
+                                        void *const dst_l[2], void *const dst_r[2], int *const flag_l[2], int *const flag_r[2],
+                                        const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
+                                        int *const flag_b[2], cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update of everybody who does not start a burst this step (update.cu) --------------

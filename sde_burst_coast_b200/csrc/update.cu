@@ -24,7 +24,10 @@ update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) 
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     sbc_trace(S, step, SBC_TR_BULK, true);
     // the list after next is idle during this step: clear its counter for the step that appends to it
-    if (blockIdx.x == 0 && threadIdx.x == 0) S.active_count[(step + 2u) % 3u] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.active_count[(step + 2u) % 3u] = 0;
+        S.active_count[4 + (step + 2u) % 3u] = 0;
+    }
     bool mine = false, rearm = false;
     uint8_t al = 0;
     uint32_t tm = 0;
@@ -42,12 +45,27 @@ update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) 
     }
     // warp-aggregated append to the rows of the next step, issued before the update: the counter's atomic returns
     // while the warp computes
-    const unsigned m = __ballot_sync(0xffffffffu, rearm);
-    int base = 0, key = 0;
+    // the agent's cell key travels with the list entry (one round trip less for the row); while the cell order is being
+    // rebuilt beside this kernel the key array is in flux, and the new key follows from the start-of-step position the
+    // build is reading too (same arithmetic as cell_count_kernel)
+    int key = 0;
+    bool edge = false;
+    if (rearm && S.cell_key) {
+        if (A.fresh_cells && A.cell_ncx > 0) {   // periodic box: the grid is fixed, the host knows it
+            const int cx = min(max((int)floorf(p.x * A.cell_inv_w), 0), A.cell_ncx - 1);
+            const int cy = min(max((int)floorf(p.y * A.cell_inv_w), 0), A.cell_ncx - 1);
+            key = cy * A.cell_ncx + cx;
+        } else if (A.fresh_cells) {
+            key = -1;   // grid fitted to the agents on the device: the row looks its key up
+        } else {
+            key = (int)S.cell_key[g];
+        }
+        edge = sbc_edge_cell(key, A);   // rows next to a slab edge are listed apart
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, rearm && !edge);
+    int base = 0, at_edge = -1;
     if (m && lane == 0) base = atomicAdd(S.active_count + nxt, __popc(m));
-    // the agent's cell key travels with the list entry (one round trip less for the row) - unless the cell order is
-    // being rebuilt beside this kernel: -1 sends the row to the key array
-    if (rearm && S.cell_key) key = A.fresh_cells ? -1 : (int)S.cell_key[g];
+    if (rearm && edge) at_edge = atomicAdd(S.active_count + 4 + nxt, 1);
     if (mine) {
         RowAcc acc;
         row_acc_clear(acc);
@@ -55,8 +73,9 @@ update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) 
     }
     if (m) {
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (rearm) S.active_list[nxt][base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)g, key);
+        if (rearm && !edge) S.active_list[nxt][base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)g, key);
     }
+    if (at_edge >= 0) S.edge_list[nxt][at_edge] = make_int2((int)g, key);
     sbc_trace(S, step, SBC_TR_BULK, false);
 }
 

@@ -15,7 +15,7 @@ import numpy as np
 from .params import SbcParams, PAIR_ACTIVE_ROWS, PAIR_ALL_ROWS  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libsbc.so')
+LIB_PATH = os.environ.get('SBC_LIB_PATH') or os.path.join(_HERE, 'lib', 'libsbc.so')   # (override: A/B runs of two builds)
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _u32p = ctypes.POINTER(ctypes.c_uint32)
