@@ -75,6 +75,7 @@ def main():
         okm = (idx >= 0) & (idx < len(t0))
         out['recv_end_in_step_us'] = float(np.median(r_end[okm] - t0[idx[okm]])) / 1e3
     if len(send):
+        out['flags_seen_after_recv_start_us'] = [float(np.median(send[:, 0] - recv[:len(send), 0])) / 1e3, float(np.median(send[:, 1] - recv[:len(send), 0])) / 1e3] if len(send) == len(recv) else None
         s_start = np.sort(send[:, 0])
         idx = np.searchsorted(t0, s_start, side='right') - 1
         okm = (idx >= 0) & (idx < len(t0))
@@ -83,8 +84,14 @@ def main():
         idx = np.searchsorted(t0, s_end, side='right') - 1
         okm = (idx >= 0) & (idx < len(t0))
         out['send_end_in_step_us'] = float(np.median(s_end[okm] - t0[idx[okm]])) / 1e3
+    if world > 1:
+        every = [None] * world
+        dist.gather_object(out, every if rank == 0 else None, dst=0)
+    else:
+        every = [out]
     if rank == 0:
-        print(json.dumps(out))
+        for o in every:
+            print(json.dumps(o))
     slab.close()
     if world > 1:
         dist.barrier()

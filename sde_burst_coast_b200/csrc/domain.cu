@@ -223,7 +223,7 @@ dom_pack_kernel(DevState S, int own_cap, float x_lo, float x_hi, float L, float 
 __global__ void __launch_bounds__(256)
 dom_unpack_kernel(DevState S, int own_cap, const DomRecord *__restrict__ recv_a, const DomRecord *__restrict__ recv_b,
                   const DomRecord *__restrict__ sent_l, const DomRecord *__restrict__ sent_r, int max_mig, int max_halo,
-                  int *__restrict__ ctl, const int *__restrict__ free_stack, int *__restrict__ halo_list) {
+                  int *__restrict__ ctl, const int *__restrict__ free_stack, int *__restrict__ halo_list, int epoch) {
     if (ctl[21]) return;   // the wait for these records timed out: leave the slots alone
     const int ma = recv_a ? (int)recv_a[0].gid : 0, mb = recv_b ? (int)recv_b[0].gid : 0;
     const int ha = recv_a ? (int)recv_a[0].pad[0] : 0, hb = recv_b ? (int)recv_b[0].pad[0] : 0;
@@ -360,12 +360,18 @@ __device__ __forceinline__ unsigned long long dom_now_ns() {
 // side turns the mark into SBC_ERR_STATE (sbc_domain_step / sbc_domain_complete).
 __device__ __forceinline__ bool dom_wait_flags(const volatile int *fa, const volatile int *fb, int epoch,
                                                unsigned long long timeout_ns) {
+    // system-scope acquire loads: the flags are written by another GPU, and a plain volatile load may be answered by a
+    // copy in this GPU's other L2 partition for several microseconds
+    auto ld_sys = [](const volatile int *p) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    };
     const unsigned long long t0 = dom_now_ns();
-    while (*fa < epoch || *fb < epoch) {
+    while (ld_sys(fa) < epoch || ld_sys(fb) < epoch) {
         if (dom_now_ns() - t0 > timeout_ns) return false;
-        __nanosleep(100);
+        __nanosleep(50);
     }
-    __threadfence_system();
     return true;
 }
 __global__ void dom_wait_kernel(const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
@@ -388,47 +394,22 @@ __device__ __forceinline__ int dom_epoch_of(const int *ctl, const uint32_t *step
     const uint32_t step = step_dev ? *step_dev + step_off : step_off;
     return (int)step - 1 + ctl[18];
 }
-struct DomPeers {   // where a refresh exchange writes (the neighbours' inboxes) and reads (this rank's own)
-    DomRecord *dst_l[2], *dst_r[2];
-    volatile int *flag_l[2], *flag_r[2];
-    const DomRecord *recv_a[2], *recv_b[2];
-    const volatile int *flag_a[2], *flag_b[2];
-};
-__device__ __forceinline__ void dom_send_body(const DevState &S, int *ctl, int epoch, const int *__restrict__ halo_list, int list_cap,
-                                              const DomPeers &X, unsigned *ticket, int bid, int nblk) {
-    const int par = epoch & 1;
-    DomRecord *dst_l0 = X.dst_l[0], *dst_l1 = X.dst_l[1], *dst_r0 = X.dst_r[0], *dst_r1 = X.dst_r[1];
-    volatile int *flag_l0 = X.flag_l[0], *flag_l1 = X.flag_l[1], *flag_r0 = X.flag_r[0], *flag_r1 = X.flag_r[1];
-    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, true);   // exchanges are indexed by their number, not by the step
-    DomRecord *dst_l = par ? dst_l1 : dst_l0, *dst_r = par ? dst_r1 : dst_r0;
-    const int t = bid * blockDim.x + threadIdx.x;
-    const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
-    if (t == 0) {
-        DomRecord h = {};
-        h.pad[1] = 1u;   // marks a refresh buffer
-        h.pad[0] = (uint32_t)nl; dst_l[0] = h;
-        h.pad[0] = (uint32_t)nr; dst_r[0] = h;
-    }
-    if (t < nl) dst_l[1 + t].pv = S.pv[halo_list[t]];
-    if (t < nr) dst_r[1 + t].pv = S.pv[halo_list[list_cap + t]];
-    __threadfence_system();   // this block's records are at the neighbours before its ticket is
-    __syncthreads();
-    sbc_trace(S, (uint32_t)epoch, SBC_TR_SEND, false);
-    if (threadIdx.x == 0) {
-        const unsigned done = atomicAdd(ticket, 1u);
-        if (done == (unsigned)nblk - 1u) {   // every block has stored its records
-            *ticket = 0u;
-            __threadfence_system();
-            *(par ? flag_l1 : flag_l0) = epoch;
-            *(par ? flag_r1 : flag_r0) = epoch;
-        }
-    }
+// The records of a refresh exchange are delivered by the threads that updated the agents (sbc_update_agent); the last
+// node of the step's graph raises the neighbours' flags (dom_publish_kernel). The receive - a branch of the NEXT step's
+// graph - holds until both neighbours' flags show exchange `epoch`, then scatters the records into the ghost slots.
+__global__ void dom_publish_kernel(const int *ctl, const uint32_t *step_dev, uint32_t step_off, volatile int *flag_l0,
+                                   volatile int *flag_l1, volatile int *flag_r0, volatile int *flag_r1) {
+    const int epoch = dom_epoch_of(ctl, step_dev, step_off), par = epoch & 1;
+    __threadfence_system();   // (the delivering kernels are complete: their stores are on their way ahead of these)
+    *(par ? flag_l1 : flag_l0) = epoch;
+    *(par ? flag_r1 : flag_r0) = epoch;
 }
-__device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, int *ctl, int epoch, const DomPeers &X,
+__device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, int *ctl, int epoch, const DomRecord *recv_a0,
+                                              const DomRecord *recv_a1, const DomRecord *recv_b0, const DomRecord *recv_b1,
+                                              const volatile int *flag_a0, const volatile int *flag_a1,
+                                              const volatile int *flag_b0, const volatile int *flag_b1,
                                               unsigned long long timeout_ns, unsigned *ticket, int bid, int nblk) {
     const int par = epoch & 1;
-    const DomRecord *recv_a0 = X.recv_a[0], *recv_a1 = X.recv_a[1], *recv_b0 = X.recv_b[0], *recv_b1 = X.recv_b[1];
-    const volatile int *flag_a0 = X.flag_a[0], *flag_a1 = X.flag_a[1], *flag_b0 = X.flag_b[0], *flag_b1 = X.flag_b[1];
     __shared__ int arrived;
     sbc_trace(S, (uint32_t)epoch, SBC_TR_RECV, true);
     if (threadIdx.x == 0) {
@@ -436,6 +417,12 @@ __device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, in
         // which is fine - every block runs its own wait and comes to the same verdict
         arrived = (*(volatile int *)(ctl + 21) == 0) &&
                   dom_wait_flags(par ? flag_a1 : flag_a0, par ? flag_b1 : flag_b0, epoch, timeout_ns);
+        if (S.trace) {   // when the first / the last block of the receive saw both flags (kernel id SBC_TR_SEND)
+            unsigned long long *w = S.trace + ((size_t)((uint32_t)epoch % SBC_TRACE_STEPS) * SBC_TR_KERNELS + SBC_TR_SEND) * 2;
+            const unsigned long long now = sbc_now_ns();
+            atomicMin(w, now);
+            atomicMax(w + 1, now);
+        }
         if (!arrived && bid == 0 && *(volatile int *)(ctl + 21) == 0) {
             ctl[6] += 1000;
             *(volatile int *)(ctl + 21) = 1;
@@ -446,11 +433,6 @@ __device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, in
         const DomRecord *recv_a = par ? recv_a1 : recv_a0, *recv_b = par ? recv_b1 : recv_b0;
         const int ha = ctl[10], hb = ctl[11], sl = ctl[12], sr = ctl[13];
         const int t = bid * blockDim.x + threadIdx.x;
-        if (t == 0) {
-            const bool ok_a = recv_a[0].pad[1] == 1u && (int)recv_a[0].pad[0] == ha + sl;
-            const bool ok_b = recv_b[0].pad[1] == 1u && (int)recv_b[0].pad[0] == hb + sr;
-            if (!ok_a || !ok_b) ctl[6] += 1;
-        }
         int k = t;
         const DomRecord *src = nullptr;
         if (k < ha) src = recv_a + 1 + k;
@@ -472,22 +454,35 @@ __device__ __forceinline__ void dom_recv_body(const DevState &S, int own_cap, in
         const unsigned done = atomicAdd(ticket, 1u);
         if (done == (unsigned)nblk - 1u) {
             *ticket = 0u;
-            __threadfence();
-            *(volatile int *)(ctl + 17) = epoch;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ctl + 17), "r"(epoch) : "memory");
         }
     }
 }
-// ONE launch for both halves: the first n_send blocks send, the others receive (they are resident and waiting while
-// the records travel; nobody in this grid waits for anything inside this grid, so co-residency is not required)
 __global__ void __launch_bounds__(256)
-dom_refresh_exchange_kernel(DevState S, int own_cap, int *ctl, const uint32_t *step_dev, uint32_t step_off,
-                            const int *__restrict__ halo_list, int list_cap, DomPeers X, unsigned long long timeout_ns, int n_send) {
+dom_refresh_receive_kernel(DevState S, int own_cap, int *ctl, const uint32_t *step_dev, uint32_t step_off, const DomRecord *recv_a0,
+                           const DomRecord *recv_a1, const DomRecord *recv_b0, const DomRecord *recv_b1,
+                           const volatile int *flag_a0, const volatile int *flag_a1, const volatile int *flag_b0,
+                           const volatile int *flag_b1, unsigned long long timeout_ns, volatile int *flag_l0,
+                           volatile int *flag_l1, volatile int *flag_r0, volatile int *flag_r1) {
     const int epoch = dom_epoch_of(ctl, step_dev, step_off);
-    if ((int)blockIdx.x < n_send)
-        dom_send_body(S, ctl, epoch, halo_list, list_cap, X, reinterpret_cast<unsigned *>(ctl + 20), blockIdx.x, n_send);
-    else
-        dom_recv_body(S, own_cap, ctl, epoch, X, timeout_ns, reinterpret_cast<unsigned *>(ctl + 22), blockIdx.x - n_send,
-                      gridDim.x - n_send);
+    // this rank's own records of the same exchange were delivered by the step that has just ended (sbc_update_agent):
+    // raise the neighbours' flags first (flag_l0 == nullptr: a publish node behind that step has done it already)
+    if (flag_l0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int par = epoch & 1;
+        __threadfence_system();
+        *(par ? flag_l1 : flag_l0) = epoch;
+        *(par ? flag_r1 : flag_r0) = epoch;
+    }
+    dom_recv_body(S, own_cap, ctl, epoch, recv_a0, recv_a1, recv_b0, recv_b1, flag_a0, flag_a1, flag_b0, flag_b1, timeout_ns,
+                  reinterpret_cast<unsigned *>(ctl + 22), blockIdx.x, gridDim.x);
+}
+
+// inverse of the refresh lists: where each listed slot's position goes in the records to the left / right neighbour
+__global__ void dom_halo_idx_kernel(const int *__restrict__ ctl, const int *__restrict__ halo_list, int list_cap, int2 *halo_idx) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nl = min(ctl[14], list_cap), nr = min(ctl[15], list_cap);
+    if (t < nl) halo_idx[halo_list[t]].x = t;
+    if (t < nr) halo_idx[halo_list[list_cap + t]].y = t;
 }
 
 // free stack of a fresh state: the free owned slots in descending order, so that pops take the lowest
@@ -541,8 +536,10 @@ __global__ void count_owned_kernel(DevState S, int own_cap, int *out) {
 
 size_t sbc_domain_record_bytes(void) { return sizeof(DomRecord); }
 
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo) {
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo, int n_slots) {
     cudaError_t e;
+    if ((e = cudaMalloc((void **)&D.halo_idx, (size_t)n_slots * sizeof(int2))) != cudaSuccess) return e;
+    if ((e = cudaMemset(D.halo_idx, 0xff, (size_t)n_slots * sizeof(int2))) != cudaSuccess) return e;
     D.nblk = (own_cap + CLS_PER_BLOCK - 1) / CLS_PER_BLOCK;
     if ((e = cudaMalloc((void **)&D.halo_list, (size_t)2 * (max_mig + max_halo) * sizeof(int))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&D.block_counts, (size_t)D.nblk * 4 * sizeof(int))) != cudaSuccess) return e;
@@ -553,7 +550,7 @@ cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig,
     return cudaMemset(D.ctl, 0, 32 * sizeof(int));
 }
 void sbc_domain_scratch_free(DomainScratch &D) {
-    cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl); cudaFree(D.halo_list);
+    cudaFree(D.block_counts); cudaFree(D.block_off); cudaFree(D.free_stack); cudaFree(D.ctl); cudaFree(D.halo_list); cudaFree(D.halo_idx);
     D = DomainScratch();
 }
 
@@ -580,8 +577,12 @@ void sbc_launch_domain_unpack(const DevState &S, DomainScratch &D, const void *r
                                                       static_cast<const DomRecord *>(recv_b),
                                                       static_cast<const DomRecord *>(sent_l),
                                                       static_cast<const DomRecord *>(sent_r), D.max_mig, D.max_halo, D.ctl,
-                                                      D.free_stack, D.halo_list);
+                                                      D.free_stack, D.halo_list, epoch);
     dom_commit_kernel<<<1, 1, 0, st>>>(D.ctl, epoch);
+    // the new refresh lists, inverted for the threads that deliver the positions themselves
+    cudaMemsetAsync(D.halo_idx, 0xff, (size_t)S.N * sizeof(int2), st);
+    const int cap = D.max_halo + D.max_mig;
+    dom_halo_idx_kernel<<<(cap + 255) / 256, 256, 0, st>>>(D.ctl, D.halo_list, cap, D.halo_idx);
 }
 
 void sbc_launch_domain_refresh_pack(const DevState &S, DomainScratch &D, void *send_l, void *send_r, cudaStream_t st) {
@@ -605,21 +606,22 @@ void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *se
                                         D.max_halo);
     dom_flag_kernel<<<1, 1, 0, st>>>(flag_l[0], flag_l[1], flag_r[0], flag_r[1], epoch);
 }
-void sbc_launch_domain_refresh_exchange(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
-                                        void *const dst_l[2], void *const dst_r[2], int *const flag_l[2], int *const flag_r[2],
-                                        const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
-                                        int *const flag_b[2], cudaStream_t st) {
-    DomPeers X;
-    for (int k = 0; k < 2; k++) {
-        X.dst_l[k] = static_cast<DomRecord *>(dst_l[k]); X.dst_r[k] = static_cast<DomRecord *>(dst_r[k]);
-        X.flag_l[k] = flag_l[k]; X.flag_r[k] = flag_r[k];
-        X.recv_a[k] = static_cast<const DomRecord *>(recv_a[k]); X.recv_b[k] = static_cast<const DomRecord *>(recv_b[k]);
-        X.flag_a[k] = flag_a[k]; X.flag_b[k] = flag_b[k];
-    }
-    const int cap = D.max_halo + D.max_mig;
-    const int n_send = (cap + 255) / 256, n_recv = (max(S.N - D.own_cap, 1) + 255) / 256;
-    sbc_launch_prio(dom_refresh_exchange_kernel, n_send + n_recv, 256, 0, st, S, D.own_cap, D.ctl, step_dev, step_off,
-                    (const int *)D.halo_list, cap, X, D.timeout_ns, n_send);
+void sbc_launch_domain_refresh_receive(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
+                                       const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
+                                       int *const flag_b[2], int *const flag_l[2], int *const flag_r[2], cudaStream_t st) {
+    const int n_recv = (max(S.N - D.own_cap, 1) + 255) / 256;
+    sbc_launch_prio(dom_refresh_receive_kernel, n_recv, 256, 0, st, S, D.own_cap, D.ctl, step_dev, step_off,
+                    static_cast<const DomRecord *>(recv_a[0]), static_cast<const DomRecord *>(recv_a[1]),
+                    static_cast<const DomRecord *>(recv_b[0]), static_cast<const DomRecord *>(recv_b[1]),
+                    (const volatile int *)flag_a[0], (const volatile int *)flag_a[1], (const volatile int *)flag_b[0],
+                    (const volatile int *)flag_b[1], D.timeout_ns, (volatile int *)flag_l[0], (volatile int *)flag_l[1],
+                    (volatile int *)flag_r[0], (volatile int *)flag_r[1]);
+}
+// exchange number = (*step_dev + step_off) - 1 + shift, as for the receive: pass the step AFTER the one that delivered
+void sbc_launch_domain_publish(DomainScratch &D, const uint32_t *step_dev, uint32_t step_off, int *const flag_l[2],
+                               int *const flag_r[2], cudaStream_t st) {
+    sbc_launch_prio(dom_publish_kernel, 1, 1, 0, st, (const int *)D.ctl, step_dev, step_off, (volatile int *)flag_l[0],
+                    (volatile int *)flag_l[1], (volatile int *)flag_r[0], (volatile int *)flag_r[1]);
 }
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], int epoch, cudaStream_t st) {
     dom_wait_kernel<<<1, 1, 0, st>>>(flag_a[0], flag_a[1], flag_b[0], flag_b[1], D.ctl, epoch, D.timeout_ns);

@@ -663,10 +663,12 @@ int sbc_get_counts(sbc_handle *h, int32_t *n_alive, int32_t *n_dead) {
 // predator move + kill behind, and in a decomposed swarm the receipt of the neighbours' records in front of the rows
 // kernel and the dispatch of this rank's records at the end. Replayed from a CUDA graph whose two branches run side
 // by side; the graph bakes pointers, so there is one per combination of the MK_* bits and the position-buffer parity.
-enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_XCHG = 8 };
+enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_XCHG = 8, MK_PUSH = 16 };
 
 static void domain_launch_refresh_exchange(sbc_handle *h, const DevState &S, const uint32_t *step_dev, uint32_t step_off,
                                            cudaStream_t st);
+static unsigned char *inbox_buf(unsigned char *base, size_t bytes, int side, int parity);
+static void domain_launch_publish(sbc_handle *h, const uint32_t *step_dev, uint32_t step_off, cudaStream_t st);
 
 static int ensure_rows(sbc_handle *h, int64_t s) {
     if (h->list_valid && h->list_step == s) return SBC_OK;
@@ -714,11 +716,13 @@ static void record_step(sbc_handle *h, const DevState &S, unsigned key, const St
     std::swap(Sn.pv, Sn.pv_nxt);
     std::swap(Sn.tm, Sn.tm_nxt);
     if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
+    // (the edge agents delivered their new positions themselves; the neighbours' flags are raised by the first block of
+    // the receive kernel that heads the next step - or ends this call)
 }
 
 // `count` consecutive steps s, s + 1, ... with the same ingredients (count > 1: no cell build among them) as ONE graph
 // launch: inside a graph the next step's kernels follow at node-to-node latency instead of a launch gap.
-static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, int count = 1) {
+static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, int count = 1, bool push = false) {
     DevState &S = h->S;
     const bool injected = S.inj_social || S.inj_dir || S.inj_k;
     if (h->use_cells) if (int rc = ensure_cells(h)) return rc;
@@ -730,7 +734,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
         h->nxt_synced = true;
     }
     const unsigned key = (h->pv_parity ? MK_PARITY : 0) | (rebuild ? MK_REBUILD : 0) | (pred_phase ? MK_PRED : 0) |
-                         (xchg_first ? MK_XCHG : 0) | ((unsigned)count << 8);
+                         (xchg_first ? MK_XCHG : 0) | (push ? MK_PUSH : 0) | ((unsigned)count << 8);
     StepArgs A = {};
     A.step = (uint32_t)s;
     A.n_update = n_update_of(h);
@@ -752,6 +756,18 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
         A.edge_blocks = 148;
         A.wait_ns = h->dom.timeout_ns;
         if (xchg_first) A.ghost_ready = h->dom.ctl + 17;
+    }
+    if (push) {   // the exchange behind this step is a refresh: the agents in the edge bands deliver their new positions
+        A.halo_idx = h->dom.halo_idx;
+        A.xshift = h->dom.ctl + 18;
+        for (int par = 0; par < 2; par++) {
+            A.xdst[0][par] = inbox_buf(h->peer_l, h->inbox_buf_bytes, 1, par);   // my left neighbour's "from the right"
+            A.xdst[1][par] = inbox_buf(h->peer_r, h->inbox_buf_bytes, 0, par);
+        }
+        // listed agents lay within `halo` of an edge at the last full exchange and have moved less than skin / 2 since
+        const float reach = h->dom.halo + 0.5f * h->cells.skin + 1e-3f * h->dom.halo;
+        A.band_lo = h->dom.x_lo + reach;
+        A.band_hi = h->dom.x_hi - reach;
     }
     const bool graphable = h->use_graphs && !injected && !S.flags && h->stream != nullptr && h->stream != cudaStreamLegacy &&
                            h->stream != cudaStreamPerThread;  // the default streams cannot be captured
@@ -1138,7 +1154,7 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     invalidate_graphs(h);
     const unsigned long long keep_timeout = h->dom.timeout_ns;
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
-    cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity, max_migrants, max_halo);
+    cudaError_t e = sbc_domain_scratch_alloc(h->dom, own_capacity, max_migrants, max_halo, h->S.N);
     h->dom.timeout_ns = keep_timeout;
     if (const char *ev = std::getenv("SBC_DOMAIN_TIMEOUT_S")) {
         const double sec = std::atof(ev);
@@ -1341,8 +1357,15 @@ static void domain_launch_refresh_exchange(sbc_handle *h, const DevState &S, con
     const void *recv_a[2], *recv_b[2];
     int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
     domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
-    sbc_launch_domain_refresh_exchange(S, h->dom, step_dev, step_off, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a,
-                                       flag_b, st);
+    sbc_launch_domain_refresh_receive(S, h->dom, step_dev, step_off, recv_a, recv_b, flag_a, flag_b, flag_l, flag_r, st);
+}
+
+static void domain_launch_publish(sbc_handle *h, const uint32_t *step_dev, uint32_t step_off, cudaStream_t st) {
+    void *dst_l[2], *dst_r[2];
+    const void *recv_a[2], *recv_b[2];
+    int *flag_l[2], *flag_r[2], *flag_a[2], *flag_b[2];
+    domain_peer_pointers(h, dst_l, dst_r, flag_l, flag_r, recv_a, recv_b, flag_a, flag_b);
+    sbc_launch_domain_publish(h->dom, step_dev, step_off, flag_l, flag_r, st);
 }
 
 // n_steps x { step ; exchange }. A refresh exchange does not sit between two steps: this rank's edge positions of step
@@ -1372,7 +1395,7 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         int count = pending ? mk_batch(h, s_first + n_steps - s) : 1;
         if (count > 1 && h->cells_age + count > h->cells_max_age) count = 1;
         if (count > 1) {
-            if (int rc = mk_step(h, s, false, true, count)) return rc;
+            if (int rc = mk_step(h, s, false, true, count, true)) return rc;
             h->dom_last_full = false;
             h->dom_epoch += count;
             s += count - 1;
@@ -1380,7 +1403,7 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         }
         const int age_after = (rebuild_now ? 0 : h->cells_age) + 1;
         const bool full_after = age_after > h->cells_max_age;
-        if (int rc = mk_step(h, s, false, pending)) return rc;
+        if (int rc = mk_step(h, s, false, pending, 1, !full_after)) return rc;
         pending = false;
         if (full_after) {
             if (int rc = sbc_domain_post(h)) return rc;

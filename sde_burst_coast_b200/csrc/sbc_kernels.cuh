@@ -70,6 +70,13 @@ struct StepArgs {
     const int *ghost_ready;
     int edge_lo, edge_hi;    // edge_hi < 0: not a decomposed swarm, nobody is listed apart
     int edge_blocks;         // rows kernel: the last edge_blocks blocks of the grid take the edge list
+    // peer-memory exchange, delivery by the updating thread: an agent listed for a refresh exchange (halo_idx[slot] =
+    // its place in the records going left / right, -1 = not listed) stores its new position straight into the
+    // neighbours' inboxes xdst[side][parity of the exchange number = step + xshift[0]]; nullptr: nobody delivers
+    const int2 *halo_idx;
+    void *xdst[2][2];
+    const int *xshift;
+    float band_lo, band_hi;  // only agents with x < band_lo or x >= band_hi can be listed (saves the halo_idx load)
     int cell_ncx;            // cells per axis (to tell a row's cell column from its key)
     float cell_inv_w;        // cells per unit length (a rebuild step derives the new key of a listed agent itself)
     unsigned long long wait_ns;
@@ -226,6 +233,20 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
     S.force[g] = make_float2(a.fx, a.fy);
     S.tm_nxt[g] = sbc_tm_pack(a.bin_step, a.stb, P);
     if (S.flags) S.flags[g] |= (uint8_t)fl;
+    if (A.halo_idx && (p.x < A.band_lo || p.x >= A.band_hi)) {
+        // decomposed swarm: an agent in an edge band delivers its new position to the neighbour itself; the step's last
+        // graph node (dom_publish_kernel) then raises the neighbours' flags
+        const int2 hi = A.halo_idx[g];
+        if ((hi.x & hi.y) != -1) {
+            const int par = ((int)step + A.xshift[0]) & 1;
+            const float4 npv = make_float4(a.x, a.y, a.vx, a.vy);
+            // 64-byte records behind a header record, position in the first 16 bytes (DomRecord, domain.cu)
+            // (selects, not a dynamic index: indexing a kernel parameter array would copy the whole struct to local memory)
+            void *dl = par ? A.xdst[0][1] : A.xdst[0][0], *dr = par ? A.xdst[1][1] : A.xdst[1][0];
+            if (hi.x >= 0) reinterpret_cast<float4 *>(dl)[(size_t)(1 + hi.x) * 4] = npv;
+            if (hi.y >= 0) reinterpret_cast<float4 *>(dr)[(size_t)(1 + hi.y) * 4] = npv;
+        }
+    }
     bool alive = true;
     if (A.net_kill) {
         // FishNetKill (agents_dynamics.cpp:780-820) against the net AFTER this step's MoveFishNet (:616-624): the
@@ -252,15 +273,19 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
 // runs on another branch of the step's graph; StepArgs::ghost_ready). Called by the rows next to a slab edge right
 // before they read candidate positions. Gives up after wait_ns (the exchange itself has put the failure on record).
 __device__ __forceinline__ void sbc_wait_ghosts(const StepArgs &A, uint32_t step) {
-    const volatile int *r = A.ghost_ready;
+    const int *r = A.ghost_ready;
     const int need = (int)step - 1 + r[1];
-    if (r[0] >= need) return;
+    auto ld_gpu = [](const int *p) {   // device-scope acquire: the word is written by the receive kernel beside this one
+        int v;
+        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+        return v;
+    };
+    if (ld_gpu(r) >= need) return;
     const unsigned long long t0 = sbc_now_ns();
-    while (r[0] < need) {
+    while (ld_gpu(r) < need) {
         if (sbc_now_ns() - t0 > A.wait_ns) break;
-        __nanosleep(100);
+        __nanosleep(50);
     }
-    __threadfence();
 }
 
 // rows kernel, lane / thread 0 of the group that sweeps row g: the row's own state is fetched BEFORE the sweep (the loads
@@ -401,6 +426,7 @@ struct DomainScratch {
                          // step index inside sbc_domain_step [20] / [22] block tickets of the refresh send / receive
                          // [21] a wait for the neighbours' records timed out (sticky until the next sbc_set_state)
     int *halo_list = nullptr;  // [2][max_halo + max_mig] slots whose positions a refresh exchange sends left / right
+    int2 *halo_idx = nullptr;  // [slots] the inverse: place of a slot in the left / right list, -1 = not listed
     float halo = 0.f;          // width of the edge band that is mirrored on the neighbour (att_range + skin)
     int nblk = 0;
     int own_cap = 0;         // slots [0, own_cap) are owned / free, [own_cap, N) ghosts
@@ -410,7 +436,7 @@ struct DomainScratch {
     bool enabled = false;
 };
 size_t sbc_domain_record_bytes(void);
-cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo);
+cudaError_t sbc_domain_scratch_alloc(DomainScratch &D, int own_cap, int max_mig, int max_halo, int n_slots);
 void sbc_domain_scratch_free(DomainScratch &D);
 void sbc_launch_domain_reset(const DevState &S, DomainScratch &D, cudaStream_t st);
 void sbc_launch_domain_pack(const DevParams &P, const DevState &S, DomainScratch &D, void *send_l, void *send_r,
@@ -423,10 +449,11 @@ void sbc_launch_domain_refresh_unpack(const DevState &S, DomainScratch &D, const
 void sbc_launch_domain_push(DomainScratch &D, const void *send_l, const void *send_r, void *const dst_l[2], void *const dst_r[2],
                             int *const flag_l[2], int *const flag_r[2], int epoch, cudaStream_t st);
 void sbc_launch_domain_wait(DomainScratch &D, int *const flag_a[2], int *const flag_b[2], int epoch, cudaStream_t st);
-void sbc_launch_domain_refresh_exchange(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
-                                        void *const dst_l[2], void *const dst_r[2], int *const flag_l[2], int *const flag_r[2],
-                                        const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
-                                        int *const flag_b[2], cudaStream_t st);
+void sbc_launch_domain_refresh_receive(const DevState &S, DomainScratch &D, const uint32_t *step_dev, uint32_t step_off,
+                                       const void *const recv_a[2], const void *const recv_b[2], int *const flag_a[2],
+                                       int *const flag_b[2], int *const flag_l[2], int *const flag_r[2], cudaStream_t st);
+void sbc_launch_domain_publish(DomainScratch &D, const uint32_t *step_dev, uint32_t step_off, int *const flag_l[2],
+                               int *const flag_r[2], cudaStream_t st);
 void sbc_launch_count_owned(const DevState &S, DomainScratch &D, cudaStream_t st);
 
 // --- per-agent update of everybody who does not start a burst this step (update.cu) --------------

@@ -143,7 +143,7 @@ class SlabSwarm:
         self.rank, self.world, self.n_global = rank, world, int(n_global)
         mean_own = n_global / world
         halo_frac = min(1.0, sp.att_range * 1.2001 / (sp.sizeL / world))   # band = att_range + skin (<= att_range / 5)
-        self.own_cap = int(own_capacity or (mean_own * 1.15 + 4096))   # slack for density fluctuations; every slot costs sort time
+        self.own_cap = int(own_capacity or (mean_own * 1.05 + 4096))   # slack for density fluctuations; every slot costs update and sort time
         self.max_halo = int(max_records or (mean_own * halo_frac * 2 + 1024))      # records per edge band
         self.max_mig = int(max(256, self.max_halo // 8))                            # migrants per edge per step
         self.ghost_cap = 0 if world == 1 else int(ghost_capacity or (2 * self.max_halo + 2 * self.max_mig))
