@@ -310,6 +310,9 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     for (int k = 0; k < 3; k++) ok = ok && dev_alloc(&S.active_list[k], total) == cudaSuccess;
     ok = ok && dev_alloc(&S.active_count, 8) == cudaSuccess;
     ok = ok && dev_alloc(&S.stats, 8) == cudaSuccess;
+    if (n_agents <= 32 && n_pred == 0) {   // ensemble kernel in queue mode: one counter, one word per group of tanks
+        ok = ok && dev_alloc(&S.ens_queue, 1) == cudaSuccess && dev_alloc(&S.ens_done, (size_t)n_replicates) == cudaSuccess;
+    }
     uint32_t *geo_dev = nullptr;
     ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
     double *eff_dev = nullptr;
@@ -369,6 +372,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.alive); cudaFree(S.acc); cudaFree(S.cnt); cudaFree(S.pred_pv); cudaFree(S.pred_phi);
     cudaFree(S.n_dead); cudaFree(S.pred_spawned); cudaFree(S.active_list[0]); cudaFree(S.active_list[1]); cudaFree(S.active_list[2]); cudaFree(S.active_count);
     cudaFree(S.edge_list[0]); cudaFree(S.edge_list[1]); cudaFree(S.edge_list[2]);
+    cudaFree(S.ens_queue); cudaFree(S.ens_done);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
     cudaFree(h->obs_dev); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);

@@ -45,6 +45,9 @@ struct DevState {
     int2 *edge_list[3];    // decomposed swarm: the rows next to a slab edge are listed apart (they wait for the ghosts)
     int *active_count;     // [3] (+ 1 pad) of active_list, [4..6] of edge_list
     const uint32_t *cell_key;  // cell key of every slot as of the last cell build (nullptr without a cell list)
+    // ensemble kernel in queue mode (swarm_block.cu, EnsQueue): unit counter and slices done per group of tanks
+    unsigned *ens_queue;
+    int *ens_done;
     // counters
     unsigned long long *stats; // [8] see sbc_get_stats
     // timeline of the multi-kernel step (test / profiling hook, sbc_debug_trace): per step (mod SBC_TRACE_STEPS) and kernel
@@ -128,6 +131,19 @@ __device__ __forceinline__ void sbc_load_agent(const DevParams &P, const DevStat
         const float2 c = S.cs[g];
         a.cu = c.x; a.su = c.y;
     }
+    a.fx = f.x; a.fy = f.y;
+    a.bin_step = sbc_tm_bin(t, P); a.stb = sbc_tm_stb(t, P);
+}
+// the same past L1 (ld.global.cg), for state another SM wrote during the running launch
+__device__ __forceinline__ void sbc_load_agent_cg(const DevParams &P, const DevState &S, size_t g, AgentState &a) {
+    const float4 p = __ldcg(S.pv + g);
+    const float2 h = __ldcg(S.hv + g);
+    const float2 c = __ldcg(S.cs + g);
+    const float2 f = __ldcg(S.force + g);
+    const uint32_t t = __ldcg(S.tm + g);
+    a.x = p.x; a.y = p.y; a.vx = p.z; a.vy = p.w;
+    a.phi = h.x; a.vproj = h.y;
+    a.cu = c.x; a.su = c.y;
     a.fx = f.x; a.fy = f.y;
     a.bin_step = sbc_tm_bin(t, P); a.stb = sbc_tm_stb(t, P);
 }

@@ -39,24 +39,55 @@ struct PredSchedule {
 
 constexpr int BC_RUNTIME = -99;   // template value: take the boundary condition from the parameters
 
-template <int TPS, int BCT, bool VOR>
-__global__ void __launch_bounds__(128)
-swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps) {
+// Work units of a launch. Classic: one warp per group of 32 / TPS tanks, all n_steps in one go - the last wave of warps
+// leaves most SMs idle (16384 warps over 4736 resident ones: 3.46 waves run as 4). Sliced: the launch is cut into
+// (group, time slice) units, one warp each, numbered slice-major so that the block scheduler itself hands them out in
+// order; a unit's state goes through HBM (112 B per agent per slice: nothing next to a few hundred steps of arithmetic)
+// and `done[group]` tells the slice that may run next - by the time a unit is dispatched, its group's previous slice
+// was dispatched n_groups warps earlier and has normally long finished. With about a dozen units per resident warp the
+// tail costs a per cent instead of an eighth. (The kernel body stays straight-line per warp: a persistent loop around
+// it makes the compiler treat every shuffle as possibly divergent - 10 % slower.)
+struct EnsSlices {
+    int *done;           // [n_groups] slices of the group completed so far; nullptr: classic mode
+    uint32_t slice;      // steps per unit
+    unsigned n_groups;
+};
+
+template <int TPS, int BCT, bool VOR, bool SLICED>
+__global__ void __launch_bounds__(128) __maxnreg__(VOR ? 128 : 64)
+swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_first, uint32_t n_steps, EnsSlices Q) {
     const int BC = (BCT == BC_RUNTIME) ? P.BC : BCT;
     constexpr int SPW = 32 / TPS;
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned unit = (unsigned)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    unsigned grp = unit, sl = 0;
+    if (SLICED) {
+        // the slice comes from the block index alone (a block's warps share it: n_groups is a multiple of the warps per
+        // block), so that the step loop's bounds are uniform for the compiler - otherwise every shuffle inside it is
+        // compiled as possibly divergent
+        sl = (blockIdx.x * (blockDim.x >> 5)) / Q.n_groups;
+        grp = unit - sl * Q.n_groups;
+        s_first += sl * Q.slice;
+        n_steps = (sl * Q.slice < n_steps) ? min(Q.slice, n_steps - sl * Q.slice) : 0u;
+    }
     const int seg = lane / TPS, t = lane % TPS;
-    const int rep = warp_global * SPW + seg;
+    const int rep = (int)grp * SPW + seg;
     const int N = S.N;
-    const bool valid = (rep < S.R) && (t < N);
+    const bool valid = (rep < S.R) && (t < N) && n_steps > 0;
     const size_t g = valid ? ((size_t)rep * N + t) : 0;
     const unsigned segmask = (TPS == 32) ? FULL : (((1u << TPS) - 1u) << (seg * TPS));
     AgentState a = {};
     bool alive = false;
+    if (SLICED && sl > 0) {   // the group's previous slice
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(Q.done + grp) : "memory");
+        } while (__any_sync(FULL, v < (int)sl));
+    }
     if (valid) {
-        sbc_load_agent(P, S, g, a, true);
+        if (SLICED) sbc_load_agent_cg(P, S, g, a);   // written by another SM during this launch: past L1
+        else sbc_load_agent(P, S, g, a, true);
         alive = S.alive[g] != 0;
     }
     uint32_t flags_acc = 0;
@@ -143,6 +174,11 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
     if (valid && alive) {
         sbc_store_agent(P, S, g, a, true);
         if (S.flags) S.flags[g] |= (uint8_t)flags_acc;
+    }
+    if (SLICED) {   // hand the group over to its next slice
+        __threadfence();
+        if (__all_sync(FULL, true) && lane == 0)   // (the vote doubles as the warp's execution barrier behind the fences)
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(Q.done + grp), "r"((int)sl + 1) : "memory");
     }
     n_amb = __reduce_add_sync(FULL, (unsigned)n_amb);
     const unsigned np = __reduce_add_sync(FULL, (unsigned)n_pairs);
@@ -799,14 +835,36 @@ bool sbc_launch_swarm_block(const DevParams &P, const DevState &S, long long s_f
         const long long warps = ((long long)S.R + spw - 1) / spw;
         const int wpb = 4;
         const unsigned blocks = (unsigned)((warps + wpb - 1) / wpb);
+        // sliced mode (see EnsSlices) when the launch is a few waves of long-running warps: units of a time slice each,
+        // about a dozen per resident warp
+        EnsSlices Q = {nullptr, ns, (unsigned)warps};
+        unsigned qblocks = blocks;
+        {
+            static int sms = 0;
+            if (!sms) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+            const long long resident = (long long)sms * 8 * wpb;   // 8 blocks of 4 warps per SM at 64 registers
+            const char *env = getenv("SBC_ENS_QUEUE");
+            const bool allow = !(env && env[0] == '0') && S.Npred == 0 && S.ens_done != nullptr && warps % wpb == 0 && !P.voronoi;
+            long long n_slices = (12 * resident + warps - 1) / warps;
+            if (const char *e2 = getenv("SBC_ENS_SLICES")) n_slices = atoll(e2);   // tuning runs
+            if (n_slices > (long long)ns / 64) n_slices = (long long)ns / 64;
+            if (allow && warps > resident && n_slices > 1) {
+                Q.done = S.ens_done;
+                Q.slice = (uint32_t)((ns + n_slices - 1) / n_slices);
+                n_slices = (ns + Q.slice - 1) / Q.slice;
+                qblocks = (unsigned)(warps * n_slices / wpb);
+                cudaMemsetAsync(S.ens_done, 0, (size_t)warps * sizeof(int), st);
+            }
+        }
 #define SBC_WARP_LAUNCH(T, B, PR)                                                                         \
     do {                                                                                                  \
         if (PR) {                                                                                         \
             if (P.voronoi) swarm_warp_pred_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched); \
             else swarm_warp_pred_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, sched);  \
         } else {                                                                                          \
-            if (P.voronoi) swarm_warp_kernel<T, B, true><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);     \
-            else swarm_warp_kernel<T, B, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns);              \
+            if (P.voronoi) swarm_warp_kernel<T, B, true, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, Q);     \
+            else if (Q.done) swarm_warp_kernel<T, B, false, true><<<qblocks, wpb * 32, 0, st>>>(P, S, s0, ns, Q);  \
+            else swarm_warp_kernel<T, B, false, false><<<blocks, wpb * 32, 0, st>>>(P, S, s0, ns, Q);              \
         }                                                                                                 \
     } while (0)
 #define SBC_WARP_BC(T)                                                                     \

@@ -271,3 +271,27 @@ def test_trajectory_divergence_reported():
     assert first_div is None or first_div > 100
     g.close()
     w.close()
+
+
+def test_queue_mode_equals_one_unit_per_warp():
+    """Large ensembles are stepped in (tanks, time slice) units handed out through a queue (swarm_block.cu, EnsQueue): the
+    result is bit-identical to the classic launch, in which every warp takes its tanks through all the steps."""
+    import os
+    N, R, K = 32, 6000, 640      # 6000 warps > the 4736 resident ones: the queue mode engages
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(8)
+    st = random_state(N * R, sp, rng)
+    state = {k: v.reshape(R, N) for k, v in st.items()}
+    out = []
+    for env in ('1', '0'):
+        os.environ['SBC_ENS_QUEUE'] = env
+        g = _swarm(sp, N, n_replicates=R, seed=3)
+        g.set_state(**state)
+        g.step(0, K)
+        g.step(K, 100)           # a second launch carries on from the first
+        out.append((g.get_state(), g.stats()))
+        g.close()
+    os.environ.pop('SBC_ENS_QUEUE')
+    for k in out[0][0]:
+        assert np.array_equal(out[0][0][k], out[1][0][k]), k
+    assert out[0][1]['pairs'] == out[1][1]['pairs'] and out[0][1]['agent_steps'] == (K + 100) * N * R
