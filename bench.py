@@ -133,6 +133,28 @@ def recorded_profile(name, want_cfg, kernel_substr, my_seconds_per_launch, tol=0
     return out
 
 
+def pin_to_gpu_numa(torch, local):
+    """Bind this process (and the threads it starts later) to the CPUs of the NUMA node the GPU hangs on, so that pinned
+    buffers are first touched there and the copy threads run there. Returns the node, or None when sysfs does not say."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for tok in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = tok.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks line of the profiling recipe, sampled during the timed region."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
@@ -360,12 +382,11 @@ def main():
     # included), so that both figures describe the same regime of the dynamics.
     snap = g.get_state()
     g.close()
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in snap.items()}
-    part = torch.empty((R, N, 7), dtype=torch.float64).pin_memory().numpy()
-    alive = torch.empty((R, N), dtype=torch.uint8).pin_memory().numpy()
+    numa = pin_to_gpu_numa(torch, local)     # before the pinned buffers are allocated (first touch)
     import ctypes
-    dp, u8p = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint8)
-    E2E_PARTS = max(1, min(4, R // 1024))
+    cores_here = len(os.sched_getaffinity(0))
+    ranks_per_node = max(1, min(world, torch.cuda.device_count()))
+    E2E_PARTS = max(1, min(4, R // 1024, max(1, cores_here * (2 if numa is not None else 1) // ranks_per_node)))
     cuts = [R * k // E2E_PARTS for k in range(E2E_PARTS + 1)]
     parts = []
     for k in range(E2E_PARTS):
@@ -374,37 +395,59 @@ def main():
         hk = Swarm(sp, N, n_replicates=r1 - r0, seed=SEED, replicate_offset=rank * R + r0, device=local, stream=sk.cuda_stream)
         parts.append((hk, sk, r0, r1))
 
-    def e2e_run(hk, r0, r1, s_first, n):
-        sub = {k: v[r0:r1] for k, v in host.items()}
-        for q in range(n):
-            hk.set_state(**sub)                      # H2D: the full state in the ABI layout (8 doubles, 2 timers, alive)
-            hk.step(s_first + q * args.chunk, args.chunk)
-            hk._check(hk.lib.sbc_get_particles(hk.h, part[r0:r1].ctypes.data_as(dp), alive[r0:r1].ctypes.data_as(u8p)))  # D2H
+    def e2e_measure(abi, n_steps):
+        """Every bench step uploads every tank's state from pinned host memory, steps it, and downloads every tank's
+        particle rows; `abi` = 'f64' (the reference's double layout) or 'f32' (the float entry points)."""
+        real = np.float64 if abi == 'f64' else np.float32
+        rp = ctypes.POINTER(ctypes.c_double if abi == 'f64' else ctypes.c_float)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        host = {}
+        for k, v in snap.items():
+            a = np.ascontiguousarray(v, dtype=real if v.dtype == np.float64 else v.dtype)
+            host[k] = torch.from_numpy(a).pin_memory().numpy()
+        part = torch.empty((R, N, 7), dtype=torch.float64 if abi == 'f64' else torch.float32).pin_memory().numpy()
+        alive = torch.empty((R, N), dtype=torch.uint8).pin_memory().numpy()
 
-    def e2e_all(s_first, n):
-        th = [threading.Thread(target=e2e_run, args=(hk, r0, r1, s_first, n)) for hk, _, r0, r1 in parts]
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
+        def run(hk, r0, r1, s_first, n):
+            sub = {k: v[r0:r1] for k, v in host.items()}
+            getp = hk.lib.sbc_get_particles if abi == 'f64' else hk.lib.sbc_get_particles_f32
+            for q in range(n):
+                (hk.set_state if abi == 'f64' else hk.set_state_f32)(**sub)      # H2D: 8 reals, 2 timers, alive per agent
+                hk.step(s_first + q * args.chunk, args.chunk)
+                hk._check(getp(hk.h, part[r0:r1].ctypes.data_as(rp), alive[r0:r1].ctypes.data_as(u8p)))  # D2H
 
-    e2e_abi = 'double (reference layout): sbc_set_state / sbc_get_particles'
+        def run_all(s_first, n):
+            th = [threading.Thread(target=run, args=(hk, r0, r1, s_first, n)) for hk, _, r0, r1 in parts]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+
+        run_all(s_now, 2)
+        barrier()
+        t0 = time.perf_counter()
+        run_all(s_now, n_steps)
+        barrier()
+        secs = time.perf_counter() - t0
+        tt = torch.tensor([secs], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return (world * R * N * args.chunk * n_steps / float(tt.item()), sum(v.nbytes for v in host.values()),
+                part.nbytes + alive.nbytes)
+
+    # The tanks are independent, so the public API is driven the way a user with host data would drive it: the ensemble
+    # is cut into E2E_PARTS handles, each on its own stream and host thread (ctypes releases the GIL), so that the upload
+    # of one part, the kernel of another and the download of a third overlap. The state every e2e step uploads is the
+    # ensemble as the timed region above left it (steady state, timers included). Headline: the float entry points
+    # (the device state is FP32; half the bytes on the host link); the reference's double layout is measured beside it.
+    e2e_value, h2d, d2h = e2e_measure('f32', args.steps)
+    log('e2e (f32 ABI) done')
+    e2e_f64_value, h2d64, d2h64 = e2e_measure('f64', max(2, args.steps // 2))
+    log('e2e (f64 ABI) done')
+    e2e_abi = 'float: sbc_set_state_f32 / sbc_get_particles_f32'
     e2e_note = ('%d handles on their own streams and host threads: uploads, kernels and downloads of different parts of the '
-                'ensemble overlap, and no L2 flush separates the launches' % E2E_PARTS)
-    e2e_all(s_now, 2)
-    log('e2e warm-up done')
-    barrier()
-    t0 = time.perf_counter()
-    e2e_all(s_now, args.steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * agent_steps_per_gpu / float(t.item())
-    h2d = sum(v.nbytes for v in host.values())
-    d2h = part.nbytes + alive.nbytes
-    log('e2e done: %.3f s' % e2e_s)
+                'ensemble overlap, and no L2 flush separates the launches; host threads and pinned buffers on the NUMA node of '
+                'the GPU (%s)' % (E2E_PARTS, 'node %d' % numa if numa is not None else 'not determined'))
     for hk, _, _, _ in parts:
         hk.close()
 
@@ -436,7 +479,9 @@ def main():
             'data': 'synthetic', 'config': workload_config(args, N),
             'pair_interactions_per_sec': world * pairs / (ms_max * 1e-3),
             'e2e': {'value': e2e_value, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'abi': e2e_abi, 'parts': E2E_PARTS, 'note': e2e_note},
+                    'abi': e2e_abi, 'parts': E2E_PARTS, 'note': e2e_note,
+                    'f64_abi': {'value': e2e_f64_value, 'h2d_bytes_per_step': h2d64, 'd2h_bytes_per_step': d2h64,
+                                'abi': 'double (reference layout): sbc_set_state / sbc_get_particles'}},
             'gpu_launches': int(launches), 'clocks': clocks,
             'roofline': {'kernel': kname, 'bound': 'fp32',
                          'achieved': ach, 'peak': peak_fp32, 'unit': 'TFLOP/s', 'frac': ach / peak_fp32,

@@ -104,9 +104,16 @@ int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, d
                   double *vproj, double *fx, double *fy, uint32_t *bin_step,
                   uint32_t *steps_till_burst, uint8_t *alive);
 
+/* The same with FLOAT arrays - what the device keeps anyway: for callers whose own data is single precision and for
+ * host links that are short of bandwidth (half the bytes of the reference layout). Same NULL rules. */
+int sbc_set_state_f32(sbc_handle *h, const float *x, const float *y, const float *vx, const float *vy,
+                      const float *phi, const float *vproj, const float *fx, const float *fy,
+                      const uint32_t *bin_step, const uint32_t *steps_till_burst, const uint8_t *alive);
+
 /* Rows in `particle::out()` layout (agents.cpp:4-17): x0 x1 v0 v1 fitness(=0) force0 force1,
  * indexed by agent id; dead agents keep all-zero rows as in /part (swarmdyn.cpp:561-600). */
 int sbc_get_particles(sbc_handle *h, double *out /* [R][N][7] */, uint8_t *alive /* [R][N] or NULL */);
+int sbc_get_particles_f32(sbc_handle *h, float *out /* [R][N][7] */, uint8_t *alive /* [R][N] or NULL */);
 /* Rows in `predator::out()` layout (agents.cpp:20-30): x0 x1 v0 v1 0 0. */
 int sbc_get_predators(sbc_handle *h, double *out /* [R][Npred][6] */);
 int sbc_set_predators(sbc_handle *h, const double *x, const double *y, const double *phi,

@@ -514,21 +514,19 @@ static int ensure_stage(sbc_handle *h) {
     return SBC_OK;
 }
 
-int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
-                  const double *vy, const double *phi, const double *vproj, const double *fx,
-                  const double *fy, const uint32_t *bin_step, const uint32_t *stb,
-                  const uint8_t *alive) {
+// shared by the double (reference layout) and the float entry point: `elem` = bytes per real number in the caller's arrays
+static int set_state_impl(sbc_handle *h, const void *const src[8], size_t elem, const uint32_t *bin_step, const uint32_t *stb,
+                          const uint8_t *alive) {
     if (!h) return SBC_ERR_INVALID;
     SBC_CUDA(cudaSetDevice(h->device));
     if (int rc = ensure_stage(h)) return rc;
     DevState &S = h->S;
     const size_t total = (size_t)S.N * S.R;
-    const double *dsrc[8] = {x, y, vx, vy, phi, vproj, fx, fy};
     unsigned mask = 0;
     for (int k = 0; k < 8; k++)
-        if (dsrc[k]) {
+        if (src[k]) {
             mask |= 1u << k;
-            SBC_CUDA(cudaMemcpyAsync(h->stage.d[k], dsrc[k], total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            SBC_CUDA(cudaMemcpyAsync(h->stage.d[k], src[k], total * elem, cudaMemcpyHostToDevice, h->stream));
         }
     if (bin_step) {
         mask |= SBC_ST_BIN;
@@ -543,15 +541,21 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
         SBC_CUDA(cudaMemcpyAsync(h->stage.al, alive, total, cudaMemcpyHostToDevice, h->stream));
     }
     if (h->state_set && !h->cs_valid) sbc_launch_refresh_cs(S, h->stream);   // a partial upload keeps the other fields
+    h->stage.f32 = (elem == sizeof(float)) ? 1 : 0;
     sbc_launch_pack_state(h->P, S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
     h->dense.sorted_valid = false;
     h->cells_valid = false;
     h->list_valid = false;
     h->nxt_synced = true;    // the pack kernel writes both position buffers
     h->cs_valid = true;
-    if (vproj)
-        for (size_t g = 0; g < total; g++)
-            if (vproj[g] > h->v0_max) h->v0_max = vproj[g];
+    // the largest speed bounds how long a cell order stays valid (Verlet skin): only the cell-list paths ask for it
+    if (src[5] && (h->use_cells || h->dom.enabled)) {
+        for (size_t g = 0; g < total; g++) {
+            const double v = (elem == sizeof(float)) ? (double)static_cast<const float *>(src[5])[g]
+                                                     : static_cast<const double *>(src[5])[g];
+            if (v > h->v0_max) h->v0_max = v;
+        }
+    }
     // a decomposed swarm rebuilds on every rank in the same step: a new state voids the agreed period (every exchange is
     // a full one until sbc_domain_rebuild_period is called again on all ranks)
     if (h->dom.enabled) h->dom_period = 0;
@@ -563,6 +567,21 @@ int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double 
     SBC_CUDA(cudaGetLastError());
     h->state_set = true;
     return SBC_OK;
+}
+
+int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
+                  const double *vy, const double *phi, const double *vproj, const double *fx,
+                  const double *fy, const uint32_t *bin_step, const uint32_t *stb,
+                  const uint8_t *alive) {
+    const void *src[8] = {x, y, vx, vy, phi, vproj, fx, fy};
+    return set_state_impl(h, src, sizeof(double), bin_step, stb, alive);
+}
+
+int sbc_set_state_f32(sbc_handle *h, const float *x, const float *y, const float *vx, const float *vy, const float *phi,
+                      const float *vproj, const float *fx, const float *fy, const uint32_t *bin_step, const uint32_t *stb,
+                      const uint8_t *alive) {
+    const void *src[8] = {x, y, vx, vy, phi, vproj, fx, fy};
+    return set_state_impl(h, src, sizeof(float), bin_step, stb, alive);
 }
 
 int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, double *phi,
@@ -579,6 +598,7 @@ int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, d
     if (bin_step) mask |= SBC_ST_BIN;
     if (stb) mask |= SBC_ST_STB;
     if (alive) mask |= SBC_ST_ALIVE;
+    h->stage.f32 = 0;
     sbc_launch_unpack_state(h->P, S, h->stage, mask, h->stream);
     h->host_stats[7]++;
     for (int k = 0; k < 8; k++)
@@ -600,9 +620,27 @@ int sbc_get_particles(sbc_handle *h, double *out, uint8_t *alive) {
         SBC_CUDA(dev_alloc(&h->part_dev, total * 7));
         SBC_CUDA(dev_alloc(&h->part_alive_dev, total));
     }
-    sbc_launch_particles(S, h->part_dev, h->part_alive_dev, h->stream);
+    sbc_launch_particles(S, h->part_dev, h->part_alive_dev, 0, h->stream);
     h->host_stats[7]++;
     SBC_CUDA(cudaMemcpyAsync(out, h->part_dev, total * 7 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (alive) SBC_CUDA(cudaMemcpyAsync(alive, h->part_alive_dev, total, cudaMemcpyDeviceToHost, h->stream));
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaGetLastError());
+    return SBC_OK;
+}
+
+int sbc_get_particles_f32(sbc_handle *h, float *out, uint8_t *alive) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    SBC_CUDA(cudaSetDevice(h->device));
+    DevState &S = h->S;
+    const size_t total = (size_t)S.N * S.R;
+    if (!h->part_dev) {
+        SBC_CUDA(dev_alloc(&h->part_dev, total * 7));
+        SBC_CUDA(dev_alloc(&h->part_alive_dev, total));
+    }
+    sbc_launch_particles(S, h->part_dev, h->part_alive_dev, 1, h->stream);
+    h->host_stats[7]++;
+    SBC_CUDA(cudaMemcpyAsync(out, h->part_dev, total * 7 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (alive) SBC_CUDA(cudaMemcpyAsync(alive, h->part_alive_dev, total, cudaMemcpyDeviceToHost, h->stream));
     SBC_CUDA(cudaStreamSynchronize(h->stream));
     SBC_CUDA(cudaGetLastError());

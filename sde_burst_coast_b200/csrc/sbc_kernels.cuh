@@ -342,6 +342,7 @@ __device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevStat
 // --- host <-> device state conversion (state_io.cu) ------------------------------------------
 // staging area in device memory holding the caller's arrays in the ABI's own layout
 struct StateStage {
+    int f32;        // the caller's real arrays hold floats (sbc_set_state_f32) instead of doubles
     double *d[8];   // x y vx vy phi vproj fx fy
     uint32_t *u[2]; // bin_step, steps_till_burst
     uint8_t *al;
@@ -351,7 +352,7 @@ enum { SBC_ST_X = 1, SBC_ST_Y = 2, SBC_ST_VX = 4, SBC_ST_VY = 8, SBC_ST_PHI = 16
 void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, int have_prev,
                            cudaStream_t stream);
 void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
-void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream);
+void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, int f32, cudaStream_t stream);
 
 // Launch with the highest stream priority as a LAUNCH ATTRIBUTE: it is recorded in the kernel node of a captured graph,
 // so the rows kernel's few blocks are dispatched ahead of the thousands of blocks of the bulk update that is launched

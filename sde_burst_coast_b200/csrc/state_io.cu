@@ -6,6 +6,11 @@
 
 namespace {
 
+// one real number of the caller's staged array k (double, or float for the _f32 entry points)
+__device__ __forceinline__ float stage_real(const StateStage &st, int k, size_t g) {
+    return st.f32 ? reinterpret_cast<const float *>(st.d[k])[g] : (float)st.d[k][g];
+}
+
 __global__ void __launch_bounds__(256)
 pack_state_kernel(const __grid_constant__ DevParams P, DevState S, StateStage st, unsigned mask, int have_prev) {
     const size_t total = (size_t)S.N * S.R;
@@ -27,19 +32,19 @@ pack_state_kernel(const __grid_constant__ DevParams P, DevState S, StateStage st
         bin = sbc_tm_bin(t, P);
         stb = sbc_tm_stb(t, P);
     }
-    if (mask & SBC_ST_X) pv.x = (float)st.d[0][g];
-    if (mask & SBC_ST_Y) pv.y = (float)st.d[1][g];
+    if (mask & SBC_ST_X) pv.x = stage_real(st, 0, g);
+    if (mask & SBC_ST_Y) pv.y = stage_real(st, 1, g);
     if (mask & SBC_ST_PHI) {
-        hv.x = (float)st.d[4][g];
+        hv.x = stage_real(st, 4, g);
         sincosf(hv.x, &cs.y, &cs.x);
     }
-    if (mask & SBC_ST_VPROJ) hv.y = (float)st.d[5][g];
-    if (mask & SBC_ST_VX) pv.z = (float)st.d[2][g];
+    if (mask & SBC_ST_VPROJ) hv.y = stage_real(st, 5, g);
+    if (mask & SBC_ST_VX) pv.z = stage_real(st, 2, g);
     else if (mask & SBC_ST_PHI) pv.z = hv.y * cs.x;  // v = vproj u(phi), settings.cpp:374-377
-    if (mask & SBC_ST_VY) pv.w = (float)st.d[3][g];
+    if (mask & SBC_ST_VY) pv.w = stage_real(st, 3, g);
     else if (mask & SBC_ST_PHI) pv.w = hv.y * cs.y;
-    if (mask & SBC_ST_FX) fo.x = (float)st.d[6][g];
-    if (mask & SBC_ST_FY) fo.y = (float)st.d[7][g];
+    if (mask & SBC_ST_FX) fo.x = stage_real(st, 6, g);
+    if (mask & SBC_ST_FY) fo.y = stage_real(st, 7, g);
     if (mask & SBC_ST_BIN) bin = min(st.u[0][g], P.tm_mask);
     if (mask & SBC_ST_STB) stb = st.u[1][g];
     if (mask & SBC_ST_ALIVE) al = st.al[g] ? 1 : 0;
@@ -85,7 +90,7 @@ unpack_state_kernel(const __grid_constant__ DevParams P, DevState S, StateStage 
 // rows of particle::out() (agents.cpp:4-17): x0 x1 v0 v1 fitness(=0) force0 force1; dead -> zeros.
 // One thread per output double so that the stores are contiguous.
 __global__ void __launch_bounds__(256)
-particles_kernel(DevState S, double *__restrict__ out, uint8_t *__restrict__ alive_out) {
+particles_kernel(DevState S, double *__restrict__ out, uint8_t *__restrict__ alive_out, int f32) {
     const size_t total = (size_t)S.N * S.R;
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= total * 7) return;
@@ -102,7 +107,8 @@ particles_kernel(DevState S, double *__restrict__ out, uint8_t *__restrict__ ali
             v = (k == 5) ? fo.x : fo.y;
         }
     }
-    out[t] = v;
+    if (f32) reinterpret_cast<float *>(out)[t] = (float)v;
+    else out[t] = v;
     if (k == 0 && alive_out) alive_out[g] = al;
 }
 
@@ -118,7 +124,7 @@ void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateS
     const size_t total = (size_t)S.N * S.R;
     unpack_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, S, st, mask);
 }
-void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, cudaStream_t stream) {
+void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, int f32, cudaStream_t stream) {
     const size_t n = (size_t)S.N * S.R * 7;
-    particles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(S, out_dev, alive_dev);
+    particles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(S, out_dev, alive_dev, f32);
 }

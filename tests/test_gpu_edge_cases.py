@@ -148,3 +148,29 @@ def test_cancelling_flee_forces_give_nan_like_the_reference():
     assert np.array_equal(fin_o[1:], fin_g[1:])
     # agent 0 sits exactly between the predators: the sum cancels to 0 (NaN) or to rounding noise (finite)
     assert np.isnan(o['fx'][0]) or abs(np.hypot(o['fx'][0], o['fy'][0]) - sp.soc_strength) < 1e-6
+
+
+def test_float_abi_equals_double_abi():
+    """sbc_set_state_f32 / sbc_get_particles_f32 carry the same numbers as the reference-layout double entry points
+    (the state is FP32 on the device either way): identical device state, identical particle rows."""
+    from sde_burst_coast_b200.swarm import Swarm
+    N, R = 30, 7
+    sp, _, _ = make_params('burst_coast', N)
+    rng = np.random.default_rng(12)
+    st = random_state(N * R, sp, rng)
+    state = {k: v.reshape(R, N) for k, v in st.items()}
+    state['alive'] = (rng.random((R, N)) > 0.1).astype(np.uint8)
+    a = Swarm(sp, N, n_replicates=R, seed=4)
+    b = Swarm(sp, N, n_replicates=R, seed=4)
+    a.set_state(**state)
+    b.set_state_f32(**state)
+    sa, sb = a.get_state(), b.get_state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k], equal_nan=True), k
+    a.step(0, 300)
+    b.step(0, 300)
+    pa, aa = a.get_particles()
+    pb, ab = b.get_particles_f32()
+    assert pb.dtype == np.float32 and np.array_equal(pa.astype(np.float32), pb) and np.array_equal(aa, ab)
+    a.close()
+    b.close()
