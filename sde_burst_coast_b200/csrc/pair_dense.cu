@@ -117,6 +117,33 @@ __global__ void iota_kernel(int *idx, int n_per_rep, size_t total) {
     if (g < total) idx[g] = (int)(g % n_per_rep);
 }
 
+// ensembles: every swarm is put in Hilbert order of its own agents. One sort over all of them with 64-bit keys
+// (replicate in the high word, curve index in the low one); the box of a swarm is the domain (periodic box, tank) or,
+// in an open domain, the bounding box of the whole ensemble (coarser cells, same locality).
+__global__ void curve_key_rep_kernel(const float4 *__restrict__ pv, int n_per_rep, size_t total, const int *__restrict__ bbox,
+                                     float fixed_lo, float fixed_hi, int use_bbox, unsigned long long *__restrict__ key,
+                                     int *__restrict__ idx) {
+    const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    float lo_x = fixed_lo, lo_y = fixed_lo, hi_x = fixed_hi, hi_y = fixed_hi;
+    if (use_bbox) {
+        lo_x = ordered_float(bbox[0]); lo_y = ordered_float(bbox[1]);
+        hi_x = ordered_float(bbox[2]); hi_y = ordered_float(bbox[3]);
+    }
+    const float4 p = pv[g];
+    uint32_t k = 0xffffffffu;   // dead agents sort behind the alive ones of their swarm
+    if (p.x == p.x) {
+        const float sx = 65535.f / fmaxf(hi_x - lo_x, 1e-20f), sy = 65535.f / fmaxf(hi_y - lo_y, 1e-20f);
+        const uint32_t qx = (uint32_t)fminf(fmaxf((p.x - lo_x) * sx, 0.f), 65535.f);
+        const uint32_t qy = (uint32_t)fminf(fmaxf((p.y - lo_y) * sy, 0.f), 65535.f);
+        k = hilbert_key(qx, qy);
+        if (k == 0xffffffffu) k = 0xfffffffeu;
+    }
+    const size_t rep = g / n_per_rep;
+    key[g] = ((unsigned long long)rep << 32) | k;
+    idx[g] = (int)(g - rep * n_per_rep);
+}
+
 __global__ void gather_sorted_kernel(const float4 *__restrict__ pv, const int *__restrict__ idx,
                                      int n_per_rep, size_t total, float4 *__restrict__ spv) {
     const size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -390,6 +417,13 @@ cudaError_t sbc_dense_scratch_alloc(DenseScratch &D, int N, int R) {
     if ((e = cudaMalloc((void **)&D.bbox, 4 * sizeof(int))) != cudaSuccess) return e;
     D.cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, D.cub_bytes, D.key_in, D.key_out, D.idx_in, D.idx_out, N);
+    if (R > 1) {   // ensembles: one sort of (replicate, curve index) keys over all swarms
+        if ((e = cudaMalloc((void **)&D.key64_in, total * sizeof(unsigned long long))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&D.key64_out, total * sizeof(unsigned long long))) != cudaSuccess) return e;
+        size_t b64 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, b64, D.key64_in, D.key64_out, D.idx_in, D.idx_out, (int)total);
+        if (b64 > D.cub_bytes) D.cub_bytes = b64;
+    }
     if ((e = cudaMalloc(&D.cub_tmp, D.cub_bytes ? D.cub_bytes : 16)) != cudaSuccess) return e;
     D.sorted_valid = false;
     return cudaSuccess;
@@ -398,6 +432,7 @@ cudaError_t sbc_dense_scratch_alloc(DenseScratch &D, int N, int R) {
 void sbc_dense_scratch_free(DenseScratch &D) {
     cudaFree(D.key_in); cudaFree(D.key_out); cudaFree(D.idx_in); cudaFree(D.idx_out);
     cudaFree(D.spv); cudaFree(D.part_f); cudaFree(D.part_i); cudaFree(D.bbox); cudaFree(D.cub_tmp);
+    cudaFree(D.key64_in); cudaFree(D.key64_out);
     D = DenseScratch();
 }
 
@@ -418,6 +453,20 @@ void sbc_launch_dense_sort(const DevParams &P, const DevState &S, DenseScratch &
         curve_key_kernel<<<blocks, 256, 0, st>>>(S.pv, N, D.bbox, lo, hi, use_bbox, D.key_in, D.idx_in);
         cub::DeviceRadixSort::SortPairs(D.cub_tmp, D.cub_bytes, D.key_in, D.key_out, D.idx_in, D.idx_out,
                                         N, 0, 32, st);
+    } else if (S.R > 1 && N > 64 && D.key64_in) {
+        float lo = 0.f, hi = P.L;
+        int use_bbox = 0;
+        if (P.BC == 5 || P.BC == 6) { lo = -P.L; hi = P.L; }
+        if (P.BC == -1) {
+            use_bbox = 1;
+            bbox_init_kernel<<<1, 1, 0, st>>>(D.bbox);
+            bbox_kernel<<<148, 256, 0, st>>>(S.pv, (int)total, D.bbox);
+        }
+        curve_key_rep_kernel<<<blocks, 256, 0, st>>>(S.pv, N, total, D.bbox, lo, hi, use_bbox, D.key64_in, D.idx_in);
+        int rep_bits = 1;
+        while ((1ll << rep_bits) < (long long)S.R) rep_bits++;
+        cub::DeviceRadixSort::SortPairs(D.cub_tmp, D.cub_bytes, D.key64_in, D.key64_out, D.idx_in, D.idx_out, (int)total, 0,
+                                        32 + rep_bits, st);
     } else {
         iota_kernel<<<blocks, 256, 0, st>>>(D.idx_out, N, total);
     }

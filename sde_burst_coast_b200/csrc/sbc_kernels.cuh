@@ -414,6 +414,7 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
 struct DenseScratch {
     uint32_t *key_in = nullptr, *key_out = nullptr;
     int *idx_in = nullptr, *idx_out = nullptr;   // idx_out[r] = agent id of sorted row r
+    unsigned long long *key64_in = nullptr, *key64_out = nullptr;   // ensembles: (replicate, curve index) keys
     float4 *spv = nullptr;                        // agents in sorted order
     float *part_f = nullptr;                      // [6][R][nsplit][N] partial zone sums
     int *part_i = nullptr;                        // [3][R][nsplit][N] partial zone counts

@@ -176,3 +176,31 @@ def test_cell_list_steps_match_all_pairs_path():
     assert np.array_equal(a['bin_step'], b['bin_step']) and np.array_equal(a['steps_till_burst'], b['steps_till_burst'])
     close = (np.abs(a['x'] - b['x']) < 1e-3) & (np.abs(a['y'] - b['y']) < 1e-3)
     assert close.mean() > 0.99
+
+
+@pytest.mark.parametrize('mode,over,N', [('natPred', dict(BC=0, size=100.0, Npred=0, alg_range=10.0), 300),
+                                        ('burst_coast', dict(BC=6, size=60.0), 200), ('burst_coast', dict(BC=-1), 150)])
+def test_dense_pass_on_an_ensemble(mode, over, N):
+    """All rows of several swarms in one launch (every swarm put in Hilbert order by one 64-bit-key sort): integers exact
+    per swarm against the oracle."""
+    from sde_burst_coast_b200.swarm import Swarm
+    R = 5
+    sp, _, _ = make_params(mode, N, **over)
+    rng = np.random.default_rng(31)
+    sts = [random_state(N, sp, rng, spread=60.0 if sp.BC == -1 else None) for _ in range(R)]
+    alive = (rng.random((R, N)) > 0.15).astype(np.uint8)
+    g = Swarm(sp, N, n_replicates=R)
+    g.set_state(alive=alive, **{k: np.stack([s[k] for s in sts]) for k in sts[0]})
+    got = g.pair_interactions(PAIR_ALL_ROWS)
+    g.close()
+    for r in range(R):
+        w = pyorc.World(sp, N)
+        w.set_state(alive=alive[r], **sts[r])
+        ref = w.pair_interactions(PAIR_ALL_ROWS)
+        w.close()
+        for k in ('c_rep', 'c_alg', 'c_att'):
+            assert np.array_equal(ref[k], got[k][r * N:(r + 1) * N]), (r, k)
+        lo, hi = got['nn_ptr'][r * N], got['nn_ptr'][(r + 1) * N]
+        assert np.array_equal(ref['nn_idx'], got['nn_idx'][lo:hi]), r
+        for k in ('f_rep', 'f_att'):
+            assert np.allclose(ref[k], got[k][r * N:(r + 1) * N], rtol=2e-5, atol=2e-5), (r, k)
