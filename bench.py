@@ -496,7 +496,8 @@ def main():
         }
         # ---- the north-star kernel: dense all-pairs three-zone pass -------------------------------
         try:
-            out['pair_kernel'] = pair_kernel_roofline(args.pair_n, local, peak_fp32, props.multi_processor_count, mhz)
+            if args.pair_n > 0:
+                out['pair_kernel'] = pair_kernel_roofline(args.pair_n, local, peak_fp32, props.multi_processor_count, mhz)
         except Exception as e:  # keep the headline line even if this leg fails
             out['pair_kernel'] = {'error': str(e)}
         log('pair kernel leg done')
@@ -527,6 +528,43 @@ def main():
         dist.destroy_process_group()
 
 
+def pair_cases(n):
+    """(name, agents, replicates, mode, parameter overrides, density, blob diameter / att_range) of the pair-kernel leg."""
+    dense = 1.6384
+    return [('open, dense', n, 1, 'burst_coast', dict(BC=-1), dense, None),
+            ('periodic, dense', n, 1, 'natPred', dict(BC=0, Npred=0), dense, None),
+            ('periodic, sparse (C4 density)', n, 1, 'natPred', dict(BC=0, Npred=0), 0.01, None),
+            ('open, dense', 16384, 1, 'burst_coast', dict(BC=-1), dense, None),
+            ('open, dense', 4096, 1, 'burst_coast', dict(BC=-1), dense, None),
+            ('open, dense', 4096, 16, 'burst_coast', dict(BC=-1), dense, None),
+            ('open, dense', 1024, 1, 'burst_coast', dict(BC=-1), dense, None),
+            ('open, dense', 1024, 64, 'burst_coast', dict(BC=-1), dense, None),
+            ('periodic, dense', 4096, 16, 'natPred', dict(BC=0, Npred=0), dense, None),
+            ('open, all near', 4096, 16, 'burst_coast', dict(BC=-1), None, 0.95)]
+
+
+def pair_case_tag(name, nn, reps, rho, blob):
+    return '%s_n%d_r%d' % (name.split(',')[0] + ('_allnear' if blob else ('_sparse' if rho == 0.01 else '')), nn, reps)
+
+
+def pair_case_state(name, nn, reps, mode, over, rho, blob):
+    """Parameters and the seeded state of one pair-kernel case (also used by profiles/pair_case.py for the ncu captures)."""
+    from helpers import make_params, f32
+    if over.get('BC') == 0:
+        over = dict(over, size=float(np.sqrt(nn / rho)))
+    sp, _, _ = make_params(mode, nn, **over)
+    rng = np.random.default_rng(SEED)
+    if blob is not None:     # a disc of diameter blob * att_range: no far pair at all
+        L = blob * sp.att_range
+        rad, th = 0.5 * L * np.sqrt(rng.random((reps, nn))), 2 * np.pi * rng.random((reps, nn))
+        x, y = rad * np.cos(th), rad * np.sin(th)
+    else:
+        L = float(np.sqrt(nn / rho))
+        x, y = L * rng.random((reps, nn)), L * rng.random((reps, nn))
+    st = dict(x=f32(x), y=f32(y), phi=f32(2 * np.pi * rng.random((reps, nn))), vproj=np.ones((reps, nn)))
+    return sp, st, L, over
+
+
 def pair_kernel_roofline(n, device, peak_fp32, sm_count, mhz):
     """Dense state (every row active, the reference state at s = 1): N(N-1) directed pairs/launch.
     Timed by sbc_bench_pair_pass with CUDA events on the handle's stream (gather + all-pairs kernel +
@@ -541,32 +579,9 @@ def pair_kernel_roofline(n, device, peak_fp32, sm_count, mhz):
     from sde_burst_coast_b200.swarm import Swarm
     from sde_burst_coast_b200.params import PAIR_ALL_ROWS
     res = {'bound': 'fp32', 'kernel': 'pair_dense_kernel', 'unit': 'TFLOP/s', 'peak': peak_fp32, 'cases': []}
-    dense = 1.6384
-    cases = [('open, dense', n, 1, 'burst_coast', dict(BC=-1), dense, None),
-             ('periodic, dense', n, 1, 'natPred', dict(BC=0, Npred=0), dense, None),
-             ('periodic, sparse (C4 density)', n, 1, 'natPred', dict(BC=0, Npred=0), 0.01, None),
-             ('open, dense', 16384, 1, 'burst_coast', dict(BC=-1), dense, None),
-             ('open, dense', 4096, 1, 'burst_coast', dict(BC=-1), dense, None),
-             ('open, dense', 4096, 16, 'burst_coast', dict(BC=-1), dense, None),
-             ('open, dense', 1024, 1, 'burst_coast', dict(BC=-1), dense, None),
-             ('open, dense', 1024, 64, 'burst_coast', dict(BC=-1), dense, None),
-             ('periodic, dense', 4096, 16, 'natPred', dict(BC=0, Npred=0), dense, None),
-             ('open, all near', 4096, 16, 'burst_coast', dict(BC=-1), None, 0.95)]
     issue_peak = 128.0 * sm_count * mhz * 1e6     # thread-instructions per second the FP32-class pipes can issue
-    for name, nn, reps, mode, over, rho, blob in cases:
-        if over.get('BC') == 0:
-            L = float(np.sqrt(nn / rho))
-            over = dict(over, size=L)
-        sp, _, _ = make_params(mode, nn, **over)
-        rng = np.random.default_rng(SEED)
-        if blob is not None:     # a disc of diameter blob * att_range: no far pair at all
-            L = blob * sp.att_range
-            rad, th = 0.5 * L * np.sqrt(rng.random((reps, nn))), 2 * np.pi * rng.random((reps, nn))
-            x, y = rad * np.cos(th), rad * np.sin(th)
-        else:
-            L = float(np.sqrt(nn / rho))
-            x, y = L * rng.random((reps, nn)), L * rng.random((reps, nn))
-        st = dict(x=f32(x), y=f32(y), phi=f32(2 * np.pi * rng.random((reps, nn))), vproj=np.ones((reps, nn)))
+    for name, nn, reps, mode, over, rho, blob in pair_cases(n):
+        sp, st, L, over = pair_case_state(name, nn, reps, mode, over, rho, blob)
         g = Swarm(sp, nn, n_replicates=reps, device=device)
         g.set_state(**st)
         s0 = g.stats()
@@ -585,7 +600,7 @@ def pair_kernel_roofline(n, device, peak_fp32, sm_count, mhz):
             case['frac_at_21_flop'] = pps * FLOP_PER_PAIR_PERIODIC / 1e12 / peak_fp32
         # issue-slot fraction of SURVEY 8(d): pairs/s * instructions per pair / (128 * SMs * f); the instruction count
         # per pair comes from smsp__thread_inst_executed of the committed ncu capture of this very case
-        tag = '%s_n%d_r%d' % (name.split(',')[0] + ('_allnear' if blob else ('_sparse' if rho == 0.01 else '')), nn, reps)
+        tag = pair_case_tag(name, nn, reps, rho, blob)
         prof = recorded_profile('r2_ncu_pair_dense_%s.txt' % tag, {'n': nn, 'replicates': reps}, 'pair_dense', ms * 1e-3, tol=0.25)
         if prof.get('used') and prof.get('warp_instructions') and prof.get('threads_per_warp_instruction'):
             ipp = prof['warp_instructions'] * prof['threads_per_warp_instruction'] / pairs

@@ -93,6 +93,13 @@ int sbc_synchronize(sbc_handle *h);
 
 /* ---- state in / out (arrays are [n_replicates][n_agents], replicate-major) ----------------- */
 
+/* Initial conditions generated ON THE DEVICE for every replicate: ResetSystem (settings.cpp:196-387) cases IC = 0..5 and
+ * the "else" branch (uniform in the box), followed by the reference's Boundary call (:384-386); unit speed, no force,
+ * burst timers 0 (InitSystem :168-193). The uniforms the reference pops from its clock-seeded GSL stream come from the
+ * handle's Philox key instead (counter: loop index, step 0xFFFFFFFF, slot 16, global replicate id), so a replicate's
+ * state does not depend on how the ensemble is split over handles or GPUs. IC 99 (a file) stays on the host. */
+int sbc_init_state(sbc_handle *h, int ic);
+
 /* Upload the agents' state; replaces InitSystem/ResetSystem output (settings.cpp:168-387) as the
  * source of x, v, phi, vproj, force, bin_step, steps_till_burst. Any pointer may be NULL to
  * keep the reference's InitSystem default (x,v from phi; vproj=1; force=0; counters=0). */
@@ -126,9 +133,24 @@ int sbc_get_counts(sbc_handle *h, int32_t *n_alive /* [R] */, int32_t *n_dead /*
  * split_dead + Step (swarmdyn.cpp:71,76,143-204) in metric neighbour mode. */
 int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps);
 
-/* ---- observables (Out_swarm subset, swarmdyn.cpp:237-344) ---------------------------------- */
+/* ---- observables on the device (Out_swarm swarmdyn.cpp:237-344, Out_swarm_fishNet :358-410) ---- */
 /* out[R][8]: N_alive, pol_order, avg_x0, avg_x1, avg_v0, avg_v1, avg_speed, NND(true nearest) */
 int sbc_observables(sbc_handle *h, double *out);
+
+/* out[R][16] = the reference's /swarm row of every replicate, from the state as it stands:
+ *   N, pol_order, L_norm, avg_x0, avg_x1, avg_v0, avg_v1, avg_speed, avg_vsquare, elongation, aspect_ratio,
+ *   a_com_maxIID, Area_ConHull, NND, IID, ND                                  (swarmdyn.cpp:324-343)
+ * with the reference's quirks (NND skips the agent listed just before i and is capped at N*alg_range :273-275, IID is
+ * the sum over j > i divided by N(N-1) :296, ND = NaN :270). extra[R][4] (may be NULL): mean distance to the TRUE
+ * nearest neighbour, mean distance over unordered pairs, the largest inter-individual distance, hull vertex count.
+ * Selections (nearest neighbour, most distant pair, extreme projections) are made in FP64 in the reference's operation
+ * order, so they pick the same agents; sums differ from a sequential double sum by summation order only.
+ * SBC_OBS_NO_PAIRS skips the O(N^2) pass: NND, IID, aspect_ratio, a_com_maxIID and extra[0..2] are NaN. */
+#define SBC_OBS_NO_PAIRS 1
+int sbc_out_swarm(sbc_handle *h, int flags, double *out, double *extra);
+
+/* out[R][4] = the /swarm_fishNet row: NfrontClose, distNet, Nfront, Ndead (swarmdyn.cpp:358-410); needs n_pred >= 1 */
+int sbc_out_swarm_fishnet(sbc_handle *h, double *out);
 
 /* ---- test hooks (parity tests call these through the ABI) --------------------------------- */
 

@@ -71,4 +71,42 @@ static inline uint32_t orc_geometric_k(const std::vector<uint32_t> &thr, uint32_
     }
     return (uint32_t)lo + 1;
 }
+
+/* ---- initial-condition protocol (ResetSystem, settings.cpp:196-387) ------------------------------
+ * The uniforms the reference pops from its serial stream, as words of Philox blocks: counter (loop index i, step
+ * 0xFFFFFFFF, slot 16): v[0] -> x draw, v[1] -> y draw, v[2] -> heading draw; counter (0xFFFFFFFE, ., 16): v[0] -> the
+ * swarm-wide heading; counter (0xFFFFFFFE, ., 17): round keys of the ring shuffle (four-round Feistel bijection on the
+ * next even power of two, cycle-walked into [0, N)). */
+static const uint32_t ORC_IC_STEP = 0xFFFFFFFFu, ORC_IC_SWARM_ID = 0xFFFFFFFEu;
+static inline uint32_t orc_ic_mix(uint32_t v) {
+    v *= 0x9E3779B1u; v ^= v >> 15; v *= 0x85EBCA77u; v ^= v >> 13;
+    return v;
+}
+static inline uint32_t orc_ic_permute(uint32_t i, uint32_t n, const OrcPhilox4 &key) {
+    uint32_t bits = 2;
+    while ((1ull << bits) < n) bits += 2;
+    const uint32_t half = bits / 2, mask = (1u << half) - 1u;
+    uint32_t x = i;
+    do {
+        uint32_t l = x >> half, r = x & mask;
+        for (int q = 0; q < 4; q++) { const uint32_t t = l ^ (orc_ic_mix(r ^ key.v[q]) & mask); l = r; r = t; }
+        x = (l << half) | r;
+    } while (x >= n);
+    return x;
+}
+/* the uniforms of one replicate in the order ResetSystem consumes them for initial condition `ic` */
+static inline std::vector<double> orc_ic_uniform_stream(uint64_t seed, uint64_t replicate, int ic, int N) {
+    std::vector<double> u;
+    const double theta_u = orc_u32_to_unit(orc_draw(seed, replicate, ORC_IC_SWARM_ID, ORC_IC_STEP, 16).v[0]);
+    if (ic == 1 || ic == 2 || ic == 3) u.push_back(theta_u);
+    for (int i = 0; i < N; i++) {
+        const OrcPhilox4 d = orc_draw(seed, replicate, (uint32_t)i, ORC_IC_STEP, 16);
+        const double ux = orc_u32_to_unit(d.v[0]), uy = orc_u32_to_unit(d.v[1]), up = orc_u32_to_unit(d.v[2]);
+        if (ic == 1 || ic == 2 || ic == 3 || ic == 4) { u.push_back(ux); u.push_back(uy); }
+        else if (ic == 5) { u.push_back(ux); u.push_back(uy); u.push_back(up); }
+        else { u.push_back(up); u.push_back(ux); u.push_back(uy); }      /* IC 0 and the "else" branch: heading first */
+    }
+    return u;
+}
+
 #endif

@@ -56,6 +56,9 @@ class OracleLib:
         L.orc_philox_decisions.argtypes = [ctypes.c_void_p, ctypes.c_int64, _dp, _dp, _u32p]
         L.orc_philox_raw.argtypes = [_u32p, _u32p, _u32p]
         L.orc_observables.argtypes = [ctypes.c_void_p, _dp]
+        L.orc_out_swarm.argtypes = [ctypes.c_void_p, _dp]
+        L.orc_init_state.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.orc_out_swarm_fishnet.argtypes = [ctypes.c_void_p, _dp]
         L.orc_ref_voronoi_step.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                            ctypes.c_uint32]
         L.orc_timed_steps.restype = ctypes.c_double
@@ -189,6 +192,24 @@ class World:
     def observables(self):
         out = np.zeros(8)
         self.L.orc_observables(self.h, _ptr(out, _dp))
+        return out
+
+    def init_state(self, ic):
+        """ResetSystem (settings.cpp:196-387) with the uniforms of the IC protocol: the port's restatement, or the
+        reference's own function fed through the replay queue."""
+        rc = self.L.orc_init_state(self.h, int(ic))
+        if rc != 0:
+            raise RuntimeError('orc_init_state(%d) -> %d' % (ic, rc))
+
+    def out_swarm(self):
+        """The 16 columns of Out_swarm (swarmdyn.cpp:237-344): the port's restatement or the reference's own function."""
+        out = np.zeros(16)
+        self.L.orc_out_swarm(self.h, _ptr(out, _dp))
+        return out
+
+    def out_swarm_fishnet(self):
+        out = np.zeros(4)
+        self.L.orc_out_swarm_fishnet(self.h, _ptr(out, _dp))
         return out
 
     def ref_out_swarm(self):

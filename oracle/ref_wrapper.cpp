@@ -423,6 +423,33 @@ void orc_ref_out_swarm(orc_world *w, double *out16) {
     for (int k = 0; k < 16; k++) out16[k] = o[k];
 }
 
+// the reference's own ResetSystem (settings.cpp:196-387) fed with the IC protocol's uniforms through the replay queue.
+// The ring shuffle of IC 3-5 is the reference's own (clock-seeded): WHICH agent sits on a ring place differs from the
+// protocol's bijection, the set of places does not.
+int orc_init_state(orc_world *w, int ic) {
+    if (ic == 99) return -1;
+    all_to_alive(w);
+    InitSystem(w->agent, w->SP);
+    gsl_rng *g = w->rng;
+    g->replay = true;
+    g->queue.clear();
+    for (double u : orc_ic_uniform_stream(w->seed, w->replicate, ic, w->N)) g->queue.push_back(u);
+    w->SP.IC = ic;
+    w->SP.N = w->N;
+    ResetSystem(w->agent, &w->SP, false, g);
+    const bool dry = g->queue.empty();
+    g->queue.clear();
+    w->SP.Ndead = 0;
+    return dry ? 0 : -2;    // -2: the reference consumed fewer uniforms than the protocol lists
+}
+
+// the reference's own rows, for both kinds of library under the same names
+void orc_out_swarm(orc_world *w, double *out16) { orc_ref_out_swarm(w, out16); }
+void orc_out_swarm_fishnet(orc_world *w, double *out4) {
+    std::vector<double> o = Out_swarm_fishNet(w->agent, w->preds, w->SP);
+    for (int k = 0; k < 4; k++) out4[k] = o[k];
+}
+
 int orc_ref_voronoi_step(orc_world *w, int64_t s_first, int64_t n_steps, uint32_t mt_seed) {
     // the shipped Step (swarmdyn.cpp:143-204): Delaunay drivers, global mt19937 stream
     if (!r) r = gsl_rng_alloc(gsl_rng_default);

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <algorithm>
 #include <vector>
+#include <limits>
 
 #include "sbc_oracle.h"
 #include "orc_philox.h"
@@ -994,6 +995,165 @@ void orc_observables(orc_world *w, double *out) {
     out[4] = av[0] / n; out[5] = av[1] / n;
     out[6] = as / n;
     out[7] = nnd / n;
+}
+
+// Out_swarm, swarmdyn.cpp:237-344 (with basic_particle_averages :486-510, get_elongation agents_operation.cpp:153-177,
+// AreaConvexHull :130-150 as a monotone-chain hull): the 16 columns of /swarm, quirks included - the nearest-neighbour
+// loop runs j < i-1 (:275) from N * alg_range (:273), IID sums j > i and is divided by N(N-1) (:296), ND divides by the
+// size of a possibly empty neighbour list (:270). Agents = the alive ones in id order (split_dead, :71).
+namespace {
+double port_elongation(const std::vector<const Agent *> &a, const double *dir) {
+    const double len = len2d(dir);
+    const double c[2] = {dir[0] / len, dir[1] / len}, q[2] = {c[1], -c[0]};
+    double mn = std::numeric_limits<double>::max(), mx = std::numeric_limits<double>::lowest(), pmn = mn, pmx = mx;
+    for (const Agent *g : a) {
+        const double d = g->x[0] * c[0] + g->x[1] * c[1], pd = g->x[0] * q[0] + g->x[1] * q[1];
+        mn = std::fmin(mn, d); mx = std::fmax(mx, d); pmn = std::fmin(pmn, pd); pmx = std::fmax(pmx, pd);
+    }
+    return std::fabs((mx - mn) / (pmx - pmn));
+}
+double port_hull_area(const std::vector<const Agent *> &a) {
+    std::vector<std::pair<double, double>> pts;
+    for (const Agent *g : a) pts.push_back({g->x[0], g->x[1]});
+    std::sort(pts.begin(), pts.end());
+    const int n = (int)pts.size();
+    if (n < 3) return 0;
+    std::vector<std::pair<double, double>> h(2 * n);
+    auto cross = [](const std::pair<double, double> &o, const std::pair<double, double> &p, const std::pair<double, double> &q) {
+        return (p.first - o.first) * (q.second - o.second) - (p.second - o.second) * (q.first - o.first);
+    };
+    int k = 0;
+    for (int i = 0; i < n; i++) { while (k >= 2 && cross(h[k - 2], h[k - 1], pts[i]) <= 0) k--; h[k++] = pts[i]; }
+    for (int i = n - 2, t = k + 1; i >= 0; i--) { while (k >= t && cross(h[k - 2], h[k - 1], pts[i]) <= 0) k--; h[k++] = pts[i]; }
+    double area = 0;
+    for (int i = 0; i + 1 < k; i++) area += h[i].first * h[i + 1].second - h[i + 1].first * h[i].second;
+    return 0.5 * area;
+}
+}  // namespace
+
+void orc_out_swarm(orc_world *w, double *out16) {
+    const sbc_params &p = w->p;
+    std::vector<const Agent *> a;
+    for (const Agent &g : w->a) if (!g.dead) a.push_back(&g);
+    const int N = (int)a.size();
+    double avg_v[2] = {0, 0}, avg_u[2] = {0, 0}, avg_s = 0, avg_v2 = 0, avg_x[2] = {0, 0};
+    for (const Agent *g : a) {   // :486-510
+        avg_v[0] += g->v[0]; avg_v[1] += g->v[1]; avg_u[0] += g->u[0]; avg_u[1] += g->u[1];
+        const double v2 = g->v[0] * g->v[0] + g->v[1] * g->v[1];
+        avg_s += std::sqrt(v2); avg_v2 += v2;
+    }
+    for (int d = 0; d < 2; d++) { avg_v[d] /= N; avg_u[d] /= N; }
+    avg_s /= N; avg_v2 /= N;
+    double IID = 0, NND = 0, ND = 0, max_IID = 0, max_vec[2] = {1, 1}, hd = 0, r[2];
+    for (int i = 0; i < N; i++) {
+        avg_x[0] += a[i]->x[0]; avg_x[1] += a[i]->x[1];
+        double nd = 0;
+        for (int j : a[i]->nn) { dist_vec(a[i]->x, w->a[j].x, p.BC, p.sizeL, r); nd += len2d(r); }   // :263-271
+        nd /= (double)a[i]->nn.size();
+        ND += nd;
+        hd = w->N * p.alg_range;                       // :273
+        for (int j = 0; j < i - 1; j++) { dist_vec(a[i]->x, a[j]->x, p.BC, p.sizeL, r); hd = std::fmin(hd, len2d(r)); }   // :275
+        for (int j = i + 1; j < N; j++) {              // :280-289
+            dist_vec(a[i]->x, a[j]->x, p.BC, p.sizeL, r);
+            const double d = len2d(r);
+            hd = std::fmin(hd, d);
+            IID += d;
+            if (d > max_IID) { max_IID = d; max_vec[0] = r[0]; max_vec[1] = r[1]; }
+        }
+        NND += hd;
+    }
+    avg_x[0] /= N; avg_x[1] /= N;
+    NND /= N; ND /= N;
+    IID /= (double)((N - 1) * N);
+    const double avgvel = len2d(avg_v), pol = len2d(avg_u);
+    double L_norm = 0;
+    for (const Agent *g : a) {   // :301-306
+        const double h[2] = {g->x[0] - avg_x[0], g->x[1] - avg_x[1]};
+        L_norm += (h[0] * g->v[1] - h[1] * g->v[0]) / len2d(h);
+    }
+    L_norm = std::fabs(L_norm) / N;
+    const double area = port_hull_area(a), elong = port_elongation(a, avg_u), aspect = port_elongation(a, max_vec);
+    double a1 = (avg_v[0] * max_vec[0] + avg_v[1] * max_vec[1]) / (avgvel * len2d(max_vec));
+    const double a2 = std::acos(-a1);
+    a1 = std::acos(a1);
+    const double o[16] = {(double)N, pol, L_norm, avg_x[0], avg_x[1], avg_v[0], avg_v[1], avg_s, avg_v2, elong, aspect,
+                          std::fmin(a1, a2), area, NND, IID, ND};
+    for (int k = 0; k < 16; k++) out16[k] = o[k];
+}
+
+// Out_swarm_fishNet, swarmdyn.cpp:358-410
+void orc_out_swarm_fishnet(orc_world *w, double *out4) {
+    const sbc_params &p = w->p;
+    int n_front_close = 0, n_front = 0, n = 0;
+    double r[2];
+    if (w->Npred > 1) {
+        const double *mv = w->preds[0].u;
+        double vnet[2];
+        dist_vec(w->preds[0].x, w->preds[1].x, p.BC, p.sizeL, vnet);
+        const double net_len = (w->Npred - 1) * len2d(vnet);
+        for (const Agent &g : w->a) {
+            if (g.dead) continue;
+            dist_vec(w->preds[0].x, g.x, p.BC, p.sizeL, r);
+            const double front = mv[0] * r[0] + mv[1] * r[1], side = vnet[0] * r[0] + vnet[1] * r[1];
+            if (side > 0 && side <= net_len) { n_front++; if (front > 0 && front < p.kill_range) n_front_close++; }
+        }
+    }
+    double dist_net = 0;
+    for (const Agent &g : w->a) {
+        if (g.dead) continue;
+        n++;
+        double dmin = p.sizeL * 2;
+        for (int j = 0; j < w->Npred; j++) { dist_vec(w->preds[j].x, g.x, p.BC, p.sizeL, r); dmin = std::fmin(dmin, len2d(r)); }
+        dist_net += dmin;
+    }
+    dist_net /= n;
+    int dead = 0;
+    for (const Agent &g : w->a) dead += g.dead;
+    out4[0] = n_front_close; out4[1] = dist_net; out4[2] = n_front; out4[3] = dead;
+}
+
+// ResetSystem, settings.cpp:196-387, on the repo's IC protocol (orc_philox.h): cases 0-5 and the "else" branch, unit
+// speed (:368-378), Boundary (:384-386). The ring shuffle of IC 3-5 is the protocol's keyed bijection (the reference
+// shuffles with a clock seed). Returns -1 for IC 99 (a file).
+int orc_init_state(orc_world *w, int ic) {
+    if (ic == 99) return -1;
+    const sbc_params &p = w->p;
+    const int N = w->N;
+    const double L = p.sizeL, range = 3 * p.rep_range;
+    const double theta_all = 2 * M_PI * orc_u32_to_unit(orc_draw(w->seed, w->replicate, ORC_IC_SWARM_ID, ORC_IC_STEP, 16).v[0]);
+    const OrcPhilox4 key = orc_draw(w->seed, w->replicate, ORC_IC_SWARM_ID, ORC_IC_STEP, 17);
+    int circle = (ic == 3) ? 1 : 3, Ncir = (ic == 3) ? 3 : int(2 * M_PI * circle), Ncap = Ncir, ccircle = 0;
+    const double sigma_space = (ic == 3) ? 0.8 : 1;
+    for (int i = 0; i < N; i++) {
+        const OrcPhilox4 d = orc_draw(w->seed, w->replicate, (uint32_t)i, ORC_IC_STEP, 16);
+        const double ux = orc_u32_to_unit(d.v[0]), uy = orc_u32_to_unit(d.v[1]), up = orc_u32_to_unit(d.v[2]);
+        int ii = i;
+        double x, y, phi;
+        if (ic == 1) { x = L * ux; y = L * uy; phi = theta_all; }                                  // :212-221
+        else if (ic == 0 || ic == 2) {                                                             // :237-257
+            x = std::fmin(L, std::sqrt(N) * range) * ux;
+            y = std::fmin(L, std::sqrt(N) * range) * uy;
+            phi = (ic == 0) ? 2 * M_PI * up : theta_all;
+        } else if (ic == 3 || ic == 4 || ic == 5) {                                                // :258-355
+            ii = (int)orc_ic_permute((uint32_t)i, (uint32_t)N, key);
+            if (i == Ncap) { circle += 1; Ncir = int(2 * M_PI * circle); Ncap += Ncir; ccircle = 0; }
+            const double angle = 2 * M_PI * ccircle / Ncir;
+            x = range * circle * std::cos(angle) + sigma_space * range * ux;
+            y = range * circle * std::sin(angle) + sigma_space * range * uy;
+            phi = (ic == 3) ? theta_all : (ic == 4) ? std::fmod(angle + M_PI / 2., 2 * M_PI) : 2 * M_PI * up;
+            ccircle += 1;
+        } else { x = L * ux; y = L * uy; phi = 2 * M_PI * up; }                                    // :357-366
+        Agent &a = w->a[ii];
+        a.x[0] = x; a.x[1] = y; a.phi = phi;
+        a.v[0] = a.u[0] = std::cos(phi); a.v[1] = a.u[1] = std::sin(phi);                          // :368-378
+        a.vproj = 1;
+        a.force[0] = a.force[1] = 0;
+        a.bin_step = a.stb = 0;
+        a.dead = false;
+        if (p.BC != -1) boundary(a, L, p.BC);   // :384-386; phi follows v only at the circular walls, as in the reference
+    }
+    w->n_dead = 0;
+    return 0;
 }
 
 int orc_ref_voronoi_step(orc_world *, int64_t, int64_t, uint32_t) { return -1; }

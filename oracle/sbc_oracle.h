@@ -77,6 +77,9 @@ void orc_philox_raw(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 
 /* Out_swarm subset (swarmdyn.cpp:237-344), same layout as sbc_observables: out[8]. */
 void orc_observables(orc_world *w, double *out);
+int orc_init_state(orc_world *w, int ic);                  /* ResetSystem settings.cpp:196-387 on the IC protocol */
+void orc_out_swarm(orc_world *w, double *out16);          /* swarmdyn.cpp:237-344 */
+void orc_out_swarm_fishnet(orc_world *w, double *out4);   /* swarmdyn.cpp:358-410 */
 
 /* reference build only: run the Step of swarmdyn.cpp:143-204 itself (Voronoi drivers on the
  * Delaunay shim, mt19937 stream) - returns -1 from the port. */

@@ -24,7 +24,7 @@ struct sbc_handle {
     std::string err;
     std::vector<uint32_t> geo_host;
     bool state_set;
-    double *obs_dev;
+    ObsScratch *obs;
     uint8_t *flags_dev;
     double *inj_social_dev;
     float *inj_dir_dev;
@@ -245,7 +245,7 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     h->replicate_offset = replicate_offset;
     h->own_stream = true;
     h->state_set = false;
-    h->obs_dev = nullptr;
+    h->obs = nullptr;
     h->flags_dev = nullptr;
     h->inj_social_dev = nullptr;
     h->inj_dir_dev = nullptr;
@@ -317,7 +317,6 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
     ok = ok && dev_alloc(&geo_dev, h->geo_host.size() ? h->geo_host.size() : 1) == cudaSuccess;
     double *eff_dev = nullptr;
     ok = ok && dev_alloc(&eff_dev, (size_t)n_agents + 1) == cudaSuccess;
-    ok = ok && dev_alloc(&h->obs_dev, (size_t)n_replicates * 8) == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("sbc_create: CUDA allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         sbc_destroy(h);
@@ -374,7 +373,7 @@ int sbc_destroy(sbc_handle *h) {
     cudaFree(S.edge_list[0]); cudaFree(S.edge_list[1]); cudaFree(S.edge_list[2]);
     cudaFree(S.ens_queue); cudaFree(S.ens_done);
     cudaFree(S.stats); cudaFree(const_cast<uint32_t *>(S.geo)); cudaFree(const_cast<double *>(S.kill_eff));
-    cudaFree(h->obs_dev); cudaFree(h->flags_dev);
+    sbc_obs_free(h->obs); cudaFree(h->flags_dev);
     if (h->dense_ready) sbc_dense_scratch_free(h->dense);
     if (h->cells_ready) sbc_cell_scratch_free(h->cells);
     if (h->dom.enabled) sbc_domain_scratch_free(h->dom);
@@ -515,6 +514,28 @@ static int ensure_stage(sbc_handle *h) {
 }
 
 // shared by the double (reference layout) and the float entry point: `elem` = bytes per real number in the caller's arrays
+// second half of every state change: the staged arrays named in `mask` become the device state
+static int finish_set_state(sbc_handle *h, unsigned mask, int have_prev) {
+    DevState &S = h->S;
+    sbc_launch_pack_state(h->P, S, h->stage, mask, have_prev, h->stream);
+    h->dense.sorted_valid = false;
+    h->cells_valid = false;
+    h->list_valid = false;
+    h->nxt_synced = true;    // the pack kernel writes both position buffers
+    h->cs_valid = true;
+    // a decomposed swarm rebuilds on every rank in the same step: a new state voids the agreed period (every exchange is
+    // a full one until sbc_domain_rebuild_period is called again on all ranks)
+    if (h->dom.enabled) h->dom_period = 0;
+    if (h->cells_ready || h->dom.enabled) set_cells_max_age(h);
+    if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
+    h->host_stats[7]++;
+    // the caller's buffers may be reused as soon as we return
+    SBC_CUDA(cudaStreamSynchronize(h->stream));
+    SBC_CUDA(cudaGetLastError());
+    h->state_set = true;
+    return SBC_OK;
+}
+
 static int set_state_impl(sbc_handle *h, const void *const src[8], size_t elem, const uint32_t *bin_step, const uint32_t *stb,
                           const uint8_t *alive) {
     if (!h) return SBC_ERR_INVALID;
@@ -542,12 +563,6 @@ static int set_state_impl(sbc_handle *h, const void *const src[8], size_t elem, 
     }
     if (h->state_set && !h->cs_valid) sbc_launch_refresh_cs(S, h->stream);   // a partial upload keeps the other fields
     h->stage.f32 = (elem == sizeof(float)) ? 1 : 0;
-    sbc_launch_pack_state(h->P, S, h->stage, mask, h->state_set ? 1 : 0, h->stream);
-    h->dense.sorted_valid = false;
-    h->cells_valid = false;
-    h->list_valid = false;
-    h->nxt_synced = true;    // the pack kernel writes both position buffers
-    h->cs_valid = true;
     // the largest speed bounds how long a cell order stays valid (Verlet skin): only the cell-list paths ask for it
     if (src[5] && (h->use_cells || h->dom.enabled)) {
         for (size_t g = 0; g < total; g++) {
@@ -556,17 +571,7 @@ static int set_state_impl(sbc_handle *h, const void *const src[8], size_t elem, 
             if (v > h->v0_max) h->v0_max = v;
         }
     }
-    // a decomposed swarm rebuilds on every rank in the same step: a new state voids the agreed period (every exchange is
-    // a full one until sbc_domain_rebuild_period is called again on all ranks)
-    if (h->dom.enabled) h->dom_period = 0;
-    if (h->cells_ready || h->dom.enabled) set_cells_max_age(h);
-    if (h->dom.enabled) sbc_launch_domain_reset(S, h->dom, h->stream);
-    h->host_stats[7]++;
-    // the caller's buffers may be reused as soon as we return
-    SBC_CUDA(cudaStreamSynchronize(h->stream));
-    SBC_CUDA(cudaGetLastError());
-    h->state_set = true;
-    return SBC_OK;
+    return finish_set_state(h, mask, h->state_set ? 1 : 0);
 }
 
 int sbc_set_state(sbc_handle *h, const double *x, const double *y, const double *vx,
@@ -582,6 +587,20 @@ int sbc_set_state_f32(sbc_handle *h, const float *x, const float *y, const float
                       const uint8_t *alive) {
     const void *src[8] = {x, y, vx, vy, phi, vproj, fx, fy};
     return set_state_impl(h, src, sizeof(float), bin_step, stb, alive);
+}
+
+int sbc_init_state(sbc_handle *h, int ic) {
+    if (!h) return SBC_ERR_INVALID;
+    if (ic == 99) return fail(h, SBC_ERR_INVALID, "sbc_init_state: IC 99 reads a file - load it on the host and call sbc_set_state");
+    if (h->dom.enabled) return fail(h, SBC_ERR_INVALID, "sbc_init_state: not available on a slab of a decomposed swarm");
+    SBC_CUDA(cudaSetDevice(h->device));
+    if (int rc = ensure_stage(h)) return rc;
+    h->stage.f32 = 0;
+    sbc_launch_init_cond(h->P, h->S, ic, h->hp.rep_range, h->stage, h->stream);
+    h->host_stats[7]++;
+    if (h->v0_max < 1.0) h->v0_max = 1.0;     // unit speed, settings.cpp:368-378
+    // have_prev = 0: everything the kernel did not write is InitSystem's default (no force, timers 0, alive)
+    return finish_set_state(h, SBC_ST_X | SBC_ST_Y | SBC_ST_VX | SBC_ST_VY | SBC_ST_PHI | SBC_ST_VPROJ, 0);
 }
 
 int sbc_get_state(sbc_handle *h, double *x, double *y, double *vx, double *vy, double *phi,
@@ -964,14 +983,35 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     return SBC_OK;
 }
 
+static int obs_ready(sbc_handle *h, const char *who) {
+    if (!h->state_set) return fail(h, SBC_ERR_STATE, std::string(who) + ": no state");
+    if (h->dom.enabled) return fail(h, SBC_ERR_INVALID, std::string(who) + ": not available on a slab of a decomposed swarm");
+    return SBC_OK;
+}
+
 int sbc_observables(sbc_handle *h, double *out) {
     if (!h || !out) return SBC_ERR_INVALID;
+    if (int rc = obs_ready(h, "sbc_observables")) return rc;
     SBC_CUDA(cudaSetDevice(h->device));
-    sbc_launch_observables(h->P, h->S, h->obs_dev, h->stream);
-    h->host_stats[7]++;
-    SBC_CUDA(cudaStreamSynchronize(h->stream));
-    SBC_CUDA(cudaMemcpy(out, h->obs_dev, (size_t)h->S.R * 8 * sizeof(double), cudaMemcpyDeviceToHost));
-    return SBC_OK;
+    h->host_stats[7] += 8;
+    return sbc_obs_out_swarm(h->P, h->S, h->hp, &h->obs, 0, nullptr, nullptr, out, h->stream, h->err);
+}
+
+int sbc_out_swarm(sbc_handle *h, int flags, double *out, double *extra) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    if (int rc = obs_ready(h, "sbc_out_swarm")) return rc;
+    SBC_CUDA(cudaSetDevice(h->device));
+    h->host_stats[7] += (flags & SBC_OBS_NO_PAIRS) ? 7 : 8;
+    return sbc_obs_out_swarm(h->P, h->S, h->hp, &h->obs, flags, out, extra, nullptr, h->stream, h->err);
+}
+
+int sbc_out_swarm_fishnet(sbc_handle *h, double *out) {
+    if (!h || !out) return SBC_ERR_INVALID;
+    if (int rc = obs_ready(h, "sbc_out_swarm_fishnet")) return rc;
+    if (h->S.Npred < 1) return fail(h, SBC_ERR_INVALID, "sbc_out_swarm_fishnet: the handle has no predators");
+    SBC_CUDA(cudaSetDevice(h->device));
+    h->host_stats[7] += 4;
+    return sbc_obs_fishnet(h->P, h->S, &h->obs, out, h->stream, h->err);
 }
 
 int sbc_pair_interactions(sbc_handle *h, int flags, int32_t *c_rep, int32_t *c_alg, int32_t *c_att,

@@ -351,6 +351,7 @@ enum { SBC_ST_X = 1, SBC_ST_Y = 2, SBC_ST_VX = 4, SBC_ST_VY = 8, SBC_ST_PHI = 16
        SBC_ST_FX = 64, SBC_ST_FY = 128, SBC_ST_BIN = 256, SBC_ST_STB = 512, SBC_ST_ALIVE = 1024 };
 void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, int have_prev,
                            cudaStream_t stream);
+void sbc_launch_init_cond(const DevParams &P, const DevState &S, int ic, double rep_range, const StateStage &st, cudaStream_t stream);
 void sbc_launch_unpack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, cudaStream_t stream);
 void sbc_launch_particles(const DevState &S, double *out_dev, uint8_t *alive_dev, int f32, cudaStream_t stream);
 
@@ -502,4 +503,11 @@ cudaError_t sbc_launch_swarm_cluster(const DevParams &P, const DevState &S, long
                                      cudaStream_t st, long long s_pred = -1, int s_trunc = 0, int needed = 0);
 
 // --- observables (observables.cu) --------------------------------------------------------------
-void sbc_launch_observables(const DevParams &P, const DevState &S, double *out_dev, cudaStream_t st);
+// observables.cu: Out_swarm / Out_swarm_fishNet rows of every replicate (results to host memory; scratch is created on first use)
+struct ObsScratch;
+struct sbc_params;
+#include <string>
+int sbc_obs_out_swarm(const DevParams &P, const DevState &S, const sbc_params &hp, ObsScratch **scr, int flags,
+                      double *out16_host, double *extra_host, double *out8_host, cudaStream_t st, std::string &err);
+int sbc_obs_fishnet(const DevParams &P, const DevState &S, ObsScratch **scr, double *out4_host, cudaStream_t st, std::string &err);
+void sbc_obs_free(ObsScratch *o);

@@ -114,6 +114,130 @@ particles_kernel(DevState S, double *__restrict__ out, uint8_t *__restrict__ ali
 
 }  // namespace
 
+
+namespace {
+// ---- initial conditions on the device (ResetSystem, /root/reference/src/settings.cpp:196-387) -------------------------
+// Every uniform the reference pops from its serial GSL stream is a word of a Philox block here:
+//   counter (agent = loop index i, step = 0xFFFFFFFF, slot = 16, replicate):  .x -> x draw, .y -> y draw, .z -> heading
+//   counter (agent = 0xFFFFFFFE, same step / slot):                           .x -> the swarm-wide heading of IC 1, 2, 3
+//   counter (agent = 0xFFFFFFFE, slot = 17):                                  four round keys of the ring shuffle
+// The shuffle of IC 3-5 (std::shuffle / random_shuffle with a clock seed in the reference) is a keyed bijection of
+// [0, N): a four-round Feistel network on the next even power of two, cycle-walked back into range. Arithmetic is FP64 in
+// the reference's operation order (no contraction), the state is rounded to FP32 by the pack kernel as for any upload.
+#define SBC_IC_STEP 0xFFFFFFFFu
+#define SBC_IC_SWARM_ID 0xFFFFFFFEu
+
+__device__ __forceinline__ uint32_t ic_mix(uint32_t v) {
+    v *= 0x9E3779B1u; v ^= v >> 15; v *= 0x85EBCA77u; v ^= v >> 13;
+    return v;
+}
+__device__ uint32_t ic_permute(uint32_t i, uint32_t n, const uint4 key) {
+    uint32_t bits = 2;
+    while ((1ull << bits) < n) bits += 2;
+    const uint32_t half = bits / 2, mask = (1u << half) - 1u;
+    const uint32_t k[4] = {key.x, key.y, key.z, key.w};
+    uint32_t x = i;
+    do {
+        uint32_t l = x >> half, r = x & mask;
+        for (int q = 0; q < 4; q++) { const uint32_t t = l ^ (ic_mix(r ^ k[q]) & mask); l = r; r = t; }
+        x = (l << half) | r;
+    } while (x >= n);
+    return x;
+}
+
+// Boundary<particle> (agents_dynamics.cpp:276-471) on a fresh agent, FP64 in the reference's operation order. As there,
+// a.phi follows the velocity only at the circular walls (:447-449, :467-469); the box walls flip or replace v and leave phi.
+__device__ void ic_boundary(double &x, double &y, double &vx, double &vy, double &phi, double L, int BC) {
+    const double dphi = 0.1;
+    if (BC == 0) {
+        x = fmod(__dadd_rn(x, L), L);
+        y = fmod(__dadd_rn(y, L), L);
+    } else if (BC == 1) {                        // :300-356 inelastic box
+        double t = 0;
+        bool hit = true;
+        if (x > L) { x = __dmul_rn(0.9999, L); t = (vy > 0.) ? __dmul_rn(0.5 + dphi, SBC_PI_D) : __dmul_rn(-(0.5 + dphi), SBC_PI_D); }
+        else if (x < 0) { x = 0.0001; t = (vy > 0.) ? __dmul_rn(0.5 - dphi, SBC_PI_D) : __dmul_rn(-(0.5 - dphi), SBC_PI_D); }
+        else hit = false;
+        if (hit) { vx = cos(t); vy = sin(t); }
+        hit = true;
+        if (y > L) { y = __dmul_rn(0.9999, L); t = (vx > 0.) ? -dphi : __dadd_rn(SBC_PI_D, dphi); }
+        else if (y < 0) { y = 0.0001; t = (vx > 0.) ? dphi : __dsub_rn(SBC_PI_D, dphi); }
+        else hit = false;
+        if (hit) { vx = cos(t); vy = sin(t); }
+    } else if (BC == 2 || BC == 3) {             // :358-406 elastic walls (BC 3: x periodic)
+        if (BC == 3) { double tx = fmod(x, L); if (tx < 0.0) tx = __dadd_rn(tx, L); x = tx; }
+        else if (x > L) { x = __dsub_rn(x, __dmul_rn(2., __dsub_rn(x, L))); vx = -vx; }
+        else if (x < 0) { x = __dsub_rn(x, __dmul_rn(2., x)); vx = -vx; }
+        if (y > L) { y = __dsub_rn(y, __dmul_rn(2., __dsub_rn(y, L))); vy = -vy; }
+        else if (y < 0) { y = __dsub_rn(y, __dmul_rn(2., y)); vy = -vy; }
+    } else if (BC == 4) {                        // :407-430 x periodic, y inelastic
+        double tx = fmod(x, L);
+        if (tx < 0.0) tx = __dadd_rn(tx, L);
+        x = tx;
+        if (y > L) { y = __dsub_rn(y, __dadd_rn(__dsub_rn(y, L), 0.0001)); vy = 0.0; }
+        else if (y < 0) { y = __dsub_rn(y, __dsub_rn(y, 0.0001)); vy = 0.0; }
+    } else if (BC == 5 || BC == 6) {             // :432-470 circular tank
+        const double r = sqrt(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+        double diff = __dsub_rn(r, L);
+        if (diff > 0) {
+            const double inv = 1 / r, nx = __dmul_rn(x, inv), ny = __dmul_rn(y, inv), f = __dmul_rn(-2, diff);
+            x = __dadd_rn(x, __dmul_rn(nx, f));
+            y = __dadd_rn(y, __dmul_rn(ny, f));
+            diff = __dadd_rn(__dmul_rn(nx, vx), __dmul_rn(ny, vy));
+            const double g = (BC == 5) ? __dmul_rn(-2, diff) : -diff;
+            vx = __dadd_rn(vx, __dmul_rn(nx, g));
+            vy = __dadd_rn(vy, __dmul_rn(ny, g));
+            const double len = sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)));
+            const double corr = 1 / len;                   // vec_set_mag, mathtools.h:138-144
+            phi = atan2(__dmul_rn(vy, corr), __dmul_rn(vx, corr));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+init_cond_kernel(const __grid_constant__ DevParams P, int N, int R, int ic, double rep_range, StateStage st) {
+    const size_t total = (size_t)N * R;
+    const size_t gi = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (gi >= total) return;
+    const uint32_t rep = (uint32_t)(gi / N), i = (uint32_t)(gi % N);     // i = the reference's loop index
+    const double u32 = 1.0 / 4294967296.0, two_pi = __dmul_rn(2, SBC_PI_D), L = P.dL;
+    const double range = __dmul_rn(3, rep_range);
+    const uint4 d = sbc_draw(P, rep, i, SBC_IC_STEP, 16u);
+    const uint4 sw = sbc_draw(P, rep, SBC_IC_SWARM_ID, SBC_IC_STEP, 16u);
+    const double ux = d.x * u32, uy = d.y * u32, up = d.z * u32, theta_all = __dmul_rn(two_pi, sw.x * u32);
+    double x, y, phi;
+    uint32_t agent = i;
+    if (ic == 1) {                                   // :212-221
+        x = __dmul_rn(L, ux); y = __dmul_rn(L, uy); phi = theta_all;
+    } else if (ic == 0 || ic == 2) {                 // :237-257
+        const double side = fmin(L, __dmul_rn(sqrt((double)N), range));
+        x = __dmul_rn(side, ux); y = __dmul_rn(side, uy);
+        phi = (ic == 0) ? __dmul_rn(two_pi, up) : theta_all;
+    } else if (ic == 3 || ic == 4 || ic == 5) {      // :258-355, agents on perturbed concentric rings
+        int circle = (ic == 3) ? 1 : 3, ncir = (ic == 3) ? 3 : (int)__dmul_rn(two_pi, 3.0), ncap = ncir, base = 0;
+        while ((int)i >= ncap) { circle++; ncir = (int)__dmul_rn(two_pi, (double)circle); base = ncap; ncap += ncir; }
+        const double ang = __dmul_rn(two_pi, (double)((int)i - base)) / (double)ncir;
+        const double sig = (ic == 3) ? 0.8 : 1.0, rc = __dmul_rn(range, (double)circle), sr = __dmul_rn(sig, range);
+        x = __dadd_rn(__dmul_rn(rc, cos(ang)), __dmul_rn(sr, ux));
+        y = __dadd_rn(__dmul_rn(rc, sin(ang)), __dmul_rn(sr, uy));
+        phi = (ic == 3) ? theta_all : (ic == 4) ? fmod(__dadd_rn(ang, SBC_PI_D / 2.), two_pi) : __dmul_rn(two_pi, up);
+        agent = ic_permute(i, (uint32_t)N, sbc_draw(P, rep, SBC_IC_SWARM_ID, SBC_IC_STEP, 17u));
+    } else {                                         // :357-366
+        x = __dmul_rn(L, ux); y = __dmul_rn(L, uy); phi = __dmul_rn(two_pi, up);
+    }
+    double vx = cos(phi), vy = sin(phi);           // :368-378 unit speed
+    if (P.BC != -1) ic_boundary(x, y, vx, vy, phi, L, P.BC);
+    const size_t g = (size_t)rep * N + agent;
+    st.d[0][g] = x; st.d[1][g] = y; st.d[2][g] = vx; st.d[3][g] = vy; st.d[4][g] = phi; st.d[5][g] = 1.0;
+}
+
+}  // namespace
+
+void sbc_launch_init_cond(const DevParams &P, const DevState &S, int ic, double rep_range, const StateStage &st, cudaStream_t stream) {
+    const size_t total = (size_t)S.N * S.R;
+    init_cond_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(P, S.N, S.R, ic, rep_range, st);
+}
+
 void sbc_launch_pack_state(const DevParams &P, const DevState &S, const StateStage &st, unsigned mask, int have_prev,
                            cudaStream_t stream) {
     const size_t total = (size_t)S.N * S.R;

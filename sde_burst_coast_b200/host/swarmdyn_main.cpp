@@ -165,253 +165,24 @@ void output_parameters(const HostParams &p) {  // input_output.cpp:161-201, same
     fclose(fp);
 }
 
-// ---- initial conditions (settings.cpp:196-387); uniforms from a seeded mt19937 ---------------------
-struct Rng {
-    std::mt19937 gen;
-    explicit Rng(uint64_t s) : gen((uint32_t)(s ^ (s >> 32))) {}
-    double uniform() { return gen() / 4294967296.0; }  // [0,1) like gsl_rng_uniform on mt19937
-};
-
-// Boundary<particle> applied once to the initial positions (settings.cpp:384-386 ->
-// agents_dynamics.cpp:276-471); only position/heading matter for an agent with v = u
-void boundary_ic(double &x, double &y, double &phi, double L, int BC) {
-    if (BC == 0) {
-        x = std::fmod(x + L, L);
-        y = std::fmod(y + L, L);
-    } else if (BC == 3 || BC == 4) {
-        x = std::fmod(x, L);
-        if (x < 0) x += L;
-        if (y > L) y = 2 * L - y; else if (y < 0) y = -y;
-    } else if (BC == 1) {
-        if (x > L) x = 0.9999 * L; else if (x < 0) x = 0.0001;
-        if (y > L) y = 0.9999 * L; else if (y < 0) y = 0.0001;
-    } else if (BC == 2) {
-        if (x > L) x = 2 * L - x; else if (x < 0) x = -x;
-        if (y > L) y = 2 * L - y; else if (y < 0) y = -y;
-    } else if (BC == 5 || BC == 6) {
-        const double r = std::sqrt(x * x + y * y);
-        if (r > L) {
-            const double nx = x / r, ny = y / r, diff = r - L;
-            x -= 2 * diff * nx;
-            y -= 2 * diff * ny;
-            double vx = std::cos(phi), vy = std::sin(phi);
-            const double vn = nx * vx + ny * vy;
-            const double g = (BC == 5) ? 2 * vn : vn;
-            vx -= g * nx;
-            vy -= g * ny;
-            phi = std::atan2(vy, vx);
-        }
-    }
-}
-
-void ring_positions(const HostParams &p, Rng &rng, int first_circle, bool ncir_from_circle, double sigma_space,
-                    std::vector<int> &order, std::vector<double> &x, std::vector<double> &y,
-                    std::vector<double> &slot_angle) {
-    // shared by IC 3, 4, 5 (settings.cpp:258-355): agents on perturbed concentric rings
+// ---- initial conditions: ResetSystem's cases (settings.cpp:196-387) are generated on the device by sbc_init_state;
+// only IC 99 reads "x y vx vy" per line from <location>initCoord.dat here (cf. settings.cpp:222-236) ----------------
+bool load_init_coord(const HostParams &p, std::vector<double> &x, std::vector<double> &y, std::vector<double> &phi,
+                     std::vector<double> &vproj) {
     const int N = p.N;
-    const double range = 3 * p.rep_range;
-    int circle = first_circle, Ncir = ncir_from_circle ? (int)(2 * M_PI * circle) : 3, Ncap = Ncir, cc = 0;
-    for (int i = 0; i < N; i++) {
-        const int ii = order[i];
-        if (i == Ncap) {
-            circle += 1;
-            Ncir = (int)(2 * M_PI * circle);
-            Ncap += Ncir;
-            cc = 0;
-        }
-        const double ang = 2 * M_PI * cc / Ncir;
-        x[ii] = range * circle * std::cos(ang) + sigma_space * range * rng.uniform();
-        y[ii] = range * circle * std::sin(ang) + sigma_space * range * rng.uniform();
-        slot_angle[ii] = ang;
-        cc++;
-    }
-}
-
-bool reset_system(const HostParams &p, Rng &rng, std::vector<double> &x, std::vector<double> &y,
-                  std::vector<double> &phi, std::vector<double> &vproj) {
-    const int N = p.N;
-    const double L = p.sizeL, range = 3 * p.rep_range;
     x.assign(N, 0); y.assign(N, 0); phi.assign(N, 0); vproj.assign(N, 1.0);
-    std::vector<int> order(N);
-    std::iota(order.begin(), order.end(), 0);
-    std::vector<double> slot(N, 0);
-    const int IC = p.IC;
-    if (IC == 1) {
-        const double th = 2 * M_PI * rng.uniform();
-        for (int i = 0; i < N; i++) { x[i] = L * rng.uniform(); y[i] = L * rng.uniform(); phi[i] = th; }
-    } else if (IC == 99) {  // "x y vx vy" per line in <location>initCoord.dat (cf. settings.cpp:222-236)
-        std::ifstream in((p.location + "initCoord.dat").c_str());
-        if (!in) { fprintf(stderr, "swarmdyn: IC 99 needs %sinitCoord.dat\n", p.location.c_str()); return false; }
-        for (int i = 0; i < N; i++) {
-            double vx = 1, vy = 0;
-            if (!(in >> x[i] >> y[i] >> vx >> vy)) { fprintf(stderr, "swarmdyn: initCoord.dat has fewer than %d rows\n", N); return false; }
-            phi[i] = std::atan2(vy, vx);
-            vproj[i] = std::sqrt(vx * vx + vy * vy);
-        }
-    } else if (IC == 0) {
-        for (int i = 0; i < N; i++) {
-            const double th = 2 * M_PI * rng.uniform();
-            x[i] = std::fmin(L, std::sqrt((double)N) * range) * rng.uniform();
-            y[i] = std::fmin(L, std::sqrt((double)N) * range) * rng.uniform();
-            phi[i] = th;
-        }
-    } else if (IC == 2) {
-        const double th = 2 * M_PI * rng.uniform();
-        for (int i = 0; i < N; i++) {
-            x[i] = std::fmin(L, std::sqrt((double)N) * range) * rng.uniform();
-            y[i] = std::fmin(L, std::sqrt((double)N) * range) * rng.uniform();
-            phi[i] = th;
-        }
-    } else if (IC == 3) {
-        const double th = 2 * M_PI * rng.uniform();
-        std::shuffle(order.begin(), order.end(), rng.gen);
-        ring_positions(p, rng, 1, false, 0.8, order, x, y, slot);
-        for (int i = 0; i < N; i++) phi[i] = th;
-    } else if (IC == 4 || IC == 5) {
-        std::shuffle(order.begin(), order.end(), rng.gen);
-        ring_positions(p, rng, 3, true, 1.0, order, x, y, slot);
-        for (int i = 0; i < N; i++)
-            phi[order[i]] = (IC == 4) ? std::fmod(slot[order[i]] + M_PI / 2., 2 * M_PI) : 2 * M_PI * rng.uniform();
-    } else {
-        for (int i = 0; i < N; i++) {
-            const double th = 2 * M_PI * rng.uniform();
-            x[i] = L * rng.uniform(); y[i] = L * rng.uniform(); phi[i] = th;
-        }
+    std::ifstream in((p.location + "initCoord.dat").c_str());
+    if (!in) { fprintf(stderr, "swarmdyn: IC 99 needs %sinitCoord.dat\n", p.location.c_str()); return false; }
+    for (int i = 0; i < N; i++) {
+        double vx = 1, vy = 0;
+        if (!(in >> x[i] >> y[i] >> vx >> vy)) { fprintf(stderr, "swarmdyn: initCoord.dat has fewer than %d rows\n", N); return false; }
+        phi[i] = std::atan2(vy, vx);
+        vproj[i] = std::sqrt(vx * vx + vy * vy);
     }
-    if (p.BC != -1)
-        for (int i = 0; i < N; i++) boundary_ic(x[i], y[i], phi[i], L, p.BC);
     return true;
 }
 
-// ---- observables of one swarm from its particle rows (Out_swarm, swarmdyn.cpp:237-344) -----------
-void dist_vec(const double *xi, const double *xj, int BC, double L, double *r) {  // mathtools.h:54-73
-    for (int d = 0; d < 2; d++) {
-        r[d] = xj[d] - xi[d];
-        if (!BC) {
-            const double s = (0.0 < r[d]) - (r[d] < 0.0);
-            r[d] = std::fmod(r[d] + s * L / 2, L) - s * L / 2;
-        }
-    }
-}
-
-double hull_area(std::vector<std::pair<double, double>> pts) {  // AreaConvexHull, agents_operation.cpp:130-150
-    std::sort(pts.begin(), pts.end());
-    pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
-    const int n = (int)pts.size();
-    if (n < 3) return 0;
-    std::vector<std::pair<double, double>> h(2 * n);
-    auto cross = [](const std::pair<double, double> &o, const std::pair<double, double> &a, const std::pair<double, double> &b) {
-        return (a.first - o.first) * (b.second - o.second) - (a.second - o.second) * (b.first - o.first);
-    };
-    int k = 0;
-    for (int i = 0; i < n; i++) { while (k >= 2 && cross(h[k - 2], h[k - 1], pts[i]) <= 0) k--; h[k++] = pts[i]; }
-    for (int i = n - 2, t = k + 1; i >= 0; i--) { while (k >= t && cross(h[k - 2], h[k - 1], pts[i]) <= 0) k--; h[k++] = pts[i]; }
-    double area = 0;
-    for (int i = 0; i + 1 < k; i++) area += h[i].first * h[i + 1].second - h[i + 1].first * h[i].second;
-    return 0.5 * area;
-}
-
-double elongation(const std::vector<double> &px, const std::vector<double> &py, const double *dir) {  // agents_operation.cpp:153-177
-    const double len = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1]);
-    const double c[2] = {dir[0] / len, dir[1] / len}, q[2] = {c[1], -c[0]};
-    double mn = std::numeric_limits<double>::max(), mx = std::numeric_limits<double>::lowest(), pmn = mn, pmx = mx;
-    for (size_t i = 0; i < px.size(); i++) {
-        const double d = px[i] * c[0] + py[i] * c[1], pd = px[i] * q[0] + py[i] * q[1];
-        mn = std::fmin(mn, d); mx = std::fmax(mx, d); pmn = std::fmin(pmn, pd); pmx = std::fmax(pmx, pd);
-    }
-    return std::fabs((mx - mn) / (pmx - pmn));
-}
-
-// rows: [N][7] of one replicate (dead rows are all zero and skipped via `alive`)
-std::vector<double> out_swarm(const double *rows, const uint8_t *alive, const HostParams &p) {
-    std::vector<double> px, py, vx, vy;
-    for (int i = 0; i < p.N; i++)
-        if (alive[i]) { px.push_back(rows[7 * i]); py.push_back(rows[7 * i + 1]); vx.push_back(rows[7 * i + 2]); vy.push_back(rows[7 * i + 3]); }
-    const int N = (int)px.size();
-    double avg_v[2] = {0, 0}, avg_u[2] = {0, 0}, avg_s = 0, avg_v2 = 0, avg_x[2] = {0, 0};
-    for (int i = 0; i < N; i++) {  // basic_particle_averages :486-510
-        const double v2 = vx[i] * vx[i] + vy[i] * vy[i], sp = std::sqrt(v2);
-        avg_v[0] += vx[i]; avg_v[1] += vy[i];
-        if (sp > 0) { avg_u[0] += vx[i] / sp; avg_u[1] += vy[i] / sp; }
-        avg_s += sp; avg_v2 += v2;
-    }
-    for (int d = 0; d < 2; d++) { avg_v[d] /= N; avg_u[d] /= N; }
-    avg_s /= N; avg_v2 /= N;
-    double IID = 0, NND = 0, max_IID = 0, max_vec[2] = {1, 1}, hd = 0;
-    for (int i = 0; i < N; i++) {
-        avg_x[0] += px[i]; avg_x[1] += py[i];
-        hd = p.N * p.alg_range;                     // :273, "arbitrary large value"
-        const double xi[2] = {px[i], py[i]};
-        double r[2];
-        for (int j = 0; j < i - 1; j++) {           // :275 (skips neighbour i-1, reproduced)
-            const double xj[2] = {px[j], py[j]};
-            dist_vec(xi, xj, p.BC, p.sizeL, r);
-            hd = std::fmin(hd, std::sqrt(r[0] * r[0] + r[1] * r[1]));
-        }
-        for (int j = i + 1; j < N; j++) {           // :280-289
-            const double xj[2] = {px[j], py[j]};
-            dist_vec(xi, xj, p.BC, p.sizeL, r);
-            const double d = std::sqrt(r[0] * r[0] + r[1] * r[1]);
-            hd = std::fmin(hd, d);
-            IID += d;
-            if (d > max_IID) { max_IID = d; max_vec[0] = r[0]; max_vec[1] = r[1]; }
-        }
-        NND += hd;
-    }
-    avg_x[0] /= N; avg_x[1] /= N;
-    NND /= N;
-    IID /= (double)(N - 1) * N;
-    const double ND = std::numeric_limits<double>::quiet_NaN();  // :270 0/0 for every row that did not start a burst
-    const double avgvel = std::sqrt(avg_v[0] * avg_v[0] + avg_v[1] * avg_v[1]);
-    const double pol = std::sqrt(avg_u[0] * avg_u[0] + avg_u[1] * avg_u[1]);
-    double L_norm = 0;
-    for (int i = 0; i < N; i++) {  // :301-306
-        const double hx = px[i] - avg_x[0], hy = py[i] - avg_x[1];
-        L_norm += (hx * vy[i] - hy * vx[i]) / std::sqrt(hx * hx + hy * hy);
-    }
-    L_norm = std::fabs(L_norm) / N;
-    std::vector<std::pair<double, double>> pts(N);
-    for (int i = 0; i < N; i++) pts[i] = {px[i], py[i]};
-    const double area = hull_area(pts);
-    const double elong = elongation(px, py, avg_u), aspect = elongation(px, py, max_vec);
-    double a1 = (avg_v[0] * max_vec[0] + avg_v[1] * max_vec[1]) / (avgvel * std::sqrt(max_vec[0] * max_vec[0] + max_vec[1] * max_vec[1]));
-    const double a2 = std::acos(-a1);
-    a1 = std::acos(a1);
-    return {(double)N, pol, L_norm, avg_x[0], avg_x[1], avg_v[0], avg_v[1], avg_s, avg_v2, elong, aspect,
-            std::fmin(a1, a2), area, NND, IID, ND};
-}
-
-std::vector<double> out_swarm_fishnet(const double *rows, const uint8_t *alive, const double *preds,
-                                      const HostParams &p, int n_dead) {  // swarmdyn.cpp:358-410
-    int n_front_close = 0, n_front = 0;
-    double r[2];
-    std::vector<int> ids;
-    for (int i = 0; i < p.N; i++) if (alive[i]) ids.push_back(i);
-    if (p.Npred > 1) {
-        const double sp = std::sqrt(preds[2] * preds[2] + preds[3] * preds[3]);
-        const double mv[2] = {sp > 0 ? preds[2] / sp : 0, sp > 0 ? preds[3] / sp : 0};
-        double vnet[2];
-        dist_vec(preds, preds + 6, p.BC, p.sizeL, vnet);
-        const double net_len = (p.Npred - 1) * std::sqrt(vnet[0] * vnet[0] + vnet[1] * vnet[1]);
-        for (int i : ids) {
-            dist_vec(preds, rows + 7 * i, p.BC, p.sizeL, r);
-            const double front = mv[0] * r[0] + mv[1] * r[1], side = vnet[0] * r[0] + vnet[1] * r[1];
-            if (side > 0 && side <= net_len) { n_front++; if (front > 0 && front < p.kill_range) n_front_close++; }
-        }
-    }
-    double dist_net = 0;
-    for (int i : ids) {
-        double dmin = p.sizeL * 2;
-        for (int j = 0; j < p.Npred; j++) {
-            dist_vec(preds + 6 * j, rows + 7 * i, p.BC, p.sizeL, r);
-            dmin = std::fmin(dmin, std::sqrt(r[0] * r[0] + r[1] * r[1]));
-        }
-        dist_net += dmin;
-    }
-    dist_net /= ids.size();
-    return {(double)n_front_close, dist_net, (double)n_front, (double)n_dead};
-}
-
+// ---- output (the observables themselves come from the library: sbc_out_swarm / sbc_out_swarm_fishnet) ----
 void write_rows(const std::string &file, const std::vector<std::vector<double>> &data) {  // WriteVector2d :322-339
     if (data.empty()) return;
     std::ofstream out(file.c_str(), std::ios_base::trunc);
@@ -473,24 +244,25 @@ int main(int argc, char **argv) {
         fprintf(stderr, "swarmdyn: sbc_create failed (%d): %s\n", rc, sbc_last_error(nullptr));
         return 2;
     }
-    // initial conditions (InitSystem + ResetSystem, swarmdyn.cpp:47-51), one stream per replicate
-    std::vector<double> X((size_t)R * N), Y((size_t)R * N), PHI((size_t)R * N), VP((size_t)R * N);
-    for (int r = 0; r < R; r++) {
-        Rng rng(p.seed + 0x9E3779B97F4A7C15ull * (uint64_t)(r + 1));
-        std::vector<double> x, y, phi, vp;
-        if (!reset_system(p, rng, x, y, phi, vp)) { sbc_destroy(h); return 1; }
-        std::copy(x.begin(), x.end(), X.begin() + (size_t)r * N);
-        std::copy(y.begin(), y.end(), Y.begin() + (size_t)r * N);
-        std::copy(phi.begin(), phi.end(), PHI.begin() + (size_t)r * N);
-        std::copy(vp.begin(), vp.end(), VP.begin() + (size_t)r * N);
+    // initial conditions (InitSystem + ResetSystem, swarmdyn.cpp:47-51): on the device for every replicate at once
+    if (p.IC != 99) {
+        SBC_CHECK(sbc_init_state(h, p.IC));
+    } else {
+        std::vector<double> x, y, phi, vp, X, Y, PHI, VP;
+        if (!load_init_coord(p, x, y, phi, vp)) { sbc_destroy(h); return 1; }
+        for (int r = 0; r < R; r++) {   // every replicate starts from the file's state
+            X.insert(X.end(), x.begin(), x.end()); Y.insert(Y.end(), y.begin(), y.end());
+            PHI.insert(PHI.end(), phi.begin(), phi.end()); VP.insert(VP.end(), vp.begin(), vp.end());
+        }
+        SBC_CHECK(sbc_set_state(h, X.data(), Y.data(), nullptr, nullptr, PHI.data(), VP.data(), nullptr, nullptr,
+                                nullptr, nullptr, nullptr));
     }
-    SBC_CHECK(sbc_set_state(h, X.data(), Y.data(), nullptr, nullptr, PHI.data(), VP.data(), nullptr, nullptr,
-                            nullptr, nullptr, nullptr));
     std::cout << "Go";  // swarmdyn.cpp:61
 
     auto suffix = [&](int r) { return r == 0 ? p.fileID : p.fileID + "_" + std::to_string(r); };
     std::vector<double> part((size_t)R * N * 7), preds((size_t)R * std::max(p.Npred, 1) * 6);
     std::vector<uint8_t> alive((size_t)R * N);
+    std::vector<double> obs16((size_t)R * 16), obs4((size_t)R * 4);
     std::vector<int32_t> n_alive(R), n_dead(R);
     std::vector<std::vector<std::vector<double>>> swarm_rows(R), net_rows(R);
     // -J 1: /part and /pred are collected in memory and written once at the end
@@ -514,16 +286,22 @@ int main(int argc, char **argv) {
         SBC_CHECK(sbc_get_counts(h, n_alive.data(), n_dead.data()));
         const bool all_dead = std::all_of(n_alive.begin(), n_alive.end(), [](int v) { return v == 0; });
         if (is_out || all_dead) {
-            SBC_CHECK(sbc_get_particles(h, part.data(), alive.data()));
-            if (p.Npred > 0) SBC_CHECK(sbc_get_predators(h, preds.data()));
             const bool pred_phase = (s_out >= p.pred_time / p.dt);
+            if (p.out_particle || all_dead) SBC_CHECK(sbc_get_particles(h, part.data(), alive.data()));
+            if (p.Npred > 0 && p.out_particle) SBC_CHECK(sbc_get_predators(h, preds.data()));
+            if (p.out_mean) {   // Out_swarm / Out_swarm_fishNet (swarmdyn.cpp:237-344, :358-410) on the device, every replicate at once
+                SBC_CHECK(sbc_out_swarm(h, 0, obs16.data(), nullptr));
+                if (pred_phase && p.Npred > 0) SBC_CHECK(sbc_out_swarm_fishnet(h, obs4.data()));
+            }
             for (int r = 0; r < R; r++) {
                 const double *rows = part.data() + (size_t)r * N * 7;
                 const uint8_t *al = alive.data() + (size_t)r * N;
                 if (p.out_mean) {
-                    swarm_rows[r].push_back(out_swarm(rows, al, p));
-                    if (pred_phase)
-                        net_rows[r].push_back(out_swarm_fishnet(rows, al, preds.data() + (size_t)r * p.Npred * 6, p, n_dead[r]));
+                    swarm_rows[r].push_back(std::vector<double>(obs16.begin() + (size_t)r * 16, obs16.begin() + (size_t)(r + 1) * 16));
+                    if (pred_phase) {
+                        if (p.Npred > 0) net_rows[r].push_back(std::vector<double>(obs4.begin() + (size_t)r * 4, obs4.begin() + (size_t)(r + 1) * 4));
+                        else net_rows[r].push_back({0.0, std::numeric_limits<double>::quiet_NaN(), 0.0, (double)n_dead[r]});
+                    }
                 }
                 if (p.out_particle && !p.out_h5) {
                     append_particles(p.location + "part_" + suffix(r) + ".dat", rows, al, N, 7);

@@ -44,7 +44,10 @@ ABI = [
     ('sbc_set_predators', ctypes.c_int, [_vp, _dp, _dp, _dp, ctypes.c_int]),
     ('sbc_get_counts', ctypes.c_int, [_vp, _i32p, _i32p]),
     ('sbc_step', ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64]),
+    ('sbc_init_state', ctypes.c_int, [_vp, ctypes.c_int]),
     ('sbc_observables', ctypes.c_int, [_vp, _dp]),
+    ('sbc_out_swarm', ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp]),
+    ('sbc_out_swarm_fishnet', ctypes.c_int, [_vp, _dp]),
     ('sbc_pair_interactions', ctypes.c_int, [_vp, ctypes.c_int, _i32p, _i32p, _i32p, _dp, _dp, _dp,
                                              _i64p, _i32p, ctypes.c_int64]),
     ('sbc_inject_decisions', ctypes.c_int, [_vp, _dp, _dp, _u32p]),
@@ -238,6 +241,25 @@ class Swarm:
     def observables(self):
         out = np.zeros((self.R, 8))
         self._check(self.lib.sbc_observables(self.h, _ptr(out, _dp)))
+        return out
+
+    def init_state(self, ic):
+        """Initial condition `ic` of the reference's ResetSystem (settings.cpp:196-387) generated on the device for
+        every replicate (Philox protocol; IC 99 is a file and stays on the host)."""
+        self._check(self.lib.sbc_init_state(self.h, int(ic)))
+
+    def out_swarm(self, no_pairs=False, want_extra=False):
+        """The reference's /swarm row of every replicate (Out_swarm, swarmdyn.cpp:237-344), computed on the device.
+        Returns out[R][16], or (out, extra[R][4]) - see include/sbc.h for the columns."""
+        out = np.zeros((self.R, 16))
+        extra = np.zeros((self.R, 4)) if want_extra else None
+        self._check(self.lib.sbc_out_swarm(self.h, 1 if no_pairs else 0, _ptr(out, _dp), _ptr(extra, _dp)))
+        return (out, extra) if want_extra else out
+
+    def out_swarm_fishnet(self):
+        """The /swarm_fishNet row of every replicate (Out_swarm_fishNet, swarmdyn.cpp:358-410): out[R][4]."""
+        out = np.zeros((self.R, 4))
+        self._check(self.lib.sbc_out_swarm_fishnet(self.h, _ptr(out, _dp)))
         return out
 
     # ---- test hooks -------------------------------------------------------------------------

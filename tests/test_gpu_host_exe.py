@@ -154,3 +154,28 @@ def test_h5_output_matches_text_output(tmp_path):
     _run(dict(d, out_h5=1, fileID='run3'), c, ['-Z', '9'])
     g = h5mini_read.File(str(c / 'out_run3.h5'))
     assert list(g.links()) == ['run3'] and np.array_equal(g.read('/run3/part'), part)
+
+
+def test_python_batch_helper_and_executable_write_the_same_rows(tmp_path):
+    """run_ensemble (sde_burst_coast_b200/ensemble.py) and `swarmdyn -y R -Z seed` drive the same library calls -
+    device initial conditions, step schedule, device observables - so their /swarm rows agree to the six significant
+    digits of the text files, replicate by replicate; a shard of the ensemble reproduces its replicates bit for bit."""
+    from sde_burst_coast_b200.ensemble import run_ensemble
+    d = P.get_base_params(0.6, 1.2, mode='natPred')
+    P.selection_line_parameter(d, 2)
+    d.update(out_h5=0, output_mode=1, N=30, pred_speed0=20, kill_rate=50, N_confu=40, IC=3)
+    R, seed = 5, 2024
+    _run(d, tmp_path, ['-Z', str(seed), '-y', str(R)])
+    res = run_ensemble(d, R, seed=seed, want_particles=True)
+    assert res['swarm'].shape[1:] == (R, 16) and res['swarm_fishNet'].shape[2] == 4
+    for r in range(R):
+        suffix = 'xx' if r == 0 else 'xx_%d' % r
+        sw = _rows(tmp_path / ('swarm_%s.dat' % suffix))
+        assert sw.shape == res['swarm'][:, r].shape
+        mine = res['swarm'][:, r]
+        ok = np.isclose(sw, mine, rtol=2e-5, atol=1e-9) | (np.isnan(sw) & np.isnan(mine))
+        assert ok.all(), (r, np.argwhere(~ok)[:5])
+        net = _rows(tmp_path / ('swarm_fishNet_%s.dat' % suffix))
+        assert np.allclose(net, res['swarm_fishNet'][:, r], rtol=2e-5, atol=1e-9)
+    shard = run_ensemble(d, 2, seed=seed, replicate_offset=3)
+    assert np.array_equal(shard['swarm'], res['swarm'][:, 3:5], equal_nan=True)

@@ -139,3 +139,58 @@ def test_observables_match_reference_out_swarm():
     p = pyorc.World(sp, N, kind='port')
     p.set_state(**st)
     assert np.array_equal(p.observables(), mine)
+
+
+@needs_ref
+@pytest.mark.parametrize('mode,N,over', [('burst_coast', 30, {}), ('natPred', 200, dict(BC=0, size=100.0, Npred=0))])
+def test_port_out_swarm_is_the_reference_row(mode, N, over):
+    """orc_out_swarm of the port (all 16 columns, quirks of swarmdyn.cpp:270-296 included) against the reference's own
+    Out_swarm on the same state, with and without dead agents: bit-identical."""
+    sp, _, _ = make_params(mode, N, **over)
+    rng = np.random.default_rng(N)
+    st = random_state(N, sp, rng)
+    for alive in (None, (rng.random(N) > 0.25).astype(np.uint8)):
+        p, w = pyorc.World(sp, N), pyorc.World(sp, N, kind='reference')
+        for o in (p, w):
+            o.set_state(alive=alive, **st) if alive is not None else o.set_state(**st)
+        assert np.array_equal(p.out_swarm(), w.ref_out_swarm(), equal_nan=True)
+
+
+@needs_ref
+@pytest.mark.parametrize('npred', [1, 20])
+def test_port_fishnet_row_is_the_reference_row(npred):
+    N = 150
+    sp, _, _ = make_params('mulFisher' if npred > 1 else 'natPred', N, BC=0, size=100.0, Npred=npred, pred_time=0.0)
+    rng = np.random.default_rng(npred)
+    st = random_state(N, sp, rng, spread=40.0)
+    alive = (rng.random(N) > 0.1).astype(np.uint8)
+    px = 40.0 + 0.5 * np.arange(npred, dtype=np.float64)
+    p, w = pyorc.World(sp, N, npred), pyorc.World(sp, N, npred, kind='reference')
+    for o in (p, w):
+        o.set_state(alive=alive, **st)
+        o.set_predators(px, np.full(npred, 48.0), np.full(npred, np.pi / 2), 1)
+    assert np.array_equal(p.out_swarm_fishnet(), w.out_swarm_fishnet())
+
+
+@needs_ref
+@pytest.mark.parametrize('ic', [0, 1, 2, 3, 4, 5, 7])
+@pytest.mark.parametrize('mode,N,over', [('burst_coast', 8, {}), ('burst_coast', 40, {}), ('natPred', 50, dict(BC=0, size=45.0, Npred=0)),
+                                         ('burst_coast', 30, dict(BC=2, size=20.0)), ('burst_coast', 30, dict(BC=1, size=20.0)),
+                                         ('burst_coast', 30, dict(BC=4, size=20.0)), ('burst_coast', 30, dict(BC=5, size=20.0)),
+                                         ('burst_coast', 30, dict(BC=-1))])
+def test_port_initial_conditions_are_the_reference_reset_system(ic, mode, N, over):
+    """orc_init_state of the port against the reference's own ResetSystem + Boundary (settings.cpp:196-387) fed with
+    the same uniforms through the replay queue: every field bit-identical. The ring cases (IC 3-5) shuffle with a clock
+    seed in the reference, so WHICH agent holds a ring place differs: rows are compared as a sorted set."""
+    sp, _, _ = make_params(mode, N, **over)
+    a, b = pyorc.World(sp, N, seed=77, replicate=3), pyorc.World(sp, N, seed=77, replicate=3, kind='reference')
+    a.init_state(ic)
+    b.init_state(ic)
+    sa, sb = a.get_state(), b.get_state()
+    ka = kb = np.arange(N)
+    if ic in (3, 4, 5):
+        ka, kb = (np.lexsort((q['vy'], q['vx'], q['phi'], q['y'], q['x'])) for q in (sa, sb))   # walls clamp several agents onto one point
+    for f in ('x', 'y', 'vx', 'vy', 'phi', 'vproj', 'fx', 'fy', 'bin_step', 'steps_till_burst', 'alive'):
+        _same(sa[f][ka], sb[f][kb], (ic, f))
+    if ic in (3, 4, 5) and over.get('BC') == -1:     # the protocol's shuffle is a bijection: every agent was placed exactly once
+        assert len(set(zip(sa['x'], sa['y']))) == N
