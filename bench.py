@@ -668,8 +668,11 @@ def domain_swarm_leg(rank, world, device, agents_per_gpu, steps=200, warmup=40):
     """The only multi-GPU path that communicates: ONE periodic swarm cut into x-slabs, one rank per GPU, halo /
     migration records stored straight into the neighbours' device memory (CUDA IPC over NVLink, sbc_domain_step).
       (1) parity: a 120,000-agent swarm stepped 130 times decomposed over all ranks vs undecomposed on rank 0 -
-          burst timers bit for bit, positions to FP32 summation order (the body of tests/multi_gpu_worker.py);
-      (2) weak scaling of config C5: agents_per_gpu agents per GPU (L grows with the GPU count, rho = 0.01)."""
+          burst timers bit for bit, positions to FP32 summation order (the body of tests/multi_gpu_worker.py) - without
+          predator, and with ONE chasing predator (kill rule 3: the closest prey, the sensed-prey count and the centre of
+          mass at spawn are all-gathered through the inboxes): the same agents die, the replicated predator is identical;
+      (2) weak scaling of config C5: agents_per_gpu agents per GPU (L grows with the GPU count, rho = 0.01), and the
+          same with the chasing predator (BASELINE config C5 "plus a variant with one chasing predator")."""
     import torch
     import torch.distributed as dist
     from helpers import base_dict, f32
@@ -678,84 +681,105 @@ def domain_swarm_leg(rank, world, device, agents_per_gpu, steps=200, warmup=40):
     from sde_burst_coast_b200.swarm import Swarm
     ts = torch.cuda.Stream()
     torch.cuda.set_stream(ts)
-    res = {}
-    # ---- (1) parity ----------------------------------------------------------------------------------------------
-    N, L, K = 120000, 3400.0, 130
-    sp, _ = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, Npred=0), path=PP.PATH_CELLLIST)
-    rng = np.random.default_rng(99)
-    st = dict(x=f32(L * rng.random(N)), y=f32(L * rng.random(N)), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=4.0 * np.ones(N))
-    slab = SlabSwarm(sp, N, rank, world, seed=7, device=device, stream=ts.cuda_stream)
-    slab.scatter_initial(st)
-    tr = PeerTransport(slab)
-    step_distributed(slab, tr, 0, 40)
-    step_distributed(slab, tr, 40, K - 40)
-    torch.cuda.synchronize()
-    gid, own = slab.owned_state()
-    cnt = slab.counts()
-    gathered = [None] * world
-    dist.gather_object((gid, {k: own[k] for k in ('x', 'y', 'bin_step', 'steps_till_burst')}, cnt), gathered if rank == 0 else None, dst=0)
-    slab.close()
-    if rank == 0:
-        whole = Swarm(sp, N, seed=7, device=device)
-        whole.set_state(**st)
-        whole.step(0, K)
-        ws = whole.get_state()
-        whole.close()
-        seen = np.zeros(N, dtype=np.int32)
-        got = {k: np.zeros(N, dtype=v.dtype) for k, v in gathered[0][1].items()}
-        for g_, o_, _c in gathered:
-            seen[g_] += 1
-            for k, v in o_.items():
-                got[k][g_] = v
-        dx = np.abs(((got['x'] - ws['x'] + L / 2) % L) - L / 2)
-        dy = np.abs(((got['y'] - ws['y'] + L / 2) % L) - L / 2)
-        checks = {'every_agent_owned_once': bool(np.all(seen == 1)),
-                  'steps_till_burst_bit_exact': bool(np.array_equal(got['steps_till_burst'], ws['steps_till_burst'])),
-                  'bin_step_bit_exact': bool(np.array_equal(got['bin_step'], ws['bin_step'])),
-                  'positions_within_1e-3': float(((dx < 1e-3) & (dy < 1e-3)).mean()),
-                  'overflow_events': int(sum(c_['overflow_events'] for _, _, c_ in gathered))}
-        ok = (checks['every_agent_owned_once'] and checks['steps_till_burst_bit_exact'] and checks['bin_step_bit_exact'] and
-              checks['positions_within_1e-3'] > 0.995 and checks['overflow_events'] == 0)
-        res['parity'] = 'ok' if ok else 'FAIL'
-        res['parity_detail'] = dict(checks, n_agents=N, steps=K, against='undecomposed swarm on rank 0 (same seed, global agent ids)')
-    dist.barrier()
-    # ---- (2) C5, weak scaling -------------------------------------------------------------------------------------
-    N = int(agents_per_gpu) * world
-    L = float(np.sqrt(N / C5_RHO))
-    sp, _ = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, Npred=0), path=PP.PATH_CELLLIST)
-    slab = SlabSwarm(sp, N, rank, world, seed=SEED, device=device, stream=ts.cuda_stream)
-    slab.scatter_initial(c5_state(N, L))
-    tr = PeerTransport(slab)
-    step_distributed(slab, tr, 0, warmup)        # includes the synchronised first burst at s = 1
-    dist.barrier()
-    torch.cuda.synchronize()
-    s0 = slab.swarm.stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ts)
-    step_distributed(slab, tr, warmup, steps)
-    e1.record(ts)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    s1 = slab.swarm.stats()
-    c = slab.counts()
-    t = torch.tensor([ms, float(s1['pairs'] - s0['pairs']), float(c['owned']), float(c['ghosts']), float(c['overflow_events']),
-                      float(s1['cell_builds'] - s0['cell_builds'])], dtype=torch.float64, device='cuda')
-    allv = [torch.zeros_like(t) for _ in range(world)]
-    dist.all_gather(allv, t)
-    slab.close()
-    torch.cuda.set_stream(torch.cuda.default_stream())
-    if rank != 0:
-        return None
-    ms_max = max(float(v[0]) for v in allv)
-    res.update({'workload': 'C5 single periodic swarm decomposed into x-slabs, peer-memory halo exchange (no NCCL in the step loop)',
-                'scaling': 'weak', 'n_gpus': world, 'n_agents': N, 'agents_per_gpu': int(agents_per_gpu), 'box': L, 'steps': steps,
-                'value': N * steps / (ms_max * 1e-3), 'unit': 'agent-steps/s', 'us_per_step': 1e3 * ms_max / steps,
-                'us_per_step_per_rank': [1e3 * float(v[0]) / steps for v in allv],
+    chase = dict(Npred=1, pred_kill=3, pred_move=1, pred_time=0.02, time=50.0, pred_speed0=40.0, kill_rate=400.0, N_confu=500)
+
+    def parity(pred):
+        N, L, K = 120000, 3400.0, 130
+        sp, npred = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, **(chase if pred else dict(Npred=0))), path=PP.PATH_CELLLIST)
+        rng = np.random.default_rng(99)
+        st = dict(x=f32(L * rng.random(N)), y=f32(L * rng.random(N)), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=4.0 * np.ones(N))
+        slab = SlabSwarm(sp, N, rank, world, seed=7, device=device, stream=ts.cuda_stream, n_pred=npred)
+        slab.scatter_initial(st)
+        tr = PeerTransport(slab)
+        step_distributed(slab, tr, 0, 40)
+        step_distributed(slab, tr, 40, K - 40)
+        torch.cuda.synchronize()
+        gid, own = slab.owned_state()
+        cnt = slab.counts()
+        gathered = [None] * world
+        dist.gather_object((gid, {k: own[k] for k in ('x', 'y', 'bin_step', 'steps_till_burst')}, cnt, slab.swarm.get_predators()),
+                           gathered if rank == 0 else None, dst=0)
+        slab.close()
+        out = None
+        if rank == 0:
+            whole = Swarm(sp, N, npred, seed=7, device=device)
+            whole.set_state(**st)
+            whole.step(0, K)
+            ws, wp = whole.get_state(), whole.get_predators()
+            whole.close()
+            seen = np.zeros(N, dtype=np.int32)
+            got = {k: np.zeros(N, dtype=v.dtype) for k, v in gathered[0][1].items()}
+            for g_, o_, _c, _p in gathered:
+                seen[g_] += 1
+                for k, v in o_.items():
+                    got[k][g_] = v
+            al = ws['alive'] == 1
+            dx = np.abs(((got['x'] - ws['x'] + L / 2) % L) - L / 2)[al]
+            dy = np.abs(((got['y'] - ws['y'] + L / 2) % L) - L / 2)[al]
+            checks = {'every_living_agent_owned_once': bool(np.array_equal(seen == 1, al) and seen.max() <= 1),
+                      'steps_till_burst_bit_exact': bool(np.array_equal(got['steps_till_burst'][al], ws['steps_till_burst'][al])),
+                      'bin_step_bit_exact': bool(np.array_equal(got['bin_step'][al], ws['bin_step'][al])),
+                      'positions_within_1e-3': float(((dx < 1e-3) & (dy < 1e-3)).mean()),
+                      'overflow_events': int(sum(c_['overflow_events'] for _, _, c_, _ in gathered))}
+            ok = (checks['every_living_agent_owned_once'] and checks['steps_till_burst_bit_exact'] and checks['bin_step_bit_exact'] and
+                  checks['positions_within_1e-3'] > 0.995 and checks['overflow_events'] == 0)
+            if pred:
+                checks['agents_killed'] = int((~al).sum())
+                checks['predator_identical_on_all_ranks'] = bool(all(np.array_equal(p_, gathered[0][3]) for _, _, _, p_ in gathered))
+                checks['predator_within_2e-3_of_undecomposed'] = bool(np.allclose(gathered[0][3][..., :2], wp[..., :2], atol=2e-3))
+                ok = ok and checks['agents_killed'] > 0 and checks['predator_identical_on_all_ranks'] and checks['predator_within_2e-3_of_undecomposed']
+            out = ('ok' if ok else 'FAIL', dict(checks, n_agents=N, steps=K, against='undecomposed swarm on rank 0 (same seed, global agent ids)'))
+        dist.barrier()
+        return out
+
+    def weak(pred):
+        N = int(agents_per_gpu) * world
+        L = float(np.sqrt(N / C5_RHO))
+        sp, npred = PP.make_sbc_params(base_dict('natPred', N, BC=0, size=L, **(chase if pred else dict(Npred=0))), path=PP.PATH_CELLLIST)
+        slab = SlabSwarm(sp, N, rank, world, seed=SEED, device=device, stream=ts.cuda_stream, n_pred=npred)
+        slab.scatter_initial(c5_state(N, L))
+        tr = PeerTransport(slab)
+        step_distributed(slab, tr, 0, warmup)        # includes the synchronised first burst at s = 1 (and the predator's spawn at s = 20)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0 = slab.swarm.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ts)
+        step_distributed(slab, tr, warmup, steps)
+        e1.record(ts)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        s1 = slab.swarm.stats()
+        c = slab.counts()
+        t = torch.tensor([ms, float(s1['pairs'] - s0['pairs']), float(c['owned']), float(c['ghosts']), float(c['overflow_events']),
+                          float(s1['cell_builds'] - s0['cell_builds'])], dtype=torch.float64, device='cuda')
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        slab.close()
+        ms_max = max(float(v[0]) for v in allv)
+        return {'n_agents': N, 'box': L, 'steps': steps, 'value': N * steps / (ms_max * 1e-3), 'unit': 'agent-steps/s',
+                'us_per_step': 1e3 * ms_max / steps, 'us_per_step_per_rank': [1e3 * float(v[0]) / steps for v in allv],
                 'pair_candidates_per_sec': sum(float(v[1]) for v in allv) / (ms_max * 1e-3),
                 'owned_per_rank': [int(v[2]) for v in allv], 'ghosts_per_rank': [int(v[3]) for v in allv],
                 'overflow_events': int(sum(float(v[4]) for v in allv)), 'full_exchanges': int(allv[0][5]),
-                'launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'other_launches')) / steps})
+                'launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'other_launches')) / steps}
+
+    res = {}
+    p0, p1 = parity(False), parity(True)
+    w0 = weak(False)
+    w1 = weak(True)
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    if rank != 0:
+        return None
+    res['parity'] = 'ok' if (p0[0] == 'ok' and p1[0] == 'ok') else 'FAIL'
+    res['parity_detail'] = p0[1]
+    res['parity_detail_with_predator'] = p1[1]
+    res.update({'workload': 'C5 single periodic swarm decomposed into x-slabs, peer-memory halo exchange (no NCCL in the step loop)',
+                'scaling': 'weak', 'n_gpus': world, 'agents_per_gpu': int(agents_per_gpu)})
+    res.update(w0)
+    res['with_chasing_predator'] = dict(w1, note='one predator replicated on every rank (natPred, chase, kill rule 3): per step an all-gather of '
+                                                 'the ranks\' closest prey and one of (sensed prey, weight sum), 64 bytes per rank each, through the inboxes')
     return res
 
 

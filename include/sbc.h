@@ -251,6 +251,12 @@ int sbc_domain_rebuild_period(sbc_handle *h, int period);
 int sbc_domain_inbox(sbc_handle *h, void **base_dev, size_t *bytes, void *ipc_handle_64 /* or NULL */);
 int sbc_domain_open_peer(sbc_handle *h, const void *ipc_handle_64, void **mapped_dev);
 int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inbox_dev);
+/* Predators of a decomposed swarm (n_pred >= 1 at sbc_create): the predator is replicated on every rank; the closest prey
+ * of the chase, the sensed-prey count / weight sum of PredKill and the centre of mass at spawn are all-gathered as one
+ * 64-byte record per rank through a predator area inside every inbox, so each handle needs the inbox of EVERY rank
+ * (device pointers in rank order, entry [rank] = its own; world <= 16). Replaces the reference's serial loops
+ * agents_dynamics.cpp:580-597, :861-877 and agents_operation.cpp:23-127 for a swarm cut over GPUs. */
+int sbc_domain_attach_world(sbc_handle *h, void *const *inboxes_dev, int n);
 int sbc_domain_post(sbc_handle *h);
 int sbc_domain_complete(sbc_handle *h);
 int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps);

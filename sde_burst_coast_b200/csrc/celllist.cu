@@ -700,3 +700,11 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
     }
 #undef SBC_CELLS_ARGS
 }
+// (see sbc_pred_preload, predator.cu: nothing may load lazily once all-gathers wait inside kernels)
+void sbc_cells_preload(void) {
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, pair_cells_warp_kernel<true>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, true>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, false>);
+    cudaFuncGetAttributes(&fa, pair_cells_kernel<true>);
+}

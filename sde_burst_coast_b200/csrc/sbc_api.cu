@@ -45,6 +45,7 @@ struct sbc_handle {
     bool dom_last_full;            // kind of the exchange in flight (pack -> unpack)
     // multi-kernel path bookkeeping
     bool list_valid;               // S.active_list[list_step % 3] holds the rows (bin_step == burst_steps) of step list_step
+    bool list_split;               // ... and S.edge_list[list_step % 3] those next to a slab edge (decomposed swarm)
     int64_t list_step;
     bool nxt_synced;               // S.pv_nxt carries the dead / free marks of S.pv (needed before a step writes into it)
     bool cs_valid;                 // S.cs == (cos, sin)(phi): true after set_state / ensemble launches, false after multi-kernel steps
@@ -62,6 +63,11 @@ struct sbc_handle {
     std::vector<void *> ipc_opened;
     unsigned char *send_own[2];            // this rank's send buffers (left, right)
     int dom_epoch;
+    // predators of a decomposed swarm (predator.cu): every rank's predator area, this rank's closest-prey key and candidates
+    PredBox pbox;
+    bool pbox_ready;
+    unsigned long long *pred_key;
+    int *pred_cand;
     // CUDA graphs of one multi-kernel step, keyed by MK_* bits | position-buffer parity
     std::map<unsigned, cudaGraphExec_t> graphs;
     uint32_t *step_dev;
@@ -384,7 +390,7 @@ int sbc_destroy(sbc_handle *h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
-    cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
+    cudaFree(h->pred_key); cudaFree(h->pred_cand); cudaFree(h->inbox); cudaFree(h->send_own[0]); cudaFree(h->send_own[1]);
     cudaFree(h->S.gid);
     cudaFree(h->step_dev);
     cudaFree(h->trace_dev);
@@ -724,7 +730,7 @@ int sbc_get_counts(sbc_handle *h, int32_t *n_alive, int32_t *n_dead) {
 // predator move + kill behind, and in a decomposed swarm the receipt of the neighbours' records in front of the rows
 // kernel and the dispatch of this rank's records at the end. Replayed from a CUDA graph whose two branches run side
 // by side; the graph bakes pointers, so there is one per combination of the MK_* bits and the position-buffer parity.
-enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_XCHG = 8, MK_PUSH = 16 };
+enum { MK_PARITY = 1, MK_REBUILD = 2, MK_PRED = 4, MK_XCHG = 8, MK_PUSH = 16, MK_SERIAL = 32 };
 
 static void domain_launch_refresh_exchange(sbc_handle *h, const DevState &S, const uint32_t *step_dev, uint32_t step_off,
                                            cudaStream_t st);
@@ -739,6 +745,7 @@ static int ensure_rows(sbc_handle *h, int64_t s) {
     h->host_stats[7] += 1;
     h->list_valid = true;
     h->list_step = s;
+    h->list_split = false;   // one list: the rows next to a slab edge are not apart
     return SBC_OK;
 }
 
@@ -755,8 +762,12 @@ static void record_step(sbc_handle *h, const DevState &S, unsigned key, const St
         cudaStreamWaitEvent(aux, h->ev_fork, 0);
         rows_st = aux;
         if (key & MK_XCHG) {
-            cudaStreamWaitEvent(aux2, h->ev_fork, 0);
-            x_st = aux2;
+            if (key & MK_SERIAL) {   // no row can wait for the ghosts inside the rows kernel: the exchange goes first
+                x_st = aux;
+            } else {
+                cudaStreamWaitEvent(aux2, h->ev_fork, 0);
+                x_st = aux2;
+            }
         }
     }
     if (key & MK_XCHG) domain_launch_refresh_exchange(h, S, A.step_dev, A.step, x_st);
@@ -768,7 +779,7 @@ static void record_step(sbc_handle *h, const DevState &S, unsigned key, const St
     if (aux) {
         cudaEventRecord(h->ev_join, aux);
         cudaStreamWaitEvent(main, h->ev_join, 0);
-        if (key & MK_XCHG) {
+        if ((key & MK_XCHG) && !(key & MK_SERIAL)) {
             cudaEventRecord(h->ev_join2, aux2);
             cudaStreamWaitEvent(main, h->ev_join2, 0);
         }
@@ -776,7 +787,14 @@ static void record_step(sbc_handle *h, const DevState &S, unsigned key, const St
     DevState Sn = S;   // what the host sees after the step: the new positions are the current ones
     std::swap(Sn.pv, Sn.pv_nxt);
     std::swap(Sn.tm, Sn.tm_nxt);
-    if (key & MK_PRED) sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
+    if (key & MK_PRED) {
+        if (h->dom.enabled) {   // replicated predator, all-gathers through the predator areas of the inboxes (predator.cu)
+            h->pbox.timeout_ns = h->dom.timeout_ns;
+            sbc_launch_domain_pred_move_kill(h->P, Sn, h->pbox, h->dom.own_cap, h->dom.ctl, h->pred_key, h->pred_cand, A, main);
+        } else {
+            sbc_launch_pred_move_kill(h->P, Sn, A.step, A.step_dev, main);
+        }
+    }
     // (the edge agents delivered their new positions themselves; the neighbours' flags are raised by the first block of
     // the receive kernel that heads the next step - or ends this call)
 }
@@ -789,13 +807,21 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
     if (h->use_cells) if (int rc = ensure_cells(h)) return rc;
     // cell order: rebuilt when stale (Verlet skin used up) and after a state change
     const bool rebuild = h->use_cells && (!h->cells_valid || h->cells_age > h->cells_max_age);
+    // slab with the peer-memory exchange: rows whose 3 x 3 cells can hold a ghost are listed apart (by the update that
+    // re-arms them) and swept by their own blocks of the lanes kernel, which wait inside the kernel for the exchange that
+    // runs beside the step. Other rows kernels (predator phase, crowded cells) sweep ONE list and cannot wait: a split
+    // list is merged again, and the exchange runs before the rows kernel instead of beside it.
+    const bool lanes_edge = h->dom.enabled && h->peer_l && h->use_cells && sbc_pair_cells_lanes(h->P, S, h->cells, pred_phase ? 1 : 0);
+    if (h->list_valid && h->list_step == s && h->list_split && !lanes_edge) h->list_valid = false;
     if (int rc = ensure_rows(h, s)) return rc;
+    const bool wait_in_rows = lanes_edge && xchg_first && h->list_split;
     if (!h->nxt_synced) {
         SBC_CUDA(cudaMemcpyAsync(S.pv_nxt, S.pv, (size_t)S.N * S.R * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
         h->nxt_synced = true;
     }
     const unsigned key = (h->pv_parity ? MK_PARITY : 0) | (rebuild ? MK_REBUILD : 0) | (pred_phase ? MK_PRED : 0) |
-                         (xchg_first ? MK_XCHG : 0) | (push ? MK_PUSH : 0) | ((unsigned)count << 8);
+                         (xchg_first ? MK_XCHG : 0) | (push ? MK_PUSH : 0) | ((xchg_first && !wait_in_rows) ? MK_SERIAL : 0) |
+                         ((unsigned)count << 8);
     StepArgs A = {};
     A.step = (uint32_t)s;
     A.n_update = n_update_of(h);
@@ -808,15 +834,13 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
         A.cell_ncx = h->cells.ncx;
         A.cell_inv_w = (float)((double)h->cells.ncx / (double)h->P.L);   // == CellGeom::inv_w (celllist.cu), bit for bit
     }
-    if (h->dom.enabled && h->peer_l && h->use_cells && sbc_pair_cells_lanes(h->P, S, h->cells, A.pred_active)) {
-        // slab with the peer-memory exchange: rows whose 3 x 3 cells can hold a ghost are listed apart and swept by
-        // their own blocks, which wait (inside the rows kernel) for the exchange that runs beside the step
+    if (lanes_edge) {
         const double inv_w = (double)h->cells.ncx / h->hp.sizeL;   // cell columns per unit length
         A.edge_lo = (int)std::floor((double)h->dom.x_lo * inv_w) + 1;
         A.edge_hi = (int)std::floor((double)h->dom.x_hi * inv_w) - 1;
         A.edge_blocks = 148;
         A.wait_ns = h->dom.timeout_ns;
-        if (xchg_first) A.ghost_ready = h->dom.ctl + 17;
+        if (wait_in_rows) A.ghost_ready = h->dom.ctl + 17;
     }
     if (push) {   // the exchange behind this step is a refresh: the agents in the edge bands deliver their new positions
         A.halo_idx = h->dom.halo_idx;
@@ -875,6 +899,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
         h->pv_parity ^= 1;
     }
     h->list_step = s + count;    // the steps' kernels appended the agents they re-armed
+    h->list_split = lanes_edge;  // ... next to a slab edge apart, if this step listed them so
     h->cs_valid = false;
     h->dense.sorted_valid = false;
     h->host_stats[0] += count;
@@ -899,9 +924,43 @@ static int mk_batch(const sbc_handle *h, int64_t want) {
     return room >= 4 ? 4 : 1;
 }
 
+// CreatePredator / CreateFishNet at step s (slot 0: first spawn, 1: the net's periodic re-creation)
+static void launch_spawn(sbc_handle *h, int64_t s, int slot) {
+    if (h->dom.enabled) {
+        h->pbox.timeout_ns = h->dom.timeout_ns;
+        sbc_launch_domain_pred_spawn(h->P, h->S, h->pbox, h->dom.own_cap, h->dom.ctl, s, slot, h->stream);
+    } else {
+        sbc_launch_pred_spawn(h->P, h->S, s, slot, h->stream);
+    }
+}
+
+// predator schedule in step indices (swarmdyn.cpp:153-170): is step s in the predator phase, does it (re)create one?
+struct PredSchedule {
+    bool active = false;
+    double x = 0;      // pred_time / dt
+    int needed = 0;    // steps between two re-creations of a fish net
+    bool phase(int64_t s) const { return active && (double)s >= x; }
+    bool spawn0(int64_t s) const { return phase(s) && (double)(s - 1) < x; }
+    bool spawn1(int64_t s, int npred) const { return npred > 1 && phase(s) && needed > 0 && ((int)s - (int)x) % needed == 0; }
+};
+static PredSchedule pred_schedule(const sbc_handle *h) {
+    PredSchedule q;
+    const sbc_params &p = h->hp;
+    if (h->S.Npred <= 0) return q;
+    q.active = true;
+    q.x = p.pred_time / p.dt;
+    if (h->S.Npred > 1) {
+        if (p.pred_speed0 > 0) q.needed = (int)(p.sizeL / 2 / (p.pred_speed0 * p.dt));
+        else q.needed = (int)((p.sim_time - p.trans_time) / 4 / p.dt);
+    }
+    return q;
+}
+
 int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
     if (!h || n_steps < 0) return SBC_ERR_INVALID;
     if (!h->state_set) return fail(h, SBC_ERR_STATE, "sbc_step: no state");
+    if (h->dom.enabled && h->S.Npred > 0 && !h->pbox_ready)
+        return fail(h, SBC_ERR_STATE, "sbc_step: the predators of a decomposed swarm need sbc_domain_attach_world");
     if (n_steps == 0) return SBC_OK;
     SBC_CUDA(cudaSetDevice(h->device));
     DevState &S = h->S;
@@ -950,13 +1009,13 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         for (int64_t s = s_first; s < s_first + n_steps; s++) {
             const bool pred_phase = S.Npred > 0 && (double)s >= p.pred_time / dt;
             if (S.Npred > 0 && (double)s >= p.pred_time / dt && (double)(s - 1) < p.pred_time / dt) {
-                sbc_launch_pred_spawn(h->P, S, s, 0, h->stream);  // swarmdyn.cpp:153-158
+                launch_spawn(h, s, 0);  // swarmdyn.cpp:153-158
                 h->host_stats[7]++;
             }
             if (S.Npred > 1 && pred_phase) {  // swarmdyn.cpp:160-170
                 const int since = (int)s - (int)(p.pred_time / dt);
                 if (needed > 0 && since % needed == 0) {
-                    sbc_launch_pred_spawn(h->P, S, s, 1, h->stream);
+                    launch_spawn(h, s, 1);
                     h->host_stats[7]++;
                 }
             }
@@ -1222,7 +1281,7 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     if (!h || world < 1 || rank < 0 || rank >= world) return SBC_ERR_INVALID;
     if (h->S.R != 1) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: one swarm per handle");
     if (h->hp.BC != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: periodic boundary (BC 0) only");
-    if (h->S.Npred != 0) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators are not decomposed yet");
+    if (h->S.Npred > 0 && world > 16) return fail(h, SBC_ERR_INVALID, "sbc_domain_config: predators need world <= 16");
     if (own_capacity < 1 || own_capacity > h->S.N || max_migrants < 1 || max_halo < 1)
         return fail(h, SBC_ERR_INVALID, "sbc_domain_config: bad capacities");
     const float skin = cells_skin_for(h);
@@ -1254,6 +1313,13 @@ int sbc_domain_config(sbc_handle *h, int rank, int world, int own_capacity, int 
     h->dom.own_cap = own_capacity;
     h->dom.max_mig = max_migrants;
     h->dom.max_halo = max_halo;
+    h->pbox.world = world;
+    h->pbox.rank = rank;
+    if (h->S.Npred > 0 && !h->pred_key) {
+        SBC_CUDA(dev_alloc(&h->pred_key, 1));
+        SBC_CUDA(cudaMemset(h->pred_key, 0xff, sizeof(unsigned long long)));
+        SBC_CUDA(dev_alloc(&h->pred_cand, (size_t)h->S.N));
+    }
     h->dom.x_lo = (float)(w * rank);
     h->dom.x_hi = (rank == world - 1) ? (float)h->hp.sizeL : (float)(w * (rank + 1));
     if (!h->S.gid) {  // default ids = slot index
@@ -1299,7 +1365,7 @@ int sbc_domain_rebuild_period(sbc_handle *h, int period) {
 }
 // ---- exchange through peer memory -----------------------------------------------------------------
 static unsigned char *inbox_buf(unsigned char *base, size_t bytes, int side, int parity) {
-    return base + 256 + (size_t)(side * 2 + parity) * bytes;
+    return base + 256 + sbc_pred_area_bytes() + (size_t)(side * 2 + parity) * bytes;   // [flags | predator area | 4 buffers]
 }
 static int *inbox_flag(unsigned char *base, int side, int parity) { return reinterpret_cast<int *>(base) + side * 2 + parity; }
 
@@ -1308,7 +1374,7 @@ int sbc_domain_inbox(sbc_handle *h, void **base_dev, size_t *bytes, void *ipc_ha
     SBC_CUDA(cudaSetDevice(h->device));
     if (!h->inbox) {
         h->inbox_buf_bytes = sbc_domain_buffer_bytes(h->dom.max_mig, h->dom.max_halo);
-        const size_t total = 256 + 4 * h->inbox_buf_bytes;
+        const size_t total = 256 + sbc_pred_area_bytes() + 4 * h->inbox_buf_bytes;
         SBC_CUDA(cudaMalloc((void **)&h->inbox, total));
         SBC_CUDA(cudaMemset(h->inbox, 0, total));
         for (int k = 0; k < 2; k++) {
@@ -1318,7 +1384,7 @@ int sbc_domain_inbox(sbc_handle *h, void **base_dev, size_t *bytes, void *ipc_ha
         h->dom_epoch = 0;
     }
     if (base_dev) *base_dev = h->inbox;
-    if (bytes) *bytes = 256 + 4 * h->inbox_buf_bytes;
+    if (bytes) *bytes = 256 + sbc_pred_area_bytes() + 4 * h->inbox_buf_bytes;
     if (ipc_handle_64) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         SBC_CUDA(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(ipc_handle_64), h->inbox));
@@ -1344,6 +1410,22 @@ int sbc_domain_attach_peers(sbc_handle *h, void *left_inbox_dev, void *right_inb
     h->peer_r = static_cast<unsigned char *>(right_inbox_dev);
     return SBC_OK;
 }
+int sbc_domain_attach_world(sbc_handle *h, void *const *inboxes_dev, int n) {
+    if (!h || !h->dom.enabled || !h->inbox) return SBC_ERR_STATE;
+    if (!inboxes_dev || n != h->pbox.world || n > 16) return fail(h, SBC_ERR_INVALID, "sbc_domain_attach_world: one inbox per rank, in rank order");
+    invalidate_graphs(h);
+    for (int r = 0; r < 16; r++) h->pbox.peer[r] = nullptr;
+    for (int r = 0; r < n; r++) {
+        if (!inboxes_dev[r]) return fail(h, SBC_ERR_INVALID, "sbc_domain_attach_world: null inbox");
+        h->pbox.peer[r] = static_cast<unsigned char *>(inboxes_dev[r]) + 256;
+    }
+    if (h->pbox.peer[h->pbox.rank] != h->inbox + 256)
+        return fail(h, SBC_ERR_INVALID, "sbc_domain_attach_world: entry [rank] must be this handle's own inbox");
+    sbc_pred_preload();
+    h->pbox_ready = true;
+    return SBC_OK;
+}
+
 static void domain_launch_push(sbc_handle *h) {
     // what I send left arrives at the left neighbour as data "from its right" (side 1), and vice versa
     void *dst_l[2], *dst_r[2];
@@ -1467,17 +1549,26 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
             h->dom_shift = shift;
         }
     }
+    if (h->S.Npred > 0 && !h->pbox_ready)
+        return fail(h, SBC_ERR_STATE, "sbc_domain_step: the predators of a decomposed swarm need sbc_domain_attach_world");
+    const PredSchedule sched = pred_schedule(h);
+    const int npred = h->S.Npred;
     bool pending = false;   // the refresh exchange behind the last step has not run yet
     int64_t s = s_first;
     for (; s < s_first + n_steps; s++) {
         if (int rc = ensure_cells(h)) return rc;
+        const bool pred_phase = sched.phase(s);
+        if (sched.spawn0(s)) { launch_spawn(h, s, 0); h->host_stats[7]++; }
+        if (sched.spawn1(s, npred)) { launch_spawn(h, s, 1); h->host_stats[7]++; }
         // the exchange behind this step is a full one when the NEXT step rebuilds the cell order
         const bool rebuild_now = !h->cells_valid || h->cells_age > h->cells_max_age;
         // four refresh steps in one graph launch when none of them ends in a full exchange
         int count = pending ? mk_batch(h, s_first + n_steps - s) : 1;
         if (count > 1 && h->cells_age + count > h->cells_max_age) count = 1;
+        for (int k = 0; k < count && count > 1; k++)   // a batch holds steps of one kind, none of which (re)creates a predator
+            if (sched.phase(s + k) != pred_phase || sched.spawn0(s + k) || sched.spawn1(s + k, npred)) count = 1;
         if (count > 1) {
-            if (int rc = mk_step(h, s, false, true, count, true)) return rc;
+            if (int rc = mk_step(h, s, pred_phase, true, count, true)) return rc;
             h->dom_last_full = false;
             h->dom_epoch += count;
             s += count - 1;
@@ -1485,7 +1576,7 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         }
         const int age_after = (rebuild_now ? 0 : h->cells_age) + 1;
         const bool full_after = age_after > h->cells_max_age;
-        if (int rc = mk_step(h, s, false, pending, 1, !full_after)) return rc;
+        if (int rc = mk_step(h, s, pred_phase, pending, 1, !full_after)) return rc;
         pending = false;
         if (full_after) {
             if (int rc = sbc_domain_post(h)) return rc;

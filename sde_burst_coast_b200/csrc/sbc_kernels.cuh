@@ -249,20 +249,6 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
     S.force[g] = make_float2(a.fx, a.fy);
     S.tm_nxt[g] = sbc_tm_pack(a.bin_step, a.stb, P);
     if (S.flags) S.flags[g] |= (uint8_t)fl;
-    if (A.halo_idx && (p.x < A.band_lo || p.x >= A.band_hi)) {
-        // decomposed swarm: an agent in an edge band delivers its new position to the neighbour itself; the step's last
-        // graph node (dom_publish_kernel) then raises the neighbours' flags
-        const int2 hi = A.halo_idx[g];
-        if ((hi.x & hi.y) != -1) {
-            const int par = ((int)step + A.xshift[0]) & 1;
-            const float4 npv = make_float4(a.x, a.y, a.vx, a.vy);
-            // 64-byte records behind a header record, position in the first 16 bytes (DomRecord, domain.cu)
-            // (selects, not a dynamic index: indexing a kernel parameter array would copy the whole struct to local memory)
-            void *dl = par ? A.xdst[0][1] : A.xdst[0][0], *dr = par ? A.xdst[1][1] : A.xdst[1][0];
-            if (hi.x >= 0) reinterpret_cast<float4 *>(dl)[(size_t)(1 + hi.x) * 4] = npv;
-            if (hi.y >= 0) reinterpret_cast<float4 *>(dr)[(size_t)(1 + hi.y) * 4] = npv;
-        }
-    }
     bool alive = true;
     if (A.net_kill) {
         // FishNetKill (agents_dynamics.cpp:780-820) against the net AFTER this step's MoveFishNet (:616-624): the
@@ -280,6 +266,22 @@ __device__ __forceinline__ bool sbc_update_agent(const DevParams &P, const DevSt
             // agents_operation.cpp:209-218) is applied by net_move_kernel behind the step's two kernels
             S.kill_list[atomicAdd(S.kill_count, 1)] = (int)g;
             alive = false;
+        }
+    }
+    if (A.halo_idx && (p.x < A.band_lo || p.x >= A.band_hi)) {
+        // decomposed swarm: an agent in an edge band delivers its new position to the neighbour itself; the step's last
+        // graph node (dom_publish_kernel) then raises the neighbours' flags
+        const int2 hi = A.halo_idx[g];
+        if ((hi.x & hi.y) != -1) {
+            const int par = ((int)step + A.xshift[0]) & 1;
+            // (an agent the net has just caught leaves as dead: NaN position, like its own slot after net_move_kernel)
+            const float qnan = __int_as_float(0x7fc00000);
+            const float4 npv = alive ? make_float4(a.x, a.y, a.vx, a.vy) : make_float4(qnan, qnan, a.vx, a.vy);
+            // 64-byte records behind a header record, position in the first 16 bytes (DomRecord, domain.cu)
+            // (selects, not a dynamic index: indexing a kernel parameter array would copy the whole struct to local memory)
+            void *dl = par ? A.xdst[0][1] : A.xdst[0][0], *dr = par ? A.xdst[1][1] : A.xdst[1][0];
+            if (hi.x >= 0) reinterpret_cast<float4 *>(dl)[(size_t)(1 + hi.x) * 4] = npv;
+            if (hi.y >= 0) reinterpret_cast<float4 *>(dr)[(size_t)(1 + hi.y) * 4] = npv;
         }
     }
     return alive && a.bin_step == P.burst_steps;
@@ -485,6 +487,19 @@ void sbc_launch_step_advance(uint32_t *step_dev, int count, cudaStream_t st);
 void sbc_launch_pred_spawn(const DevParams &P, const DevState &S, long long step, int respawn_slot,
                            cudaStream_t st);
 // step_back: the device-resident step index has already moved on (the kernel runs behind the step's two kernels)
+// decomposed swarm: where every rank's predator area lives (device pointers, own rank included), see predator.cu
+struct PredBox {
+    unsigned char *peer[16];
+    int world, rank;
+    unsigned long long timeout_ns;
+};
+size_t sbc_pred_area_bytes(void);
+void sbc_pred_preload(void);
+void sbc_cells_preload(void);
+void sbc_launch_domain_pred_spawn(const DevParams &P, const DevState &S, const PredBox &B, int own_cap, int *ctl, long long step,
+                                  int slot, cudaStream_t st);
+void sbc_launch_domain_pred_move_kill(const DevParams &P, const DevState &S, const PredBox &B, int own_cap, int *ctl,
+                                      unsigned long long *key, int *cand, const StepArgs &A, cudaStream_t st);
 void sbc_launch_pred_move_kill(const DevParams &P, const DevState &S, long long step, const uint32_t *step_dev,
                                cudaStream_t st);
 

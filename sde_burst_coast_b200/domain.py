@@ -95,6 +95,8 @@ class PeerTransport:
         slab.swarm._check(lib.sbc_domain_inbox(h, ctypes.byref(base), ctypes.byref(nbytes), handle))
         if self.world == 1:
             slab.swarm._check(lib.sbc_domain_attach_peers(h, base, base))
+            if slab.n_pred > 0:
+                slab.swarm._check(lib.sbc_domain_attach_world(h, (ctypes.c_void_p * 1)(base), 1))
             return
         dev = 'cuda' if dist.get_backend(group) == 'nccl' else 'cpu'
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
@@ -102,12 +104,18 @@ class PeerTransport:
         dist.all_gather(every, mine, group=group)
         left, right = neighbours(self.rank, self.world)
         mapped = {}
-        for peer in {left, right}:
+        # the halo exchange talks to the two ring neighbours; a predator's all-gathers (closest prey, kill sums, centre
+        # of mass) to everybody: with predators every rank maps every inbox
+        for peer in (set(range(self.world)) - {self.rank}) if slab.n_pred > 0 else {left, right}:
             raw = (ctypes.c_ubyte * 64)(*every[peer].cpu().tolist())
             p = ctypes.c_void_p()
             slab.swarm._check(lib.sbc_domain_open_peer(h, raw, ctypes.byref(p)))
             mapped[peer] = p
+        mapped[self.rank] = base
         slab.swarm._check(lib.sbc_domain_attach_peers(h, mapped[left], mapped[right]))
+        if slab.n_pred > 0:
+            arr = (ctypes.c_void_p * self.world)(*[mapped[r] for r in range(self.world)])
+            slab.swarm._check(lib.sbc_domain_attach_world(h, arr, self.world))
         dist.barrier(group=group)   # every inbox is mapped before anybody pushes
 
     def min_int(self, v):
@@ -134,7 +142,7 @@ class SlabSwarm:
     """One slab of the decomposed swarm on one GPU."""
 
     def __init__(self, sp, n_global, rank, world, seed=0, device=0, stream=None, own_capacity=None,
-                 ghost_capacity=None, max_records=None):
+                 ghost_capacity=None, max_records=None, n_pred=0):
         import torch
         from .swarm import Swarm
         from . import params as P
@@ -152,7 +160,8 @@ class SlabSwarm:
         self.sp = sp2
         self.dev = torch.device('cuda', device)
         self.stream = stream   # cudaStream_t (int) the handle's kernels run on; None = the handle's private stream
-        self.swarm = Swarm(sp2, self.own_cap + self.ghost_cap, 0, 1, seed=seed, device=device, stream=stream)
+        self.n_pred = int(n_pred)   # replicated on every rank (sbc_domain_attach_world)
+        self.swarm = Swarm(sp2, self.own_cap + self.ghost_cap, self.n_pred, 1, seed=seed, device=device, stream=stream)
         lib, h = self.swarm.lib, self.swarm.h
         self.swarm._check(lib.sbc_domain_config(h, rank, world, self.own_cap, self.max_mig, self.max_halo))
         nbytes = lib.sbc_domain_buffer_bytes(self.max_mig, self.max_halo)
@@ -287,6 +296,33 @@ def attach_loopback_peers(slabs):
     for sl in slabs:
         left, right = neighbours(sl.rank, world)
         sl.swarm._check(sl.swarm.lib.sbc_domain_attach_peers(sl.swarm.h, bases[left], bases[right]))
+        if sl.n_pred > 0:   # (the slabs then need their own streams: a predator's all-gather waits inside a kernel)
+            sl.swarm._check(sl.swarm.lib.sbc_domain_attach_world(sl.swarm.h, (ctypes.c_void_p * world)(*bases), world))
+
+
+def _step_all(slabs, s):
+    """One local step of every slab. With predators a slab's step waits INSIDE its kernels for the other slabs' records
+    (and libsbc may synchronise the slab's stream), so the slabs are driven by one host thread each, as one process
+    per GPU would."""
+    if not any(sl.n_pred > 0 for sl in slabs):
+        for sl in slabs:
+            sl.step_local(s)
+        return
+    import threading
+    err = []
+
+    def run(sl):
+        try:
+            sl.step_local(s)
+        except Exception as e:   # noqa: BLE001
+            err.append(e)
+    th = [threading.Thread(target=run, args=(sl,)) for sl in slabs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if err:
+        raise err[0]
 
 
 def step_loopback(slabs, s_first, n_steps, peer=False):
@@ -310,8 +346,7 @@ def step_loopback(slabs, s_first, n_steps, peer=False):
             for sl in slabs:
                 sl.primed = True
         for s in range(s_first, s_first + n_steps):
-            for sl in slabs:
-                sl.step_local(s)
+            _step_all(slabs, s)
             if world > 1:
                 exchange()
         return
@@ -333,8 +368,7 @@ def step_loopback(slabs, s_first, n_steps, peer=False):
         for sl in slabs:
             sl.primed = True
     for s in range(s_first, s_first + n_steps):
-        for sl in slabs:
-            sl.step_local(s)
+        _step_all(slabs, s)
         if world > 1:
             exchange()
 

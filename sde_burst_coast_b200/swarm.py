@@ -69,6 +69,7 @@ ABI = [
     ('sbc_domain_inbox', ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), _vp]),
     ('sbc_domain_open_peer', ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_void_p)]),
     ('sbc_domain_attach_peers', ctypes.c_int, [_vp, _vp, _vp]),
+    ('sbc_domain_attach_world', ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]),
     ('sbc_domain_post', ctypes.c_int, [_vp]),
     ('sbc_domain_complete', ctypes.c_int, [_vp]),
     ('sbc_domain_step', ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_int64]),

@@ -11,17 +11,24 @@ from sde_burst_coast_b200.domain import SlabSwarm, PeerTransport, DistTransport,
 from sde_burst_coast_b200.swarm import Swarm
 
 transport = sys.argv[1] if len(sys.argv) > 1 else 'peer'
+scenario = sys.argv[2] if len(sys.argv) > 2 else 'none'   # none | chase (one chasing predator, kill rule 3) | net (fish net)
 world, rank, local = int(os.environ['WORLD_SIZE']), int(os.environ['RANK']), int(os.environ['LOCAL_RANK'])
 torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 N, L, K = 120000, 3400.0, 130
-d = base_dict('natPred', N, BC=0, size=L, Npred=0)
-sp, _ = PP.make_sbc_params(d, path=PP.PATH_CELLLIST)
+if scenario == 'chase':
+    d = base_dict('natPred', N, BC=0, size=L, Npred=1, pred_kill=3, pred_move=1, pred_time=0.02, time=50.0, pred_speed0=40.0,
+                  kill_rate=400.0, N_confu=500)
+elif scenario == 'net':
+    d = base_dict('mulFisher', N, BC=0, size=L, Npred=200, pred_kill=1, pred_move=0, pred_time=0.02, time=50.0, pred_speed0=40.0)
+else:
+    d = base_dict('natPred', N, BC=0, size=L, Npred=0)
+sp, npred = PP.make_sbc_params(d, path=PP.PATH_CELLLIST)
 rng = np.random.default_rng(99)
 st = dict(x=f32(L * rng.random(N)), y=f32(L * rng.random(N)), phi=f32(2 * np.pi * rng.random(N) - np.pi), vproj=4.0 * np.ones(N))
 ts = torch.cuda.Stream()
 torch.cuda.set_stream(ts)
-slab = SlabSwarm(sp, N, rank, world, seed=7, device=local, stream=ts.cuda_stream)
+slab = SlabSwarm(sp, N, rank, world, seed=7, device=local, stream=ts.cuda_stream, n_pred=npred)
 slab.scatter_initial(st)
 tr = PeerTransport(slab) if transport == 'peer' else DistTransport(rank, world)
 step_distributed(slab, tr, 0, 40)
@@ -31,29 +38,37 @@ gid, own = slab.owned_state()
 c = slab.counts()
 stats = slab.swarm.stats()
 gathered = [None] * world
-dist.gather_object((gid, own, c, stats['cell_builds']), gathered if rank == 0 else None, dst=0)
+pred_here = slab.swarm.get_predators()
+dist.gather_object((gid, own, c, stats['cell_builds'], pred_here), gathered if rank == 0 else None, dst=0)
 if rank == 0:
-    whole = Swarm(sp, N, seed=7, device=local)
+    whole = Swarm(sp, N, npred, seed=7, device=local)
     whole.set_state(**st)
     whole.step(0, K)
     ws = whole.get_state()
+    wpred = whole.get_predators()
     whole.close()
     seen = np.zeros(N, dtype=np.int32)
     got = {k: np.zeros(N, dtype=v.dtype) for k, v in gathered[0][1].items()}
-    for g_, o_, c_, builds in gathered:
+    for g_, o_, c_, builds, pr_ in gathered:
+        assert np.allclose(pr_[..., :2], wpred[..., :2], atol=2e-3), 'every rank holds the whole swarm\'s predator'
+        assert np.array_equal(pr_, gathered[0][4]), 'the replicated predator is bit-identical on all ranks'
         assert c_['overflow_events'] == 0, c_
         assert builds < K // 2, builds      # most exchanges were refreshes
         seen[g_] += 1
         for k, v in o_.items():
             got[k][g_] = v
-    assert np.all(seen == 1), 'every agent is owned by exactly one rank'
-    assert np.array_equal(got['steps_till_burst'], ws['steps_till_burst'])
-    assert np.array_equal(got['bin_step'], ws['bin_step'])
+    al = ws['alive'] == 1
+    assert np.array_equal(seen == 1, al) and seen.max() <= 1, 'every living agent is owned by exactly one rank, the same agents died'
+    if npred:
+        assert (~al).sum() > 0, 'the scenario should kill somebody'
+    assert np.array_equal(got['steps_till_burst'][al], ws['steps_till_burst'][al])
+    assert np.array_equal(got['bin_step'][al], ws['bin_step'][al])
     dx = np.abs(((got['x'] - ws['x'] + L / 2) % L) - L / 2)
     dy = np.abs(((got['y'] - ws['y'] + L / 2) % L) - L / 2)
-    close = (dx < 1e-3) & (dy < 1e-3)
+    close = ((dx < 1e-3) & (dy < 1e-3))[al]
     assert close.mean() > 0.995, close.mean()
-    print('multi-gpu-ok world=%d transport=%s close=%.5f migrated=%s' % (world, transport, close.mean(), [int(x[2]['owned']) for x in gathered]))
+    print('multi-gpu-ok world=%d transport=%s scenario=%s close=%.5f killed=%d migrated=%s' %
+          (world, transport, scenario, close.mean(), int((~al).sum()), [int(x[2]['owned']) for x in gathered]))
 slab.close()
 dist.barrier()
 dist.destroy_process_group()

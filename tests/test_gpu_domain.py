@@ -131,3 +131,69 @@ def test_peer_memory_exchange_equals_buffer_exchange(world):
             sl.close()
     for k in out[0]:
         assert np.array_equal(out[0][k], out[1][k]), k
+
+
+def _pred_setup(N, L, seed, mode, npred, kill, move, **over):
+    d = base_dict(mode, N, BC=0, size=L, Npred=npred, pred_kill=kill, pred_move=move, pred_time=0.005, time=50.0, **over)
+    sp, np_ = PP.make_sbc_params(d, path=PP.PATH_CELLLIST)
+    assert np_ == npred
+    rng = np.random.default_rng(seed)
+    st = random_state(N, sp, rng)
+    return sp, st
+
+
+def _pred_slabs(sp, st, N, world, seed, npred):
+    """Slabs with predators need their own streams: a predator's all-gather waits inside a kernel for the other ranks."""
+    import torch
+    from sde_burst_coast_b200.domain import SlabSwarm, attach_loopback_peers
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    slabs = [SlabSwarm(sp, N, r, world, seed=seed, stream=streams[r].cuda_stream, n_pred=npred) for r in range(world)]
+    for sl in slabs:
+        sl.scatter_initial(st)
+        sl._keep = streams
+    attach_loopback_peers(slabs)
+    return slabs
+
+
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('mode,npred,kill,move,over', [
+    ('natPred', 1, 3, 1, dict(kill_rate=400.0, N_confu=500)),        # chase: closest prey over all ranks; confusion sums
+    ('natPred', 1, 4, 1, dict(kill_rate=4000.0, N_confu=500)),       # + selection weights
+    ('natPred', 1, 1, 1, {}),                                        # radial kill
+    ('natPredNoConfu', 1, 2, 0, dict(kill_rate=400.0)),              # random walk, plain probabilistic kill
+    ('mulFisher', 40, 1, 0, {})])                                    # fish net
+def test_decomposed_swarm_with_predators_matches_whole_swarm(world, mode, npred, kill, move, over, monkeypatch):
+    """Predator phase over several slabs (spawn at the global centre of mass, chase of the globally closest prey,
+    PredKill with global sensed-prey count and weight sum, fish net) against the undecomposed swarm: the same agents
+    die, burst timers of the survivors are bit-identical, the predator ends where the whole swarm's predator ends."""
+    from sde_burst_coast_b200.domain import gather_global, step_loopback
+    from sde_burst_coast_b200.swarm import Swarm
+    N, L, K = 6000, 400.0, 70
+    sp, st = _pred_setup(N, L, 31 + kill, mode, npred, kill, move, pred_speed0=40.0, **over)
+    whole = Swarm(sp, N, npred, seed=23)
+    whole.set_state(**st)
+    whole.step(0, K)
+    ws, wp = whole.get_state(), whole.get_predators()
+    whole.close()
+    n_killed = int(N - ws['alive'].sum())
+    assert n_killed > 0, 'the scenario should kill somebody'
+    # (sbc_step + explicit exchanges, one host thread per slab, eager launches. Several handles of one process share a
+    # device: a graph instantiation of one handle waits for the whole device, i.e. for the other handles' kernels, while
+    # those wait inside an all-gather for records this handle has yet to send. One PROCESS per slab has no such cycle -
+    # tests/test_gpu_multi.py runs the graph-replayed, pipelined loop sbc_domain_step with predators on real GPUs.)
+    monkeypatch.setenv('SBC_NO_GRAPHS', '1')
+    for pipelined in (False,):
+        slabs = _pred_slabs(sp, st, N, world, 23, npred)
+        step_loopback(slabs, 0, K, peer=True)
+        got, seen = gather_global(slabs, N)
+        alive_dec = seen == 1
+        assert np.array_equal(alive_dec, ws['alive'] == 1), (pipelined, int(alive_dec.sum()), int(ws['alive'].sum()))
+        al = ws['alive'] == 1
+        assert np.array_equal(got['steps_till_burst'][al], ws['steps_till_burst'][al])
+        assert np.array_equal(got['bin_step'][al], ws['bin_step'][al])
+        for sl in slabs:
+            pp = sl.swarm.get_predators()
+            assert np.allclose(pp[..., :2], wp[..., :2], atol=2e-3), (sl.rank, pp[0, 0], wp[0, 0])
+        assert sum(sl.counts()['overflow_events'] for sl in slabs) == 0
+        for sl in slabs:
+            sl.close()
