@@ -61,7 +61,90 @@ def run(name, d, npred_expected, steps, cpu_steps, neighbour=PP.NEIGHBOUR_METRIC
     print(json.dumps(out), flush=True)
 
 
+def c2_runs(cpu_seconds):
+    """16,384 independent tanks, N in {8, 16, 32, 64} (10,000 steps each), a mixed ensemble
+    (N = 8 * 2^(r mod 4): four handles of 4,096 tanks on four streams at once) and one 40,000-step run; the reference's
+    own translation units on ONE core beside each (a bounded sample of single tanks, throughput per agent-step)."""
+    import torch
+    import bench
+    from helpers import make_params
+    from sde_burst_coast_b200.swarm import Swarm
+    from oracle import pyorc
+    kind = 'reference' if pyorc.have_reference() else 'port'
+    R = 16384
+
+    def cpu_rate(sp, N):
+        rate, secs, n = bench.cpu_sample(sp, N, max(1, 8 // max(1, N // 8)), int(2000 * cpu_seconds), kind, 1, bench.SEED)
+        return rate
+
+    def gpu_run(N, tanks, steps, stream, first=0):
+        sp, _, _ = make_params('burst_coast', N)
+        g = Swarm(sp, N, n_replicates=tanks, seed=bench.SEED, replicate_offset=first, stream=stream.cuda_stream)
+        g.set_state(**bench.tank_ensemble_state(tanks, N, sp, bench.SEED, first_replicate=first))
+        return sp, g
+
+    for N, steps in ((8, 10000), (16, 10000), (32, 10000), (64, 10000), (32, 40000)):
+        ts = torch.cuda.Stream()
+        sp, g = gpu_run(N, R, steps, ts)
+        with torch.cuda.stream(ts):
+            g.step(0, 1000)
+            torch.cuda.synchronize()
+            s0 = g.stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ts)
+            g.step(1000, steps)
+            e1.record(ts)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        s1 = g.stats()
+        g.close()
+        cpu = cpu_rate(sp, N)
+        out = {'config': 'C2 ensemble %d tanks x N=%d, %d steps' % (R, N, steps), 'n_agents': N, 'replicates': R, 'gpu_steps': steps,
+               'gpu_ms': ms, 'gpu_agent_steps_per_s': N * R * steps / (ms * 1e-3),
+               'gpu_pairs_per_s': (s1['pairs'] - s0['pairs']) / (ms * 1e-3), 'gpu_launches': int(s1['block_launches'] - s0['block_launches']),
+               'kernel': 'swarm_warp_kernel (%d lanes per tank)' % max(8, N) if N <= 32 else 'swarm_block_kernel (one block per tank)',
+               'cpu_kind': kind, 'cpu_cores': 1, 'cpu_agent_steps_per_s': cpu}
+        out['speedup_vs_1_core'] = out['gpu_agent_steps_per_s'] / cpu
+        print(json.dumps(out), flush=True)
+    # mixed ensemble: replicate r holds N = 8 * 2^(r mod 4) agents -> four homogeneous handles of 4096 tanks, run at once
+    steps = 10000
+    parts = []
+    for k, N in enumerate((8, 16, 32, 64)):
+        ts = torch.cuda.Stream()
+        sp, g = gpu_run(N, R // 4, steps, ts, first=k * (R // 4))
+        parts.append((N, ts, g))
+    for N, ts, g in parts:
+        g.step(0, 1000)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for N, ts, g in parts:
+        g.step(1000, steps)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    agents = sum(N * (R // 4) for N, _, _ in parts)
+    for _, _, g in parts:
+        g.close()
+    print(json.dumps({'config': 'C2 mixed ensemble: %d tanks, N = 8 * 2^(r mod 4), %d steps, four handles on four streams' % (R, steps),
+                      'agents_total': agents, 'gpu_steps': steps, 'gpu_ms': secs * 1e3, 'timing': 'wall clock around the four launches, synchronised',
+                      'gpu_agent_steps_per_s': agents * steps / secs}), flush=True)
+
+
+def c4_sweep():
+    """mulFisher N = 16,384, L = 1280, 640 net nodes, prob_social in {0, .25, .5, .71, .74, 1}."""
+    for ps in (0.0, 0.25, 0.5, 0.71, 0.74, 1.0):
+        d = base_dict('mulFisher', 16384, BC=0, size=1280.0, Npred=640, pred_kill=1, pred_time=0.02, time=12.0, prob_social=ps)
+        run('C4 mulFisher N=16384 L=1280 prob_social=%g' % ps, d, 640, 1000, 2)
+
+
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--set', default='base', choices=['base', 'c2', 'c4sweep'])
+    ap.add_argument('--cpu-seconds', type=float, default=4.0)
+    args = ap.parse_args()
+    if args.set == 'c2':
+        return c2_runs(args.cpu_seconds)
+    if args.set == 'c4sweep':
+        return c4_sweep()
     # C1: single tank, N = 8 and 30, metric and Voronoi rule
     for N in (8, 30):
         d = base_dict('burst_coast', N)
