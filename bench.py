@@ -274,7 +274,11 @@ def run_reference(args, sp, N):
         'config': workload_config(args, N, tanks_override=tanks),
         'cpu_baseline': {'value': val, 'unit': 'agent-steps/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': val, 'unit': 'agent-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0}))
+        'gpu_launches': 0,
+        'note': 'the reference\'s own translation units (oracle/_ref) when present, else the port. Bookkeeping of this arm (VERDICT r1 #14): the '
+                'decisions come from one Philox block per agent and step computed inside the timed loop (the reference draws from a '
+                'serial MT19937), and the Gaussian the reference draws and discards per agent and step (swarmdyn.cpp:188) is left '
+                'out - roughly cancelling, a few per cent of the CPU time either way'}))
 
 
 def workload_config(args, N, tanks_override=None):

@@ -36,8 +36,11 @@ typedef enum sbc_status {
 
 /* neighbour rule: which candidate set feeds the three-zone filter */
 enum { SBC_NEIGHBOUR_METRIC = 0 /* = InteractionGlobal, agents_interact.cpp:144-157 */,
-       SBC_NEIGHBOUR_VORONOI = 1 /* = InteractionVoronoiF2F, :26-77 (the shipped default): Delaunay
-                                    neighbours; non-periodic swarms of <= 1024 agents, no predators */ };
+       SBC_NEIGHBOUR_VORONOI = 1 /* = InteractionVoronoiF2F :26-77 / F2FP :79-141 (the shipped default): Delaunay
+                                    neighbours, swarms of <= 1024 agents. Periodic boxes: nearest-image
+                                    triangulation (what GetCopies4PeriodicBC, agents_operation.cpp:240-293,
+                                    means to build); predator phase: predators are vertices, every edge
+                                    interacts both ways (the reference: one arbitrary way) */ };
 /* pair-search path */
 enum { SBC_PATH_AUTO = 0, SBC_PATH_ALLPAIRS = 1, SBC_PATH_CELLLIST = 2 };
 

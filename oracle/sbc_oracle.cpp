@@ -442,17 +442,34 @@ void interact_all_pairs(orc_world &w, bool gate) {
 // from one side; the edge exists iff max(lower) <= min(upper). Same criterion and arithmetic as the
 // brute-force CGAL stand-in the reference build links against (oracle/shims/CGAL/
 // Delaunay_triangulation_2.h), which is what InteractionVoronoiF2F (agents_interact.cpp:26-77) sees.
-bool delaunay_edge(const orc_world &w, int i, int j) {
-    const double ax = w.a[i].x[0], ay = w.a[i].x[1], bx = w.a[j].x[0], by = w.a[j].x[1];
+// Periodic boxes (InteractionVoronoiF2FP + GetCopies4PeriodicBC, agents_operation.cpp:240-293): the reference means to
+// triangulate the agents together with shifted copies that give every agent its surroundings up to L/2 (its quadrant
+// flags are never reset: undefined behaviour). Well-defined equivalent: the test for row i sees every other
+// point at its image nearest to row i (CalcDistVec's minimum image, mathtools.h:54-73). In the predator phase the
+// predators are vertices of the reference's triangulation (agents_interact.cpp:103-110): they can only remove edges.
+inline double vor_pos(double ref, double v, int BC, double L) {
+    if (BC != 0) return v;
+    double r = v - ref;
+    const double sign = sgn(r);
+    r = std::fmod(r + sign * L / 2, L) - sign * L / 2;
+    return ref + r;
+}
+bool delaunay_edge(const orc_world &w, int i, int j, bool with_preds) {
+    const int BC = w.p.BC;
+    const double L = w.p.sizeL;
+    const double ax = w.a[i].x[0], ay = w.a[i].x[1];
+    const double bx = vor_pos(ax, w.a[j].x[0], BC, L), by = vor_pos(ay, w.a[j].x[1], BC, L);
     const double dx = bx - ax, dy = by - ay;
     const double len2 = dx * dx + dy * dy;
     if (len2 == 0) return false;
     const double mx = 0.5 * (ax + bx), my = 0.5 * (ay + by);
     const double nx = -dy, ny = dx;
     double lo = -INFINITY, hi = INFINITY;
-    for (int k = 0; k < w.N; k++) {
-        if (k == i || k == j || w.a[k].dead) continue;
-        const double qx = w.a[k].x[0] - mx, qy = w.a[k].x[1] - my;
+    const int n_pts = w.N + (with_preds ? w.Npred : 0);
+    for (int k = 0; k < n_pts; k++) {
+        if (k < w.N && (k == i || k == j || w.a[k].dead)) continue;
+        const double *xk = (k < w.N) ? w.a[k].x : w.preds[k - w.N].x;
+        const double qx = vor_pos(ax, xk[0], BC, L) - mx, qy = vor_pos(ay, xk[1], BC, L) - my;
         const double c = qx * qx + qy * qy - 0.25 * len2;
         const double s = qx * nx + qy * ny;
         if (s > 0) {
@@ -471,7 +488,7 @@ bool delaunay_edge(const orc_world &w, int i, int j) {
 
 // agents_interact.cpp:26-77 InteractionVoronoiF2F (non-periodic domains): both directions of every
 // Delaunay edge go through IntCalcPrey; a row receives its partners in ascending id
-void interact_voronoi(orc_world &w, bool gate) {
+void interact_voronoi(orc_world &w, bool gate, bool with_preds) {
     const int N = w.N;
     for (int i = 0; i < N; i++) {
         if (w.a[i].dead) continue;
@@ -479,16 +496,19 @@ void interact_voronoi(orc_world &w, bool gate) {
             if (w.a[j].dead) continue;
             const bool need_i = !gate || w.a[i].bin_step == w.p.burst_steps;
             const bool need_j = !gate || w.a[j].bin_step == w.p.burst_steps;
-            if (!need_i && !need_j) continue;
-            if (!delaunay_edge(w, i, j)) continue;
-            pair_term(w, w.a[i], w.a[j], j, gate);
-            pair_term(w, w.a[j], w.a[i], i, gate);
+            // the test runs in the frame of the receiving row (its own position, everybody else's nearest image): the
+            // same edge in exact arithmetic, and in an open domain the very same floating-point decisions both ways
+            if (need_i && delaunay_edge(w, i, j, with_preds)) pair_term(w, w.a[i], w.a[j], j, gate);
+            if (need_j && delaunay_edge(w, j, i, with_preds)) pair_term(w, w.a[j], w.a[i], i, gate);
         }
     }
 }
 
-void interact(orc_world &w, bool gate) {
-    if (w.p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) interact_voronoi(w, gate);
+// with_preds: the predator phase of Voronoi mode (InteractionVoronoiF2FP, agents_interact.cpp:79-141) - the predators are
+// vertices of the triangulation. Both directions of every edge are applied, as in F2F (the reference applies
+// ONE direction there, which one depends on CGAL's internal edge representation).
+void interact(orc_world &w, bool gate, bool with_preds = false) {
+    if (w.p.neighbour_mode == SBC_NEIGHBOUR_VORONOI) interact_voronoi(w, gate, with_preds);
     else interact_all_pairs(w, gate);
 }
 
@@ -741,7 +761,7 @@ void one_step(orc_world &w, int64_t s, uint8_t *flags) {
     }
     for (Agent &a : w.a) a.nn.clear();  // :172-173
     // :179-182 interaction
-    interact(w, true);
+    interact(w, true, have_pred && !(s < p.pred_time / dt));
     if (have_pred && !(s < p.pred_time / dt)) {
         for (int i = 0; i < N; i++) {
             Agent &a = w.a[i];

@@ -53,11 +53,16 @@ pair_rows_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs SA) {
             }
             if (P.voronoi && z < 3) {
                 DelaunayEdge e;
-                sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+                sbc_delaunay_begin(e, pi.x, pi.y, sbc_vor_pos(pi.x, pj.x, P), sbc_vor_pos(pi.y, pj.y, P));
                 for (int kk = 0; kk < N; kk++) {
                     const float4 pk = pv[kk];
-                    if (kk != i && kk != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                    if (kk != i && kk != j && pk.x == pk.x) sbc_delaunay_add(e, sbc_vor_pos(pi.x, pk.x, P), sbc_vor_pos(pi.y, pk.y, P));
                 }
+                if (SA.pred_active)   // the predators are vertices of F2FP's triangulation (agents_interact.cpp:103-110)
+                    for (int q = 0; q < S.Npred; q++) {
+                        const float4 pq = S.pred_pv[(size_t)rep * S.Npred + q];
+                        sbc_delaunay_add(e, sbc_vor_pos(pi.x, pq.x, P), sbc_vor_pos(pi.y, pq.y, P));
+                    }
                 if (!sbc_delaunay_end(e)) z = 3;
             }
             const float rinv = rsqrtf(fmaxf(d2, 1e-30f));
@@ -132,10 +137,10 @@ __global__ void nn_fill_kernel(const __grid_constant__ DevParams P, DevState S, 
         if (amb) z = sbc_zone_exact(pi.x, pi.y, pj.x, pj.y, P);
         if (P.voronoi && z < 3) {
             DelaunayEdge e;
-            sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+            sbc_delaunay_begin(e, pi.x, pi.y, sbc_vor_pos(pi.x, pj.x, P), sbc_vor_pos(pi.y, pj.y, P));
             for (int k = 0; k < N; k++) {
                 const float4 pk = pv[k];
-                if (k != i && k != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                if (k != i && k != j && pk.x == pk.x) sbc_delaunay_add(e, sbc_vor_pos(pi.x, pk.x, P), sbc_vor_pos(pi.y, pk.y, P));
             }
             if (!sbc_delaunay_end(e)) z = 3;
         }

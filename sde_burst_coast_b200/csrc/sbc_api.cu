@@ -215,10 +215,10 @@ int sbc_create(const sbc_params *p, int n_agents, int n_pred, int n_replicates, 
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need n_agents >= 1, n_replicates >= 1, n_pred >= 0");
     if (p->neighbour_mode != SBC_NEIGHBOUR_METRIC && p->neighbour_mode != SBC_NEIGHBOUR_VORONOI)
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: unknown neighbour_mode");
-    if (p->neighbour_mode == SBC_NEIGHBOUR_VORONOI && (p->BC == 0 || n_pred > 0 || n_agents > 1024))
+    if (p->neighbour_mode == SBC_NEIGHBOUR_VORONOI && n_agents > 1024)
         return fail(nullptr, SBC_ERR_INVALID,
-                    "sbc_create: the Voronoi neighbour rule is implemented for non-periodic swarms of up to 1024 "
-                    "agents without predators (InteractionVoronoiF2F on tanks)");
+                    "sbc_create: the Voronoi neighbour rule (InteractionVoronoiF2F / F2FP) is implemented for swarms of up to "
+                    "1024 agents");
     if (!(p->dt > 0) || !(p->burst_rate > 0) || !(p->burst_rate * p->dt < 1))
         return fail(nullptr, SBC_ERR_INVALID, "sbc_create: need dt > 0 and 0 < burst_rate*dt < 1");
     if (!(p->rep_range <= p->alg_range && p->alg_range <= p->att_range))

@@ -240,7 +240,17 @@ struct DelaunayEdge {
     double mx, my, nx, ny, q4, lo, hi;
     bool ok;
 };
-__device__ __forceinline__ void sbc_delaunay_begin(DelaunayEdge &e, float xi, float yi, float xj, float yj) {
+// Periodic boxes (InteractionVoronoiF2FP with GetCopies4PeriodicBC, agents_operation.cpp:240-293): the reference means
+// to triangulate the agents together with shifted copies that give every agent its surroundings up to L/2 in each
+// direction (its quadrant flags are never reset - undefined behaviour). The well-defined equivalent used here:
+// the test for row i sees every other point at its image NEAREST to row i, which is the periodic Delaunay
+// triangulation as long as the empty circles are smaller than L/2. Predators are vertices of the reference's
+// triangulation in the predator phase (agents_interact.cpp:103-110): they are added as points that can only remove edges.
+__device__ __forceinline__ double sbc_vor_pos(float ref, float v, const DevParams &P) {
+    if (P.BC != 0) return (double)v;
+    return __dadd_rn((double)ref, sbc_min_image_dd(__dsub_rn((double)v, (double)ref), P.dL));
+}
+__device__ __forceinline__ void sbc_delaunay_begin(DelaunayEdge &e, double xi, double yi, double xj, double yj) {
     const double ax = xi, ay = yi, bx = xj, by = yj;
     const double dx = __dsub_rn(bx, ax), dy = __dsub_rn(by, ay);
     const double len2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
@@ -253,8 +263,8 @@ __device__ __forceinline__ void sbc_delaunay_begin(DelaunayEdge &e, float xi, fl
     e.hi = INFINITY;
     e.ok = (len2 != 0.0);
 }
-__device__ __forceinline__ void sbc_delaunay_add(DelaunayEdge &e, float xk, float yk) {
-    const double qx = __dsub_rn((double)xk, e.mx), qy = __dsub_rn((double)yk, e.my);
+__device__ __forceinline__ void sbc_delaunay_add(DelaunayEdge &e, double xk, double yk) {
+    const double qx = __dsub_rn(xk, e.mx), qy = __dsub_rn(yk, e.my);
     const double c = __dsub_rn(__dadd_rn(__dmul_rn(qx, qx), __dmul_rn(qy, qy)), e.q4);
     const double s = __dadd_rn(__dmul_rn(qx, e.nx), __dmul_rn(qy, e.ny));
     if (s > 0.0) {

@@ -125,13 +125,13 @@ swarm_warp_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_fi
             }
             if (VOR) {  // keep only Delaunay neighbours of the row (warp-uniform loop over the tank)
                 DelaunayEdge e;
-                sbc_delaunay_begin(e, xi, yi, a.x, a.y);
+                sbc_delaunay_begin(e, xi, yi, sbc_vor_pos(xi, a.x, P), sbc_vor_pos(yi, a.y, P));
                 const unsigned alive_mask = __ballot_sync(FULL, alive);
                 const int seg0 = seg * TPS;
                 for (int k = 0; k < TPS; k++) {
                     const int lk = seg0 + k;
                     const float xk = __shfl_sync(FULL, a.x, lk), yk = __shfl_sync(FULL, a.y, lk);
-                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, xk, yk);
+                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, sbc_vor_pos(xi, xk, P), sbc_vor_pos(yi, yk, P));
                 }
                 if (z < 3 && !sbc_delaunay_end(e)) z = 3;
             }
@@ -292,14 +292,15 @@ swarm_warp_pred_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t
             }
             if (VOR) {  // keep only Delaunay neighbours of the row (warp-uniform loop over the tank)
                 DelaunayEdge e;
-                sbc_delaunay_begin(e, xi, yi, a.x, a.y);
+                sbc_delaunay_begin(e, xi, yi, sbc_vor_pos(xi, a.x, P), sbc_vor_pos(yi, a.y, P));
                 const unsigned alive_mask = __ballot_sync(FULL, alive);
                 const int seg0 = seg * TPS;
                 for (int k = 0; k < TPS; k++) {
                     const int lk = seg0 + k;
                     const float xk = __shfl_sync(FULL, a.x, lk), yk = __shfl_sync(FULL, a.y, lk);
-                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, xk, yk);
+                    if (((alive_mask >> lk) & 1u) && lk != src && lk != lane) sbc_delaunay_add(e, sbc_vor_pos(xi, xk, P), sbc_vor_pos(yi, yk, P));
                 }
+                if (pred_phase) sbc_delaunay_add(e, sbc_vor_pos(xi, pred.x, P), sbc_vor_pos(yi, pred.y, P));   // a vertex of F2FP's triangulation
                 if (z < 3 && !sbc_delaunay_end(e)) z = 3;
             }
             const int cr = __popc(__ballot_sync(FULL, z == 0) & segmask);
@@ -646,11 +647,16 @@ swarm_block_kernel(const __grid_constant__ DevParams P, DevState S, uint32_t s_f
                         if (j == row) z = 3;
                         if (P.voronoi && z < 3) {  // Delaunay edge test against every other agent of the swarm
                             DelaunayEdge e;
-                            sbc_delaunay_begin(e, pi.x, pi.y, pj.x, pj.y);
+                            sbc_delaunay_begin(e, pi.x, pi.y, sbc_vor_pos(pi.x, pj.x, P), sbc_vor_pos(pi.y, pj.y, P));
                             for (int kk = 0; kk < N; kk++) {
                                 const float4 pk = pv_s[kk];
-                                if (kk != row && kk != j && pk.x == pk.x) sbc_delaunay_add(e, pk.x, pk.y);
+                                if (kk != row && kk != j && pk.x == pk.x) sbc_delaunay_add(e, sbc_vor_pos(pi.x, pk.x, P), sbc_vor_pos(pi.y, pk.y, P));
                             }
+                            if (pred_phase)   // the predators are vertices of F2FP's triangulation (agents_interact.cpp:103-110)
+                                for (int q = 0; q < NP; q++) {
+                                    const float4 pq = S.pred_pv[(size_t)rep * NP + q];
+                                    sbc_delaunay_add(e, sbc_vor_pos(pi.x, pq.x, P), sbc_vor_pos(pi.y, pq.y, P));
+                                }
                             if (!sbc_delaunay_end(e)) z = 3;
                         }
                         const float rinv = rsqrtf(fmaxf(d2, 1e-30f));

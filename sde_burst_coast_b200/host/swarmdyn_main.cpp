@@ -10,8 +10,9 @@
 //                    seeds from the wall clock, swarmdyn.cpp:126-141; 0 or absent = clock)
 //   -y <replicates>  run an ensemble of independent swarms in one process (default 1); replicate r>0
 //                    writes its files with the suffix _<r> after fileID
-//   -V 1             Voronoi neighbour rule (InteractionVoronoiF2F, agents_interact.cpp:26-77, the shipped
-//                    default of the reference): tanks / open domains of up to 1024 agents without predators
+//   -V 1             Voronoi neighbour rule (InteractionVoronoiF2F / F2FP, agents_interact.cpp:26-141, the shipped
+//                    default of the reference): swarms of up to 1024 agents (DESIGN.md section 2 for the periodic
+//                    box and the predator phase)
 // Default neighbour rule: METRIC (InteractionGlobal, agents_interact.cpp:144-157) - see DESIGN.md section 2.
 // Output: -J 0 text files exactly as the reference writes them; -J 1 writes out_<fileID>.h5 with the
 // reference's datasets (/part, /pred, /swarm, /swarm_fishNet; under /<fileID>/ when fileID != "xx") through

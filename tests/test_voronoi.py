@@ -127,7 +127,87 @@ def test_gpu_voronoi_step_parity(N, R):
 @pytest.mark.gpu
 def test_voronoi_mode_rejected_where_not_implemented():
     from sde_burst_coast_b200.swarm import Swarm, SbcError
-    d = base_dict('natPred', 100, BC=0, size=100.0, Npred=0)
+    d = base_dict('natPred', 2000, BC=0, size=400.0, Npred=0)
     sp, _ = PP.make_sbc_params(d, neighbour_mode=PP.NEIGHBOUR_VORONOI)
     with pytest.raises(SbcError, match='Voronoi'):
-        Swarm(sp, 100)
+        Swarm(sp, 2000)
+
+
+def _vsp(mode, N, **over):
+    d = base_dict(mode, N, **over)
+    return PP.make_sbc_params(d, neighbour_mode=PP.NEIGHBOUR_VORONOI)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,L', [(30, 60.0), (200, 100.0), (700, 150.0)])
+def test_gpu_periodic_voronoi_neighbours_exact(N, L):
+    """Periodic box (InteractionVoronoiF2FP's tiling, agents_operation.cpp:240-293, as the well-defined nearest-image
+    triangulation): neighbour lists and zone counters of the CUDA kernels identical to the port's, and the edge set is
+    the Delaunay triangulation of the 3 x 3 tiled point set (scipy) wherever that one is unambiguous."""
+    from sde_burst_coast_b200.swarm import Swarm
+    sp, _ = _vsp('natPred', N, BC=0, size=L, Npred=0, alg_range=10.0)
+    rng = np.random.default_rng(N)
+    st = random_state(N, sp, rng)
+    w = pyorc.World(sp, N)
+    w.set_state(**st)
+    g = Swarm(sp, N)
+    g.set_state(**st)
+    ref, got = w.pair_interactions(1), g.pair_interactions(1)
+    for k in ('c_rep', 'c_alg', 'c_att', 'nn_ptr', 'nn_idx'):
+        assert np.array_equal(ref[k], got[k]), k
+    g.close()
+    w.close()
+    # independent check of the criterion: Qhull on the tiled set; an agent's metric neighbours that are Delaunay
+    # neighbours of one of its images must be exactly the port's list
+    from scipy.spatial import Delaunay
+    pts = np.stack([st['x'], st['y']], axis=1)
+    tiles = np.concatenate([pts + np.array([a * L, b * L]) for a in (-1, 0, 1) for b in (-1, 0, 1)])
+    tri = Delaunay(tiles)
+    indptr, indices = tri.vertex_neighbor_vertices
+    centre = 4 * N    # the (0, 0) tile
+    sets = nn_sets(ref, N)
+    for i in range(N):
+        nb = set(int(v) % N for v in indices[indptr[centre + i]:indptr[centre + i + 1]]) - {i}
+        dx = (pts[:, 0] - pts[i, 0] + L / 2) % L - L / 2
+        dy = (pts[:, 1] - pts[i, 1] + L / 2) % L - L / 2
+        near = set(np.where(np.hypot(dx, dy) <= sp.att_range)[0]) - {i}
+        assert set(sets[i]) == (nb & near), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('mode,N,npred,kill,move,L', [('natPred', 30, 1, 3, 1, 100.0), ('natPred', 200, 1, 1, 0, 100.0),
+                                                      ('mulFisher', 300, 20, 1, 0, 100.0)])
+def test_gpu_voronoi_predator_phase_matches_port(mode, N, npred, kill, move, L):
+    """Voronoi candidates in the predator phase (InteractionVoronoiF2FP, agents_interact.cpp:79-141): the predators are
+    vertices of the triangulation, both directions of an edge interact. CUDA kernels against the port on
+    the same states: the same agents die, timers bit-identical, one step within the FP32 tolerance."""
+    from sde_burst_coast_b200.swarm import Swarm
+    sp, np_ = _vsp(mode, N, BC=0, size=L, Npred=npred, pred_kill=kill, pred_move=move, pred_time=0.0, time=50.0,
+                   kill_rate=400.0, N_confu=500)
+    assert np_ == npred
+    rng = np.random.default_rng(N + kill)
+    st = random_state(N, sp, rng, spread=40.0)
+    st['bin_step'] = np.where(rng.random(N) < 0.4, sp.burst_steps, st['bin_step']).astype(np.uint32)
+    px = 45.0 + 0.5 * np.arange(npred, dtype=np.float64)
+    py, pphi = np.full(npred, 48.0), np.full(npred, np.pi / 2)
+    w = pyorc.World(sp, N, npred, seed=9)
+    g = Swarm(sp, N, npred, seed=9)
+    for o in (w, g):
+        o.set_state(**st)
+        o.set_predators(px, py, pphi, 1)
+    w.step(5, 1)
+    g.step(5, 1)
+    o, gs = w.get_state(), g.get_state()
+    assert np.array_equal(o['alive'], gs['alive'])
+    al = o['alive'] == 1
+    assert np.array_equal(o['bin_step'][al], gs['bin_step'][al]) and np.array_equal(o['steps_till_burst'][al], gs['steps_till_burst'][al])
+    ok = (np.abs(o['x'] - gs['x']) <= 1e-4) & (np.abs(o['y'] - gs['y']) <= 1e-4) & (ang_diff(o['phi'], gs['phi']) <= 1e-4)
+    assert ok[al].mean() > 0.97, ok[al].mean()
+    w.step(6, 300)
+    g.step(6, 300)
+    o, gs = w.get_state(), g.get_state()
+    al = (o['alive'] == 1) & (gs['alive'] == 1)
+    assert np.array_equal(o['steps_till_burst'][al], gs['steps_till_burst'][al])
+    assert abs(int(o['alive'].sum()) - int(gs['alive'].sum())) <= max(2, N // 20)   # trajectories diverge in FP32: kills agree in number
+    g.close()
+    w.close()
