@@ -335,6 +335,7 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
                                                  const int2 *__restrict__ list, int n_rows, int bid, int nblk, unsigned &n_amb,
                                                  unsigned &n_cand) {
     constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW, NB = 8;
+    __shared__ int s_first[GPB][9], s_pref[GPB][10];   // per row group: start of each cell's range, running candidate count
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / TPR, t = lane % TPR;
     const unsigned gmask = ((1u << TPR) - 1u) << (grp * TPR);
@@ -352,46 +353,66 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
         // travelled with the list entry unless the cell order was rebuilt since
         const int ck = !has ? 0 : ((SA.fresh_cells || e.y < 0) ? (int)build_key[i] : e.y);
         const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
-        int r0[2] = {0, 0}, r1[2] = {0, 0};
+        // The nine cell ranges of the row are laid end to end (lane t fetches the bounds of cell t, lane 0 also the ninth)
+        // and the candidates are dealt round-robin to the eight lanes: every lane sweeps total / 8 of them, whatever the
+        // single cells hold. (A lane per cell made every row of the warp wait for its fullest cell - twice the work.)
+        int *first = s_first[warp * GPW + grp], *pref = s_pref[warp * GPW + grp];
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const int tc = t + u * TPR;   // lane 0 owns cells 0 and 8
-            if (has && tc < 9) {
-                int yy = cy + tc / 3 - 1, xx = cx + tc % 3 - 1;
-                bool ok = true;
-                if (PERIODIC) {
-                    yy += (yy < 0) ? g.ncy : 0; yy -= (yy >= g.ncy) ? g.ncy : 0;
-                    xx += (xx < 0) ? g.ncx : 0; xx -= (xx >= g.ncx) ? g.ncx : 0;
-                } else {
-                    ok = yy >= 0 && yy < g.ncy && xx >= 0 && xx < g.ncx;
+            const int tc = t + u * TPR;
+            if (tc < 9) {
+                int c0 = 0, c1 = 0;
+                if (has) {
+                    int yy = cy + tc / 3 - 1, xx = cx + tc % 3 - 1;
+                    bool ok = true;
+                    if (PERIODIC) {
+                        yy += (yy < 0) ? g.ncy : 0; yy -= (yy >= g.ncy) ? g.ncy : 0;
+                        xx += (xx < 0) ? g.ncx : 0; xx -= (xx >= g.ncx) ? g.ncx : 0;
+                    } else {
+                        ok = yy >= 0 && yy < g.ncy && xx >= 0 && xx < g.ncx;
+                    }
+                    if (ok) {
+                        const int2 cr = cell_range[yy * g.ncx + xx];
+                        c0 = cr.x;
+                        c1 = cr.y;
+                    }
                 }
-                if (ok) {
-                    const int2 cr = cell_range[yy * g.ncx + xx];
-                    r0[u] = cr.x;
-                    r1[u] = cr.y;
-                }
+                first[tc] = c0;
+                pref[tc + 1] = c1 - c0;
             }
         }
+        __syncwarp();
+        if (t == 0) {
+            int run = 0;
+            pref[0] = 0;
+#pragma unroll
+            for (int c = 0; c < 9; c++) { run += pref[c + 1]; pref[c + 1] = run; }
+        }
+        __syncwarp();
+        const int total = pref[9];
+        if (t == 0) n_cand += (unsigned)total;
         RowAcc A;
         row_acc_clear(A);
+        for (int qb = t; qb < total; qb += TPR * NB) {
+            int jj[NB];
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            n_cand += (unsigned)(r1[u] - r0[u]);
-            for (int r = r0[u]; r < r1[u]; r += NB) {
-                int jj[NB];
+            for (int b = 0; b < NB; b++) {
+                const int q = qb + b * TPR;
+                int c = 0;
 #pragma unroll
-                for (int b = 0; b < NB; b++) jj[b] = (r + b < r1[u]) ? sidx[r + b] : -1;
-                if (EDGE) sbc_wait_ghosts(SA, step);
+                for (int kk = 1; kk < 9; kk++) c += (q >= pref[kk]) ? 1 : 0;
+                jj[b] = (q < total) ? sidx[first[c] + (q - pref[c])] : -1;
+            }
+            if (EDGE) sbc_wait_ghosts(SA, step);
 #pragma unroll
-                for (int h = 0; h < NB; h += 4) {
-                    float4 pj[4];
+            for (int h = 0; h < NB; h += 4) {
+                float4 pj[4];
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
-                        pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
-                                : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
+                for (int b = 0; b < 4; b++)
+                    pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
+                            : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
 #pragma unroll
-                    for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
-                }
+                for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
             }
         }
         A.c_rep = __reduce_add_sync(gmask, A.c_rep);
@@ -678,7 +699,9 @@ bool sbc_pair_cells_lanes(const DevParams &P, const DevState &S, const CellScrat
 int sbc_pair_cells_blocks(const DevParams &P, const DevState &S, const CellScratch &C) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const size_t cap = (size_t)sms * (cells_warp_rows(P, S, C) ? 4 : 2);
+    int per_sm = cells_warp_rows(P, S, C) ? 4 : 2;
+    if (const char *e = getenv("SBC_ROWS_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0 && v <= 8) per_sm = v; }   // tuning runs
+    const size_t cap = (size_t)sms * per_sm;
     return (int)min(cap, max((size_t)16, (size_t)S.N / 64));
 }
 
