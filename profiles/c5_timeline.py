@@ -49,6 +49,11 @@ def main():
            'rows_last_block_start_us': float(np.median(tr[steps, 4, 1] - t0)) / 1e3,
            'bulk_last_block_start_us': float(np.median(tr[steps, 5, 1] - t0)) / 1e3,
            'busy_us': float(np.median(t1 - t0)) / 1e3, 'gap_to_next_step_us': float(np.median(t0[1:] - t1[:-1])) / 1e3}
+    # phase marks of the rows kernel (celllist.cu, cells_phase_mark): the latest warp past each phase
+    for name, slot in (('rows_bounds_in_us', 2), ('rows_sweep_done_us', 3), ('rows_reduced_us', 6), ('rows_updated_us', 7)):
+        v = tr[steps, slot, 1]
+        if (v > 0).any():
+            out[name] = float(np.median((v - t0)[v > 0])) / 1e3
     long = period[period > 2 * np.median(period)]
     out['long_periods'] = int(long.size)
     out['long_period_mean_us'] = float(long.mean()) / 1e3 if long.size else 0.0

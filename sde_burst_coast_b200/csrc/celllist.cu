@@ -119,12 +119,36 @@ __global__ void cell_scatter_kernel(const uint32_t *__restrict__ key, int n, uin
     if (k == dead_key) return;
     sidx[start[k] + atomicSub(cnt + k, 1) - 1] = i;
 }
+// cell bounds + the agents of every cell in ascending id order (the scatter's order depends on the atomics' timing; sums
+// must not). A cell of up to eight agents is fetched at once, sorted in registers by a 19-comparator network and
+// written back: two memory round trips per cell instead of a dependent load/store chain per element (37 -> 9 us per
+// build at C5 size).
 __global__ void cell_finish_kernel(int ncells, const int *__restrict__ start, int *__restrict__ sidx, int2 *__restrict__ cell_range) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncells) return;
     const int r0 = start[c], r1 = start[c + 1];
     cell_range[c] = make_int2(r0, r1);
-    for (int a = r0 + 1; a < r1; a++) {   // insertion sort of a handful of indices
+    const int n = r1 - r0;
+    if (n < 2) return;
+    if (n <= 8) {
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (k < n) ? sidx[r0 + k] : 0x7fffffff;
+#define SBC_CSWAP(a, b) { const int lo = min(v[a], v[b]), hi = max(v[a], v[b]); v[a] = lo; v[b] = hi; }
+        SBC_CSWAP(0, 1) SBC_CSWAP(2, 3) SBC_CSWAP(4, 5) SBC_CSWAP(6, 7)
+        SBC_CSWAP(0, 2) SBC_CSWAP(1, 3) SBC_CSWAP(4, 6) SBC_CSWAP(5, 7)
+        SBC_CSWAP(1, 2) SBC_CSWAP(5, 6) SBC_CSWAP(0, 4) SBC_CSWAP(3, 7)
+        SBC_CSWAP(1, 5) SBC_CSWAP(2, 6)
+        SBC_CSWAP(1, 4) SBC_CSWAP(3, 6)
+        SBC_CSWAP(2, 4) SBC_CSWAP(3, 5)
+        SBC_CSWAP(3, 4)
+#undef SBC_CSWAP
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (k < n) sidx[r0 + k] = v[k];
+        return;
+    }
+    for (int a = r0 + 1; a < r1; a++) {   // fuller cells: insertion sort in place
         const int v = sidx[a];
         int b = a - 1;
         while (b >= r0 && sidx[b] > v) { sidx[b + 1] = sidx[b]; b--; }
@@ -267,7 +291,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
             cells_row_store(S, i, A);
             if (SA.finish) {
                 if (SA.pred_active) { A.flee_x = s_flee[0]; A.flee_y = s_flee[1]; A.c_flee = s_cflee; }
-                sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
+                sbc_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
             }
         }
         __syncthreads();   // pref / first are rewritten by the next row
@@ -318,9 +342,19 @@ __device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, 
 // The row's own update, NOT inlined: the interior and the edge blocks of the lanes kernel must run the very same
 // instructions - an inlined copy per call site may contract floating-point expressions differently, and a row's
 // result must not depend on which list it was on. (P, S, A are __grid_constant__ kernel parameters: no copies.)
+template <int BCT>
 static __device__ __noinline__ void cells_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc,
                                                      const RowState &r, uint32_t step, const StepArgs &A) {
-    sbc_finish_row(P, S, g, acc, r, step, A);
+    sbc_finish_row<BCT>(P, S, g, acc, r, step, A);
+}
+
+// profiling hook (sbc_debug_trace, undecomposed swarms only - the slots are the exchange's otherwise): the LATEST moment
+// any warp of the step's rows kernel passed a phase of its dependent chain. Entry 1 of slot 2: row positions and cell
+// bounds have arrived; slot 3: candidate indices and positions have arrived and the sweep is done; slot 6: reductions
+// done; slot 7: the rows are updated.
+__device__ __forceinline__ void cells_phase_mark(const DevState &S, const StepArgs &SA, uint32_t step, int slot, int lane) {
+    if (!S.trace || SA.halo_idx || lane != 0) return;
+    atomicMax(S.trace + ((size_t)(step % SBC_TRACE_STEPS) * SBC_TR_KERNELS + slot) * 2 + 1, sbc_now_ns());
 }
 
 // One pass of a group of eight lanes over the rows of `list`: lane t walks cell t of the row's 3 x 3 block (lane 0 also
@@ -390,6 +424,7 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
         }
         __syncwarp();
         const int total = pref[9];
+        if (!EDGE) cells_phase_mark(S, SA, step, 2, lane);
         if (t == 0) n_cand += (unsigned)total;
         RowAcc A;
         row_acc_clear(A);
@@ -415,6 +450,7 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
                 for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
             }
         }
+        if (!EDGE) cells_phase_mark(S, SA, step, 3, lane);
         A.c_rep = __reduce_add_sync(gmask, A.c_rep);
         A.c_alg = __reduce_add_sync(gmask, A.c_alg);
         A.c_att = __reduce_add_sync(gmask, A.c_att);
@@ -424,11 +460,13 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
             A.alg_x += __shfl_xor_sync(0xffffffffu, A.alg_x, o); A.alg_y += __shfl_xor_sync(0xffffffffu, A.alg_y, o);
             A.att_x += __shfl_xor_sync(0xffffffffu, A.att_x, o); A.att_y += __shfl_xor_sync(0xffffffffu, A.att_y, o);
         }
+        if (!EDGE) cells_phase_mark(S, SA, step, 6, lane);
         if (t == 0 && has) {
             cells_row_store(S, i, A);
-            if (SA.finish) cells_finish_row(P, S, (size_t)i, A, rs, step, SA);
+            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
         }
         __syncwarp();
+        if (!EDGE) cells_phase_mark(S, SA, step, 7, lane);
     }
 }
 
@@ -503,7 +541,7 @@ __device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const D
         }
         if (lane == 0) {
             cells_row_store(S, i, A);
-            if (SA.finish) cells_finish_row(P, S, (size_t)i, A, rs, step, SA);
+            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
         }
         __syncwarp();
     }
@@ -586,7 +624,7 @@ pair_cells_warp_kernel(const __grid_constant__ DevParams P, DevState S, const Ce
         if (lane == 0) cells_row_store(S, i, A);
         __syncwarp();
         if (SA.pred_active) sbc_detect_row_warp(P, S, (size_t)i, S.pv[i], step, lane, A);
-        if (SA.finish && lane == 0) sbc_finish_row(P, S, (size_t)i, A, rs, step, SA);
+        if (SA.finish && lane == 0) sbc_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
         __syncwarp();
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);

@@ -16,6 +16,7 @@
 
 namespace {
 
+template <int BCT>   // 0: periodic box, known at compile time (sbc_update_agent); SBC_BC_RUNTIME otherwise
 __global__ void __launch_bounds__(256)
 update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) {
     const uint32_t step = sbc_step_of(A);
@@ -69,7 +70,7 @@ update_bulk_kernel(const __grid_constant__ DevParams P, DevState S, StepArgs A) 
     if (mine) {
         RowAcc acc;
         row_acc_clear(acc);
-        sbc_update_agent(P, S, g, acc, tm, p, hv, f, step, A);
+        sbc_update_agent<BCT>(P, S, g, acc, tm, p, hv, f, step, A);
     }
     if (m) {
         base = __shfl_sync(0xffffffffu, base, 0);
@@ -154,7 +155,9 @@ __global__ void refresh_cs_kernel(DevState S) {
 int sbc_update_bulk_blocks(int n_update) { return (n_update + 255) / 256; }
 
 void sbc_launch_update_bulk(const DevParams &P, const DevState &S, const StepArgs &A, cudaStream_t st) {
-    update_bulk_kernel<<<(unsigned)sbc_update_bulk_blocks(A.n_update), 256, 0, st>>>(P, S, A);
+    const unsigned blocks = (unsigned)sbc_update_bulk_blocks(A.n_update);
+    if (P.BC == 0) update_bulk_kernel<0><<<blocks, 256, 0, st>>>(P, S, A);
+    else update_bulk_kernel<SBC_BC_RUNTIME><<<blocks, 256, 0, st>>>(P, S, A);
 }
 
 // compact the rows that start a burst (or, all_alive, every alive agent) of slots [0, n_scan) into list / count
