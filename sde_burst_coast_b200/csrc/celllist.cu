@@ -304,7 +304,7 @@ pair_cells_kernel(const __grid_constant__ DevParams P, DevState S, const CellGeo
 }
 
 // one candidate of a row: zone decision as on the all-pairs path (FP32 band + FP64 re-decision), accumulation
-template <bool PERIODIC>
+template <bool PERIODIC, bool ALG = true>
 __device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, const float4 pj, RowAcc &A, unsigned &n_amb) {
     float dx = pj.x - pi.x, dy = pj.y - pi.y;
     if (PERIODIC) {
@@ -323,7 +323,7 @@ __device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, 
         A.rep_x = __fmaf_rn(-dx, rinv, A.rep_x);
         A.rep_y = __fmaf_rn(-dy, rinv, A.rep_y);
         A.c_rep++;
-    } else if (z == 1) {
+    } else if (ALG && z == 1) {   // (!ALG: alg_range == rep_range, the zone is empty and pj carries no velocity)
         A.alg_x += pj.z;
         A.alg_y += pj.w;
         A.c_alg++;
@@ -343,9 +343,19 @@ __device__ __forceinline__ void cells_pair(const DevParams &P, const float4 pi, 
 // instructions - an inlined copy per call site may contract floating-point expressions differently, and a row's
 // result must not depend on which list it was on. (P, S, A are __grid_constant__ kernel parameters: no copies.)
 template <int BCT>
+// The row's own state is asked for twice: a prefetch into L1 when the row is picked up (no register is held through the
+// sweep - ten registers kept alive there were spilled, and a spill store waits for its load right where it is issued),
+// the loads themselves here, after the sweep.
 static __device__ __noinline__ void cells_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc,
-                                                     const RowState &r, uint32_t step, const StepArgs &A) {
+                                                     uint32_t step, const StepArgs &A) {
+    const RowState r = sbc_row_prefetch(S, g);
     sbc_finish_row<BCT>(P, S, g, acc, r, step, A);
+}
+__device__ __forceinline__ void cells_row_touch(const DevState &S, size_t g) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.tm + g));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.hv + g));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.force + g));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.alive + g));
 }
 
 // profiling hook (sbc_debug_trace, undecomposed swarms only - the slots are the exchange's otherwise): the LATEST moment
@@ -362,7 +372,7 @@ __device__ __forceinline__ void cells_phase_mark(const DevState &S, const StepAr
 // so the dependent chain of a row is list -> (key) -> cell bounds -> indices -> positions whatever the cell holds.
 // EDGE: the rows next to a slab edge of a decomposed swarm - everything up to the indices goes on while the ghosts
 // are on their way; the group holds right before it reads positions (past L1: the exchange writes them meanwhile).
-template <bool PERIODIC, bool EDGE>
+template <bool PERIODIC, bool EDGE, bool ALG>
 __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevState &S, const CellGeom &g,
                                                  const int2 *__restrict__ cell_range, const uint32_t *__restrict__ build_key,
                                                  const int *__restrict__ sidx, const StepArgs &SA, uint32_t step,
@@ -380,8 +390,7 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
         const bool has = k < n_rows;
         const int2 e = has ? list[k] : make_int2(0, 0);
         const int i = e.x;
-        RowState rs = {};
-        if (SA.finish && t == 0 && has) rs = sbc_row_prefetch(S, (size_t)i);
+        if (SA.finish && t == 0 && has) cells_row_touch(S, (size_t)i);
         const float4 pi = has ? S.pv[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         // the row's cell at build time (agents alive now were alive then: nobody is born between builds); the key
         // travelled with the list entry unless the cell order was rebuilt since
@@ -439,15 +448,29 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
                 jj[b] = (q < total) ? sidx[first[c] + (q - pref[c])] : -1;
             }
             if (EDGE) sbc_wait_ghosts(SA, step);
+            if (!ALG) {
+                // no alignment zone (alg_range == rep_range: natPred, the default tank): only the candidates' POSITIONS
+                // are read - eight bytes each, all eight of a lane in flight at once (one round trip per pass; with the
+                // velocities the registers allow four at a time, i.e. two)
+                float2 qj[NB];
 #pragma unroll
-            for (int h = 0; h < NB; h += 4) {
-                float4 pj[4];
+                for (int b = 0; b < NB; b++) {
+                    const float2 *src = reinterpret_cast<const float2 *>(S.pv + (jj[b] >= 0 ? jj[b] : 0));
+                    qj[b] = !(jj[b] >= 0 && jj[b] != i) ? make_float2(qnan, qnan) : EDGE ? __ldcg(src) : *src;
+                }
 #pragma unroll
-                for (int b = 0; b < 4; b++)
-                    pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
-                            : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
+                for (int b = 0; b < NB; b++) cells_pair<PERIODIC, false>(P, pi, make_float4(qj[b].x, qj[b].y, 0.f, 0.f), A, n_amb);
+            } else {
 #pragma unroll
-                for (int b = 0; b < 4; b++) cells_pair<PERIODIC>(P, pi, pj[b], A, n_amb);
+                for (int h = 0; h < NB; h += 4) {
+                    float4 pj[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
+                                : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) cells_pair<PERIODIC, true>(P, pi, pj[b], A, n_amb);
+                }
             }
         }
         if (!EDGE) cells_phase_mark(S, SA, step, 3, lane);
@@ -463,7 +486,7 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
         if (!EDGE) cells_phase_mark(S, SA, step, 6, lane);
         if (t == 0 && has) {
             cells_row_store(S, i, A);
-            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
+            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, step, SA);
         }
         __syncwarp();
         if (!EDGE) cells_phase_mark(S, SA, step, 7, lane);
@@ -488,8 +511,7 @@ __device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const D
     for (int k = bid * WPB + warp; k < n_rows; k += nblk * WPB) {
         const int2 e = list[k];
         const int i = e.x;
-        RowState rs = {};
-        if (SA.finish && lane == 0) rs = sbc_row_prefetch(S, (size_t)i);
+        if (SA.finish && lane == 0) cells_row_touch(S, (size_t)i);
         const float4 pi = S.pv[i];
         const int ck = (SA.fresh_cells || e.y < 0) ? (int)build_key[i] : e.y;
         const int cy = ck / g.ncx, cx = ck - cy * g.ncx;
@@ -541,7 +563,7 @@ __device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const D
         }
         if (lane == 0) {
             cells_row_store(S, i, A);
-            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, rs, step, SA);
+            if (SA.finish) cells_finish_row<PERIODIC ? 0 : SBC_BC_RUNTIME>(P, S, (size_t)i, A, step, SA);
         }
         __syncwarp();
     }
@@ -552,8 +574,11 @@ __device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const D
 // Decomposed swarm: the last SA.edge_blocks blocks of the grid take the rows next to a slab edge (listed apart by
 // whoever re-armed them); with GHOSTS they wait for the exchange that runs beside this kernel. The other blocks never
 // see a ghost and never wait.
-template <bool PERIODIC, bool GHOSTS>
-__global__ void __launch_bounds__(CELLS_THREADS, 8)   // 64 registers: the whole grid is resident on a quarter of the register file
+template <bool PERIODIC, bool GHOSTS, bool ALG>
+#ifndef SBC_ROWS_MINB
+#define SBC_ROWS_MINB 8   // 64 registers: the whole grid is resident on a quarter of the register file
+#endif
+__global__ void __launch_bounds__(CELLS_THREADS, SBC_ROWS_MINB)
 pair_cells_lanes_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
                         const CellGeom *__restrict__ geom, const int2 *__restrict__ cell_range,
                         const uint32_t *__restrict__ build_key, const int *__restrict__ sidx,
@@ -567,7 +592,7 @@ pair_cells_lanes_kernel(const __grid_constant__ DevParams P, const __grid_consta
     unsigned n_amb = 0, n_cand = 0;
     if (!edge_part) {
         sbc_trace(S, step, SBC_TR_ROWS, true);
-        cells_lanes_rows<PERIODIC, false>(P, S, g, cell_range, build_key, sidx, SA, step, S.active_list[par], S.active_count[par],
+        cells_lanes_rows<PERIODIC, false, ALG>(P, S, g, cell_range, build_key, sidx, SA, step, S.active_list[par], S.active_count[par],
                                           (int)blockIdx.x, n_main, n_amb, n_cand);
     } else if (GHOSTS) {
         if (S.trace && threadIdx.x == 0)
@@ -575,7 +600,7 @@ pair_cells_lanes_kernel(const __grid_constant__ DevParams P, const __grid_consta
         cells_warp_edge_rows<PERIODIC>(P, S, g, cell_range, build_key, sidx, SA, step, S.edge_list[par], S.active_count[4 + par],
                                        (int)blockIdx.x - n_main, SA.edge_blocks, n_amb, n_cand);
     } else {
-        cells_lanes_rows<PERIODIC, false>(P, S, g, cell_range, build_key, sidx, SA, step, S.edge_list[par], S.active_count[4 + par],
+        cells_lanes_rows<PERIODIC, false, ALG>(P, S, g, cell_range, build_key, sidx, SA, step, S.edge_list[par], S.active_count[4 + par],
                                           (int)blockIdx.x - n_main, SA.edge_blocks, n_amb, n_cand);
     }
     n_amb = __reduce_add_sync(0xffffffffu, n_amb);
@@ -751,8 +776,10 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
     if (P.BC == 0) {
         if (cells_warp_rows(P, S, C)) {
             if (A.pred_active) sbc_launch_prio(pair_cells_warp_kernel<true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
-            else if (A.ghost_ready) sbc_launch_prio(pair_cells_lanes_kernel<true, true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
-            else sbc_launch_prio(pair_cells_lanes_kernel<true, false>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else if (A.ghost_ready && P.has_alg_zone) sbc_launch_prio(pair_cells_lanes_kernel<true, true, true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else if (A.ghost_ready) sbc_launch_prio(pair_cells_lanes_kernel<true, true, false>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else if (P.has_alg_zone) sbc_launch_prio(pair_cells_lanes_kernel<true, false, true>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
+            else sbc_launch_prio(pair_cells_lanes_kernel<true, false, false>, blocks, CELLS_THREADS, 0, st, SBC_CELLS_ARGS);
         } else {
             sbc_launch_prio(pair_cells_kernel<true>, blocks, CELLS_BLOCK_THREADS, 0, st, SBC_CELLS_ARGS);
         }
@@ -765,7 +792,9 @@ void sbc_launch_pair_cells(const DevParams &P, const DevState &S, CellScratch &C
 void sbc_cells_preload(void) {
     cudaFuncAttributes fa;
     cudaFuncGetAttributes(&fa, pair_cells_warp_kernel<true>);
-    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, true>);
-    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, false>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, true, true>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, true, false>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, false, true>);
+    cudaFuncGetAttributes(&fa, pair_cells_lanes_kernel<true, false, false>);
     cudaFuncGetAttributes(&fa, pair_cells_kernel<true>);
 }

@@ -337,11 +337,14 @@ template <int BCT = SBC_BC_RUNTIME>
 __device__ __forceinline__ void sbc_finish_row(const DevParams &P, const DevState &S, size_t g, const RowAcc &acc, const RowState &r,
                                                uint32_t step, const StepArgs &A) {
     if (!r.al) return;   // killed after it was listed
-    int at = -1;
+    int at = -1, key = 0;
+    bool edge = false;
     const int nxt = (int)((step + 1u) % 3u);
-    const int key = S.cell_key ? (int)S.cell_key[g] : 0;   // (this kernel runs behind the cell build, if there was one)
-    const bool edge = sbc_edge_cell(key, A);
-    if (sbc_will_rearm(r.tm, P)) at = atomicAdd(S.active_count + nxt + (edge ? 4 : 0), 1);
+    if (sbc_will_rearm(r.tm, P)) {   // rare for a row (it re-armed one step ago): the key's round trip only then
+        key = S.cell_key ? (int)S.cell_key[g] : 0;   // (this kernel runs behind the cell build, if there was one)
+        edge = sbc_edge_cell(key, A);
+        at = atomicAdd(S.active_count + nxt + (edge ? 4 : 0), 1);
+    }
     sbc_update_agent<BCT>(P, S, g, acc, r.tm, r.p, r.hv, r.f, step, A);
     // (an agent the net caught this step is dropped by the next rows kernel)
     if (at >= 0) (edge ? S.edge_list : S.active_list)[nxt][at] = make_int2((int)g, key);
