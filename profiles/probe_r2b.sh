@@ -1,7 +1,6 @@
 #!/bin/bash
-# A/B of builds of the rows kernel (register budget): in-situ timeline and C5 step time
+# final-state check on two GPUs: multi-GPU parity tests, timeline of the decomposed swarm, timeline of the undecomposed one
 O=gpurun_out
-for v in "" sde_burst_coast_b200/lib/variants/libsbc_rows6.so sde_burst_coast_b200/lib/variants/libsbc_rows5.so; do
-  echo "lib=$v: $(SBC_LIB_PATH=$v python profiles/c5_timeline.py 2>&1 | tail -1)"
-  echo "lib=$v: $(SBC_LIB_PATH=$v python profiles/bench_c5.py --steps 400 --warmup 60 2>/dev/null | tail -1 | python -c "import json,sys; print(json.loads(sys.stdin.read())['us_per_step'])")"
-done > $O/p7_rows_regs.txt
+timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_domain.py -m gpu -q -x 2>&1 | tail -3 > $O/p8_tests.txt
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 profiles/domain_timeline.py > $O/p8_domain_timeline.txt 2>/dev/null
+python profiles/c5_timeline.py > $O/p8_c5_timeline.txt 2>&1

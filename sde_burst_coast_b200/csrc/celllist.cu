@@ -378,7 +378,14 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
                                                  const int *__restrict__ sidx, const StepArgs &SA, uint32_t step,
                                                  const int2 *__restrict__ list, int n_rows, int bid, int nblk, unsigned &n_amb,
                                                  unsigned &n_cand) {
-    constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW, NB = 8;
+    // candidates a lane takes per pass: one pass covers 8 lanes x NB of them. A second pass is two more memory round trips
+// for the whole warp, and the kernel ends with its slowest warp: at rho = 0.01 a row meets 52 +- 7 candidates, 80 cover
+// all but one row in ten thousand (64 left one warp in six with a second pass). The order of a lane's sum does not depend
+// on NB (candidate q always goes to lane q mod 8).
+#ifndef SBC_ROWS_NB
+#define SBC_ROWS_NB 10
+#endif
+    constexpr int TPR = 8, WPB = CELLS_THREADS / 32, GPW = 32 / TPR, GPB = WPB * GPW, NB = SBC_ROWS_NB;
     __shared__ int s_first[GPB][9], s_pref[GPB][10];   // per row group: start of each cell's range, running candidate count
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / TPR, t = lane % TPR;
@@ -466,10 +473,12 @@ __device__ __forceinline__ void cells_lanes_rows(const DevParams &P, const DevSt
                     float4 pj[4];
 #pragma unroll
                     for (int b = 0; b < 4; b++)
-                        pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
-                                : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
+                        if (h + b < NB)
+                            pj[b] = !(jj[h + b] >= 0 && jj[h + b] != i) ? make_float4(qnan, qnan, 0.f, 0.f)
+                                    : EDGE ? __ldcg(S.pv + jj[h + b]) : S.pv[jj[h + b]];
 #pragma unroll
-                    for (int b = 0; b < 4; b++) cells_pair<PERIODIC, true>(P, pi, pj[b], A, n_amb);
+                    for (int b = 0; b < 4; b++)
+                        if (h + b < NB) cells_pair<PERIODIC, true>(P, pi, pj[b], A, n_amb);
                 }
             }
         }
@@ -575,8 +584,11 @@ __device__ __forceinline__ void cells_warp_edge_rows(const DevParams &P, const D
 // whoever re-armed them); with GHOSTS they wait for the exchange that runs beside this kernel. The other blocks never
 // see a ghost and never wait.
 template <bool PERIODIC, bool GHOSTS, bool ALG>
+// Register budget of the rows kernel: 80 (six resident blocks at most). Only the ~2 blocks per SM that carry rows stay -
+// a third of the register file; the others exit at once. At 64 registers the sweep spilled (A/B on one GPU, C5: rows
+// kernel done after 20.5 us at 64 registers, 19.3 at 80; with ten candidates per lane and pass 18.2 / 16.9).
 #ifndef SBC_ROWS_MINB
-#define SBC_ROWS_MINB 8   // 64 registers: the whole grid is resident on a quarter of the register file
+#define SBC_ROWS_MINB 6
 #endif
 __global__ void __launch_bounds__(CELLS_THREADS, SBC_ROWS_MINB)
 pair_cells_lanes_kernel(const __grid_constant__ DevParams P, const __grid_constant__ DevState S,
