@@ -856,7 +856,7 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
     }
     const bool graphable = h->use_graphs && !injected && !S.flags && h->stream != nullptr && h->stream != cudaStreamLegacy &&
                            h->stream != cudaStreamPerThread;  // the default streams cannot be captured
-    if (count > 1 && (!graphable || rebuild)) return fail(h, SBC_ERR_STATE, "mk_step: a batch needs graph replay and no cell build");
+    if (count > 1 && !graphable) return fail(h, SBC_ERR_STATE, "mk_step: a batch needs graph replay");
     if (graphable) {
         if (!h->step_dev) SBC_CUDA(dev_alloc(&h->step_dev, 1));
         if (h->step_dev_value != s) {   // the step index lives on the device and is advanced by the step itself
@@ -872,7 +872,8 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
             DevState Sc = S;
             for (int k = 0; k < count; k++) {
                 A.step = (uint32_t)k;   // offset inside the launch; the base lives in *step_dev
-                record_step(h, Sc, key, A, h->stream, h->stream2, h->stream3);
+                A.fresh_cells = (rebuild && k == 0) ? 1 : 0;   // only the first step of a batch may build the cell order
+                record_step(h, Sc, k == 0 ? key : (key & ~(unsigned)MK_REBUILD), A, h->stream, h->stream2, h->stream3);
                 std::swap(Sc.pv, Sc.pv_nxt);
                 std::swap(Sc.tm, Sc.tm_nxt);
             }
@@ -912,16 +913,29 @@ static int mk_step(sbc_handle *h, int64_t s, bool pred_phase, bool xchg_first, i
     return SBC_OK;
 }
 
-// how many of the next `want` steps can go into one graph launch: no cell build among them
-static int mk_batch(const sbc_handle *h, int64_t want) {
+// how many of the next steps can go into one graph launch: a build of the cell order may head a batch, none falls
+// inside it. (A launch gap costs about a fifth of a step, and the kernels of consecutive steps follow each other faster
+// inside a graph: 2.6 us between two steps at four per launch, 1.3 at eight.) Every batch size is a graph of its own
+// (about a millisecond to capture and instantiate), so only a few sizes are used: a whole cycle of the cell order (the
+// build and every step it serves; in a decomposed swarm the steps between the build and the next full exchange), else
+// a power of two. `limit`: the largest size the caller can use.
+static int mk_batch(const sbc_handle *h, int64_t limit) {
     if (!h->use_graphs || h->S.flags || h->S.inj_social || h->S.inj_dir || h->S.inj_k) return 1;
     if (h->stream == nullptr || h->stream == cudaStreamLegacy || h->stream == cudaStreamPerThread) return 1;
-    int64_t room = want;
+    static int cap = 0;
+    if (!cap) { cap = 32; if (const char *e = std::getenv("SBC_MAX_BATCH")) cap = std::max(1, atoi(e)); }   // (tuning runs)
+    int64_t room = std::min<int64_t>(limit, cap);
     if (h->use_cells) {
-        if (!h->cells_ready || !h->cells_valid || h->cells_age > h->cells_max_age) return 1;   // this step rebuilds
-        room = std::min<int64_t>(room, (int64_t)h->cells_max_age - h->cells_age + 1);
+        if (!h->cells_ready) return 1;
+        const bool rebuild = !h->cells_valid || h->cells_age > h->cells_max_age;   // this step rebuilds: age 0 again
+        room = std::min<int64_t>(room, (int64_t)h->cells_max_age - (rebuild ? 0 : h->cells_age) + 1);
+        const int cycle = h->cells_max_age + 1;
+        if (rebuild && room >= cycle) return cycle;
+        if (h->dom.enabled && !rebuild && h->cells_age == 1 && room >= cycle - 2 && cycle > 3) return cycle - 2;
     }
-    return room >= 4 ? 4 : 1;
+    for (int b = 16; b > 1; b >>= 1)
+        if (room >= b) return b;
+    return 1;
 }
 
 // CreatePredator / CreateFishNet at step s (slot 0: first spawn, 1: the net's periodic re-creation)
@@ -1019,16 +1033,20 @@ int sbc_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
                     h->host_stats[7]++;
                 }
             }
-            // plain steps go four to a graph launch: none of them spawns (the spawn kernels above are launched eagerly)
+            // plain steps go up to eight to a graph launch: none of them spawns (the spawn kernels above are launched
+            // eagerly); a batch that would hold a spawn or a change of phase is halved until it does not
             int count = mk_batch(h, s_first + n_steps - s);
-            if (count > 1 && S.Npred > 0) {
-                for (int k = 1; k < count; k++) {
+            while (count > 1 && S.Npred > 0) {
+                bool clean = true;
+                for (int k = 1; k < count && clean; k++) {
                     const int64_t sk = s + k;
                     const bool ph = (double)sk >= p.pred_time / dt;
                     const bool spawn0 = ph && (double)(sk - 1) < p.pred_time / dt;
                     const bool spawn1 = S.Npred > 1 && ph && needed > 0 && ((int)sk - (int)(p.pred_time / dt)) % needed == 0;
-                    if (ph != pred_phase || spawn0 || spawn1) { count = 1; break; }
+                    if (ph != pred_phase || spawn0 || spawn1) clean = false;
                 }
+                if (clean) break;
+                count = mk_batch(h, count - 1);
             }
             if (int rc = mk_step(h, s, pred_phase, false, count)) return rc;
             s += count - 1;
@@ -1562,11 +1580,17 @@ int sbc_domain_step(sbc_handle *h, int64_t s_first, int64_t n_steps) {
         if (sched.spawn1(s, npred)) { launch_spawn(h, s, 1); h->host_stats[7]++; }
         // the exchange behind this step is a full one when the NEXT step rebuilds the cell order
         const bool rebuild_now = !h->cells_valid || h->cells_age > h->cells_max_age;
-        // four refresh steps in one graph launch when none of them ends in a full exchange
+        // the refresh steps up to the next full exchange in one graph launch
         int count = pending ? mk_batch(h, s_first + n_steps - s) : 1;
-        if (count > 1 && h->cells_age + count > h->cells_max_age) count = 1;
-        for (int k = 0; k < count && count > 1; k++)   // a batch holds steps of one kind, none of which (re)creates a predator
-            if (sched.phase(s + k) != pred_phase || sched.spawn0(s + k) || sched.spawn1(s + k, npred)) count = 1;
+        // (the step that ends in a full exchange goes alone; a step that rebuilds the cell order heads no batch here)
+        if (count > 1) count = rebuild_now ? 1 : mk_batch(h, std::min<int64_t>(count, h->cells_max_age - h->cells_age));
+        while (count > 1) {   // a batch holds steps of one kind, none of which (re)creates a predator: halved until it does
+            bool clean = true;
+            for (int k = 0; k < count && clean; k++)
+                if (sched.phase(s + k) != pred_phase || sched.spawn0(s + k) || sched.spawn1(s + k, npred)) clean = false;
+            if (clean) break;
+            count = mk_batch(h, count - 1);
+        }
         if (count > 1) {
             if (int rc = mk_step(h, s, pred_phase, true, count, true)) return rc;
             h->dom_last_full = false;
