@@ -174,3 +174,27 @@ def test_headline_kernel_register_budget():
             assert int(m.group(5)) <= 64, (name, m.group(5))
             assert int(m.group(3)) <= 64, ('spill stores', name, m.group(3))
     assert seen == 2
+
+
+def test_multi_kernel_step_register_budgets():
+    """The two kernels of a multi-kernel step share every SM (large single swarm): the bulk update of a
+    periodic box was measured at 40 registers (at 32 it slowed the rows kernel beside it, at 48 itself), the rows kernel at
+    80 (at 64 its sweep spilled: +3.6 us per step at C5 size). Checked against the ptxas logs the build leaves behind."""
+    import os, re, subprocess
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'sde_burst_coast_b200', 'csrc')
+    logs = {k: os.path.join(csrc, k + '.ptxas.log') for k in ('update', 'celllist')}
+    if not all(os.path.exists(p) for p in logs.values()):
+        pytest.skip('no ptxas logs (library not built here)')
+    pat = re.compile(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                     r"(\d+) bytes spill loads\n.*?Used (\d+) registers")
+    found = {}
+    for key, path in logs.items():
+        for m in pat.finditer(open(path).read()):
+            name = subprocess.run(['c++filt', m.group(1)], capture_output=True, text=True).stdout
+            found[name.strip()] = (int(m.group(5)), int(m.group(3)))
+    bulk = [v for k, v in found.items() if 'update_bulk_kernel<0>' in k]
+    rows = [v for k, v in found.items() if 'pair_cells_lanes_kernel<true, ' in k]
+    assert len(bulk) == 1 and len(rows) == 4, sorted(found)
+    assert bulk[0][0] <= 40 and bulk[0][1] <= 16, bulk
+    for regs, spill in rows:
+        assert regs <= 80 and spill <= 64, rows
