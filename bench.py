@@ -658,14 +658,54 @@ def c5_single_gpu(device, hbm_gbs, n_agents, steps=400, warmup=60):
     g.close()
     us = 1e3 * ms / steps
     gbs = C5_BYTES_PER_AGENT_STEP * N / (us * 1e-6) / 1e9
+    traffic, prof = None, c5_recorded_profile(N)
+    if prof.get('used'):
+        traffic = prof['update_bulk_kernel']['dram_bytes_read'] + prof['update_bulk_kernel']['dram_bytes_write']
     return {'workload': 'C5 single periodic swarm, cell list, rho = 0.01', 'n_agents': N, 'box': L, 'steps': steps,
             'us_per_step': us, 'agent_steps_per_sec': N * steps / (ms * 1e-3),
             'pair_candidates_per_sec': (s1['pairs'] - s0['pairs']) / (ms * 1e-3),
             'cell_builds': s1['cell_builds'] - s0['cell_builds'],
             'launches_per_step': sum(s1[k] - s0[k] for k in ('pair_launches', 'update_launches', 'other_launches')) / steps,
             'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_gbs, 'unit': 'GB/s', 'frac': gbs / hbm_gbs,
-                         'bytes_per_agent_step': C5_BYTES_PER_AGENT_STEP, 'traffic': None,
-                         'note': 'whole step (pair pass + update + amortised cell build) against the HBM figure of the update alone'}}
+                         'bytes_per_agent_step': C5_BYTES_PER_AGENT_STEP, 'traffic': traffic, 'recorded_profile': prof,
+                         'note': 'whole step (pair pass + update + amortised cell build) against the HBM figure of the update alone; '
+                                 'traffic = DRAM bytes of ONE launch of the bulk update in the committed ncu capture (cold L2, '
+                                 'kernel alone: its 36 MB of stores stay in the L2, hence less than the algorithmic 72 B/agent)'}}
+
+
+def c5_recorded_profile(n_agents):
+    """The committed ncu summaries of the two kernels of a C5 step (profiles/r2_c5_step_breakdown.txt, written by
+    profiles/capture_r2.sh c5 + finish_r2.sh), if they are of this swarm size. Inside the graph the two kernels run side by
+    side, so this run has no duration of its own to hold against the capture's: the key says so."""
+    name = 'r2_c5_step_breakdown.txt'
+    out = {'file': 'profiles/' + name, 'used': False}
+    try:
+        got = read_ncu_summary(name)
+        if got is None:
+            out['why'] = 'no such summary committed'
+            return out
+        cfg, launches = got
+        out['config'] = cfg
+        if str(cfg.get('n_agents')) != str(n_agents):
+            out['why'] = 'summary is for another swarm size'
+            return out
+        for key in ('update_bulk_kernel', 'pair_cells_lanes_kernel'):
+            rows = [l for l in launches if key in l['kernel']]
+            if not rows:
+                out['why'] = 'kernel %s not in the summary' % key
+                return out
+            r = rows[0]
+            out[key] = {'ncu_seconds_per_launch': r.get('gpu__time_duration.sum'),
+                        'dram_bytes_read': r.get('dram__bytes_read.sum', 0.0), 'dram_bytes_write': r.get('dram__bytes_write.sum', 0.0),
+                        'issue_slot_utilisation': r.get('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                        'registers_per_thread': r.get('launch__registers_per_thread'),
+                        'warp_instructions': r.get('smsp__inst_executed.sum')}
+        out['used'] = True
+        out['check'] = ('none possible from this run: the kernels overlap inside a graph (in-situ timeline: '
+                        'profiles/r2_runs/c5_timeline.json)')
+    except Exception as e:   # a malformed summary must not cost the bench line
+        out['why'] = 'unreadable: %s' % e
+    return out
 
 
 def domain_swarm_leg(rank, world, device, agents_per_gpu, steps=200, warmup=40):

@@ -15,7 +15,7 @@ for f in $O/r2_pair_*_n*_r*.ncu-rep; do
 done
 [ -f $O/r2_launches_bench.csv ] && python $P/summarize.py launches $O/r2_launches_bench.csv > $P/r2_launches_bench.txt
 if [ -f $O/c5_r2f_launches.csv ]; then
-  { echo "# C5 (N = 1,048,576, L = 10,240) on one GPU: graph-replayed and eager step time, then the eager launch list"; cat $O/c5_r2f_graph.json $O/c5_r2f_eager.json;
+  { echo "# C5 (N = 1,048,576, L = 10,240) on one GPU: graph-replayed and eager step time, then the eager launch list"; echo "# config: n_agents=1048576 box=10240"; cat $O/c5_r2f_graph.json $O/c5_r2f_eager.json;
     python $P/summarize.py launches $O/c5_r2f_launches.csv; echo; echo "# ncu --set full of the two kernels of a steady-state step";
     cat $O/c5_r2f_bulk.txt $O/c5_r2f_rows.txt; } > $P/r2_c5_step_breakdown.txt
 fi
